@@ -1,0 +1,123 @@
+"""Conv / SPADE building blocks — drop-ins for ``climategan/blocks.py`` (same class names,
+constructor signatures and state_dict keys), operating on NHWC storage tensors through libcgb200.
+"""
+from __future__ import annotations
+
+import torch.nn as nn
+
+from . import _lib, ops
+from .norms import SPADE, SpectralNorm, conv_weight_bias
+
+_ACTS = {
+    "relu": (_lib.ACT_RELU, 0.0),
+    "lrelu": (_lib.ACT_LRELU, 0.2),
+    "tanh": (_lib.ACT_TANH, 0.0),
+    "sigmoid": (_lib.ACT_SIGMOID, 0.0),
+    "none": (_lib.ACT_NONE, 0.0),
+}
+
+
+class InterpolateNearest2d(nn.Module):
+    """``climategan.blocks.InterpolateNearest2d`` (blocks.py:11-43) on storage tensors."""
+
+    def __init__(self, scale_factor=2):
+        super().__init__()
+        self.scale_factor = scale_factor
+
+    def forward(self, x):
+        return ops.resize_nearest(x, x.shape[1] * self.scale_factor, x.shape[2] * self.scale_factor)
+
+
+class Conv2dBlock(nn.Module):
+    """``climategan.blocks.Conv2dBlock`` (blocks.py:49-147): pad -> conv -> norm -> activation.
+
+    Built so far: pad_type zero/reflect, norm none / spectral, activations relu/lrelu/tanh/sigmoid/none
+    (bias + activation run in the conv epilogue; reflect/zero padding in the conv loader).
+    """
+
+    def __init__(self, input_dim, output_dim, kernel_size, stride=1, padding=0, dilation=1, norm="none",
+                 activation="relu", pad_type="zero", bias=True):
+        super().__init__()
+        self.use_bias = bias
+        if pad_type == "reflect":
+            self.pad_mode = _lib.PAD_REFLECT
+        elif pad_type == "zero":
+            self.pad_mode = _lib.PAD_ZERO
+        else:
+            raise NotImplementedError("Unsupported padding type: {}".format(pad_type))
+        self.padding, self.stride, self.dilation = padding, stride, dilation
+        use_spectral_norm = False
+        if norm.startswith("spectral_"):
+            norm = norm.replace("spectral_", "")
+            use_spectral_norm = True
+        if norm in ("spectral", "none"):
+            self.norm = None
+        else:
+            raise NotImplementedError("Conv2dBlock norm '{}' is not built yet".format(norm))
+        if activation not in _ACTS:
+            raise NotImplementedError("Unsupported activation: {}".format(activation))
+        self.act, self.slope = _ACTS[activation]
+        self.activation = None if activation == "none" else activation
+        conv = nn.Conv2d(input_dim, output_dim, kernel_size, stride, dilation=dilation,
+                         bias=self.use_bias if norm != "batch" else False)
+        self.conv = SpectralNorm(conv) if (norm == "spectral" or use_spectral_norm) else conv
+
+    def forward(self, x, residual=None):
+        w, b = conv_weight_bias(self.conv)
+        return ops.conv2d(x, w, b, residual, stride=self.stride, dil=self.dilation, pad=self.padding,
+                          pad_mode=self.pad_mode, act=self.act, slope=self.slope)
+
+
+class SPADEResnetBlock(nn.Module):
+    """``climategan.blocks.SPADEResnetBlock`` (blocks.py:325-398).
+
+    forward (blocks.py:369-392):  x_s = conv_s(norm_s(x)) | x ;  dx = conv_0(lrelu(norm_0(x))) ;
+    dx = conv_1(lrelu(norm_1(dx))) ; out = x_s + dx.  Here the leaky-relu rides in the SPADE
+    modulation kernel, the residual add in conv_1's epilogue, and norm_0 / norm_s share one
+    instance-norm statistics pass over x.
+    """
+
+    def __init__(self, fin, fout, cond_nc, spade_use_spectral_norm, spade_param_free_norm, spade_kernel_size,
+                 last_activation=None):
+        super().__init__()
+        self.fin = fin
+        self.fout = fout
+        self.use_spectral_norm = spade_use_spectral_norm
+        self.param_free_norm = spade_param_free_norm
+        self.kernel_size = spade_kernel_size
+        self.learned_shortcut = fin != fout
+        self.last_activation = last_activation
+        if last_activation not in (None, "lrelu"):
+            raise NotImplementedError("The type of activation is not supported: {}".format(last_activation))
+        fmiddle = min(fin, fout)
+        # same construction order as the reference so a shared RNG seed gives identical initial weights
+        self.conv_0 = nn.Conv2d(fin, fmiddle, kernel_size=3, padding=1)
+        self.conv_1 = nn.Conv2d(fmiddle, fout, kernel_size=3, padding=1)
+        if self.learned_shortcut:
+            self.conv_s = nn.Conv2d(fin, fout, kernel_size=1, bias=False)
+        if spade_use_spectral_norm:
+            self.conv_0 = SpectralNorm(self.conv_0)
+            self.conv_1 = SpectralNorm(self.conv_1)
+            if self.learned_shortcut:
+                self.conv_s = SpectralNorm(self.conv_s)
+        self.norm_0 = SPADE(spade_param_free_norm, spade_kernel_size, fin, cond_nc)
+        self.norm_1 = SPADE(spade_param_free_norm, spade_kernel_size, fmiddle, cond_nc)
+        if self.learned_shortcut:
+            self.norm_s = SPADE(spade_param_free_norm, spade_kernel_size, fin, cond_nc)
+
+    def forward(self, x, seg):
+        """x: storage [N,H,W,round8(fin)] ; seg: storage conditioning at the same H,W."""
+        stats = ops.instnorm_stats(x)
+        if self.learned_shortcut:
+            # reference order (blocks.py:370,389): shortcut first -> conv_s's power iteration runs first
+            w_s, _ = conv_weight_bias(self.conv_s)
+            x_s = ops.conv2d(self.norm_s(x, seg, stats, _lib.ACT_NONE), w_s, None)
+        else:
+            x_s = x
+        w0, b0 = conv_weight_bias(self.conv_0)
+        dx = ops.conv2d(self.norm_0(x, seg, stats, _lib.ACT_LRELU, 0.2), w0, b0, pad=1)
+        w1, b1 = conv_weight_bias(self.conv_1)
+        out = ops.conv2d(self.norm_1(dx, seg, None, _lib.ACT_LRELU, 0.2), w1, b1, x_s, pad=1)
+        if self.last_activation == "lrelu":
+            out = ops.activation(out, _lib.ACT_LRELU, 0.2)
+        return out

@@ -1,0 +1,632 @@
+// HBM-bound kernels of the hot path: instance-norm statistics, SPADE modulation (+backward),
+// nearest resampling, layout conversion, compositing, L1 loss, spectral-norm power iteration.
+// All are coalesced, 16/32-byte vectorised over the NHWC channel dimension; reductions use
+// warp shuffles -> shared memory -> one fp64 atomic per (n,c) per CTA.
+#include "common.cuh"
+
+namespace cgb {
+
+// number of pixel-chunks per image for the reduction kernels
+static inline int pick_chunks(int n, int hw, int cv) {
+  // target >= 4 CTAs per SM overall, each CTA >= 256 pixels
+  int want = (148 * 4 + n - 1) / n;
+  int maxc = (hw + 255) / 256;
+  if (want > maxc) want = maxc;
+  if (want < 1) want = 1;
+  return want;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// instance-norm statistics: x [n,hw,c] -> sum, sumsq (fp64) per (n,c)
+// grid (chunks, n); block 256 threads = lanes x cv, cv = c/8 vector columns.
+template <typename T>
+__global__ void __launch_bounds__(256)
+in_stats_kernel(const T* __restrict__ x, double* __restrict__ ws, int hw, int c, int px_per_chunk) {
+  extern __shared__ float sm[];  // [2][c]
+  const int cv = c >> 3;
+  const int lanes = 256 / cv;
+  const int tid = threadIdx.x;
+  const int lane = tid / cv, v = tid - lane * cv;
+  const int img = blockIdx.y;
+  for (int i = tid; i < 2 * c; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  if (lane < lanes) {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const int p0 = blockIdx.x * px_per_chunk;
+    int p1 = p0 + px_per_chunk;
+    if (p1 > hw) p1 = hw;
+    const T* base = x + ((long long)img * hw) * c + v * 8;
+    for (int p = p0 + lane; p < p1; p += lanes) {
+      float f[8];
+      Vec8<T>::load(base + (long long)p * c, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        q[j] = fmaf(f[j], f[j], q[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sm[v * 8 + j], s[j]);
+      atomicAdd(&sm[c + v * 8 + j], q[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < c; i += 256) {
+    atomicAdd(&ws[((long long)img * c + i) * 2 + 0], (double)sm[i]);
+    atomicAdd(&ws[((long long)img * c + i) * 2 + 1], (double)sm[c + i]);
+  }
+}
+
+__global__ void in_stats_finalize_kernel(const double* __restrict__ ws, float* __restrict__ mean,
+                                         float* __restrict__ rstd, int count, double inv_hw, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const double m = ws[2 * i] * inv_hw;
+  double var = ws[2 * i + 1] * inv_hw - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SPADE modulation forward: one thread per (pixel, 8-channel vector)
+template <typename T>
+__global__ void __launch_bounds__(256)
+spade_mod_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const T* __restrict__ gb, T* __restrict__ out,
+                     long long total_vec, int hw, int c, int act, float slope) {
+  const int cv = c >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int v = (int)(i - pix * cv);
+    const int img = (int)(pix / hw);
+    float xv[8], g[8], b[8], o[8];
+    Vec8<T>::load(x + pix * c + v * 8, xv);
+    Vec8<T>::load(gb + pix * 2 * c + v * 8, g);
+    Vec8<T>::load(gb + pix * 2 * c + c + v * 8, b);
+    const float* mp = mean + (long long)img * c + v * 8;
+    const float* rp = rstd + (long long)img * c + v * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float xh = (xv[j] - mp[j]) * rp[j];
+      o[j] = act_apply(fmaf(xh, 1.f + g[j], b[j]), act, slope);
+    }
+    Vec8<T>::store(out + pix * c + v * 8, o);
+  }
+}
+
+// SPADE modulation backward (part 1) — see cgb200.h
+template <typename T>
+__global__ void __launch_bounds__(256)
+spade_mod_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const T* __restrict__ gb,
+                     const T* __restrict__ gout, T* __restrict__ ggb, T* __restrict__ gxhat,
+                     double* __restrict__ sums, int hw, int c, int px_per_chunk, int act, float slope) {
+  extern __shared__ float sm[];  // [2][c]
+  const int cv = c >> 3;
+  const int lanes = 256 / cv;
+  const int tid = threadIdx.x;
+  const int lane = tid / cv, v = tid - lane * cv;
+  const int img = blockIdx.y;
+  for (int i = tid; i < 2 * c; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  if (lane < lanes) {
+    float s1[8], s2[8], mu[8], rs[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1[j] = s2[j] = 0.f;
+      mu[j] = mean[(long long)img * c + v * 8 + j];
+      rs[j] = rstd[(long long)img * c + v * 8 + j];
+    }
+    const int p0 = blockIdx.x * px_per_chunk;
+    int p1 = p0 + px_per_chunk;
+    if (p1 > hw) p1 = hw;
+    for (int p = p0 + lane; p < p1; p += lanes) {
+      const long long pix = (long long)img * hw + p;
+      float xv[8], g[8], b[8], go[8], gg[8], gbt[8], gxh[8];
+      Vec8<T>::load(x + pix * c + v * 8, xv);
+      Vec8<T>::load(gb + pix * 2 * c + v * 8, g);
+      Vec8<T>::load(gb + pix * 2 * c + c + v * 8, b);
+      Vec8<T>::load(gout + pix * c + v * 8, go);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xv[j] - mu[j]) * rs[j];
+        const float pre = fmaf(xh, 1.f + g[j], b[j]);
+        float d = 1.f;
+        if (act == CGB_ACT_LRELU) d = pre > 0.f ? 1.f : slope;
+        else if (act == CGB_ACT_RELU) d = pre > 0.f ? 1.f : 0.f;
+        const float gs = go[j] * d;
+        gg[j] = gs * xh;
+        gbt[j] = gs;
+        gxh[j] = gs * (1.f + g[j]);
+        s1[j] += gxh[j];
+        s2[j] = fmaf(gxh[j], xh, s2[j]);
+      }
+      Vec8<T>::store(ggb + pix * 2 * c + v * 8, gg);
+      Vec8<T>::store(ggb + pix * 2 * c + c + v * 8, gbt);
+      Vec8<T>::store(gxhat + pix * c + v * 8, gxh);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sm[v * 8 + j], s1[j]);
+      atomicAdd(&sm[c + v * 8 + j], s2[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < c; i += 256) {
+    atomicAdd(&sums[((long long)img * c + i) * 2 + 0], (double)sm[i]);
+    atomicAdd(&sums[((long long)img * c + i) * 2 + 1], (double)sm[c + i]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+in_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+              const double* __restrict__ sums, T* __restrict__ g, long long total_vec, int hw, int c) {
+  const int cv = c >> 3;
+  const float inv_hw = 1.f / (float)hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int v = (int)(i - pix * cv);
+    const int img = (int)(pix / hw);
+    float xv[8], gv[8], o[8];
+    Vec8<T>::load(x + pix * c + v * 8, xv);
+    Vec8<T>::load(g + pix * c + v * 8, gv);
+    const long long sc = (long long)img * c + v * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float rs = rstd[sc + j];
+      const float xh = (xv[j] - mean[sc + j]) * rs;
+      const float m1 = (float)(sums[(sc + j) * 2 + 0]) * inv_hw;
+      const float m2 = (float)(sums[(sc + j) * 2 + 1]) * inv_hw;
+      o[j] = rs * (gv[j] - m1 - xh * m2);
+    }
+    Vec8<T>::store(g + pix * c + v * 8, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+resize_nearest_kernel(const T* __restrict__ x, T* __restrict__ y, long long total_vec, int hi, int wi,
+                      int ho, int wo, int c) {
+  const int cv = c >> 3;
+  const float sh = (float)hi / (float)ho, sw = (float)wi / (float)wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int v = (int)(i - pix * cv);
+    const int ox = (int)(pix % wo);
+    const long long t = pix / wo;
+    const int oy = (int)(t % ho);
+    const int img = (int)(t / ho);
+    // ATen nearest: src = min(floor(dst * scale), in-1), scale = in/out in fp32
+    int sy = (int)floorf(oy * sh);
+    int sx = (int)floorf(ox * sw);
+    if (sy > hi - 1) sy = hi - 1;
+    if (sx > wi - 1) sx = wi - 1;
+    const uint4* src = reinterpret_cast<const uint4*>(x + (((long long)img * hi + sy) * wi + sx) * c + v * 8);
+    uint4* dst = reinterpret_cast<uint4*>(y + pix * c + v * 8);
+    dst[0] = src[0];
+    if (sizeof(T) == 4) dst[1] = src[1];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample_bwd_kernel(const T* __restrict__ gy, T* __restrict__ gx, long long total_vec, int hi, int wi,
+                    int f, int c) {
+  const int cv = c >> 3;
+  const int ho = hi * f, wo = wi * f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int v = (int)(i - pix * cv);
+    const int ix = (int)(pix % wi);
+    const long long t = pix / wi;
+    const int iy = (int)(t % hi);
+    const int img = (int)(t / hi);
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    for (int a = 0; a < f; ++a)
+      for (int b = 0; b < f; ++b) {
+        float g[8];
+        Vec8<T>::load(gy + (((long long)img * ho + iy * f + a) * wo + ix * f + b) * c + v * 8, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += g[j];
+      }
+    Vec8<T>::store(gx + pix * c + v * 8, s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// NCHW fp32 <-> NHWC storage.  Tile transpose through shared memory: 32 pixels x cs channels.
+template <typename T>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int c, int hw, int cs) {
+  extern __shared__ float tile[];  // [cs][33]
+  const int img = blockIdx.y;
+  const int p0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < cs * 32; i += blockDim.x) {
+    const int ch = i >> 5, p = i & 31;
+    float v = 0.f;
+    if (ch < c && p0 + p < hw) v = x[((long long)img * c + ch) * hw + p0 + p];
+    tile[ch * 33 + p] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < cs * 32; i += blockDim.x) {
+    const int p = i / cs, ch = i - p * cs;
+    if (p0 + p < hw) y[((long long)img * hw + p0 + p) * cs + ch] = from_f<T>(tile[ch * 33 + p]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int c, int hw, int cs) {
+  extern __shared__ float tile[];  // [cs][33]
+  const int img = blockIdx.y;
+  const int p0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < cs * 32; i += blockDim.x) {
+    const int p = i / cs, ch = i - p * cs;
+    float v = 0.f;
+    if (p0 + p < hw) v = to_f<T>(x[((long long)img * hw + p0 + p) * cs + ch]);
+    tile[ch * 33 + p] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c * 32; i += blockDim.x) {
+    const int ch = i >> 5, p = i & 31;
+    if (p0 + p < hw) y[((long long)img * c + ch) * hw + p0 + p] = tile[ch * 33 + p];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ y, T* __restrict__ gx, long long count,
+               int act, float slope) {
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < count;
+       i += (long long)gridDim.x * blockDim.x * 8) {
+    float g[8], yy[8], o[8];
+    Vec8<T>::load(gy + i, g);
+    Vec8<T>::load(y + i, yy);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = g[j] * act_grad_from_out(yy[j], act, slope);
+    Vec8<T>::store(gx + i, o);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long count, int act, float slope) {
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < count;
+       i += (long long)gridDim.x * blockDim.x * 8) {
+    float v[8], o[8];
+    Vec8<T>::load(x + i, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = act_apply(v[j], act, slope);
+    Vec8<T>::store(y + i, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// compositing (generator.py:279-297)
+template <typename T>
+__global__ void __launch_bounds__(256)
+mask_cond_kernel(const float* __restrict__ x, const float* __restrict__ m, T* __restrict__ cond, int hw,
+                 int cs, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(i / hw);
+    const int p = (int)(i - (long long)img * hw);
+    const float k = 1.f - m[i];
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) v[ch] = x[((long long)img * 3 + ch) * hw + p] * k;
+    T* dst = cond + i * cs;
+    Vec8<T>::store(dst, v);
+    for (int ch = 8; ch < cs; ++ch) dst[ch] = from_f<T>(0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+paste_fwd_kernel(const float* __restrict__ x, const float* __restrict__ m, const float* __restrict__ fake,
+                 float* __restrict__ out, int hw, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pl = i / hw;  // img*3+ch
+    const int p = (int)(i - pl * hw);
+    const float mm = m[(pl / 3) * hw + p];
+    out[i] = x[i] * (1.f - mm) + fake[i] * mm;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+paste_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ m, float* __restrict__ gfake,
+                 int hw, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pl = i / hw;
+    const int p = (int)(i - pl * hw);
+    gfake[i] = gout[i] * m[(pl / 3) * hw + p];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+l1_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ loss,
+               float* __restrict__ ga, long long count, float scale) {
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float d = a[i] - b[i];
+    s += fabsf(d);
+    if (ga) ga[i] = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += ws[i];
+    atomicAdd(loss, t * scale);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Spectral norm power iteration (norms.py:100-112): single CTA of 1024 threads, W [rows, cols] fp32.
+__device__ __forceinline__ float block_sum_1024(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < 32; ++i) t += red[i];
+  return t;
+}
+
+__global__ void __launch_bounds__(1024)
+spectral_power_iter_kernel(const float* __restrict__ w, float* __restrict__ u, float* __restrict__ v,
+                           float* __restrict__ sigma, int rows, int cols) {
+  __shared__ float red[32];
+  const int tid = threadIdx.x;
+  const float eps = 1e-12f;
+  // v = W^T u  (each thread owns columns tid, tid+1024, ...) ; coalesced over columns
+  float nv = 0.f;
+  for (int cidx = tid; cidx < cols; cidx += 1024) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s = fmaf(w[(long long)r * cols + cidx], u[r], s);
+    v[cidx] = s;
+    nv = fmaf(s, s, nv);
+  }
+  nv = block_sum_1024(nv, red);
+  const float inv_v = 1.f / (sqrtf(nv) + eps);
+  for (int cidx = tid; cidx < cols; cidx += 1024) v[cidx] *= inv_v;
+  __syncthreads();
+  // u = W v : one warp per row (strided), lanes over columns
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int r = warp; r < rows; r += 32) {
+    float s = 0.f;
+    for (int cidx = lane; cidx < cols; cidx += 32) s = fmaf(w[(long long)r * cols + cidx], v[cidx], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) u[r] = s;  // un-normalised W v
+  }
+  __syncthreads();
+  float nu = 0.f;
+  for (int r = tid; r < rows; r += 1024) nu = fmaf(u[r], u[r], nu);
+  nu = block_sum_1024(nu, red);
+  const float norm_u = sqrtf(nu);
+  const float inv_u = 1.f / (norm_u + eps);
+  // sigma = u_new . (W v) = |Wv|^2 / (|Wv| + eps)
+  for (int r = tid; r < rows; r += 1024) u[r] *= inv_u;
+  if (tid == 0) sigma[0] = nu * inv_u;
+}
+
+}  // namespace cgb
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+using namespace cgb;
+
+static inline int grid_for(long long work, int block = 256) {
+  long long g = (work + block - 1) / block;
+  const long long cap = 148LL * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+#define DISPATCH_T(dtype, ...)                          \
+  if ((dtype) == CGB_F32) {                             \
+    using T = float;                                    \
+    __VA_ARGS__                                         \
+  } else if ((dtype) == CGB_BF16) {                     \
+    using T = __nv_bfloat16;                            \
+    __VA_ARGS__                                         \
+  } else {                                              \
+    set_error("unknown dtype %d", (int)(dtype));        \
+    return CGB_BAD_ARG;                                 \
+  }
+
+extern "C" int cgb_instnorm_stats(const void* x, int32_t dtype, int32_t n, int32_t hw, int32_t c,
+                                  float eps, double* ws, float* mean, float* rstd, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && ws && mean && rstd, "instnorm_stats: null pointer");
+  CGB_REQUIRE(c % 8 == 0 && c >= 8 && c <= 2048, "instnorm_stats: c=%d must be a multiple of 8 in [8,2048]", c);
+  CGB_REQUIRE(n > 0 && hw > 0, "instnorm_stats: empty input");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)n * c, st);
+  const int chunks = pick_chunks(n, hw, c / 8);
+  const int ppc = (hw + chunks - 1) / chunks;
+  dim3 grid((hw + ppc - 1) / ppc, n);
+  DISPATCH_T(dtype, in_stats_kernel<T><<<grid, 256, 2 * c * sizeof(float), st>>>((const T*)x, ws, hw, c, ppc);)
+  int s = after_launch("in_stats");
+  if (s) return s;
+  in_stats_finalize_kernel<<<(n * c + 255) / 256, 256, 0, st>>>(ws, mean, rstd, n * c, 1.0 / (double)hw, eps);
+  return after_launch("in_stats_finalize");
+}
+
+extern "C" int cgb_spade_modulate_fwd(const void* x, const float* mean, const float* rstd,
+                                      const void* gb, void* out, int32_t dtype, int32_t n, int32_t hw,
+                                      int32_t c, int32_t act, float slope, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && mean && rstd && gb && out, "spade_modulate_fwd: null pointer");
+  CGB_REQUIRE(c % 8 == 0 && c >= 8, "spade_modulate_fwd: c=%d must be a multiple of 8", c);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)n * hw * (c / 8);
+  DISPATCH_T(dtype, spade_mod_fwd_kernel<T><<<grid_for(total), 256, 0, st>>>(
+                        (const T*)x, mean, rstd, (const T*)gb, (T*)out, total, hw, c, act, slope);)
+  return after_launch("spade_mod_fwd");
+}
+
+extern "C" int cgb_spade_modulate_bwd(const void* x, const float* mean, const float* rstd,
+                                      const void* gb, const void* gout, void* ggb, void* gxhat,
+                                      double* sums, int32_t dtype, int32_t n, int32_t hw, int32_t c,
+                                      int32_t act, float slope, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && mean && rstd && gb && gout && ggb && gxhat && sums, "spade_modulate_bwd: null pointer");
+  CGB_REQUIRE(c % 8 == 0 && c >= 8 && c <= 2048, "spade_modulate_bwd: c=%d must be a multiple of 8 in [8,2048]", c);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = pick_chunks(n, hw, c / 8);
+  const int ppc = (hw + chunks - 1) / chunks;
+  dim3 grid((hw + ppc - 1) / ppc, n);
+  DISPATCH_T(dtype, spade_mod_bwd_kernel<T><<<grid, 256, 2 * c * sizeof(float), st>>>(
+                        (const T*)x, mean, rstd, (const T*)gb, (const T*)gout, (T*)ggb, (T*)gxhat, sums,
+                        hw, c, ppc, act, slope);)
+  return after_launch("spade_mod_bwd");
+}
+
+extern "C" int cgb_instnorm_bwd(const void* x, const float* mean, const float* rstd, const double* sums,
+                                void* g, int32_t dtype, int32_t n, int32_t hw, int32_t c, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && mean && rstd && sums && g, "instnorm_bwd: null pointer");
+  CGB_REQUIRE(c % 8 == 0 && c >= 8, "instnorm_bwd: c=%d must be a multiple of 8", c);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)n * hw * (c / 8);
+  DISPATCH_T(dtype, in_bwd_kernel<T><<<grid_for(total), 256, 0, st>>>((const T*)x, mean, rstd, sums, (T*)g,
+                                                                     total, hw, c);)
+  return after_launch("in_bwd");
+}
+
+extern "C" int cgb_resize_nearest_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t hi,
+                                      int32_t wi, int32_t ho, int32_t wo, int32_t c, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y, "resize_nearest: null pointer");
+  CGB_REQUIRE(c % 8 == 0 && c >= 8, "resize_nearest: c=%d must be a multiple of 8", c);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)n * ho * wo * (c / 8);
+  DISPATCH_T(dtype, resize_nearest_kernel<T><<<grid_for(total), 256, 0, st>>>((const T*)x, (T*)y, total, hi,
+                                                                             wi, ho, wo, c);)
+  return after_launch("resize_nearest");
+}
+
+extern "C" int cgb_upsample_nearest_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi,
+                                        int32_t wi, int32_t f, int32_t c, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(gy && gx, "upsample_bwd: null pointer");
+  CGB_REQUIRE(c % 8 == 0 && c >= 8 && f >= 1, "upsample_bwd: bad c=%d or f=%d", c, f);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)n * hi * wi * (c / 8);
+  DISPATCH_T(dtype, upsample_bwd_kernel<T><<<grid_for(total), 256, 0, st>>>((const T*)gy, (T*)gx, total, hi,
+                                                                           wi, f, c);)
+  return after_launch("upsample_bwd");
+}
+
+extern "C" int cgb_nchw_to_nhwc(const float* x, void* y, int32_t dtype, int32_t n, int32_t c, int32_t hw,
+                                int32_t cs, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y, "nchw_to_nhwc: null pointer");
+  CGB_REQUIRE(cs % 8 == 0 && cs >= c && cs <= 1024, "nchw_to_nhwc: bad cs=%d for c=%d", cs, c);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((hw + 31) / 32, n);
+  DISPATCH_T(dtype, nchw_to_nhwc_kernel<T><<<grid, 256, cs * 33 * sizeof(float), st>>>(x, (T*)y, c, hw, cs);)
+  return after_launch("nchw_to_nhwc");
+}
+
+extern "C" int cgb_nhwc_to_nchw(const void* x, float* y, int32_t dtype, int32_t n, int32_t c, int32_t hw,
+                                int32_t cs, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y, "nhwc_to_nchw: null pointer");
+  CGB_REQUIRE(cs % 8 == 0 && cs >= c && cs <= 1024, "nhwc_to_nchw: bad cs=%d for c=%d", cs, c);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((hw + 31) / 32, n);
+  DISPATCH_T(dtype, nhwc_to_nchw_kernel<T><<<grid, 256, cs * 33 * sizeof(float), st>>>((const T*)x, y, c, hw, cs);)
+  return after_launch("nhwc_to_nchw");
+}
+
+extern "C" int cgb_act_bwd(const void* gy, const void* y, void* gx, int32_t dtype, int64_t count,
+                           int32_t act, float slope, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(gy && y && gx, "act_bwd: null pointer");
+  CGB_REQUIRE(count % 8 == 0, "act_bwd: count must be a multiple of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_T(dtype, act_bwd_kernel<T><<<grid_for(count / 8), 256, 0, st>>>((const T*)gy, (const T*)y, (T*)gx,
+                                                                          count, act, slope);)
+  return after_launch("act_bwd");
+}
+
+extern "C" int cgb_act_fwd(const void* x, void* y, int32_t dtype, int64_t count, int32_t act, float slope,
+                           void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y, "act_fwd: null pointer");
+  CGB_REQUIRE(count % 8 == 0, "act_fwd: count must be a multiple of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_T(dtype, act_fwd_kernel<T><<<grid_for(count / 8), 256, 0, st>>>((const T*)x, (T*)y, count, act, slope);)
+  return after_launch("act_fwd");
+}
+
+extern "C" int cgb_mask_cond(const float* x, const float* m, void* cond, int32_t dtype, int32_t n,
+                             int32_t hw, int32_t cs, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && m && cond, "mask_cond: null pointer");
+  CGB_REQUIRE(cs % 8 == 0 && cs >= 8, "mask_cond: bad cs=%d", cs);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)n * hw;
+  DISPATCH_T(dtype, mask_cond_kernel<T><<<grid_for(total), 256, 0, st>>>(x, m, (T*)cond, hw, cs, total);)
+  return after_launch("mask_cond");
+}
+
+extern "C" int cgb_paste_fwd(const float* x, const float* m, const float* fake, float* out, int32_t n,
+                             int32_t hw, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && m && fake && out, "paste_fwd: null pointer");
+  const long long total = (long long)n * 3 * hw;
+  paste_fwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, m, fake, out, hw, total);
+  return after_launch("paste_fwd");
+}
+
+extern "C" int cgb_paste_bwd(const float* gout, const float* m, float* gfake, int32_t n, int32_t hw,
+                             void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(gout && m && gfake, "paste_bwd: null pointer");
+  const long long total = (long long)n * 3 * hw;
+  paste_bwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(gout, m, gfake, hw, total);
+  return after_launch("paste_bwd");
+}
+
+extern "C" int cgb_l1_loss(const float* a, const float* b, float* loss, float* ga, int64_t count,
+                           float scale, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(a && b && loss, "l1_loss: null pointer");
+  l1_loss_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(a, b, loss, ga, count, scale);
+  return after_launch("l1_loss");
+}
+
+extern "C" int cgb_spectral_power_iter(const float* w, float* u, float* v, float* sigma, int32_t rows,
+                                       int32_t cols, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(w && u && v && sigma, "spectral_power_iter: null pointer");
+  CGB_REQUIRE(rows > 0 && cols > 0, "spectral_power_iter: empty matrix");
+  spectral_power_iter_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(w, u, v, sigma, rows, cols);
+  return after_launch("spectral_power_iter");
+}

@@ -1,0 +1,102 @@
+"""Normalisation layers of the hot path — same class names, constructor arguments, parameter
+names and state_dict layout as ``climategan/norms.py`` in the reference, computing through
+libcgb200 on NHWC storage tensors (see :mod:`climategan_b200.ops`).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+
+def l2normalize(v, eps=1e-12):
+    return v / (v.norm() + eps)
+
+
+class SpectralNorm(nn.Module):
+    """Drop-in for ``climategan.norms.SpectralNorm`` (norms.py:84-143).
+
+    Parameters live on the wrapped module exactly as in the reference: ``module.weight_bar``
+    (trainable), ``module.weight_u`` / ``module.weight_v`` (``requires_grad=False``), in that
+    registration order after ``bias`` (norms.py:123-139), so checkpoints interchange.
+    The power iteration runs on every :meth:`effective_weight` call — train *and* eval — and
+    mutates ``u``/``v`` in place, as ``_update_u_v`` does (norms.py:100-112).
+    """
+
+    def __init__(self, module, name="weight", power_iterations=1):
+        super().__init__()
+        if power_iterations != 1:
+            raise NotImplementedError("the reference only ever uses power_iterations=1")
+        self.module = module
+        self.name = name
+        self.power_iterations = power_iterations
+        if not self._made_params():
+            self._make_params()
+
+    def _made_params(self):
+        return all(hasattr(self.module, self.name + s) for s in ("_u", "_v", "_bar"))
+
+    def _make_params(self):
+        w = getattr(self.module, self.name)
+        height = w.data.shape[0]
+        width = w.view(height, -1).data.shape[1]
+        # same RNG draws, in the same order, as the reference
+        u = nn.Parameter(w.data.new(height).normal_(0, 1), requires_grad=False)
+        v = nn.Parameter(w.data.new(width).normal_(0, 1), requires_grad=False)
+        u.data = l2normalize(u.data)
+        v.data = l2normalize(v.data)
+        w_bar = nn.Parameter(w.data)
+        del self.module._parameters[self.name]
+        self.module.register_parameter(self.name + "_u", u)
+        self.module.register_parameter(self.name + "_v", v)
+        self.module.register_parameter(self.name + "_bar", w_bar)
+
+    def effective_weight(self) -> torch.Tensor:
+        m = self.module
+        return ops.spectral_weight(getattr(m, self.name + "_bar"), getattr(m, self.name + "_u").data,
+                                   getattr(m, self.name + "_v").data)
+
+    @property
+    def bias(self):
+        return self.module.bias
+
+
+def conv_weight_bias(conv):
+    """(weight, bias) of an nn.Conv2d or a SpectralNorm-wrapped one (runs the power iteration)."""
+    if isinstance(conv, SpectralNorm):
+        return conv.effective_weight(), conv.module.bias
+    return conv.weight, conv.bias
+
+
+class SPADE(nn.Module):
+    """Drop-in for ``climategan.norms.SPADE`` (norms.py:146-186), instance-norm flavour.
+
+    ``forward(x, segmap, stats=None, act=ACT_NONE)`` takes/returns NHWC storage tensors; ``segmap``
+    must already be at x's resolution (the caller resizes once per resolution and shares it, the
+    reference re-interpolates per layer, norms.py:179 — same values).  ``stats`` lets norm_0 and
+    norm_s of a block share one statistics pass over the same x.
+    """
+
+    def __init__(self, param_free_norm_type, kernel_size, norm_nc, cond_nc):
+        super().__init__()
+        if param_free_norm_type == "instance":
+            self.param_free_norm = nn.InstanceNorm2d(norm_nc, affine=False)  # holds no state
+        elif param_free_norm_type == "batch":
+            raise NotImplementedError("SPADE(batch) (masker SPADE decoder) is not built yet")
+        else:
+            raise ValueError("%s is not a recognized param-free norm type in SPADE" % param_free_norm_type)
+        nhidden = 128
+        pw = kernel_size // 2
+        self.norm_nc = norm_nc
+        self.mlp_shared = nn.Sequential(nn.Conv2d(cond_nc, nhidden, kernel_size=kernel_size, padding=pw), nn.ReLU())
+        self.mlp_gamma = nn.Conv2d(nhidden, norm_nc, kernel_size=kernel_size, padding=pw)
+        self.mlp_beta = nn.Conv2d(nhidden, norm_nc, kernel_size=kernel_size, padding=pw)
+
+    def forward(self, x, segmap, stats=None, act=_lib.ACT_NONE, slope=0.2):
+        if segmap.shape[1:3] != x.shape[1:3]:
+            segmap = ops.resize_nearest(segmap, x.shape[1], x.shape[2])
+        mean, rstd = stats if stats is not None else ops.instnorm_stats(x, self.param_free_norm.eps)
+        sh = self.mlp_shared[0]
+        return ops.spade(x, mean, rstd, segmap, sh.weight, sh.bias, self.mlp_gamma.weight, self.mlp_gamma.bias,
+                         self.mlp_beta.weight, self.mlp_beta.bias, act, slope)

@@ -1,0 +1,462 @@
+"""Autograd operators over libcgb200 (the C ABI in include/cgb200.h).
+
+Tensors between operators are *storage tensors*: contiguous ``[N, H, W, Cs]`` (NHWC) with
+``Cs = round_up(C, 8)`` and zero pad channels, dtype ``torch.float32`` or ``torch.bfloat16``.
+The reference's NCHW fp32 tensors exist only at the API edges (:func:`to_storage`,
+:func:`from_storage`).  PyTorch is used for memory, streams and the autograd tape only; every
+array operation on an activation goes through a ``cgb_*`` entry point.  Nothing here has a CPU
+or eager fallback — ops raise :class:`CgbError` without an sm_100 device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import ConvDesc, check
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def round8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _L():
+    return _lib.lib()
+
+
+def _chk_storage(x: torch.Tensor, name: str = "x") -> None:
+    if x.dim() != 4 or not x.is_contiguous() or x.shape[-1] % 8 or x.dtype not in _DT or not x.is_cuda:
+        raise ValueError(
+            f"{name}: expected a contiguous CUDA NHWC storage tensor with C%8==0 (fp32/bf16), got "
+            f"shape={tuple(x.shape)} dtype={x.dtype} device={x.device} contiguous={x.is_contiguous()}"
+        )
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing:  OIHW fp32  <->  [Os][kh*kw][Is] storage dtype
+# ------------------------------------------------------------------------------------------------
+def pack_weight(w: torch.Tensor, dtype: torch.dtype, cis: Optional[int] = None, cos: Optional[int] = None) -> torch.Tensor:
+    o, i, kh, kw = w.shape
+    cos = cos or round8(o)
+    cis = cis or round8(i)
+    wp = torch.zeros(cos, kh * kw, cis, dtype=dtype, device=w.device)
+    wp[:o, :, :i] = w.detach().permute(0, 2, 3, 1).reshape(o, kh * kw, i)
+    return wp
+
+
+def unpack_weight_grad(gwp: torch.Tensor, shape) -> torch.Tensor:
+    o, i, kh, kw = shape
+    return gwp[:o, :, :i].reshape(o, kh, kw, i).permute(0, 3, 1, 2).contiguous()
+
+
+def pad_bias(b: Optional[torch.Tensor], cos: int) -> Optional[torch.Tensor]:
+    if b is None:
+        return None
+    bp = torch.zeros(cos, dtype=torch.float32, device=b.device)
+    bp[: b.numel()] = b.detach().float()
+    return bp
+
+
+# ------------------------------------------------------------------------------------------------
+# raw (non-autograd) wrappers
+# ------------------------------------------------------------------------------------------------
+class ConvGeom:
+    """kernel geometry + epilogue of one conv (forward view)."""
+
+    __slots__ = ("kh", "kw", "stride", "dil", "pad", "pad_mode", "act", "slope", "engine")
+
+    def __init__(self, kh, kw, stride=1, dil=1, pad=0, pad_mode=_lib.PAD_ZERO, act=_lib.ACT_NONE,
+                 slope=0.2, engine=_lib.ENGINE_AUTO):
+        self.kh, self.kw, self.stride, self.dil, self.pad = kh, kw, stride, dil, pad
+        self.pad_mode, self.act, self.slope, self.engine = pad_mode, act, slope, engine
+
+    def out_hw(self, hi, wi):
+        ho = (hi + 2 * self.pad - self.dil * (self.kh - 1) - 1) // self.stride + 1
+        wo = (wi + 2 * self.pad - self.dil * (self.kw - 1) - 1) // self.stride + 1
+        return ho, wo
+
+    def desc(self, n, hi, wi, ci, co, dtype) -> ConvDesc:
+        ho, wo = self.out_hw(hi, wi)
+        return ConvDesc(n, hi, wi, ci, ho, wo, co, self.kh, self.kw, self.stride, self.dil, self.pad,
+                        self.pad_mode, _DT[dtype], self.act, self.slope, self.engine)
+
+
+def conv_fwd_raw(x, wp, bias, residual, g: ConvGeom):
+    _chk_storage(x)
+    n, hi, wi, ci = x.shape
+    co = wp.shape[0]
+    assert wp.shape[2] == ci and wp.shape[1] == g.kh * g.kw and wp.dtype == x.dtype, (wp.shape, x.shape)
+    d = g.desc(n, hi, wi, ci, co, x.dtype)
+    y = torch.empty((n, d.ho, d.wo, co), dtype=x.dtype, device=x.device)
+    check(_L().cgb_conv2d_fwd(C.byref(d), _p(x), _p(wp), _p(bias), _p(residual), _p(y), _st()), "conv2d_fwd")
+    return y
+
+
+def conv_dgrad_raw(gy, wp, x_shape, g: ConvGeom, dact=_lib.ACT_NONE, mask_src=None):
+    _chk_storage(gy, "gy")
+    n, hi, wi, ci = x_shape
+    co = wp.shape[0]
+    d = g.desc(n, hi, wi, ci, co, gy.dtype)
+    assert (d.ho, d.wo, co) == tuple(gy.shape[1:]), (d.ho, d.wo, co, gy.shape)
+    gx = torch.empty(x_shape, dtype=gy.dtype, device=gy.device)
+    check(_L().cgb_conv2d_dgrad(C.byref(d), _p(gy), _p(wp), dact, _p(mask_src), _p(gx), _st()), "conv2d_dgrad")
+    return gx
+
+
+def conv_wgrad_raw(x, gy, g: ConvGeom, want_bias: bool):
+    _chk_storage(x)
+    _chk_storage(gy, "gy")
+    n, hi, wi, ci = x.shape
+    co = gy.shape[-1]
+    d = g.desc(n, hi, wi, ci, co, x.dtype)
+    gw = torch.empty((co, g.kh * g.kw, ci), dtype=torch.float32, device=x.device)
+    gb = torch.empty((co,), dtype=torch.float32, device=x.device) if want_bias else None
+    check(_L().cgb_conv2d_wgrad(C.byref(d), _p(x), _p(gy), _p(gw), _p(gb), 0, _st()), "conv2d_wgrad")
+    return gw, gb
+
+
+def instnorm_stats(x: torch.Tensor, eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-(n,c) mean and 1/sqrt(var+eps) of a storage tensor (nn.InstanceNorm2d, norms.py:151)."""
+    _chk_storage(x)
+    n, h, w, c = x.shape
+    ws = torch.empty((n, c, 2), dtype=torch.float64, device=x.device)
+    mean = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    check(_L().cgb_instnorm_stats(_p(x), _DT[x.dtype], n, h * w, c, eps, _p(ws), _p(mean), _p(rstd), _st()),
+          "instnorm_stats")
+    return mean, rstd
+
+
+def act_bwd_raw(gy, y, act, slope):
+    gx = torch.empty_like(gy)
+    check(_L().cgb_act_bwd(_p(gy), _p(y), _p(gx), _DT[gy.dtype], gy.numel(), act, slope, _st()), "act_bwd")
+    return gx
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd functions
+# ------------------------------------------------------------------------------------------------
+class _Conv2d(Function):
+    """y = act(conv(x, w) + b) (+ residual); w is OIHW fp32 (master / spectrally normalised)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, residual, g: ConvGeom):
+        wp = pack_weight(w, x.dtype, cis=x.shape[-1])
+        bp = pad_bias(bias, wp.shape[0])
+        y = conv_fwd_raw(x, wp, bp, residual, g)
+        ctx.g = g
+        ctx.w_shape = tuple(w.shape)
+        ctx.has_bias = bias is not None
+        ctx.nb = 0 if bias is None else bias.numel()
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, wp, y if g.act != _lib.ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, wp, y = ctx.saved_tensors
+        g = ctx.g
+        gy = gy.contiguous()
+        gpre = act_bwd_raw(gy, y, g.act, g.slope) if g.act != _lib.ACT_NONE else gy
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = conv_dgrad_raw(gpre, wp, tuple(x.shape), g)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            gwp, gbp = conv_wgrad_raw(x, gpre, g, ctx.has_bias)
+            gw = unpack_weight_grad(gwp, ctx.w_shape)
+            if ctx.has_bias:
+                gb = gbp[: ctx.nb].clone()
+        gres = gy if ctx.has_res else None
+        return gx, gw, gb, gres, None
+
+
+def conv2d(x, w, bias=None, residual=None, *, stride=1, dil=1, pad=0, pad_mode=_lib.PAD_ZERO,
+           act=_lib.ACT_NONE, slope=0.2, engine=_lib.ENGINE_AUTO):
+    g = ConvGeom(w.shape[2], w.shape[3], stride, dil, pad, pad_mode, act, slope, engine)
+    return _Conv2d.apply(x, w, bias, residual, g)
+
+
+class _Spade(Function):
+    """SPADE.forward (climategan/norms.py:174-186) + the leaky-relu that follows it in
+    SPADEResnetBlock (blocks.py:372-373), as one autograd node.
+
+    out = act( IN(x) * (1 + conv_g(a)) + conv_b(a) ),  a = relu(conv_sh(seg))
+    mean/rstd are the instance-norm statistics of x (shared by norm_0 / norm_s of a block); the
+    backward differentiates through them.
+    """
+
+    @staticmethod
+    def forward(ctx, x, mean, rstd, seg, w_sh, b_sh, w_g, b_g, w_b, b_b, act, slope, engine):
+        dt = x.dtype
+        n, h, w_, cs = x.shape
+        c = w_g.shape[0]
+        k = w_sh.shape[2]
+        pad = k // 2
+        g_sh = ConvGeom(k, k, 1, 1, pad, _lib.PAD_ZERO, _lib.ACT_RELU, 0.0, engine)
+        g_gb = ConvGeom(k, k, 1, 1, pad, _lib.PAD_ZERO, _lib.ACT_NONE, 0.0, engine)
+        wp_sh = pack_weight(w_sh, dt, cis=seg.shape[-1])
+        bp_sh = pad_bias(b_sh, wp_sh.shape[0])
+        actv = conv_fwd_raw(seg, wp_sh, bp_sh, None, g_sh)
+        nh = actv.shape[-1]
+        # gamma || beta as ONE conv with co = 2*cs (norms.py:180-182 share the input actv)
+        wp_gb = torch.zeros(2 * cs, k * k, nh, dtype=dt, device=x.device)
+        wp_gb[:c] = w_g.detach().permute(0, 2, 3, 1).reshape(c, k * k, nh)
+        wp_gb[cs:cs + c] = w_b.detach().permute(0, 2, 3, 1).reshape(c, k * k, nh)
+        bp_gb = torch.zeros(2 * cs, dtype=torch.float32, device=x.device)
+        bp_gb[:c] = b_g.detach()
+        bp_gb[cs:cs + c] = b_b.detach()
+        gb = conv_fwd_raw(actv, wp_gb, bp_gb, None, g_gb)
+        out = torch.empty_like(x)
+        check(_L().cgb_spade_modulate_fwd(_p(x), _p(mean), _p(rstd), _p(gb), _p(out), _DT[dt], n, h * w_, cs,
+                                          act, slope, _st()), "spade_modulate_fwd")
+        ctx.save_for_backward(x, mean, rstd, seg, actv, gb, wp_gb)
+        ctx.meta = (act, slope, g_sh, g_gb, tuple(w_sh.shape), tuple(w_g.shape), c, cs)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, mean, rstd, seg, actv, gb, wp_gb = ctx.saved_tensors
+        act, slope, g_sh, g_gb, sh_shape, g_shape, c, cs = ctx.meta
+        n, h, w_, _ = x.shape
+        dt = x.dtype
+        gout = gout.contiguous()
+        ggb = torch.empty_like(gb)
+        gx = torch.empty_like(x)
+        sums = torch.zeros((n, cs, 2), dtype=torch.float64, device=x.device)
+        check(_L().cgb_spade_modulate_bwd(_p(x), _p(mean), _p(rstd), _p(gb), _p(gout), _p(ggb), _p(gx), _p(sums),
+                                          _DT[dt], n, h * w_, cs, act, slope, _st()), "spade_modulate_bwd")
+        check(_L().cgb_instnorm_bwd(_p(x), _p(mean), _p(rstd), _p(sums), _p(gx), _DT[dt], n, h * w_, cs, _st()),
+              "instnorm_bwd")
+        # gamma||beta conv: weight grads + data grad (ReLU of mlp_shared fused as a mask)
+        gwp_gb, gbp_gb = conv_wgrad_raw(actv, ggb, g_gb, True)
+        gactv = conv_dgrad_raw(ggb, wp_gb, tuple(actv.shape), g_gb, _lib.ACT_RELU, actv)
+        gwp_sh, gbp_sh = conv_wgrad_raw(seg, gactv, g_sh, True)
+        gw_g = unpack_weight_grad(gwp_gb[:cs], g_shape)
+        gw_b = unpack_weight_grad(gwp_gb[cs:], g_shape)
+        gb_g = gbp_gb[:c].clone()
+        gb_b = gbp_gb[cs:cs + c].clone()
+        gw_sh = unpack_weight_grad(gwp_sh, sh_shape)
+        gb_sh = gbp_sh[: sh_shape[0]].clone()
+        if not ctx.needs_input_grad[0]:
+            gx = None
+        return gx, None, None, None, gw_sh, gb_sh, gw_g, gb_g, gw_b, gb_b, None, None, None
+
+
+def spade(x, mean, rstd, seg, w_sh, b_sh, w_g, b_g, w_b, b_b, act=_lib.ACT_NONE, slope=0.2,
+          engine=_lib.ENGINE_AUTO):
+    return _Spade.apply(x, mean, rstd, seg, w_sh, b_sh, w_g, b_g, w_b, b_b, act, slope, engine)
+
+
+class _ResizeNearest(Function):
+    @staticmethod
+    def forward(ctx, x, ho, wo):
+        _chk_storage(x)
+        n, hi, wi, c = x.shape
+        y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
+        check(_L().cgb_resize_nearest_fwd(_p(x), _p(y), _DT[x.dtype], n, hi, wi, ho, wo, c, _st()), "resize_nearest")
+        ctx.shape = (n, hi, wi, c)
+        ctx.f = ho // hi if (hi and ho % hi == 0 and wo % wi == 0 and ho // hi == wo // wi) else 0
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, hi, wi, c = ctx.shape
+        if ctx.f < 1:
+            raise NotImplementedError("backward of nearest resize is only implemented for integer up-scaling")
+        gy = gy.contiguous()
+        gx = torch.empty(ctx.shape, dtype=gy.dtype, device=gy.device)
+        check(_L().cgb_upsample_nearest_bwd(_p(gy), _p(gx), _DT[gy.dtype], n, hi, wi, ctx.f, c, _st()), "upsample_bwd")
+        return gx, None, None
+
+
+def resize_nearest(x, ho, wo):
+    """F.interpolate(x, size=(ho, wo), mode='nearest') on a storage tensor."""
+    return _ResizeNearest.apply(x, ho, wo)
+
+
+def upsample2x(x):
+    """InterpolateNearest2d(scale_factor=2) (climategan/blocks.py:11-43)."""
+    return _ResizeNearest.apply(x, x.shape[1] * 2, x.shape[2] * 2)
+
+
+class _Act(Function):
+    @staticmethod
+    def forward(ctx, x, act, slope):
+        y = torch.empty_like(x)
+        check(_L().cgb_act_fwd(_p(x), _p(y), _DT[x.dtype], x.numel(), act, slope, _st()), "act_fwd")
+        ctx.save_for_backward(y)
+        ctx.meta = (act, slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        return act_bwd_raw(gy.contiguous(), y, *ctx.meta), None, None
+
+
+def activation(x, act, slope=0.2):
+    return _Act.apply(x, act, slope)
+
+
+class _ToStorage(Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        x = x.contiguous().float()
+        n, c, h, w = x.shape
+        cs = round8(c)
+        y = torch.empty((n, h, w, cs), dtype=dtype, device=x.device)
+        check(_L().cgb_nchw_to_nhwc(_p(x), _p(y), _DT[dtype], n, c, h * w, cs, _st()), "nchw_to_nhwc")
+        ctx.c = c
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        gy = gy.contiguous()
+        n, h, w, cs = gy.shape
+        gx = torch.empty((n, ctx.c, h, w), dtype=torch.float32, device=gy.device)
+        check(_L().cgb_nhwc_to_nchw(_p(gy), _p(gx), _DT[gy.dtype], n, ctx.c, h * w, cs, _st()), "nhwc_to_nchw")
+        return gx, None
+
+
+class _FromStorage(Function):
+    @staticmethod
+    def forward(ctx, x, c):
+        _chk_storage(x)
+        n, h, w, cs = x.shape
+        y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+        check(_L().cgb_nhwc_to_nchw(_p(x), _p(y), _DT[x.dtype], n, c, h * w, cs, _st()), "nhwc_to_nchw")
+        ctx.meta = (cs, x.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        cs, dtype = ctx.meta
+        gy = gy.contiguous().float()
+        n, c, h, w = gy.shape
+        gx = torch.empty((n, h, w, cs), dtype=dtype, device=gy.device)
+        check(_L().cgb_nchw_to_nhwc(_p(gy), _p(gx), _DT[dtype], n, c, h * w, cs, _st()), "nchw_to_nhwc")
+        return gx, None
+
+
+def to_storage(x_nchw: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """NCHW fp32 (reference layout) -> NHWC storage tensor with zero channel padding."""
+    _lib.require_device()
+    if not x_nchw.is_cuda:
+        raise _lib.CgbError("climategan_b200 tensors must live on a CUDA device (no CPU path)")
+    return _ToStorage.apply(x_nchw, dtype)
+
+
+def from_storage(x: torch.Tensor, c: int) -> torch.Tensor:
+    """NHWC storage tensor -> NCHW fp32 with the logical channel count ``c``."""
+    return _FromStorage.apply(x, c)
+
+
+# ------------------------------------------------------------------------------------------------
+# compositing / losses
+# ------------------------------------------------------------------------------------------------
+def mask_cond(x: torch.Tensor, m: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Painter conditioning ``x * (1 - m)`` (generator.py:294) written straight into storage layout.
+    Not differentiable (m is ground truth / detached in the painter step)."""
+    _lib.require_device()
+    x = x.detach().contiguous().float()
+    m = m.detach().contiguous().float()
+    n, c, h, w = x.shape
+    assert c == 3 and m.shape == (n, 1, h, w), (x.shape, m.shape)
+    cond = torch.empty((n, h, w, 8), dtype=dtype, device=x.device)
+    check(_L().cgb_mask_cond(_p(x), _p(m), _p(cond), _DT[dtype], n, h * w, 8, _st()), "mask_cond")
+    return cond
+
+
+class _Paste(Function):
+    @staticmethod
+    def forward(ctx, x, m, fake):
+        x = x.contiguous().float()
+        m = m.contiguous().float()
+        fake = fake.contiguous()
+        n, _, h, w = x.shape
+        out = torch.empty_like(x)
+        check(_L().cgb_paste_fwd(_p(x), _p(m), _p(fake), _p(out), n, h * w, _st()), "paste_fwd")
+        ctx.save_for_backward(m)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (m,) = ctx.saved_tensors
+        gout = gout.contiguous()
+        n, _, h, w = gout.shape
+        gf = torch.empty_like(gout)
+        check(_L().cgb_paste_bwd(_p(gout), _p(m), _p(gf), n, h * w, _st()), "paste_bwd")
+        return None, None, gf
+
+
+def paste(x, m, fake):
+    """``x * (1 - m) + fake * m`` (generator.py:295-296); gradient flows to ``fake`` only."""
+    return _Paste.apply(x, m, fake)
+
+
+class _L1(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a = a.contiguous()
+        b = b.contiguous()
+        loss = torch.zeros((), dtype=torch.float32, device=a.device)
+        ga = torch.empty_like(a)
+        check(_L().cgb_l1_loss(_p(a), _p(b), _p(loss), _p(ga), a.numel(), 1.0 / a.numel(), _st()), "l1_loss")
+        ctx.save_for_backward(ga)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (ga,) = ctx.saved_tensors
+        return ga * g, None
+
+
+def l1_loss(a, b):
+    """nn.L1Loss()(a, b) (mean reduction; climategan/losses.py:290-301) — fp32 tensors."""
+    return _L1.apply(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# spectral norm
+# ------------------------------------------------------------------------------------------------
+class _SpectralWeight(Function):
+    """SpectralNorm._update_u_v (climategan/norms.py:100-112): one power iteration that mutates
+    u and v in place (on every call, train or eval), then w = w_bar / sigma with sigma = u.(W v)
+    differentiated w.r.t. w_bar only (u, v are .data in the reference)."""
+
+    @staticmethod
+    def forward(ctx, w_bar, u, v):
+        rows = w_bar.shape[0]
+        cols = w_bar.numel() // rows
+        wb = w_bar.detach().contiguous()
+        sigma = torch.empty((1,), dtype=torch.float32, device=w_bar.device)
+        check(_L().cgb_spectral_power_iter(_p(wb), _p(u), _p(v), _p(sigma), rows, cols, _st()), "spectral_power_iter")
+        w = wb / sigma
+        ctx.save_for_backward(w, u.detach().clone(), v.detach().clone(), sigma)
+        return w
+
+    @staticmethod
+    def backward(ctx, gw):
+        w, u, v, sigma = ctx.saved_tensors
+        rows = w.shape[0]
+        # d(w_bar/sigma) = g/sigma - <g, w_bar>/sigma^2 * u v^T = (g - <g, w> u v^T) / sigma
+        dot = (gw * w).sum()
+        gwb = (gw - dot * torch.outer(u, v).view_as(w)) / sigma
+        return gwb.view_as(w), None, None
+
+
+def spectral_weight(w_bar, u, v):
+    return _SpectralWeight.apply(w_bar, u, v)

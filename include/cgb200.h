@@ -1,0 +1,185 @@
+/*
+ * cgb200.h — C ABI of libcgb200.so: the sm_100a (B200) kernels behind the
+ * ClimateGAN conv-GAN hot path (SURVEY.md §8b "Downward" row).
+ *
+ * The reference (cc-ai/climategan) has no FFI: its "kernels" are torch.nn library
+ * calls.  Every entry point below therefore cites the reference *Python* call it
+ * replaces (file:line under the reference tree).  A maintainer binds these with
+ * ctypes from the reference's own modules — see INTEGRATION.md.
+ *
+ * Conventions
+ *  - All tensors are device pointers owned by the caller (PyTorch's allocator).
+ *    The library never allocates, frees or synchronises; all work is enqueued on
+ *    `stream` (a cudaStream_t passed as void*).
+ *  - Activations are NHWC, contiguous, with the channel count rounded up to a
+ *    multiple of 8 ("storage channels"); pad channels hold zeros.
+ *  - dtype: CGB_F32 or CGB_BF16 for activations / packed weights.  Accumulation
+ *    is always fp32 (fp64 for normalisation statistics).
+ *  - Packed conv weights: [co][kh*kw][ci] (K-major, ci fastest), zero padded to the
+ *    storage channel counts.  Weight gradients are fp32 in the same layout.
+ *  - Return value: CGB_OK (0) or a negative cgb_status; cgb_last_error() returns a
+ *    thread-local message.  There is no CPU fallback: without an sm_100 device
+ *    every compute entry point returns CGB_UNSUPPORTED_ARCH.
+ */
+#ifndef CGB200_H
+#define CGB200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  CGB_OK = 0,
+  CGB_BAD_ARG = -1,
+  CGB_UNSUPPORTED = -2,
+  CGB_LAUNCH_FAILURE = -3,
+  CGB_UNSUPPORTED_ARCH = -4
+} cgb_status;
+
+typedef enum { CGB_F32 = 0, CGB_BF16 = 1 } cgb_dtype;
+
+typedef enum {
+  CGB_ACT_NONE = 0,
+  CGB_ACT_RELU = 1,
+  CGB_ACT_LRELU = 2, /* slope given separately (0.2 everywhere in the reference) */
+  CGB_ACT_TANH = 3,
+  CGB_ACT_SIGMOID = 4
+} cgb_act;
+
+typedef enum { CGB_PAD_ZERO = 0, CGB_PAD_REFLECT = 1 } cgb_pad_mode;
+
+typedef enum {
+  CGB_ENGINE_AUTO = 0,   /* tcgen05 when the shape qualifies, else SIMT */
+  CGB_ENGINE_SIMT = 1,   /* CUDA-core implicit GEMM (any shape, fp32 or bf16) */
+  CGB_ENGINE_TCGEN05 = 2 /* TMA + tcgen05/TMEM implicit GEMM (bf16); error if the shape does not qualify */
+} cgb_engine;
+
+/* One 2-D convolution, forward geometry.  Used unchanged by fwd / dgrad / wgrad. */
+typedef struct cgb_conv_desc {
+  int32_t n, hi, wi, ci; /* input  [n,hi,wi,ci]  (ci = storage channels, %8==0) */
+  int32_t ho, wo, co;    /* output [n,ho,wo,co]  (co = storage channels, %8==0) */
+  int32_t kh, kw;
+  int32_t stride, dil, pad; /* symmetric */
+  int32_t pad_mode;         /* cgb_pad_mode */
+  int32_t dtype;            /* cgb_dtype of x, w, y, residual, mask_src */
+  int32_t act;              /* epilogue activation (fwd) */
+  float slope;              /* leaky-relu slope */
+  int32_t engine;           /* cgb_engine */
+} cgb_conv_desc;
+
+/* ---- library --------------------------------------------------------------------------- */
+const char* cgb_version(void);
+const char* cgb_last_error(void);
+/* 1 when the current device is sm_100 (B200), else 0. */
+int cgb_device_ok(void);
+/* number of kernels this library has launched since load / since the last reset (bench "gpu_launches") */
+int64_t cgb_launch_count(void);
+void cgb_launch_count_reset(void);
+/* 1 if cgb_conv2d_fwd / dgrad / wgrad with this desc would run on tcgen05 */
+int cgb_conv2d_uses_tcgen05(const cgb_conv_desc* d, int which /*0 fwd, 1 dgrad, 2 wgrad*/);
+
+/* ---- convolution -------------------------------------------------------------------------
+ * Replaces nn.Conv2d / F.conv2d as used by Conv2dBlock (climategan/blocks.py:138-144),
+ * SPADE.mlp_shared/mlp_gamma/mlp_beta (climategan/norms.py:164-171,180-182) and the
+ * SPADEResnetBlock convs (climategan/blocks.py:349-353), padding (blocks.py:66-71) included.
+ *   y = act(conv(x, w) + bias) (+ residual)
+ * residual: optional [n,ho,wo,co], added after the activation (blocks.py:196, :377).
+ */
+int cgb_conv2d_fwd(const cgb_conv_desc* d, const void* x, const void* w, const float* bias,
+                   const void* residual, void* y, void* stream);
+
+/* Data gradient of the same conv (autograd of F.conv2d w.r.t. its input):
+ *   gx = conv_transpose(gy, w)   [n,hi,wi,ci]
+ * dact/mask_src (optional): multiply gx by the derivative of the activation that PRODUCED x,
+ * evaluated from mask_src = that layer's output ([n,hi,wi,ci]): relu/lrelu use sign(mask_src),
+ * tanh uses 1-mask_src^2.  This fuses e.g. the ReLU of SPADE.mlp_shared (norms.py:165) into
+ * the dgrad of mlp_gamma/mlp_beta.  gy is the gradient w.r.t. the conv's pre-activation output. */
+int cgb_conv2d_dgrad(const cgb_conv_desc* d, const void* gy, const void* w, int32_t dact,
+                     const void* mask_src, void* gx, void* stream);
+
+/* Weight (+bias) gradient: gw[co][kh*kw][ci] (fp32), gbias[co] (fp32, optional).
+ * accumulate=0 zero-fills gw/gbias first. */
+int cgb_conv2d_wgrad(const cgb_conv_desc* d, const void* x, const void* gy, float* gw, float* gbias,
+                     int32_t accumulate, void* stream);
+
+/* ---- normalisation -----------------------------------------------------------------------
+ * nn.InstanceNorm2d(affine=False), eps 1e-5, biased variance (climategan/norms.py:151,176;
+ * discriminator.py:71-73).  x [n,hw,c] -> mean,rstd [n,c] fp32.  ws: n*c*2 doubles scratch. */
+int cgb_instnorm_stats(const void* x, int32_t dtype, int32_t n, int32_t hw, int32_t c, float eps,
+                       double* ws, float* mean, float* rstd, void* stream);
+
+/* SPADE de-normalisation + following activation (norms.py:184 then blocks.py:372-373,394):
+ *   out = act( (x-mean)*rstd * (1+gamma) + beta ),  gamma = gb[...,0:c], beta = gb[...,c:2c]
+ * gb is the [n,hw,2c] output of the fused mlp_gamma||mlp_beta conv. */
+int cgb_spade_modulate_fwd(const void* x, const float* mean, const float* rstd, const void* gb,
+                           void* out, int32_t dtype, int32_t n, int32_t hw, int32_t c, int32_t act,
+                           float slope, void* stream);
+
+/* Backward of the above, part 1.  Recomputes the pre-activation, then
+ *   gs = gout*act'(pre); ggb = [gs*xhat || gs]; gxhat = gs*(1+gamma)
+ * and accumulates sums[n,c,0] += sum_hw gxhat, sums[n,c,1] += sum_hw gxhat*xhat (fp64; caller zeroes). */
+int cgb_spade_modulate_bwd(const void* x, const float* mean, const float* rstd, const void* gb,
+                           const void* gout, void* ggb, void* gxhat, double* sums, int32_t dtype,
+                           int32_t n, int32_t hw, int32_t c, int32_t act, float slope, void* stream);
+
+/* Backward of instance norm, part 2 (in place on gxhat -> gx):
+ *   gx = rstd * (gxhat - sums0/hw - xhat*sums1/hw) */
+int cgb_instnorm_bwd(const void* x, const float* mean, const float* rstd, const double* sums,
+                     void* gxhat_inout, int32_t dtype, int32_t n, int32_t hw, int32_t c, void* stream);
+
+/* ---- resampling --------------------------------------------------------------------------
+ * F.interpolate(mode="nearest") (blocks.py:39-43 InterpolateNearest2d; norms.py:179; painter.py:152):
+ * src index = floor(dst * in/out). */
+int cgb_resize_nearest_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t hi, int32_t wi,
+                           int32_t ho, int32_t wo, int32_t c, void* stream);
+/* adjoint of the above for integer up-scaling factors (ho = hi*f): gx = sum over the f*f replicas */
+int cgb_upsample_nearest_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi, int32_t wi,
+                             int32_t f, int32_t c, void* stream);
+
+/* ---- layout / elementwise ----------------------------------------------------------------
+ * NCHW fp32 (the reference's tensor layout at the API edge) <-> NHWC storage. */
+int cgb_nchw_to_nhwc(const float* x, void* y, int32_t dtype, int32_t n, int32_t c, int32_t hw,
+                     int32_t cs, void* stream);
+int cgb_nhwc_to_nchw(const void* x, float* y, int32_t dtype, int32_t n, int32_t c, int32_t hw,
+                     int32_t cs, void* stream);
+/* gx = gy * act'(y)  (y = activation output) */
+int cgb_act_bwd(const void* gy, const void* y, void* gx, int32_t dtype, int64_t count, int32_t act,
+                float slope, void* stream);
+/* y = act(x) elementwise (F.leaky_relu before conv_img, painter.py:166) */
+int cgb_act_fwd(const void* x, void* y, int32_t dtype, int64_t count, int32_t act, float slope,
+                void* stream);
+
+/* ---- compositing -------------------------------------------------------------------------
+ * OmniGenerator.paint (climategan/generator.py:279-297), NCHW fp32 at the API edge:
+ *   cond = x*(1-m)                       -> NHWC storage (painter input)
+ *   out  = x*(1-m) + fake*m              (paste_original_content)
+ * m is [n,1,h,w]; x, fake, out are [n,3,h,w] fp32. */
+int cgb_mask_cond(const float* x, const float* m, void* cond, int32_t dtype, int32_t n, int32_t hw,
+                  int32_t cs, void* stream);
+int cgb_paste_fwd(const float* x, const float* m, const float* fake, float* out, int32_t n, int32_t hw,
+                  void* stream);
+/* gfake = gout * m */
+int cgb_paste_bwd(const float* gout, const float* m, float* gfake, int32_t n, int32_t hw, void* stream);
+
+/* ---- losses ------------------------------------------------------------------------------
+ * mean |a-b| and its gradient w.r.t. a (nn.L1Loss; climategan/losses.py:290-301, FeatMatchLoss :86-103):
+ *   loss[0] (+)= scale * sum|a-b| ;  ga = scale*gscale * sign(a-b)   (ga optional)
+ * `loss` is a device fp32 scalar the caller zeroes. */
+int cgb_l1_loss(const float* a, const float* b, float* loss, float* ga, int64_t count, float scale,
+                void* stream);
+
+/* ---- spectral norm -----------------------------------------------------------------------
+ * SpectralNorm._update_u_v (climategan/norms.py:100-112), one power iteration:
+ *   v <- normalize(W^T u) ; u <- normalize(W v) ; sigma = u.(W v)
+ * W is w_bar viewed [rows, cols] fp32 row-major; u[rows], v[cols] updated in place; sigma -> device scalar.
+ * One CTA per call; tiny (W <= 640x5760). */
+int cgb_spectral_power_iter(const float* w, float* u, float* v, float* sigma, int32_t rows,
+                            int32_t cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGB200_H */

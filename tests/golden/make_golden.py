@@ -1,0 +1,89 @@
+"""Generate tests/golden/painter_small.{npz,json} by running the UNMODIFIED reference modules
+(imported from /root/reference through oracle/refshim.py) on CPU.  Run in the build container:
+
+    python tests/golden/make_golden.py
+
+The reference has no golden vectors of its own; these pin the oracle
+(oracle/painter_oracle.py) and, through it and directly, the CUDA path.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import refshim  # noqa: E402
+from tests.golden.weights import fill_state_dict, synth_inputs  # noqa: E402
+from climategan_b200.utils import default_painter_opts  # noqa: E402
+
+CASES = {
+    # name: (latent_dim, spade_n_up, batch, size)   channels 40->40->40->20 exercise the %8 padding
+    "painter_small": (40, 3, 2, 32),
+}
+
+
+def run_case(name, latent_dim, n_up, batch, size):
+    painter_mod, generator_mod = refshim.load("painter", "generator")
+    opts = default_painter_opts(latent_dim=latent_dim, spade_n_up=n_up)
+    torch.manual_seed(0)
+    G = generator_mod.OmniGenerator(opts)  # tasks = ['p'] -> painter only (generator.py:65-101)
+    G.painter.set_latent_shape(size, True)
+    shapes = [(k, tuple(v.shape)) for k, v in G.painter.state_dict().items()]
+    sd = fill_state_dict(shapes, seed=1234)
+    G.painter.load_state_dict(sd, strict=True)
+    G.train()
+    x, m, target = synth_inputs(batch, size, seed=99)
+    out = G.paint(m, x)  # generator.py:279-297
+    loss = torch.nn.L1Loss()(out, target)
+    loss.backward()
+    sd_after = {k: v.clone() for k, v in G.painter.state_dict().items()}  # after exactly one forward
+    fake = None
+    with torch.no_grad():
+        # second forward: spectral-norm u/v have advanced one step (norms.py:106-108)
+        out2 = G.paint(m, x)
+        G2 = generator_mod.OmniGenerator(opts)
+        G2.painter.set_latent_shape(size, True)
+        G2.painter.load_state_dict(sd, strict=True)
+        fake = G2.paint(m, x, no_paste=True)
+    grads = {k: p.grad for k, p in G.painter.named_parameters() if p.grad is not None}
+    full = ["fc.weight", "conv_img.weight", "conv_img.bias", "final_spade.norm_1.mlp_gamma.weight",
+            "final_spade.norm_0.mlp_shared.0.weight", "up_spades.0.conv_s.module.weight_bar",
+            "head_0.conv_0.module.weight_bar", "up_spades.0.norm_s.mlp_beta.bias"]
+    arrays = {
+        "out": out.detach().numpy(),
+        "out_second_forward": out2.numpy(),
+        "fake_no_paste": fake.numpy(),
+        "loss": np.float32(loss.item()),
+        "grad_norms": np.array([float(grads[k].norm()) for k, _ in shapes if k in grads], dtype=np.float64),
+        "u_after": sd_after["head_0.conv_0.module.weight_u"].numpy(),
+        "v_after": sd_after["up_spades.0.conv_s.module.weight_v"].numpy(),
+    }
+    for k in full:
+        arrays["grad::" + k] = grads[k].numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+    meta = {
+        "case": name, "latent_dim": latent_dim, "spade_n_up": n_up, "batch": batch, "size": size,
+        "weight_seed": 1234, "input_seed": 99,
+        "shapes": [[k, list(s)] for k, s in shapes],
+        "grad_keys": [k for k, _ in shapes if k in grads],
+        "reference": "cc-ai/climategan @ /root/reference (climategan/{painter,generator,blocks,norms}.py)",
+        "torch": torch.__version__,
+    }
+    with open(os.path.join(HERE, name + ".json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print(name, "loss", float(loss), "out absmax", float(out.abs().max()), "npz bytes",
+          os.path.getsize(os.path.join(HERE, name + ".npz")))
+
+
+if __name__ == "__main__":
+    if not refshim.available():
+        sys.exit("reference tree not available; goldens can only be regenerated in the build container")
+    for name, cfg in CASES.items():
+        run_case(name, *cfg)

@@ -1,0 +1,82 @@
+"""CPU tests: the oracle (oracle/painter_oracle.py) against the committed golden vectors that the
+unmodified reference produced, and — when the reference tree is present — against the reference
+modules themselves."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import painter_oracle as po
+from oracle import refshim
+from tests.helpers import load_golden, rel_max
+
+
+def _oracle_run(sd, x, m, target, meta):
+    sd = {k: v.clone().requires_grad_(not (k.endswith("_u") or k.endswith("_v"))) for k, v in sd.items()}
+    z = meta["size"] // 2 ** meta["spade_n_up"]
+    out = po.paint(sd, m, x, z, z, po.n_up_spades_of(sd))
+    loss = torch.nn.functional.l1_loss(out, target)
+    loss.backward()
+    return sd, out, loss
+
+
+def test_oracle_matches_golden():
+    meta, g, sd, (x, m, t) = load_golden()
+    sd, out, loss = _oracle_run(sd, x, m, t, meta)
+    assert rel_max(out, torch.from_numpy(g["out"])) < 1e-5
+    assert abs(float(loss) - float(g["loss"])) < 1e-6
+    norms = np.array([float(sd[k].grad.norm()) for k in meta["grad_keys"]])
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=2e-4, atol=1e-7)
+    for k, v in g.items():
+        if k.startswith("grad::"):
+            assert rel_max(sd[k[6:]].grad, torch.from_numpy(v)) < 2e-4, k
+    # spectral-norm state advanced exactly one power iteration
+    assert rel_max(sd["head_0.conv_0.module.weight_u"], torch.from_numpy(g["u_after"])) < 1e-5
+    assert rel_max(sd["up_spades.0.conv_s.module.weight_v"], torch.from_numpy(g["v_after"])) < 1e-5
+
+
+def test_oracle_second_forward_and_no_paste():
+    meta, g, sd, (x, m, t) = load_golden()
+    z = meta["size"] // 2 ** meta["spade_n_up"]
+    n_up = po.n_up_spades_of(sd)
+    with torch.no_grad():
+        sd1 = {k: v.clone() for k, v in sd.items()}
+        fake = po.paint(sd1, m, x, z, z, n_up, paste=False)
+        assert rel_max(fake, torch.from_numpy(g["fake_no_paste"])) < 1e-5
+        out2 = po.paint(sd1, m, x, z, z, n_up)  # u/v advanced by the first call
+        assert rel_max(out2, torch.from_numpy(g["out_second_forward"])) < 1e-5
+
+
+def test_spectral_norm_properties():
+    torch.manual_seed(3)
+    w = torch.randn(24, 16, 3, 3)
+    u = po.l2normalize(torch.randn(24))
+    v = po.l2normalize(torch.randn(16 * 9))
+    for _ in range(200):
+        wn, u, v = po.spectral_norm_weight(w, u, v)
+    s = torch.linalg.svdvals(w.view(24, -1))[0]
+    assert abs(float(torch.linalg.svdvals(wn.view(24, -1))[0]) - 1.0) < 1e-3
+    assert abs(float((w / wn).flatten()[0]) - float(s)) / float(s) < 1e-3
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted")
+def test_oracle_vs_reference_modules():
+    """Bit-level agreement of the restatement with the reference's own modules (CPU, fp32)."""
+    from climategan_b200.utils import default_painter_opts
+
+    painter_mod = refshim.load("painter")
+    for latent, n_up, size in [(40, 3, 32), (16, 4, 64)]:
+        opts = default_painter_opts(latent_dim=latent, spade_n_up=n_up)
+        torch.manual_seed(1)
+        ref = painter_mod.PainterSpadeDecoder(opts)
+        ref.set_latent_shape(size, True)
+        sd = {k: v.clone() for k, v in ref.state_dict().items()}
+        cond = torch.rand(2, 3, size, size) * 2 - 1
+        with torch.no_grad():
+            a = ref(None, cond)
+            b = po.painter_forward(sd, cond, ref.z_h, ref.z_w, po.n_up_spades_of(sd))
+        assert float((a - b).abs().max()) < 1e-6
+        # u/v state after the forward must agree too
+        for k, v in ref.state_dict().items():
+            if k.endswith("_u") or k.endswith("_v"):
+                assert float((v - sd[k]).abs().max()) < 1e-6, k
