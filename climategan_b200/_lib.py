@@ -76,6 +76,8 @@ SIGNATURES = {
     "cgb_device_ok": ([], C.c_int),
     "cgb_launch_count": ([], C.c_int64),
     "cgb_launch_count_reset": ([], None),
+    "cgb_prof_enable": ([C.c_int], None),
+    "cgb_prof_dump": ([C.c_char_p, C.c_int64], C.c_int),
     "cgb_conv2d_uses_tcgen05": ([_DP, C.c_int], C.c_int),
     "cgb_conv2d_fwd": ([_DP, _P, _P, _P, _P, _P, _P], C.c_int),
     "cgb_conv2d_dgrad": ([_DP, _P, _P, _I, _P, _P, _P], C.c_int),

@@ -2,6 +2,10 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <string.h>
+#include <vector>
+#include <mutex>
+#include <map>
+#include <string>
 
 namespace cgb {
 
@@ -36,6 +40,30 @@ int check_device() {
   if (st != CGB_OK) set_error("libcgb200 needs an sm_100 (B200) device; no CPU fallback exists");
   return st;
 }
+
+// ---- optional per-launch timing of the conv engines (bench.py roofline leg) ----------------------
+// When enabled, every conv launch is bracketed by two CUDA events recorded on the launching stream;
+// cgb_prof_dump() (after the caller synchronised) folds them into per-(op,engine,shape) totals.
+struct ProfRec { cudaEvent_t a, b; cgb_conv_desc d; int which; int tc; };
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+static std::atomic<int> g_prof_on{0};
+
+struct ProfScope {
+  bool on; ProfRec r; cudaStream_t st;
+  ProfScope(const cgb_conv_desc* d, int which, bool tc, cudaStream_t s) : on(g_prof_on.load() != 0), st(s) {
+    if (!on) return;
+    r.d = *d; r.which = which; r.tc = tc ? 1 : 0;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.b, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+  }
+};
 
 // engines
 int conv_simt_fwd(const cgb_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t);
@@ -118,6 +146,7 @@ extern "C" int cgb_conv2d_fwd(const cgb_conv_desc* d, const void* x, const void*
   s = pick_engine(d, 0, "conv2d_fwd", &tc);
   if (s) return s;
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(d, 0, tc, st);
   return tc ? conv_tc_fwd(d, x, w, bias, residual, y, st) : conv_simt_fwd(d, x, w, bias, residual, y, st);
 }
 
@@ -136,6 +165,7 @@ extern "C" int cgb_conv2d_dgrad(const cgb_conv_desc* d, const void* gy, const vo
   s = pick_engine(d, 1, "conv2d_dgrad", &tc);
   if (s) return s;
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(d, 1, tc, st);
   return tc ? conv_tc_dgrad(d, gy, w, dact, mask_src, gx, st) : conv_simt_dgrad(d, gy, w, dact, mask_src, gx, st);
 }
 
@@ -153,5 +183,42 @@ extern "C" int cgb_conv2d_wgrad(const cgb_conv_desc* d, const void* x, const voi
   bool tc = false;
   s = pick_engine(d, 2, "conv2d_wgrad", &tc);
   if (s) return s;
+  ProfScope ps(d, 2, tc, st);
   return tc ? conv_tc_wgrad(d, x, gy, gw, gbias, st) : conv_simt_wgrad(d, x, gy, gw, gbias, st);
+}
+
+// ---- profiler ABI ---------------------------------------------------------------------------------
+extern "C" void cgb_prof_enable(int on) {
+  g_prof_on.store(on ? 1 : 0);
+}
+
+// Folds all recorded launches into text lines "which engine n hi wi ci ho wo co kh kw stride dil count total_ms"
+// written to buf (NUL terminated, truncated to cap).  Caller must have synchronised the device.
+// Returns the number of distinct keys, clears the records.
+extern "C" int cgb_prof_dump(char* buf, int64_t cap) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  std::map<std::string, std::pair<int, double>> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    char key[256];
+    snprintf(key, sizeof(key), "%d %d %d %d %d %d %d %d %d %d %d %d %d", r.which, r.tc, r.d.n, r.d.hi, r.d.wi,
+             r.d.ci, r.d.ho, r.d.wo, r.d.co, r.d.kh, r.d.kw, r.d.stride, r.d.dil);
+    auto& e = agg[key];
+    e.first += 1; e.second += ms;
+  }
+  g_prof.clear();
+  std::string out;
+  for (auto& kv : agg) {
+    char line[384];
+    snprintf(line, sizeof(line), "%s %d %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    out += line;
+  }
+  if (buf && cap > 0) {
+    size_t nb = out.size() < (size_t)(cap - 1) ? out.size() : (size_t)(cap - 1);
+    memcpy(buf, out.data(), nb);
+    buf[nb] = 0;
+  }
+  return (int)agg.size();
 }

@@ -250,38 +250,42 @@ upsample_bwd_kernel(const T* __restrict__ gy, T* __restrict__ gx, long long tota
 template <typename T>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int c, int hw, int cs) {
-  extern __shared__ float tile[];  // [cs][33]
+  __shared__ float tile[64 * 33];  // [64 channels][32 pixels + 1]
   const int img = blockIdx.y;
   const int p0 = blockIdx.x * 32;
-  for (int i = threadIdx.x; i < cs * 32; i += blockDim.x) {
+  const int c0 = blockIdx.z * 64;
+  const int cn = min(64, cs - c0);  // channels in this block (multiple of 8)
+  for (int i = threadIdx.x; i < cn * 32; i += blockDim.x) {
     const int ch = i >> 5, p = i & 31;
     float v = 0.f;
-    if (ch < c && p0 + p < hw) v = x[((long long)img * c + ch) * hw + p0 + p];
+    if (c0 + ch < c && p0 + p < hw) v = x[((long long)img * c + c0 + ch) * hw + p0 + p];
     tile[ch * 33 + p] = v;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < cs * 32; i += blockDim.x) {
-    const int p = i / cs, ch = i - p * cs;
-    if (p0 + p < hw) y[((long long)img * hw + p0 + p) * cs + ch] = from_f<T>(tile[ch * 33 + p]);
+  for (int i = threadIdx.x; i < cn * 32; i += blockDim.x) {
+    const int p = i / cn, ch = i - p * cn;
+    if (p0 + p < hw) y[((long long)img * hw + p0 + p) * cs + c0 + ch] = from_f<T>(tile[ch * 33 + p]);
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int c, int hw, int cs) {
-  extern __shared__ float tile[];  // [cs][33]
+  __shared__ float tile[64 * 33];
   const int img = blockIdx.y;
   const int p0 = blockIdx.x * 32;
-  for (int i = threadIdx.x; i < cs * 32; i += blockDim.x) {
-    const int p = i / cs, ch = i - p * cs;
+  const int c0 = blockIdx.z * 64;
+  const int cn = min(64, cs - c0);
+  for (int i = threadIdx.x; i < cn * 32; i += blockDim.x) {
+    const int p = i / cn, ch = i - p * cn;
     float v = 0.f;
-    if (p0 + p < hw) v = to_f<T>(x[((long long)img * hw + p0 + p) * cs + ch]);
+    if (p0 + p < hw) v = to_f<T>(x[((long long)img * hw + p0 + p) * cs + c0 + ch]);
     tile[ch * 33 + p] = v;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < c * 32; i += blockDim.x) {
+  for (int i = threadIdx.x; i < cn * 32; i += blockDim.x) {
     const int ch = i >> 5, p = i & 31;
-    if (p0 + p < hw) y[((long long)img * c + ch) * hw + p0 + p] = tile[ch * 33 + p];
+    if (c0 + ch < c && p0 + p < hw) y[((long long)img * c + c0 + ch) * hw + p0 + p] = tile[ch * 33 + p];
   }
 }
 
@@ -546,10 +550,10 @@ extern "C" int cgb_nchw_to_nhwc(const float* x, void* y, int32_t dtype, int32_t 
                                 int32_t cs, void* stream) {
   CGB_CHECK_DEVICE();
   CGB_REQUIRE(x && y, "nchw_to_nhwc: null pointer");
-  CGB_REQUIRE(cs % 8 == 0 && cs >= c && cs <= 1024, "nchw_to_nhwc: bad cs=%d for c=%d", cs, c);
+  CGB_REQUIRE(cs % 8 == 0 && cs >= c && n <= 65535, "nchw_to_nhwc: bad cs=%d for c=%d", cs, c);
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((hw + 31) / 32, n);
-  DISPATCH_T(dtype, nchw_to_nhwc_kernel<T><<<grid, 256, cs * 33 * sizeof(float), st>>>(x, (T*)y, c, hw, cs);)
+  dim3 grid((hw + 31) / 32, n, (cs + 63) / 64);
+  DISPATCH_T(dtype, nchw_to_nhwc_kernel<T><<<grid, 256, 0, st>>>(x, (T*)y, c, hw, cs);)
   return after_launch("nchw_to_nhwc");
 }
 
@@ -557,10 +561,10 @@ extern "C" int cgb_nhwc_to_nchw(const void* x, float* y, int32_t dtype, int32_t 
                                 int32_t cs, void* stream) {
   CGB_CHECK_DEVICE();
   CGB_REQUIRE(x && y, "nhwc_to_nchw: null pointer");
-  CGB_REQUIRE(cs % 8 == 0 && cs >= c && cs <= 1024, "nhwc_to_nchw: bad cs=%d for c=%d", cs, c);
+  CGB_REQUIRE(cs % 8 == 0 && cs >= c && n <= 65535, "nhwc_to_nchw: bad cs=%d for c=%d", cs, c);
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((hw + 31) / 32, n);
-  DISPATCH_T(dtype, nhwc_to_nchw_kernel<T><<<grid, 256, cs * 33 * sizeof(float), st>>>((const T*)x, y, c, hw, cs);)
+  dim3 grid((hw + 31) / 32, n, (cs + 63) / 64);
+  DISPATCH_T(dtype, nhwc_to_nchw_kernel<T><<<grid, 256, 0, st>>>((const T*)x, y, c, hw, cs);)
   return after_launch("nhwc_to_nchw");
 }
 

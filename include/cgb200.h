@@ -78,6 +78,12 @@ int cgb_device_ok(void);
 /* number of kernels this library has launched since load / since the last reset (bench "gpu_launches") */
 int64_t cgb_launch_count(void);
 void cgb_launch_count_reset(void);
+/* Per-launch timing of the conv engines (CUDA events on the launching stream), for bench.py's roofline
+ * leg — the analogue of the reference's utils.Timer (climategan/utils.py:919-959).
+ * cgb_prof_dump: after the caller synchronised, writes one line per (op, engine, shape):
+ *   "which tc n hi wi ci ho wo co kh kw stride dil count total_ms"  and clears the records. */
+void cgb_prof_enable(int on);
+int cgb_prof_dump(char* buf, int64_t cap);
 /* 1 if cgb_conv2d_fwd / dgrad / wgrad with this desc would run on tcgen05 */
 int cgb_conv2d_uses_tcgen05(const cgb_conv_desc* d, int which /*0 fwd, 1 dgrad, 2 wgrad*/);
 
@@ -166,7 +172,7 @@ int cgb_paste_bwd(const float* gout, const float* m, float* gfake, int32_t n, in
 
 /* ---- losses ------------------------------------------------------------------------------
  * mean |a-b| and its gradient w.r.t. a (nn.L1Loss; climategan/losses.py:290-301, FeatMatchLoss :86-103):
- *   loss[0] (+)= scale * sum|a-b| ;  ga = scale*gscale * sign(a-b)   (ga optional)
+ *   loss[0] += scale * sum|a-b| ;  ga = scale * sign(a-b)   (ga optional)
  * `loss` is a device fp32 scalar the caller zeroes. */
 int cgb_l1_loss(const float* a, const float* b, float* loss, float* ga, int64_t count, float scale,
                 void* stream);
