@@ -80,7 +80,8 @@ SIGNATURES = {
     "cgb_prof_dump": ([C.c_char_p, C.c_int64], C.c_int),
     "cgb_conv2d_uses_tcgen05": ([_DP, C.c_int], C.c_int),
     "cgb_conv2d_fwd": ([_DP, _P, _P, _P, _P, _P, _P], C.c_int),
-    "cgb_conv2d_dgrad": ([_DP, _P, _P, _I, _P, _P, _P], C.c_int),
+    "cgb_conv2d_dgrad": ([_DP, _P, _P, _P, _I, _P, _P, _P], C.c_int),
+    "cgb_conv2d_pack_dgrad_weight": ([_DP, _P, _P, _P], C.c_int),
     "cgb_conv2d_wgrad": ([_DP, _P, _P, _P, _P, _I, _P], C.c_int),
     "cgb_instnorm_stats": ([_P, _I, _I, _I, _I, _F, _P, _P, _P, _P], C.c_int),
     "cgb_spade_modulate_fwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),

@@ -73,6 +73,7 @@ bool conv_tc_supported(const cgb_conv_desc*, int which);
 int conv_tc_fwd(const cgb_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t);
 int conv_tc_dgrad(const cgb_conv_desc*, const void*, const void*, int, const void*, void*, cudaStream_t);
 int conv_tc_wgrad(const cgb_conv_desc*, const void*, const void*, float*, float*, cudaStream_t);
+int pack_dgrad_weight(const cgb_conv_desc*, const void*, void*, cudaStream_t);
 
 static int validate(const cgb_conv_desc* d, const char* who) {
   if (!d) { set_error("%s: null descriptor", who); return CGB_BAD_ARG; }
@@ -150,12 +151,20 @@ extern "C" int cgb_conv2d_fwd(const cgb_conv_desc* d, const void* x, const void*
   return tc ? conv_tc_fwd(d, x, w, bias, residual, y, st) : conv_simt_fwd(d, x, w, bias, residual, y, st);
 }
 
-extern "C" int cgb_conv2d_dgrad(const cgb_conv_desc* d, const void* gy, const void* w, int32_t dact,
+extern "C" int cgb_conv2d_pack_dgrad_weight(const cgb_conv_desc* d, const void* w, void* wt, void* stream) {
+  CGB_CHECK_DEVICE();
+  int s = validate(d, "conv2d_pack_dgrad_weight");
+  if (s) return s;
+  CGB_REQUIRE(w && wt, "conv2d_pack_dgrad_weight: null pointer");
+  return pack_dgrad_weight(d, w, wt, (cudaStream_t)stream);
+}
+
+extern "C" int cgb_conv2d_dgrad(const cgb_conv_desc* d, const void* gy, const void* w, const void* wt, int32_t dact,
                                 const void* mask_src, void* gx, void* stream) {
   CGB_CHECK_DEVICE();
   int s = validate(d, "conv2d_dgrad");
   if (s) return s;
-  CGB_REQUIRE(gy && w && gx, "conv2d_dgrad: null pointer");
+  CGB_REQUIRE(gy && (w || wt) && gx, "conv2d_dgrad: null pointer");
   if (d->pad_mode == CGB_PAD_REFLECT && d->pad > 0) {
     set_error("conv2d_dgrad: reflect padding is not implemented for the data gradient");
     return CGB_UNSUPPORTED;
@@ -164,9 +173,17 @@ extern "C" int cgb_conv2d_dgrad(const cgb_conv_desc* d, const void* gy, const vo
   bool tc = false;
   s = pick_engine(d, 1, "conv2d_dgrad", &tc);
   if (s) return s;
+  if (tc && !wt) {
+    if (d->engine == CGB_ENGINE_TCGEN05) {
+      set_error("conv2d_dgrad: the tcgen05 engine needs the dgrad weight packing (wt)");
+      return CGB_BAD_ARG;
+    }
+    tc = false;
+  }
+  CGB_REQUIRE(tc || w, "conv2d_dgrad: the SIMT engine needs the forward weight packing (w)");
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope ps(d, 1, tc, st);
-  return tc ? conv_tc_dgrad(d, gy, w, dact, mask_src, gx, st) : conv_simt_dgrad(d, gy, w, dact, mask_src, gx, st);
+  return tc ? conv_tc_dgrad(d, gy, wt, dact, mask_src, gx, st) : conv_simt_dgrad(d, gy, w, dact, mask_src, gx, st);
 }
 
 extern "C" int cgb_conv2d_wgrad(const cgb_conv_desc* d, const void* x, const void* gy, float* gw,

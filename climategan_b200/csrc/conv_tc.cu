@@ -1,8 +1,494 @@
-// tcgen05 engine placeholder (filled in below in the same commit series)
+// tcgen05 engine: TMA-fed implicit-GEMM convolution on the 5th-gen tensor cores (sm_100a).
+//
+//   GEMM view (fprop, and dgrad of stride-1 convs run as an fprop over gy with flipped/transposed weights):
+//     D[M = 128 output pixels][N = out channels] += A[M][K] * B[N][K]^T ,  K = taps x in-channels
+//   * A operand: for every filter tap, ONE 4-D TMA box {64 ch, TW*s, TH*s, TN} (element strides s) of the
+//     NHWC activation tensor, shifted by the tap offset.  Out-of-bounds coordinates (the zero padding, ragged
+//     tile edges, channel tails) are zero-filled by TMA, so there is no padded copy and no predicate in the
+//     loader (replaces ZeroPad2d + im2col of the reference's cuDNN path, climategan/blocks.py:66-71,117-144).
+//   * B operand: 3-D TMA box {64 ch, 1 tap, BN out-channels} of the packed weights [co][tap][ci].
+//   * Both land in shared memory in the 128-byte-swizzled K-major layout UMMA descriptors address directly.
+//   * One elected thread issues tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 -> fp32) into a TMEM accumulator;
+//     tcgen05.commit releases smem stages back to the TMA producer through mbarriers.
+//   * 4 epilogue warps read the accumulator with tcgen05.ld (32 lanes x 16 columns per instruction) and apply
+//     bias / activation / residual add / activation-derivative mask, then store bf16 NHWC.
+//   Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+//
+//   wgrad:  D[M = in-channels][N = out-channels] += X^T[M][K] * G^T[N][K]^T , K = pixels.  Both operands are
+//   "MN-major" for UMMA (the contraction index is the slow one in NHWC memory), loaded by the same shifted
+//   TMA boxes; one TMEM accumulator per filter tap, fp32 red.global.add into gw at the end.
 #include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+
 namespace cgb {
-bool conv_tc_supported(const cgb_conv_desc*, int) { return false; }
-int conv_tc_fwd(const cgb_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t) { return CGB_UNSUPPORTED; }
-int conv_tc_dgrad(const cgb_conv_desc*, const void*, const void*, int, const void*, void*, cudaStream_t) { return CGB_UNSUPPORTED; }
-int conv_tc_wgrad(const cgb_conv_desc*, const void*, const void*, float*, float*, cudaStream_t) { return CGB_UNSUPPORTED; }
+
+// ------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, 128B swizzle (layout_type 2), descriptor version 1 (Blackwell).
+//   K-major  operand: rows (M/N index) of 128 B, 8-row swizzle atoms 1024 B apart (SBO); LBO unused (1).
+//   MN-major operand: rows are K indices of 128 B = 64 contiguous M/N elements; groups of 8 K-rows are SBO=1024 B
+//                     apart; the next 64 M/N elements start LBO bytes further (one TMA box).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // version
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: bf16 x bf16 -> fp32, M=128
+__host__ __device__ inline uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                          // c_format  F32
+  d |= 1u << 7;                          // a_format  BF16
+  d |= 1u << 10;                         // b_format  BF16
+  d |= (a_mn_major ? 1u : 0u) << 15;     // a_major
+  d |= (b_mn_major ? 1u : 0u) << 16;     // b_major
+  d |= (uint32_t)(n >> 3) << 17;         // N >> 3
+  d |= (uint32_t)(128 >> 4) << 24;       // M >> 4
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// fprop / dgrad kernel
+// ------------------------------------------------------------------------------------------------------
+struct TcParams {
+  int n, hout, wout, cout_s, cin_s;
+  int kh, kw, dil, stride, pad_y, pad_x;
+  int tw_log, th_log;          // tile = TN x TH x TW pixels, product 128 (powers of two)
+  int tiles_x, tiles_y;
+  int bn;                      // N tile (multiple of 16, <= 256)
+  int kblocks;                 // ceil(cin_s / 64)
+  int stages;
+  int tmem_cols;
+  int act;
+  float slope;
+  int dact;                    // derivative mask (dgrad) from mask_src
+};
+
+constexpr int TC_THREADS = 192;
+constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 64 bf16
+
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
+               const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
+               const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // 1024-B alignment for the 128B swizzle atoms
+  const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
+  const uint32_t stage_bytes = A_TILE_BYTES + b_tile_bytes;
+  const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;  // full[s], empty[s], tmem_full, tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(p.stages + s); };
+  const uint32_t tmem_full_bar = bar_base + 16u * (uint32_t)p.stages;
+  const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  const int tile = blockIdx.x;
+  const int tx = tile % p.tiles_x;
+  const int ty = (tile / p.tiles_x) % p.tiles_y;
+  const int tn = tile / (p.tiles_x * p.tiles_y);
+  const int ox0 = tx << p.tw_log;
+  const int oy0 = ty << p.th_log;
+  const int n0 = tn << (7 - p.tw_log - p.th_log);
+  const int cn0 = blockIdx.y * p.bn;
+  const int taps = p.kh * p.kw;
+  const int iters = taps * p.kblocks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tap = 0; tap < taps; ++tap) {
+        const int dy = tap / p.kw, dx = tap - dy * p.kw;
+        const int cx = ox0 * p.stride - p.pad_x + dx * p.dil;
+        const int cy = oy0 * p.stride - p.pad_y + dy * p.dil;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t a_dst = base + (uint32_t)s * stage_bytes;
+          mbar_expect_tx(full_bar(s), stage_bytes);
+          tma_load_4d(a_dst, &tmA, full_bar(s), kb * 64, cx, cy, n0);
+          tma_load_3d(a_dst + A_TILE_BYTES, &tmB, full_bar(s), kb * 64, tap, cn0);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = make_idesc(p.bn, false, false);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < iters; ++it) {
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const int kb = it % p.kblocks;
+        int rem = p.cin_s - kb * 64;
+        if (rem > 64) rem = 64;
+        const int ksteps = (rem + 15) >> 4;
+        const uint32_t a_addr = base + (uint32_t)s * stage_bytes;
+        const uint32_t b_addr = a_addr + A_TILE_BYTES;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t ad = make_desc(a_addr + (uint32_t)k * 32u, 16u, 1024u);
+          const uint64_t bd = make_desc(b_addr + (uint32_t)k * 32u, 16u, 1024u);
+          umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));  // frees this smem stage once the MMAs above have read it
+        if (it == iters - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++s == p.stages) { s = 0; ph ^= 1u; }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;     // tile row == TMEM lane == pixel within the tile
+    const int tw_i = row & ((1 << p.tw_log) - 1);
+    const int th_i = (row >> p.tw_log) & ((1 << p.th_log) - 1);
+    const int tn_i = row >> (p.tw_log + p.th_log);
+    const int ox = ox0 + tw_i, oy = oy0 + th_i, img = n0 + tn_i;
+    const bool pix_ok = (ox < p.wout) && (oy < p.hout) && (img < p.n);
+    const long long pix = ((long long)img * p.hout + oy) * p.wout + ox;
+    mbar_wait(tmem_full_bar, 0u);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int c0 = 0; c0 < p.bn; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(t_row + (uint32_t)c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ch = cn0 + c0 + h * 8;
+        if (!pix_ok || ch >= p.cout_s) continue;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[h * 8 + j]);
+        if (bias) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + ch));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + ch + 4));
+          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+        if (p.act != CGB_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], p.act, p.slope);
+        }
+        const long long off = pix * p.cout_s + ch;
+        if (residual) {
+          float rr[8];
+          Vec8<__nv_bfloat16>::load(residual + off, rr);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] += rr[j];
+        }
+        if (mask_src) {
+          float mm[8];
+          Vec8<__nv_bfloat16>::load(mask_src + off, mm);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] *= act_grad_from_out(mm[j], p.dact, p.slope);
+        }
+        Vec8<__nv_bfloat16>::store(y + off, v);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+    else
+      cudaGetLastError();
+  });
+  return fn;
+}
+
+static bool encode_map(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                       const cuuint32_t* box, const cuuint32_t* estr, const char* what) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("tcgen05 engine: cuTensorMapEncodeTiled is unavailable in this driver");
+    return false;
+  }
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("tcgen05 engine: cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, (int)r);
+    return false;
+  }
+  return true;
+}
+
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
+// choose TW x TH x TN = 128 (powers of two) minimising the number of tiles; ties -> wider TW
+static void pick_tile(int n, int h, int w, int stride, int* tw_log, int* th_log) {
+  long long best = -1;
+  int bw = 7, bh = 0;
+  for (int a = 7; a >= 0; --a) {
+    if (((1 << a) * stride) > 256) continue;
+    for (int b = 7 - a; b >= 0; --b) {
+      if (((1 << b) * stride) > 256) continue;
+      const int c = 7 - a - b;
+      const long long tiles = (long long)((w + (1 << a) - 1) >> a) * ((h + (1 << b) - 1) >> b) * ((n + (1 << c) - 1) >> c);
+      if (best < 0 || tiles < best) {
+        best = tiles;
+        bw = a;
+        bh = b;
+      }
+    }
+  }
+  *tw_log = bw;
+  *th_log = bh;
+}
+
+static int pick_bn(int co) {
+  // largest multiple of 16 <= 256 that tiles co with the least padded work
+  const int co16 = (co + 15) / 16 * 16;
+  if (co16 <= 256) return co16;
+  int best_bn = 256;
+  long long best_waste = -1;
+  for (int bn = 256; bn >= 64; bn -= 16) {
+    const int tiles = (co + bn - 1) / bn;
+    const long long waste = (long long)tiles * bn - co;
+    if (best_waste < 0 || waste < best_waste) {
+      best_waste = waste;
+      best_bn = bn;
+    }
+  }
+  return best_bn;
+}
+
+bool conv_tc_supported(const cgb_conv_desc* d, int which) {
+  if (d->dtype != CGB_BF16) return false;
+  if (d->pad_mode != CGB_PAD_ZERO && d->pad > 0) return false;
+  if (which == 0) return d->stride <= 2;
+  if (which == 1) return d->stride == 1 && d->pad <= d->dil * (d->kh - 1) && d->pad <= d->dil * (d->kw - 1);
+  return false;  // wgrad: see conv_tc_wgrad
+}
+
+// Launch the fprop kernel on (in -> out).  in: [n,hin,win,cin_s], w: [cout_s][taps][cin_s], out: [n,hout,wout,cout_s]
+static int launch_fprop(const void* in, const void* w, void* out, int n, int hin, int win, int cin_s, int hout, int wout,
+                        int cout_s, int kh, int kw, int stride, int dil, int pad_y, int pad_x, int act, float slope,
+                        const float* bias, const void* residual, int dact, const void* mask_src, cudaStream_t st) {
+  TcParams p;
+  p.n = n; p.hout = hout; p.wout = wout; p.cout_s = cout_s; p.cin_s = cin_s;
+  p.kh = kh; p.kw = kw; p.dil = dil; p.stride = stride; p.pad_y = pad_y; p.pad_x = pad_x;
+  pick_tile(n, hout, wout, stride, &p.tw_log, &p.th_log);
+  const int tn_log = 7 - p.tw_log - p.th_log;
+  p.tiles_x = (wout + (1 << p.tw_log) - 1) >> p.tw_log;
+  p.tiles_y = (hout + (1 << p.th_log) - 1) >> p.th_log;
+  const int tiles_n = (n + (1 << tn_log) - 1) >> tn_log;
+  p.bn = pick_bn(cout_s);
+  p.kblocks = (cin_s + 63) / 64;
+  const int stage_bytes = A_TILE_BYTES + p.bn * 128;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 6) stages = 6;
+  const int iters = kh * kw * p.kblocks;
+  if (stages > iters) stages = iters;
+  if (stages < 1) stages = 1;
+  // keep >= 2 CTAs per SM resident when the tile is small (prologue/epilogue overlap between CTAs)
+  if (stage_bytes * stages > 100 * 1024 && stage_bytes * 4 <= 100 * 1024) stages = 4;
+  p.stages = stages;
+  int cols = 32;
+  while (cols < p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  p.act = act; p.slope = slope; p.dact = dact;
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)cin_s, (cuuint64_t)win, (cuuint64_t)hin, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)cin_s * 2, (cuuint64_t)win * cin_s * 2, (cuuint64_t)hin * win * cin_s * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)((1 << p.tw_log) * stride), (cuuint32_t)((1 << p.th_log) * stride),
+                         (cuuint32_t)(1 << tn_log)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    if (!encode_map(&tmA, in, 4, dims, strides, box, estr, "activations")) return CGB_LAUNCH_FAILURE;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)cin_s, (cuuint64_t)(kh * kw), (cuuint64_t)cout_s};
+    cuuint64_t strides[2] = {(cuuint64_t)cin_s * 2, (cuuint64_t)kh * kw * cin_s * 2};
+    cuuint32_t box[3] = {64, 1, (cuuint32_t)p.bn};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (!encode_map(&tmB, w, 3, dims, strides, box, estr, "weights")) return CGB_LAUNCH_FAILURE;
+  }
+  const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 16 + 1024;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * tiles_n), (unsigned)((cout_s + p.bn - 1) / p.bn));
+  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p, bias, (const __nv_bfloat16*)residual,
+                                                 (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out);
+  return after_launch("conv_tc");
+}
+
+int conv_tc_fwd(const cgb_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
+                cudaStream_t st) {
+  return launch_fprop(x, w, y, d->n, d->hi, d->wi, d->ci, d->ho, d->wo, d->co, d->kh, d->kw, d->stride, d->dil, d->pad,
+                      d->pad, d->act, d->slope, bias, residual, CGB_ACT_NONE, nullptr, st);
+}
+
+// wt: dgrad packing [ci][taps][co] with the taps reversed (cgb_conv2d_pack_dgrad_weight)
+int conv_tc_dgrad(const cgb_conv_desc* d, const void* gy, const void* wt, int dact, const void* mask_src, void* gx,
+                  cudaStream_t st) {
+  return launch_fprop(gy, wt, gx, d->n, d->ho, d->wo, d->co, d->hi, d->wi, d->ci, d->kh, d->kw, 1, d->dil,
+                      d->dil * (d->kh - 1) - d->pad, d->dil * (d->kw - 1) - d->pad, CGB_ACT_NONE, d->slope, nullptr, nullptr,
+                      dact, mask_src, st);
+}
+
+int conv_tc_wgrad(const cgb_conv_desc*, const void*, const void*, float*, float*, cudaStream_t) {
+  set_error("tcgen05 wgrad is not built yet");
+  return CGB_UNSUPPORTED;
+}
+
+// wt[ci][taps-1-t][co] = w[co][t][ci]
+template <typename T>
+__global__ void pack_dgrad_weight_kernel(const T* __restrict__ w, T* __restrict__ wt, int co, int taps, int ci) {
+  const long long total = (long long)co * taps * ci;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % co);
+    const long long r = i / co;
+    const int t = (int)(r % taps);
+    const int c = (int)(r / taps);
+    wt[i] = w[((long long)o * taps + (taps - 1 - t)) * ci + c];
+  }
+}
+
+int pack_dgrad_weight(const cgb_conv_desc* d, const void* w, void* wt, cudaStream_t st) {
+  const int taps = d->kh * d->kw;
+  const long long total = (long long)d->co * taps * d->ci;
+  int grid = (int)((total + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (d->dtype == CGB_F32)
+    pack_dgrad_weight_kernel<float><<<grid, 256, 0, st>>>((const float*)w, (float*)wt, d->co, taps, d->ci);
+  else
+    pack_dgrad_weight_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)w, (__nv_bfloat16*)wt, d->co, taps, d->ci);
+  return after_launch("pack_dgrad_weight");
+}
+
+}  // namespace cgb

@@ -112,7 +112,11 @@ def conv_dgrad_raw(gy, wp, x_shape, g: ConvGeom, dact=_lib.ACT_NONE, mask_src=No
     d = g.desc(n, hi, wi, ci, co, gy.dtype)
     assert (d.ho, d.wo, co) == tuple(gy.shape[1:]), (d.ho, d.wo, co, gy.shape)
     gx = torch.empty(x_shape, dtype=gy.dtype, device=gy.device)
-    check(_L().cgb_conv2d_dgrad(C.byref(d), _p(gy), _p(wp), dact, _p(mask_src), _p(gx), _st()), "conv2d_dgrad")
+    wt = None
+    if _L().cgb_conv2d_uses_tcgen05(C.byref(d), 1):
+        wt = torch.empty((ci, g.kh * g.kw, co), dtype=wp.dtype, device=wp.device)
+        check(_L().cgb_conv2d_pack_dgrad_weight(C.byref(d), _p(wp), _p(wt), _st()), "conv2d_pack_dgrad_weight")
+    check(_L().cgb_conv2d_dgrad(C.byref(d), _p(gy), _p(wp), _p(wt), dact, _p(mask_src), _p(gx), _st()), "conv2d_dgrad")
     return gx
 
 

@@ -103,8 +103,13 @@ int cgb_conv2d_fwd(const cgb_conv_desc* d, const void* x, const void* w, const f
  * evaluated from mask_src = that layer's output ([n,hi,wi,ci]): relu/lrelu use sign(mask_src),
  * tanh uses 1-mask_src^2.  This fuses e.g. the ReLU of SPADE.mlp_shared (norms.py:165) into
  * the dgrad of mlp_gamma/mlp_beta.  gy is the gradient w.r.t. the conv's pre-activation output. */
-int cgb_conv2d_dgrad(const cgb_conv_desc* d, const void* gy, const void* w, int32_t dact,
+int cgb_conv2d_dgrad(const cgb_conv_desc* d, const void* gy, const void* w, const void* wt, int32_t dact,
                      const void* mask_src, void* gx, void* stream);
+
+/* Weight packing the tcgen05 engine uses for the data gradient: wt[ci][kh*kw][co] with the taps reversed,
+ * wt[c][T-1-t][o] = w[o][t][c] — the stride-1 dgrad is then an ordinary conv of gy with wt (pad' = dil*(k-1)-pad).
+ * cgb_conv2d_dgrad takes w (SIMT engine) and/or wt (tcgen05 engine; NULL -> SIMT). */
+int cgb_conv2d_pack_dgrad_weight(const cgb_conv_desc* d, const void* w, void* wt, void* stream);
 
 /* Weight (+bias) gradient: gw[co][kh*kw][ci] (fp32), gbias[co] (fp32, optional).
  * accumulate=0 zero-fills gw/gbias first. */
