@@ -389,7 +389,7 @@ bool conv_tc_supported(const cgb_conv_desc* d, int which) {
   if (d->pad_mode != CGB_PAD_ZERO && d->pad > 0) return false;
   if (which == 0) return d->stride <= 2;
   if (which == 1) return d->stride == 1 && d->pad <= d->dil * (d->kh - 1) && d->pad <= d->dil * (d->kw - 1);
-  return false;  // wgrad: see conv_tc_wgrad
+  return d->stride <= 2 && d->co <= 2048;  // wgrad
 }
 
 // Launch the fprop kernel on (in -> out).  in: [n,hin,win,cin_s], w: [cout_s][taps][cin_s], out: [n,hout,wout,cout_s]
@@ -461,9 +461,283 @@ int conv_tc_dgrad(const cgb_conv_desc* d, const void* gy, const void* wt, int da
                       dact, mask_src, st);
 }
 
-int conv_tc_wgrad(const cgb_conv_desc*, const void*, const void*, float*, float*, cudaStream_t) {
-  set_error("tcgen05 wgrad is not built yet");
-  return CGB_UNSUPPORTED;
+// ------------------------------------------------------------------------------------------------------
+// wgrad kernel:  gw[co][tap][ci] += sum_pixels gy[pix][co] * x[pix shifted by tap][ci]
+//   UMMA view: D_tap[M][N] += P^T[M][K] * Q^T[N][K]^T with K = 128 pixels per step; M is whichever of (ci, co)
+//   is larger (fills the 128 TMEM lanes), N the other.  Both operands are MN-major in shared memory (a TMA box
+//   row is one pixel = one K index holding 64 contiguous channels).  One TMEM accumulator per filter tap of the
+//   CTA's tap group; the un-shifted operand (gy) is loaded once per pixel tile, the shifted one (x) once per tap.
+// ------------------------------------------------------------------------------------------------------
+struct WgParams {
+  int n, ho, wo;               // output-pixel domain (the reduction runs over it)
+  int kh, kw, dil, stride, pad;
+  int tw_log, th_log, tiles_x, tiles_y, total_tiles, tiles_per_cta;
+  int m_dim, n_dim;            // channel extents of the M-side / N-side operand
+  int m_boxes, n_boxes;        // 64-channel TMA boxes per operand tile
+  int bn;                      // UMMA N (multiple of 16)
+  int taps_per_group, tap_groups;
+  int x_is_m;                  // 1: M side = x (shifted per tap), N side = gy ; 0: M side = gy, N side = x
+  int stages_s, stages_u;      // ring depths: shifted (x) tiles, un-shifted (gy) tiles
+  int tmem_cols;
+  long long sm, sn, st;        // gw index = m*sm + n*sn + tap*st
+};
+
+constexpr int BOX_BYTES = 128 * 128;  // 128 pixels x 64 channels bf16
+
+__global__ void __launch_bounds__(TC_THREADS)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgParams p,
+                float* __restrict__ gw) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int s_boxes = p.x_is_m ? p.m_boxes : p.n_boxes;  // boxes per shifted (x) tile
+  const int u_boxes = p.x_is_m ? p.n_boxes : p.m_boxes;  // boxes per un-shifted (gy) tile
+  const uint32_t s_bytes = (uint32_t)s_boxes * BOX_BYTES, u_bytes = (uint32_t)u_boxes * BOX_BYTES;  // allocation
+  const uint32_t s_base = base;
+  const uint32_t u_base = base + (uint32_t)p.stages_s * s_bytes;
+  const uint32_t bar_base = u_base + (uint32_t)p.stages_u * u_bytes;
+  auto s_full = [&](int i) { return bar_base + 8u * (uint32_t)i; };
+  auto s_empty = [&](int i) { return bar_base + 8u * (uint32_t)(p.stages_s + i); };
+  auto u_full = [&](int i) { return bar_base + 8u * (uint32_t)(2 * p.stages_s + i); };
+  auto u_empty = [&](int i) { return bar_base + 8u * (uint32_t)(2 * p.stages_s + p.stages_u + i); };
+  const uint32_t tmem_full_bar = bar_base + 16u * (uint32_t)(p.stages_s + p.stages_u);
+  const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * 128;
+  const int grp = blockIdx.z % p.tap_groups;
+  const int n0 = (blockIdx.z / p.tap_groups) * p.bn;
+  const int taps = p.kh * p.kw;
+  const int tap0 = grp * p.taps_per_group;
+  int ntaps = taps - tap0;
+  if (ntaps > p.taps_per_group) ntaps = p.taps_per_group;
+  const int tile0 = blockIdx.x * p.tiles_per_cta;
+  int tile1 = tile0 + p.tiles_per_cta;
+  if (tile1 > p.total_tiles) tile1 = p.total_tiles;
+  const int tn_log = 7 - p.tw_log - p.th_log;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmG);
+    for (int i = 0; i < p.stages_s; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 1); }
+    for (int i = 0; i < p.stages_u; ++i) { mbar_init(u_full(i), 1); mbar_init(u_empty(i), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  const int x_ch0 = p.x_is_m ? m0 : n0;   // first channel of the x / gy slices this CTA reduces
+  const int g_ch0 = p.x_is_m ? n0 : m0;
+  // the M-side tile always owns two 64-channel boxes of smem (UMMA reads 128 rows) but only the boxes that hold
+  // real channels are loaded; accumulator rows beyond m_dim are never written out.
+  const int m_load = (p.m_dim - m0 > 64) ? 2 : 1;
+  const int s_load = p.x_is_m ? m_load : s_boxes;
+  const int u_load = p.x_is_m ? u_boxes : m_load;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ss = 0, us = 0;
+      uint32_t sph = 0, uph = 0;
+      for (int tile = tile0; tile < tile1; ++tile) {
+        const int tx = tile % p.tiles_x;
+        const int ty = (tile / p.tiles_x) % p.tiles_y;
+        const int tn = tile / (p.tiles_x * p.tiles_y);
+        const int ox0 = tx << p.tw_log, oy0 = ty << p.th_log, img0 = tn << tn_log;
+        mbar_wait(u_empty(us), uph ^ 1u);
+        mbar_expect_tx(u_full(us), (uint32_t)u_load * BOX_BYTES);
+        for (int b = 0; b < u_load; ++b)
+          tma_load_4d(u_base + (uint32_t)us * u_bytes + (uint32_t)b * BOX_BYTES, &tmG, u_full(us), g_ch0 + b * 64, ox0, oy0, img0);
+        if (++us == p.stages_u) { us = 0; uph ^= 1u; }
+        for (int t = 0; t < ntaps; ++t) {
+          const int tap = tap0 + t;
+          const int dy = tap / p.kw, dx = tap - dy * p.kw;
+          mbar_wait(s_empty(ss), sph ^ 1u);
+          mbar_expect_tx(s_full(ss), (uint32_t)s_load * BOX_BYTES);
+          for (int b = 0; b < s_load; ++b)
+            tma_load_4d(s_base + (uint32_t)ss * s_bytes + (uint32_t)b * BOX_BYTES, &tmX, s_full(ss), x_ch0 + b * 64,
+                        ox0 * p.stride - p.pad + dx * p.dil, oy0 * p.stride - p.pad + dy * p.dil, img0);
+          if (++ss == p.stages_s) { ss = 0; sph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(p.bn, true, true);
+    int ss = 0, us = 0;
+    uint32_t sph = 0, uph = 0;
+    for (int tile = tile0; tile < tile1; ++tile) {
+      mbar_wait(u_full(us), uph);
+      const uint32_t u_addr = u_base + (uint32_t)us * u_bytes;
+      for (int t = 0; t < ntaps; ++t) {
+        mbar_wait(s_full(ss), sph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t s_addr = s_base + (uint32_t)ss * s_bytes;
+          const uint32_t a_addr = p.x_is_m ? s_addr : u_addr;
+          const uint32_t b_addr = p.x_is_m ? u_addr : s_addr;
+          const uint32_t d_addr = tmem_base + (uint32_t)(t * p.bn);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {  // 8 x 16 pixels
+            const uint64_t ad = make_desc(a_addr + (uint32_t)k * 2048u, BOX_BYTES, 1024u);
+            const uint64_t bd = make_desc(b_addr + (uint32_t)k * 2048u, BOX_BYTES, 1024u);
+            umma_bf16(d_addr, ad, bd, idesc, (tile > tile0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(s_empty(ss));
+          if (t == ntaps - 1) {
+            umma_commit(u_empty(us));
+            if (tile == tile1 - 1) umma_commit(tmem_full_bar);
+          }
+        }
+        __syncwarp();
+        if (++ss == p.stages_s) { ss = 0; sph ^= 1u; }
+      }
+      if (++us == p.stages_u) { us = 0; uph ^= 1u; }
+    }
+  } else if (tile1 > tile0) {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    const bool m_ok = m < p.m_dim;
+    mbar_wait(tmem_full_bar, 0u);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int t = 0; t < ntaps; ++t) {
+      const long long tap_off = (long long)(tap0 + t) * p.st + (long long)m * p.sm;
+      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(t_row + (uint32_t)(t * p.bn + c0), r);
+        tmem_ld_wait();
+        if (!m_ok) continue;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int nn = n0 + c0 + j;
+          if (nn < p.n_dim) atomicAdd(gw + tap_off + (long long)nn * p.sn, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// per-channel sum over pixels (bias gradient): x [pixels, c] bf16 -> out[c] += sum
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long pixels, int c, long long px_per_cta) {
+  extern __shared__ float sm[];
+  const int cv = c >> 3;
+  const int lanes = 256 / cv;
+  const int tid = threadIdx.x;
+  const int lane = tid / cv, v = tid - lane * cv;
+  for (int i = tid; i < c; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  if (lane < lanes) {
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    const long long p0 = (long long)blockIdx.x * px_per_cta;
+    long long p1 = p0 + px_per_cta;
+    if (p1 > pixels) p1 = pixels;
+    for (long long px = p0 + lane; px < p1; px += lanes) {
+      float f[8];
+      Vec8<__nv_bfloat16>::load(x + px * c + v * 8, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sm[v * 8 + j], s[j]);
+  }
+  __syncthreads();
+  for (int i = tid; i < c; i += 256) atomicAdd(out + i, sm[i]);
+}
+
+int conv_tc_wgrad(const cgb_conv_desc* d, const void* x, const void* gy, float* gw, float* gbias, cudaStream_t st) {
+  WgParams p;
+  p.n = d->n; p.ho = d->ho; p.wo = d->wo;
+  p.kh = d->kh; p.kw = d->kw; p.dil = d->dil; p.stride = d->stride; p.pad = d->pad;
+  pick_tile(d->n, d->ho, d->wo, d->stride, &p.tw_log, &p.th_log);
+  const int tn_log = 7 - p.tw_log - p.th_log;
+  p.tiles_x = (d->wo + (1 << p.tw_log) - 1) >> p.tw_log;
+  p.tiles_y = (d->ho + (1 << p.th_log) - 1) >> p.th_log;
+  const int tiles_n = (d->n + (1 << tn_log) - 1) >> tn_log;
+  p.total_tiles = p.tiles_x * p.tiles_y * tiles_n;
+  const int taps = d->kh * d->kw;
+  p.x_is_m = d->ci >= d->co ? 1 : 0;
+  p.m_dim = p.x_is_m ? d->ci : d->co;
+  p.n_dim = p.x_is_m ? d->co : d->ci;
+  p.bn = pick_bn(p.n_dim);
+  p.m_boxes = 2;
+  p.n_boxes = (p.bn + 63) / 64;
+  if (p.x_is_m) { p.sm = 1; p.sn = (long long)taps * d->ci; } else { p.sm = (long long)taps * d->ci; p.sn = 1; }
+  p.st = d->ci;
+  int tpg = 512 / p.bn;
+  if (tpg > taps) tpg = taps;
+  p.tap_groups = (taps + tpg - 1) / tpg;
+  p.taps_per_group = (taps + p.tap_groups - 1) / p.tap_groups;
+  int cols = 32;
+  while (cols < p.taps_per_group * p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  const int s_boxes = p.x_is_m ? p.m_boxes : p.n_boxes;
+  const int u_boxes = p.x_is_m ? p.n_boxes : p.m_boxes;
+  p.stages_u = 2;
+  int budget = 200 * 1024 - p.stages_u * u_boxes * BOX_BYTES;
+  p.stages_s = budget / (s_boxes * BOX_BYTES);
+  if (p.stages_s > 6) p.stages_s = 6;
+  if (p.stages_s < 2) {
+    set_error("tcgen05 wgrad: tile does not fit shared memory (s_boxes=%d u_boxes=%d)", s_boxes, u_boxes);
+    return CGB_UNSUPPORTED;
+  }
+  const int m_tiles = (p.m_dim + 127) / 128;
+  const int n_tiles = (p.n_dim + p.bn - 1) / p.bn;
+  const int zdim = n_tiles * p.tap_groups;
+  // pixel splits: ~2 waves of CTAs over 148 SMs (1 CTA per SM: the accumulators own most of TMEM)
+  int splits = (148 * 2 + m_tiles * zdim - 1) / (m_tiles * zdim);
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_cta = (p.total_tiles + splits - 1) / splits;
+  splits = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+
+  CUtensorMap tmX, tmG;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->ci, (cuuint64_t)d->wi, (cuuint64_t)d->hi, (cuuint64_t)d->n};
+    cuuint64_t strides[3] = {(cuuint64_t)d->ci * 2, (cuuint64_t)d->wi * d->ci * 2, (cuuint64_t)d->hi * d->wi * d->ci * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)((1 << p.tw_log) * d->stride), (cuuint32_t)((1 << p.th_log) * d->stride),
+                         (cuuint32_t)(1 << tn_log)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    if (!encode_map(&tmX, x, 4, dims, strides, box, estr, "wgrad x")) return CGB_LAUNCH_FAILURE;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->co, (cuuint64_t)d->wo, (cuuint64_t)d->ho, (cuuint64_t)d->n};
+    cuuint64_t strides[3] = {(cuuint64_t)d->co * 2, (cuuint64_t)d->wo * d->co * 2, (cuuint64_t)d->ho * d->wo * d->co * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(1 << p.tw_log), (cuuint32_t)(1 << p.th_log), (cuuint32_t)(1 << tn_log)};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (!encode_map(&tmG, gy, 4, dims, strides, box, estr, "wgrad gy")) return CGB_LAUNCH_FAILURE;
+  }
+  const size_t smem = (size_t)p.stages_s * s_boxes * BOX_BYTES + (size_t)p.stages_u * u_boxes * BOX_BYTES +
+                      16 * (p.stages_s + p.stages_u) + 16 + 1024;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  dim3 grid((unsigned)splits, (unsigned)m_tiles, (unsigned)zdim);
+  wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmX, tmG, p, gw);
+  int s = after_launch("wgrad_tc");
+  if (s) return s;
+  if (gbias) {
+    const long long pixels = (long long)d->n * d->ho * d->wo;
+    int ctas = (int)((pixels + 1023) / 1024);
+    if (ctas > 148 * 4) ctas = 148 * 4;
+    if (ctas < 1) ctas = 1;
+    const long long ppc = (pixels + ctas - 1) / ctas;
+    colsum_kernel<<<ctas, 256, d->co * sizeof(float), st>>>((const __nv_bfloat16*)gy, gbias, pixels, d->co, ppc);
+    s = after_launch("colsum");
+  }
+  return s;
 }
 
 // wt[ci][taps-1-t][co] = w[co][t][ci]

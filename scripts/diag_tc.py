@@ -49,3 +49,14 @@ for idx, (n, ci, co, h, w, k, s, dil, pad) in enumerate(CASES):
         a, b = r2[_lib.ENGINE_SIMT], r2[_lib.ENGINE_TCGEN05]
         msg += f" dgrad relmax {float((a - b).abs().max() / a.abs().max()):.3e}"
     print(msg, flush=True)
+
+    if True:
+        gy = torch.randn_like(res[_lib.ENGINE_SIMT]).bfloat16()
+        r3 = {}
+        for eng in (_lib.ENGINE_SIMT, _lib.ENGINE_TCGEN05):
+            g = ops.ConvGeom(k, k, s, dil, pad, _lib.PAD_ZERO, _lib.ACT_NONE, 0.2, eng)
+            gw, gb = ops.conv_wgrad_raw(x, gy, g, True)
+            torch.cuda.synchronize()
+            r3[eng] = (gw, gb)
+        (a, ab), (b, bb) = r3[_lib.ENGINE_SIMT], r3[_lib.ENGINE_TCGEN05]
+        print(f"     wgrad relmax {float((a - b).abs().max() / a.abs().max()):.3e} bias relmax {float((ab - bb).abs().max() / ab.abs().max()):.3e}", flush=True)
