@@ -135,10 +135,12 @@ struct TcParams {
   int kh, kw, dil, stride, pad_y, pad_x;
   int tw_log, th_log;          // tile = TN x TH x TW pixels, product 128 (powers of two)
   int tiles_x, tiles_y;
+  int n_tiles, total_tiles;    // total = pixel tiles * n_tiles, n-tile fastest (A tile reuse through L2)
   int bn;                      // N tile (multiple of 16, <= 256)
   int kblocks;                 // ceil(cin_s / 64)
   int stages;
-  int tmem_cols;
+  int tmem_cols;               // >= 2*bn: two accumulator buffers
+  int stage_pitch;             // bytes per staging row = bn*2 + 16
   int act;
   float slope;
   int dact;                    // derivative mask (dgrad) from mask_src
@@ -147,6 +149,13 @@ struct TcParams {
 constexpr int TC_THREADS = 192;
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 64 bf16
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Persistent kernel: grid = min(#tiles, #SMs); CTA c processes tiles c, c+grid, ...
+// smem: [stages x (A 16 KB | B bn*128 B)] [staging 128 x (bn*2+16) B] [barriers]
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
                const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
@@ -156,27 +165,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t base = (raw + 1023u) & ~1023u;  // 1024-B alignment for the 128B swizzle atoms
   const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
   const uint32_t stage_bytes = A_TILE_BYTES + b_tile_bytes;
-  const uint32_t bar_base = base + (uint32_t)p.stages * stage_bytes;  // full[s], empty[s], tmem_full, tmem_ptr
+  const uint32_t staging = base + (uint32_t)p.stages * stage_bytes;
+  const uint32_t bar_base = staging + 128u * (uint32_t)p.stage_pitch;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(p.stages + s); };
-  const uint32_t tmem_full_bar = bar_base + 16u * (uint32_t)p.stages;
-  const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+  auto tfull_bar = [&](int b) { return bar_base + 16u * (uint32_t)p.stages + 8u * (uint32_t)b; };
+  auto tempty_bar = [&](int b) { return bar_base + 16u * (uint32_t)p.stages + 16u + 8u * (uint32_t)b; };
+  const uint32_t tmem_ptr_addr = bar_base + 16u * (uint32_t)p.stages + 32u;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+  uint8_t* staging_gen = smem_raw + (staging - raw);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // ---- tile coordinates
-  const int tile = blockIdx.x;
-  const int tx = tile % p.tiles_x;
-  const int ty = (tile / p.tiles_x) % p.tiles_y;
-  const int tn = tile / (p.tiles_x * p.tiles_y);
-  const int ox0 = tx << p.tw_log;
-  const int oy0 = ty << p.th_log;
-  const int n0 = tn << (7 - p.tw_log - p.th_log);
-  const int cn0 = blockIdx.y * p.bn;
   const int taps = p.kh * p.kw;
   const int iters = taps * p.kblocks;
+  const int tn_log = 7 - p.tw_log - p.th_log;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -185,12 +188,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 4);  // one arrive per epilogue warp
+    }
     fence_barrier_init();
   }
-  if (warp == 1) {
-    tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
-  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -201,17 +205,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tap = 0; tap < taps; ++tap) {
-        const int dy = tap / p.kw, dx = tap - dy * p.kw;
-        const int cx = ox0 * p.stride - p.pad_x + dx * p.dil;
-        const int cy = oy0 * p.stride - p.pad_y + dy * p.dil;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          const uint32_t a_dst = base + (uint32_t)s * stage_bytes;
-          mbar_expect_tx(full_bar(s), stage_bytes);
-          tma_load_4d(a_dst, &tmA, full_bar(s), kb * 64, cx, cy, n0);
-          tma_load_3d(a_dst + A_TILE_BYTES, &tmB, full_bar(s), kb * 64, tap, cn0);
-          if (++s == p.stages) { s = 0; ph ^= 1u; }
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        const int pt = tile / p.n_tiles;
+        const int tx = pt % p.tiles_x;
+        const int ty = (pt / p.tiles_x) % p.tiles_y;
+        const int tn = pt / (p.tiles_x * p.tiles_y);
+        const int ox0 = tx << p.tw_log, oy0 = ty << p.th_log, n0 = tn << tn_log;
+        const int cn0 = nt * p.bn;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int dy = tap / p.kw, dx = tap - dy * p.kw;
+          const int cx = ox0 * p.stride - p.pad_x + dx * p.dil;
+          const int cy = oy0 * p.stride - p.pad_y + dy * p.dil;
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            const uint32_t a_dst = base + (uint32_t)s * stage_bytes;
+            mbar_expect_tx(full_bar(s), stage_bytes);
+            tma_load_4d(a_dst, &tmA, full_bar(s), kb * 64, cx, cy, n0);
+            tma_load_3d(a_dst + A_TILE_BYTES, &tmB, full_bar(s), kb * 64, tap, cn0);
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
         }
       }
     }
@@ -220,75 +233,136 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t idesc = make_idesc(p.bn, false, false);
     int s = 0;
     uint32_t ph = 0;
-    for (int it = 0; it < iters; ++it) {
-      mbar_wait(full_bar(s), ph);
+    int lt = 0;  // local tile counter
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const uint32_t bph = (uint32_t)(lt >> 1) & 1u;
+      mbar_wait(tempty_bar(buf), bph ^ 1u);  // epilogue has drained this accumulator buffer
       tc_fence_after();
-      if (lane == 0) {
-        const int kb = it % p.kblocks;
-        int rem = p.cin_s - kb * 64;
-        if (rem > 64) rem = 64;
-        const int ksteps = (rem + 15) >> 4;
-        const uint32_t a_addr = base + (uint32_t)s * stage_bytes;
-        const uint32_t b_addr = a_addr + A_TILE_BYTES;
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t ad = make_desc(a_addr + (uint32_t)k * 32u, 16u, 1024u);
-          const uint64_t bd = make_desc(b_addr + (uint32_t)k * 32u, 16u, 1024u);
-          umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+      const uint32_t d_addr = tmem_base + (uint32_t)(buf * p.bn);
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const int kb = it % p.kblocks;
+          int rem = p.cin_s - kb * 64;
+          if (rem > 64) rem = 64;
+          const int ksteps = (rem + 15) >> 4;
+          const uint32_t a_addr = base + (uint32_t)s * stage_bytes;
+          const uint32_t b_addr = a_addr + A_TILE_BYTES;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t ad = make_desc(a_addr + (uint32_t)k * 32u, 16u, 1024u);
+            const uint64_t bd = make_desc(b_addr + (uint32_t)k * 32u, 16u, 1024u);
+            umma_bf16(d_addr, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));  // frees this smem stage once the MMAs above have read it
+          if (it == iters - 1) umma_commit(tfull_bar(buf));
         }
-        umma_commit(empty_bar(s));  // frees this smem stage once the MMAs above have read it
-        if (it == iters - 1) umma_commit(tmem_full_bar);
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
-      if (++s == p.stages) { s = 0; ph ^= 1u; }
     }
   } else {
     // ================= epilogue (warps 2..5) =================
     const int q = warp & 3;            // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;     // tile row == TMEM lane == pixel within the tile
+    const int et = threadIdx.x - 64;   // 0..127 within the epilogue group
     const int tw_i = row & ((1 << p.tw_log) - 1);
     const int th_i = (row >> p.tw_log) & ((1 << p.th_log) - 1);
     const int tn_i = row >> (p.tw_log + p.th_log);
-    const int ox = ox0 + tw_i, oy = oy0 + th_i, img = n0 + tn_i;
-    const bool pix_ok = (ox < p.wout) && (oy < p.hout) && (img < p.n);
-    const long long pix = ((long long)img * p.hout + oy) * p.wout + ox;
-    mbar_wait(tmem_full_bar, 0u);
-    tc_fence_after();
-    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int c0 = 0; c0 < p.bn; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(t_row + (uint32_t)c0, r);
-      tmem_ld_wait();
+    const int chunks_per_row = p.bn >> 3;  // 16-byte chunks per staged row
+    const bool fuse_mask_late = (mask_src != nullptr) && (p.dact == CGB_ACT_RELU);  // exact in bf16
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const uint32_t bph = (uint32_t)(lt >> 1) & 1u;
+      const int nt = tile % p.n_tiles;
+      const int pt = tile / p.n_tiles;
+      const int tx = pt % p.tiles_x;
+      const int ty = (pt / p.tiles_x) % p.tiles_y;
+      const int tn = pt / (p.tiles_x * p.tiles_y);
+      const int ox0 = tx << p.tw_log, oy0 = ty << p.th_log, n0 = tn << tn_log;
+      const int cn0 = nt * p.bn;
+      const int ox = ox0 + tw_i, oy = oy0 + th_i, img = n0 + tn_i;
+      const bool pix_ok = (ox < p.wout) && (oy < p.hout) && (img < p.n);
+      const long long pix = ((long long)img * p.hout + oy) * p.wout + ox;
+
+      mbar_wait(tfull_bar(buf), bph);
+      tc_fence_after();
+      epi_bar_sync();  // previous tile's copy-out has finished reading the staging buffer
+      // ---- phase 1: TMEM -> registers -> (bias, act, residual, mask) -> bf16 -> staging row
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.bn);
+      uint8_t* my_row = staging_gen + (size_t)row * p.stage_pitch;
+      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(t_row + (uint32_t)c0, r);
+        tmem_ld_wait();
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int ch = cn0 + c0 + h * 8;
-        if (!pix_ok || ch >= p.cout_s) continue;
-        float v[8];
+        for (int h = 0; h < 2; ++h) {
+          const int ch = cn0 + c0 + h * 8;
+          float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[h * 8 + j]);
-        if (bias) {
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + ch));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + ch + 4));
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[h * 8 + j]);
+          if (ch < p.cout_s) {
+            if (bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + ch));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + ch + 4));
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (p.act != CGB_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], p.act, p.slope);
+            }
+            if (pix_ok && residual) {
+              float rr[8];
+              Vec8<__nv_bfloat16>::load(residual + pix * p.cout_s + ch, rr);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += rr[j];
+            }
+            if (pix_ok && mask_src && !fuse_mask_late) {
+              float mm[8];
+              Vec8<__nv_bfloat16>::load(mask_src + pix * p.cout_s + ch, mm);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] *= act_grad_from_out(mm[j], p.dact, p.slope);
+            }
+          }
+          Vec8<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(my_row + (size_t)(c0 + h * 8) * 2), v);
         }
-        if (p.act != CGB_ACT_NONE) {
+      }
+      // accumulator buffer drained: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(buf));
+      epi_bar_sync();  // staging complete
+      // ---- phase 2: coalesced copy-out, 16 B per thread, consecutive threads -> consecutive chunks of a pixel
+      const int total_chunks = 128 * chunks_per_row;
+      for (int i = et; i < total_chunks; i += 128) {
+        const int r2 = i / chunks_per_row;
+        const int c = i - r2 * chunks_per_row;
+        const int ch = cn0 + c * 8;
+        if (ch >= p.cout_s) continue;
+        const int tw2 = r2 & ((1 << p.tw_log) - 1);
+        const int th2 = (r2 >> p.tw_log) & ((1 << p.th_log) - 1);
+        const int tn2 = r2 >> (p.tw_log + p.th_log);
+        const int ox2 = ox0 + tw2, oy2 = oy0 + th2, img2 = n0 + tn2;
+        if (ox2 >= p.wout || oy2 >= p.hout || img2 >= p.n) continue;
+        const long long off = (((long long)img2 * p.hout + oy2) * p.wout + ox2) * p.cout_s + ch;
+        uint4 val = *reinterpret_cast<const uint4*>(staging_gen + (size_t)r2 * p.stage_pitch + (size_t)c * 16);
+        if (fuse_mask_late) {
+          const uint4 mk = *reinterpret_cast<const uint4*>(mask_src + off);
+          const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mk);
+          __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&val);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], p.act, p.slope);
+          for (int j = 0; j < 4; ++j) {
+            const float2 mf = __bfloat1622float2(mh[j]);
+            float2 vf = __bfloat1622float2(vh[j]);
+            vf.x = mf.x > 0.f ? vf.x : 0.f;
+            vf.y = mf.y > 0.f ? vf.y : 0.f;
+            vh[j] = __floats2bfloat162_rn(vf.x, vf.y);
+          }
         }
-        const long long off = pix * p.cout_s + ch;
-        if (residual) {
-          float rr[8];
-          Vec8<__nv_bfloat16>::load(residual + off, rr);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += rr[j];
-        }
-        if (mask_src) {
-          float mm[8];
-          Vec8<__nv_bfloat16>::load(mask_src + off, mm);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] *= act_grad_from_out(mm[j], p.dact, p.slope);
-        }
-        Vec8<__nv_bfloat16>::store(y + off, v);
+        *reinterpret_cast<uint4*>(y + off) = val;
       }
     }
   }
@@ -340,10 +414,15 @@ static bool encode_map(CUtensorMap* tm, const void* ptr, int rank, const cuuint6
   return true;
 }
 
-static int ilog2(int v) {
-  int l = 0;
-  while ((1 << l) < v) ++l;
-  return l;
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
 }
 
 // choose TW x TH x TN = 128 (powers of two) minimising the number of tiles; ties -> wider TW
@@ -407,16 +486,16 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
   p.bn = pick_bn(cout_s);
   p.kblocks = (cin_s + 63) / 64;
   const int stage_bytes = A_TILE_BYTES + p.bn * 128;
-  int stages = (200 * 1024) / stage_bytes;
-  if (stages > 6) stages = 6;
-  const int iters = kh * kw * p.kblocks;
-  if (stages > iters) stages = iters;
-  if (stages < 1) stages = 1;
-  // keep >= 2 CTAs per SM resident when the tile is small (prologue/epilogue overlap between CTAs)
-  if (stage_bytes * stages > 100 * 1024 && stage_bytes * 4 <= 100 * 1024) stages = 4;
+  p.stage_pitch = p.bn * 2 + 16;
+  const int staging_bytes = 128 * p.stage_pitch;
+  int stages = (222 * 1024 - staging_bytes - 256) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
   p.stages = stages;
+  p.n_tiles = (cout_s + p.bn - 1) / p.bn;
+  p.total_tiles = p.tiles_x * p.tiles_y * tiles_n * p.n_tiles;
   int cols = 32;
-  while (cols < p.bn) cols <<= 1;
+  while (cols < 2 * p.bn) cols <<= 1;
   p.tmem_cols = cols;
   p.act = act; p.slope = slope; p.dact = dact;
 
@@ -436,12 +515,12 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
     cuuint32_t estr[3] = {1, 1, 1};
     if (!encode_map(&tmB, w, 3, dims, strides, box, estr, "weights")) return CGB_LAUNCH_FAILURE;
   }
-  const size_t smem = (size_t)stages * stage_bytes + 16 * stages + 16 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 16 * stages + 48 + 1024;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
     cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
-  dim3 grid((unsigned)(p.tiles_x * p.tiles_y * tiles_n), (unsigned)((cout_s + p.bn - 1) / p.bn));
+  dim3 grid((unsigned)(p.total_tiles < num_sms() ? p.total_tiles : num_sms()));
   conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p, bias, (const __nv_bfloat16*)residual,
                                                  (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out);
   return after_launch("conv_tc");
