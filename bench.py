@@ -328,7 +328,7 @@ def main():
         "step_frac_of_bf16_peak": step_tflops / (world * peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])),
         "top_kernels": [
             {"kernel": f"{r['op']}[{r['engine']}] {r['ci']}->{r['co']} k{r['k']} @{r['hi']}x{r['wi']}",
-             "count": r["count"], "total_ms": round(r["total_ms"], 3)} for r in rows[:8]],
+             "count": r["count"], "total_ms": round(r["total_ms"], 3)} for r in rows[:int(os.environ.get("CGB_TOPK", "8"))]],
     }
     print(json.dumps(line), flush=True)
     if world > 1:

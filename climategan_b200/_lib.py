@@ -89,6 +89,7 @@ SIGNATURES = {
     "cgb_instnorm_bwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P], C.c_int),
     "cgb_resize_nearest_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_upsample_nearest_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_im2col": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_nchw_to_nhwc": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_nhwc_to_nchw": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_act_bwd": ([_P, _P, _P, _I, _L, _I, _F, _P], C.c_int),

@@ -105,19 +105,24 @@ class SPADEResnetBlock(nn.Module):
         if self.learned_shortcut:
             self.norm_s = SPADE(spade_param_free_norm, spade_kernel_size, fin, cond_nc)
 
-    def forward(self, x, seg):
-        """x: storage [N,H,W,round8(fin)] ; seg: storage conditioning at the same H,W."""
+    def forward(self, x, seg, seg_col=None):
+        """x: storage [N,H,W,round8(fin)] ; seg: storage conditioning at the same H,W ; seg_col: its im2col
+        patches (ops.im2col), computed here when not supplied and shared by the block's 2-3 SPADE layers."""
+        if seg_col is None:
+            sh = self.norm_0.mlp_shared[0]
+            if sh.kernel_size[0] ** 2 * sh.in_channels <= 64:
+                seg_col = ops.im2col(seg, sh.in_channels, sh.kernel_size[0], sh.kernel_size[0] // 2)
         stats = ops.instnorm_stats(x)
         if self.learned_shortcut:
             # reference order (blocks.py:370,389): shortcut first -> conv_s's power iteration runs first
             w_s, _ = conv_weight_bias(self.conv_s)
-            x_s = ops.conv2d(self.norm_s(x, seg, stats, _lib.ACT_NONE), w_s, None)
+            x_s = ops.conv2d(self.norm_s(x, seg, stats, _lib.ACT_NONE, 0.2, seg_col), w_s, None)
         else:
             x_s = x
         w0, b0 = conv_weight_bias(self.conv_0)
-        dx = ops.conv2d(self.norm_0(x, seg, stats, _lib.ACT_LRELU, 0.2), w0, b0, pad=1)
+        dx = ops.conv2d(self.norm_0(x, seg, stats, _lib.ACT_LRELU, 0.2, seg_col), w0, b0, pad=1)
         w1, b1 = conv_weight_bias(self.conv_1)
-        out = ops.conv2d(self.norm_1(dx, seg, None, _lib.ACT_LRELU, 0.2), w1, b1, x_s, pad=1)
+        out = ops.conv2d(self.norm_1(dx, seg, None, _lib.ACT_LRELU, 0.2, seg_col), w1, b1, x_s, pad=1)
         if self.last_activation == "lrelu":
             out = ops.activation(out, _lib.ACT_LRELU, 0.2)
         return out

@@ -318,6 +318,41 @@ act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long count, int 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// im2col of a few-channel tensor (the 3-channel SPADE conditioning): y[n,oy,ox, tap*c + ch] = x[n,oy+dy*dil-pad,
+// ox+dx*dil-pad, ch], zero outside; lets SPADE.mlp_shared (norms.py:164-166) run as a K=32 1x1 GEMM on the
+// tensor cores instead of 9 mostly-empty 64-channel K blocks.  One thread per (pixel, 8 output channels).
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const T* __restrict__ x, T* __restrict__ y, long long total_vec, int h, int w, int cs_in, int c,
+              int k, int pad, int dil, int cs_out) {
+  const int ov = cs_out >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / ov;
+    const int v = (int)(i - pix * ov);
+    const int ox = (int)(pix % w);
+    const long long t = pix / w;
+    const int oy = (int)(t % h);
+    const long long img = t / h;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int oc = v * 8 + j;
+      const int tap = oc / c;
+      const int ch = oc - tap * c;
+      float val = 0.f;
+      if (tap < k * k) {
+        const int dy = tap / k, dx = tap - dy * k;
+        const int sy = oy + dy * dil - pad, sx = ox + dx * dil - pad;
+        if (sy >= 0 && sy < h && sx >= 0 && sx < w) val = to_f<T>(x[((img * h + sy) * w + sx) * cs_in + ch]);
+      }
+      o[j] = val;
+    }
+    Vec8<T>::store(y + pix * cs_out + v * 8, o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // compositing (generator.py:279-297)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -544,6 +579,19 @@ extern "C" int cgb_upsample_nearest_bwd(const void* gy, void* gx, int32_t dtype,
   DISPATCH_T(dtype, upsample_bwd_kernel<T><<<grid_for(total), 256, 0, st>>>((const T*)gy, (T*)gx, total, hi,
                                                                            wi, f, c);)
   return after_launch("upsample_bwd");
+}
+
+extern "C" int cgb_im2col(const void* x, void* y, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t cs_in,
+                          int32_t c, int32_t k, int32_t pad, int32_t dil, int32_t cs_out, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y, "im2col: null pointer");
+  CGB_REQUIRE(cs_in % 8 == 0 && cs_out % 8 == 0 && c >= 1 && c <= cs_in && k * k * c <= cs_out,
+              "im2col: bad channels cs_in=%d c=%d k=%d cs_out=%d", cs_in, c, k, cs_out);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)n * h * w * (cs_out / 8);
+  DISPATCH_T(dtype, im2col_kernel<T><<<grid_for(total), 256, 0, st>>>((const T*)x, (T*)y, total, h, w, cs_in, c, k,
+                                                                     pad, dil, cs_out);)
+  return after_launch("im2col");
 }
 
 extern "C" int cgb_nchw_to_nhwc(const float* x, void* y, int32_t dtype, int32_t n, int32_t c, int32_t hw,

@@ -93,10 +93,16 @@ class SPADE(nn.Module):
         self.mlp_gamma = nn.Conv2d(nhidden, norm_nc, kernel_size=kernel_size, padding=pw)
         self.mlp_beta = nn.Conv2d(nhidden, norm_nc, kernel_size=kernel_size, padding=pw)
 
-    def forward(self, x, segmap, stats=None, act=_lib.ACT_NONE, slope=0.2):
-        if segmap.shape[1:3] != x.shape[1:3]:
-            segmap = ops.resize_nearest(segmap, x.shape[1], x.shape[2])
-        mean, rstd = stats if stats is not None else ops.instnorm_stats(x, self.param_free_norm.eps)
+    def forward(self, x, segmap, stats=None, act=_lib.ACT_NONE, slope=0.2, seg_col=None):
+        """seg_col: optional im2col patches of segmap (ops.im2col) shared by all SPADE layers of a resolution."""
         sh = self.mlp_shared[0]
-        return ops.spade(x, mean, rstd, segmap, sh.weight, sh.bias, self.mlp_gamma.weight, self.mlp_gamma.bias,
-                         self.mlp_beta.weight, self.mlp_beta.bias, act, slope)
+        k = sh.kernel_size[0]
+        if seg_col is None:
+            if segmap.shape[1:3] != x.shape[1:3]:
+                segmap = ops.resize_nearest(segmap, x.shape[1], x.shape[2])
+            if k * k * sh.in_channels <= 64:
+                seg_col = ops.im2col(segmap, sh.in_channels, k, k // 2)
+        mean, rstd = stats if stats is not None else ops.instnorm_stats(x, self.param_free_norm.eps)
+        seg_in, is_col = (seg_col, True) if seg_col is not None else (segmap, False)
+        return ops.spade(x, mean, rstd, seg_in, sh.weight, sh.bias, self.mlp_gamma.weight, self.mlp_gamma.bias,
+                         self.mlp_beta.weight, self.mlp_beta.bias, act, slope, seg_is_col=is_col)

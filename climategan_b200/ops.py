@@ -144,6 +144,16 @@ def instnorm_stats(x: torch.Tensor, eps: float = 1e-5) -> Tuple[torch.Tensor, to
     return mean, rstd
 
 
+def im2col(x: torch.Tensor, c: int, k: int = 3, pad: int = 1, dil: int = 1) -> torch.Tensor:
+    """[N,H,W,Cs] storage tensor with c logical channels -> [N,H,W,round8(k*k*c)] patches (tap-major)."""
+    _chk_storage(x)
+    n, h, w, cs = x.shape
+    cs_out = round8(k * k * c)
+    y = torch.empty((n, h, w, cs_out), dtype=x.dtype, device=x.device)
+    check(_L().cgb_im2col(_p(x), _p(y), _DT[x.dtype], n, h, w, cs, c, k, pad, dil, cs_out, _st()), "im2col")
+    return y
+
+
 def act_bwd_raw(gy, y, act, slope):
     gx = torch.empty_like(gy)
     check(_L().cgb_act_bwd(_p(gy), _p(y), _p(gx), _DT[gy.dtype], gy.numel(), act, slope, _st()), "act_bwd")
@@ -203,15 +213,22 @@ class _Spade(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, mean, rstd, seg, w_sh, b_sh, w_g, b_g, w_b, b_b, act, slope, engine):
+    def forward(ctx, x, mean, rstd, seg, w_sh, b_sh, w_g, b_g, w_b, b_b, act, slope, engine, seg_is_col):
         dt = x.dtype
         n, h, w_, cs = x.shape
         c = w_g.shape[0]
         k = w_sh.shape[2]
         pad = k // 2
-        g_sh = ConvGeom(k, k, 1, 1, pad, _lib.PAD_ZERO, _lib.ACT_RELU, 0.0, engine)
         g_gb = ConvGeom(k, k, 1, 1, pad, _lib.PAD_ZERO, _lib.ACT_NONE, 0.0, engine)
-        wp_sh = pack_weight(w_sh, dt, cis=seg.shape[-1])
+        if seg_is_col:
+            # seg holds im2col patches [.., tap*cin + ch]: mlp_shared becomes a 1x1 conv with K = k*k*cin
+            g_sh = ConvGeom(1, 1, 1, 1, 0, _lib.PAD_ZERO, _lib.ACT_RELU, 0.0, engine)
+            o_sh, i_sh = w_sh.shape[0], w_sh.shape[1]
+            wp_sh = torch.zeros(round8(o_sh), 1, seg.shape[-1], dtype=dt, device=x.device)
+            wp_sh[:o_sh, 0, : k * k * i_sh] = w_sh.detach().permute(0, 2, 3, 1).reshape(o_sh, k * k * i_sh)
+        else:
+            g_sh = ConvGeom(k, k, 1, 1, pad, _lib.PAD_ZERO, _lib.ACT_RELU, 0.0, engine)
+            wp_sh = pack_weight(w_sh, dt, cis=seg.shape[-1])
         bp_sh = pad_bias(b_sh, wp_sh.shape[0])
         actv = conv_fwd_raw(seg, wp_sh, bp_sh, None, g_sh)
         nh = actv.shape[-1]
@@ -227,13 +244,13 @@ class _Spade(Function):
         check(_L().cgb_spade_modulate_fwd(_p(x), _p(mean), _p(rstd), _p(gb), _p(out), _DT[dt], n, h * w_, cs,
                                           act, slope, _st()), "spade_modulate_fwd")
         ctx.save_for_backward(x, mean, rstd, seg, actv, gb, wp_gb)
-        ctx.meta = (act, slope, g_sh, g_gb, tuple(w_sh.shape), tuple(w_g.shape), c, cs)
+        ctx.meta = (act, slope, g_sh, g_gb, tuple(w_sh.shape), tuple(w_g.shape), c, cs, seg_is_col)
         return out
 
     @staticmethod
     def backward(ctx, gout):
         x, mean, rstd, seg, actv, gb, wp_gb = ctx.saved_tensors
-        act, slope, g_sh, g_gb, sh_shape, g_shape, c, cs = ctx.meta
+        act, slope, g_sh, g_gb, sh_shape, g_shape, c, cs, seg_is_col = ctx.meta
         n, h, w_, _ = x.shape
         dt = x.dtype
         gout = gout.contiguous()
@@ -252,16 +269,22 @@ class _Spade(Function):
         gw_b = unpack_weight_grad(gwp_gb[cs:], g_shape)
         gb_g = gbp_gb[:c].clone()
         gb_b = gbp_gb[cs:cs + c].clone()
-        gw_sh = unpack_weight_grad(gwp_sh, sh_shape)
+        if seg_is_col:
+            o_sh, i_sh, kk, _ = sh_shape
+            gw_sh = gwp_sh[:o_sh, 0, : kk * kk * i_sh].reshape(o_sh, kk, kk, i_sh).permute(0, 3, 1, 2).contiguous()
+        else:
+            gw_sh = unpack_weight_grad(gwp_sh, sh_shape)
         gb_sh = gbp_sh[: sh_shape[0]].clone()
         if not ctx.needs_input_grad[0]:
             gx = None
-        return gx, None, None, None, gw_sh, gb_sh, gw_g, gb_g, gw_b, gb_b, None, None, None
+        return gx, None, None, None, gw_sh, gb_sh, gw_g, gb_g, gw_b, gb_b, None, None, None, None
 
 
 def spade(x, mean, rstd, seg, w_sh, b_sh, w_g, b_g, w_b, b_b, act=_lib.ACT_NONE, slope=0.2,
-          engine=_lib.ENGINE_AUTO):
-    return _Spade.apply(x, mean, rstd, seg, w_sh, b_sh, w_g, b_g, w_b, b_b, act, slope, engine)
+          engine=_lib.ENGINE_AUTO, seg_is_col=False):
+    """seg: conditioning storage tensor at x's resolution, or (seg_is_col) its im2col patches from
+    :func:`im2col` — then SPADE.mlp_shared runs as one K=round8(9*cond_nc) GEMM."""
+    return _Spade.apply(x, mean, rstd, seg, w_sh, b_sh, w_g, b_g, w_b, b_b, act, slope, engine, seg_is_col)
 
 
 class _ResizeNearest(Function):

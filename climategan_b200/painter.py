@@ -79,8 +79,14 @@ class PainterSpadeDecoder(nn.Module):
                 segs[(h, w)] = cond_st if (h, w) == tuple(cond_st.shape[1:3]) else ops.resize_nearest(cond_st, h, w)
             return segs[(h, w)]
 
+        cols = {}
+
         def run(blk, y):
-            return blk(y, seg_at(y.shape[1], y.shape[2]))
+            hw = (y.shape[1], y.shape[2])
+            seg = seg_at(*hw)
+            if hw not in cols:  # im2col patches of the conditioning: once per resolution, shared by all SPADEs
+                cols[hw] = ops.im2col(seg, 3, 3, 1)
+            return blk(y, seg, cols[hw])
 
         z = ops.conv2d(seg_at(self.z_h, self.z_w), self.fc.weight, self.fc.bias, pad=1)
         y = run(self.head_0, z)

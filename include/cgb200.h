@@ -150,6 +150,12 @@ int cgb_resize_nearest_fwd(const void* x, void* y, int32_t dtype, int32_t n, int
 int cgb_upsample_nearest_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi, int32_t wi,
                              int32_t f, int32_t c, void* stream);
 
+/* im2col of a few-channel NHWC tensor: y[n,oy,ox, tap*c + ch] = x[n, oy+dy*dil-pad, ox+dx*dil-pad, ch] (zero outside,
+ * zero for channels >= k*k*c).  Turns the 3-channel SPADE.mlp_shared 3x3 conv (norms.py:164-166) into a K=32 1x1
+ * GEMM for the tensor cores; computed once per resolution and shared by every SPADE layer at that resolution. */
+int cgb_im2col(const void* x, void* y, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t cs_in, int32_t c,
+               int32_t k, int32_t pad, int32_t dil, int32_t cs_out, void* stream);
+
 /* ---- layout / elementwise ----------------------------------------------------------------
  * NCHW fp32 (the reference's tensor layout at the API edge) <-> NHWC storage. */
 int cgb_nchw_to_nhwc(const float* x, void* y, int32_t dtype, int32_t n, int32_t c, int32_t hw,

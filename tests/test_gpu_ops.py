@@ -113,7 +113,8 @@ def test_instnorm_stats(cuda, c, h, w, dtype):
 @pytest.mark.parametrize("c,h,w", [(20, 12, 12), (40, 6, 10), (128, 4, 4)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("act", [_lib.ACT_NONE, _lib.ACT_LRELU])
-def test_spade_layer(cuda, c, h, w, dtype, act):
+@pytest.mark.parametrize("col", [False, True])
+def test_spade_layer(cuda, c, h, w, dtype, act, col):
     """One whole SPADE layer (norms.py:174-186) + lrelu, forward and every gradient."""
     from oracle import painter_oracle as po
 
@@ -139,9 +140,12 @@ def test_spade_layer(cuda, c, h, w, dtype, act):
     xs = _st(x, dtype, cuda).requires_grad_(True)
     segs = _st(seg, dtype, cuda)
     mean, rstd = ops.instnorm_stats(xs)
+    if col:  # mlp_shared as one K=32 GEMM over im2col patches of the conditioning
+        segs = ops.im2col(segs, 3, 3, 1)
+        assert segs.shape[-1] == 32
     out = ops.spade(xs, mean, rstd, segs, sdg["p.mlp_shared.0.weight"], sdg["p.mlp_shared.0.bias"],
                     sdg["p.mlp_gamma.weight"], sdg["p.mlp_gamma.bias"], sdg["p.mlp_beta.weight"],
-                    sdg["p.mlp_beta.bias"], act, 0.2)
+                    sdg["p.mlp_beta.bias"], act, 0.2, seg_is_col=col)
     o = ops.from_storage(out, c)
     # Stated tolerances.  fp32 storage: 5e-5 of full scale everywhere.  bf16 storage: forward 1e-2 of full
     # scale; gradients are compared by cosine / relative L2 because a leaky-relu whose pre-activation flips
