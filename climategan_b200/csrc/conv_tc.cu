@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <mutex>
+#include <string.h>
 
 namespace cgb {
 
@@ -88,6 +89,44 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// elect.sync: one lane of a converged warp.  ptxas knows the guarded region is single-threaded, keeps the MMA
+// operands in uniform registers and emits back-to-back UTCHMMA (measured: 44 cycles per M=128,N=48,K=16 MMA = the
+// shared-memory operand-read bound (4096+32N)/128, vs 73 with a lane==0 predicate and ~130 with a lane==0 branch).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Warp-uniform issue: every lane of the MMA warp computes the (uniform) descriptors, one lane (`elected`) issues.
+// Keeping the operands provably warp-uniform lets ptxas hold them in uniform registers; branching on lane==0 around
+// the address arithmetic instead makes it emit a VOTEU/BRA.U.ANY uniformisation loop per MMA (~130 cycles each).
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t elected) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "setp.ne.b32 q, %5, 0;\n"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar, uint32_t elected) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "setp.ne.b32 q, %1, 0;\n"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(bar), "r"(elected)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -114,6 +153,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
+// split form for tight issue loops: hi word is loop-invariant, lo word = start-address field (+LBO), so stepping the
+// operand is one 32-bit add (no carry out of the 14-bit address field: smem < 256 KB)
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
+
 // instruction descriptor: bf16 x bf16 -> fp32, M=128
 __host__ __device__ inline uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
   uint32_t d = 0;
@@ -135,27 +184,151 @@ struct TcParams {
   int kh, kw, dil, stride, pad_y, pad_x;
   int tw_log, th_log;          // tile = TN x TH x TW pixels, product 128 (powers of two)
   int tiles_x, tiles_y;
-  int n_tiles, total_tiles;    // total = pixel tiles * n_tiles, n-tile fastest (A tile reuse through L2)
+  int n_tiles, total_tiles;    // streaming kernel: total = pixel tiles * n_tiles, n-tile fastest
+  int pix_tiles;               // weight-stationary kernel: pixel tiles (each CTA keeps one n-tile)
   int bn;                      // N tile (multiple of 16, <= 256)
   int kblocks;                 // ceil(cin_s / 64)
   int stages;
   int tmem_cols;               // >= 2*bn: two accumulator buffers
   int stage_pitch;             // bytes per staging row = bn*2 + 16
+  int twh, thh;                // weight-stationary kernel: halo tile extent (pixels)
+  int a_stage_bytes;           // weight-stationary kernel: bytes per halo stage (1024-aligned)
   int act;
   float slope;
   int dact;                    // derivative mask (dgrad) from mask_src
 };
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
+constexpr int EPI_THREADS = 256;
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 64 bf16
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// Persistent kernel: grid = min(#tiles, #SMs); CTA c processes tiles c, c+grid, ...
+// ---- epilogue of one 128-pixel x bn tile, executed by the 8 epilogue warps --------------------------------
+// phase 1: TMEM -> registers (two tcgen05.ld in flight) -> bias / activation / residual / mask -> bf16 -> staging row
+// phase 2: coalesced 16-byte copy-out (consecutive threads write consecutive chunks of a pixel's channel vector)
+__device__ __forceinline__ void epi_chunk(const TcParams& p, const uint32_t (&r)[16], int c, int cn0, bool pix_ok,
+                                          long long pix, float neg, bool mask_early, const float* __restrict__ bias,
+                                          const __nv_bfloat16* __restrict__ residual,
+                                          const __nv_bfloat16* __restrict__ mask_src, uint8_t* my_row) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int ch = cn0 + c * 16 + h * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[h * 8 + j]);
+    if (ch < p.cout_s) {
+      if (bias) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + ch));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + ch + 4));
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if (p.act <= CGB_ACT_LRELU) {  // none / relu / lrelu: branch-free select
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * neg;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], p.act, p.slope);
+      }
+      if (pix_ok && residual) {
+        float rr[8];
+        Vec8<__nv_bfloat16>::load(residual + pix * p.cout_s + ch, rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += rr[j];
+      }
+      if (pix_ok && mask_early) {
+        float mm[8];
+        Vec8<__nv_bfloat16>::load(mask_src + pix * p.cout_s + ch, mm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= act_grad_from_out(mm[j], p.dact, p.slope);
+      }
+    }
+    Vec8<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(my_row + (size_t)(c * 16 + h * 8) * 2), v);
+  }
+}
+
+__device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_acc, uint8_t* staging_gen, int ox0, int oy0,
+                                              int n0, int cn0, const float* __restrict__ bias,
+                                              const __nv_bfloat16* __restrict__ residual,
+                                              const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y,
+                                              uint32_t tempty_bar, int warp, int lane) {
+  const int q = warp & 3;              // TMEM lane quarter this warp may access
+  const int half = (warp - 2) >> 2;    // two warps share a quarter: even / odd 16-column chunks
+  const int row = q * 32 + lane;       // tile row == TMEM lane == pixel within the tile
+  const int et = threadIdx.x - 64;     // 0..255 within the epilogue group
+  const int tw_i = row & ((1 << p.tw_log) - 1);
+  const int th_i = (row >> p.tw_log) & ((1 << p.th_log) - 1);
+  const int tn_i = row >> (p.tw_log + p.th_log);
+  const int ox = ox0 + tw_i, oy = oy0 + th_i, img = n0 + tn_i;
+  const bool pix_ok = (ox < p.wout) && (oy < p.hout) && (img < p.n);
+  const long long pix = ((long long)img * p.hout + oy) * p.wout + ox;
+  const bool mask_late = (mask_src != nullptr) && (p.dact == CGB_ACT_RELU);  // 0/1 mask: exact on bf16
+  const bool mask_early = (mask_src != nullptr) && !mask_late;
+  const float neg = p.act == CGB_ACT_NONE ? 1.f : (p.act == CGB_ACT_RELU ? 0.f : p.slope);
+
+  epi_bar_sync();  // previous tile's copy-out has finished reading the staging buffer
+  const uint32_t t_row = tmem_acc + ((uint32_t)(q * 32) << 16);
+  uint8_t* my_row = staging_gen + (size_t)row * p.stage_pitch;
+  const int nchunks = p.bn >> 4;
+  for (int c = half; c < nchunks; c += 4) {
+    uint32_t ra[16], rb[16];
+    const bool two = (c + 2) < nchunks;
+    tmem_ld16(t_row + (uint32_t)(c * 16), ra);
+    if (two) tmem_ld16(t_row + (uint32_t)((c + 2) * 16), rb);
+    tmem_ld_wait();
+    epi_chunk(p, ra, c, cn0, pix_ok, pix, neg, mask_early, bias, residual, mask_src, my_row);
+    if (two) epi_chunk(p, rb, c + 2, cn0, pix_ok, pix, neg, mask_early, bias, residual, mask_src, my_row);
+  }
+  // accumulator buffer drained: hand it back to the MMA warp
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(tempty_bar);
+  epi_bar_sync();  // staging complete
+  // phase 2: lanes cover (rows_per_iter x chunks_per_row) 16-byte chunks; the row/chunk split of a lane is fixed, so
+  // the only per-iteration work is the pixel address.  Consecutive lanes write consecutive chunks of a pixel and then
+  // the next pixel: full 32-byte sectors, no read-modify-write.
+  const int chunks_per_row = p.bn >> 3;                 // <= 32
+  const int rows_per_iter = 32 / chunks_per_row;        // >= 1
+  const int rsub = lane / chunks_per_row;
+  const int c = lane - rsub * chunks_per_row;
+  const int ch = cn0 + c * 8;
+  if (rsub < rows_per_iter && ch < p.cout_s) {
+    const int ew = warp - 2;  // 0..7
+    for (int r2 = ew * rows_per_iter + rsub; r2 < 128; r2 += 8 * rows_per_iter) {
+      const int tw2 = r2 & ((1 << p.tw_log) - 1);
+      const int th2 = (r2 >> p.tw_log) & ((1 << p.th_log) - 1);
+      const int tn2 = r2 >> (p.tw_log + p.th_log);
+      const int ox2 = ox0 + tw2, oy2 = oy0 + th2, img2 = n0 + tn2;
+      if (ox2 >= p.wout || oy2 >= p.hout || img2 >= p.n) continue;
+      const long long off = (((long long)img2 * p.hout + oy2) * p.wout + ox2) * p.cout_s + ch;
+      uint4 val = *reinterpret_cast<const uint4*>(staging_gen + (size_t)r2 * p.stage_pitch + (size_t)c * 16);
+      if (mask_late) {
+        const uint4 mk = *reinterpret_cast<const uint4*>(mask_src + off);
+        const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mk);
+        __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 mf = __bfloat1622float2(mh[j]);
+          float2 vf = __bfloat1622float2(vh[j]);
+          vf.x = mf.x > 0.f ? vf.x : 0.f;
+          vf.y = mf.y > 0.f ? vf.y : 0.f;
+          vh[j] = __floats2bfloat162_rn(vf.x, vf.y);
+        }
+      }
+      *reinterpret_cast<uint4*>(y + off) = val;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Streaming kernel (any geometry): per (tap, 64-channel block) one A box + one B box through a smem ring.
+// Persistent: grid = min(#tiles, #SMs); CTA c processes tiles c, c+grid, ...
 // smem: [stages x (A 16 KB | B bn*128 B)] [staging 128 x (bn*2+16) B] [barriers]
+// ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
                const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
@@ -190,7 +363,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(b), 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -202,7 +375,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -231,6 +404,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ================= MMA issuer =================
     const uint32_t idesc = make_idesc(p.bn, false, false);
+    const uint32_t hi1024 = desc_hi(1024u);
+    const int ksteps_last = ((p.cin_s - (p.kblocks - 1) * 64) + 15) >> 4;
     int s = 0;
     uint32_t ph = 0;
     int lt = 0;  // local tile counter
@@ -240,38 +415,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tempty_bar(buf), bph ^ 1u);  // epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t d_addr = tmem_base + (uint32_t)(buf * p.bn);
+      int kb = 0;
       for (int it = 0; it < iters; ++it) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
-        if (lane == 0) {
-          const int kb = it % p.kblocks;
-          int rem = p.cin_s - kb * 64;
-          if (rem > 64) rem = 64;
-          const int ksteps = (rem + 15) >> 4;
+        if (elect_one_sync()) {
+          const int ksteps = (kb == p.kblocks - 1) ? ksteps_last : 4;
           const uint32_t a_addr = base + (uint32_t)s * stage_bytes;
-          const uint32_t b_addr = a_addr + A_TILE_BYTES;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t ad = make_desc(a_addr + (uint32_t)k * 32u, 16u, 1024u);
-            const uint64_t bd = make_desc(b_addr + (uint32_t)k * 32u, 16u, 1024u);
-            umma_bf16(d_addr, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          const uint32_t a_lo = desc_lo(a_addr, 16u), b_lo = desc_lo(a_addr + A_TILE_BYTES, 16u);
+          uint32_t acc = it > 0 ? 1u : 0u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k < ksteps) {
+              umma_bf16(d_addr, desc_join(a_lo + 2u * k, hi1024), desc_join(b_lo + 2u * k, hi1024), idesc, acc);
+              acc = 1u;
+            }
           }
           umma_commit(empty_bar(s));  // frees this smem stage once the MMAs above have read it
           if (it == iters - 1) umma_commit(tfull_bar(buf));
         }
         __syncwarp();
+        if (++kb == p.kblocks) kb = 0;
         if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
-    const int q = warp & 3;            // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;     // tile row == TMEM lane == pixel within the tile
-    const int et = threadIdx.x - 64;   // 0..127 within the epilogue group
-    const int tw_i = row & ((1 << p.tw_log) - 1);
-    const int th_i = (row >> p.tw_log) & ((1 << p.th_log) - 1);
-    const int tn_i = row >> (p.tw_log + p.th_log);
-    const int chunks_per_row = p.bn >> 3;  // 16-byte chunks per staged row
-    const bool fuse_mask_late = (mask_src != nullptr) && (p.dact == CGB_ACT_RELU);  // exact in bf16
+    // ================= epilogue (warps 2..9) =================
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -281,89 +450,160 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tx = pt % p.tiles_x;
       const int ty = (pt / p.tiles_x) % p.tiles_y;
       const int tn = pt / (p.tiles_x * p.tiles_y);
-      const int ox0 = tx << p.tw_log, oy0 = ty << p.th_log, n0 = tn << tn_log;
-      const int cn0 = nt * p.bn;
-      const int ox = ox0 + tw_i, oy = oy0 + th_i, img = n0 + tn_i;
-      const bool pix_ok = (ox < p.wout) && (oy < p.hout) && (img < p.n);
-      const long long pix = ((long long)img * p.hout + oy) * p.wout + ox;
-
       mbar_wait(tfull_bar(buf), bph);
       tc_fence_after();
-      epi_bar_sync();  // previous tile's copy-out has finished reading the staging buffer
-      // ---- phase 1: TMEM -> registers -> (bias, act, residual, mask) -> bf16 -> staging row
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.bn);
-      uint8_t* my_row = staging_gen + (size_t)row * p.stage_pitch;
-      for (int c0 = 0; c0 < p.bn; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(t_row + (uint32_t)c0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int ch = cn0 + c0 + h * 8;
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[h * 8 + j]);
-          if (ch < p.cout_s) {
-            if (bias) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + ch));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + ch + 4));
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (p.act != CGB_ACT_NONE) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], p.act, p.slope);
-            }
-            if (pix_ok && residual) {
-              float rr[8];
-              Vec8<__nv_bfloat16>::load(residual + pix * p.cout_s + ch, rr);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] += rr[j];
-            }
-            if (pix_ok && mask_src && !fuse_mask_late) {
-              float mm[8];
-              Vec8<__nv_bfloat16>::load(mask_src + pix * p.cout_s + ch, mm);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] *= act_grad_from_out(mm[j], p.dact, p.slope);
-            }
-          }
-          Vec8<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(my_row + (size_t)(c0 + h * 8) * 2), v);
+      epilogue_tile(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen, tx << p.tw_log, ty << p.th_log, tn << tn_log,
+                    nt * p.bn, bias, residual, mask_src, y, tempty_bar(buf), warp, lane);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Weight-stationary halo kernel (stride-1 k x k convs on large maps — the SPADE gamma/beta convs and their dgrad).
+// L2->SM bandwidth (~6.6 TB/s, about the HBM rate on this part) is what bounds the streaming kernel: it re-reads
+// the activation tile once per filter tap and the weights once per pixel tile.  Here
+//   * the CTA's weight slice [kblocks][taps][bn][64] is loaded ONCE into shared memory and stays resident,
+//   * per 64-channel block ONE halo box (TH+dil*(kh-1)) x (TW+dil*(kw-1)) pixels is loaded, and every filter tap is
+//     an UMMA descriptor into that same box: start address shifted by (dy*dil*TWh + dx*dil) rows of 128 B, 8-row
+//     group stride SBO = TWh*128 B (the 128B swizzle is a function of the smem address, so row-shifted starts
+//     read correctly — verified on hardware, scripts/exp/shift_desc.cu).
+// Tile = 16 rows x 8 pixels (each 8-row swizzle group is one image-row segment).
+// smem: [weights] [stages x halo tile] [staging] [barriers].  grid is a multiple of n_tiles; CTA c keeps n-tile c % n_tiles.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
+                  const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
+                  const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int taps = p.kh * p.kw;
+  const uint32_t w_tap_bytes = (uint32_t)p.bn * 128u;
+  const uint32_t w_bytes = (uint32_t)(p.kblocks * taps) * w_tap_bytes;
+  const uint32_t a_base = base + w_bytes;
+  const uint32_t staging = a_base + (uint32_t)p.stages * (uint32_t)p.a_stage_bytes;
+  const uint32_t bar_base = staging + 128u * (uint32_t)p.stage_pitch;
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(p.stages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 16u * (uint32_t)p.stages + 8u * (uint32_t)b; };
+  auto tempty_bar = [&](int b) { return bar_base + 16u * (uint32_t)p.stages + 16u + 8u * (uint32_t)b; };
+  const uint32_t w_bar = bar_base + 16u * (uint32_t)p.stages + 32u;
+  const uint32_t tmem_ptr_addr = w_bar + 8u;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+  uint8_t* staging_gen = smem_raw + (staging - raw);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nt = blockIdx.x % p.n_tiles;
+  const int cn0 = nt * p.bn;
+  const int pt0 = blockIdx.x / p.n_tiles;
+  const int pt_step = gridDim.x / p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 8);
+    }
+    mbar_init(w_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      // resident weights: kblocks*taps boxes of {64 ch, 1 tap, bn rows}
+      mbar_expect_tx(w_bar, w_bytes);
+      for (int kb = 0; kb < p.kblocks; ++kb)
+        for (int tap = 0; tap < taps; ++tap)
+          tma_load_3d(base + (uint32_t)(kb * taps + tap) * w_tap_bytes, &tmB, w_bar, kb * 64, tap, cn0);
+      const uint32_t halo_bytes = (uint32_t)(p.twh * p.thh) * 128u;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int pt = pt0; pt < p.pix_tiles; pt += pt_step) {
+        const int tx = pt % p.tiles_x;
+        const int ty = (pt / p.tiles_x) % p.tiles_y;
+        const int img = pt / (p.tiles_x * p.tiles_y);
+        const int cx = (tx << 3) - p.pad_x, cy = (ty << 4) - p.pad_y;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), halo_bytes);
+          tma_load_4d(a_base + (uint32_t)s * (uint32_t)p.a_stage_bytes, &tmA, full_bar(s), kb * 64, cx, cy, img);
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
-      // accumulator buffer drained: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(buf));
-      epi_bar_sync();  // staging complete
-      // ---- phase 2: coalesced copy-out, 16 B per thread, consecutive threads -> consecutive chunks of a pixel
-      const int total_chunks = 128 * chunks_per_row;
-      for (int i = et; i < total_chunks; i += 128) {
-        const int r2 = i / chunks_per_row;
-        const int c = i - r2 * chunks_per_row;
-        const int ch = cn0 + c * 8;
-        if (ch >= p.cout_s) continue;
-        const int tw2 = r2 & ((1 << p.tw_log) - 1);
-        const int th2 = (r2 >> p.tw_log) & ((1 << p.th_log) - 1);
-        const int tn2 = r2 >> (p.tw_log + p.th_log);
-        const int ox2 = ox0 + tw2, oy2 = oy0 + th2, img2 = n0 + tn2;
-        if (ox2 >= p.wout || oy2 >= p.hout || img2 >= p.n) continue;
-        const long long off = (((long long)img2 * p.hout + oy2) * p.wout + ox2) * p.cout_s + ch;
-        uint4 val = *reinterpret_cast<const uint4*>(staging_gen + (size_t)r2 * p.stage_pitch + (size_t)c * 16);
-        if (fuse_mask_late) {
-          const uint4 mk = *reinterpret_cast<const uint4*>(mask_src + off);
-          const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mk);
-          __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&val);
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(p.bn, false, false);
+    const uint32_t hi_a = desc_hi((uint32_t)p.twh * 128u), hi_b = desc_hi(1024u);
+    const int ksteps_last = ((p.cin_s - (p.kblocks - 1) * 64) + 15) >> 4;
+    mbar_wait(w_bar, 0u);
+    int s = 0;
+    uint32_t ph = 0;
+    int lt = 0;
+    for (int pt = pt0; pt < p.pix_tiles; pt += pt_step, ++lt) {
+      const int buf = lt & 1;
+      const uint32_t bph = (uint32_t)(lt >> 1) & 1u;
+      mbar_wait(tempty_bar(buf), bph ^ 1u);
+      tc_fence_after();
+      const uint32_t d_addr = tmem_base + (uint32_t)(buf * p.bn);
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const int ksteps = (kb == p.kblocks - 1) ? ksteps_last : 4;
+          const uint32_t a_lo0 = desc_lo(a_base + (uint32_t)s * (uint32_t)p.a_stage_bytes, 16u);
+          uint32_t b_lo = desc_lo(base + (uint32_t)(kb * taps) * w_tap_bytes, 16u);
+          uint32_t acc = kb > 0 ? 1u : 0u;
+          for (int dy = 0; dy < p.kh; ++dy) {
+            uint32_t a_lo = a_lo0 + (uint32_t)(dy * p.dil * p.twh) * 8u;
+            for (int dx = 0; dx < p.kw; ++dx) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 mf = __bfloat1622float2(mh[j]);
-            float2 vf = __bfloat1622float2(vh[j]);
-            vf.x = mf.x > 0.f ? vf.x : 0.f;
-            vf.y = mf.y > 0.f ? vf.y : 0.f;
-            vh[j] = __floats2bfloat162_rn(vf.x, vf.y);
+              for (int k = 0; k < 4; ++k) {
+                if (k < ksteps) {
+                  umma_bf16(d_addr, desc_join(a_lo + 2u * k, hi_a), desc_join(b_lo + 2u * k, hi_b), idesc, acc);
+                  acc = 1u;
+                }
+              }
+              a_lo += (uint32_t)p.dil * 8u;
+              b_lo += w_tap_bytes >> 4;
+            }
           }
+          umma_commit(empty_bar(s));
+          if (kb == p.kblocks - 1) umma_commit(tfull_bar(buf));
         }
-        *reinterpret_cast<uint4*>(y + off) = val;
+        __syncwarp();
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
+    }
+  } else {
+    int lt = 0;
+    for (int pt = pt0; pt < p.pix_tiles; pt += pt_step, ++lt) {
+      const int buf = lt & 1;
+      const uint32_t bph = (uint32_t)(lt >> 1) & 1u;
+      const int tx = pt % p.tiles_x;
+      const int ty = (pt / p.tiles_x) % p.tiles_y;
+      const int img = pt / (p.tiles_x * p.tiles_y);
+      mbar_wait(tfull_bar(buf), bph);
+      tc_fence_after();
+      epilogue_tile(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen, tx << 3, ty << 4, img, cn0, bias, residual,
+                    mask_src, y, tempty_bar(buf), warp, lane);
     }
   }
 
@@ -471,55 +711,109 @@ bool conv_tc_supported(const cgb_conv_desc* d, int which) {
   return d->stride <= 2 && d->co <= 2048;  // wgrad
 }
 
-// Launch the fprop kernel on (in -> out).  in: [n,hin,win,cin_s], w: [cout_s][taps][cin_s], out: [n,hout,wout,cout_s]
+// Launch an fprop on (in -> out).  in: [n,hin,win,cin_s], w: [cout_s][taps][cin_s], out: [n,hout,wout,cout_s]
+static const size_t SMEM_LIMIT = 227 * 1024;
+
 static int launch_fprop(const void* in, const void* w, void* out, int n, int hin, int win, int cin_s, int hout, int wout,
                         int cout_s, int kh, int kw, int stride, int dil, int pad_y, int pad_x, int act, float slope,
                         const float* bias, const void* residual, int dact, const void* mask_src, cudaStream_t st) {
   TcParams p;
+  memset(&p, 0, sizeof(p));
   p.n = n; p.hout = hout; p.wout = wout; p.cout_s = cout_s; p.cin_s = cin_s;
   p.kh = kh; p.kw = kw; p.dil = dil; p.stride = stride; p.pad_y = pad_y; p.pad_x = pad_x;
-  pick_tile(n, hout, wout, stride, &p.tw_log, &p.th_log);
-  const int tn_log = 7 - p.tw_log - p.th_log;
-  p.tiles_x = (wout + (1 << p.tw_log) - 1) >> p.tw_log;
-  p.tiles_y = (hout + (1 << p.th_log) - 1) >> p.th_log;
-  const int tiles_n = (n + (1 << tn_log) - 1) >> tn_log;
-  p.bn = pick_bn(cout_s);
   p.kblocks = (cin_s + 63) / 64;
-  const int stage_bytes = A_TILE_BYTES + p.bn * 128;
+  p.act = act; p.slope = slope; p.dact = dact;
+  const int taps = kh * kw;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    cudaFuncSetAttribute(conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+  });
+
+  // ---- streaming configuration (always valid)
+  int s_tw_log, s_th_log;
+  pick_tile(n, hout, wout, stride, &s_tw_log, &s_th_log);
+  const int s_tn_log = 7 - s_tw_log - s_th_log;
+  const int s_tiles_x = (wout + (1 << s_tw_log) - 1) >> s_tw_log;
+  const int s_tiles_y = (hout + (1 << s_th_log) - 1) >> s_th_log;
+  const int s_tiles_n = (n + (1 << s_tn_log) - 1) >> s_tn_log;
+  const int s_bn = pick_bn(cout_s);
+  const int s_ntiles = (cout_s + s_bn - 1) / s_bn;
+  const double stream_bytes = (double)s_tiles_x * s_tiles_y * s_tiles_n * s_ntiles * taps * p.kblocks * (A_TILE_BYTES + s_bn * 128.0);
+
+  // ---- weight-stationary halo configuration (stride-1 k>1 convs on large maps)
+  bool use_ws = false;
+  int ws_bn = 0, ws_ntiles = 0, ws_stages = 0;
+  const int twh = 8 + dil * (kw - 1), thh = 16 + dil * (kh - 1);
+  const int a_stage = ((twh * thh * 128) + 1023) / 1024 * 1024;
+  if (stride == 1 && taps > 1 && wout >= 24 && hout >= 32 && twh <= 256 && thh <= 256 && a_stage <= 48 * 1024) {
+    for (int nt = 1; nt <= 8 && !use_ws; ++nt) {
+      int bn = ((cout_s + nt - 1) / nt + 15) / 16 * 16;
+      if (bn > 256) continue;
+      const size_t wb = (size_t)p.kblocks * taps * bn * 128;
+      const size_t fixed = wb + 128 * (size_t)(bn * 2 + 16) + 1024 + 256;
+      if (fixed + 2 * (size_t)a_stage > SMEM_LIMIT) continue;
+      int stg = (int)((SMEM_LIMIT - fixed) / a_stage);
+      if (stg > 6) stg = 6;
+      const double ws_bytes = (double)((wout + 7) / 8) * ((hout + 15) / 16) * n * nt * p.kblocks * (double)(twh * thh * 128);
+      if (ws_bytes < 0.8 * stream_bytes) {
+        use_ws = true; ws_bn = bn; ws_ntiles = nt; ws_stages = stg;
+      }
+      break;  // the smallest feasible n-split is the cheapest in activation re-reads
+    }
+  }
+
+  CUtensorMap tmA, tmB;
+  if (use_ws) {
+    p.tw_log = 3; p.th_log = 4;
+    p.tiles_x = (wout + 7) / 8; p.tiles_y = (hout + 15) / 16;
+    p.pix_tiles = p.tiles_x * p.tiles_y * n;
+    p.bn = ws_bn; p.n_tiles = ws_ntiles; p.stages = ws_stages;
+    p.twh = twh; p.thh = thh; p.a_stage_bytes = a_stage;
+  } else {
+    p.tw_log = s_tw_log; p.th_log = s_th_log; p.tiles_x = s_tiles_x; p.tiles_y = s_tiles_y;
+    p.bn = s_bn; p.n_tiles = s_ntiles;
+    p.total_tiles = s_tiles_x * s_tiles_y * s_tiles_n * s_ntiles;
+  }
   p.stage_pitch = p.bn * 2 + 16;
   const int staging_bytes = 128 * p.stage_pitch;
-  int stages = (222 * 1024 - staging_bytes - 256) / stage_bytes;
-  if (stages > 8) stages = 8;
-  if (stages < 2) stages = 2;
-  p.stages = stages;
-  p.n_tiles = (cout_s + p.bn - 1) / p.bn;
-  p.total_tiles = p.tiles_x * p.tiles_y * tiles_n * p.n_tiles;
   int cols = 32;
   while (cols < 2 * p.bn) cols <<= 1;
   p.tmem_cols = cols;
-  p.act = act; p.slope = slope; p.dact = dact;
-
-  CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)cin_s, (cuuint64_t)win, (cuuint64_t)hin, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)cin_s * 2, (cuuint64_t)win * cin_s * 2, (cuuint64_t)hin * win * cin_s * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)((1 << p.tw_log) * stride), (cuuint32_t)((1 << p.th_log) * stride),
-                         (cuuint32_t)(1 << tn_log)};
+    cuuint32_t box[4];
+    if (use_ws) {
+      box[0] = 64; box[1] = (cuuint32_t)twh; box[2] = (cuuint32_t)thh; box[3] = 1;
+    } else {
+      box[0] = 64; box[1] = (cuuint32_t)((1 << p.tw_log) * stride); box[2] = (cuuint32_t)((1 << p.th_log) * stride);
+      box[3] = (cuuint32_t)(1 << s_tn_log);
+    }
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     if (!encode_map(&tmA, in, 4, dims, strides, box, estr, "activations")) return CGB_LAUNCH_FAILURE;
   }
   {
-    cuuint64_t dims[3] = {(cuuint64_t)cin_s, (cuuint64_t)(kh * kw), (cuuint64_t)cout_s};
-    cuuint64_t strides[2] = {(cuuint64_t)cin_s * 2, (cuuint64_t)kh * kw * cin_s * 2};
+    cuuint64_t dims[3] = {(cuuint64_t)cin_s, (cuuint64_t)taps, (cuuint64_t)cout_s};
+    cuuint64_t strides[2] = {(cuuint64_t)cin_s * 2, (cuuint64_t)taps * cin_s * 2};
     cuuint32_t box[3] = {64, 1, (cuuint32_t)p.bn};
     cuuint32_t estr[3] = {1, 1, 1};
     if (!encode_map(&tmB, w, 3, dims, strides, box, estr, "weights")) return CGB_LAUNCH_FAILURE;
   }
+  if (use_ws) {
+    const size_t smem = (size_t)p.kblocks * taps * p.bn * 128 + (size_t)p.stages * a_stage + staging_bytes + 16 * p.stages + 64 + 1024;
+    int ctas = num_sms() / p.n_tiles * p.n_tiles;
+    if (ctas > p.pix_tiles * p.n_tiles) ctas = p.pix_tiles * p.n_tiles;
+    conv_tc_ws_kernel<<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, p, bias, (const __nv_bfloat16*)residual,
+                                                      (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out);
+    return after_launch("conv_tc_ws");
+  }
+  const int stage_bytes = A_TILE_BYTES + p.bn * 128;
+  int stages = (int)((SMEM_LIMIT - 1024 - 256 - staging_bytes) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 16 * stages + 48 + 1024;
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
   dim3 grid((unsigned)(p.total_tiles < num_sms() ? p.total_tiles : num_sms()));
   conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p, bias, (const __nv_bfloat16*)residual,
                                                  (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out);
@@ -562,8 +856,9 @@ struct WgParams {
 };
 
 constexpr int BOX_BYTES = 128 * 128;  // 128 pixels x 64 channels bf16
+constexpr int WG_THREADS = 192;       // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
 
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(WG_THREADS)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgParams p,
                 float* __restrict__ gw) {
   extern __shared__ uint8_t smem_raw[];
@@ -653,16 +948,18 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (int t = 0; t < ntaps; ++t) {
         mbar_wait(s_full(ss), sph);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one_sync()) {
           const uint32_t s_addr = s_base + (uint32_t)ss * s_bytes;
           const uint32_t a_addr = p.x_is_m ? s_addr : u_addr;
           const uint32_t b_addr = p.x_is_m ? u_addr : s_addr;
           const uint32_t d_addr = tmem_base + (uint32_t)(t * p.bn);
+          const uint32_t a_lo = desc_lo(a_addr, BOX_BYTES), b_lo = desc_lo(b_addr, BOX_BYTES);
+          const uint32_t hi = desc_hi(1024u);
+          uint32_t acc = tile > tile0 ? 1u : 0u;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {  // 8 x 16 pixels
-            const uint64_t ad = make_desc(a_addr + (uint32_t)k * 2048u, BOX_BYTES, 1024u);
-            const uint64_t bd = make_desc(b_addr + (uint32_t)k * 2048u, BOX_BYTES, 1024u);
-            umma_bf16(d_addr, ad, bd, idesc, (tile > tile0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 8; ++k) {  // 8 x 16 pixels, 2048 B (16 rows) apart
+            umma_bf16(d_addr, desc_join(a_lo + 128u * k, hi), desc_join(b_lo + 128u * k, hi), idesc, acc);
+            acc = 1u;
           }
           umma_commit(s_empty(ss));
           if (t == ntaps - 1) {
@@ -804,7 +1101,7 @@ int conv_tc_wgrad(const cgb_conv_desc* d, const void* x, const void* gy, float* 
     cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   dim3 grid((unsigned)splits, (unsigned)m_tiles, (unsigned)zdim);
-  wgrad_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmX, tmG, p, gw);
+  wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(tmX, tmG, p, gw);
   int s = after_launch("wgrad_tc");
   if (s) return s;
   if (gbias) {

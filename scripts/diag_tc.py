@@ -20,6 +20,12 @@ CASES = [
     (2, 8, 16, 16, 16, 4, 2, 1, 1),
     (1, 320, 160, 40, 40, 3, 1, 1, 1),
     (2, 128, 48, 64, 64, 3, 1, 1, 1),
+    (1, 24, 24, 40, 48, 3, 1, 1, 1),
+    (2, 128, 80, 33, 50, 3, 1, 1, 1),
+    (1, 64, 32, 64, 64, 3, 1, 2, 2),
+    (1, 128, 160, 48, 40, 3, 1, 1, 1),
+    (1, 48, 128, 64, 32, 3, 1, 1, 1),
+    (1, 32, 128, 64, 64, 1, 1, 1, 0),
 ]
 only = int(sys.argv[1]) if len(sys.argv) > 1 else None
 for idx, (n, ci, co, h, w, k, s, dil, pad) in enumerate(CASES):
