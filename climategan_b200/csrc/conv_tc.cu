@@ -654,6 +654,8 @@ static bool encode_map(CUtensorMap* tm, const void* ptr, int rank, const cuuint6
   return true;
 }
 
+static const size_t SMEM_LIMIT = 227 * 1024;
+
 static int num_sms() {
   static int n = 0;
   if (!n) {
@@ -712,8 +714,6 @@ bool conv_tc_supported(const cgb_conv_desc* d, int which) {
 }
 
 // Launch an fprop on (in -> out).  in: [n,hin,win,cin_s], w: [cout_s][taps][cin_s], out: [n,hout,wout,cout_s]
-static const size_t SMEM_LIMIT = 227 * 1024;
-
 static int launch_fprop(const void* in, const void* w, void* out, int n, int hin, int win, int cin_s, int hout, int wout,
                         int cout_s, int kh, int kw, int stride, int dil, int pad_y, int pad_x, int act, float slope,
                         const float* bias, const void* residual, int dact, const void* mask_src, cudaStream_t st) {
@@ -1002,6 +1002,238 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// wgrad, halo variant (stride-1 k x k convs on large maps): the x tile is loaded ONCE per pixel tile as a halo box
+// (16 + dil*(ndy-1)) x (8 + dil*(kw-1)) pixels and every tap of the CTA's dy-group is an MN-major UMMA descriptor into
+// it (row-shifted start, 8-row group stride SBO = TWh*128 B) — instead of one shifted box per tap.  Tile = 16 rows x 8
+// pixels of one image; K step = 16 pixels = two tile rows.
+// ------------------------------------------------------------------------------------------------------
+struct WgHaloParams {
+  int n, ho, wo;
+  int kh, kw, dil, pad;
+  int tiles_x, tiles_y, total_tiles, tiles_per_cta;
+  int m_dim, n_dim, bn, n_boxes;
+  int rows_per_group, row_groups;  // dy rows per CTA, number of dy groups
+  int x_is_m;
+  int twh, thh;                    // halo extent for a full group
+  int x_box_bytes;                 // 1024-aligned bytes of one 64-channel halo box
+  int stages_x, stages_g;
+  int tmem_cols;
+  long long sm, sn, st;
+};
+
+__global__ void __launch_bounds__(WG_THREADS)
+wgrad_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgHaloParams p,
+                     float* __restrict__ gw) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int x_boxes = p.x_is_m ? 2 : p.n_boxes;   // allocation (M side always owns two boxes)
+  const int g_boxes = p.x_is_m ? p.n_boxes : 2;
+  const uint32_t xs_bytes = (uint32_t)x_boxes * (uint32_t)p.x_box_bytes, gs_bytes = (uint32_t)g_boxes * BOX_BYTES;
+  const uint32_t x_base = base;
+  const uint32_t g_base = base + (uint32_t)p.stages_x * xs_bytes;
+  const uint32_t bar_base = g_base + (uint32_t)p.stages_g * gs_bytes;
+  auto x_full = [&](int i) { return bar_base + 8u * (uint32_t)i; };
+  auto x_empty = [&](int i) { return bar_base + 8u * (uint32_t)(p.stages_x + i); };
+  auto g_full = [&](int i) { return bar_base + 8u * (uint32_t)(2 * p.stages_x + i); };
+  auto g_empty = [&](int i) { return bar_base + 8u * (uint32_t)(2 * p.stages_x + p.stages_g + i); };
+  const uint32_t tmem_full_bar = bar_base + 16u * (uint32_t)(p.stages_x + p.stages_g);
+  const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * 128;
+  const int grp = blockIdx.z % p.row_groups;
+  const int n0 = (blockIdx.z / p.row_groups) * p.bn;
+  const int dy0 = grp * p.rows_per_group;
+  int ndy = p.kh - dy0;
+  if (ndy > p.rows_per_group) ndy = p.rows_per_group;
+  const int ntaps = ndy * p.kw;
+  const int tile0 = blockIdx.x * p.tiles_per_cta;
+  int tile1 = tile0 + p.tiles_per_cta;
+  if (tile1 > p.total_tiles) tile1 = p.total_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmG);
+    for (int i = 0; i < p.stages_x; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 1); }
+    for (int i = 0; i < p.stages_g; ++i) { mbar_init(g_full(i), 1); mbar_init(g_empty(i), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  const int x_ch0 = p.x_is_m ? m0 : n0;
+  const int g_ch0 = p.x_is_m ? n0 : m0;
+  const int m_load = (p.m_dim - m0 > 64) ? 2 : 1;
+  const int x_load = p.x_is_m ? m_load : x_boxes;
+  const int g_load = p.x_is_m ? g_boxes : m_load;
+  const uint32_t halo_bytes = (uint32_t)(p.twh * p.thh) * 128u;   // bytes one TMA box really delivers
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      int xs = 0, gs = 0;
+      uint32_t xph = 0, gph = 0;
+      for (int tile = tile0; tile < tile1; ++tile) {
+        const int tx = tile % p.tiles_x;
+        const int ty = (tile / p.tiles_x) % p.tiles_y;
+        const int img = tile / (p.tiles_x * p.tiles_y);
+        const int ox0 = tx << 3, oy0 = ty << 4;
+        mbar_wait(g_empty(gs), gph ^ 1u);
+        mbar_expect_tx(g_full(gs), (uint32_t)g_load * BOX_BYTES);
+        for (int b = 0; b < g_load; ++b)
+          tma_load_4d(g_base + (uint32_t)gs * gs_bytes + (uint32_t)b * BOX_BYTES, &tmG, g_full(gs), g_ch0 + b * 64, ox0, oy0, img);
+        if (++gs == p.stages_g) { gs = 0; gph ^= 1u; }
+        mbar_wait(x_empty(xs), xph ^ 1u);
+        mbar_expect_tx(x_full(xs), (uint32_t)x_load * halo_bytes);
+        for (int b = 0; b < x_load; ++b)
+          tma_load_4d(x_base + (uint32_t)xs * xs_bytes + (uint32_t)b * (uint32_t)p.x_box_bytes, &tmX, x_full(xs), x_ch0 + b * 64,
+                      ox0 - p.pad, oy0 - p.pad + dy0 * p.dil, img);
+        if (++xs == p.stages_x) { xs = 0; xph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc(p.bn, true, true);
+    const uint32_t hi_x = desc_hi((uint32_t)p.twh * 128u), hi_g = desc_hi(1024u);
+    const uint32_t kstep_x = (uint32_t)(2 * p.twh) * 8u;   // two halo rows per 16-pixel K step, in 16-byte units
+    int xs = 0, gs = 0;
+    uint32_t xph = 0, gph = 0;
+    for (int tile = tile0; tile < tile1; ++tile) {
+      mbar_wait(g_full(gs), gph);
+      mbar_wait(x_full(xs), xph);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t x_lo0 = desc_lo(x_base + (uint32_t)xs * xs_bytes, (uint32_t)p.x_box_bytes);
+        const uint32_t g_lo0 = desc_lo(g_base + (uint32_t)gs * gs_bytes, BOX_BYTES);
+        const uint32_t acc0 = tile > tile0 ? 1u : 0u;
+        int t = 0;
+        for (int dy = 0; dy < ndy; ++dy) {
+          for (int dx = 0; dx < p.kw; ++dx, ++t) {
+            const uint32_t x_lo = x_lo0 + (uint32_t)((dy * p.dil) * p.twh + dx * p.dil) * 8u;
+            const uint32_t d_addr = tmem_base + (uint32_t)(t * p.bn);
+            uint32_t acc = acc0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint64_t xd = desc_join(x_lo + kstep_x * k, hi_x);
+              const uint64_t gd = desc_join(g_lo0 + 128u * k, hi_g);
+              if (p.x_is_m) umma_bf16(d_addr, xd, gd, idesc, acc);
+              else umma_bf16(d_addr, gd, xd, idesc, acc);
+              acc = 1u;
+            }
+          }
+        }
+        umma_commit(x_empty(xs));
+        umma_commit(g_empty(gs));
+        if (tile == tile1 - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++xs == p.stages_x) { xs = 0; xph ^= 1u; }
+      if (++gs == p.stages_g) { gs = 0; gph ^= 1u; }
+    }
+  } else if (tile1 > tile0) {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    const bool m_ok = m < p.m_dim;
+    mbar_wait(tmem_full_bar, 0u);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int t = 0; t < ntaps; ++t) {
+      const long long tap_off = (long long)(dy0 * p.kw + t) * p.st + (long long)m * p.sm;
+      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(t_row + (uint32_t)(t * p.bn + c0), r);
+        tmem_ld_wait();
+        if (!m_ok) continue;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int nn = n0 + c0 + j;
+          if (nn < p.n_dim) atomicAdd(gw + tap_off + (long long)nn * p.sn, __uint_as_float(r[j]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+static int launch_colsum(const cgb_conv_desc* d, const void* gy, float* gbias, cudaStream_t st);
+
+// returns CGB_UNSUPPORTED when the halo variant does not apply (caller falls back to the per-tap kernel)
+static int try_wgrad_halo(const cgb_conv_desc* d, const void* x, const void* gy, float* gw, cudaStream_t st) {
+  const int taps = d->kh * d->kw;
+  if (d->stride != 1 || taps == 1 || d->wo < 24 || d->ho < 32) return CGB_UNSUPPORTED;
+  WgHaloParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = d->n; p.ho = d->ho; p.wo = d->wo; p.kh = d->kh; p.kw = d->kw; p.dil = d->dil; p.pad = d->pad;
+  p.x_is_m = d->ci >= d->co ? 1 : 0;
+  p.m_dim = p.x_is_m ? d->ci : d->co;
+  p.n_dim = p.x_is_m ? d->co : d->ci;
+  p.bn = pick_bn(p.n_dim);
+  if (p.kw * p.bn > 512) return CGB_UNSUPPORTED;
+  p.n_boxes = (p.bn + 63) / 64;
+  p.rows_per_group = 512 / (p.kw * p.bn);
+  if (p.rows_per_group > p.kh) p.rows_per_group = p.kh;
+  p.row_groups = (p.kh + p.rows_per_group - 1) / p.rows_per_group;
+  p.rows_per_group = (p.kh + p.row_groups - 1) / p.row_groups;
+  p.twh = 8 + d->dil * (d->kw - 1);
+  p.thh = 16 + d->dil * (p.rows_per_group - 1);
+  if (p.twh > 256 || p.thh > 256) return CGB_UNSUPPORTED;
+  p.x_box_bytes = (p.twh * p.thh * 128 + 1023) / 1024 * 1024;
+  const int x_boxes = p.x_is_m ? 2 : p.n_boxes, g_boxes = p.x_is_m ? p.n_boxes : 2;
+  const size_t xs = (size_t)x_boxes * p.x_box_bytes, gs = (size_t)g_boxes * BOX_BYTES;
+  if (2 * (xs + gs) + 2048 > SMEM_LIMIT) return CGB_UNSUPPORTED;
+  int stages = (int)((SMEM_LIMIT - 2048) / (xs + gs));
+  if (stages > 4) stages = 4;
+  p.stages_x = p.stages_g = stages;
+  int cols = 32;
+  while (cols < p.rows_per_group * p.kw * p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  if (p.x_is_m) { p.sm = 1; p.sn = (long long)taps * d->ci; } else { p.sm = (long long)taps * d->ci; p.sn = 1; }
+  p.st = d->ci;
+  p.tiles_x = (d->wo + 7) / 8; p.tiles_y = (d->ho + 15) / 16;
+  p.total_tiles = p.tiles_x * p.tiles_y * d->n;
+  const int m_tiles = (p.m_dim + 127) / 128;
+  const int n_tiles = (p.n_dim + p.bn - 1) / p.bn;
+  const int zdim = n_tiles * p.row_groups;
+  int splits = num_sms() / (m_tiles * zdim);
+  if (splits < 1) splits = 1;
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  p.tiles_per_cta = (p.total_tiles + splits - 1) / splits;
+  splits = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+
+  CUtensorMap tmX, tmG;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->ci, (cuuint64_t)d->wi, (cuuint64_t)d->hi, (cuuint64_t)d->n};
+    cuuint64_t strides[3] = {(cuuint64_t)d->ci * 2, (cuuint64_t)d->wi * d->ci * 2, (cuuint64_t)d->hi * d->wi * d->ci * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.twh, (cuuint32_t)p.thh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (!encode_map(&tmX, x, 4, dims, strides, box, estr, "wgrad halo x")) return CGB_LAUNCH_FAILURE;
+  }
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->co, (cuuint64_t)d->wo, (cuuint64_t)d->ho, (cuuint64_t)d->n};
+    cuuint64_t strides[3] = {(cuuint64_t)d->co * 2, (cuuint64_t)d->wo * d->co * 2, (cuuint64_t)d->ho * d->wo * d->co * 2};
+    cuuint32_t box[4] = {64, 8, 16, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (!encode_map(&tmG, gy, 4, dims, strides, box, estr, "wgrad halo gy")) return CGB_LAUNCH_FAILURE;
+  }
+  const size_t smem = (size_t)stages * (xs + gs) + 32 * stages + 16 + 1024;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(wgrad_tc_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+  });
+  dim3 grid((unsigned)splits, (unsigned)m_tiles, (unsigned)zdim);
+  wgrad_tc_halo_kernel<<<grid, WG_THREADS, smem, st>>>(tmX, tmG, p, gw);
+  return after_launch("wgrad_tc_halo");
+}
+
 // per-channel sum over pixels (bias gradient): x [pixels, c] bf16 -> out[c] += sum
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long pixels, int c, long long px_per_cta) {
@@ -1033,6 +1265,11 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long
 }
 
 int conv_tc_wgrad(const cgb_conv_desc* d, const void* x, const void* gy, float* gw, float* gbias, cudaStream_t st) {
+  {
+    const int hs = try_wgrad_halo(d, x, gy, gw, st);
+    if (hs == CGB_OK) return gbias ? launch_colsum(d, gy, gbias, st) : CGB_OK;
+    if (hs != CGB_UNSUPPORTED) return hs;
+  }
   WgParams p;
   p.n = d->n; p.ho = d->ho; p.wo = d->wo;
   p.kh = d->kh; p.kw = d->kw; p.dil = d->dil; p.stride = d->stride; p.pad = d->pad;
@@ -1104,16 +1341,17 @@ int conv_tc_wgrad(const cgb_conv_desc* d, const void* x, const void* gy, float* 
   wgrad_tc_kernel<<<grid, WG_THREADS, smem, st>>>(tmX, tmG, p, gw);
   int s = after_launch("wgrad_tc");
   if (s) return s;
-  if (gbias) {
-    const long long pixels = (long long)d->n * d->ho * d->wo;
-    int ctas = (int)((pixels + 1023) / 1024);
-    if (ctas > 148 * 4) ctas = 148 * 4;
-    if (ctas < 1) ctas = 1;
-    const long long ppc = (pixels + ctas - 1) / ctas;
-    colsum_kernel<<<ctas, 256, d->co * sizeof(float), st>>>((const __nv_bfloat16*)gy, gbias, pixels, d->co, ppc);
-    s = after_launch("colsum");
-  }
-  return s;
+  return gbias ? launch_colsum(d, gy, gbias, st) : CGB_OK;
+}
+
+static int launch_colsum(const cgb_conv_desc* d, const void* gy, float* gbias, cudaStream_t st) {
+  const long long pixels = (long long)d->n * d->ho * d->wo;
+  int ctas = (int)((pixels + 1023) / 1024);
+  if (ctas > 148 * 8) ctas = 148 * 8;
+  if (ctas < 1) ctas = 1;
+  const long long ppc = (pixels + ctas - 1) / ctas;
+  colsum_kernel<<<ctas, 256, d->co * sizeof(float), st>>>((const __nv_bfloat16*)gy, gbias, pixels, d->co, ppc);
+  return after_launch("colsum");
 }
 
 // wt[ci][taps-1-t][co] = w[co][t][ci]

@@ -8,8 +8,8 @@ namespace cgb {
 
 // number of pixel-chunks per image for the reduction kernels
 static inline int pick_chunks(int n, int hw, int cv) {
-  // target >= 4 CTAs per SM overall, each CTA >= 256 pixels
-  int want = (148 * 4 + n - 1) / n;
+  // target >= 8 CTAs per SM overall, each CTA >= 256 pixels
+  int want = (148 * 8 + n - 1) / n;
   int maxc = (hw + 255) / 256;
   if (want > maxc) want = maxc;
   if (want < 1) want = 1;
@@ -72,28 +72,38 @@ __global__ void in_stats_finalize_kernel(const double* __restrict__ ws, float* _
 }
 
 // ---------------------------------------------------------------------------------------------------
-// SPADE modulation forward: one thread per (pixel, 8-channel vector)
+// SPADE modulation forward.  grid (pixel chunks, n); a thread owns one 8-channel vector (its mean/rstd live in
+// registers) and walks the chunk's pixels: 3 vector loads + 1 vector store per (pixel, vector), 2 FMAs per element.
 template <typename T>
 __global__ void __launch_bounds__(256)
 spade_mod_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const T* __restrict__ gb, T* __restrict__ out,
-                     long long total_vec, int hw, int c, int act, float slope) {
+                     int hw, int c, int px_per_chunk, int act, float slope) {
   const int cv = c >> 3;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / cv;
-    const int v = (int)(i - pix * cv);
-    const int img = (int)(pix / hw);
+  const int lanes = 256 / cv;
+  const int lane = threadIdx.x / cv, v = threadIdx.x - lane * cv;
+  if (lane >= lanes) return;
+  const int img = blockIdx.y;
+  float rs[8], nm[8];  // xhat = x*rs + nm
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    rs[j] = rstd[(long long)img * c + v * 8 + j];
+    nm[j] = -mean[(long long)img * c + v * 8 + j] * rs[j];
+  }
+  const float neg = act == CGB_ACT_NONE ? 1.f : (act == CGB_ACT_RELU ? 0.f : slope);
+  const int p0 = blockIdx.x * px_per_chunk;
+  const int p1 = min(hw, p0 + px_per_chunk);
+  for (int p = p0 + lane; p < p1; p += lanes) {
+    const long long pix = (long long)img * hw + p;
     float xv[8], g[8], b[8], o[8];
     Vec8<T>::load(x + pix * c + v * 8, xv);
     Vec8<T>::load(gb + pix * 2 * c + v * 8, g);
     Vec8<T>::load(gb + pix * 2 * c + c + v * 8, b);
-    const float* mp = mean + (long long)img * c + v * 8;
-    const float* rp = rstd + (long long)img * c + v * 8;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float xh = (xv[j] - mp[j]) * rp[j];
-      o[j] = act_apply(fmaf(xh, 1.f + g[j], b[j]), act, slope);
+      const float xh = fmaf(xv[j], rs[j], nm[j]);
+      const float t = fmaf(xh, 1.f + g[j], b[j]);
+      o[j] = t > 0.f ? t : t * neg;
     }
     Vec8<T>::store(out + pix * c + v * 8, o);
   }
@@ -163,30 +173,38 @@ spade_mod_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean,
   }
 }
 
+// gx = rstd*(g - m1 - xhat*m2) = A*g + B*x + C with per-(n,c) constants held in registers (same chunked mapping)
 template <typename T>
 __global__ void __launch_bounds__(256)
 in_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
-              const double* __restrict__ sums, T* __restrict__ g, long long total_vec, int hw, int c) {
+              const double* __restrict__ sums, T* __restrict__ g, int hw, int c, int px_per_chunk) {
   const int cv = c >> 3;
+  const int lanes = 256 / cv;
+  const int lane = threadIdx.x / cv, v = threadIdx.x - lane * cv;
+  if (lane >= lanes) return;
+  const int img = blockIdx.y;
   const float inv_hw = 1.f / (float)hw;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / cv;
-    const int v = (int)(i - pix * cv);
-    const int img = (int)(pix / hw);
-    float xv[8], gv[8], o[8];
-    Vec8<T>::load(x + pix * c + v * 8, xv);
-    Vec8<T>::load(g + pix * c + v * 8, gv);
-    const long long sc = (long long)img * c + v * 8;
+  float A[8], B[8], Cc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float rs = rstd[sc + j];
-      const float xh = (xv[j] - mean[sc + j]) * rs;
-      const float m1 = (float)(sums[(sc + j) * 2 + 0]) * inv_hw;
-      const float m2 = (float)(sums[(sc + j) * 2 + 1]) * inv_hw;
-      o[j] = rs * (gv[j] - m1 - xh * m2);
-    }
-    Vec8<T>::store(g + pix * c + v * 8, o);
+  for (int j = 0; j < 8; ++j) {
+    const long long sc = (long long)img * c + v * 8 + j;
+    const float rs = rstd[sc], mu = mean[sc];
+    const float m1 = (float)sums[sc * 2 + 0] * inv_hw;
+    const float m2 = (float)sums[sc * 2 + 1] * inv_hw;
+    A[j] = rs;
+    B[j] = -rs * rs * m2;
+    Cc[j] = rs * rs * m2 * mu - rs * m1;
+  }
+  const int p0 = blockIdx.x * px_per_chunk;
+  const int p1 = min(hw, p0 + px_per_chunk);
+  for (int p = p0 + lane; p < p1; p += lanes) {
+    const long long off = ((long long)img * hw + p) * c + v * 8;
+    float xv[8], gv[8], o[8];
+    Vec8<T>::load(x + off, xv);
+    Vec8<T>::load(g + off, gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], gv[j], fmaf(B[j], xv[j], Cc[j]));
+    Vec8<T>::store(g + off, o);
   }
 }
 
@@ -421,53 +439,66 @@ l1_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, float* 
 
 // ---------------------------------------------------------------------------------------------------
 // Spectral norm power iteration (norms.py:100-112): single CTA of 1024 threads, W [rows, cols] fp32.
-__device__ __forceinline__ float block_sum_1024(float v, float* red) {
+
+// Spectral-norm power iteration (norms.py:100-112) as three small multi-CTA kernels (W is up to 640 x 5760):
+//   K1: v_raw += W[rows-slice]^T u          grid (col chunks of 256, row slices of 64), atomics into zeroed v
+//   K2: u_raw  = W (v_raw / (|v_raw|+eps))  one warp per row; every CTA recomputes |v_raw| (<= 23 KB read)
+//   K3: v = v_raw/(|v_raw|+eps) ; u = u_raw/(|u_raw|+eps) ; sigma = |u_raw|^2/(|u_raw|+eps)      one CTA
+__global__ void __launch_bounds__(256)
+sn_wtu_kernel(const float* __restrict__ w, const float* __restrict__ u, float* __restrict__ v, int rows, int cols) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int r0 = blockIdx.y * 64;
+  const int r1 = min(rows, r0 + 64);
+  __shared__ float us[64];
+  if (threadIdx.x < 64 && r0 + threadIdx.x < rows) us[threadIdx.x] = u[r0 + threadIdx.x];
+  __syncthreads();
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s = fmaf(w[(long long)r * cols + c], us[r - r0], s);
+  atomicAdd(v + c, s);
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   float t = 0.f;
-  for (int i = 0; i < 32; ++i) t += red[i];
+  for (int i = 0; i < 8; ++i) t += red[i];
   return t;
 }
 
-__global__ void __launch_bounds__(1024)
-spectral_power_iter_kernel(const float* __restrict__ w, float* __restrict__ u, float* __restrict__ v,
-                           float* __restrict__ sigma, int rows, int cols) {
-  __shared__ float red[32];
-  const int tid = threadIdx.x;
-  const float eps = 1e-12f;
-  // v = W^T u  (each thread owns columns tid, tid+1024, ...) ; coalesced over columns
+__global__ void __launch_bounds__(256)
+sn_wv_kernel(const float* __restrict__ w, const float* __restrict__ v, float* __restrict__ u, int rows, int cols) {
+  __shared__ float red[8];
   float nv = 0.f;
-  for (int cidx = tid; cidx < cols; cidx += 1024) {
-    float s = 0.f;
-    for (int r = 0; r < rows; ++r) s = fmaf(w[(long long)r * cols + cidx], u[r], s);
-    v[cidx] = s;
-    nv = fmaf(s, s, nv);
-  }
-  nv = block_sum_1024(nv, red);
-  const float inv_v = 1.f / (sqrtf(nv) + eps);
-  for (int cidx = tid; cidx < cols; cidx += 1024) v[cidx] *= inv_v;
-  __syncthreads();
-  // u = W v : one warp per row (strided), lanes over columns
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int r = warp; r < rows; r += 32) {
-    float s = 0.f;
-    for (int cidx = lane; cidx < cols; cidx += 32) s = fmaf(w[(long long)r * cols + cidx], v[cidx], s);
+  for (int c = threadIdx.x; c < cols; c += 256) nv = fmaf(v[c], v[c], nv);
+  nv = block_sum_256(nv, red);
+  const float inv_v = 1.f / (sqrtf(nv) + 1e-12f);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s = fmaf(w[(long long)r * cols + c], v[c], s);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) u[r] = s;  // un-normalised W v
-  }
-  __syncthreads();
-  float nu = 0.f;
-  for (int r = tid; r < rows; r += 1024) nu = fmaf(u[r], u[r], nu);
-  nu = block_sum_1024(nu, red);
-  const float norm_u = sqrtf(nu);
-  const float inv_u = 1.f / (norm_u + eps);
-  // sigma = u_new . (W v) = |Wv|^2 / (|Wv| + eps)
-  for (int r = tid; r < rows; r += 1024) u[r] *= inv_u;
-  if (tid == 0) sigma[0] = nu * inv_u;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) u[r] = s * inv_v;
+}
+
+__global__ void __launch_bounds__(256)
+sn_finalize_kernel(float* __restrict__ u, float* __restrict__ v, float* __restrict__ sigma, int rows, int cols) {
+  __shared__ float red[8];
+  float nv = 0.f, nu = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) nv = fmaf(v[c], v[c], nv);
+  nv = block_sum_256(nv, red);
+  for (int r = threadIdx.x; r < rows; r += 256) nu = fmaf(u[r], u[r], nu);
+  nu = block_sum_256(nu, red);
+  const float inv_v = 1.f / (sqrtf(nv) + 1e-12f);
+  const float inv_u = 1.f / (sqrtf(nu) + 1e-12f);
+  for (int c = threadIdx.x; c < cols; c += 256) v[c] *= inv_v;
+  for (int r = threadIdx.x; r < rows; r += 256) u[r] *= inv_u;
+  if (threadIdx.x == 0) sigma[0] = nu * inv_u;  // u_new . (W v_new) = |Wv|^2 / (|Wv| + eps)
 }
 
 }  // namespace cgb
@@ -521,10 +552,14 @@ extern "C" int cgb_spade_modulate_fwd(const void* x, const float* mean, const fl
   CGB_CHECK_DEVICE();
   CGB_REQUIRE(x && mean && rstd && gb && out, "spade_modulate_fwd: null pointer");
   CGB_REQUIRE(c % 8 == 0 && c >= 8, "spade_modulate_fwd: c=%d must be a multiple of 8", c);
+  CGB_REQUIRE(c <= 2048, "spade_modulate_fwd: c=%d too large", c);
+  CGB_REQUIRE(act == CGB_ACT_NONE || act == CGB_ACT_RELU || act == CGB_ACT_LRELU, "spade_modulate_fwd: act must be none/relu/lrelu");
   cudaStream_t st = (cudaStream_t)stream;
-  const long long total = (long long)n * hw * (c / 8);
-  DISPATCH_T(dtype, spade_mod_fwd_kernel<T><<<grid_for(total), 256, 0, st>>>(
-                        (const T*)x, mean, rstd, (const T*)gb, (T*)out, total, hw, c, act, slope);)
+  const int chunks = pick_chunks(n, hw, c / 8);
+  const int ppc = (hw + chunks - 1) / chunks;
+  dim3 grid((hw + ppc - 1) / ppc, n);
+  DISPATCH_T(dtype, spade_mod_fwd_kernel<T><<<grid, 256, 0, st>>>((const T*)x, mean, rstd, (const T*)gb, (T*)out, hw, c,
+                                                                 ppc, act, slope);)
   return after_launch("spade_mod_fwd");
 }
 
@@ -550,10 +585,12 @@ extern "C" int cgb_instnorm_bwd(const void* x, const float* mean, const float* r
   CGB_CHECK_DEVICE();
   CGB_REQUIRE(x && mean && rstd && sums && g, "instnorm_bwd: null pointer");
   CGB_REQUIRE(c % 8 == 0 && c >= 8, "instnorm_bwd: c=%d must be a multiple of 8", c);
+  CGB_REQUIRE(c <= 2048, "instnorm_bwd: c=%d too large", c);
   cudaStream_t st = (cudaStream_t)stream;
-  const long long total = (long long)n * hw * (c / 8);
-  DISPATCH_T(dtype, in_bwd_kernel<T><<<grid_for(total), 256, 0, st>>>((const T*)x, mean, rstd, sums, (T*)g,
-                                                                     total, hw, c);)
+  const int chunks = pick_chunks(n, hw, c / 8);
+  const int ppc = (hw + chunks - 1) / chunks;
+  dim3 grid((hw + ppc - 1) / ppc, n);
+  DISPATCH_T(dtype, in_bwd_kernel<T><<<grid, 256, 0, st>>>((const T*)x, mean, rstd, sums, (T*)g, hw, c, ppc);)
   return after_launch("in_bwd");
 }
 
@@ -679,6 +716,15 @@ extern "C" int cgb_spectral_power_iter(const float* w, float* u, float* v, float
   CGB_CHECK_DEVICE();
   CGB_REQUIRE(w && u && v && sigma, "spectral_power_iter: null pointer");
   CGB_REQUIRE(rows > 0 && cols > 0, "spectral_power_iter: empty matrix");
-  spectral_power_iter_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(w, u, v, sigma, rows, cols);
-  return after_launch("spectral_power_iter");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(v, 0, sizeof(float) * (size_t)cols, st);
+  dim3 g1((cols + 255) / 256, (rows + 63) / 64);
+  sn_wtu_kernel<<<g1, 256, 0, st>>>(w, u, v, rows, cols);
+  int s1 = after_launch("sn_wtu");
+  if (s1) return s1;
+  sn_wv_kernel<<<(rows + 7) / 8, 256, 0, st>>>(w, v, u, rows, cols);
+  s1 = after_launch("sn_wv");
+  if (s1) return s1;
+  sn_finalize_kernel<<<1, 256, 0, st>>>(u, v, sigma, rows, cols);
+  return after_launch("sn_finalize");
 }

@@ -192,7 +192,7 @@ int cgb_l1_loss(const float* a, const float* b, float* loss, float* ga, int64_t 
  * SpectralNorm._update_u_v (climategan/norms.py:100-112), one power iteration:
  *   v <- normalize(W^T u) ; u <- normalize(W v) ; sigma = u.(W v)
  * W is w_bar viewed [rows, cols] fp32 row-major; u[rows], v[cols] updated in place; sigma -> device scalar.
- * One CTA per call; tiny (W <= 640x5760). */
+ * Three small multi-CTA kernels (W <= 640x5760). */
 int cgb_spectral_power_iter(const float* w, float* u, float* v, float* sigma, int32_t rows,
                             int32_t cols, void* stream);
 
