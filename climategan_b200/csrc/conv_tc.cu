@@ -198,14 +198,16 @@ struct TcParams {
   int dact;                    // derivative mask (dgrad) from mask_src
 };
 
-constexpr int TC_THREADS = 320;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2..9: epilogue
-constexpr int EPI_THREADS = 256;
+constexpr int EPI_WARPS = 16;                      // 4 per TMEM lane quarter (latency hiding: the epilogue is a long
+constexpr int EPI_PER_Q = EPI_WARPS / 4;           // dependent chain per warp, more warps -> more chains in flight)
+constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;    // warp 0: TMA producer, warp 1: MMA issuer, then the epilogue warps
+constexpr int EPI_THREADS = 32 * EPI_WARPS;
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 64 bf16
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
 
 // ---- epilogue of one 128-pixel x bn tile, executed by the 8 epilogue warps --------------------------------
 // phase 1: TMEM -> registers (two tcgen05.ld in flight) -> bias / activation / residual / mask -> bf16 -> staging row
@@ -227,9 +229,10 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const uint32_t (&r)
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
         v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
       }
-      if (p.act <= CGB_ACT_LRELU) {  // none / relu / lrelu: branch-free select
+      if (p.act == CGB_ACT_NONE) {
+      } else if (p.act <= CGB_ACT_LRELU) {  // relu / lrelu (0 <= slope < 1): max(v, v*neg), 2 instructions
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * neg;
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], v[j] * neg);
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], p.act, p.slope);
@@ -257,7 +260,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
                                               const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y,
                                               uint32_t tempty_bar, int warp, int lane) {
   const int q = warp & 3;              // TMEM lane quarter this warp may access
-  const int half = (warp - 2) >> 2;    // two warps share a quarter: even / odd 16-column chunks
+  const int half = (warp - 2) >> 2;    // EPI_PER_Q warps share a quarter: 16-column chunks interleaved among them
   const int row = q * 32 + lane;       // tile row == TMEM lane == pixel within the tile
   const int et = threadIdx.x - 64;     // 0..255 within the epilogue group
   const int tw_i = row & ((1 << p.tw_log) - 1);
@@ -274,14 +277,14 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
   const uint32_t t_row = tmem_acc + ((uint32_t)(q * 32) << 16);
   uint8_t* my_row = staging_gen + (size_t)row * p.stage_pitch;
   const int nchunks = p.bn >> 4;
-  for (int c = half; c < nchunks; c += 4) {
+  for (int c = half; c < nchunks; c += 2 * EPI_PER_Q) {
     uint32_t ra[16], rb[16];
-    const bool two = (c + 2) < nchunks;
+    const bool two = (c + EPI_PER_Q) < nchunks;
     tmem_ld16(t_row + (uint32_t)(c * 16), ra);
-    if (two) tmem_ld16(t_row + (uint32_t)((c + 2) * 16), rb);
+    if (two) tmem_ld16(t_row + (uint32_t)((c + EPI_PER_Q) * 16), rb);
     tmem_ld_wait();
     epi_chunk(p, ra, c, cn0, pix_ok, pix, neg, mask_early, bias, residual, mask_src, my_row);
-    if (two) epi_chunk(p, rb, c + 2, cn0, pix_ok, pix, neg, mask_early, bias, residual, mask_src, my_row);
+    if (two) epi_chunk(p, rb, c + EPI_PER_Q, cn0, pix_ok, pix, neg, mask_early, bias, residual, mask_src, my_row);
   }
   // accumulator buffer drained: hand it back to the MMA warp
   tc_fence_before();
@@ -297,8 +300,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
   const int c = lane - rsub * chunks_per_row;
   const int ch = cn0 + c * 8;
   if (rsub < rows_per_iter && ch < p.cout_s) {
-    const int ew = warp - 2;  // 0..7
-    for (int r2 = ew * rows_per_iter + rsub; r2 < 128; r2 += 8 * rows_per_iter) {
+    const int ew = warp - 2;  // 0..EPI_WARPS-1
+    for (int r2 = ew * rows_per_iter + rsub; r2 < 128; r2 += EPI_WARPS * rows_per_iter) {
       const int tw2 = r2 & ((1 << p.tw_log) - 1);
       const int th2 = (r2 >> p.tw_log) & ((1 << p.th_log) - 1);
       const int tn2 = r2 >> (p.tw_log + p.th_log);
@@ -306,18 +309,13 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
       if (ox2 >= p.wout || oy2 >= p.hout || img2 >= p.n) continue;
       const long long off = (((long long)img2 * p.hout + oy2) * p.wout + ox2) * p.cout_s + ch;
       uint4 val = *reinterpret_cast<const uint4*>(staging_gen + (size_t)r2 * p.stage_pitch + (size_t)c * 16);
-      if (mask_late) {
+      if (mask_late) {  // relu derivative: keep where the forward output was > 0 (packed bf16x2 compare + multiply)
         const uint4 mk = *reinterpret_cast<const uint4*>(mask_src + off);
         const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mk);
         __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&val);
+        const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.f);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 mf = __bfloat1622float2(mh[j]);
-          float2 vf = __bfloat1622float2(vh[j]);
-          vf.x = mf.x > 0.f ? vf.x : 0.f;
-          vf.y = mf.y > 0.f ? vf.y : 0.f;
-          vh[j] = __floats2bfloat162_rn(vf.x, vf.y);
-        }
+        for (int j = 0; j < 4; ++j) vh[j] = __hmul2(vh[j], __hgt2(mh[j], zero2));
       }
       *reinterpret_cast<uint4*>(y + off) = val;
     }
@@ -363,7 +361,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 8);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(b), EPI_WARPS);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -440,7 +438,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ================= epilogue (warps 2..9) =================
+    // ================= epilogue warps =================
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -515,7 +513,7 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 8);
+      mbar_init(tempty_bar(b), EPI_WARPS);
     }
     mbar_init(w_bar, 1);
     fence_barrier_init();
