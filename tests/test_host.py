@@ -92,3 +92,13 @@ def test_state_dict_surface_matches_reference():
 def test_full_size_param_count():
     p = PainterSpadeDecoder(default_painter_opts())
     assert sum(v.numel() for v in p.state_dict().values()) == 42_341_735  # SURVEY.md §8a [probe]
+
+
+def test_product_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing under climategan_b200/ may import or execute it."""
+    pkg = os.path.join(ROOT, "climategan_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("# oracle", ""), f"{f} references the oracle"

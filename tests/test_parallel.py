@@ -1,0 +1,75 @@
+"""CPU test of the N>1 path: world_size-2 gloo process group, flat gradient bucket all-reduce == what the reference
+wrapped in DDP would produce (mean of the per-shard gradients)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from climategan_b200.parallel import GradBucket, shard_batch
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)  # identical initial weights on every rank
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(4, 2, 1))
+    frozen = torch.nn.Parameter(torch.ones(3), requires_grad=False)
+    x = torch.arange(4 * 3 * 5 * 5, dtype=torch.float32).reshape(4, 3, 5, 5) / 100.0
+    xs = shard_batch(x, rank, world)
+    net(xs).pow(2).mean().backward()
+    if rank == 1:
+        net[2].bias.grad = None  # a rank with a missing grad still takes part
+    bucket = GradBucket(list(net.parameters()) + [frozen])
+    assert bucket.numel == sum(p.numel() for p in net.parameters())
+    bucket.allreduce()
+    out[rank] = [p.grad.clone() for p in net.parameters()]
+    dist.destroy_process_group()
+
+
+def test_grad_bucket_allreduce_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    # reference: per-shard gradients averaged
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(4, 2, 1))
+    x = torch.arange(4 * 3 * 5 * 5, dtype=torch.float32).reshape(4, 3, 5, 5) / 100.0
+    grads = []
+    for r in range(world):
+        net.zero_grad()
+        net(x[r * 2:(r + 1) * 2]).pow(2).mean().backward()
+        g = [p.grad.clone() for p in net.parameters()]
+        if r == 1:
+            g[3] = torch.zeros_like(g[3])
+        grads.append(g)
+    mean = [(a + b) / 2 for a, b in zip(*grads)]
+    for r in range(world):
+        for got, want in zip(out[r], mean):
+            assert torch.allclose(got, want, rtol=1e-6, atol=1e-7)
+    # both ranks hold identical gradients after the collective
+    for a, b in zip(out[0], out[1]):
+        assert torch.equal(a, b)
+
+
+def test_shard_batch():
+    x = torch.arange(12).reshape(6, 2)
+    assert torch.equal(shard_batch(x, 1, 3), x[2:4])
+    try:
+        shard_batch(x, 0, 4)
+    except ValueError:
+        pass
+    else:
+        raise AssertionError("uneven shard must raise")
