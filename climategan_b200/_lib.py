@@ -87,6 +87,12 @@ SIGNATURES = {
     "cgb_spade_modulate_fwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),
     "cgb_spade_modulate_bwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),
     "cgb_instnorm_bwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_instnorm_apply_fwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),
+    "cgb_instnorm_apply_bwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),
+    "cgb_avgpool3s2_fwd": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_avgpool3s2_bwd": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_const_target_loss": ([_P, _P, _P, _L, _I, _F, _F, _P], C.c_int),
+    "cgb_l1_loss_storage": ([_P, _P, _P, _P, _I, _L, _F, _P], C.c_int),
     "cgb_resize_nearest_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_upsample_nearest_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_im2col": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),

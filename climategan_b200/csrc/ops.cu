@@ -336,6 +336,216 @@ act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long count, int 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// instance norm + activation (discriminator.py:120-133: conv -> InstanceNorm2d(affine=False) -> LeakyReLU(0.2))
+template <typename T>
+__global__ void __launch_bounds__(256)
+in_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    T* __restrict__ y, int hw, int c, int px_per_chunk, float neg) {
+  const int cv = c >> 3;
+  const int lanes = 256 / cv;
+  const int lane = threadIdx.x / cv, v = threadIdx.x - lane * cv;
+  if (lane >= lanes) return;
+  const int img = blockIdx.y;
+  float rs[8], nm[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    rs[j] = rstd[(long long)img * c + v * 8 + j];
+    nm[j] = -mean[(long long)img * c + v * 8 + j] * rs[j];
+  }
+  const int p0 = blockIdx.x * px_per_chunk;
+  const int p1 = min(hw, p0 + px_per_chunk);
+  for (int p = p0 + lane; p < p1; p += lanes) {
+    const long long off = ((long long)img * hw + p) * c + v * 8;
+    float xv[8], o[8];
+    Vec8<T>::load(x + off, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float t = fmaf(xv[j], rs[j], nm[j]);
+      o[j] = fmaxf(t, t * neg);
+    }
+    Vec8<T>::store(y + off, o);
+  }
+}
+
+// backward part 1: gxhat = gy * act'(xhat) (in place allowed), sums += (sum gxhat, sum gxhat*xhat)
+template <typename T>
+__global__ void __launch_bounds__(256)
+in_apply_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const T* __restrict__ gy, T* __restrict__ gxhat, double* __restrict__ sums, int hw, int c,
+                    int px_per_chunk, float neg) {
+  extern __shared__ float sm[];
+  const int cv = c >> 3;
+  const int lanes = 256 / cv;
+  const int tid = threadIdx.x;
+  const int lane = tid / cv, v = tid - lane * cv;
+  const int img = blockIdx.y;
+  for (int i = tid; i < 2 * c; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  if (lane < lanes) {
+    float s1[8], s2[8], rs[8], nm[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1[j] = s2[j] = 0.f;
+      rs[j] = rstd[(long long)img * c + v * 8 + j];
+      nm[j] = -mean[(long long)img * c + v * 8 + j] * rs[j];
+    }
+    const int p0 = blockIdx.x * px_per_chunk;
+    const int p1 = min(hw, p0 + px_per_chunk);
+    for (int p = p0 + lane; p < p1; p += lanes) {
+      const long long off = ((long long)img * hw + p) * c + v * 8;
+      float xv[8], g[8], o[8];
+      Vec8<T>::load(x + off, xv);
+      Vec8<T>::load(gy + off, g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = fmaf(xv[j], rs[j], nm[j]);
+        o[j] = g[j] * (xh > 0.f ? 1.f : neg);
+        s1[j] += o[j];
+        s2[j] = fmaf(o[j], xh, s2[j]);
+      }
+      Vec8<T>::store(gxhat + off, o);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sm[v * 8 + j], s1[j]);
+      atomicAdd(&sm[c + v * 8 + j], s2[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < c; i += 256) {
+    atomicAdd(&sums[((long long)img * c + i) * 2 + 0], (double)sm[i]);
+    atomicAdd(&sums[((long long)img * c + i) * 2 + 1], (double)sm[c + i]);
+  }
+}
+
+// nn.AvgPool2d(3, stride=2, padding=1, count_include_pad=False) (discriminator.py:223-225), NHWC
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256)
+avgpool3s2_kernel(const T* __restrict__ src, T* __restrict__ dst, long long total_vec, int hi, int wi, int ho, int wo,
+                  int c) {
+  const int cv = c >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int v = (int)(i - pix * cv);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (!BWD) {  // dst = pooled output pixel (oy, ox)
+      const int ox = (int)(pix % wo);
+      const long long t = pix / wo;
+      const int oy = (int)(t % ho);
+      const long long img = t / ho;
+      int cnt = 0;
+      for (int dy = 0; dy < 3; ++dy)
+        for (int dx = 0; dx < 3; ++dx) {
+          const int sy = oy * 2 - 1 + dy, sx = ox * 2 - 1 + dx;
+          if (sy < 0 || sy >= hi || sx < 0 || sx >= wi) continue;
+          float f[8];
+          Vec8<T>::load(src + ((img * hi + sy) * wi + sx) * c + v * 8, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+          ++cnt;
+        }
+      const float inv = 1.f / (float)cnt;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    } else {     // dst = input-gradient pixel (iy, ix); src = pooled-output gradient
+      const int ix = (int)(pix % wi);
+      const long long t = pix / wi;
+      const int iy = (int)(t % hi);
+      const long long img = t / hi;
+      for (int oy = (iy + 1) / 2 - 1; oy <= (iy + 1) / 2; ++oy)
+        for (int ox = (ix + 1) / 2 - 1; ox <= (ix + 1) / 2; ++ox) {
+          if (oy < 0 || oy >= ho || ox < 0 || ox >= wo) continue;
+          if (iy < oy * 2 - 1 || iy > oy * 2 + 1 || ix < ox * 2 - 1 || ix > ox * 2 + 1) continue;
+          const int y0 = max(oy * 2 - 1, 0), y1 = min(oy * 2 + 1, hi - 1);
+          const int x0 = max(ox * 2 - 1, 0), x1 = min(ox * 2 + 1, wi - 1);
+          const float inv = 1.f / (float)((y1 - y0 + 1) * (x1 - x0 + 1));
+          float f[8];
+          Vec8<T>::load(src + ((img * ho + oy) * wo + ox) * c + v * 8, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], inv, acc[j]);
+        }
+    }
+    Vec8<T>::store(dst + pix * c + v * 8, acc);
+  }
+}
+
+// mean-reduced losses against a constant target (GANLoss / HingeLoss, losses.py:13-83, :550-593) on fp32 arrays.
+//   kind 0: BCE-with-logits(x, t)   1: MSE(x, t)   2: hinge D real  -mean(min(x-1,0))   3: hinge D fake -mean(min(-x-1,0))
+//   kind 4: -mean(x) (hinge / WGAN generator term)
+// loss[0] += scale * sum(l_i), gx_i = scale * dl_i/dx_i   (scale = weight / count)
+__global__ void __launch_bounds__(256)
+const_target_loss_kernel(const float* __restrict__ x, float* __restrict__ loss, float* __restrict__ gx, long long count,
+                         int kind, float t, float scale) {
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    float l, g;
+    if (kind == 0) {
+      l = fmaxf(v, 0.f) - v * t + log1pf(__expf(-fabsf(v)));
+      g = 1.f / (1.f + __expf(-v)) - t;
+    } else if (kind == 1) {
+      l = (v - t) * (v - t);
+      g = 2.f * (v - t);
+    } else if (kind == 2) {
+      l = -fminf(v - 1.f, 0.f);
+      g = v < 1.f ? -1.f : 0.f;
+    } else if (kind == 3) {
+      l = -fminf(-v - 1.f, 0.f);
+      g = v > -1.f ? 1.f : 0.f;
+    } else {
+      l = -v;
+      g = -1.f;
+    }
+    s += l;
+    if (gx) gx[i] = g * scale;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tt = 0.f;
+    for (int i = 0; i < 8; ++i) tt += ws[i];
+    atomicAdd(loss, tt * scale);
+  }
+}
+
+// L1 between two storage tensors (FeatMatchLoss, losses.py:86-103): loss += scale*sum|a-b|, ga = scale*sign(a-b)
+template <typename T>
+__global__ void __launch_bounds__(256)
+l1_storage_kernel(const T* __restrict__ a, const T* __restrict__ b, float* __restrict__ loss, T* __restrict__ ga,
+                  long long count, float scale) {
+  float s = 0.f;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < count;
+       i += (long long)gridDim.x * blockDim.x * 8) {
+    float x[8], y[8], g[8];
+    Vec8<T>::load(a + i, x);
+    Vec8<T>::load(b + i, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = x[j] - y[j];
+      s += fabsf(d);
+      g[j] = d > 0.f ? scale : (d < 0.f ? -scale : 0.f);
+    }
+    if (ga) Vec8<T>::store(ga + i, g);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tt = 0.f;
+    for (int i = 0; i < 8; ++i) tt += ws[i];
+    atomicAdd(loss, tt * scale);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // im2col of a few-channel tensor (the 3-channel SPADE conditioning): y[n,oy,ox, tap*c + ch] = x[n,oy+dy*dil-pad,
 // ox+dx*dil-pad, ch], zero outside; lets SPADE.mlp_shared (norms.py:164-166) run as a K=32 1x1 GEMM on the
 // tensor cores instead of 9 mostly-empty 64-channel K blocks.  One thread per (pixel, 8 output channels).
@@ -727,4 +937,78 @@ extern "C" int cgb_spectral_power_iter(const float* w, float* u, float* v, float
   if (s1) return s1;
   sn_finalize_kernel<<<1, 256, 0, st>>>(u, v, sigma, rows, cols);
   return after_launch("sn_finalize");
+}
+
+extern "C" int cgb_instnorm_apply_fwd(const void* x, const float* mean, const float* rstd, void* y, int32_t dtype,
+                                      int32_t n, int32_t hw, int32_t c, int32_t act, float slope, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && mean && rstd && y, "instnorm_apply_fwd: null pointer");
+  CGB_REQUIRE(c % 8 == 0 && c >= 8 && c <= 2048, "instnorm_apply_fwd: bad c=%d", c);
+  CGB_REQUIRE(act == CGB_ACT_NONE || act == CGB_ACT_RELU || act == CGB_ACT_LRELU, "instnorm_apply_fwd: act must be none/relu/lrelu");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float neg = act == CGB_ACT_NONE ? 1.f : (act == CGB_ACT_RELU ? 0.f : slope);
+  const int chunks = pick_chunks(n, hw, c / 8);
+  const int ppc = (hw + chunks - 1) / chunks;
+  dim3 grid((hw + ppc - 1) / ppc, n);
+  DISPATCH_T(dtype, in_apply_fwd_kernel<T><<<grid, 256, 0, st>>>((const T*)x, mean, rstd, (T*)y, hw, c, ppc, neg);)
+  return after_launch("in_apply_fwd");
+}
+
+extern "C" int cgb_instnorm_apply_bwd(const void* x, const float* mean, const float* rstd, const void* gy, void* gxhat,
+                                      double* sums, int32_t dtype, int32_t n, int32_t hw, int32_t c, int32_t act,
+                                      float slope, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && mean && rstd && gy && gxhat && sums, "instnorm_apply_bwd: null pointer");
+  CGB_REQUIRE(c % 8 == 0 && c >= 8 && c <= 2048, "instnorm_apply_bwd: bad c=%d", c);
+  cudaStream_t st = (cudaStream_t)stream;
+  const float neg = act == CGB_ACT_NONE ? 1.f : (act == CGB_ACT_RELU ? 0.f : slope);
+  const int chunks = pick_chunks(n, hw, c / 8);
+  const int ppc = (hw + chunks - 1) / chunks;
+  dim3 grid((hw + ppc - 1) / ppc, n);
+  DISPATCH_T(dtype, in_apply_bwd_kernel<T><<<grid, 256, 2 * c * sizeof(float), st>>>((const T*)x, mean, rstd, (const T*)gy,
+                                                                                     (T*)gxhat, sums, hw, c, ppc, neg);)
+  return after_launch("in_apply_bwd");
+}
+
+extern "C" int cgb_avgpool3s2_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t c,
+                                  void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y, "avgpool3s2_fwd: null pointer");
+  CGB_REQUIRE(c % 8 == 0 && c >= 8, "avgpool3s2_fwd: bad c=%d", c);
+  const int ho = (hi + 2 - 3) / 2 + 1, wo = (wi + 2 - 3) / 2 + 1;
+  const long long total = (long long)n * ho * wo * (c / 8);
+  DISPATCH_T(dtype, (avgpool3s2_kernel<T, false><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total,
+                                                                                                  hi, wi, ho, wo, c));)
+  return after_launch("avgpool3s2_fwd");
+}
+
+extern "C" int cgb_avgpool3s2_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t c,
+                                  void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(gy && gx, "avgpool3s2_bwd: null pointer");
+  CGB_REQUIRE(c % 8 == 0 && c >= 8, "avgpool3s2_bwd: bad c=%d", c);
+  const int ho = (hi + 2 - 3) / 2 + 1, wo = (wi + 2 - 3) / 2 + 1;
+  const long long total = (long long)n * hi * wi * (c / 8);
+  DISPATCH_T(dtype, (avgpool3s2_kernel<T, true><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)gy, (T*)gx, total,
+                                                                                                 hi, wi, ho, wo, c));)
+  return after_launch("avgpool3s2_bwd");
+}
+
+extern "C" int cgb_const_target_loss(const float* x, float* loss, float* gx, int64_t count, int32_t kind, float target,
+                                     float scale, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && loss, "const_target_loss: null pointer");
+  CGB_REQUIRE(kind >= 0 && kind <= 4 && count > 0, "const_target_loss: bad kind %d or count", kind);
+  const_target_loss_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(x, loss, gx, count, kind, target, scale);
+  return after_launch("const_target_loss");
+}
+
+extern "C" int cgb_l1_loss_storage(const void* a, const void* b, float* loss, void* ga, int32_t dtype, int64_t count,
+                                   float scale, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(a && b && loss, "l1_loss_storage: null pointer");
+  CGB_REQUIRE(count % 8 == 0 && count > 0, "l1_loss_storage: count must be a positive multiple of 8");
+  DISPATCH_T(dtype, l1_storage_kernel<T><<<grid_for(count / 8), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, loss,
+                                                                                               (T*)ga, count, scale);)
+  return after_launch("l1_loss_storage");
 }

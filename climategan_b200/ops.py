@@ -487,3 +487,116 @@ class _SpectralWeight(Function):
 
 def spectral_weight(w_bar, u, v):
     return _SpectralWeight.apply(w_bar, u, v)
+
+
+# ------------------------------------------------------------------------------------------------
+# discriminator path: instance norm + activation, avg-pool between scales, GAN / feature-matching losses
+# ------------------------------------------------------------------------------------------------
+class _InstNormAct(Function):
+    """act(InstanceNorm2d(affine=False)(x)) — the conv -> IN -> LeakyReLU(0.2) block of NLayerDiscriminator
+    (climategan/discriminator.py:120-133, 146-148)."""
+
+    @staticmethod
+    def forward(ctx, x, act, slope, eps):
+        mean, rstd = instnorm_stats(x, eps)
+        n, h, w, c = x.shape
+        y = torch.empty_like(x)
+        check(_L().cgb_instnorm_apply_fwd(_p(x), _p(mean), _p(rstd), _p(y), _DT[x.dtype], n, h * w, c, act, slope, _st()),
+              "instnorm_apply_fwd")
+        ctx.save_for_backward(x, mean, rstd)
+        ctx.meta = (act, slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, mean, rstd = ctx.saved_tensors
+        act, slope = ctx.meta
+        n, h, w, c = x.shape
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        sums = torch.zeros((n, c, 2), dtype=torch.float64, device=x.device)
+        check(_L().cgb_instnorm_apply_bwd(_p(x), _p(mean), _p(rstd), _p(gy), _p(gx), _p(sums), _DT[x.dtype], n, h * w, c,
+                                          act, slope, _st()), "instnorm_apply_bwd")
+        check(_L().cgb_instnorm_bwd(_p(x), _p(mean), _p(rstd), _p(sums), _p(gx), _DT[x.dtype], n, h * w, c, _st()),
+              "instnorm_bwd")
+        return gx, None, None, None
+
+
+def instnorm_act(x, act=_lib.ACT_NONE, slope=0.2, eps=1e-5):
+    return _InstNormAct.apply(x, act, slope, eps)
+
+
+class _AvgPool3s2(Function):
+    """nn.AvgPool2d(3, stride=2, padding=[1, 1], count_include_pad=False) (discriminator.py:223-225)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _chk_storage(x)
+        n, hi, wi, c = x.shape
+        ho, wo = (hi - 1) // 2 + 1, (wi - 1) // 2 + 1
+        y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
+        check(_L().cgb_avgpool3s2_fwd(_p(x), _p(y), _DT[x.dtype], n, hi, wi, c, _st()), "avgpool3s2_fwd")
+        ctx.shape = (n, hi, wi, c)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, hi, wi, c = ctx.shape
+        gy = gy.contiguous()
+        gx = torch.empty(ctx.shape, dtype=gy.dtype, device=gy.device)
+        check(_L().cgb_avgpool3s2_bwd(_p(gy), _p(gx), _DT[gy.dtype], n, hi, wi, c, _st()), "avgpool3s2_bwd")
+        return gx
+
+
+def avgpool3s2(x):
+    return _AvgPool3s2.apply(x)
+
+
+LOSS_BCE_LOGITS, LOSS_MSE, LOSS_HINGE_D_REAL, LOSS_HINGE_D_FAKE, LOSS_NEG_MEAN = 0, 1, 2, 3, 4
+
+
+class _ConstTargetLoss(Function):
+    @staticmethod
+    def forward(ctx, x, kind, target):
+        x = x.contiguous().float()
+        loss = torch.zeros((), dtype=torch.float32, device=x.device)
+        gx = torch.empty_like(x)
+        check(_L().cgb_const_target_loss(_p(x), _p(loss), _p(gx), x.numel(), kind, float(target), 1.0 / x.numel(), _st()),
+              "const_target_loss")
+        ctx.save_for_backward(gx)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (gx,) = ctx.saved_tensors
+        return gx * g, None, None
+
+
+def const_target_loss(x, kind, target=0.0):
+    """mean-reduced BCE-with-logits / MSE / hinge against a constant target (fp32 tensor of any shape)."""
+    return _ConstTargetLoss.apply(x, kind, target)
+
+
+class _L1Storage(Function):
+    @staticmethod
+    def forward(ctx, a, b, logical_count):
+        _chk_storage(a)
+        assert a.shape == b.shape and a.dtype == b.dtype
+        loss = torch.zeros((), dtype=torch.float32, device=a.device)
+        ga = torch.empty_like(a)
+        check(_L().cgb_l1_loss_storage(_p(a), _p(b.contiguous()), _p(loss), _p(ga), _DT[a.dtype], a.numel(),
+                                       1.0 / logical_count, _st()), "l1_loss_storage")
+        ctx.save_for_backward(ga)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (ga,) = ctx.saved_tensors
+        return ga * g.to(ga.dtype), None, None
+
+
+def l1_loss_storage(a, b, c_logical):
+    """nn.L1Loss()(a, b.detach()) for two storage tensors with ``c_logical`` real channels (pad channels are equal
+    zeros on both sides and contribute nothing; the mean divides by the logical element count)."""
+    n, h, w, _ = a.shape
+    return _L1Storage.apply(a, b.detach(), n * h * w * c_logical)

@@ -141,6 +141,20 @@ int cgb_spade_modulate_bwd(const void* x, const float* mean, const float* rstd, 
 int cgb_instnorm_bwd(const void* x, const float* mean, const float* rstd, const double* sums,
                      void* gxhat_inout, int32_t dtype, int32_t n, int32_t hw, int32_t c, void* stream);
 
+/* InstanceNorm2d(affine=False) applied + LeakyReLU, the NLayerDiscriminator block (discriminator.py:120-133,146-148):
+ *   y = act((x-mean)*rstd).   Backward part 1: gxhat = gy*act'(xhat), sums += (sum gxhat, sum gxhat*xhat); part 2 is
+ *   cgb_instnorm_bwd. */
+int cgb_instnorm_apply_fwd(const void* x, const float* mean, const float* rstd, void* y, int32_t dtype, int32_t n,
+                           int32_t hw, int32_t c, int32_t act, float slope, void* stream);
+int cgb_instnorm_apply_bwd(const void* x, const float* mean, const float* rstd, const void* gy, void* gxhat,
+                           double* sums, int32_t dtype, int32_t n, int32_t hw, int32_t c, int32_t act, float slope,
+                           void* stream);
+
+/* nn.AvgPool2d(3, stride=2, padding=1, count_include_pad=False) between discriminator scales
+ * (discriminator.py:223-225).  ho = (hi-1)/2+1. */
+int cgb_avgpool3s2_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t c, void* stream);
+int cgb_avgpool3s2_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t c, void* stream);
+
 /* ---- resampling --------------------------------------------------------------------------
  * F.interpolate(mode="nearest") (blocks.py:39-43 InterpolateNearest2d; norms.py:179; painter.py:152):
  * src index = floor(dst * in/out). */
@@ -187,6 +201,15 @@ int cgb_paste_bwd(const float* gout, const float* m, float* gfake, int32_t n, in
  * `loss` is a device fp32 scalar the caller zeroes. */
 int cgb_l1_loss(const float* a, const float* b, float* loss, float* ga, int64_t count, float scale,
                 void* stream);
+
+/* Mean-reduced losses against a constant target on fp32 arrays — GANLoss (BCEWithLogits / MSE, losses.py:13-83) and
+ * HingeLoss (losses.py:550-593):  kind 0 BCE-with-logits, 1 MSE, 2 hinge-D-real, 3 hinge-D-fake, 4 -mean(x).
+ *   loss[0] += scale*sum(l_i) ; gx_i = scale*dl_i/dx_i  (gx optional; scale = weight/count). */
+int cgb_const_target_loss(const float* x, float* loss, float* gx, int64_t count, int32_t kind, float target, float scale,
+                          void* stream);
+/* L1 between two storage tensors (FeatMatchLoss, losses.py:86-103): loss[0] += scale*sum|a-b| ; ga = scale*sign(a-b). */
+int cgb_l1_loss_storage(const void* a, const void* b, float* loss, void* ga, int32_t dtype, int64_t count, float scale,
+                        void* stream);
 
 /* ---- spectral norm -----------------------------------------------------------------------
  * SpectralNorm._update_u_v (climategan/norms.py:100-112), one power iteration:

@@ -82,8 +82,57 @@ def run_case(name, latent_dim, n_up, batch, size):
           os.path.getsize(os.path.join(HERE, name + ".npz")))
 
 
+def run_disc_case(name="disc_small", ndf=8, n_layers=3, num_d=2, batch=2, size=64):
+    """Painter discriminator D["p"] on cat(real, fake) + GANLoss(BCE) + FeatMatchLoss, as Trainer.get_painter_loss
+    assembles them (climategan/trainer.py:1362-1383) — generator-side gradients w.r.t. the fake image and D's params."""
+    disc_mod, losses_mod, tutils_mod = refshim.load("discriminator", "losses", "tutils")
+    from climategan_b200.utils import Dict
+
+    opts = Dict(tasks=["p"], dis=dict(p=dict(ndf=ndf, n_layers=n_layers, norm="instance", use_sigmoid=False, num_D=num_d,
+                                             get_intermediate_features=True, use_local_discriminator=False,
+                                             init_type="xavier", init_gain=0.02)))
+    torch.manual_seed(0)
+    D = disc_mod.OmniDiscriminator(opts)
+    shapes = [(k, tuple(v.shape)) for k, v in D.state_dict().items()]
+    sd = fill_state_dict(shapes, seed=4321)
+    D.load_state_dict(sd, strict=True)
+    rs = np.random.RandomState(7)
+    real = torch.from_numpy((rs.random_sample((batch, 4, size, size)) * 2 - 1).astype(np.float32))
+    fake = torch.from_numpy((rs.random_sample((batch, 4, size, size)) * 2 - 1).astype(np.float32)).requires_grad_(True)
+    out = D["p"](torch.cat([real, fake], dim=0))
+    pred_real, pred_fake = tutils_mod.divide_pred(out)
+    g_gan = losses_mod.GANLoss(use_lsgan=False)(pred_fake, True)
+    g_feat = losses_mod.FeatMatchLoss()(pred_real, pred_fake)
+    d_hinge = losses_mod.HingeLoss()(pred_fake, False, True) + losses_mod.HingeLoss()(pred_real, True, True)
+    loss = g_gan + 10.0 * g_feat
+    loss.backward()
+    grads = {k: p.grad for k, p in D.named_parameters() if p.grad is not None}
+    arrays = {
+        "real": real.numpy(), "fake": fake.detach().numpy(),
+        "g_gan": np.float32(g_gan.item()), "g_feat": np.float32(g_feat.item()), "d_hinge": np.float32(d_hinge.item()),
+        "fake_grad": fake.grad.numpy(),
+        "grad_norms": np.array([float(grads[k].norm()) for k, _ in shapes if k in grads], dtype=np.float64),
+        "grad::p.discriminator_0.model0.0.module.weight_bar": grads["p.discriminator_0.model0.0.module.weight_bar"].numpy(),
+        "grad::p.discriminator_1.model2.0.module.weight_bar": grads["p.discriminator_1.model2.0.module.weight_bar"].numpy(),
+    }
+    for i, feats in enumerate(out):
+        arrays[f"pred_{i}"] = feats[-1].detach().numpy()
+        arrays[f"feat_{i}_1"] = feats[1].detach().numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+    meta = {"case": name, "ndf": ndf, "n_layers": n_layers, "num_D": num_d, "batch": batch, "size": size,
+            "weight_seed": 4321, "shapes": [[k, list(s)] for k, s in shapes],
+            "grad_keys": [k for k, _ in shapes if k in grads],
+            "reference": "cc-ai/climategan @ /root/reference (climategan/{discriminator,losses,tutils}.py)",
+            "torch": torch.__version__}
+    with open(os.path.join(HERE, name + ".json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print(name, "g_gan", float(g_gan), "g_feat", float(g_feat), "d_hinge", float(d_hinge), "npz bytes",
+          os.path.getsize(os.path.join(HERE, name + ".npz")))
+
+
 if __name__ == "__main__":
     if not refshim.available():
         sys.exit("reference tree not available; goldens can only be regenerated in the build container")
     for name, cfg in CASES.items():
         run_case(name, *cfg)
+    run_disc_case()

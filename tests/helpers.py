@@ -18,6 +18,8 @@ def load_golden(name="painter_small"):
     arrs = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
     shapes = [(k, tuple(s)) for k, s in meta["shapes"]]
     sd = fill_state_dict(shapes, meta["weight_seed"])
+    if "input_seed" not in meta:
+        return meta, arrs, sd, None
     x, m, target = synth_inputs(meta["batch"], meta["size"], meta["input_seed"])
     return meta, arrs, sd, (x, m, target)
 

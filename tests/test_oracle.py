@@ -80,3 +80,28 @@ def test_oracle_vs_reference_modules():
         for k, v in ref.state_dict().items():
             if k.endswith("_u") or k.endswith("_v"):
                 assert float((v - sd[k]).abs().max()) < 1e-6, k
+
+
+def test_discriminator_oracle_matches_golden():
+    """oracle/discriminator_oracle.py vs the reference's OmniDiscriminator['p'] + GANLoss + FeatMatchLoss + HingeLoss."""
+    from oracle import discriminator_oracle as do
+
+    meta, g, sd, _ = load_golden("disc_small")
+    sd = {k[2:]: v.clone().requires_grad_(not k.endswith(("_u", "_v"))) for k, v in sd.items()}  # strip "p."
+    real = torch.from_numpy(g["real"])
+    fake = torch.from_numpy(g["fake"]).requires_grad_(True)
+    out = do.multiscale_forward(sd, torch.cat([real, fake], 0))
+    pred_real, pred_fake = do.divide_pred(out)
+    g_gan = do.gan_loss(pred_fake, True)
+    g_feat = do.feat_match_loss(pred_real, pred_fake)
+    d_hinge = do.hinge_loss(pred_fake, False) + do.hinge_loss(pred_real, True)
+    (g_gan + 10.0 * g_feat).backward()
+    assert abs(float(g_gan) - float(g["g_gan"])) < 1e-6
+    assert abs(float(g_feat) - float(g["g_feat"])) < 1e-5
+    assert abs(float(d_hinge) - float(g["d_hinge"])) < 1e-5
+    for i in range(meta["num_D"]):
+        assert rel_max(out[i][-1], torch.from_numpy(g[f"pred_{i}"])) < 1e-5
+        assert rel_max(out[i][1], torch.from_numpy(g[f"feat_{i}_1"])) < 1e-5
+    assert rel_max(fake.grad, torch.from_numpy(g["fake_grad"])) < 1e-4
+    norms = np.array([float(sd[k[2:]].grad.norm()) for k in meta["grad_keys"]])
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=5e-4, atol=1e-7)
