@@ -93,6 +93,11 @@ SIGNATURES = {
     "cgb_avgpool3s2_bwd": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_const_target_loss": ([_P, _P, _P, _L, _I, _F, _F, _P], C.c_int),
     "cgb_l1_loss_storage": ([_P, _P, _P, _P, _I, _L, _F, _P], C.c_int),
+    "cgb_vgg_preprocess_fwd": ([_P, _P, _P, _I, _I, _I, _P], C.c_int),
+    "cgb_vgg_preprocess_bwd": ([_P, _P, _P, _I, _I, _I, _P], C.c_int),
+    "cgb_maxpool2_fwd": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_maxpool2_bwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_extra_adam": ([_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _I, _I, _P], C.c_int),
     "cgb_resize_nearest_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_upsample_nearest_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_im2col": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),

@@ -546,6 +546,128 @@ l1_storage_kernel(const T* __restrict__ a, const T* __restrict__ b, float* __res
 }
 
 // ---------------------------------------------------------------------------------------------------
+// ExtraAdam (climategan/optim.py:137-291) over flat fp32 arrays: one launch per parameter group.
+//   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; u = -step_size * m / (sqrt(v) + eps)
+//   mode 0 (extrapolation, optim.py:153-170): if save_copy: c = p ;  p += u
+//   mode 1 (step, optim.py:172-197):           p = c + u
+__global__ void __launch_bounds__(256)
+extra_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                  float* __restrict__ c, long long count, float b1, float b2, float eps, float wd, float step_size,
+                  int mode, int save_copy) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float u = -step_size * mi / (sqrtf(vi) + eps);
+    if (mode == 0) {
+      if (save_copy) c[i] = pi;
+      p[i] = pi + u;
+    } else {
+      p[i] = c[i] + u;
+    }
+  }
+}
+
+// nn.MaxPool2d(2, 2) of torchvision's VGG19 features (losses.py:304-336), NHWC; bwd routes to the first max
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long total_vec, int hi, int wi, int c) {
+  const int cv = c >> 3;
+  const int ho = hi >> 1, wo = wi >> 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int v = (int)(i - pix * cv);
+    const int ox = (int)(pix % wo);
+    const long long t = pix / wo;
+    const int oy = (int)(t % ho);
+    const long long img = t / ho;
+    float best[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] = -3.4e38f;
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx) {
+        float f[8];
+        Vec8<T>::load(x + ((img * hi + oy * 2 + dy) * wi + ox * 2 + dx) * c + v * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], f[j]);
+      }
+    Vec8<T>::store(y + pix * c + v * 8, best);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool2_bwd_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ gy, T* __restrict__ gx,
+                    long long total_vec, int hi, int wi, int c) {
+  const int cv = c >> 3;
+  const int ho = hi >> 1, wo = wi >> 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;  // pooled pixel
+    const int v = (int)(i - pix * cv);
+    const int ox = (int)(pix % wo);
+    const long long t = pix / wo;
+    const int oy = (int)(t % ho);
+    const long long img = t / ho;
+    float ym[8], g[8];
+    bool taken[8];
+    Vec8<T>::load(y + pix * c + v * 8, ym);
+    Vec8<T>::load(gy + pix * c + v * 8, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) taken[j] = false;
+    for (int dy = 0; dy < 2; ++dy)
+      for (int dx = 0; dx < 2; ++dx) {
+        const long long off = ((img * hi + oy * 2 + dy) * wi + ox * 2 + dx) * c + v * 8;
+        float f[8], o[8];
+        Vec8<T>::load(x + off, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool hit = !taken[j] && f[j] == ym[j];
+          o[j] = hit ? g[j] : 0.f;
+          taken[j] = taken[j] || hit;
+        }
+        Vec8<T>::store(gx + off, o);
+      }
+  }
+}
+
+// vgg_preprocess(img * m) (climategan/tutils.py:416-427 applied to fake*m / x*m, trainer.py:1281-1283):
+// RGB->BGR, [-1,1] -> [0,255], subtract the caffe means; NCHW fp32 in, NHWC storage (8 ch) out.  bwd is the adjoint.
+template <typename T>
+__global__ void __launch_bounds__(256)
+vgg_pre_fwd_kernel(const float* __restrict__ x, const float* __restrict__ m, T* __restrict__ y, int hw, long long total) {
+  const float mean[3] = {103.939f, 116.779f, 123.680f};
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / hw;
+    const int p = (int)(i - img * hw);
+    const float mk = m ? m[i] : 1.f;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) v[ch] = (x[(img * 3 + (2 - ch)) * hw + p] * mk + 1.f) * 127.5f - mean[ch];
+    Vec8<T>::store(y + i * 8, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+vgg_pre_bwd_kernel(const T* __restrict__ gy, const float* __restrict__ m, float* __restrict__ gx, int hw, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / hw;
+    const int p = (int)(i - img * hw);
+    const float mk = m ? m[i] : 1.f;
+    float g[8];
+    Vec8<T>::load(gy + i * 8, g);
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) gx[(img * 3 + (2 - ch)) * hw + p] = g[ch] * 127.5f * mk;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // im2col of a few-channel tensor (the 3-channel SPADE conditioning): y[n,oy,ox, tap*c + ch] = x[n,oy+dy*dil-pad,
 // ox+dx*dil-pad, ch], zero outside; lets SPADE.mlp_shared (norms.py:164-166) run as a K=32 1x1 GEMM on the
 // tensor cores instead of 9 mostly-empty 64-channel K blocks.  One thread per (pixel, 8 output channels).
@@ -1011,4 +1133,57 @@ extern "C" int cgb_l1_loss_storage(const void* a, const void* b, float* loss, vo
   DISPATCH_T(dtype, l1_storage_kernel<T><<<grid_for(count / 8), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, loss,
                                                                                                (T*)ga, count, scale);)
   return after_launch("l1_loss_storage");
+}
+
+extern "C" int cgb_extra_adam(float* p, const float* g, float* m, float* v, float* c, int64_t count, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, int32_t step, int32_t mode, int32_t save_copy,
+                              void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(p && g && m && v && c, "extra_adam: null pointer");
+  CGB_REQUIRE(count > 0 && step >= 1 && (mode == 0 || mode == 1), "extra_adam: bad count/step/mode");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr * sqrt(bc2) / bc1);
+  extra_adam_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, c, count, beta1, beta2, eps, weight_decay,
+                                                                       step_size, mode, save_copy);
+  return after_launch("extra_adam");
+}
+
+extern "C" int cgb_maxpool2_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t c,
+                                void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y, "maxpool2_fwd: null pointer");
+  CGB_REQUIRE(c % 8 == 0 && c >= 8 && hi >= 2 && wi >= 2, "maxpool2_fwd: bad shape");
+  const long long total = (long long)n * (hi / 2) * (wi / 2) * (c / 8);
+  DISPATCH_T(dtype, maxpool2_fwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total, hi, wi, c);)
+  return after_launch("maxpool2_fwd");
+}
+
+extern "C" int cgb_maxpool2_bwd(const void* x, const void* y, const void* gy, void* gx, int32_t dtype, int32_t n,
+                                int32_t hi, int32_t wi, int32_t c, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y && gy && gx, "maxpool2_bwd: null pointer");
+  CGB_REQUIRE(c % 8 == 0 && c >= 8 && hi % 2 == 0 && wi % 2 == 0, "maxpool2_bwd: needs even spatial size");
+  const long long total = (long long)n * (hi / 2) * (wi / 2) * (c / 8);
+  DISPATCH_T(dtype, maxpool2_bwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, (const T*)y, (const T*)gy,
+                                                                                             (T*)gx, total, hi, wi, c);)
+  return after_launch("maxpool2_bwd");
+}
+
+extern "C" int cgb_vgg_preprocess_fwd(const float* x, const float* m, void* y, int32_t dtype, int32_t n, int32_t hw,
+                                      void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y, "vgg_preprocess_fwd: null pointer");
+  const long long total = (long long)n * hw;
+  DISPATCH_T(dtype, vgg_pre_fwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, m, (T*)y, hw, total);)
+  return after_launch("vgg_preprocess_fwd");
+}
+
+extern "C" int cgb_vgg_preprocess_bwd(const void* gy, const float* m, float* gx, int32_t dtype, int32_t n, int32_t hw,
+                                      void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(gy && gx, "vgg_preprocess_bwd: null pointer");
+  const long long total = (long long)n * hw;
+  DISPATCH_T(dtype, vgg_pre_bwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)gy, m, gx, hw, total);)
+  return after_launch("vgg_preprocess_bwd");
 }

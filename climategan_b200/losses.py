@@ -8,7 +8,7 @@ from random import random as rand
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 
 
 class GANLoss(nn.Module):
@@ -77,3 +77,73 @@ class FeatMatchLoss(nn.Module):
             for j in range(len(pred_fake[i]) - 1):
                 total = total + ops.l1_loss(pred_fake[i][j], pred_real[i][j].detach()) / num_D
         return total
+
+
+_VGG19_CFG = [(0, 3, 64), (2, 64, 64), "M", (5, 64, 128), (7, 128, 128), "M", (10, 128, 256), (12, 256, 256), (14, 256, 256),
+              (16, 256, 256), "M", (19, 256, 512), (21, 512, 512), (23, 512, 512), (25, 512, 512), "M", (28, 512, 512)]
+_VGG19_SLICES = [(0, 2), (2, 7), (7, 12), (12, 21), (21, 30)]
+
+
+class Vgg19(nn.Module):
+    """``climategan.losses.Vgg19`` (losses.py:304-336): torchvision vgg19.features[:30] cut into five slices ending at
+    relu1_1, relu2_1, relu3_1, relu4_1, relu5_1.  Same state_dict keys (``slice{k}.{idx}.weight``).  The reference loads
+    ImageNet weights (``pretrained=True``, a download); here the weights are whatever is loaded into the module
+    (random init in the bench) — frozen, so only data gradients flow."""
+
+    def __init__(self, requires_grad=False, storage_dtype=torch.bfloat16):
+        super().__init__()
+        self.storage_dtype = storage_dtype
+        layers = {}
+        for item in _VGG19_CFG:
+            if item != "M":
+                idx, ci, co = item
+                layers[idx] = nn.Conv2d(ci, co, 3, padding=1)
+        for k, (a, b) in enumerate(_VGG19_SLICES, start=1):
+            seq = nn.Sequential()
+            for idx in range(a, b):
+                if idx in layers:
+                    seq.add_module(str(idx), layers[idx])
+                elif any(it == "M" for it in _VGG19_CFG) and idx in (4, 9, 18, 27):
+                    seq.add_module(str(idx), nn.MaxPool2d(2, 2))
+                else:
+                    seq.add_module(str(idx), nn.ReLU(inplace=True))
+            setattr(self, f"slice{k}", seq)
+        if not requires_grad:
+            for p in self.parameters():
+                p.requires_grad = False
+
+    def forward_storage(self, x):
+        """x: storage [N,H,W,8] (vgg-preprocessed BGR).  Returns the five relu feature maps (storage tensors)."""
+        outs = []
+        for k in range(1, 6):
+            for m in getattr(self, f"slice{k}"):
+                if isinstance(m, nn.Conv2d):
+                    x = ops.conv2d(x, m.weight, m.bias, pad=1, act=_lib.ACT_RELU)  # conv + the ReLU that follows it
+                elif isinstance(m, nn.MaxPool2d):
+                    x = ops.maxpool2(x)
+            outs.append(x)
+        return outs
+
+
+class VGGLoss(nn.Module):
+    """``climategan.losses.VGGLoss`` (losses.py:338-350): sum_i w_i * L1(vgg(x)_i, vgg(y)_i.detach()), w = 1/32..1.
+    ``forward(x, y, mask=None)`` takes the NCHW fp32 images *before* ``vgg_preprocess`` (the preprocess and the
+    optional ``* m`` of trainer.py:1281-1283 run inside one kernel)."""
+
+    def __init__(self, device=None, storage_dtype=torch.bfloat16):
+        super().__init__()
+        self.vgg = Vgg19(storage_dtype=storage_dtype).eval()
+        if device is not None:
+            self.vgg.to(device)
+        self.weights = [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]
+        self.channels = [64, 128, 256, 512, 512]
+
+    def forward(self, x, y, mask=None):
+        dt = self.vgg.storage_dtype
+        x_vgg = self.vgg.forward_storage(ops.vgg_preprocess(x, mask, dt))
+        with torch.no_grad():
+            y_vgg = self.vgg.forward_storage(ops.vgg_preprocess(y, mask, dt))
+        loss = 0
+        for w, a, b, c in zip(self.weights, x_vgg, y_vgg, self.channels):
+            loss = loss + w * ops.l1_loss_storage(a, b, c)
+        return loss

@@ -600,3 +600,62 @@ def l1_loss_storage(a, b, c_logical):
     zeros on both sides and contribute nothing; the mean divides by the logical element count)."""
     n, h, w, _ = a.shape
     return _L1Storage.apply(a, b.detach(), n * h * w * c_logical)
+
+
+# ------------------------------------------------------------------------------------------------
+# VGG perceptual loss edge
+# ------------------------------------------------------------------------------------------------
+class _MaxPool2(Function):
+    @staticmethod
+    def forward(ctx, x):
+        _chk_storage(x)
+        n, hi, wi, c = x.shape
+        y = torch.empty((n, hi // 2, wi // 2, c), dtype=x.dtype, device=x.device)
+        check(_L().cgb_maxpool2_fwd(_p(x), _p(y), _DT[x.dtype], n, hi, wi, c, _st()), "maxpool2_fwd")
+        ctx.save_for_backward(x, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y = ctx.saved_tensors
+        n, hi, wi, c = x.shape
+        gx = torch.zeros_like(x) if (hi % 2 or wi % 2) else torch.empty_like(x)
+        check(_L().cgb_maxpool2_bwd(_p(x), _p(y), _p(gy.contiguous()), _p(gx), _DT[x.dtype], n, hi, wi, c, _st()), "maxpool2_bwd")
+        return gx
+
+
+def maxpool2(x):
+    """nn.MaxPool2d(kernel_size=2, stride=2) on a storage tensor."""
+    return _MaxPool2.apply(x)
+
+
+class _VggPreprocess(Function):
+    @staticmethod
+    def forward(ctx, img, m, dtype):
+        img = img.contiguous().float()
+        n, c, h, w = img.shape
+        assert c == 3
+        mm = None if m is None else m.detach().contiguous().float()
+        y = torch.empty((n, h, w, 8), dtype=dtype, device=img.device)
+        check(_L().cgb_vgg_preprocess_fwd(_p(img), _p(mm), _p(y), _DT[dtype], n, h * w, _st()), "vgg_preprocess_fwd")
+        ctx.mm = mm
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        gy = gy.contiguous()
+        n, h, w, _ = gy.shape
+        gx = torch.empty((n, 3, h, w), dtype=torch.float32, device=gy.device)
+        check(_L().cgb_vgg_preprocess_bwd(_p(gy), _p(ctx.mm), _p(gx), _DT[gy.dtype], n, h * w, _st()), "vgg_preprocess_bwd")
+        return gx, None, None
+
+
+def vgg_preprocess(img, m, dtype):
+    """vgg_preprocess(img * m) (tutils.py:416-427; trainer.py:1281-1283) -> storage tensor [N,H,W,8]."""
+    return _VggPreprocess.apply(img, m, dtype)
+
+
+def cat_mask_image(m, img):
+    """torch.cat([m, img], dim=1) (trainer.py:1363) with gradient flowing to ``img`` only — a pure copy; kept as a
+    torch op (memory plumbing, no arithmetic)."""
+    return torch.cat([m.detach(), img], dim=1)

@@ -64,11 +64,20 @@ class _Pending(Dict):
         dict.__setitem__(self, k, v)
 
 
-def default_painter_opts(latent_dim=640, spade_n_up=7, tasks=("p",)):
-    """The painter section of shared/trainer/defaults.yaml:141-160 (reference values)."""
+def default_painter_opts(latent_dim=640, spade_n_up=7, tasks=("p",), ndf=64, n_layers=4, num_D=3):
+    """The painter-related sections of shared/trainer/defaults.yaml (reference values): gen.p :141-160, gen.opt :73-90,
+    dis :193-228, train.lambdas.G.p :293-300."""
     return Dict(
         tasks=list(tasks),
+        dis=dict(
+            soft_shift=0.2, flip_prob=0.05,
+            opt=dict(optimizer="ExtraAdam", beta1=0.5, lr=dict(default=0.00002), lr_policy="step", lr_step_size=15, lr_gamma=0.5),
+            p=dict(input_nc=3, ndf=ndf, n_layers=n_layers, norm="instance", init_type="xavier", init_gain=0.02,
+                   use_sigmoid=False, num_D=num_D, get_intermediate_features=True, use_local_discriminator=False),
+        ),
+        train=dict(lambdas=dict(G=dict(p=dict(context=0, dm=1, featmatch=10, gan=1, reconstruction=0, tv=0, vgg=10)))),
         gen=dict(
+            opt=dict(optimizer="ExtraAdam", beta1=0.9, lr=dict(default=0.00005), lr_policy="step", lr_step_size=5, lr_gamma=0.5),
             p=dict(
                 latent_dim=latent_dim,
                 loss="gan",
@@ -81,6 +90,7 @@ def default_painter_opts(latent_dim=640, spade_n_up=7, tasks=("p",)):
                 spade_param_free_norm="instance",
                 spade_use_spectral_norm=True,
                 use_final_shortcut=False,
+                diff_aug=dict(use=False),
             )
         ),
     )

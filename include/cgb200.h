@@ -211,6 +211,25 @@ int cgb_const_target_loss(const float* x, float* loss, float* gx, int64_t count,
 int cgb_l1_loss_storage(const void* a, const void* b, float* loss, void* ga, int32_t dtype, int64_t count, float scale,
                         void* stream);
 
+/* VGG perceptual-loss edge (climategan/losses.py:304-350, tutils.py:416-427):
+ *   vgg_preprocess(img * m): RGB->BGR, [-1,1]->[0,255], minus the caffe channel means; NCHW fp32 (+ optional [n,1,h,w]
+ *   mask) -> NHWC storage with 8 channels.  _bwd is its adjoint (gradient w.r.t. img).
+ *   nn.MaxPool2d(2,2) of torchvision's vgg19.features, NHWC (bwd routes to the first maximum, like ATen). */
+int cgb_vgg_preprocess_fwd(const float* x, const float* m, void* y, int32_t dtype, int32_t n, int32_t hw, void* stream);
+int cgb_vgg_preprocess_bwd(const void* gy, const float* m, float* gx, int32_t dtype, int32_t n, int32_t hw, void* stream);
+int cgb_maxpool2_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t c, void* stream);
+int cgb_maxpool2_bwd(const void* x, const void* y, const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi,
+                     int32_t wi, int32_t c, void* stream);
+
+/* ---- optimiser ---------------------------------------------------------------------------
+ * ExtraAdam (climategan/optim.py:137-291; Trainer.g_opt_step/d_opt_step, trainer.py:674-694) over flat fp32 arrays:
+ *   m,v Adam moments; u = -lr*sqrt(1-b2^step)/(1-b1^step) * m/(sqrt(v)+eps)
+ *   mode 0 = extrapolation: (save_copy ? c = p : -) ; p += u        mode 1 = step: p = c + u
+ * `step` is the per-parameter Adam step count AFTER this call's increment (the reference increments it in both modes). */
+int cgb_extra_adam(float* p, const float* g, float* m, float* v, float* c, int64_t count, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int32_t step, int32_t mode, int32_t save_copy,
+                   void* stream);
+
 /* ---- spectral norm -----------------------------------------------------------------------
  * SpectralNorm._update_u_v (climategan/norms.py:100-112), one power iteration:
  *   v <- normalize(W^T u) ; u <- normalize(W v) ; sigma = u.(W v)

@@ -36,6 +36,7 @@ def _install_stubs():
 
     _stub("addict", Dict=Dict)
     _stub("comet_ml", Experiment=type("Experiment", (), {}), ExistingExperiment=type("ExistingExperiment", (), {}))
+    _stub("torch_optimizer", NovoGrad=type("NovoGrad", (), {}), RAdam=type("RAdam", (), {}))
     sk = _stub("skimage")
     sk.io = _stub("skimage.io")
     sk.color = _stub("skimage.color")

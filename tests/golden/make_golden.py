@@ -130,9 +130,97 @@ def run_disc_case(name="disc_small", ndf=8, n_layers=3, num_d=2, batch=2, size=6
           os.path.getsize(os.path.join(HERE, name + ".npz")))
 
 
+def run_step_case(name="painter_step", latent=16, n_up=4, ndf=8, n_layers=3, num_d=2, batch=2, size=64):
+    """Three consecutive optimiser steps of the painter task composed from the reference's OWN modules exactly as
+    Trainer.update_G / update_D do (trainer.py:989-1032, :1256-1387, :1071-1107, :674-694): G step (ExtraAdam
+    extrapolation), D step (extrapolation), then G step and D step again (ExtraAdam step).  soft_shift = flip_prob = 0."""
+    generator_mod, disc_mod, losses_mod, tutils_mod, optim_mod = refshim.load("generator", "discriminator", "losses", "tutils", "optim")
+    import torchvision
+    from climategan_b200.losses import Vgg19 as KeyHolder
+
+    # offline + CPU patches of hard-coded assumptions (SURVEY.md §8c rows 2 and 6)
+    _orig_vgg19 = torchvision.models.vgg19
+    losses_mod.models.vgg19 = lambda pretrained=True: _orig_vgg19(weights=None)
+
+    def vgg_preprocess_cpu(batch):
+        (r, g, b) = torch.chunk(batch, 3, dim=1)
+        batch = torch.cat((b, g, r), dim=1)
+        batch = (batch + 1) * 255 * 0.5
+        mean = torch.zeros_like(batch)
+        mean[:, 0], mean[:, 1], mean[:, 2] = 103.939, 116.779, 123.680
+        return batch.sub(mean)
+
+    opts = default_painter_opts(latent_dim=latent, spade_n_up=n_up, ndf=ndf, n_layers=n_layers, num_D=num_d)
+    torch.manual_seed(0)
+    G = generator_mod.OmniGenerator(opts)
+    G.painter.set_latent_shape(size, True)
+    D = disc_mod.OmniDiscriminator(opts)
+    vggloss = losses_mod.VGGLoss("cpu")
+    g_shapes = [(k, tuple(v.shape)) for k, v in G.painter.state_dict().items()]
+    d_shapes = [(k, tuple(v.shape)) for k, v in D.state_dict().items()]
+    v_shapes = [(k, tuple(v.shape)) for k, v in KeyHolder().state_dict().items()]
+    G.painter.load_state_dict(fill_state_dict(g_shapes, seed=11), strict=True)
+    D.load_state_dict(fill_state_dict(d_shapes, seed=12), strict=True)
+    vggloss.vgg.load_state_dict(fill_state_dict(v_shapes, seed=13), strict=True)
+    g_opt = optim_mod.ExtraAdam(G.parameters(), lr=opts.gen.opt.lr.default, betas=(opts.gen.opt.beta1, 0.999))
+    d_opt = optim_mod.ExtraAdam(D.parameters(), lr=opts.dis.opt.lr.default, betas=(opts.dis.opt.beta1, 0.999))
+    gan = losses_mod.GANLoss(use_lsgan=False, soft_shift=0.0, flip_prob=0.0)
+    featmatch = losses_mod.FeatMatchLoss()
+    x, m, _ = synth_inputs(batch, size, seed=5)
+    lam = opts.train.lambdas.G.p
+    logs = []
+    for it in range(4):
+        global_step = it // 2
+        if it % 2 == 0:  # update_G
+            for p in D.parameters():
+                p.requires_grad_(False) if p.requires_grad else None
+            tutils_mod.zero_grad(G)
+            fake = G.paint(m, x)
+            l_vgg = vggloss(vgg_preprocess_cpu(fake * m), vgg_preprocess_cpu(x * m)) * lam.vgg
+            real_fake = torch.cat([torch.cat([m, x], 1), torch.cat([m, fake], 1)], 0)
+            real_d, fake_d = tutils_mod.divide_pred(D["p"](real_fake))
+            l_gan = gan(fake_d, True, False)
+            l_feat = featmatch(real_d, fake_d) * lam.featmatch
+            (l_vgg + l_gan + l_feat).backward()
+            (g_opt.extrapolation if global_step % 2 == 0 else g_opt.step)()
+            for n_, p in D.named_parameters():
+                if not n_.endswith(("weight_u", "weight_v")):
+                    p.requires_grad_(True)
+            logs += [float(l_vgg), float(l_gan), float(l_feat)]
+        else:            # update_D
+            tutils_mod.zero_grad(D)
+            with torch.no_grad():
+                fake = G.paint(m, x)
+            real_fake = torch.cat([torch.cat([m, x], 1), torch.cat([m, fake.detach()], 1)], 0)
+            real_d, fake_d = tutils_mod.divide_pred(D["p"](real_fake))
+            l_d = gan(fake_d, False, True) + gan(real_d, True, True)
+            l_d.backward()
+            (d_opt.extrapolation if global_step % 2 == 0 else d_opt.step)()
+            logs += [float(l_d)]
+    gsd, dsd = G.painter.state_dict(), D.state_dict()
+    arrays = {"logs": np.array(logs, dtype=np.float64),
+              "G::conv_img.weight": gsd["conv_img.weight"].numpy(), "G::fc.bias": gsd["fc.bias"].numpy(),
+              "G::head_0.conv_0.module.weight_bar": gsd["head_0.conv_0.module.weight_bar"].numpy(),
+              "G::final_spade.norm_1.mlp_gamma.weight": gsd["final_spade.norm_1.mlp_gamma.weight"].numpy(),
+              "D::p.discriminator_0.model0.0.module.weight_bar": dsd["p.discriminator_0.model0.0.module.weight_bar"].numpy(),
+              "D::p.discriminator_1.model3.0.module.bias": dsd["p.discriminator_1.model3.0.module.bias"].numpy()}
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+    meta = {"case": name, "latent_dim": latent, "spade_n_up": n_up, "ndf": ndf, "n_layers": n_layers, "num_D": num_d,
+            "batch": batch, "size": size, "seeds": {"G": 11, "D": 12, "vgg": 13, "inputs": 5},
+            "g_shapes": [[k, list(s)] for k, s in g_shapes], "d_shapes": [[k, list(s)] for k, s in d_shapes],
+            "v_shapes": [[k, list(s)] for k, s in v_shapes],
+            "log_names": ["G0.vgg", "G0.gan", "G0.featmatch", "D0", "G1.vgg", "G1.gan", "G1.featmatch", "D1"],
+            "reference": "cc-ai/climategan @ /root/reference (generator, discriminator, losses, tutils, optim modules)",
+            "torch": torch.__version__}
+    with open(os.path.join(HERE, name + ".json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print(name, "logs", [round(v, 5) for v in logs], "npz bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
+
+
 if __name__ == "__main__":
     if not refshim.available():
         sys.exit("reference tree not available; goldens can only be regenerated in the build container")
     for name, cfg in CASES.items():
         run_case(name, *cfg)
     run_disc_case()
+    run_step_case()

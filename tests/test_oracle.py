@@ -105,3 +105,59 @@ def test_discriminator_oracle_matches_golden():
     assert rel_max(fake.grad, torch.from_numpy(g["fake_grad"])) < 1e-4
     norms = np.array([float(sd[k[2:]].grad.norm()) for k in meta["grad_keys"]])
     np.testing.assert_allclose(norms, g["grad_norms"], rtol=5e-4, atol=1e-7)
+
+
+def test_trainer_oracle_matches_reference_step_golden():
+    """oracle/trainer_oracle.py (painter G/D losses + ExtraAdam) vs 4 optimiser steps run with the reference's modules."""
+    import json
+    import os
+
+    from oracle import painter_oracle as po
+    from oracle import trainer_oracle as to
+    from oracle.painter_oracle import SNState
+    from tests.golden.weights import fill_state_dict, synth_inputs
+    from tests.helpers import GOLDEN
+
+    meta = json.load(open(os.path.join(GOLDEN, "painter_step.json")))
+    g = dict(np.load(os.path.join(GOLDEN, "painter_step.npz")))
+
+    def mk(shapes, seed):
+        sd = fill_state_dict([(k, tuple(s)) for k, s in shapes], seed)
+        return {k: v.clone().requires_grad_(not k.endswith(("_u", "_v"))) for k, v in sd.items()}
+
+    gsd, dsd_full, vsd = mk(meta["g_shapes"], 11), mk(meta["d_shapes"], 12), mk(meta["v_shapes"], 13)
+    for v in vsd.values():
+        v.requires_grad_(False)
+    dsd = {k[2:]: v for k, v in dsd_full.items()}
+    x, m, _ = synth_inputs(meta["batch"], meta["size"], 5)
+    z = meta["size"] // 2 ** meta["spade_n_up"]
+    g_opt = to.ExtraAdam([v for v in gsd.values() if v.requires_grad], lr=0.00005, betas=(0.9, 0.999))
+    d_opt = to.ExtraAdam([v for v in dsd.values() if v.requires_grad], lr=0.00002, betas=(0.5, 0.999))
+    g_sn, d_sn = SNState(gsd), SNState(dsd)
+    logs = []
+    for it in range(4):
+        gs = it // 2
+        if it % 2 == 0:
+            for v in gsd.values():
+                v.grad = None
+            for v in dsd.values():
+                v.grad = None
+            loss, terms = to.painter_g_loss(gsd, dsd, vsd, x, m, z, g_sn=g_sn, d_sn=d_sn)
+            loss.backward()
+            for v in dsd.values():
+                v.grad = None  # D is frozen during update_G
+            (g_opt.extrapolation if gs % 2 == 0 else g_opt.step)()
+            logs += [float(terms["vgg"]), float(terms["gan"]), float(terms["featmatch"])]
+        else:
+            for v in dsd.values():
+                v.grad = None
+            ld = to.painter_d_loss(gsd, dsd, x, m, z, g_sn=g_sn, d_sn=d_sn)
+            ld.backward()
+            (d_opt.extrapolation if gs % 2 == 0 else d_opt.step)()
+            logs.append(float(ld))
+    np.testing.assert_allclose(np.array(logs), g["logs"], rtol=2e-5)
+    for k, v in g.items():
+        if k.startswith("G::"):
+            assert rel_max(gsd[k[3:]], torch.from_numpy(v)) < 1e-5, k
+        if k.startswith("D::"):
+            assert rel_max(dsd_full[k[3:]], torch.from_numpy(v)) < 1e-5, k
