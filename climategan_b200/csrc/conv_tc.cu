@@ -196,6 +196,13 @@ struct TcParams {
   int act;
   float slope;
   int dact;                    // derivative mask (dgrad) from mask_src
+  // streaming kernel, generalised taps: tap t reads the input at (oy*stride + tap_dy[t], ox*stride + tap_dx[t]) and
+  // uses weight tap tap_w[t]; ntaps <= 64.  Output pixel (oy, ox) of the tile grid is written at
+  // (oy*out_stride + out_off_y, ox*out_stride + out_off_x) of an [n, hfull, wfull, cout_s] tensor — this is how the
+  // stride-s dgrad runs as s*s stride-1 sub-convolutions, one per output parity class.
+  int ntaps;
+  int out_stride, out_off_y, out_off_x, hfull, wfull;
+  short tap_dy[64], tap_dx[64], tap_w[64];
 };
 
 constexpr int EPI_WARPS = 16;                      // 4 per TMEM lane quarter (latency hiding: the epilogue is a long
@@ -268,7 +275,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
   const int tn_i = row >> (p.tw_log + p.th_log);
   const int ox = ox0 + tw_i, oy = oy0 + th_i, img = n0 + tn_i;
   const bool pix_ok = (ox < p.wout) && (oy < p.hout) && (img < p.n);
-  const long long pix = ((long long)img * p.hout + oy) * p.wout + ox;
+  const long long pix = ((long long)img * p.hfull + (oy * p.out_stride + p.out_off_y)) * p.wfull + (ox * p.out_stride + p.out_off_x);
   const bool mask_late = (mask_src != nullptr) && (p.dact == CGB_ACT_RELU);  // 0/1 mask: exact on bf16
   const bool mask_early = (mask_src != nullptr) && !mask_late;
   const float neg = p.act == CGB_ACT_NONE ? 1.f : (p.act == CGB_ACT_RELU ? 0.f : p.slope);
@@ -307,7 +314,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
       const int tn2 = r2 >> (p.tw_log + p.th_log);
       const int ox2 = ox0 + tw2, oy2 = oy0 + th2, img2 = n0 + tn2;
       if (ox2 >= p.wout || oy2 >= p.hout || img2 >= p.n) continue;
-      const long long off = (((long long)img2 * p.hout + oy2) * p.wout + ox2) * p.cout_s + ch;
+      const long long off = (((long long)img2 * p.hfull + (oy2 * p.out_stride + p.out_off_y)) * p.wfull +
+                             (ox2 * p.out_stride + p.out_off_x)) * p.cout_s + ch;
       uint4 val = *reinterpret_cast<const uint4*>(staging_gen + (size_t)r2 * p.stage_pitch + (size_t)c * 16);
       if (mask_late) {  // relu derivative: keep where the forward output was > 0 (packed bf16x2 compare + multiply)
         const uint4 mk = *reinterpret_cast<const uint4*>(mask_src + off);
@@ -348,7 +356,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int taps = p.kh * p.kw;
+  const int taps = p.ntaps;
   const int iters = taps * p.kblocks;
   const int tn_log = 7 - p.tw_log - p.th_log;
 
@@ -385,15 +393,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ox0 = tx << p.tw_log, oy0 = ty << p.th_log, n0 = tn << tn_log;
         const int cn0 = nt * p.bn;
         for (int tap = 0; tap < taps; ++tap) {
-          const int dy = tap / p.kw, dx = tap - dy * p.kw;
-          const int cx = ox0 * p.stride - p.pad_x + dx * p.dil;
-          const int cy = oy0 * p.stride - p.pad_y + dy * p.dil;
+          const int cx = ox0 * p.stride + p.tap_dx[tap];
+          const int cy = oy0 * p.stride + p.tap_dy[tap];
+          const int wtap = p.tap_w[tap];
           for (int kb = 0; kb < p.kblocks; ++kb) {
             mbar_wait(empty_bar(s), ph ^ 1u);
             const uint32_t a_dst = base + (uint32_t)s * stage_bytes;
             mbar_expect_tx(full_bar(s), stage_bytes);
             tma_load_4d(a_dst, &tmA, full_bar(s), kb * 64, cx, cy, n0);
-            tma_load_3d(a_dst + A_TILE_BYTES, &tmB, full_bar(s), kb * 64, tap, cn0);
+            tma_load_3d(a_dst + A_TILE_BYTES, &tmB, full_bar(s), kb * 64, wtap, cn0);
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
         }
@@ -707,38 +715,91 @@ bool conv_tc_supported(const cgb_conv_desc* d, int which) {
   if (d->dtype != CGB_BF16) return false;
   if (d->pad_mode != CGB_PAD_ZERO && d->pad > 0) return false;
   if (which == 0) return d->stride <= 2;
-  if (which == 1) return d->stride == 1 && d->pad <= d->dil * (d->kh - 1) && d->pad <= d->dil * (d->kw - 1);
+  if (which == 1) {
+    if (d->stride == 1) return d->pad <= d->dil * (d->kh - 1) && d->pad <= d->dil * (d->kw - 1);
+    return d->stride == 2 && d->kh * d->kw <= 64;  // parity-class decomposition
+  }
   return d->stride <= 2 && d->co <= 2048;  // wgrad
+}
+
+// ---- streaming launch with an explicit tap table and output mapping ---------------------------------------------
+struct TapTable {
+  int ntaps;
+  short dy[64], dx[64], w[64];
+};
+
+static int launch_stream(const void* in, const void* w, void* out, int n, int hin, int win, int cin_s, int hgrid, int wgrid,
+                         int cout_s, int wtaps_total, const TapTable& tt, int in_stride, int out_stride, int out_off_y,
+                         int out_off_x, int hfull, int wfull, int act, float slope, const float* bias,
+                         const void* residual, int dact, const void* mask_src, cudaStream_t st) {
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = n; p.hout = hgrid; p.wout = wgrid; p.cout_s = cout_s; p.cin_s = cin_s;
+  p.stride = in_stride;
+  p.kblocks = (cin_s + 63) / 64;
+  p.act = act; p.slope = slope; p.dact = dact;
+  p.ntaps = tt.ntaps;
+  for (int t = 0; t < tt.ntaps; ++t) { p.tap_dy[t] = tt.dy[t]; p.tap_dx[t] = tt.dx[t]; p.tap_w[t] = tt.w[t]; }
+  p.out_stride = out_stride; p.out_off_y = out_off_y; p.out_off_x = out_off_x; p.hfull = hfull; p.wfull = wfull;
+  pick_tile(n, hgrid, wgrid, in_stride, &p.tw_log, &p.th_log);
+  const int tn_log = 7 - p.tw_log - p.th_log;
+  p.tiles_x = (wgrid + (1 << p.tw_log) - 1) >> p.tw_log;
+  p.tiles_y = (hgrid + (1 << p.th_log) - 1) >> p.th_log;
+  const int tiles_n = (n + (1 << tn_log) - 1) >> tn_log;
+  p.bn = pick_bn(cout_s);
+  p.n_tiles = (cout_s + p.bn - 1) / p.bn;
+  p.total_tiles = p.tiles_x * p.tiles_y * tiles_n * p.n_tiles;
+  p.stage_pitch = p.bn * 2 + 16;
+  const int staging_bytes = 128 * p.stage_pitch;
+  int cols = 32;
+  while (cols < 2 * p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  const int stage_bytes = A_TILE_BYTES + p.bn * 128;
+  int stages = (int)((SMEM_LIMIT - 1024 - 256 - staging_bytes) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)cin_s, (cuuint64_t)win, (cuuint64_t)hin, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)cin_s * 2, (cuuint64_t)win * cin_s * 2, (cuuint64_t)hin * win * cin_s * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)((1 << p.tw_log) * in_stride), (cuuint32_t)((1 << p.th_log) * in_stride),
+                         (cuuint32_t)(1 << tn_log)};
+    cuuint32_t estr[4] = {1, (cuuint32_t)in_stride, (cuuint32_t)in_stride, 1};
+    if (!encode_map(&tmA, in, 4, dims, strides, box, estr, "activations")) return CGB_LAUNCH_FAILURE;
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)cin_s, (cuuint64_t)wtaps_total, (cuuint64_t)cout_s};
+    cuuint64_t strides[2] = {(cuuint64_t)cin_s * 2, (cuuint64_t)wtaps_total * cin_s * 2};
+    cuuint32_t box[3] = {64, 1, (cuuint32_t)p.bn};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (!encode_map(&tmB, w, 3, dims, strides, box, estr, "weights")) return CGB_LAUNCH_FAILURE;
+  }
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+  });
+  const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 16 * stages + 48 + 1024;
+  dim3 grid((unsigned)(p.total_tiles < num_sms() ? p.total_tiles : num_sms()));
+  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p, bias, (const __nv_bfloat16*)residual,
+                                                 (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out);
+  return after_launch("conv_tc");
 }
 
 // Launch an fprop on (in -> out).  in: [n,hin,win,cin_s], w: [cout_s][taps][cin_s], out: [n,hout,wout,cout_s]
 static int launch_fprop(const void* in, const void* w, void* out, int n, int hin, int win, int cin_s, int hout, int wout,
                         int cout_s, int kh, int kw, int stride, int dil, int pad_y, int pad_x, int act, float slope,
                         const float* bias, const void* residual, int dact, const void* mask_src, cudaStream_t st) {
-  TcParams p;
-  memset(&p, 0, sizeof(p));
-  p.n = n; p.hout = hout; p.wout = wout; p.cout_s = cout_s; p.cin_s = cin_s;
-  p.kh = kh; p.kw = kw; p.dil = dil; p.stride = stride; p.pad_y = pad_y; p.pad_x = pad_x;
-  p.kblocks = (cin_s + 63) / 64;
-  p.act = act; p.slope = slope; p.dact = dact;
   const int taps = kh * kw;
-  static std::once_flag attr_once;
-  std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
-    cudaFuncSetAttribute(conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
-  });
-
-  // ---- streaming configuration (always valid)
+  // ---- traffic estimate of the streaming configuration
   int s_tw_log, s_th_log;
   pick_tile(n, hout, wout, stride, &s_tw_log, &s_th_log);
   const int s_tn_log = 7 - s_tw_log - s_th_log;
-  const int s_tiles_x = (wout + (1 << s_tw_log) - 1) >> s_tw_log;
-  const int s_tiles_y = (hout + (1 << s_th_log) - 1) >> s_th_log;
-  const int s_tiles_n = (n + (1 << s_tn_log) - 1) >> s_tn_log;
+  const int kblocks = (cin_s + 63) / 64;
   const int s_bn = pick_bn(cout_s);
-  const int s_ntiles = (cout_s + s_bn - 1) / s_bn;
-  const double stream_bytes = (double)s_tiles_x * s_tiles_y * s_tiles_n * s_ntiles * taps * p.kblocks * (A_TILE_BYTES + s_bn * 128.0);
-
+  const double stream_bytes = (double)((wout + (1 << s_tw_log) - 1) >> s_tw_log) * ((hout + (1 << s_th_log) - 1) >> s_th_log) *
+                              ((n + (1 << s_tn_log) - 1) >> s_tn_log) * ((cout_s + s_bn - 1) / s_bn) * taps * kblocks *
+                              (A_TILE_BYTES + s_bn * 128.0);
   // ---- weight-stationary halo configuration (stride-1 k>1 convs on large maps)
   bool use_ws = false;
   int ws_bn = 0, ws_ntiles = 0, ws_stages = 0;
@@ -748,47 +809,61 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
     for (int nt = 1; nt <= 8 && !use_ws; ++nt) {
       int bn = ((cout_s + nt - 1) / nt + 15) / 16 * 16;
       if (bn > 256) continue;
-      const size_t wb = (size_t)p.kblocks * taps * bn * 128;
+      const size_t wb = (size_t)kblocks * taps * bn * 128;
       const size_t fixed = wb + 128 * (size_t)(bn * 2 + 16) + 1024 + 256;
       if (fixed + 2 * (size_t)a_stage > SMEM_LIMIT) continue;
       int stg = (int)((SMEM_LIMIT - fixed) / a_stage);
       if (stg > 6) stg = 6;
-      const double ws_bytes = (double)((wout + 7) / 8) * ((hout + 15) / 16) * n * nt * p.kblocks * (double)(twh * thh * 128);
+      const double ws_bytes = (double)((wout + 7) / 8) * ((hout + 15) / 16) * n * nt * kblocks * (double)(twh * thh * 128);
       if (ws_bytes < 0.8 * stream_bytes) {
         use_ws = true; ws_bn = bn; ws_ntiles = nt; ws_stages = stg;
       }
       break;  // the smallest feasible n-split is the cheapest in activation re-reads
     }
   }
-
-  CUtensorMap tmA, tmB;
-  if (use_ws) {
-    p.tw_log = 3; p.th_log = 4;
-    p.tiles_x = (wout + 7) / 8; p.tiles_y = (hout + 15) / 16;
-    p.pix_tiles = p.tiles_x * p.tiles_y * n;
-    p.bn = ws_bn; p.n_tiles = ws_ntiles; p.stages = ws_stages;
-    p.twh = twh; p.thh = thh; p.a_stage_bytes = a_stage;
-  } else {
-    p.tw_log = s_tw_log; p.th_log = s_th_log; p.tiles_x = s_tiles_x; p.tiles_y = s_tiles_y;
-    p.bn = s_bn; p.n_tiles = s_ntiles;
-    p.total_tiles = s_tiles_x * s_tiles_y * s_tiles_n * s_ntiles;
+  if (!use_ws) {
+    if (taps > 64) {
+      set_error("tcgen05 engine: more than 64 filter taps");
+      return CGB_UNSUPPORTED;
+    }
+    TapTable tt;
+    tt.ntaps = taps;
+    for (int t = 0; t < taps; ++t) {
+      tt.dy[t] = (short)((t / kw) * dil - pad_y);
+      tt.dx[t] = (short)((t % kw) * dil - pad_x);
+      tt.w[t] = (short)t;
+    }
+    return launch_stream(in, w, out, n, hin, win, cin_s, hout, wout, cout_s, taps, tt, stride, 1, 0, 0, hout, wout, act, slope,
+                         bias, residual, dact, mask_src, st);
   }
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = n; p.hout = hout; p.wout = wout; p.cout_s = cout_s; p.cin_s = cin_s;
+  p.kh = kh; p.kw = kw; p.dil = dil; p.stride = stride; p.pad_y = pad_y; p.pad_x = pad_x;
+  p.kblocks = kblocks;
+  p.act = act; p.slope = slope; p.dact = dact;
+  p.out_stride = 1; p.hfull = hout; p.wfull = wout;
+  static std::once_flag attr_once;
+  std::call_once(attr_once, [] {
+    cudaFuncSetAttribute(conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+  });
+  p.tw_log = 3; p.th_log = 4;
+  p.tiles_x = (wout + 7) / 8; p.tiles_y = (hout + 15) / 16;
+  p.pix_tiles = p.tiles_x * p.tiles_y * n;
+  p.bn = ws_bn; p.n_tiles = ws_ntiles; p.stages = ws_stages;
+  p.twh = twh; p.thh = thh; p.a_stage_bytes = a_stage;
   p.stage_pitch = p.bn * 2 + 16;
   const int staging_bytes = 128 * p.stage_pitch;
   int cols = 32;
   while (cols < 2 * p.bn) cols <<= 1;
   p.tmem_cols = cols;
+  CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)cin_s, (cuuint64_t)win, (cuuint64_t)hin, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)cin_s * 2, (cuuint64_t)win * cin_s * 2, (cuuint64_t)hin * win * cin_s * 2};
-    cuuint32_t box[4];
-    if (use_ws) {
-      box[0] = 64; box[1] = (cuuint32_t)twh; box[2] = (cuuint32_t)thh; box[3] = 1;
-    } else {
-      box[0] = 64; box[1] = (cuuint32_t)((1 << p.tw_log) * stride); box[2] = (cuuint32_t)((1 << p.th_log) * stride);
-      box[3] = (cuuint32_t)(1 << s_tn_log);
-    }
-    cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)twh, (cuuint32_t)thh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
     if (!encode_map(&tmA, in, 4, dims, strides, box, estr, "activations")) return CGB_LAUNCH_FAILURE;
   }
   {
@@ -798,24 +873,12 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
     cuuint32_t estr[3] = {1, 1, 1};
     if (!encode_map(&tmB, w, 3, dims, strides, box, estr, "weights")) return CGB_LAUNCH_FAILURE;
   }
-  if (use_ws) {
-    const size_t smem = (size_t)p.kblocks * taps * p.bn * 128 + (size_t)p.stages * a_stage + staging_bytes + 16 * p.stages + 64 + 1024;
-    int ctas = num_sms() / p.n_tiles * p.n_tiles;
-    if (ctas > p.pix_tiles * p.n_tiles) ctas = p.pix_tiles * p.n_tiles;
-    conv_tc_ws_kernel<<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, p, bias, (const __nv_bfloat16*)residual,
-                                                      (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out);
-    return after_launch("conv_tc_ws");
-  }
-  const int stage_bytes = A_TILE_BYTES + p.bn * 128;
-  int stages = (int)((SMEM_LIMIT - 1024 - 256 - staging_bytes) / stage_bytes);
-  if (stages > 8) stages = 8;
-  if (stages < 2) stages = 2;
-  p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 16 * stages + 48 + 1024;
-  dim3 grid((unsigned)(p.total_tiles < num_sms() ? p.total_tiles : num_sms()));
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p, bias, (const __nv_bfloat16*)residual,
-                                                 (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out);
-  return after_launch("conv_tc");
+  const size_t smem = (size_t)p.kblocks * taps * p.bn * 128 + (size_t)p.stages * a_stage + staging_bytes + 16 * p.stages + 64 + 1024;
+  int ctas = num_sms() / p.n_tiles * p.n_tiles;
+  if (ctas > p.pix_tiles * p.n_tiles) ctas = p.pix_tiles * p.n_tiles;
+  conv_tc_ws_kernel<<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, p, bias, (const __nv_bfloat16*)residual,
+                                                    (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out);
+  return after_launch("conv_tc_ws");
 }
 
 int conv_tc_fwd(const cgb_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
@@ -827,6 +890,53 @@ int conv_tc_fwd(const cgb_conv_desc* d, const void* x, const void* w, const floa
 // wt: dgrad packing [ci][taps][co] with the taps reversed (cgb_conv2d_pack_dgrad_weight)
 int conv_tc_dgrad(const cgb_conv_desc* d, const void* gy, const void* wt, int dact, const void* mask_src, void* gx,
                   cudaStream_t st) {
+  if (d->stride > 1) {
+    // stride-s dgrad = s*s stride-1 sub-convolutions over gy, one per parity class (ry, rx) of the input pixel:
+    //   gx[s*j+ry, s*i+rx] = sum over taps (dy,dx) with (ry+pad-dy) % s == 0 of gy[j + (ry+pad-dy)/s, ...] * W[dy][dx]
+    // each written at the strided positions of gx by the epilogue.  wt is the dgrad packing [ci][T-1-t][co].
+    const int s_ = d->stride, T = d->kh * d->kw;
+    bool need_zero = false;
+    for (int ry = 0; ry < s_; ++ry)
+      for (int rx = 0; rx < s_; ++rx) {
+        TapTable tt;
+        tt.ntaps = 0;
+        for (int dy = 0; dy < d->kh; ++dy) {
+          if ((ry + d->pad - dy * d->dil) % s_ != 0) continue;
+          for (int dx = 0; dx < d->kw; ++dx) {
+            if ((rx + d->pad - dx * d->dil) % s_ != 0) continue;
+            const int t = tt.ntaps++;
+            // floor division is exact here (divisible); C division of a negative multiple of s is exact too
+            tt.dy[t] = (short)((ry + d->pad - dy * d->dil) / s_);
+            tt.dx[t] = (short)((rx + d->pad - dx * d->dil) / s_);
+            tt.w[t] = (short)(T - 1 - (dy * d->kw + dx));
+          }
+        }
+        if (tt.ntaps == 0) need_zero = true;
+      }
+    if (need_zero)
+      cudaMemsetAsync(gx, 0, (size_t)d->n * d->hi * d->wi * d->ci * 2, st);
+    for (int ry = 0; ry < s_; ++ry)
+      for (int rx = 0; rx < s_; ++rx) {
+        TapTable tt;
+        tt.ntaps = 0;
+        for (int dy = 0; dy < d->kh; ++dy) {
+          if ((ry + d->pad - dy * d->dil) % s_ != 0) continue;
+          for (int dx = 0; dx < d->kw; ++dx) {
+            if ((rx + d->pad - dx * d->dil) % s_ != 0) continue;
+            const int t = tt.ntaps++;
+            tt.dy[t] = (short)((ry + d->pad - dy * d->dil) / s_);
+            tt.dx[t] = (short)((rx + d->pad - dx * d->dil) / s_);
+            tt.w[t] = (short)(T - 1 - (dy * d->kw + dx));
+          }
+        }
+        const int hc = (d->hi - ry + s_ - 1) / s_, wc = (d->wi - rx + s_ - 1) / s_;
+        if (tt.ntaps == 0 || hc <= 0 || wc <= 0) continue;
+        int r = launch_stream(gy, wt, gx, d->n, d->ho, d->wo, d->co, hc, wc, d->ci, T, tt, 1, s_, ry, rx, d->hi, d->wi,
+                              CGB_ACT_NONE, d->slope, nullptr, nullptr, dact, mask_src, st);
+        if (r) return r;
+      }
+    return CGB_OK;
+  }
   return launch_fprop(gy, wt, gx, d->n, d->ho, d->wo, d->co, d->hi, d->wi, d->ci, d->kh, d->kw, 1, d->dil,
                       d->dil * (d->kh - 1) - d->pad, d->dil * (d->kw - 1) - d->pad, CGB_ACT_NONE, d->slope, nullptr, nullptr,
                       dact, mask_src, st);

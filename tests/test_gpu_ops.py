@@ -45,7 +45,7 @@ CONV_CASES = [
 @pytest.mark.parametrize("engine", ENGINES)
 def test_conv_fwd_bwd(cuda, case, dtype, engine):
     n, ci, co, h, w, k, stride, dil, pad, pad_mode, act = case
-    torch.manual_seed(hash(case) % 1000)
+    torch.manual_seed(CONV_CASES.index(case) * 7 + 1)  # deterministic (hash() of a tuple with str is salted per process)
     x = _q(torch.randn(n, ci, h, w), dtype)
     wt = _q(torch.randn(co, ci, k, k) / (ci * k * k) ** 0.5, dtype)
     b = torch.randn(co) * 0.1
