@@ -37,7 +37,7 @@ class ConvDesc(C.Structure):
         ("kh", C.c_int32), ("kw", C.c_int32),
         ("stride", C.c_int32), ("dil", C.c_int32), ("pad", C.c_int32),
         ("pad_mode", C.c_int32), ("dtype", C.c_int32), ("act", C.c_int32),
-        ("slope", C.c_float), ("engine", C.c_int32),
+        ("slope", C.c_float), ("engine", C.c_int32), ("res_before_act", C.c_int32),
     ]
 
 
@@ -98,6 +98,12 @@ SIGNATURES = {
     "cgb_maxpool2_fwd": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_maxpool2_bwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_extra_adam": ([_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _I, _I, _P], C.c_int),
+    "cgb_maxpool3s2_ceil_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_resize_bilinear_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_resize_bicubic_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_channel_mean": ([_P, _P, _I, _L, _I, _I, _P], C.c_int),
+    "cgb_mul": ([_P, _P, _P, _I, _L, _P], C.c_int),
+    "cgb_make_m_cond": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_resize_nearest_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_upsample_nearest_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_im2col": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),

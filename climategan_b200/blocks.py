@@ -52,8 +52,11 @@ class Conv2dBlock(nn.Module):
             use_spectral_norm = True
         if norm in ("spectral", "none"):
             self.norm = None
+        elif norm == "batch":
+            self.norm = nn.BatchNorm2d(output_dim)  # inference only: folded into the conv (forward_infer)
         else:
             raise NotImplementedError("Conv2dBlock norm '{}' is not built yet".format(norm))
+        self.kernel_size = kernel_size
         if activation not in _ACTS:
             raise NotImplementedError("Unsupported activation: {}".format(activation))
         self.act, self.slope = _ACTS[activation]
@@ -63,9 +66,28 @@ class Conv2dBlock(nn.Module):
         self.conv = SpectralNorm(conv) if (norm == "spectral" or use_spectral_norm) else conv
 
     def forward(self, x, residual=None):
+        if self.norm is not None:
+            raise NotImplementedError("Conv2dBlock(norm='batch') is built for inference only: use forward_infer")
         w, b = conv_weight_bias(self.conv)
         return ops.conv2d(x, w, b, residual, stride=self.stride, dil=self.dilation, pad=self.padding,
                           pad_mode=self.pad_mode, act=self.act, slope=self.slope)
+
+    def forward_infer(self, x, residual=None):
+        """Inference forward (no autograd tape): pad -> conv [-> eval BatchNorm folded] -> activation [+ residual]."""
+        import torch
+
+        with torch.no_grad():
+            w, b = conv_weight_bias(self.conv)  # runs the spectral-norm power iteration, as the reference does in eval
+            if self.norm is not None:
+                scale = self.norm.weight / torch.sqrt(self.norm.running_var + self.norm.eps)
+                bb = self.norm.bias - self.norm.running_mean * scale
+                if b is not None:
+                    bb = bb + b * scale
+                w, b = w * scale.view(-1, 1, 1, 1), bb
+            wp = ops.pack_weight(w, x.dtype, cis=x.shape[-1])
+            return ops.conv2d_infer(x, wp, ops.pad_bias(b, wp.shape[0]), residual, k=self.kernel_size, stride=self.stride,
+                                    dil=self.dilation, pad=self.padding, pad_mode=self.pad_mode, act=self.act,
+                                    slope=self.slope)
 
 
 class SPADEResnetBlock(nn.Module):
@@ -126,3 +148,75 @@ class SPADEResnetBlock(nn.Module):
         if self.last_activation == "lrelu":
             out = ops.activation(out, _lib.ACT_LRELU, 0.2)
         return out
+
+
+class ResBlock(nn.Module):
+    """``climategan.blocks.ResBlock`` (blocks.py:174-197): two 3x3 Conv2dBlocks + in-place residual (fused in the 2nd
+    conv's epilogue)."""
+
+    def __init__(self, dim, norm="in", activation="relu", pad_type="zero"):
+        super().__init__()
+        self.dim, self.norm, self.activation = dim, norm, activation
+        self.model = nn.Sequential(
+            Conv2dBlock(dim, dim, 3, 1, 1, norm=norm, activation=activation, pad_type=pad_type),
+            Conv2dBlock(dim, dim, 3, 1, 1, norm=norm, activation="none", pad_type=pad_type),
+        )
+
+    def forward_infer(self, x):
+        return self.model[1].forward_infer(self.model[0].forward_infer(x), residual=x)
+
+
+class ResBlocks(nn.Module):
+    """``climategan.blocks.ResBlocks`` (blocks.py:153-171)."""
+
+    def __init__(self, num_blocks, dim, norm="in", activation="relu", pad_type="zero"):
+        super().__init__()
+        self.model = nn.Sequential(*[ResBlock(dim, norm=norm, activation=activation, pad_type=pad_type)
+                                     for _ in range(num_blocks)])
+
+    def forward_infer(self, x):
+        for blk in self.model:
+            x = blk.forward_infer(x)
+        return x
+
+
+class BaseDecoder(nn.Module):
+    """``climategan.blocks.BaseDecoder`` (blocks.py:206-318) without the v3 low-level-feature branch: proj 1x1 ->
+    ResBlocks -> n_upsample x [nearest x2, 3x3 halving conv] -> 3x3 output conv."""
+
+    def __init__(self, n_upsample=4, n_res=4, input_dim=2048, proj_dim=64, output_dim=3, norm="batch", activ="relu",
+                 pad_type="zero", output_activ="tanh", low_level_feats_dim=-1, use_dada=False):
+        super().__init__()
+        if low_level_feats_dim > 0:
+            raise NotImplementedError("BaseDecoder low-level features (deeplabv3 encoder) are not built")
+        self.low_level_feats_dim = low_level_feats_dim
+        self.use_dada = use_dada
+        self.low_level_conv = None
+        if proj_dim != -1:
+            self.proj_conv = Conv2dBlock(input_dim, proj_dim, 1, 1, 0, norm=norm, activation=activ)
+        else:
+            self.proj_conv = None
+            proj_dim = input_dim
+        model = [ResBlocks(n_res, proj_dim, norm, activ, pad_type=pad_type)]
+        dim = proj_dim
+        for _ in range(n_upsample):
+            model += [InterpolateNearest2d(scale_factor=2),
+                      Conv2dBlock(input_dim=dim, output_dim=dim // 2, kernel_size=3, stride=1, padding=1, pad_type=pad_type,
+                                  norm=norm, activation=activ)]
+            dim //= 2
+        model += [Conv2dBlock(input_dim=dim, output_dim=output_dim, kernel_size=3, stride=1, padding=1, pad_type=pad_type,
+                              norm="none", activation=output_activ)]
+        self.model = nn.Sequential(*model)
+        self.output_dim = output_dim
+
+    def forward_storage(self, z, cond=None, z_depth=None):
+        if z_depth is not None and self.use_dada:
+            z = ops.mul(z, z_depth)
+        if self.proj_conv is not None:
+            z = self.proj_conv.forward_infer(z)
+        for m in self.model:
+            if isinstance(m, InterpolateNearest2d):
+                z = m(z)
+            else:
+                z = m.forward_infer(z)
+        return z

@@ -142,7 +142,8 @@ extern "C" int cgb_conv2d_fwd(const cgb_conv_desc* d, const void* x, const void*
   int s = validate(d, "conv2d_fwd");
   if (s) return s;
   CGB_REQUIRE(x && w && y, "conv2d_fwd: null pointer");
-  CGB_REQUIRE(!(residual && d->act != CGB_ACT_NONE), "conv2d_fwd: residual requires act=none");
+  CGB_REQUIRE(!(residual && d->act != CGB_ACT_NONE && !d->res_before_act),
+              "conv2d_fwd: residual after an activation requires act=none (set res_before_act for act(conv+residual))");
   bool tc = false;
   s = pick_engine(d, 0, "conv2d_fwd", &tc);
   if (s) return s;

@@ -16,6 +16,7 @@ struct ConvP {
   int act;
   float slope;
   int dact;
+  int res_before_act;
 };
 
 static ConvP make_p(const cgb_conv_desc* d) {
@@ -23,7 +24,7 @@ static ConvP make_p(const cgb_conv_desc* d) {
   p.n = d->n; p.hi = d->hi; p.wi = d->wi; p.ci = d->ci;
   p.ho = d->ho; p.wo = d->wo; p.co = d->co;
   p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.dil = d->dil; p.pad = d->pad;
-  p.pad_mode = d->pad_mode; p.act = d->act; p.slope = d->slope; p.dact = 0;
+  p.pad_mode = d->pad_mode; p.act = d->act; p.slope = d->slope; p.dact = 0; p.res_before_act = d->res_before_act;
   return p;
 }
 
@@ -168,9 +169,13 @@ conv_simt_kernel(ConvP p, const T* __restrict__ A, const T* __restrict__ W,
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] += bias[nn + j];
       }
+      if (residual && p.res_before_act) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] += to_f<T>(residual[off + j]);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] = act_apply(v[j], p.act, p.slope);
-      if (residual) {
+      if (residual && !p.res_before_act) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] += to_f<T>(residual[off + j]);
       }

@@ -196,6 +196,7 @@ struct TcParams {
   int act;
   float slope;
   int dact;                    // derivative mask (dgrad) from mask_src
+  int res_before_act;          // 1: act(acc + bias + residual), 0: act(acc + bias) + residual
   // streaming kernel, generalised taps: tap t reads the input at (oy*stride + tap_dy[t], ox*stride + tap_dx[t]) and
   // uses weight tap tap_w[t]; ntaps <= 64.  Output pixel (oy, ox) of the tile grid is written at
   // (oy*out_stride + out_off_y, ox*out_stride + out_off_x) of an [n, hfull, wfull, cout_s] tensor — this is how the
@@ -236,6 +237,12 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const uint32_t (&r)
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
         v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
       }
+      if (pix_ok && residual && p.res_before_act) {
+        float rr[8];
+        Vec8<__nv_bfloat16>::load(residual + pix * p.cout_s + ch, rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += rr[j];
+      }
       if (p.act == CGB_ACT_NONE) {
       } else if (p.act <= CGB_ACT_LRELU) {  // relu / lrelu (0 <= slope < 1): max(v, v*neg), 2 instructions
 #pragma unroll
@@ -244,7 +251,7 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const uint32_t (&r)
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = act_apply(v[j], p.act, p.slope);
       }
-      if (pix_ok && residual) {
+      if (pix_ok && residual && !p.res_before_act) {
         float rr[8];
         Vec8<__nv_bfloat16>::load(residual + pix * p.cout_s + ch, rr);
 #pragma unroll
@@ -731,9 +738,10 @@ struct TapTable {
 static int launch_stream(const void* in, const void* w, void* out, int n, int hin, int win, int cin_s, int hgrid, int wgrid,
                          int cout_s, int wtaps_total, const TapTable& tt, int in_stride, int out_stride, int out_off_y,
                          int out_off_x, int hfull, int wfull, int act, float slope, const float* bias,
-                         const void* residual, int dact, const void* mask_src, cudaStream_t st) {
+                         const void* residual, int dact, const void* mask_src, cudaStream_t st, int res_before_act = 0) {
   TcParams p;
   memset(&p, 0, sizeof(p));
+  p.res_before_act = res_before_act;
   p.n = n; p.hout = hgrid; p.wout = wgrid; p.cout_s = cout_s; p.cin_s = cin_s;
   p.stride = in_stride;
   p.kblocks = (cin_s + 63) / 64;
@@ -789,7 +797,8 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
 // Launch an fprop on (in -> out).  in: [n,hin,win,cin_s], w: [cout_s][taps][cin_s], out: [n,hout,wout,cout_s]
 static int launch_fprop(const void* in, const void* w, void* out, int n, int hin, int win, int cin_s, int hout, int wout,
                         int cout_s, int kh, int kw, int stride, int dil, int pad_y, int pad_x, int act, float slope,
-                        const float* bias, const void* residual, int dact, const void* mask_src, cudaStream_t st) {
+                        const float* bias, const void* residual, int dact, const void* mask_src, cudaStream_t st,
+                        int res_before_act = 0) {
   const int taps = kh * kw;
   // ---- traffic estimate of the streaming configuration
   int s_tw_log, s_th_log;
@@ -834,11 +843,12 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
       tt.w[t] = (short)t;
     }
     return launch_stream(in, w, out, n, hin, win, cin_s, hout, wout, cout_s, taps, tt, stride, 1, 0, 0, hout, wout, act, slope,
-                         bias, residual, dact, mask_src, st);
+                         bias, residual, dact, mask_src, st, res_before_act);
   }
 
   TcParams p;
   memset(&p, 0, sizeof(p));
+  p.res_before_act = res_before_act;
   p.n = n; p.hout = hout; p.wout = wout; p.cout_s = cout_s; p.cin_s = cin_s;
   p.kh = kh; p.kw = kw; p.dil = dil; p.stride = stride; p.pad_y = pad_y; p.pad_x = pad_x;
   p.kblocks = kblocks;
@@ -884,7 +894,7 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
 int conv_tc_fwd(const cgb_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
                 cudaStream_t st) {
   return launch_fprop(x, w, y, d->n, d->hi, d->wi, d->ci, d->ho, d->wo, d->co, d->kh, d->kw, d->stride, d->dil, d->pad,
-                      d->pad, d->act, d->slope, bias, residual, CGB_ACT_NONE, nullptr, st);
+                      d->pad, d->act, d->slope, bias, residual, CGB_ACT_NONE, nullptr, st, d->res_before_act);
 }
 
 // wt: dgrad packing [ci][taps][co] with the taps reversed (cgb_conv2d_pack_dgrad_weight)

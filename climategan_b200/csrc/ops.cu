@@ -3,6 +3,7 @@
 // All are coalesced, 16/32-byte vectorised over the NHWC channel dimension; reductions use
 // warp shuffles -> shared memory -> one fp64 atomic per (n,c) per CTA.
 #include "common.cuh"
+#include <vector>
 
 namespace cgb {
 
@@ -668,6 +669,216 @@ vgg_pre_bwd_kernel(const T* __restrict__ gy, const float* __restrict__ m, float*
 }
 
 // ---------------------------------------------------------------------------------------------------
+// masker inference helpers (NHWC storage)
+// nn.MaxPool2d(3, stride=2, padding=0, ceil_mode=True) (deeplab/resnetmulti_v2.py:76-78)
+template <typename T>
+__global__ void __launch_bounds__(256)
+maxpool3s2_ceil_kernel(const T* __restrict__ x, T* __restrict__ y, long long total_vec, int hi, int wi, int ho, int wo, int c) {
+  const int cv = c >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int v = (int)(i - pix * cv);
+    const int ox = (int)(pix % wo);
+    const long long t = pix / wo;
+    const int oy = (int)(t % ho);
+    const long long img = t / ho;
+    float best[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) best[j] = -3.4e38f;
+    for (int dy = 0; dy < 3; ++dy)
+      for (int dx = 0; dx < 3; ++dx) {
+        const int sy = oy * 2 + dy, sx = ox * 2 + dx;
+        if (sy >= hi || sx >= wi) continue;
+        float f[8];
+        Vec8<T>::load(x + ((img * hi + sy) * wi + sx) * c + v * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) best[j] = fmaxf(best[j], f[j]);
+      }
+    Vec8<T>::store(y + pix * c + v * 8, best);
+  }
+}
+
+// F.interpolate(mode="bilinear", align_corners=ac) (ATen area_pixel_compute_source_index semantics)
+template <typename T>
+__global__ void __launch_bounds__(256)
+resize_bilinear_kernel(const T* __restrict__ x, T* __restrict__ y, long long total_vec, int hi, int wi, int ho, int wo,
+                       int c, int ac) {
+  const int cv = c >> 3;
+  const float sh = ac ? (ho > 1 ? (float)(hi - 1) / (float)(ho - 1) : 0.f) : (float)hi / (float)ho;
+  const float sw = ac ? (wo > 1 ? (float)(wi - 1) / (float)(wo - 1) : 0.f) : (float)wi / (float)wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int v = (int)(i - pix * cv);
+    const int ox = (int)(pix % wo);
+    const long long t = pix / wo;
+    const int oy = (int)(t % ho);
+    const long long img = t / ho;
+    float fy = ac ? sh * oy : fmaxf(sh * (oy + 0.5f) - 0.5f, 0.f);
+    float fx = ac ? sw * ox : fmaxf(sw * (ox + 0.5f) - 0.5f, 0.f);
+    const int y0 = min((int)fy, hi - 1), x0 = min((int)fx, wi - 1);
+    const int y1 = min(y0 + 1, hi - 1), x1 = min(x0 + 1, wi - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    float a[8], b[8], cc[8], d[8], o[8];
+    const T* base = x + img * hi * wi * c + v * 8;
+    Vec8<T>::load(base + ((long long)y0 * wi + x0) * c, a);
+    Vec8<T>::load(base + ((long long)y0 * wi + x1) * c, b);
+    Vec8<T>::load(base + ((long long)y1 * wi + x0) * c, cc);
+    Vec8<T>::load(base + ((long long)y1 * wi + x1) * c, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o[j] = (1.f - ly) * ((1.f - lx) * a[j] + lx * b[j]) + ly * ((1.f - lx) * cc[j] + lx * d[j]);
+    Vec8<T>::store(y + pix * c + v * 8, o);
+  }
+}
+
+// F.interpolate(mode="bicubic", align_corners=False) (A = -0.75, clamped taps) — depth.py:144-149
+__device__ __forceinline__ void cubic_coeffs(float t, float (&w)[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  w[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  w[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  w[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  w[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+resize_bicubic_kernel(const T* __restrict__ x, T* __restrict__ y, long long total_vec, int hi, int wi, int ho, int wo, int c) {
+  const int cv = c >> 3;
+  const float sh = (float)hi / (float)ho, sw = (float)wi / (float)wo;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int v = (int)(i - pix * cv);
+    const int ox = (int)(pix % wo);
+    const long long t = pix / wo;
+    const int oy = (int)(t % ho);
+    const long long img = t / ho;
+    const float fy = sh * (oy + 0.5f) - 0.5f, fx = sw * (ox + 0.5f) - 0.5f;
+    const int iy = (int)floorf(fy), ix = (int)floorf(fx);
+    float wy[4], wx[4];
+    cubic_coeffs(fy - (float)iy, wy);
+    cubic_coeffs(fx - (float)ix, wx);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    const T* base = x + img * hi * wi * c + v * 8;
+    for (int a = 0; a < 4; ++a) {
+      const int sy = min(max(iy - 1 + a, 0), hi - 1);
+      for (int b = 0; b < 4; ++b) {
+        const int sx = min(max(ix - 1 + b, 0), wi - 1);
+        float f[8];
+        Vec8<T>::load(base + ((long long)sy * wi + sx) * c, f);
+        const float wgt = wy[a] * wx[b];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(wgt, f[j], o[j]);
+      }
+    }
+    Vec8<T>::store(y + pix * c + v * 8, o);
+  }
+}
+
+// torch.mean(x, dim=1, keepdim=True) over the c_logical real channels -> channel 0 of an 8-channel storage tensor
+template <typename T>
+__global__ void __launch_bounds__(256)
+channel_mean_kernel(const T* __restrict__ x, T* __restrict__ y, long long pixels, int cs, int c_logical) {
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int v = 0; v < cs; v += 8) {
+      float f[8];
+      Vec8<T>::load(x + p * cs + v, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += (v + j < c_logical) ? f[j] : 0.f;
+    }
+    float o[8] = {s / (float)c_logical, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    Vec8<T>::store(y + p * 8, o);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+mul_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, long long count) {
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < count; i += (long long)gridDim.x * blockDim.x * 8) {
+    float x[8], z[8], o[8];
+    Vec8<T>::load(a + i, x);
+    Vec8<T>::load(b + i, z);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = x[j] * z[j];
+    Vec8<T>::store(y + i, o);
+  }
+}
+
+// per-sample min / max of channel 0 (tutils.normalize :567-575): mm[n] = {min, max}; caller initialises to {+inf,-inf}
+__device__ __forceinline__ void atomic_min_f(float* addr, float v) {
+  int* ai = reinterpret_cast<int*>(addr);
+  int old = *ai;
+  while (__int_as_float(old) > v) {
+    const int assumed = old;
+    old = atomicCAS(ai, assumed, __float_as_int(v));
+    if (old == assumed) break;
+  }
+}
+__device__ __forceinline__ void atomic_max_f(float* addr, float v) {
+  int* ai = reinterpret_cast<int*>(addr);
+  int old = *ai;
+  while (__int_as_float(old) < v) {
+    const int assumed = old;
+    old = atomicCAS(ai, assumed, __float_as_int(v));
+    if (old == assumed) break;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+minmax_c0_kernel(const T* __restrict__ x, float* __restrict__ mm, int hw, int cs) {
+  const int img = blockIdx.y;
+  float lo = 3.4e38f, hi = -3.4e38f;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += gridDim.x * blockDim.x) {
+    const float v = to_f<T>(x[((long long)img * hw + p) * cs]);
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomic_min_f(mm + 2 * img, lo);
+    atomic_max_f(mm + 2 * img + 1, hi);
+  }
+}
+
+// OmniGenerator.make_m_cond (generator.py:196-230): cat[ normalize(d), softmax(s, dim=1), x resized ] -> 16-ch storage
+//   d [n,hw,8] (channel 0), s [n,hw,ss] with ns classes, xr [n,hw,8] (3 channels, already bilinear-resized), mm per-sample min/max
+template <typename T>
+__global__ void __launch_bounds__(256)
+m_cond_kernel(const T* __restrict__ d, const T* __restrict__ s, const T* __restrict__ xr, const float* __restrict__ mm,
+              T* __restrict__ out, long long pixels, int hw, int ss, int ns, int cs_out) {
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < pixels; p += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(p / hw);
+    const float lo = mm[2 * img], hi = mm[2 * img + 1];
+    float o[24];
+#pragma unroll
+    for (int j = 0; j < 24; ++j) o[j] = 0.f;
+    o[0] = (to_f<T>(d[p * 8]) - lo) / (hi - lo);
+    float mx = -3.4e38f;
+    for (int k = 0; k < ns; ++k) mx = fmaxf(mx, to_f<T>(s[p * ss + k]));
+    float sum = 0.f;
+    for (int k = 0; k < ns; ++k) {
+      const float e = __expf(to_f<T>(s[p * ss + k]) - mx);
+      o[1 + k] = e;
+      sum += e;
+    }
+    const float inv = 1.f / sum;
+    for (int k = 0; k < ns; ++k) o[1 + k] *= inv;
+    if (xr) {
+      for (int k = 0; k < 3; ++k) o[1 + ns + k] = to_f<T>(xr[p * 8 + k]);
+    }
+    for (int k = 0; k < cs_out; ++k) out[p * cs_out + k] = from_f<T>(o[k]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // im2col of a few-channel tensor (the 3-channel SPADE conditioning): y[n,oy,ox, tap*c + ch] = x[n,oy+dy*dil-pad,
 // ox+dx*dil-pad, ch], zero outside; lets SPADE.mlp_shared (norms.py:164-166) run as a K=32 1x1 GEMM on the
 // tensor cores instead of 9 mostly-empty 64-channel K blocks.  One thread per (pixel, 8 output channels).
@@ -1186,4 +1397,73 @@ extern "C" int cgb_vgg_preprocess_bwd(const void* gy, const float* m, float* gx,
   const long long total = (long long)n * hw;
   DISPATCH_T(dtype, vgg_pre_bwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)gy, m, gx, hw, total);)
   return after_launch("vgg_preprocess_bwd");
+}
+
+extern "C" int cgb_maxpool3s2_ceil_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t ho,
+                                       int32_t wo, int32_t c, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y && c % 8 == 0 && c >= 8, "maxpool3s2_ceil_fwd: bad arguments");
+  const long long total = (long long)n * ho * wo * (c / 8);
+  DISPATCH_T(dtype, maxpool3s2_ceil_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total, hi, wi,
+                                                                                                ho, wo, c);)
+  return after_launch("maxpool3s2_ceil");
+}
+
+extern "C" int cgb_resize_bilinear_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t ho,
+                                       int32_t wo, int32_t c, int32_t align_corners, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y && c % 8 == 0 && c >= 8, "resize_bilinear_fwd: bad arguments");
+  const long long total = (long long)n * ho * wo * (c / 8);
+  DISPATCH_T(dtype, resize_bilinear_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total, hi, wi,
+                                                                                                ho, wo, c, align_corners);)
+  return after_launch("resize_bilinear");
+}
+
+extern "C" int cgb_resize_bicubic_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t ho,
+                                      int32_t wo, int32_t c, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y && c % 8 == 0 && c >= 8, "resize_bicubic_fwd: bad arguments");
+  const long long total = (long long)n * ho * wo * (c / 8);
+  DISPATCH_T(dtype, resize_bicubic_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total, hi, wi,
+                                                                                               ho, wo, c);)
+  return after_launch("resize_bicubic");
+}
+
+extern "C" int cgb_channel_mean(const void* x, void* y, int32_t dtype, int64_t pixels, int32_t cs, int32_t c_logical,
+                                void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y && cs % 8 == 0 && c_logical >= 1 && c_logical <= cs, "channel_mean: bad arguments");
+  DISPATCH_T(dtype, channel_mean_kernel<T><<<grid_for(pixels), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, pixels, cs,
+                                                                                              c_logical);)
+  return after_launch("channel_mean");
+}
+
+extern "C" int cgb_mul(const void* a, const void* b, void* y, int32_t dtype, int64_t count, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(a && b && y && count % 8 == 0, "mul: bad arguments");
+  DISPATCH_T(dtype, mul_kernel<T><<<grid_for(count / 8), 256, 0, (cudaStream_t)stream>>>((const T*)a, (const T*)b, (T*)y, count);)
+  return after_launch("mul");
+}
+
+extern "C" int cgb_make_m_cond(const void* d, const void* s, const void* xr, float* mm, void* out, int32_t dtype, int32_t n,
+                               int32_t hw, int32_t ss, int32_t ns, int32_t cs_out, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(d && s && mm && out, "make_m_cond: null pointer");
+  CGB_REQUIRE(ns >= 1 && ns <= ss && 1 + ns + (xr ? 3 : 0) <= cs_out && cs_out <= 24, "make_m_cond: bad channel counts");
+  cudaStream_t st = (cudaStream_t)stream;
+  // mm <- {+inf, -inf} per sample
+  {
+    std::vector<float> init(2 * (size_t)n);
+    for (int i = 0; i < n; ++i) { init[2 * i] = 3.4e38f; init[2 * i + 1] = -3.4e38f; }
+    cudaMemcpyAsync(mm, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);  // init is a stack/heap buffer: make the copy complete before it goes away (tiny, inference only)
+  }
+  dim3 g1((hw + 255) / 256 < 64 ? (hw + 255) / 256 : 64, n);
+  DISPATCH_T(dtype, minmax_c0_kernel<T><<<g1, 256, 0, st>>>((const T*)d, mm, hw, 8);)
+  int r = after_launch("minmax_c0");
+  if (r) return r;
+  const long long pixels = (long long)n * hw;
+  DISPATCH_T(dtype, m_cond_kernel<T><<<grid_for(pixels), 256, 0, st>>>((const T*)d, (const T*)s, (const T*)xr, mm, (T*)out, pixels,
+                                                                      hw, ss, ns, cs_out);)
+  return after_launch("m_cond");
 }

@@ -1,0 +1,109 @@
+"""Caffe-style ResNet-101 (``climategan/deeplab/resnetmulti_v2.py``): same module tree and state_dict keys.
+Inference forward: every conv + its eval-mode BatchNorm (+ ReLU, + the bottleneck's residual add) is ONE libcgb200 conv
+launch — BN folded into the packed weights/bias, ``relu(conv3 + residual)`` in the epilogue (``res_before_act``)."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import _lib, ops
+
+affine_par = True
+
+
+def fold_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d, dtype, cis=None):
+    """Packed weights/bias of conv followed by eval-mode BatchNorm: w' = w*g/sqrt(var+eps), b' = beta + (b-mean)*g/sqrt(..)."""
+    scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+    w = conv.weight.detach() * scale.view(-1, 1, 1, 1)
+    b = bn.bias.detach() - bn.running_mean * scale
+    if conv.bias is not None:
+        b = b + conv.bias.detach() * scale
+    wp = ops.pack_weight(w, dtype, cis=cis)
+    return wp, ops.pad_bias(b, wp.shape[0])
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, dilation=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=1, stride=stride, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes, affine=affine_par)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, stride=1, padding=dilation, bias=False, dilation=dilation)
+        self.bn2 = nn.BatchNorm2d(planes, affine=affine_par)
+        self.conv3 = nn.Conv2d(planes, planes * 4, kernel_size=1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4, affine=affine_par)
+        for bn in (self.bn1, self.bn2, self.bn3):
+            for p in bn.parameters():
+                p.requires_grad = False
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+        self.dilation = dilation
+
+    def forward_storage(self, x):
+        dt = x.dtype
+        w1, b1 = fold_bn(self.conv1, self.bn1, dt, cis=x.shape[-1])
+        out = ops.conv2d_infer(x, w1, b1, k=1, stride=self.stride, act=_lib.ACT_RELU)
+        w2, b2 = fold_bn(self.conv2, self.bn2, dt, cis=out.shape[-1])
+        out = ops.conv2d_infer(out, w2, b2, k=3, dil=self.dilation, pad=self.dilation, act=_lib.ACT_RELU)
+        residual = x
+        if self.downsample is not None:
+            wd, bd = fold_bn(self.downsample[0], self.downsample[1], dt, cis=x.shape[-1])
+            residual = ops.conv2d_infer(x, wd, bd, k=1, stride=self.downsample[0].stride[0])
+        w3, b3 = fold_bn(self.conv3, self.bn3, dt, cis=out.shape[-1])
+        return ops.conv2d_infer(out, w3, b3, residual, k=1, act=_lib.ACT_RELU, res_before_act=1)
+
+
+class ResNetMulti(nn.Module):
+    def __init__(self, layers, n_res=4, res_norm="instance", activ="lrelu", pad_type="reflect"):
+        super().__init__()
+        self.inplanes = 64
+        block = Bottleneck
+        self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64, affine=affine_par)
+        for p in self.bn1.parameters():
+            p.requires_grad = False
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=0, ceil_mode=True)
+        self.layer1 = self._make_layer(block, 64, layers[0])
+        self.layer2 = self._make_layer(block, 128, layers[1], stride=2)
+        self.layer3 = self._make_layer(block, 256, layers[2], stride=1, dilation=2)
+        self.layer4 = self._make_layer(block, 512, layers[3], stride=1, dilation=4)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                m.weight.data.normal_(0, 0.01)
+            elif isinstance(m, nn.BatchNorm2d):
+                m.weight.data.fill_(1)
+                m.bias.data.zero_()
+        if n_res != 0:
+            raise NotImplementedError("encoder.n_res > 0 (layer_res ResBlocks; 0 in defaults.yaml:105) is not built")
+        self.layer_res = nn.Module()
+        self.layer_res.model = nn.Sequential()  # ResBlocks(0, ...) holds an empty Sequential: no state
+
+    def _make_layer(self, block, planes, blocks, stride=1, dilation=1):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * block.expansion or dilation == 2 or dilation == 4:
+            downsample = nn.Sequential(
+                nn.Conv2d(self.inplanes, planes * block.expansion, kernel_size=1, stride=stride, bias=False),
+                nn.BatchNorm2d(planes * block.expansion, affine=affine_par),
+            )
+        for p in downsample._modules["1"].parameters():
+            p.requires_grad = False
+        layers = [block(self.inplanes, planes, stride, dilation=dilation, downsample=downsample)]
+        self.inplanes = planes * block.expansion
+        for _ in range(1, blocks):
+            layers.append(block(self.inplanes, planes, dilation=dilation))
+        return nn.Sequential(*layers)
+
+    def forward_storage(self, x):
+        """x: storage [N,H,W,8] (3 real channels) -> z storage [N,H/8,W/8,2048]."""
+        if self.training:
+            raise NotImplementedError("the masker encoder is built for inference (eval mode) only")
+        w, b = fold_bn(self.conv1, self.bn1, x.dtype, cis=x.shape[-1])
+        x = ops.conv2d_infer(x, w, b, k=7, stride=2, pad=3, act=_lib.ACT_RELU)
+        x = ops.maxpool3s2_ceil(x)
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for blk in layer:
+                x = blk.forward_storage(x)
+        return x

@@ -1,0 +1,59 @@
+"""DADA depth decoder (``climategan/depth.py:25-158``): same module tree / state_dict keys; inference forward on storage
+tensors (Conv2dBlock(norm="batch") = conv + folded eval BatchNorm + leaky-relu in one launch)."""
+from __future__ import annotations
+
+import torch.nn as nn
+
+from . import _lib, ops
+from .blocks import Conv2dBlock, InterpolateNearest2d
+from .deeplab.deeplab_v2 import find_target_size
+
+
+def create_depth_decoder(opts, no_init=False, verbose=0):
+    if opts.gen.d.architecture == "base":
+        raise NotImplementedError("gen.d.architecture=base is not built (dada only)")
+    return DADADepthDecoder(opts)
+
+
+class DADADepthDecoder(nn.Module):
+    def __init__(self, opts):
+        super().__init__()
+        res_dim, mid_dim = 2048, 512
+        self.do_feat_fusion = False
+        if opts.gen.m.use_dada or ("s" in opts.tasks and opts.gen.s.use_dada):
+            self.do_feat_fusion = True
+            self.dec4 = Conv2dBlock(128, res_dim, 1, stride=1, padding=0, bias=True, activation="lrelu", norm="none")
+        self.relu = nn.ReLU(inplace=True)
+        kw = dict(stride=1, bias=False, activation="lrelu", pad_type="reflect", norm="batch")
+        self.enc4_1 = Conv2dBlock(res_dim, mid_dim, 1, padding=0, **kw)
+        self.enc4_2 = Conv2dBlock(mid_dim, mid_dim, 3, padding=1, **kw)
+        self.enc4_3 = Conv2dBlock(mid_dim, 128, 1, padding=0, **kw)
+        self.upsample = None
+        if opts.gen.d.upsample_featuremaps:
+            self.upsample = nn.Sequential(InterpolateNearest2d(), Conv2dBlock(128, 32, 3, padding=1, **kw),
+                                          nn.Conv2d(32, 1, kernel_size=1, stride=1, padding=0))
+        self._target_size = find_target_size(opts, "d")
+
+    def set_target_size(self, size):
+        self._target_size = size[:2] if isinstance(size, (list, tuple)) else (size, size)
+
+    def forward_storage(self, z):
+        """z storage [N,h,w,2048] -> (depth storage [N,T,T,8] (1 real channel), z_depth storage or None)."""
+        if self.training:
+            raise NotImplementedError("the depth decoder is built for inference (eval mode) only")
+        z4 = self.enc4_3.forward_infer(self.enc4_2.forward_infer(self.enc4_1.forward_infer(z)))
+        z_depth = self.dec4.forward_infer(z4) if self.do_feat_fusion else None
+        c_log = 128
+        if self.upsample is not None:
+            y = self.upsample[0](z4)
+            y = self.upsample[1].forward_infer(y)
+            last = self.upsample[2]
+            wl = ops.pack_weight(last.weight, y.dtype, cis=y.shape[-1])
+            z4 = ops.conv2d_infer(y, wl, ops.pad_bias(last.bias, wl.shape[0]), k=1)
+            c_log = 1
+        depth = ops.channel_mean(z4, c_log)               # torch.mean(z4_enc, dim=1, keepdim=True)
+        ts = self._target_size
+        if depth.shape[2] != ts:                          # depth.py:143 compares the width with the int target size
+            depth = ops.resize_bicubic(depth, 384, 384)   # MiDaS inference size, bicubic, align_corners=False
+            depth = ops.resize_nearest(depth, ts, ts)
+        return depth, z_depth

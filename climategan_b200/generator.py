@@ -1,12 +1,16 @@
-"""OmniGenerator — drop-in surface for ``climategan/generator.py``.  Built so far: the painter
-path (``paint``, ``sample_painter_z``); the masker methods raise until their kernels land.
+"""OmniGenerator — drop-in surface for ``climategan/generator.py``: the painter path (``paint``; training and
+inference) and the v2 masker path for INFERENCE (``encode``, ``decode``, ``depth``, ``make_m_cond``, ``mask``: DeepLab-v2
+ResNet-101 encoder, DADA depth decoder, DeepLab-v2 segmentation decoder, base mask decoder; eval mode only).
 """
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
+from .deeplab import create_encoder, create_segmentation_decoder
+from .depth import create_depth_decoder
+from .masker import create_mask_decoder
 from .painter import create_painter
 
 
@@ -23,9 +27,17 @@ class OmniGenerator(nn.Module):
         self.opts = opts
         self.verbose = verbose
         self.encoder = None
+        self.storage_dtype = storage_dtype
         if any(t in opts.tasks for t in "msd"):
-            raise NotImplementedError("masker tasks (m, s, d) are not built yet in climategan_b200")
-        self.decoders = nn.ModuleDict({})
+            self.encoder = create_encoder(opts, no_init, verbose)
+        decoders = {}
+        if "d" in opts.tasks:
+            decoders["d"] = create_depth_decoder(opts, no_init, verbose)
+        if "s" in opts.tasks:
+            decoders["s"] = create_segmentation_decoder(opts, no_init, verbose)
+        if "m" in opts.tasks:
+            decoders["m"] = create_mask_decoder(opts, no_init, verbose)
+        self.decoders = nn.ModuleDict(decoders)
         self.painter = nn.Module()
         if "p" in self.opts.tasks:
             self.painter = create_painter(opts, no_init, verbose)
@@ -49,3 +61,72 @@ class OmniGenerator(nn.Module):
         if self.opts.gen.p.paste_original_content and not no_paste:
             return ops.paste(x, m.to(x.dtype), fake)
         return fake
+
+    # ------------------------------------------------------------------ masker (inference)
+    def encode(self, x):
+        """generator.py:107-118.  NCHW fp32 image -> z as an NHWC storage tensor [N,H/8,W/8,2048] (kept in storage
+        layout: z only ever feeds the decoders below)."""
+        assert self.encoder is not None
+        with torch.no_grad():
+            return self.encoder.forward_storage(ops.to_storage(x, self.storage_dtype))
+
+    def depth(self, x=None, z=None, return_z_depth=False):
+        """generator.py:330-355."""
+        assert x is not None or z is not None
+        assert not (x is not None and z is not None)
+        if z is None:
+            z = self.encode(x)
+        with torch.no_grad():
+            d, z_depth = self.decoders["d"].forward_storage(z)
+        d = ops.from_storage(d, 1)
+        return (d, z_depth) if return_z_depth else d
+
+    def make_m_cond(self, d, s, x=None):
+        """generator.py:196-230: d, s NCHW fp32 predictions; returns the NCHW conditioning tensor (12 or 15 channels)."""
+        with torch.no_grad():
+            dt = self.storage_dtype
+            ds, ss = ops.to_storage(d, dt), ops.to_storage(s, dt)
+            xr = None
+            if self.opts.gen.m.spade.cond_nc == 15:
+                if x is None:
+                    raise ValueError("When using spade for the Masker with 15 channels, x MUST be provided")
+                xr = ops.resize_bilinear(ops.to_storage(x, dt), s.shape[-2], s.shape[-1], align_corners=True)
+            cond = ops.make_m_cond(ds, ss, xr, s.shape[1])
+            return ops.from_storage(cond, 1 + s.shape[1] + (3 if xr is not None else 0))
+
+    def mask(self, x=None, z=None, cond=None, z_depth=None, sigmoid=True):
+        """generator.py:232-277 (base mask decoder: cond is accepted and unused, as in BaseDecoder.forward)."""
+        assert x is not None or z is not None
+        if z is None:
+            z = self.encode(x)
+        with torch.no_grad():
+            if z_depth is None and self.opts.gen.m.use_dada:
+                _, z_depth = self.decoders["d"].forward_storage(z)
+            logits = self.decoders["m"].forward_storage(z, cond, z_depth)
+            if sigmoid:
+                logits = ops.activation(logits, _lib.ACT_SIGMOID)
+            return ops.from_storage(logits, 1)
+
+    def decode(self, x=None, z=None, return_z=False, return_z_depth=False):
+        """generator.py:120-176."""
+        assert x is not None or z is not None
+        out = {}
+        z_depth = cond = d = s = None
+        if z is None:
+            z = self.encode(x)
+        if return_z:
+            out["z"] = z
+        with torch.no_grad():
+            if "d" in self.decoders:
+                d_st, z_depth = self.decoders["d"].forward_storage(z)
+                d = out["d"] = ops.from_storage(d_st, 1)
+            if return_z_depth:
+                out["z_depth"] = z_depth
+            if "s" in self.decoders:
+                s_st = self.decoders["s"].forward_storage(z, z_depth)
+                s = out["s"] = ops.from_storage(s_st, self.decoders["s"].output_dim)
+        if "m" in self.decoders:
+            if s is not None and d is not None and self.opts.gen.m.use_spade:
+                cond = self.make_m_cond(d, s, x)
+            out["m"] = self.mask(z=z, cond=cond, z_depth=z_depth)
+        return out

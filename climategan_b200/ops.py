@@ -76,12 +76,13 @@ def pad_bias(b: Optional[torch.Tensor], cos: int) -> Optional[torch.Tensor]:
 class ConvGeom:
     """kernel geometry + epilogue of one conv (forward view)."""
 
-    __slots__ = ("kh", "kw", "stride", "dil", "pad", "pad_mode", "act", "slope", "engine")
+    __slots__ = ("kh", "kw", "stride", "dil", "pad", "pad_mode", "act", "slope", "engine", "res_before_act")
 
     def __init__(self, kh, kw, stride=1, dil=1, pad=0, pad_mode=_lib.PAD_ZERO, act=_lib.ACT_NONE,
-                 slope=0.2, engine=_lib.ENGINE_AUTO):
+                 slope=0.2, engine=_lib.ENGINE_AUTO, res_before_act=0):
         self.kh, self.kw, self.stride, self.dil, self.pad = kh, kw, stride, dil, pad
         self.pad_mode, self.act, self.slope, self.engine = pad_mode, act, slope, engine
+        self.res_before_act = res_before_act
 
     def out_hw(self, hi, wi):
         ho = (hi + 2 * self.pad - self.dil * (self.kh - 1) - 1) // self.stride + 1
@@ -91,7 +92,7 @@ class ConvGeom:
     def desc(self, n, hi, wi, ci, co, dtype) -> ConvDesc:
         ho, wo = self.out_hw(hi, wi)
         return ConvDesc(n, hi, wi, ci, ho, wo, co, self.kh, self.kw, self.stride, self.dil, self.pad,
-                        self.pad_mode, _DT[dtype], self.act, self.slope, self.engine)
+                        self.pad_mode, _DT[dtype], self.act, self.slope, self.engine, self.res_before_act)
 
 
 def conv_fwd_raw(x, wp, bias, residual, g: ConvGeom):
@@ -659,3 +660,83 @@ def cat_mask_image(m, img):
     """torch.cat([m, img], dim=1) (trainer.py:1363) with gradient flowing to ``img`` only — a pure copy; kept as a
     torch op (memory plumbing, no arithmetic)."""
     return torch.cat([m.detach(), img], dim=1)
+
+
+# ------------------------------------------------------------------------------------------------
+# masker inference helpers (forward only: the masker is built for inference so far)
+# ------------------------------------------------------------------------------------------------
+def conv2d_infer(x, wp, bias, residual=None, *, k, stride=1, dil=1, pad=0, pad_mode=_lib.PAD_ZERO, act=_lib.ACT_NONE,
+                 slope=0.2, res_before_act=0):
+    """Forward-only conv on pre-packed weights (eval-mode BatchNorm already folded into wp / bias)."""
+    g = ConvGeom(k, k, stride, dil, pad, pad_mode, act, slope, _lib.ENGINE_AUTO, res_before_act)
+    return conv_fwd_raw(x, wp, bias, residual, g)
+
+
+def maxpool3s2_ceil(x):
+    """nn.MaxPool2d(3, stride=2, padding=0, ceil_mode=True) (deeplab/resnetmulti_v2.py:76-78)."""
+    _chk_storage(x)
+    n, hi, wi, c = x.shape
+
+    def out(sz):
+        o = -(-(sz - 3) // 2) + 1
+        if (o - 1) * 2 >= sz:
+            o -= 1
+        return o
+
+    ho, wo = out(hi), out(wi)
+    y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
+    check(_L().cgb_maxpool3s2_ceil_fwd(_p(x), _p(y), _DT[x.dtype], n, hi, wi, ho, wo, c, _st()), "maxpool3s2_ceil")
+    return y
+
+
+def resize_bilinear(x, ho, wo, align_corners=False):
+    _chk_storage(x)
+    n, hi, wi, c = x.shape
+    y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
+    check(_L().cgb_resize_bilinear_fwd(_p(x), _p(y), _DT[x.dtype], n, hi, wi, ho, wo, c, 1 if align_corners else 0, _st()),
+          "resize_bilinear")
+    return y
+
+
+def resize_bicubic(x, ho, wo):
+    _chk_storage(x)
+    n, hi, wi, c = x.shape
+    y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
+    check(_L().cgb_resize_bicubic_fwd(_p(x), _p(y), _DT[x.dtype], n, hi, wi, ho, wo, c, _st()), "resize_bicubic")
+    return y
+
+
+def channel_mean(x, c_logical):
+    _chk_storage(x)
+    n, h, w, cs = x.shape
+    y = torch.empty((n, h, w, 8), dtype=x.dtype, device=x.device)
+    check(_L().cgb_channel_mean(_p(x), _p(y), _DT[x.dtype], n * h * w, cs, c_logical, _st()), "channel_mean")
+    return y
+
+
+def mul(a, b):
+    _chk_storage(a)
+    assert a.shape == b.shape and a.dtype == b.dtype
+    y = torch.empty_like(a)
+    check(_L().cgb_mul(_p(a), _p(b.contiguous()), _p(y), _DT[a.dtype], a.numel(), _st()), "mul")
+    return y
+
+
+def make_m_cond(d, s, xr, ns):
+    """generator.py:196-230: cat[normalize(d), softmax(s, dim=1), x bilinear-resized] -> [N,H,W,round8(1+ns+3)]."""
+    _chk_storage(d)
+    _chk_storage(s)
+    n, h, w, ss = s.shape
+    c_out = 1 + ns + (3 if xr is not None else 0)
+    cs_out = round8(c_out)
+    mm = torch.empty((n, 2), dtype=torch.float32, device=d.device)
+    out = torch.empty((n, h, w, cs_out), dtype=d.dtype, device=d.device)
+    check(_L().cgb_make_m_cond(_p(d), _p(s), _p(xr), _p(mm), _p(out), _DT[d.dtype], n, h * w, ss, ns, cs_out, _st()),
+          "make_m_cond")
+    return out
+
+
+def global_mean(x):
+    """AdaptiveAvgPool2d(1) as a storage tensor [N,1,1,Cs] (ASPP global branch, deeplab_v2.py:97-102)."""
+    mean, _ = instnorm_stats(x)
+    return mean.to(x.dtype).view(x.shape[0], 1, 1, x.shape[-1]).contiguous()

@@ -94,3 +94,22 @@ def default_painter_opts(latent_dim=640, spade_n_up=7, tasks=("p",), ndf=64, n_l
             )
         ),
     )
+
+
+def default_masker_opts(tasks=("m", "s", "d"), nblocks=(3, 4, 23, 3), size=640, with_painter=False, **painter_kw):
+    """gen.{encoder,deeplabv2,d,s,m} of shared/trainer/defaults.yaml with the deeplabv2 architecture the north star names
+    (defaults.yaml:100-192) and data.transforms[-1].new_size (:62-67: x 640, d/s 160 -> here size and size/4)."""
+    o = default_painter_opts(tasks=tuple(tasks) + (("p",) if with_painter else ()), **painter_kw)
+    o.data = Dict(transforms=[Dict(name="resize", new_size=Dict(default=size, d=size // 4, s=size // 4))])
+    o.gen.encoder = Dict(architecture="deeplabv2", n_res=0, norm="spectral", activ="lrelu", pad_type="reflect")
+    o.gen.deeplabv2 = Dict(nblocks=list(nblocks), use_pretrained=False)
+    o.gen.deeplabv3 = Dict(backbone="resnet", output_stride=8)
+    o.gen.d = Dict(architecture="dada", upsample_featuremaps=True, output_dim=1, norm="batch", loss="sigm",
+                   classify=Dict(enable=False))
+    o.gen.s = Dict(architecture="deeplabv2", num_classes=11, output_dim=11, use_advent=True, use_minent=True,
+                   upsample_featuremaps=False, use_dada=True, depth_feat_fusion=False, depth_dada_fusion=False)
+    o.gen.m = Dict(use_spade=False, output_dim=1, n_res=3, n_upsample=3, proj_dim=64, norm="spectral", activ="lrelu",
+                   pad_type="reflect", use_low_level_feats=True, use_dada=False, use_advent=True,
+                   spade=Dict(latent_dim=128, detach=False, cond_nc=15, spade_use_spectral_norm=True,
+                              spade_param_free_norm="batch", num_layers=3))
+    return o

@@ -68,6 +68,7 @@ typedef struct cgb_conv_desc {
   int32_t act;              /* epilogue activation (fwd) */
   float slope;              /* leaky-relu slope */
   int32_t engine;           /* cgb_engine */
+  int32_t res_before_act;   /* 1: y = act(conv + bias + residual) (ResNet bottleneck, resnetmulti_v2.py:50-52); 0: act first */
 } cgb_conv_desc;
 
 /* ---- library --------------------------------------------------------------------------- */
@@ -169,6 +170,22 @@ int cgb_upsample_nearest_bwd(const void* gy, void* gx, int32_t dtype, int32_t n,
  * GEMM for the tensor cores; computed once per resolution and shared by every SPADE layer at that resolution. */
 int cgb_im2col(const void* x, void* y, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t cs_in, int32_t c,
                int32_t k, int32_t pad, int32_t dil, int32_t cs_out, void* stream);
+
+/* ---- masker (inference) helpers, NHWC storage ---------------------------------------------
+ * nn.MaxPool2d(3, stride=2, padding=0, ceil_mode=True) (deeplab/resnetmulti_v2.py:76-78); caller passes ho/wo.
+ * F.interpolate bilinear (deeplab_v2.py:116,198; generator.py:227) and bicubic (depth.py:144-149, align_corners=False).
+ * torch.mean(z, dim=1, keepdim=True) (depth.py:142); z * z_depth (deeplab_v2.py:193, blocks.py:306).
+ * OmniGenerator.make_m_cond (generator.py:196-230): cat[normalize(d), softmax(s), x resized]; mm = n*2 floats scratch. */
+int cgb_maxpool3s2_ceil_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t ho, int32_t wo,
+                            int32_t c, void* stream);
+int cgb_resize_bilinear_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t ho, int32_t wo,
+                            int32_t c, int32_t align_corners, void* stream);
+int cgb_resize_bicubic_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t ho, int32_t wo,
+                           int32_t c, void* stream);
+int cgb_channel_mean(const void* x, void* y, int32_t dtype, int64_t pixels, int32_t cs, int32_t c_logical, void* stream);
+int cgb_mul(const void* a, const void* b, void* y, int32_t dtype, int64_t count, void* stream);
+int cgb_make_m_cond(const void* d, const void* s, const void* xr, float* mm, void* out, int32_t dtype, int32_t n, int32_t hw,
+                    int32_t ss, int32_t ns, int32_t cs_out, void* stream);
 
 /* ---- layout / elementwise ----------------------------------------------------------------
  * NCHW fp32 (the reference's tensor layout at the API edge) <-> NHWC storage. */

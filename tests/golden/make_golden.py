@@ -217,6 +217,39 @@ def run_step_case(name="painter_step", latent=16, n_up=4, ndf=8, n_layers=3, num
     print(name, "logs", [round(v, 5) for v in logs], "npz bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
 
 
+def run_masker_case(name="masker_small", nblocks=(2, 2, 3, 2), batch=2, size=64):
+    """Masker inference (eval mode) with the reference's OmniGenerator, deeplabv2 encoder + DADA depth + deeplabv2
+    segmentation + base mask decoder: G.decode(x) as Trainer.infer_all drives it (trainer.py:272-287)."""
+    generator_mod = refshim.load("generator")
+    from climategan_b200.utils import default_masker_opts
+
+    opts = default_masker_opts(nblocks=nblocks, size=size)
+    opts.data.transforms[-1].new_size.d = 24   # != the decoder's native 16 -> exercises the bicubic(384)+nearest path
+    opts.data.transforms[-1].new_size.s = 24   # make_m_cond needs d and s at the same resolution
+    torch.manual_seed(0)
+    G = generator_mod.OmniGenerator(opts)
+    shapes = [(k, tuple(v.shape)) for k, v in G.state_dict().items()]
+    G.load_state_dict(fill_state_dict(shapes, seed=77), strict=True)
+    G.eval()
+    x, _, _ = synth_inputs(batch, size, seed=3)
+    with torch.no_grad():
+        out = G.decode(x=x, return_z=True, return_z_depth=True)
+        cond = G.make_m_cond(out["d"], out["s"], x)
+        m_logits = G.mask(z=out["z"], z_depth=out["z_depth"], sigmoid=False)
+    arrays = {"m_logits": m_logits.numpy(), "d": out["d"].numpy(), "s": out["s"].numpy(), "m": out["m"].numpy(), "cond": cond.numpy(),
+              "z_mean_abs": np.float32(out["z"].abs().mean().item()), "z_sample": out["z"][:, ::97].numpy(),
+              "z_depth_sample": out["z_depth"][:, ::97].numpy()}
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+    meta = {"case": name, "nblocks": list(nblocks), "batch": batch, "size": size, "d_size": 24, "s_size": 24, "weight_seed": 77,
+            "input_seed": 3, "shapes": [[k, list(s)] for k, s in shapes],
+            "reference": "cc-ai/climategan @ /root/reference (generator, deeplab/*, depth, masker, blocks modules)",
+            "torch": torch.__version__}
+    with open(os.path.join(HERE, name + ".json"), "w") as f:
+        json.dump(meta, f)
+    print(name, {k: tuple(v.shape) for k, v in out.items() if hasattr(v, "shape")}, "m range", float(out["m"].min()),
+          float(out["m"].max()), "npz bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
+
+
 if __name__ == "__main__":
     if not refshim.available():
         sys.exit("reference tree not available; goldens can only be regenerated in the build container")
@@ -224,3 +257,4 @@ if __name__ == "__main__":
         run_case(name, *cfg)
     run_disc_case()
     run_step_case()
+    run_masker_case()

@@ -14,14 +14,24 @@ def fill_state_dict(shapes, seed: int):
     """shapes: ordered list of (key, shape).  Returns {key: fp32 tensor}.
 
     conv weights ~ N(0, 0.7^2/fan_in) ; biases ~ N(0, 0.1^2) ; spectral-norm u/v: unit-norm gaussians
-    (as the reference initialises them, climategan/norms.py:129-133).
+    (as the reference initialises them, climategan/norms.py:129-133) ; BatchNorm: weight 1+0.1n, running_mean 0.1n,
+    running_var 0.5+0.5|n|, num_batches_tracked 0.
     """
     rs = np.random.RandomState(seed)
     out = {}
     for key, shape in shapes:
         shape = tuple(shape)
         a = rs.standard_normal(size=shape).astype(np.float32)
-        if key.endswith("weight_u") or key.endswith("weight_v"):
+        if key.endswith("num_batches_tracked"):
+            out[key] = torch.zeros(shape, dtype=torch.int64)
+            continue
+        if key.endswith("running_var"):
+            a = np.abs(a) * 0.5 + 0.5
+        elif key.endswith("running_mean"):
+            a = a * 0.1
+        elif len(shape) == 1 and key.endswith("weight"):  # BatchNorm scale
+            a = 1.0 + 0.1 * a
+        elif key.endswith("weight_u") or key.endswith("weight_v"):
             a = a / (np.linalg.norm(a) + 1e-12)
         elif key.endswith("bias"):
             a = a * 0.1

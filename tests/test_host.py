@@ -35,7 +35,7 @@ def test_no_cpu_fallback():
     """Without an sm_100 device every compute entry point refuses; the Python ops raise."""
     lib = _lib.lib()
     assert lib.cgb_device_ok() == 0
-    d = _lib.ConvDesc(1, 8, 8, 8, 8, 8, 8, 3, 3, 1, 1, 1, 0, 0, 0, 0.2, 0)
+    d = _lib.ConvDesc(1, 8, 8, 8, 8, 8, 8, 3, 3, 1, 1, 1, 0, 0, 0, 0.2, 0, 0)
     import ctypes as C
 
     assert lib.cgb_conv2d_fwd(C.byref(d), None, None, None, None, None, None) == -4  # CGB_UNSUPPORTED_ARCH

@@ -161,3 +161,18 @@ def test_trainer_oracle_matches_reference_step_golden():
             assert rel_max(gsd[k[3:]], torch.from_numpy(v)) < 1e-5, k
         if k.startswith("D::"):
             assert rel_max(dsd_full[k[3:]], torch.from_numpy(v)) < 1e-5, k
+
+
+def test_masker_oracle_matches_reference_golden():
+    """oracle/masker_oracle.py vs the reference OmniGenerator.decode / make_m_cond / mask in eval mode."""
+    from oracle import masker_oracle as mo
+
+    meta, g, sd, (x, _, _) = load_golden("masker_small")
+    with torch.no_grad():
+        out = mo.decode(sd, x, meta["d_size"], meta["s_size"])
+        cond = mo.make_m_cond(out["d"], out["s"], x)
+    for k in ("d", "s", "m"):
+        assert rel_max(out[k], torch.from_numpy(g[k])) < 1e-4, k
+    assert rel_max(cond, torch.from_numpy(g["cond"])) < 1e-4
+    assert rel_max(out["z"][:, ::97], torch.from_numpy(g["z_sample"])) < 1e-4
+    assert rel_max(out["z_depth"][:, ::97], torch.from_numpy(g["z_depth_sample"])) < 1e-4
