@@ -14,7 +14,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 _CSRC = _PKG / "csrc"
 _SO = _PKG / "libcgb200.so"
-_SOURCES = ["api.cu", "ops.cu", "conv_simt.cu", "conv_tc.cu"]
+_SOURCES = ["api.cu", "ops.cu", "masker_ops.cu", "conv_simt.cu", "conv_tc.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -104,6 +104,27 @@ SIGNATURES = {
     "cgb_channel_mean": ([_P, _P, _I, _L, _I, _I, _P], C.c_int),
     "cgb_mul": ([_P, _P, _P, _I, _L, _P], C.c_int),
     "cgb_make_m_cond": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_bn_apply_fwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P], C.c_int),
+    "cgb_bn_apply_bwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P], C.c_int),
+    "cgb_bn_bwd_finalize": ([_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P], C.c_int),
+    "cgb_bn_update_running": ([_P, _P, _P, _P, _I, _L, _F, _F, _P], C.c_int),
+    "cgb_maxpool3s2_ceil_bwd": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_resize_bilinear_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_reflect_pad_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_reflect_pad_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_channel_mean_bwd": ([_P, _P, _I, _L, _I, _I, _P], C.c_int),
+    "cgb_broadcast_hw": ([_P, _P, _I, _I, _I, _I, _F, _P], C.c_int),
+    "cgb_dropout": ([_P, _P, _I, _L, _F, C.c_uint64, _P], C.c_int),
+    "cgb_softmax_nchw_fwd": ([_P, _P, _I, _I, _I, _P], C.c_int),
+    "cgb_softmax_nchw_bwd": ([_P, _P, _P, _I, _I, _I, _P], C.c_int),
+    "cgb_cross_entropy_nchw": ([_P, _P, _P, _P, _I, _I, _I, _P], C.c_int),
+    "cgb_entropy_nchw": ([_P, _P, _P, _P, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_minent_loss": ([_P, _P, _P, _P, _I, _I, _I, _I, _F, _P], C.c_int),
+    "cgb_sigmoid_pair": ([_P, _P, _P, _I, _I, _I, _P], C.c_int),
+    "cgb_tv_loss": ([_P, _P, _P, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_bce_logits_loss": ([_P, _P, _P, _P, _L, _P], C.c_int),
+    "cgb_ground_intersection_loss": ([_P, _P, _P, _L, _P], C.c_int),
+    "cgb_sigm_loss": ([_P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P], C.c_int),
     "cgb_resize_nearest_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_upsample_nearest_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_im2col": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),

@@ -53,7 +53,7 @@ class Conv2dBlock(nn.Module):
         if norm in ("spectral", "none"):
             self.norm = None
         elif norm == "batch":
-            self.norm = nn.BatchNorm2d(output_dim)  # inference only: folded into the conv (forward_infer)
+            self.norm = nn.BatchNorm2d(output_dim)  # eval: folded into the conv (forward_infer); train: batch statistics
         else:
             raise NotImplementedError("Conv2dBlock norm '{}' is not built yet".format(norm))
         self.kernel_size = kernel_size
@@ -66,11 +66,19 @@ class Conv2dBlock(nn.Module):
         self.conv = SpectralNorm(conv) if (norm == "spectral" or use_spectral_norm) else conv
 
     def forward(self, x, residual=None):
-        if self.norm is not None:
-            raise NotImplementedError("Conv2dBlock(norm='batch') is built for inference only: use forward_infer")
+        """Training-capable forward (autograd tape): explicit reflect pad -> conv (tcgen05, pad 0) -> [train-mode
+        BatchNorm + activation as one apply pass] ; bias + activation ride in the conv epilogue when there is no norm."""
         w, b = conv_weight_bias(self.conv)
-        return ops.conv2d(x, w, b, residual, stride=self.stride, dil=self.dilation, pad=self.padding,
-                          pad_mode=self.pad_mode, act=self.act, slope=self.slope)
+        pad, pad_mode = self.padding, self.pad_mode
+        if pad_mode == _lib.PAD_REFLECT and pad > 0:
+            x = ops.reflect_pad(x, pad)
+            pad, pad_mode = 0, _lib.PAD_ZERO
+        if self.norm is not None:
+            y = ops.conv2d(x, w, b, None, stride=self.stride, dil=self.dilation, pad=pad, pad_mode=pad_mode)
+            y = ops.batchnorm_act(y, self.norm, None, self.act, self.slope)
+            return y if residual is None else y + residual
+        return ops.conv2d(x, w, b, residual, stride=self.stride, dil=self.dilation, pad=pad, pad_mode=pad_mode,
+                          act=self.act, slope=self.slope)
 
     def forward_infer(self, x, residual=None):
         """Inference forward (no autograd tape): pad -> conv [-> eval BatchNorm folded] -> activation [+ residual]."""
@@ -162,6 +170,9 @@ class ResBlock(nn.Module):
             Conv2dBlock(dim, dim, 3, 1, 1, norm=norm, activation="none", pad_type=pad_type),
         )
 
+    def forward(self, x):
+        return self.model[1](self.model[0](x), residual=x)
+
     def forward_infer(self, x):
         return self.model[1].forward_infer(self.model[0].forward_infer(x), residual=x)
 
@@ -173,6 +184,11 @@ class ResBlocks(nn.Module):
         super().__init__()
         self.model = nn.Sequential(*[ResBlock(dim, norm=norm, activation=activation, pad_type=pad_type)
                                      for _ in range(num_blocks)])
+
+    def forward(self, x):
+        for blk in self.model:
+            x = blk(x)
+        return x
 
     def forward_infer(self, x):
         for blk in self.model:
@@ -210,12 +226,14 @@ class BaseDecoder(nn.Module):
         self.output_dim = output_dim
 
     def forward_storage(self, z, cond=None, z_depth=None):
+        """blocks.py:291-318.  Train mode (or grad enabled on a training module): autograd forwards; eval: fused inference."""
+        train = self.training
         if z_depth is not None and self.use_dada:
             z = ops.mul(z, z_depth)
         if self.proj_conv is not None:
-            z = self.proj_conv.forward_infer(z)
+            z = self.proj_conv(z) if train else self.proj_conv.forward_infer(z)
         for m in self.model:
-            if isinstance(m, InterpolateNearest2d):
+            if isinstance(m, InterpolateNearest2d) or train:
                 z = m(z)
             else:
                 z = m.forward_infer(z)

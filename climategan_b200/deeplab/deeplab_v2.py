@@ -37,6 +37,9 @@ class _ASPPModule(nn.Module):
 
     def forward_storage(self, x):
         c = self.atrous_conv
+        if self.training:
+            y = ops.conv2d(x, c.weight, None, dil=c.dilation[0], pad=c.padding[0])
+            return ops.batchnorm_act(y, self.bn, None, _lib.ACT_RELU)
         w, b = fold_bn(c, self.bn, x.dtype, cis=x.shape[-1])
         return ops.conv2d_infer(x, w, b, k=c.kernel_size[0], dil=c.dilation[0], pad=c.padding[0], act=_lib.ACT_RELU)
 
@@ -76,6 +79,14 @@ class ASPP(nn.Module):
         x3 = self.aspp3.forward_storage(x)
         x4 = self.aspp4.forward_storage(x)
         g = ops.global_mean(x)                                     # AdaptiveAvgPool2d(1)
+        if self.training:
+            x5 = ops.conv2d(g, self.global_avg_pool[1].weight, None)
+            x5 = ops.batchnorm_act(x5, self.global_avg_pool[2], None, _lib.ACT_RELU)   # batch stats over N only (1x1 maps)
+            x5 = ops.broadcast_hw(x5, h, w)                        # bilinear 1x1 -> h x w = broadcast (deeplab_v2.py:116)
+            y = torch.cat((x1, x2, x3, x4, x5), dim=-1)
+            y = ops.conv2d(y, self.conv1.weight, None)
+            y = ops.batchnorm_act(y, self.bn1, None, _lib.ACT_RELU)
+            return ops.dropout(y, self.dropout.p, True)
         wg, bg = fold_bn(self.global_avg_pool[1], self.global_avg_pool[2], x.dtype, cis=g.shape[-1])
         x5 = ops.conv2d_infer(g, wg, bg, k=1, act=_lib.ACT_RELU)
         x5 = ops.resize_bilinear(x5, h, w, align_corners=True)     # 1x1 -> h x w broadcast (deeplab_v2.py:116)
@@ -104,8 +115,6 @@ class DeepLabV2Decoder(nn.Module):
         self._target_size = size[:2] if isinstance(size, (list, tuple)) else (size, size)
 
     def forward_storage(self, z, z_depth=None):
-        if self.training:
-            raise NotImplementedError("the segmentation decoder is built for inference (eval mode) only")
         if self._target_size is None:
             raise Exception("self._target_size should be set with self.set_target_size()")
         if z.shape[-1] != 2048:
@@ -113,12 +122,19 @@ class DeepLabV2Decoder(nn.Module):
         if z_depth is not None and self.use_dada:
             z = ops.mul(z, z_depth)
         y = self.aspp.forward_storage(z)
-        for i in (0, 4):
-            w, b = fold_bn(self.conv[i], self.conv[i + 1], y.dtype, cis=y.shape[-1])
-            y = ops.conv2d_infer(y, w, b, k=3, pad=1, act=_lib.ACT_RELU)
         last = self.conv[8]
-        wl = ops.pack_weight(last.weight, y.dtype, cis=y.shape[-1])
-        y = ops.conv2d_infer(y, wl, ops.pad_bias(last.bias, wl.shape[0]), k=1)
+        if self.training:
+            for i in (0, 4):
+                y = ops.conv2d(y, self.conv[i].weight, None, pad=1)
+                y = ops.batchnorm_act(y, self.conv[i + 1], None, _lib.ACT_RELU)
+                y = ops.dropout(y, self.conv[i + 3].p, True)
+            y = ops.conv2d(y, last.weight, last.bias)
+        else:
+            for i in (0, 4):
+                w, b = fold_bn(self.conv[i], self.conv[i + 1], y.dtype, cis=y.shape[-1])
+                y = ops.conv2d_infer(y, w, b, k=3, pad=1, act=_lib.ACT_RELU)
+            wl = ops.pack_weight(last.weight, y.dtype, cis=y.shape[-1])
+            y = ops.conv2d_infer(y, wl, ops.pad_bias(last.bias, wl.shape[0]), k=1)
         ts = self._target_size
         th, tw = (ts, ts) if isinstance(ts, int) else ts
         return ops.resize_bilinear(y, th, tw, align_corners=True)

@@ -42,6 +42,8 @@ class Bottleneck(nn.Module):
         self.dilation = dilation
 
     def forward_storage(self, x):
+        if self.training:
+            return self._forward_train(x)
         dt = x.dtype
         w1, b1 = fold_bn(self.conv1, self.bn1, dt, cis=x.shape[-1])
         out = ops.conv2d_infer(x, w1, b1, k=1, stride=self.stride, act=_lib.ACT_RELU)
@@ -53,6 +55,20 @@ class Bottleneck(nn.Module):
             residual = ops.conv2d_infer(x, wd, bd, k=1, stride=self.downsample[0].stride[0])
         w3, b3 = fold_bn(self.conv3, self.bn3, dt, cis=out.shape[-1])
         return ops.conv2d_infer(out, w3, b3, residual, k=1, act=_lib.ACT_RELU, res_before_act=1)
+
+    def _forward_train(self, x):
+        """resnetmulti_v2.py:40-56 in train mode: BatchNorm uses BATCH statistics (only its affine parameters are frozen,
+        :16-18) and updates its running statistics; conv -> [stats pass] -> [normalise + ReLU (+ residual) pass]."""
+        out = ops.conv2d(x, self.conv1.weight, None, stride=self.stride)
+        out = ops.batchnorm_act(out, self.bn1, None, _lib.ACT_RELU)
+        out = ops.conv2d(out, self.conv2.weight, None, dil=self.dilation, pad=self.dilation)
+        out = ops.batchnorm_act(out, self.bn2, None, _lib.ACT_RELU)
+        out = ops.conv2d(out, self.conv3.weight, None)
+        residual = x
+        if self.downsample is not None:
+            residual = ops.conv2d(x, self.downsample[0].weight, None, stride=self.downsample[0].stride[0])
+            residual = ops.batchnorm_act(residual, self.downsample[1], None, _lib.ACT_NONE)
+        return ops.batchnorm_act(out, self.bn3, residual, _lib.ACT_RELU)
 
 
 class ResNetMulti(nn.Module):
@@ -99,9 +115,11 @@ class ResNetMulti(nn.Module):
     def forward_storage(self, x):
         """x: storage [N,H,W,8] (3 real channels) -> z storage [N,H/8,W/8,2048]."""
         if self.training:
-            raise NotImplementedError("the masker encoder is built for inference (eval mode) only")
-        w, b = fold_bn(self.conv1, self.bn1, x.dtype, cis=x.shape[-1])
-        x = ops.conv2d_infer(x, w, b, k=7, stride=2, pad=3, act=_lib.ACT_RELU)
+            x = ops.conv2d(x, self.conv1.weight, None, stride=2, pad=3)
+            x = ops.batchnorm_act(x, self.bn1, None, _lib.ACT_RELU)
+        else:
+            w, b = fold_bn(self.conv1, self.bn1, x.dtype, cis=x.shape[-1])
+            x = ops.conv2d_infer(x, w, b, k=7, stride=2, pad=3, act=_lib.ACT_RELU)
         x = ops.maxpool3s2_ceil(x)
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
             for blk in layer:

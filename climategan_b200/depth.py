@@ -39,17 +39,19 @@ class DADADepthDecoder(nn.Module):
 
     def forward_storage(self, z):
         """z storage [N,h,w,2048] -> (depth storage [N,T,T,8] (1 real channel), z_depth storage or None)."""
-        if self.training:
-            raise NotImplementedError("the depth decoder is built for inference (eval mode) only")
-        z4 = self.enc4_3.forward_infer(self.enc4_2.forward_infer(self.enc4_1.forward_infer(z)))
-        z_depth = self.dec4.forward_infer(z4) if self.do_feat_fusion else None
+        run = (lambda blk, t: blk(t)) if self.training else (lambda blk, t: blk.forward_infer(t))
+        z4 = run(self.enc4_3, run(self.enc4_2, run(self.enc4_1, z)))
+        z_depth = run(self.dec4, z4) if self.do_feat_fusion else None
         c_log = 128
         if self.upsample is not None:
             y = self.upsample[0](z4)
-            y = self.upsample[1].forward_infer(y)
+            y = run(self.upsample[1], y)
             last = self.upsample[2]
-            wl = ops.pack_weight(last.weight, y.dtype, cis=y.shape[-1])
-            z4 = ops.conv2d_infer(y, wl, ops.pad_bias(last.bias, wl.shape[0]), k=1)
+            if self.training:
+                z4 = ops.conv2d(y, last.weight, last.bias)
+            else:
+                wl = ops.pack_weight(last.weight, y.dtype, cis=y.shape[-1])
+                z4 = ops.conv2d_infer(y, wl, ops.pad_bias(last.bias, wl.shape[0]), k=1)
             c_log = 1
         depth = ops.channel_mean(z4, c_log)               # torch.mean(z4_enc, dim=1, keepdim=True)
         ts = self._target_size

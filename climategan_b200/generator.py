@@ -1,6 +1,7 @@
 """OmniGenerator — drop-in surface for ``climategan/generator.py``: the painter path (``paint``; training and
-inference) and the v2 masker path for INFERENCE (``encode``, ``decode``, ``depth``, ``make_m_cond``, ``mask``: DeepLab-v2
-ResNet-101 encoder, DADA depth decoder, DeepLab-v2 segmentation decoder, base mask decoder; eval mode only).
+inference) and the v2 masker path (``encode``, ``decode``, ``depth``, ``make_m_cond``, ``mask``: DeepLab-v2
+ResNet-101 encoder, DADA depth decoder, DeepLab-v2 segmentation decoder, base mask decoder) in train mode (autograd tape,
+batch-statistics BatchNorm) and eval mode (fused inference kernels).
 """
 from __future__ import annotations
 
@@ -31,6 +32,7 @@ class OmniGenerator(nn.Module):
         if any(t in opts.tasks for t in "msd"):
             self.encoder = create_encoder(opts, no_init, verbose)
         decoders = {}
+        self.painter = nn.Module()   # registered before the decoders, as in the reference (fixes the parameter order)
         if "d" in opts.tasks:
             decoders["d"] = create_depth_decoder(opts, no_init, verbose)
         if "s" in opts.tasks:
@@ -38,7 +40,6 @@ class OmniGenerator(nn.Module):
         if "m" in opts.tasks:
             decoders["m"] = create_mask_decoder(opts, no_init, verbose)
         self.decoders = nn.ModuleDict(decoders)
-        self.painter = nn.Module()
         if "p" in self.opts.tasks:
             self.painter = create_painter(opts, no_init, verbose)
             self.painter.storage_dtype = storage_dtype
@@ -62,13 +63,35 @@ class OmniGenerator(nn.Module):
             return ops.paste(x, m.to(x.dtype), fake)
         return fake
 
-    # ------------------------------------------------------------------ masker (inference)
+    # ------------------------------------------------------------------ masker
+    # z and z_depth are NHWC storage tensors (they only ever travel between these methods); d, s, m are NCHW fp32 like the
+    # reference's.  Train mode records the autograd tape (BatchNorm on batch statistics, dropout active); eval mode runs the
+    # fused inference kernels under no_grad.
+    def _grad_ctx(self):
+        return torch.enable_grad() if (self.training and torch.is_grad_enabled()) else torch.no_grad()
+
     def encode(self, x):
-        """generator.py:107-118.  NCHW fp32 image -> z as an NHWC storage tensor [N,H/8,W/8,2048] (kept in storage
-        layout: z only ever feeds the decoders below)."""
+        """generator.py:107-118.  NCHW fp32 image -> z [N,H/8,W/8,2048] (storage layout)."""
         assert self.encoder is not None
-        with torch.no_grad():
+        with self._grad_ctx():
             return self.encoder.forward_storage(ops.to_storage(x, self.storage_dtype))
+
+    def decode_d(self, z):
+        """``self.decoders["d"](z)`` of the reference (depth.py:128-155): (d NCHW fp32 [N,1,T,T], z_depth storage)."""
+        with self._grad_ctx():
+            d, z_depth = self.decoders["d"].forward_storage(z)
+            return ops.from_storage(d, 1), z_depth
+
+    def decode_s(self, z, z_depth=None):
+        """``self.decoders["s"](z, z_depth)`` (deeplab_v2.py:181-198): seg logits NCHW fp32 [N,11,T,T]."""
+        with self._grad_ctx():
+            dec = self.decoders["s"]
+            return ops.from_storage(dec.forward_storage(z, z_depth), dec.output_dim)
+
+    def decode_m(self, z, cond=None, z_depth=None):
+        """``self.decoders["m"](z, cond=cond, z_depth=z_depth)`` (blocks.py:291-318): mask logits NCHW fp32 [N,1,H,W]."""
+        with self._grad_ctx():
+            return ops.from_storage(self.decoders["m"].forward_storage(z, cond, z_depth), 1)
 
     def depth(self, x=None, z=None, return_z_depth=False):
         """generator.py:330-355."""
@@ -76,9 +99,7 @@ class OmniGenerator(nn.Module):
         assert not (x is not None and z is not None)
         if z is None:
             z = self.encode(x)
-        with torch.no_grad():
-            d, z_depth = self.decoders["d"].forward_storage(z)
-        d = ops.from_storage(d, 1)
+        d, z_depth = self.decode_d(z)
         return (d, z_depth) if return_z_depth else d
 
     def make_m_cond(self, d, s, x=None):
@@ -99,7 +120,7 @@ class OmniGenerator(nn.Module):
         assert x is not None or z is not None
         if z is None:
             z = self.encode(x)
-        with torch.no_grad():
+        with self._grad_ctx():
             if z_depth is None and self.opts.gen.m.use_dada:
                 _, z_depth = self.decoders["d"].forward_storage(z)
             logits = self.decoders["m"].forward_storage(z, cond, z_depth)
@@ -116,15 +137,13 @@ class OmniGenerator(nn.Module):
             z = self.encode(x)
         if return_z:
             out["z"] = z
-        with torch.no_grad():
-            if "d" in self.decoders:
-                d_st, z_depth = self.decoders["d"].forward_storage(z)
-                d = out["d"] = ops.from_storage(d_st, 1)
-            if return_z_depth:
-                out["z_depth"] = z_depth
-            if "s" in self.decoders:
-                s_st = self.decoders["s"].forward_storage(z, z_depth)
-                s = out["s"] = ops.from_storage(s_st, self.decoders["s"].output_dim)
+        if "d" in self.decoders:
+            d, z_depth = self.decode_d(z)
+            out["d"] = d
+        if return_z_depth:
+            out["z_depth"] = z_depth
+        if "s" in self.decoders:
+            s = out["s"] = self.decode_s(z, z_depth)
         if "m" in self.decoders:
             if s is not None and d is not None and self.opts.gen.m.use_spade:
                 cond = self.make_m_cond(d, s, x)

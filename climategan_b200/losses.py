@@ -147,3 +147,88 @@ class VGGLoss(nn.Module):
         for w, a, b, c in zip(self.weights, x_vgg, y_vgg, self.channels):
             loss = loss + w * ops.l1_loss_storage(a, b, c)
         return loss
+
+
+# ------------------------------------------------------------------------------------------------
+# masker losses — climategan/losses.py CrossEntropy :106-112, TVLoss :140-171, MinentLoss :177-196, SIGMLoss :232-278,
+# GroundIntersectionLoss :449-455, CustomBCELoss :466-477, ADVENTAdversarialLoss :480-524 — same call signatures, NCHW
+# fp32 tensors in, each evaluated by one or two libcgb200 kernels that emit the scalar and its gradient together.
+# ------------------------------------------------------------------------------------------------
+class CrossEntropy(nn.Module):
+    def __call__(self, logits, target):
+        return ops.cross_entropy_nchw(logits, target.to(logits.device).long())
+
+
+class TVLoss(nn.Module):
+    def __init__(self, tvloss_weight=1):
+        super().__init__()
+        self.tvloss_weight = tvloss_weight
+
+    def forward(self, x):
+        return self.tvloss_weight * ops.tv_loss(x)
+
+
+class MinentLoss(nn.Module):
+    def __init__(self, version=1, lambda_var=0.1):
+        super().__init__()
+        self.version = version
+        self.lambda_var = lambda_var
+
+    def __call__(self, pred):
+        assert pred.dim() == 4
+        return ops.minent_loss(pred, self.version, self.lambda_var)
+
+
+class SIGMLoss(nn.Module):
+    def __init__(self, gmweight=0.5, scale=4, device="cuda"):
+        super().__init__()
+        self.gmweight = gmweight
+        self.scale = scale
+
+    def __call__(self, prediction, target):
+        return ops.sigm_loss(prediction, target, self.gmweight, self.scale)
+
+
+class BCEWithLogits(nn.Module):
+    """nn.BCEWithLogitsLoss() with a tensor target (losses.py:419)."""
+
+    def __call__(self, prediction, target):
+        return ops.bce_logits_loss(prediction, target)
+
+
+class GroundIntersectionLoss(nn.Module):
+    def __call__(self, pred, pseudo_ground):
+        return ops.ground_intersection_loss(pred, pseudo_ground)
+
+
+class CustomBCELoss(nn.Module):
+    """BCE-with-logits against an int domain label (losses.py:466-477)."""
+
+    def __call__(self, prediction, target):
+        return ops.const_target_loss(prediction, ops.LOSS_BCE_LOGITS, float(target))
+
+
+class ADVENTAdversarialLoss(nn.Module):
+    """losses.py:480-524.  gan_type "GAN" -> CustomBCELoss; anything else -> the WGAN form
+    ``-mean(y*x + (1-y)*(1-x))`` (the reference's ``elif gan_type == "WGAN" or "WGAN_gp" or "WGAN_norm"`` is always true)."""
+
+    def __init__(self, opts, gan_type="GAN"):
+        super().__init__()
+        self.opts = opts
+        self.gan_type = gan_type
+        self.bce = CustomBCELoss() if gan_type == "GAN" else None
+
+    def loss(self, d_out, target):
+        if self.bce is not None:
+            return self.bce(d_out, target)
+        y = float(target)
+        neg_mean = ops.const_target_loss(d_out, ops.LOSS_NEG_MEAN)   # -mean(x)
+        # -mean(y x + (1-y)(1-x)) = (2y-1)*(-mean x) - (1-y)
+        return (2.0 * y - 1.0) * neg_mean - (1.0 - y)
+
+    def __call__(self, prediction, target, discriminator, depth_preds=None):
+        d_in = ops.prob_2_entropy(prediction, depth_preds)
+        d_out = discriminator(d_in)
+        if self.opts.dis.m.architecture == "OmniDiscriminator":
+            raise NotImplementedError("dis.m.architecture=OmniDiscriminator (multiDiscriminatorAdapter) is not built")
+        return self.loss(d_out, target)

@@ -54,8 +54,9 @@ class SpectralNorm(nn.Module):
 
     def effective_weight(self) -> torch.Tensor:
         m = self.module
-        return ops.spectral_weight(getattr(m, self.name + "_bar"), getattr(m, self.name + "_u").data,
-                                   getattr(m, self.name + "_v").data)
+        # u / v are passed as the Parameters themselves: the kernel updates their storage in place (as ``u.data = ...`` does,
+        # norms.py:106-108) and, when the trainer has flipped their requires_grad (discriminators), they receive gradients
+        return ops.spectral_weight(getattr(m, self.name + "_bar"), getattr(m, self.name + "_u"), getattr(m, self.name + "_v"))
 
     @property
     def bias(self):

@@ -473,17 +473,33 @@ class _SpectralWeight(Function):
         sigma = torch.empty((1,), dtype=torch.float32, device=w_bar.device)
         check(_L().cgb_spectral_power_iter(_p(wb), _p(u), _p(v), _p(sigma), rows, cols, _st()), "spectral_power_iter")
         w = wb / sigma
-        ctx.save_for_backward(w, u.detach().clone(), v.detach().clone(), sigma)
+        ctx.save_for_backward(w, sigma)
+        # u, v are kept BY REFERENCE, not snapshotted: the reference's autograd graph holds the u/v Parameters themselves and
+        # _update_u_v swaps their .data (norms.py:106-108), so when a layer runs twice before one backward (mask decoder and
+        # AdvEnt discriminators: r batch then s batch) both backward passes see the u, v of the last forward.  Kept as is.
+        ctx.u, ctx.v = u, v
         return w
 
     @staticmethod
     def backward(ctx, gw):
-        w, u, v, sigma = ctx.saved_tensors
+        w, sigma = ctx.saved_tensors
+        u, v = ctx.u, ctx.v
         rows = w.shape[0]
         # d(w_bar/sigma) = g/sigma - <g, w_bar>/sigma^2 * u v^T = (g - <g, w> u v^T) / sigma
         dot = (gw * w).sum()
         gwb = (gw - dot * torch.outer(u, v).view_as(w)) / sigma
-        return gwb.view_as(w), None, None
+        gu = gv = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            # Trainer.run_epoch un-freezes the discriminator with `param.requires_grad = True` on EVERY parameter
+            # (trainer.py:971-973), u and v included, so from then on sigma = u.(W v) is differentiated w.r.t. them too and
+            # ExtraAdam moves them: dL/dsigma = -<g, w_bar>/sigma^2 = -dot/sigma ; dsigma/du = W v ; dsigma/dv = W^T u.
+            w2 = (w * sigma).view(rows, -1)
+            coef = -dot / sigma
+            if ctx.needs_input_grad[1]:
+                gu = coef * torch.mv(w2, v)
+            if ctx.needs_input_grad[2]:
+                gv = coef * torch.mv(w2.t(), u)
+        return gwb.view_as(w), gu, gv
 
 
 def spectral_weight(w_bar, u, v):
@@ -672,54 +688,300 @@ def conv2d_infer(x, wp, bias, residual=None, *, k, stride=1, dil=1, pad=0, pad_m
     return conv_fwd_raw(x, wp, bias, residual, g)
 
 
+def _pool_out(sz):
+    o = -(-(sz - 3) // 2) + 1
+    if (o - 1) * 2 >= sz:
+        o -= 1
+    return o
+
+
+class _MaxPool3s2Ceil(Function):
+    @staticmethod
+    def forward(ctx, x):
+        _chk_storage(x)
+        n, hi, wi, c = x.shape
+        ho, wo = _pool_out(hi), _pool_out(wi)
+        y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
+        check(_L().cgb_maxpool3s2_ceil_fwd(_p(x), _p(y), _DT[x.dtype], n, hi, wi, ho, wo, c, _st()), "maxpool3s2_ceil")
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        n, hi, wi, c = x.shape
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        check(_L().cgb_maxpool3s2_ceil_bwd(_p(x), _p(gy), _p(gx), _DT[x.dtype], n, hi, wi, gy.shape[1], gy.shape[2], c, _st()),
+              "maxpool3s2_ceil_bwd")
+        return gx
+
+
 def maxpool3s2_ceil(x):
     """nn.MaxPool2d(3, stride=2, padding=0, ceil_mode=True) (deeplab/resnetmulti_v2.py:76-78)."""
-    _chk_storage(x)
-    n, hi, wi, c = x.shape
+    return _MaxPool3s2Ceil.apply(x)
 
-    def out(sz):
-        o = -(-(sz - 3) // 2) + 1
-        if (o - 1) * 2 >= sz:
-            o -= 1
-        return o
 
-    ho, wo = out(hi), out(wi)
-    y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
-    check(_L().cgb_maxpool3s2_ceil_fwd(_p(x), _p(y), _DT[x.dtype], n, hi, wi, ho, wo, c, _st()), "maxpool3s2_ceil")
-    return y
+class _ResizeBilinear(Function):
+    @staticmethod
+    def forward(ctx, x, ho, wo, ac):
+        _chk_storage(x)
+        n, hi, wi, c = x.shape
+        y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
+        check(_L().cgb_resize_bilinear_fwd(_p(x), _p(y), _DT[x.dtype], n, hi, wi, ho, wo, c, ac, _st()), "resize_bilinear")
+        ctx.meta = (n, hi, wi, c, ho, wo, ac)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, hi, wi, c, ho, wo, ac = ctx.meta
+        gy = gy.contiguous()
+        gx = torch.empty((n, hi, wi, c), dtype=gy.dtype, device=gy.device)
+        check(_L().cgb_resize_bilinear_bwd(_p(gy), _p(gx), _DT[gy.dtype], n, hi, wi, ho, wo, c, ac, _st()), "resize_bilinear_bwd")
+        return gx, None, None, None
 
 
 def resize_bilinear(x, ho, wo, align_corners=False):
-    _chk_storage(x)
-    n, hi, wi, c = x.shape
-    y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
-    check(_L().cgb_resize_bilinear_fwd(_p(x), _p(y), _DT[x.dtype], n, hi, wi, ho, wo, c, 1 if align_corners else 0, _st()),
-          "resize_bilinear")
-    return y
+    return _ResizeBilinear.apply(x, ho, wo, 1 if align_corners else 0)
 
 
 def resize_bicubic(x, ho, wo):
+    """Forward only (depth.py:144-149 runs it only when the prediction is not at the target size, i.e. at inference)."""
     _chk_storage(x)
+    if x.requires_grad and torch.is_grad_enabled():
+        raise NotImplementedError("bicubic resize has no backward (not on the training path at the reference's sizes)")
     n, hi, wi, c = x.shape
     y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
     check(_L().cgb_resize_bicubic_fwd(_p(x), _p(y), _DT[x.dtype], n, hi, wi, ho, wo, c, _st()), "resize_bicubic")
     return y
 
 
+class _ChannelMean(Function):
+    @staticmethod
+    def forward(ctx, x, c_logical):
+        _chk_storage(x)
+        n, h, w, cs = x.shape
+        y = torch.empty((n, h, w, 8), dtype=x.dtype, device=x.device)
+        check(_L().cgb_channel_mean(_p(x), _p(y), _DT[x.dtype], n * h * w, cs, c_logical, _st()), "channel_mean")
+        ctx.meta = (n, h, w, cs, c_logical)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, h, w, cs, c_logical = ctx.meta
+        gy = gy.contiguous()
+        gx = torch.empty((n, h, w, cs), dtype=gy.dtype, device=gy.device)
+        check(_L().cgb_channel_mean_bwd(_p(gy), _p(gx), _DT[gy.dtype], n * h * w, cs, c_logical, _st()), "channel_mean_bwd")
+        return gx, None
+
+
 def channel_mean(x, c_logical):
-    _chk_storage(x)
-    n, h, w, cs = x.shape
-    y = torch.empty((n, h, w, 8), dtype=x.dtype, device=x.device)
-    check(_L().cgb_channel_mean(_p(x), _p(y), _DT[x.dtype], n * h * w, cs, c_logical, _st()), "channel_mean")
+    """torch.mean(x, dim=1, keepdim=True) (depth.py:142) -> storage [N,H,W,8] with 1 real channel."""
+    return _ChannelMean.apply(x, c_logical)
+
+
+def _mul_raw(a, b):
+    y = torch.empty_like(a)
+    check(_L().cgb_mul(_p(a), _p(b), _p(y), _DT[a.dtype], a.numel(), _st()), "mul")
     return y
+
+
+class _Mul(Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        _chk_storage(a)
+        assert a.shape == b.shape and a.dtype == b.dtype
+        b = b.contiguous()
+        ctx.save_for_backward(a, b)
+        return _mul_raw(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.contiguous()
+        ga = _mul_raw(g, b) if ctx.needs_input_grad[0] else None
+        gb = _mul_raw(g, a) if ctx.needs_input_grad[1] else None
+        return ga, gb
 
 
 def mul(a, b):
-    _chk_storage(a)
-    assert a.shape == b.shape and a.dtype == b.dtype
-    y = torch.empty_like(a)
-    check(_L().cgb_mul(_p(a), _p(b.contiguous()), _p(y), _DT[a.dtype], a.numel(), _st()), "mul")
-    return y
+    """Elementwise product of two storage tensors (z * z_depth, deeplab_v2.py:193, blocks.py:306)."""
+    return _Mul.apply(a, b)
+
+
+def _broadcast_hw_raw(src, h, w, scale):
+    n, c = src.shape[0], src.shape[-1]
+    dst = torch.empty((n, h, w, c), dtype=src.dtype, device=src.device)
+    check(_L().cgb_broadcast_hw(_p(src.contiguous()), _p(dst), _DT[src.dtype], n, h * w, c, float(scale), _st()), "broadcast_hw")
+    return dst
+
+
+def _spatial_mean(x):
+    mean, _ = instnorm_stats(x)
+    return mean
+
+
+class _GlobalMean(Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
+        return _spatial_mean(x).to(x.dtype).view(x.shape[0], 1, 1, x.shape[-1]).contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        n, h, w, c = ctx.shape
+        return _broadcast_hw_raw(g.contiguous(), h, w, 1.0 / (h * w))
+
+
+def global_mean(x):
+    """AdaptiveAvgPool2d(1) as a storage tensor [N,1,1,Cs] (ASPP global branch, deeplab_v2.py:97-102)."""
+    return _GlobalMean.apply(x)
+
+
+class _BroadcastHW(Function):
+    @staticmethod
+    def forward(ctx, x, h, w):
+        ctx.hw = (h, w)
+        return _broadcast_hw_raw(x, h, w, 1.0)
+
+    @staticmethod
+    def backward(ctx, g):
+        h, w = ctx.hw
+        g = g.contiguous()
+        gm = (_spatial_mean(g) * float(h * w)).to(g.dtype)
+        return gm.view(g.shape[0], 1, 1, g.shape[-1]).contiguous(), None, None
+
+
+def broadcast_hw(x, h, w):
+    """F.interpolate of a 1x1 map to (h, w) (bilinear, align_corners=True: a pure broadcast; deeplab_v2.py:116)."""
+    assert x.shape[1] == 1 and x.shape[2] == 1
+    return _BroadcastHW.apply(x, h, w)
+
+
+class _ReflectPad(Function):
+    @staticmethod
+    def forward(ctx, x, pad):
+        _chk_storage(x)
+        n, h, w, c = x.shape
+        y = torch.empty((n, h + 2 * pad, w + 2 * pad, c), dtype=x.dtype, device=x.device)
+        check(_L().cgb_reflect_pad_fwd(_p(x), _p(y), _DT[x.dtype], n, h, w, c, pad, _st()), "reflect_pad_fwd")
+        ctx.meta = (n, h, w, c, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, h, w, c, pad = ctx.meta
+        gy = gy.contiguous()
+        gx = torch.empty((n, h, w, c), dtype=gy.dtype, device=gy.device)
+        check(_L().cgb_reflect_pad_bwd(_p(gy), _p(gx), _DT[gy.dtype], n, h, w, c, pad, _st()), "reflect_pad_bwd")
+        return gx, None
+
+
+def reflect_pad(x, pad):
+    """nn.ReflectionPad2d(pad) (blocks.py:66-67) as an explicit padded copy: the conv that follows then runs with pad 0
+    on the tcgen05 engine, and the adjoint folds the border gradients back."""
+    return x if pad == 0 else _ReflectPad.apply(x, pad)
+
+
+class _Dropout(Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        _chk_storage(x)
+        y = torch.empty_like(x)
+        check(_L().cgb_dropout(_p(x), _p(y), _DT[x.dtype], x.numel(), p, seed, _st()), "dropout")
+        ctx.meta = (p, seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        p, seed = ctx.meta
+        g = g.contiguous()
+        gx = torch.empty_like(g)
+        check(_L().cgb_dropout(_p(g), _p(gx), _DT[g.dtype], g.numel(), p, seed, _st()), "dropout_bwd")
+        return gx, None, None
+
+
+_dropout_calls = [0]
+
+
+def dropout(x, p, training):
+    """nn.Dropout(p) (deeplab_v2.py:106,148,152).  The keep-mask comes from a counter-based hash of (seed, element index);
+    the seed is drawn from torch's CPU generator so torch.manual_seed makes runs reproducible."""
+    if not training or p == 0.0:
+        return x
+    _dropout_calls[0] += 1
+    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return _Dropout.apply(x, float(p), seed)
+
+
+class _BatchNormAct(Function):
+    """act(BatchNorm2d(x) (+ residual)) with batch statistics (train) or running statistics (eval) — one statistics pass
+    and one apply pass over x; the backward is two passes (see include/cgb200.h)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, momentum, eps, act, slope):
+        _chk_storage(x)
+        n, h, w, cs = x.shape
+        npix = n * h * w
+        c = weight.numel() if weight is not None else (running_mean.numel() if running_mean is not None else cs)
+        dev = x.device
+        if training or running_mean is None:
+            mean, rstd = instnorm_stats(x.view(1, npix, 1, cs), eps)
+            mean, rstd = mean.view(cs), rstd.view(cs)
+            if running_mean is not None and training:
+                check(_L().cgb_bn_update_running(_p(mean), _p(rstd), _p(running_mean), _p(running_var), c, npix,
+                                                 float(momentum), float(eps), _st()), "bn_update_running")
+        else:
+            mean = torch.zeros(cs, dtype=torch.float32, device=dev)
+            rstd = torch.ones(cs, dtype=torch.float32, device=dev)
+            mean[:c] = running_mean
+            rstd[:c] = torch.rsqrt(running_var + eps)
+        wp = bp = None
+        if weight is not None:
+            wp = torch.zeros(cs, dtype=torch.float32, device=dev)
+            wp[:c] = weight.detach()
+            bp = torch.zeros(cs, dtype=torch.float32, device=dev)
+            bp[:c] = bias.detach()
+        y = torch.empty_like(x)
+        res = residual.contiguous() if residual is not None else None
+        check(_L().cgb_bn_apply_fwd(_p(x), _p(mean), _p(rstd), _p(wp), _p(bp), _p(res), _p(y), _DT[x.dtype], npix, cs, act,
+                                    slope, _st()), "bn_apply_fwd")
+        ctx.save_for_backward(x, mean, rstd, wp, y if act != _lib.ACT_NONE else None)
+        ctx.meta = (act, slope, c, residual is not None, bool(training or running_mean is None))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, mean, rstd, wp, y = ctx.saved_tensors
+        act, slope, c, has_res, batch_stats = ctx.meta
+        n, h, w, cs = x.shape
+        npix = n * h * w
+        gy = gy.contiguous()
+        gpre = torch.empty_like(x)
+        sums = torch.empty((cs, 2), dtype=torch.float64, device=x.device)
+        check(_L().cgb_bn_apply_bwd(_p(x), _p(mean), _p(rstd), _p(y), _p(gy), _p(gpre), _p(sums), _DT[x.dtype], npix, cs, act,
+                                    slope, _st()), "bn_apply_bwd")
+        gw = gb = gx = None
+        if wp is not None and ctx.needs_input_grad[1]:
+            gw = sums[:c, 1].float()
+        if wp is not None and ctx.needs_input_grad[2]:
+            gb = sums[:c, 0].float()
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            s = sums if batch_stats else torch.zeros_like(sums)
+            check(_L().cgb_bn_bwd_finalize(_p(x), _p(mean), _p(rstd), _p(wp), _p(s), _p(gpre), _p(gx), _DT[x.dtype], npix, cs,
+                                           _st()), "bn_bwd_finalize")
+        return gx, gw, gb, (gpre if has_res else None), None, None, None, None, None, None, None
+
+
+def batchnorm_act(x, bn, residual=None, act=_lib.ACT_NONE, slope=0.2):
+    """``act(bn(x) (+ residual))`` for an ``nn.BatchNorm2d`` parameter container ``bn`` (train: batch statistics + running
+    update, exactly F.batch_norm's semantics; eval: running statistics)."""
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    return _BatchNormAct.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.training, momentum, bn.eps,
+                               act, slope)
 
 
 def make_m_cond(d, s, xr, ns):
@@ -736,7 +998,169 @@ def make_m_cond(d, s, xr, ns):
     return out
 
 
-def global_mean(x):
-    """AdaptiveAvgPool2d(1) as a storage tensor [N,1,1,Cs] (ASPP global branch, deeplab_v2.py:97-102)."""
-    mean, _ = instnorm_stats(x)
-    return mean.to(x.dtype).view(x.shape[0], 1, 1, x.shape[-1]).contiguous()
+# ------------------------------------------------------------------------------------------------
+# masker losses (NCHW fp32 tensors, as Trainer.masker_{d,s,m}_loss receive them; trainer.py:1389-1616)
+# ------------------------------------------------------------------------------------------------
+def _f32c(t):
+    return t.contiguous().float()
+
+
+class _SoftmaxNCHW(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _f32c(x)
+        n, c, h, w = x.shape
+        y = torch.empty_like(x)
+        check(_L().cgb_softmax_nchw_fwd(_p(x), _p(y), n, c, h * w, _st()), "softmax_nchw_fwd")
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (y,) = ctx.saved_tensors
+        n, c, h, w = y.shape
+        gx = torch.empty_like(y)
+        check(_L().cgb_softmax_nchw_bwd(_p(y), _p(_f32c(gy)), _p(gx), n, c, h * w, _st()), "softmax_nchw_bwd")
+        return gx
+
+
+def softmax_nchw(x):
+    """torch.softmax(x, dim=1) (trainer.py:1449,1475)."""
+    return _SoftmaxNCHW.apply(x)
+
+
+class _FusedLoss(Function):
+    """Loss kernels that produce the scalar and the gradient w.r.t. their first argument in one pass."""
+
+    @staticmethod
+    def forward(ctx, x, run):
+        x = _f32c(x)
+        loss = torch.zeros((), dtype=torch.float32, device=x.device)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        run(x, loss, gx)
+        ctx.save_for_backward(gx)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (gx,) = ctx.saved_tensors
+        return (gx * g if gx is not None else None), None
+
+
+def cross_entropy_nchw(logits, target):
+    """nn.CrossEntropyLoss()(logits [N,C,H,W], target [N,H,W] int64) (losses.py:106-112)."""
+    n, c, h, w = logits.shape
+    tgt = target.contiguous().long()
+    assert tgt.shape == (n, h, w), (tgt.shape, logits.shape)
+
+    def run(x, loss, gx):
+        check(_L().cgb_cross_entropy_nchw(_p(x), _p(tgt), _p(loss), _p(gx), n, c, h * w, _st()), "cross_entropy_nchw")
+
+    return _FusedLoss.apply(logits, run)
+
+
+def minent_loss(prob, version=1, lambda_var=0.1):
+    """MinentLoss (losses.py:177-196) on a probability map [N,C,H,W]."""
+    n, c, h, w = prob.shape
+
+    def run(x, loss, gx):
+        acc = torch.empty((1,), dtype=torch.float64, device=x.device)
+        check(_L().cgb_minent_loss(_p(x), _p(loss), _p(gx), _p(acc), n, c, h * w, version, float(lambda_var), _st()), "minent_loss")
+
+    return _FusedLoss.apply(prob, run)
+
+
+def tv_loss(x):
+    """TVLoss(tvloss_weight=1) (losses.py:140-171)."""
+    n, c, h, w = x.shape
+
+    def run(xx, loss, gx):
+        check(_L().cgb_tv_loss(_p(xx), _p(loss), _p(gx), n, c, h, w, _st()), "tv_loss")
+
+    return _FusedLoss.apply(x, run)
+
+
+def bce_logits_loss(x, target):
+    """nn.BCEWithLogitsLoss()(x, target) with a tensor target (losses.py:419; trainer.py:1550)."""
+    tgt = _f32c(target.detach())
+    assert tgt.shape == x.shape, (tgt.shape, x.shape)
+
+    def run(xx, loss, gx):
+        check(_L().cgb_bce_logits_loss(_p(xx), _p(tgt), _p(loss), _p(gx), xx.numel(), _st()), "bce_logits_loss")
+
+    return _FusedLoss.apply(x, run)
+
+
+def ground_intersection_loss(pred, ground):
+    """GroundIntersectionLoss (losses.py:449-455): mean(1.0 * ((ground - pred) > 0.5)); piecewise constant (no gradient)."""
+    p, g = _f32c(pred.detach()), _f32c(ground.detach())
+    loss = torch.zeros((), dtype=torch.float32, device=p.device)
+    check(_L().cgb_ground_intersection_loss(_p(p), _p(g), _p(loss), p.numel(), _st()), "ground_intersection_loss")
+    return loss
+
+
+def sigm_loss(pred, target, gmweight=0.5, scales=4):
+    """SIGMLoss(gmweight, scale=4) (losses.py:232-278) on depth maps [N,1,H,W]."""
+    n, c, h, w = pred.shape
+    assert c == 1 and tuple(target.shape) == tuple(pred.shape), (pred.shape, target.shape)
+    tgt = _f32c(target.detach())
+
+    def run(x, loss, gx):
+        ws = torch.empty((16 + 2 * x.numel(),), dtype=torch.float32, device=x.device)
+        if gx is None:
+            gx = torch.empty_like(x)
+        check(_L().cgb_sigm_loss(_p(x), _p(tgt), _p(loss), _p(gx), _p(ws), n, h, w, float(gmweight), scales, _st()), "sigm_loss")
+
+    return _FusedLoss.apply(pred, run)
+
+
+class _EntropyNCHW(Function):
+    @staticmethod
+    def forward(ctx, prob, depth):
+        prob = _f32c(prob)
+        n, c, h, w = prob.shape
+        d = None if depth is None else _f32c(depth.detach())
+        if d is not None:
+            assert d.shape == (n, 1, h, w), (d.shape, prob.shape)
+        out = torch.empty_like(prob)
+        check(_L().cgb_entropy_nchw(_p(prob), _p(d), None, _p(out), n, c, h * w, 0, _st()), "entropy_nchw")
+        ctx.save_for_backward(prob, d)
+        return out
+
+    @staticmethod
+    def backward(ctx, ge):
+        prob, d = ctx.saved_tensors
+        n, c, h, w = prob.shape
+        gp = torch.empty_like(prob)
+        check(_L().cgb_entropy_nchw(_p(prob), _p(d), _p(_f32c(ge)), _p(gp), n, c, h * w, 1, _st()), "entropy_nchw_bwd")
+        return gp, None
+
+
+def prob_2_entropy(prob, depth=None):
+    """prob_2_entropy(prob) [* depth] (losses.py:466-471, 541-543): the AdvEnt discriminator's input."""
+    return _EntropyNCHW.apply(prob, depth)
+
+
+class _SigmoidPair(Function):
+    @staticmethod
+    def forward(ctx, logits):
+        logits = _f32c(logits)
+        n, c, h, w = logits.shape
+        assert c == 1
+        out = torch.empty((n, 2, h, w), dtype=torch.float32, device=logits.device)
+        check(_L().cgb_sigmoid_pair(_p(logits), None, _p(out), n, h * w, 0, _st()), "sigmoid_pair")
+        ctx.save_for_backward(logits)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (logits,) = ctx.saved_tensors
+        n, _, h, w = logits.shape
+        gl = torch.empty_like(logits)
+        check(_L().cgb_sigmoid_pair(_p(logits), _p(_f32c(g)), _p(gl), n, h * w, 1, _st()), "sigmoid_pair_bwd")
+        return gl
+
+
+def sigmoid_pair(logits):
+    """cat([sigmoid(l), 1 - sigmoid(l)], dim=1) (trainer.py:1532-1534) for mask logits [N,1,H,W]."""
+    return _SigmoidPair.apply(logits)

@@ -64,3 +64,20 @@ class GradBucket:
                 p.grad = v.clone()
             else:
                 p.grad.copy_(v)
+
+
+def allreduce_flat_grads(optimizer, group: Optional[dist.ProcessGroup] = None) -> int:
+    """Average the optimiser's flat fp32 gradient buffers (``ExtraAdam.flat_grads``: parameters and ``.grad``s are views of one
+    buffer per parameter group, so there is no pack / unpack copy) over the process group: one all-reduce per group.
+    Returns the number of bytes reduced (0 when not distributed)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 0
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 0
+    total = 0
+    for flat in optimizer.flat_grads:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.mul_(1.0 / world)
+        total += flat.numel() * 4
+    return total

@@ -14,7 +14,9 @@ import torch
 from . import ops
 from .discriminator import create_discriminator
 from .generator import create_generator
-from .losses import FeatMatchLoss, GANLoss, HingeLoss, VGGLoss
+from .losses import (ADVENTAdversarialLoss, BCEWithLogits, CrossEntropy, FeatMatchLoss, GANLoss, GroundIntersectionLoss,
+                     HingeLoss, MinentLoss, SIGMLoss, TVLoss, VGGLoss)
+from .discriminator import fc_discriminator_forward
 from .optim import get_optimizer
 from .utils import Dict
 
@@ -40,6 +42,24 @@ def get_losses(opts, verbose=0, device=None, storage_dtype=torch.bfloat16):
             losses["G"]["p"]["vgg"] = VGGLoss(device, storage_dtype=storage_dtype)
         losses["G"]["p"]["featmatch"] = FeatMatchLoss()
         losses["D"]["p"] = losses["G"]["p"]["gan"]
+    if "d" in opts.tasks:
+        if opts.gen.d.classify.enable or opts.gen.d.loss == "dada":
+            raise NotImplementedError("depth loss: only gen.d.loss='sigm' without classification (defaults.yaml:124,127) is built")
+        losses["G"]["tasks"]["d"] = SIGMLoss(opts.train.lambdas.G.d.gml)
+    if "s" in opts.tasks:
+        losses["G"]["tasks"]["s"] = {"crossent": CrossEntropy(), "minent": MinentLoss(),
+                                     "advent": ADVENTAdversarialLoss(opts, gan_type=opts.dis.s.gan_type)}
+    if "m" in opts.tasks:
+        losses["G"]["tasks"]["m"] = {
+            "bce": BCEWithLogits(),
+            "minent": (MinentLoss(version=2, lambda_var=opts.train.lambdas.advent.ent_var) if opts.gen.m.use_minent_var
+                       else MinentLoss()),
+            "tv": TVLoss(),
+            "advent": ADVENTAdversarialLoss(opts, gan_type=opts.dis.m.gan_type),
+            "gi": GroundIntersectionLoss(),
+        }
+    if "m" in opts.tasks or "s" in opts.tasks:
+        losses["D"]["advent"] = ADVENTAdversarialLoss(opts)   # losses.py:440: always gan_type="GAN" (BCE), as the reference
     return losses
 
 
@@ -65,8 +85,10 @@ class Trainer:
         self.G = self.D = self.g_opt = self.d_opt = self.losses = None
         self.g_scheduler = self.d_scheduler = None
         self.kitti_pretrain = False
-        if any(t in opts.tasks for t in "msd"):
-            raise NotImplementedError("Trainer is built for the painter task only so far (tasks=['p'])")
+        self.use_pl4m = False
+        self.data_parallel = False
+        self.pseudo_training_tasks = set(opts.train.pseudo.tasks or [])
+        self.domain_labels = {"s": 0, "r": 1}
 
     @property
     def has_painter(self):
@@ -109,14 +131,25 @@ class Trainer:
 
     @staticmethod
     def _set_requires_grad(net, flag):
+        """run_epoch's freeze / un-freeze of the discriminator (trainer.py:958-973): EVERY parameter, the spectral-norm u / v
+        vectors included — after the first un-freeze they are trained by ExtraAdam like any weight (reference behaviour)."""
         for p in net.parameters():
-            if p.dtype.is_floating_point and not (p.requires_grad is False and getattr(p, "_cgb_frozen", False)):
-                pass
-        # spectral-norm u/v are permanent non-trainable parameters: never flip them
-        for name, p in net.named_parameters():
-            if name.endswith(("weight_u", "weight_v")):
-                continue
             p.requires_grad_(flag)
+
+    # ---------------------------------------------------------------- data parallelism
+    def enable_data_parallel(self, group=None):
+        """One process per GPU, each with its own slice of every domain batch: after each backward the flat G (or D) gradient
+        buffer is averaged over the ranks (NCCL all-reduce), then every rank applies the same ExtraAdam update.
+        BatchNorm statistics stay per-rank, as wrapping the reference in DDP (no SyncBN) would leave them."""
+        self.data_parallel = True
+        self._dp_group = group
+        return self
+
+    def _sync_grads(self, opt):
+        if self.data_parallel:
+            from .parallel import allreduce_flat_grads
+
+            allreduce_flat_grads(opt, self._dp_group)
 
     # ---------------------------------------------------------------- update steps
     def update_G(self, multi_domain_batch, verbose=0):
@@ -124,6 +157,7 @@ class Trainer:
         self.g_opt.zero_grad()
         g_loss = self.get_G_loss(multi_domain_batch, verbose)
         g_loss.backward()
+        self._sync_grads(self.g_opt)
         self.g_opt_step()
         self._set_requires_grad(self.D, True)    # trainer.py:971-973
         self.logger.log_losses(model_to_update="G", mode="train")
@@ -133,13 +167,19 @@ class Trainer:
         self.d_opt.zero_grad()
         d_loss = self.get_D_loss(multi_domain_batch, verbose)
         d_loss.backward()
+        self._sync_grads(self.d_opt)
         self.d_opt_step()
         self.logger.losses.disc.total_loss = d_loss.detach()
         self.logger.log_losses(model_to_update="D", mode="train")
         return d_loss
 
     def get_G_loss(self, multi_domain_batch, verbose=0):
+        """trainer.py:1162-1182."""
         g_loss = 0
+        if any(t in self.opts.tasks for t in "msd"):
+            m_loss = self.get_masker_loss(multi_domain_batch)
+            self.logger.losses.gen.masker = m_loss.detach()
+            g_loss = g_loss + m_loss
         if "p" in self.opts.tasks and not self.kitti_pretrain:
             p_loss = self.get_painter_loss(multi_domain_batch)
             self.logger.losses.gen.painter = p_loss.detach()
@@ -147,6 +187,162 @@ class Trainer:
         assert not isinstance(g_loss, int), "No update in get_G_loss!"
         self.logger.losses.gen.total_loss = g_loss.detach()
         return g_loss
+
+    # ---------------------------------------------------------------- masker
+    def _advent_D(self, task):
+        net = self.D[task]["Advent"]
+        return lambda t: fc_discriminator_forward(net, t, self.storage_dtype)
+
+    def get_masker_loss(self, multi_domain_batch):
+        """trainer.py:1184-1254."""
+        m_loss = 0
+        for domain, batch in multi_domain_batch.items():
+            if domain == "rf":
+                continue
+            x = batch["data"]["x"]
+            z = self.G.encode(x)
+            d_pred = s_pred = z_depth = None
+            for task in ["d", "s", "m"]:
+                if task not in batch["data"] or task not in self.opts.tasks:
+                    continue
+                target = batch["data"][task]
+                if task == "d":
+                    loss, d_pred, z_depth = self.masker_d_loss(x, z, target, domain, "G")
+                    m_loss = m_loss + loss
+                    self.logger.losses.gen.task["d"][domain] = loss.detach()
+                elif task == "s":
+                    loss, s_pred = self.masker_s_loss(x, z, d_pred, z_depth, target, domain, "G")
+                    m_loss = m_loss + loss
+                    self.logger.losses.gen.task["s"][domain] = loss.detach()
+                elif task == "m":
+                    cond = None
+                    if self.opts.gen.m.use_spade:
+                        raise NotImplementedError("gen.m.use_spade (MaskSpadeDecoder) is not built")
+                    loss, _ = self.masker_m_loss(x, z, target, domain, "G", cond=cond, z_depth=z_depth, depth_preds=d_pred)
+                    m_loss = m_loss + loss
+                    self.logger.losses.gen.task["m"][domain] = loss.detach()
+        return m_loss
+
+    def _zero(self):
+        return torch.zeros((), dtype=torch.float32, device=self.device)
+
+    def masker_d_loss(self, x, z, target, domain, for_="G"):
+        """trainer.py:1389-1407."""
+        assert for_ in {"G", "D"}
+        assert x.shape[0] == target.shape[0]
+        weight = self.opts.train.lambdas.G.d.main
+        prediction, z_depth = self.G.decode_d(z)
+        if weight == 0 or (domain == "r" and "d" not in self.pseudo_training_tasks):
+            return self._zero(), prediction, z_depth    # the reference evaluates the loss and discards it
+        full_loss = self.losses["G"]["tasks"]["d"](prediction, target) * weight
+        return full_loss, prediction, z_depth
+
+    def masker_s_loss(self, x, z, depth_preds, z_depth, target, domain, for_="G"):
+        """trainer.py:1409-1516."""
+        assert for_ in {"G", "D"}
+        assert domain in {"r", "s"}
+        full_loss = self._zero()
+        softmax_preds = None
+        pred = None
+        lam = self.opts.train.lambdas
+        if for_ == "G" or self.opts.gen.s.use_advent:
+            pred = self.G.decode_s(z, z_depth)
+        if for_ == "G":
+            if domain == "s" or "s" in self.pseudo_training_tasks:
+                key = "crossent" if domain == "s" else "crossent_pseudo"
+                weight = lam.G["s"][key]
+                if weight != 0:
+                    loss = self.losses["G"]["tasks"]["s"]["crossent"](pred, target.squeeze(1)) * weight
+                    full_loss = full_loss + loss
+                    self.logger.losses.gen.task["s"][key][domain] = loss.detach()
+            if domain == "r":
+                weight = lam.G["s"]["minent"]
+                if self.opts.gen.s.use_minent and weight != 0:
+                    softmax_preds = ops.softmax_nchw(pred)
+                    loss = self.losses["G"]["tasks"]["s"]["minent"](softmax_preds) * weight
+                    full_loss = full_loss + loss
+                    self.logger.losses.gen.task["s"]["minent"]["r"] = loss.detach()
+        if self.opts.gen.s.use_advent:
+            if self.opts.gen.s.use_dada and depth_preds is not None:
+                depth_preds = depth_preds.detach()
+            else:
+                depth_preds = None
+            if for_ == "D":
+                domain_label = domain
+                logger = {}
+                loss_func = self.losses["D"]["advent"]
+                pred = pred.detach()
+                weight = lam.advent.adv_main
+            else:
+                domain_label = "s"
+                logger = self.logger.losses.gen.task["s"]["advent"]
+                loss_func = self.losses["G"]["tasks"]["s"]["advent"]
+                weight = lam.G["s"]["advent"]
+            if (for_ == "D" or domain == "r") and weight != 0:
+                if softmax_preds is None:
+                    softmax_preds = ops.softmax_nchw(pred)
+                loss = loss_func(softmax_preds, self.domain_labels[domain_label], self._advent_D("s"), depth_preds) * weight
+                full_loss = full_loss + loss
+                logger[domain] = loss.detach()
+                # trainer.py:1487: `gan_type == "GAN" or "WGAN_norm"` is always true -> never any clipping / gradient penalty
+        return full_loss, pred
+
+    def masker_m_loss(self, x, z, target, domain, for_="G", cond=None, z_depth=None, depth_preds=None):
+        """trainer.py:1518-1616."""
+        assert for_ in {"G", "D"}
+        assert domain in {"r", "s"}
+        full_loss = self._zero()
+        lam = self.opts.train.lambdas
+        pred_logits = self.G.decode_m(z, cond=cond, z_depth=z_depth)
+        prob = ops.sigmoid_pair(pred_logits)            # cat[sigmoid(l), 1 - sigmoid(l)]
+        pred_prob = prob[:, :1]
+        if for_ == "G":
+            weight = lam.G.m.tv
+            if weight != 0:
+                loss = self.losses["G"]["tasks"]["m"]["tv"](pred_prob) * weight
+                full_loss = full_loss + loss
+                self.logger.losses.gen.task["m"]["tv"][domain] = loss.detach()
+            weight = lam.G.m.bce
+            if domain == "s" and weight != 0:
+                loss = self.losses["G"]["tasks"]["m"]["bce"](pred_logits, target) * weight
+                full_loss = full_loss + loss
+                self.logger.losses.gen.task["m"]["bce"]["s"] = loss.detach()
+            if domain == "r":
+                weight = lam.G["m"]["gi"]
+                if self.opts.gen.m.use_ground_intersection and weight != 0:
+                    loss = self.losses["G"]["tasks"]["m"]["gi"](pred_prob, target) * weight
+                    full_loss = full_loss + loss
+                    self.logger.losses.gen.task["m"]["gi"]["r"] = loss.detach()
+                weight = lam.G.m.pl4m
+                if self.use_pl4m and weight != 0:
+                    raise NotImplementedError("painter loss for the masker (pl4m; off until epoch 49, defaults.yaml:147) is not built")
+                weight = lam.advent.ent_main
+                if self.opts.gen.m.use_minent and weight != 0:
+                    loss = self.losses["G"]["tasks"]["m"]["minent"](prob) * weight
+                    full_loss = full_loss + loss
+                    self.logger.losses.gen.task["m"]["minent"]["r"] = loss.detach()
+        if self.opts.gen.m.use_advent:
+            if self.opts.gen.m.use_dada and depth_preds is not None:
+                dp = ops.to_storage(depth_preds.detach(), self.storage_dtype)
+                depth_preds = ops.from_storage(ops.resize_nearest(dp, x.shape[-2], x.shape[-1]), 1)
+            else:
+                depth_preds = None
+            if for_ == "D":
+                domain_label = domain
+                logger = {}
+                loss_func = self.losses["D"]["advent"]
+                prob = prob.detach()
+                weight = lam.advent.adv_main
+            else:
+                domain_label = "s"
+                logger = self.logger.losses.gen.task["m"]["advent"]
+                loss_func = self.losses["G"]["tasks"]["m"]["advent"]
+                weight = lam.advent.adv_main
+            if (for_ == "D" or domain == "r") and weight != 0:
+                loss = loss_func(prob, self.domain_labels[domain_label], self._advent_D("m"), depth_preds) * weight
+                full_loss = full_loss + loss
+                logger[domain] = loss.detach()
+        return full_loss, prob
 
     def get_painter_loss(self, multi_domain_batch):
         """trainer.py:1256-1387 (vgg, gan, featmatch; tv/context/reconstruction have lambda 0 in defaults.yaml:294-299)."""
@@ -179,8 +375,9 @@ class Trainer:
         return step_loss
 
     def get_D_loss(self, multi_domain_batch, verbose=0):
-        """trainer.py:1034-1160, painter branch."""
-        disc_loss = {"p": {"gan": 0}}
+        """trainer.py:1034-1160."""
+        disc_loss = {"m": {"Advent": 0}, "s": {"Advent": 0}, "p": {"gan": 0}}
+        lam = self.opts.train.lambdas
         for domain, batch in multi_domain_batch.items():
             x = batch["data"]["x"]
             if domain == "rf" and self.has_painter:
@@ -194,9 +391,38 @@ class Trainer:
                 real_d, fake_d = divide_pred(real_fake_d)
                 disc_loss["p"]["gan"] = (self.losses["D"]["p"](fake_d, False, True)
                                          + self.losses["D"]["p"](real_d, True, True))
+            elif domain != "rf" and any(t in self.opts.tasks for t in "msd"):
+                # every generator output is detached before it reaches a discriminator (trainer.py:1467,1585), so the
+                # generator runs without an autograd tape here; BatchNorm still runs on (and updates) batch statistics.
+                with torch.no_grad():
+                    z = self.G.encode(x)
+                    s_pred = d_pred = cond = z_depth = None
+                    if "s" in batch["data"] and "s" in self.opts.tasks:
+                        if "d" in self.opts.tasks and self.opts.gen.s.use_dada:
+                            d_pred, z_depth = self.G.decode_d(z)
+                if "s" in batch["data"] and "s" in self.opts.tasks:
+                    step_loss, s_pred = self._no_g_tape(self.masker_s_loss, x, z, d_pred, z_depth, None, domain, for_="D")
+                    disc_loss["s"]["Advent"] = disc_loss["s"]["Advent"] + step_loss * lam.advent.adv_main
+                if "m" in batch["data"] and "m" in self.opts.tasks:
+                    if "d" in self.opts.tasks and self.opts.gen.m.use_dada and d_pred is None:
+                        with torch.no_grad():
+                            d_pred, z_depth = self.G.decode_d(z)
+                    step_loss, _ = self._no_g_tape(self.masker_m_loss, x, z, None, domain, for_="D", cond=cond,
+                                                   z_depth=z_depth, depth_preds=d_pred)
+                    disc_loss["m"]["Advent"] = disc_loss["m"]["Advent"] + step_loss * lam.advent.adv_main
         self.logger.losses.disc.update({dom: {k: (v.detach() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
                                         for dom, d in disc_loss.items()})
         return sum(v for d in disc_loss.values() for v in d.values())
+
+    def _no_g_tape(self, fn, *args, **kwargs):
+        """Run a masker_*_loss(for_="D") with the generator's decoders un-taped (their outputs are detached by the loss)."""
+        G = self.G
+        orig = G._grad_ctx
+        G._grad_ctx = torch.no_grad
+        try:
+            return fn(*args, **kwargs)
+        finally:
+            G._grad_ctx = orig
 
     def losses_to_host(self):
         """One sync for all logged scalars (the reference calls .item() ~10x per step)."""

@@ -18,9 +18,9 @@ class Dict(dict):
     @classmethod
     def _wrap(cls, v):
         if isinstance(v, dict) and not isinstance(v, Dict):
-            return cls(v)
+            return Dict(v)
         if isinstance(v, (list, tuple)):
-            return type(v)(cls._wrap(i) for i in v)
+            return type(v)(Dict._wrap(i) for i in v)
         return v
 
     def __getattr__(self, k):
@@ -38,6 +38,18 @@ class Dict(dict):
 
     def __deepcopy__(self, memo):
         return Dict({k: copy.deepcopy(v, memo) for k, v in self.items()})
+
+    def update(self, *args, **kwargs):
+        """addict.Dict.update: recursive merge of nested dicts."""
+        other = {}
+        if args:
+            other.update(args[0])
+        other.update(kwargs)
+        for k, v in other.items():
+            if k in self and isinstance(self[k], dict) and isinstance(v, dict):
+                self[k].update(v)
+            else:
+                self[k] = self._wrap(v)
 
     def to_dict(self):
         return {k: (v.to_dict() if isinstance(v, Dict) else v) for k, v in self.items()}
@@ -62,6 +74,10 @@ class _Pending(Dict):
     def __setitem__(self, k, v):
         self._attach()
         dict.__setitem__(self, k, v)
+
+    def update(self, *args, **kwargs):
+        self._attach()
+        Dict.update(self, *args, **kwargs)
 
 
 def default_painter_opts(latent_dim=640, spade_n_up=7, tasks=("p",), ndf=64, n_layers=4, num_D=3):
@@ -113,3 +129,58 @@ def default_masker_opts(tasks=("m", "s", "d"), nblocks=(3, 4, 23, 3), size=640, 
                    spade=Dict(latent_dim=128, detach=False, cond_nc=15, spade_use_spectral_norm=True,
                               spade_param_free_norm="batch", num_layers=3))
     return o
+
+
+def full_opts(nblocks=(2, 2, 3, 2), size=128, latent=16, n_up=4, ndf=8, n_layers=3, num_d=2, tasks=("d", "s", "m", "p")):
+    """shared/trainer/defaults.yaml values on a small network (deeplabv2 encoder, as the north star names)."""
+    with_p = "p" in tasks
+    o = default_masker_opts(tasks=tuple(t for t in tasks if t != "p"), nblocks=nblocks, size=size, with_painter=with_p,
+                            latent_dim=latent, spade_n_up=n_up, ndf=ndf, n_layers=n_layers, num_D=num_d)
+    o.tasks = list(tasks)
+    o.domains = ["r", "s"] + (["rf"] if with_p else [])
+    o.gen.default = Dict(init_type="xavier", init_gain=0.02)
+    for k in ("encoder", "d", "s", "m", "p"):
+        o.gen[k].init_type = "xavier"
+        o.gen[k].init_gain = 0.02
+    o.gen.m.use_minent = True
+    o.gen.m.use_minent_var = True
+    o.gen.m.use_ground_intersection = True
+    o.gen.m.use_pl4m = False
+    o.gen.m.use_proj = True
+    o.gen.p.pl4m_epoch = 49
+    o.gen.opt.lr = Dict(default=0.00005)
+    o.dis.soft_shift = 0.0
+    o.dis.flip_prob = 0.0
+    base = dict(input_nc=3, ndf=64, n_layers=4, norm="instance", init_type="xavier", init_gain=0.02, use_sigmoid=False,
+                num_D=1, get_intermediate_features=False)
+    o.dis.m = Dict(base, multi_level=False, architecture="base", gan_type="WGAN_norm", wgan_clamp_lower=-0.01,
+                   wgan_clamp_upper=0.01)
+    o.dis.s = Dict(base, gan_type="WGAN_norm", wgan_clamp_lower=-0.01, wgan_clamp_upper=0.01)
+    o.train = Dict(
+        amp=False, kitti=Dict(pretrain=False), pseudo=Dict(tasks=[], epochs=10), log_level=0, latent_domain_adaptation=False,
+        lambdas=Dict(
+            G=Dict(d=Dict(main=1, gml=0.5), s=Dict(crossent=1, crossent_pseudo=0.001, minent=0.001, advent=0.001),
+                   m=Dict(bce=1, tv=1, gi=0.05, pl4m=1),
+                   p=Dict(context=0, dm=1, featmatch=10, gan=1, reconstruction=0, tv=0, vgg=10)),
+            advent=Dict(ent_main=0.5, ent_aux=0.0, ent_var=0.1, adv_main=1.0, adv_aux=0.0, dis_main=1.0, dis_aux=0.0, WGAN_gp=10)))
+    return o
+
+
+def synth_batch(opts, batch, size, seed):
+    """Synthetic multi_domain_batch of the shape Trainer.update_G/update_D consume: x ~ U(-1,1), m in {0,1},
+    s int64 labels at size/4, d ~ U(0,1) at size/4."""
+    import numpy as np
+    import torch
+
+    rs = np.random.RandomState(seed)
+    out = {}
+    q = size // 4
+    for dom in opts.domains:
+        data = {"x": torch.from_numpy((rs.random_sample((batch, 3, size, size)) * 2 - 1).astype(np.float32)),
+                "m": torch.from_numpy((rs.random_sample((batch, 1, size // 8, size // 8)) > 0.5).astype(np.float32))
+                .repeat_interleave(8, 2).repeat_interleave(8, 3)}
+        if dom != "rf":
+            data["s"] = torch.from_numpy(rs.randint(0, 11, size=(batch, 1, q, q)).astype(np.int64))
+            data["d"] = torch.from_numpy(rs.random_sample((batch, 1, q, q)).astype(np.float32))
+        out[dom] = {"data": data, "domain": [dom] * batch, "mode": ["train"] * batch, "paths": {}}
+    return out

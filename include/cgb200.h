@@ -187,6 +187,71 @@ int cgb_mul(const void* a, const void* b, void* y, int32_t dtype, int64_t count,
 int cgb_make_m_cond(const void* d, const void* s, const void* xr, float* mm, void* out, int32_t dtype, int32_t n, int32_t hw,
                     int32_t ss, int32_t ns, int32_t cs_out, void* stream);
 
+/* ---- masker training path -----------------------------------------------------------------
+ * nn.BatchNorm2d in TRAIN mode (batch statistics; resnetmulti_v2.py:16-18,30-34,72 freeze only weight/bias;
+ * deeplab_v2.py:23,100,104,146; depth.py:57-105 via Conv2dBlock(norm="batch") blocks.py:95-96), fused with the ReLU /
+ * LeakyReLU that follows and the bottleneck's residual add (resnetmulti_v2.py:50-52).  Statistics come from
+ * cgb_instnorm_stats with n=1, hw=N*H*W.  weight/bias are per-channel fp32 (NULL = 1 / 0), padded to c.
+ *   fwd:      y = act((x-mean)*rstd*weight + bias (+ residual))
+ *   bwd (1):  gpre = gy*act'(y) (also the gradient of the residual) ; sums[c][0] = sum gpre (= gbias),
+ *             sums[c][1] = sum gpre*xhat (= gweight)   (fp64, zeroed by the call)
+ *   bwd (2):  gx = weight*rstd*(gpre - sums0/M - xhat*sums1/M)
+ *   running:  running_mean/var <- (1-momentum)*running + momentum*batch (unbiased variance), as F.batch_norm does. */
+int cgb_bn_apply_fwd(const void* x, const float* mean, const float* rstd, const float* weight, const float* bias,
+                     const void* residual, void* y, int32_t dtype, int64_t npix, int32_t c, int32_t act, float slope,
+                     void* stream);
+int cgb_bn_apply_bwd(const void* x, const float* mean, const float* rstd, const void* y, const void* gy, void* gpre,
+                     double* sums, int32_t dtype, int64_t npix, int32_t c, int32_t act, float slope, void* stream);
+int cgb_bn_bwd_finalize(const void* x, const float* mean, const float* rstd, const float* weight, const double* sums,
+                        const void* gpre, void* gx, int32_t dtype, int64_t npix, int32_t c, void* stream);
+int cgb_bn_update_running(const float* mean, const float* rstd, float* running_mean, float* running_var, int32_t c,
+                          int64_t count, float momentum, float eps, void* stream);
+/* adjoints of cgb_maxpool3s2_ceil_fwd (gradient to the first maximum of each window, as ATen), cgb_resize_bilinear_fwd,
+ * cgb_channel_mean; nn.ReflectionPad2d (blocks.py:66-67) as an explicit copy + its fold-back adjoint so reflect-padded
+ * convs run as pad-0 convs on the tcgen05 engine; dst[n,hw,c] = src[n,c]*scale (AdaptiveAvgPool2d(1) backward and the
+ * 1x1 -> HxW bilinear of the ASPP image-pool branch, deeplab_v2.py:97-102,116); nn.Dropout (deeplab_v2.py:106,148,152)
+ * with a counter-based mask from (seed, element index): the same call on the gradient is its backward. */
+int cgb_maxpool3s2_ceil_bwd(const void* x, const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi, int32_t wi,
+                            int32_t ho, int32_t wo, int32_t c, void* stream);
+int cgb_resize_bilinear_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t ho,
+                            int32_t wo, int32_t c, int32_t align_corners, void* stream);
+int cgb_reflect_pad_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad,
+                        void* stream);
+int cgb_reflect_pad_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad,
+                        void* stream);
+int cgb_channel_mean_bwd(const void* gy, void* gx, int32_t dtype, int64_t pixels, int32_t cs, int32_t c_logical, void* stream);
+int cgb_broadcast_hw(const void* src, void* dst, int32_t dtype, int32_t n, int32_t hw, int32_t c, float scale, void* stream);
+int cgb_dropout(const void* x, void* y, int32_t dtype, int64_t count, float p, uint64_t seed, void* stream);
+
+/* ---- masker losses (NCHW fp32, the layout Trainer.masker_{d,s,m}_loss receive; trainer.py:1389-1616) --------------
+ * Each *_loss entry ADDS the mean-reduced loss to the device scalar `loss` (caller zeroes) and writes the gradient of
+ * that loss w.r.t. its first argument (optional unless stated).
+ *   softmax over dim 1 (trainer.py:1449,1475) fwd / bwd
+ *   cross_entropy: nn.CrossEntropyLoss (losses.py:106-112), target int64 [n,h,w]
+ *   entropy: prob_2_entropy (losses.py:466-471) optionally times a [n,1,h,w] depth map (ADVENTAdversarialLoss.__call__
+ *            losses.py:541-543); backward=1 writes ge*d(entropy)/dp into out
+ *   minent: MinentLoss v1 / v2 (losses.py:177-196); acc = 1 double scratch
+ *   sigmoid_pair: cat[sigmoid(l), 1-sigmoid(l)] (trainer.py:1532-1534); backward=1 writes the logits gradient into out
+ *   tv: TVLoss (losses.py:140-171) ; bce_logits: nn.BCEWithLogitsLoss with a tensor target (losses.py:419) ;
+ *   ground_intersection: GroundIntersectionLoss (losses.py:449-455; piecewise constant, no gradient)
+ *   sigm: SIGMLoss (losses.py:232-278): median/MAD alignment of prediction and target, 0.5/num_pix*sum|R| + Sobel gradient
+ *         matching over `scales` nearest-downsampled scales; gpred required; ws = 16 + 2*n*h*w floats of scratch.
+ *         The gradient flows through the median (shared among ties, as torch.median's backward) and the MAD scale. */
+int cgb_softmax_nchw_fwd(const float* x, float* y, int32_t n, int32_t c, int32_t hw, void* stream);
+int cgb_softmax_nchw_bwd(const float* y, const float* gy, float* gx, int32_t n, int32_t c, int32_t hw, void* stream);
+int cgb_cross_entropy_nchw(const float* logits, const int64_t* target, float* loss, float* glogits, int32_t n, int32_t c,
+                           int32_t hw, void* stream);
+int cgb_entropy_nchw(const float* p, const float* depth, const float* ge, float* out, int32_t n, int32_t c, int32_t hw,
+                     int32_t backward, void* stream);
+int cgb_minent_loss(const float* p, float* loss, float* gp, double* acc, int32_t n, int32_t c, int32_t hw, int32_t version,
+                    float lambda_var, void* stream);
+int cgb_sigmoid_pair(const float* logits, const float* gprob, float* out, int32_t n, int32_t hw, int32_t backward, void* stream);
+int cgb_tv_loss(const float* x, float* loss, float* gx, int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
+int cgb_bce_logits_loss(const float* x, const float* target, float* loss, float* gx, int64_t count, void* stream);
+int cgb_ground_intersection_loss(const float* pred, const float* ground, float* loss, int64_t count, void* stream);
+int cgb_sigm_loss(const float* pred, const float* target, float* loss, float* gpred, float* ws, int32_t n, int32_t h, int32_t w,
+                  float gmweight, int32_t scales, void* stream);
+
 /* ---- layout / elementwise ----------------------------------------------------------------
  * NCHW fp32 (the reference's tensor layout at the API edge) <-> NHWC storage. */
 int cgb_nchw_to_nhwc(const float* x, void* y, int32_t dtype, int32_t n, int32_t c, int32_t hw,

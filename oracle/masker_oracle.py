@@ -16,7 +16,29 @@ import torch.nn.functional as F
 from oracle.painter_oracle import SNState
 
 
+BN_TRAIN = [False]  # set through train_mode(): nn.BatchNorm2d in train mode = batch statistics + running-stat update
+
+
+class train_mode:
+    """with train_mode(): every bn() below behaves as nn.BatchNorm2d.train() (momentum 0.1, running stats updated in place
+    in the state_dict, num_batches_tracked incremented) — what G.train() gives the reference's masker."""
+
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        self.prev = BN_TRAIN[0]
+        BN_TRAIN[0] = self.on
+
+    def __exit__(self, *a):
+        BN_TRAIN[0] = self.prev
+
+
 def bn(sd, p, x):
+    if BN_TRAIN[0]:
+        if p + ".num_batches_tracked" in sd:
+            sd[p + ".num_batches_tracked"] += 1
+        return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"], True, 0.1, 1e-5)
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"], False, 0.0, 1e-5)
 
 

@@ -43,11 +43,19 @@ class SNState:
         self.sd = sd
 
     def weight(self, prefix: str) -> Tensor:
-        w, u, v = spectral_norm_weight(self.sd[prefix + ".weight_bar"], self.sd[prefix + ".weight_u"],
-                                       self.sd[prefix + ".weight_v"])
-        self.sd[prefix + ".weight_u"] = u
-        self.sd[prefix + ".weight_v"] = v
-        return w
+        """One power iteration + w_bar / sigma.  u and v are PERSISTENT tensors whose ``.data`` is swapped in place, exactly as
+        ``SpectralNorm._update_u_v`` does (norms.py:106-108): autograd saved them by reference for ``sigma = u.(W v)``, so
+        when a layer runs twice before one backward (the mask decoder and the AdvEnt discriminators see the r and the s
+        batch), BOTH backward passes use the u, v of the LAST forward in d(sigma)/dW = u v^T.  Reference behaviour, kept."""
+        w_bar, u, v = self.sd[prefix + ".weight_bar"], self.sd[prefix + ".weight_u"], self.sd[prefix + ".weight_v"]
+        w2 = w_bar.view(w_bar.shape[0], -1)
+        with torch.no_grad():
+            v_new = l2normalize(torch.mv(w2.t(), u))
+            u_new = l2normalize(torch.mv(w2, v_new))
+        v.data = v_new
+        u.data = u_new
+        sigma = u.dot(w2.mv(v))
+        return w_bar / sigma.expand_as(w_bar)
 
 
 def spade(sd: Dict[str, Tensor], prefix: str, x: Tensor, segmap: Tensor) -> Tensor:

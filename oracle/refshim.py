@@ -42,6 +42,46 @@ def _install_stubs():
     sk.color = _stub("skimage.color")
     sk.transform = _stub("skimage.transform")
     sk.filters = _stub("skimage.filters")
+    sk.io.imread = sk.color.rgba2rgb = sk.transform.resize = None
+    # needed only to IMPORT climategan.trainer / data / eval_metrics / fire (never called on the oracle's paths, except
+    # kornia's two Gaussian-blur helpers, restated from their published definition — SURVEY.md §8c row (ii))
+    _stub("imageio", imread=None)
+    mpl = _stub("matplotlib")
+    mpl.pyplot = _stub("matplotlib.pyplot")
+    _stub("seaborn")
+    _install_kornia_stub()
+
+
+def _install_kornia_stub():
+    """kornia 0.5.10 ``filters.filter2D`` / ``filters.kernels.get_gaussian_kernel2d`` as used by climategan/fire.py:9-12,
+    108-111 — restated: kernel = outer product of two normalised 1-D Gaussians exp(-(i - k//2)^2 / (2 sigma^2)) (even sizes
+    shifted by half a pixel as kornia's ``gaussian`` does); filter2D = reflect-pad by k//2 + per-channel cross-correlation
+    (``normalized=False``)."""
+    import torch
+    import torch.nn.functional as F
+
+    def gaussian(window_size, sigma):
+        x = torch.arange(window_size, dtype=torch.float32) - window_size // 2
+        if window_size % 2 == 0:
+            x = x + 0.5
+        g = torch.exp(-x.pow(2.0) / (2 * sigma ** 2))
+        return g / g.sum()
+
+    def get_gaussian_kernel2d(kernel_size, sigma, force_even=False):
+        kx, ky = gaussian(kernel_size[1], sigma[1]), gaussian(kernel_size[0], sigma[0])
+        return torch.matmul(ky.unsqueeze(-1), kx.unsqueeze(-1).t())
+
+    def filter2D(input, kernel, border_type="reflect", normalized=False):
+        b, c, h, w = input.shape
+        k = kernel.to(input)
+        kh, kw = k.shape[-2:]
+        x = F.pad(input, (kw // 2, kw // 2, kh // 2, kh // 2), mode=border_type)
+        out = F.conv2d(x, k.expand(c, 1, kh, kw).contiguous(), groups=c)
+        return out[..., :h, :w]
+
+    k = _stub("kornia")
+    k.filters = _stub("kornia.filters", filter2D=filter2D, filter2d=filter2D)
+    k.filters.kernels = _stub("kornia.filters.kernels", get_gaussian_kernel2d=get_gaussian_kernel2d)
 
 
 def load(*submodules: str):

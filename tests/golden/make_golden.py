@@ -183,9 +183,8 @@ def run_step_case(name="painter_step", latent=16, n_up=4, ndf=8, n_layers=3, num
             l_feat = featmatch(real_d, fake_d) * lam.featmatch
             (l_vgg + l_gan + l_feat).backward()
             (g_opt.extrapolation if global_step % 2 == 0 else g_opt.step)()
-            for n_, p in D.named_parameters():
-                if not n_.endswith(("weight_u", "weight_v")):
-                    p.requires_grad_(True)
+            for p in D.parameters():   # trainer.py:971-973: every parameter, the spectral-norm u / v included
+                p.requires_grad_(True)
             logs += [float(l_vgg), float(l_gan), float(l_feat)]
         else:            # update_D
             tutils_mod.zero_grad(D)
@@ -250,6 +249,78 @@ def run_masker_case(name="masker_small", nblocks=(2, 2, 3, 2), batch=2, size=64)
           float(out["m"].max()), "npz bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
 
 
+def _flatten_logs(d, prefix=""):
+    out = {}
+    for k, v in d.items():
+        if isinstance(v, dict):
+            out.update(_flatten_logs(v, prefix + k + "."))
+        else:
+            out[prefix + k] = float(v)
+    return out
+
+
+def _sample(a, cap=8192):
+    """Large tensors are stored as a strided sample of their flattened values (stride = ceil(numel / cap))."""
+    a = np.asarray(a).reshape(-1)
+    k = max(1, -(-a.size // cap))
+    return a[::k].copy()
+
+
+def run_full_step_case(name="full_step", batch=2, size=128):
+    """Two iterations of the reference's OWN ``Trainer.update_G`` / ``update_D`` (trainer.py:989-1032) on tasks [d,s,m,p]
+    — deeplabv2 masker (ResNet [2,2,3,2], train-mode BatchNorm, dropout p=0) + SPADE painter + all three discriminators —
+    driven as ``run_epoch`` does (oracle/ref_trainer.py).  Stores every logged loss, the gradient norm of every parameter
+    after the first G and D backward, a few full gradients, and a few parameters / BatchNorm running statistics after the
+    second iteration (ExtraAdam extrapolation then step)."""
+    from oracle import ref_trainer as rt
+
+    opts = rt.full_opts(size=size)
+    t = rt.build_reference_trainer(opts, size)
+    g_shapes, d_shapes, v_shapes = rt.load_weights(t)
+    mdb = rt.synth_batch(opts, batch, size, seed=7)
+    arrays = {}
+    logs = []
+    full_g = ["encoder.model.conv1.weight", "encoder.model.layer3.1.conv2.weight", "decoders.d.enc4_2.conv.weight", "decoders.d.enc4_2.norm.weight",
+              "decoders.s.aspp.aspp3.atrous_conv.weight", "decoders.s.conv.8.bias", "decoders.m.proj_conv.conv.module.weight_bar",
+              "decoders.m.model.6.conv.module.weight_bar", "painter.conv_img.weight"]
+    full_d = ["m.Advent.0.module.weight_bar", "s.Advent.8.module.weight_bar", "p.discriminator_0.model0.0.module.weight_bar"]
+    for it in range(2):
+        for p_ in t.D.parameters():
+            p_.requires_grad = False
+        t.update_G(mdb)
+        if it == 0:
+            gp = dict(t.G.named_parameters())
+            arrays["G.gradnorm"] = np.array([float(p_.grad.norm()) if p_.grad is not None else -1.0 for p_ in gp.values()], dtype=np.float64)
+            for k in full_g:
+                arrays["G.grad::" + k] = _sample(gp[k].grad.detach().numpy())
+        for p_ in t.D.parameters():
+            p_.requires_grad = True
+        t.update_D(mdb)
+        if it == 0:
+            dp = dict(t.D.named_parameters())
+            arrays["D.gradnorm"] = np.array([float(p_.grad.norm()) if p_.grad is not None else -1.0 for p_ in dp.values()], dtype=np.float64)
+            for k in full_d:
+                arrays["D.grad::" + k] = _sample(dp[k].grad.detach().numpy())
+        t.logger.global_step += 1
+        logs.append(_flatten_logs(t.logger.losses.to_dict()))
+    gsd, dsd = t.G.state_dict(), t.D.state_dict()
+    for k in full_g + ["encoder.model.bn1.running_mean", "encoder.model.layer4.0.bn2.running_var", "decoders.s.aspp.global_avg_pool.2.running_var",
+                       "decoders.d.enc4_1.norm.running_mean", "decoders.m.model.0.model.1.model.0.conv.module.weight_u"]:
+        arrays["G.final::" + k] = _sample(gsd[k].numpy())
+    for k in full_d:
+        arrays["D.final::" + k] = _sample(dsd[k].numpy())
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+    meta = {"case": name, "batch": batch, "size": size, "seeds": {"G": 21, "D": 22, "vgg": 23, "inputs": 7},
+            "g_shapes": [[k, list(s_)] for k, s_ in g_shapes], "d_shapes": [[k, list(s_)] for k, s_ in d_shapes],
+            "v_shapes": [[k, list(s_)] for k, s_ in v_shapes], "g_param_names": [k for k, _ in t.G.named_parameters()],
+            "d_param_names": [k for k, _ in t.D.named_parameters()], "logs": logs, "full_g": full_g, "full_d": full_d,
+            "reference": "cc-ai/climategan @ /root/reference: climategan.trainer.Trainer.update_G/update_D (unmodified), CPU, torch "
+                         + torch.__version__}
+    with open(os.path.join(HERE, name + ".json"), "w") as f:
+        json.dump(meta, f)
+    print(name, "logs[0]", {k: round(v, 5) for k, v in logs[0].items()}, "npz bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
+
+
 if __name__ == "__main__":
     if not refshim.available():
         sys.exit("reference tree not available; goldens can only be regenerated in the build container")
@@ -258,3 +329,4 @@ if __name__ == "__main__":
     run_disc_case()
     run_step_case()
     run_masker_case()
+    run_full_step_case()

@@ -51,11 +51,30 @@ def test_masker_decode_matches_reference_golden(cuda, dtype):
     assert rel_max(d2, torch.from_numpy(g["d"])) < tol
 
 
-def test_masker_training_mode_refuses(cuda):
+def test_masker_train_mode_uses_batch_statistics(cuda):
+    """Train mode: BatchNorm normalises with BATCH statistics and updates the running ones (resnetmulti_v2.py:16-18 only
+    freezes the affine parameters), gradients reach the encoder's first conv; frozen BN affine parameters get none."""
     meta, g, sd, (x, _, _) = load_golden("masker_small")
     G = _build(meta, sd, torch.float32, cuda).train()
-    with pytest.raises(NotImplementedError):
-        G.encode(x.to(cuda))
+    for m in G.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    q = meta["size"] // 4
+    G.decoders["d"]._target_size = q     # native resolution of the decoders: no bicubic re-sampling on the training path
+    G.decoders["s"]._target_size = q     # (ints, as find_target_size yields; depth.py:143 compares the width with an int)
+    rm0 = G.encoder.model.bn1.running_mean.clone()
+    z = G.encode(x.to(cuda))
+    assert z.requires_grad
+    assert not torch.equal(G.encoder.model.bn1.running_mean, rm0)
+    assert int(G.encoder.model.bn1.num_batches_tracked) == 1
+    d, z_depth = G.decode_d(z)
+    s = G.decode_s(z, z_depth)
+    m = G.decode_m(z)
+    (d.mean() + s.mean() + m.mean()).backward()
+    gw = G.encoder.model.conv1.weight.grad
+    assert gw is not None and bool(torch.isfinite(gw).all()) and float(gw.abs().max()) > 0
+    assert G.encoder.model.bn1.weight.grad is None
+    assert G.decoders["d"].enc4_1.norm.weight.grad is not None
 
 
 def test_masker_full_size_shapes(cuda):

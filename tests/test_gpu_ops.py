@@ -37,6 +37,16 @@ CONV_CASES = [
     (1, 64, 32, 20, 20, 3, 1, 6, 6, "zero", _lib.ACT_NONE),     # ASPP atrous d6
     (1, 8, 16, 23, 23, 7, 2, 1, 3, "zero", _lib.ACT_RELU),      # stem 7x7 s2
     (3, 128, 256, 5, 5, 3, 1, 1, 1, "zero", _lib.ACT_NONE),     # tiny spatial, larger channels
+    # masker training path (ResNet-101 encoder / ASPP / decoders)
+    (2, 3, 64, 64, 64, 7, 2, 1, 3, "zero", _lib.ACT_NONE),      # stem 7x7 s2, 3 real input channels
+    (2, 64, 128, 32, 32, 1, 2, 1, 0, "zero", _lib.ACT_NONE),    # layer2 1x1 stride 2 (conv1 / downsample)
+    (2, 128, 128, 16, 16, 3, 1, 2, 2, "zero", _lib.ACT_NONE),   # layer3 3x3 dilation 2
+    (2, 64, 64, 16, 16, 3, 1, 4, 4, "zero", _lib.ACT_NONE),     # layer4 3x3 dilation 4
+    (2, 256, 64, 16, 16, 3, 1, 12, 12, "zero", _lib.ACT_NONE),  # ASPP d12: most taps fall in the padding
+    (2, 256, 64, 16, 16, 3, 1, 18, 18, "zero", _lib.ACT_NONE),  # ASPP d18 >= map size: only the centre tap is live
+    (2, 512, 128, 1, 1, 1, 1, 1, 0, "zero", _lib.ACT_RELU),     # ASPP image-pool branch: 1x1 conv on a 1x1 map
+    (2, 64, 64, 18, 18, 3, 1, 1, 0, "zero", _lib.ACT_LRELU),    # pad-0 3x3 after an explicit reflect pad
+    (2, 2048, 64, 8, 8, 1, 1, 1, 0, "zero", _lib.ACT_LRELU),    # mask decoder proj_conv, K = 2048
 ]
 
 

@@ -1,13 +1,16 @@
 """CPU tests: the oracle (oracle/painter_oracle.py) against the committed golden vectors that the
 unmodified reference produced, and — when the reference tree is present — against the reference
 modules themselves."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 from oracle import painter_oracle as po
 from oracle import refshim
-from tests.helpers import load_golden, rel_max
+from tests.golden.weights import fill_state_dict
+from tests.helpers import GOLDEN, load_golden, rel_max
 
 
 def _oracle_run(sd, x, m, target, meta):
@@ -132,7 +135,7 @@ def test_trainer_oracle_matches_reference_step_golden():
     x, m, _ = synth_inputs(meta["batch"], meta["size"], 5)
     z = meta["size"] // 2 ** meta["spade_n_up"]
     g_opt = to.ExtraAdam([v for v in gsd.values() if v.requires_grad], lr=0.00005, betas=(0.9, 0.999))
-    d_opt = to.ExtraAdam([v for v in dsd.values() if v.requires_grad], lr=0.00002, betas=(0.5, 0.999))
+    d_opt = to.ExtraAdam(list(dsd.values()), lr=0.00002, betas=(0.5, 0.999))   # every D tensor, u / v included (optim.py:72)
     g_sn, d_sn = SNState(gsd), SNState(dsd)
     logs = []
     for it in range(4):
@@ -145,7 +148,8 @@ def test_trainer_oracle_matches_reference_step_golden():
             loss, terms = to.painter_g_loss(gsd, dsd, vsd, x, m, z, g_sn=g_sn, d_sn=d_sn)
             loss.backward()
             for v in dsd.values():
-                v.grad = None  # D is frozen during update_G
+                v.grad = None  # D is frozen during update_G ...
+                v.requires_grad_(True)  # ... and un-frozen wholesale afterwards: u / v train from here on (trainer.py:971-973)
             (g_opt.extrapolation if gs % 2 == 0 else g_opt.step)()
             logs += [float(terms["vgg"]), float(terms["gan"]), float(terms["featmatch"])]
         else:
@@ -176,3 +180,48 @@ def test_masker_oracle_matches_reference_golden():
     assert rel_max(cond, torch.from_numpy(g["cond"])) < 1e-4
     assert rel_max(out["z"][:, ::97], torch.from_numpy(g["z_sample"])) < 1e-4
     assert rel_max(out["z_depth"][:, ::97], torch.from_numpy(g["z_depth_sample"])) < 1e-4
+
+
+def test_full_step_oracle_matches_reference_trainer_golden():
+    """oracle/full_step_oracle.py (restated masker losses, train-mode BatchNorm masker, G/D loss assembly) against the
+    first iteration of the reference's own Trainer.update_G / update_D (tests/golden/full_step.*): every logged loss term,
+    the gradient norm of every parameter, sampled full gradients."""
+    import json as _json
+
+    from climategan_b200.utils import full_opts, synth_batch
+    from oracle import full_step_oracle as fo
+
+    meta = _json.load(open(os.path.join(GOLDEN, "full_step.json")))
+    g = dict(np.load(os.path.join(GOLDEN, "full_step.npz")))
+    size, batch = meta["size"], meta["batch"]
+    mk = lambda shapes, seed: fill_state_dict([(k, tuple(s)) for k, s in shapes], seed)  # noqa: E731
+    gsd, dsd, vsd = mk(meta["g_shapes"], 21), mk(meta["d_shapes"], 22), mk(meta["v_shapes"], 23)
+    g_names, d_names = meta["g_param_names"], meta["d_param_names"]
+    frozen = {k for k in g_names if ".bn" in k or "downsample.1" in k}  # encoder BatchNorm affine params (resnetmulti_v2.py:16-18)
+    for k in g_names:
+        gsd[k].requires_grad_(not k.endswith(("weight_u", "weight_v")) and not (k.startswith("encoder.") and k in frozen))
+    opts = full_opts(size=size)
+    mdb = synth_batch(opts, batch, size, meta["seeds"]["inputs"])
+    z_hw = size // 2 ** opts.gen.p.spade_n_up
+    # ---- update_G (D frozen)
+    loss, terms = fo.full_g_loss(gsd, dsd, vsd, mdb, z_hw)
+    loss.backward()
+    ref = meta["logs"][0]
+    assert abs(float(loss) - ref["gen.total_loss"]) < 1e-5 * abs(ref["gen.total_loss"])
+    pairs = {"d.s": "gen.task.d.s", "s.crossent.s": "gen.task.s.crossent.s", "s.minent.r": "gen.task.s.minent.r",
+             "s.advent.r": "gen.task.s.advent.r", "m.tv.r": "gen.task.m.tv.r", "m.tv.s": "gen.task.m.tv.s",
+             "m.bce.s": "gen.task.m.bce.s", "m.gi.r": "gen.task.m.gi.r", "m.minent.r": "gen.task.m.minent.r",
+             "m.advent.r": "gen.task.m.advent.r", "p.vgg": "gen.p.vgg", "p.gan": "gen.p.gan", "p.featmatch": "gen.p.featmatch"}
+    for ours, theirs in pairs.items():
+        assert abs(float(terms[ours]) - ref[theirs]) <= 1e-5 * abs(ref[theirs]) + 1e-7, (ours, float(terms[ours]), ref[theirs])
+    gn = g["G.gradnorm"]
+    for name, r in zip(g_names, gn):
+        p = gsd[name]
+        if r < 0:
+            assert p.grad is None or not p.requires_grad, name
+        else:
+            assert abs(float(p.grad.norm()) - r) <= 1e-4 * r + 1e-7 * gn.max(), (name, float(p.grad.norm()), r)
+    for k in meta["full_g"]:
+        a = gsd[k].grad.numpy().reshape(-1)
+        a = a[::max(1, -(-a.size // 8192))]
+        assert np.abs(a - g["G.grad::" + k]).max() <= 1e-4 * np.abs(g["G.grad::" + k]).max(), k
