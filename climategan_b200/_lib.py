@@ -14,7 +14,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 _CSRC = _PKG / "csrc"
 _SO = _PKG / "libcgb200.so"
-_SOURCES = ["api.cu", "ops.cu", "masker_ops.cu", "conv_simt.cu", "conv_tc.cu"]
+_SOURCES = ["api.cu", "ops.cu", "masker_ops.cu", "events.cu", "conv_simt.cu", "conv_tc.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -125,6 +125,16 @@ SIGNATURES = {
     "cgb_bce_logits_loss": ([_P, _P, _P, _P, _L, _P], C.c_int),
     "cgb_ground_intersection_loss": ([_P, _P, _P, _L, _P], C.c_int),
     "cgb_sigm_loss": ([_P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P], C.c_int),
+    "cgb_minmax_per_sample": ([_P, _P, _I, _L, _P], C.c_int),
+    "cgb_fire_tone": ([_P, _P, _P, _P, _I, _I, _F, _F, _P], C.c_int),
+    "cgb_sky_mask": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_plane_resize_nearest": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_box_dilate": ([_P, _P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_gauss_blur": ([_P, _P, _P, _I, _I, _I, _I, _F, _P], C.c_int),
+    "cgb_fire_paste": ([_P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _F, _P], C.c_int),
+    "cgb_smog": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _F, _F, _P], C.c_int),
+    "cgb_to_uint8_nhwc": ([_P, _P, _P, _I, _I, _P], C.c_int),
+    "cgb_mask_to_uint8": ([_P, _P, _F, _L, _P], C.c_int),
     "cgb_resize_nearest_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_upsample_nearest_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_im2col": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),

@@ -18,6 +18,7 @@
 //   "MN-major" for UMMA (the contraction index is the slow one in NHWC memory), loaded by the same shifted
 //   TMA boxes; one TMEM accumulator per filter tap, fp32 red.global.add into gw at the end.
 #include "common.cuh"
+#include <cstdlib>
 #include <cuda.h>
 #include <mutex>
 #include <string.h>
@@ -824,7 +825,14 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
       int stg = (int)((SMEM_LIMIT - fixed) / a_stage);
       if (stg > 6) stg = 6;
       const double ws_bytes = (double)((wout + 7) / 8) * ((hout + 15) / 16) * n * nt * kblocks * (double)(twh * thh * 128);
-      if (ws_bytes < 0.8 * stream_bytes) {
+      // Measured on B200 (gpurun_out/ws_sweep.log -> profiles/r01_ws_vs_streaming.txt): the weight-stationary kernel only
+      // wins for narrow outputs fed by few channels (gamma||beta 128->48 @640^2: 1.22 vs 1.50 ms; 24->24: 0.59 vs 2.03 ms).
+      // As soon as the weights need several slices, or N >= 80, the streaming kernel is 1.3-3x faster (256->256 d2 @80^2:
+      // 0.054 vs 0.153 ms; 128->160 @160^2: 0.143 vs 0.250 ms): narrow slices make the MMA itself inefficient (cost
+      // max(N/2, (4096+32N)/128) cycles, scripts/exp/mma_rate.cu) and re-read the halo once per slice.
+      static const int ws_max_co = getenv("CGB_WS_MAX_CO") ? atoi(getenv("CGB_WS_MAX_CO")) : 64;
+      // ... and for wide outputs fed by a single 64-channel block (the dgrad of gamma||beta, 48->128: 1.82 vs 1.97 ms)
+      if (ws_bytes < 0.8 * stream_bytes && (cout_s <= ws_max_co || kblocks == 1)) {
         use_ws = true; ws_bn = bn; ws_ntiles = nt; ws_stages = stg;
       }
       break;  // the smallest feasible n-split is the cheapest in activation re-reads

@@ -1,0 +1,104 @@
+"""Climate events on the device — the compositing half of ``Trainer.infer_all`` (climategan/trainer.py:218-334):
+``add_fire`` (climategan/fire.py:68-127), ``compute_smog`` (trainer.py:1879-1939), ``normalize`` -> uint8 NHWC output
+(trainer.py:312-327).  NCHW fp32 tensors in and out, like the reference; every array op is a libcgb200 kernel."""
+from __future__ import annotations
+
+import ctypes as C
+import random
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _st():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _L():
+    return _lib.lib()
+
+
+def _img(x):
+    _lib.require_device()
+    if not x.is_cuda:
+        raise _lib.CgbError("climategan_b200 tensors must live on a CUDA device (no CPU path)")
+    return x.detach().contiguous().float()
+
+
+def minmax_per_sample(x):
+    """Per-sample (min, max) over all other dimensions -> fp32 [N, 2] (tutils.normalize :567-576)."""
+    x = _img(x)
+    n = x.shape[0]
+    mm = torch.empty((n, 2), dtype=torch.float32, device=x.device)
+    check(_L().cgb_minmax_per_sample(_p(x), _p(mm), n, x.numel() // n, _st()), "minmax_per_sample")
+    return mm
+
+
+def add_fire(x, seg_preds, fire_opts, green=None):
+    """fire.add_fire(x, seg_preds, opts.events.fire): x NCHW in [-1,1], seg_preds logits [N,C,hs,ws] -> float image in [0,255].
+    ``green``: the filter's G value; the reference draws random.randint(100, 150) per call (fire.py:115) — same draw here."""
+    x, seg = _img(x), _img(seg_preds)
+    n, c, h, w = x.shape
+    assert c == 3
+    hw = h * w
+    mm = minmax_per_sample(x)
+    toned = torch.empty_like(x)
+    gray = torch.empty((n,), dtype=torch.float64, device=x.device)
+    check(_L().cgb_fire_tone(_p(x), _p(mm), _p(toned), _p(gray), n, hw, 1.5, 0.73, _st()), "fire_tone")   # fire.py:90-91
+    _, cs, hs, ws = seg.shape
+    sky_small = torch.empty((n, hs, ws), dtype=torch.float32, device=x.device)
+    check(_L().cgb_sky_mask(_p(seg), _p(sky_small), n, cs, hs, ws, 9, 1 if fire_opts.get("crop_bottom_sky_mask") else 0, _st()),
+          "sky_mask")
+    a = torch.empty((n, h, w), dtype=torch.float32, device=x.device)
+    b = torch.empty_like(a)
+    t = torch.empty_like(a)
+    check(_L().cgb_plane_resize_nearest(_p(sky_small), _p(a), n, hs, ws, h, w, _st()), "plane_resize_nearest")
+    n_lines, n_cols = int(0.18 * h), int(0.18 * w)                                                          # fire.py:103
+    check(_L().cgb_box_dilate(_p(a), _p(t), _p(b), n, h, w, max(n_cols - 1, 0), max(n_lines - 1, 0), _st()), "box_dilate")
+    ksize = int(fire_opts.get("kernel_size", 301) or 301)
+    sigma = float(fire_opts.get("kernel_sigma", 150.5) or 150.5)
+    check(_L().cgb_gauss_blur(_p(b), _p(t), _p(a), n, h, w, ksize, sigma, _st()), "gauss_blur")
+    if green is None:
+        green = random.randint(100, 150)
+    out = torch.empty_like(x)
+    check(_L().cgb_fire_paste(_p(toned), _p(a), _p(out), n, h, w, 255.0, float(green), 0.0, 200.0, 0.8, _st()), "fire_paste")
+    return out
+
+
+def add_smog(x, d, smog_opts):
+    """Trainer.compute_smog given the depth prediction d [N,1,hd,wd] (trainer.py:1902-1939)."""
+    x, d = _img(x), _img(d)
+    n, c, h, w = x.shape
+    assert c == 3 and d.shape[0] == n and d.shape[1] == 1
+    mmx, mmd = minmax_per_sample(x), minmax_per_sample(d)
+    out = torch.empty_like(x)
+    yc = smog_opts.yellow_color
+    alpha = smog_opts.alpha / 255
+    check(_L().cgb_smog(_p(x), _p(mmx), _p(d), _p(mmd), _p(out), n, h, w, d.shape[2], d.shape[3], float(smog_opts.airlight),
+                        float(smog_opts.beta / smog_opts.vr), float(alpha), yc[0] / 255, yc[1] / 255, yc[2] / 255, _st()), "smog")
+    return out
+
+
+def to_uint8_nhwc(t):
+    """normalize(t) -> permute(0,2,3,1) -> (t*255).astype(uint8) (trainer.py:312-327) as one device kernel: uint8 [N,H,W,3]."""
+    t = _img(t)
+    n, c, h, w = t.shape
+    assert c == 3
+    mm = minmax_per_sample(t)
+    out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=t.device)
+    check(_L().cgb_to_uint8_nhwc(_p(t), _p(mm), _p(out), n, h * w, _st()), "to_uint8_nhwc")
+    return out
+
+
+def mask_to_uint8(mask, bin_value):
+    """((mask > bin_value) * 255).astype(uint8) (trainer.py:330-332)."""
+    m = _img(mask)
+    out = torch.empty(m.shape, dtype=torch.uint8, device=m.device)
+    check(_L().cgb_mask_to_uint8(_p(m), _p(out), float(bin_value), m.numel(), _st()), "mask_to_uint8")
+    return out

@@ -10,6 +10,7 @@ or eager fallback — ops raise :class:`CgbError` without an sm_100 device.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -57,14 +58,68 @@ def pack_weight(w: torch.Tensor, dtype: torch.dtype, cis: Optional[int] = None, 
     return wp
 
 
+# Packed copies of nn.Parameter weights are cached between optimiser updates: the encoder runs 4 forwards + 2 backwards per
+# train step on the same weights (r and s batches in update_G, again in update_D).  A cache entry is valid while the
+# parameter object, its storage, its autograd version and the global epoch (bumped by every optimiser update, which writes
+# parameters through raw kernels that autograd's version counter cannot see) are unchanged.  Spectrally-normalised weights
+# are fresh tensors on every call and are never cached.
+_WCACHE = {}
+_WEPOCH = [0]
+
+
+def invalidate_weight_cache() -> None:
+    """Called by the optimisers after every parameter update."""
+    _WEPOCH[0] += 1
+    if len(_WCACHE) > 4096:
+        _WCACHE.clear()
+
+
+_DBG = set(os.environ.get("CGB_DEBUG_DISABLE", "").split(","))   # debugging switches: wcache, viewgrad, aliasparam
+
+
+def pack_weight_cached(w: torch.Tensor, dtype: torch.dtype, cis: Optional[int] = None) -> torch.Tensor:
+    if not isinstance(w, torch.nn.Parameter) or "wcache" in _DBG:
+        return pack_weight(w, dtype, cis=cis)
+    key = (id(w), dtype, cis)
+    ent = _WCACHE.get(key)
+    if ent is not None and ent[0] == _WEPOCH[0] and ent[1] == w._version and ent[2] == w.data_ptr() and ent[3]() is w:
+        return ent[4]
+    wp = pack_weight(w, dtype, cis=cis)
+    import weakref
+
+    _WCACHE[key] = (_WEPOCH[0], w._version, w.data_ptr(), weakref.ref(w), wp)
+    return wp
+
+
+def cached_pack(params, tag, builder):
+    """Generic form of :func:`pack_weight_cached` for packings built from several nn.Parameters (SPADE's fused gamma||beta
+    weights): ``builder()`` runs only when one of ``params`` changed since the cached copy was made."""
+    if not all(isinstance(p, torch.nn.Parameter) for p in params) or "wcache" in _DBG:
+        return builder()
+    import weakref
+
+    key = (tag,) + tuple(id(p) for p in params)
+    sig = (_WEPOCH[0],) + tuple((p._version, p.data_ptr()) for p in params)
+    ent = _WCACHE.get(key)
+    if ent is not None and ent[0] == sig and all(r() is p for r, p in zip(ent[1], params)):
+        return ent[2]
+    out = builder()
+    _WCACHE[key] = (sig, [weakref.ref(p) for p in params], out)
+    return out
+
+
 def unpack_weight_grad(gwp: torch.Tensor, shape) -> torch.Tensor:
     o, i, kh, kw = shape
+    if gwp.shape[0] == o and gwp.shape[2] == i and "viewgrad" not in _DBG:
+        return gwp.view(o, kh, kw, i).permute(0, 3, 1, 2)   # no channel padding: a strided view, no copy
     return gwp[:o, :, :i].reshape(o, kh, kw, i).permute(0, 3, 1, 2).contiguous()
 
 
 def pad_bias(b: Optional[torch.Tensor], cos: int) -> Optional[torch.Tensor]:
     if b is None:
         return None
+    if b.numel() == cos and b.dtype == torch.float32 and b.is_contiguous() and "aliasparam" not in _DBG:
+        return b.detach()
     bp = torch.zeros(cos, dtype=torch.float32, device=b.device)
     bp[: b.numel()] = b.detach().float()
     return bp
@@ -115,8 +170,11 @@ def conv_dgrad_raw(gy, wp, x_shape, g: ConvGeom, dact=_lib.ACT_NONE, mask_src=No
     gx = torch.empty(x_shape, dtype=gy.dtype, device=gy.device)
     wt = None
     if _L().cgb_conv2d_uses_tcgen05(C.byref(d), 1):
-        wt = torch.empty((ci, g.kh * g.kw, co), dtype=wp.dtype, device=wp.device)
-        check(_L().cgb_conv2d_pack_dgrad_weight(C.byref(d), _p(wp), _p(wt), _st()), "conv2d_pack_dgrad_weight")
+        wt = getattr(wp, "_cgb_wt", None)   # a cached packed weight (pack_weight_cached) keeps its dgrad packing alongside
+        if wt is None or wt.shape != (ci, g.kh * g.kw, co):
+            wt = torch.empty((ci, g.kh * g.kw, co), dtype=wp.dtype, device=wp.device)
+            check(_L().cgb_conv2d_pack_dgrad_weight(C.byref(d), _p(wp), _p(wt), _st()), "conv2d_pack_dgrad_weight")
+            wp._cgb_wt = wt
     check(_L().cgb_conv2d_dgrad(C.byref(d), _p(gy), _p(wp), _p(wt), dact, _p(mask_src), _p(gx), _st()), "conv2d_dgrad")
     return gx
 
@@ -169,7 +227,7 @@ class _Conv2d(Function):
 
     @staticmethod
     def forward(ctx, x, w, bias, residual, g: ConvGeom):
-        wp = pack_weight(w, x.dtype, cis=x.shape[-1])
+        wp = pack_weight_cached(w, x.dtype, cis=x.shape[-1])
         bp = pad_bias(bias, wp.shape[0])
         y = conv_fwd_raw(x, wp, bp, residual, g)
         ctx.g = g
@@ -193,7 +251,7 @@ class _Conv2d(Function):
             gwp, gbp = conv_wgrad_raw(x, gpre, g, ctx.has_bias)
             gw = unpack_weight_grad(gwp, ctx.w_shape)
             if ctx.has_bias:
-                gb = gbp[: ctx.nb].clone()
+                gb = gbp if (gbp.numel() == ctx.nb and "viewgrad" not in _DBG) else gbp[: ctx.nb].clone()
         gres = gy if ctx.has_res else None
         return gx, gw, gb, gres, None
 
@@ -225,21 +283,31 @@ class _Spade(Function):
             # seg holds im2col patches [.., tap*cin + ch]: mlp_shared becomes a 1x1 conv with K = k*k*cin
             g_sh = ConvGeom(1, 1, 1, 1, 0, _lib.PAD_ZERO, _lib.ACT_RELU, 0.0, engine)
             o_sh, i_sh = w_sh.shape[0], w_sh.shape[1]
-            wp_sh = torch.zeros(round8(o_sh), 1, seg.shape[-1], dtype=dt, device=x.device)
-            wp_sh[:o_sh, 0, : k * k * i_sh] = w_sh.detach().permute(0, 2, 3, 1).reshape(o_sh, k * k * i_sh)
+
+            def build_sh():
+                wp = torch.zeros(round8(o_sh), 1, seg.shape[-1], dtype=dt, device=x.device)
+                wp[:o_sh, 0, : k * k * i_sh] = w_sh.detach().permute(0, 2, 3, 1).reshape(o_sh, k * k * i_sh)
+                return wp
+
+            wp_sh = cached_pack([w_sh], ("spade_sh_col", dt, seg.shape[-1]), build_sh)
         else:
             g_sh = ConvGeom(k, k, 1, 1, pad, _lib.PAD_ZERO, _lib.ACT_RELU, 0.0, engine)
-            wp_sh = pack_weight(w_sh, dt, cis=seg.shape[-1])
+            wp_sh = pack_weight_cached(w_sh, dt, cis=seg.shape[-1])
         bp_sh = pad_bias(b_sh, wp_sh.shape[0])
         actv = conv_fwd_raw(seg, wp_sh, bp_sh, None, g_sh)
         nh = actv.shape[-1]
+
         # gamma || beta as ONE conv with co = 2*cs (norms.py:180-182 share the input actv)
-        wp_gb = torch.zeros(2 * cs, k * k, nh, dtype=dt, device=x.device)
-        wp_gb[:c] = w_g.detach().permute(0, 2, 3, 1).reshape(c, k * k, nh)
-        wp_gb[cs:cs + c] = w_b.detach().permute(0, 2, 3, 1).reshape(c, k * k, nh)
-        bp_gb = torch.zeros(2 * cs, dtype=torch.float32, device=x.device)
-        bp_gb[:c] = b_g.detach()
-        bp_gb[cs:cs + c] = b_b.detach()
+        def build_gb():
+            wp = torch.zeros(2 * cs, k * k, nh, dtype=dt, device=x.device)
+            wp[:c] = w_g.detach().permute(0, 2, 3, 1).reshape(c, k * k, nh)
+            wp[cs:cs + c] = w_b.detach().permute(0, 2, 3, 1).reshape(c, k * k, nh)
+            bp = torch.zeros(2 * cs, dtype=torch.float32, device=x.device)
+            bp[:c] = b_g.detach()
+            bp[cs:cs + c] = b_b.detach()
+            return wp, bp
+
+        wp_gb, bp_gb = cached_pack([w_g, w_b, b_g, b_b], ("spade_gb", dt, cs, nh), build_gb)
         gb = conv_fwd_raw(actv, wp_gb, bp_gb, None, g_gb)
         out = torch.empty_like(x)
         check(_L().cgb_spade_modulate_fwd(_p(x), _p(mean), _p(rstd), _p(gb), _p(out), _DT[dt], n, h * w_, cs,
@@ -478,6 +546,9 @@ class _SpectralWeight(Function):
         # _update_u_v swaps their .data (norms.py:106-108), so when a layer runs twice before one backward (mask decoder and
         # AdvEnt discriminators: r batch then s batch) both backward passes see the u, v of the last forward.  Kept as is.
         ctx.u, ctx.v = u, v
+        # d(sigma)/du = W v is the one factor autograd evaluated at FORWARD time (a saved intermediate, not a leaf):
+        # W v = sigma * u_forward since u = normalize(W v) and sigma = u.(W v)
+        ctx.u_fwd = u.detach().clone() if u.requires_grad else None
         return w
 
     @staticmethod
@@ -496,7 +567,7 @@ class _SpectralWeight(Function):
             w2 = (w * sigma).view(rows, -1)
             coef = -dot / sigma
             if ctx.needs_input_grad[1]:
-                gu = coef * torch.mv(w2, v)
+                gu = coef * sigma * (ctx.u_fwd if ctx.u_fwd is not None else u)
             if ctx.needs_input_grad[2]:
                 gv = coef * torch.mv(w2.t(), u)
         return gwb.view_as(w), gu, gv
@@ -938,10 +1009,13 @@ class _BatchNormAct(Function):
             rstd[:c] = torch.rsqrt(running_var + eps)
         wp = bp = None
         if weight is not None:
-            wp = torch.zeros(cs, dtype=torch.float32, device=dev)
-            wp[:c] = weight.detach()
-            bp = torch.zeros(cs, dtype=torch.float32, device=dev)
-            bp[:c] = bias.detach()
+            if c == cs and weight.dtype == torch.float32 and "aliasparam" not in _DBG:
+                wp, bp = weight.detach(), bias.detach()
+            else:
+                wp = torch.zeros(cs, dtype=torch.float32, device=dev)
+                wp[:c] = weight.detach()
+                bp = torch.zeros(cs, dtype=torch.float32, device=dev)
+                bp[:c] = bias.detach()
         y = torch.empty_like(x)
         res = residual.contiguous() if residual is not None else None
         check(_L().cgb_bn_apply_fwd(_p(x), _p(mean), _p(rstd), _p(wp), _p(bp), _p(res), _p(y), _DT[x.dtype], npix, cs, act,
@@ -962,10 +1036,10 @@ class _BatchNormAct(Function):
         check(_L().cgb_bn_apply_bwd(_p(x), _p(mean), _p(rstd), _p(y), _p(gy), _p(gpre), _p(sums), _DT[x.dtype], npix, cs, act,
                                     slope, _st()), "bn_apply_bwd")
         gw = gb = gx = None
-        if wp is not None and ctx.needs_input_grad[1]:
-            gw = sums[:c, 1].float()
-        if wp is not None and ctx.needs_input_grad[2]:
-            gb = sums[:c, 0].float()
+        if wp is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
+            sf = sums[:c].float()
+            gw = sf[:, 1] if ctx.needs_input_grad[1] else None
+            gb = sf[:, 0] if ctx.needs_input_grad[2] else None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
             s = sums if batch_stats else torch.zeros_like(sums)

@@ -41,8 +41,9 @@ class ExtraAdam(Optimizer):
                 flats.append(None)
                 continue
             dev = ps[0].device
-            n = sum(p.numel() for p in ps)
-            fp = torch.empty(n, dtype=torch.float32, device=dev)
+            al = 64   # every parameter starts on a 256-byte boundary: kernels read parameters with 16-byte vector loads
+            n = sum((p.numel() + al - 1) // al * al for p in ps)
+            fp = torch.zeros(n, dtype=torch.float32, device=dev)   # the alignment gaps stay zero under the update (g = 0)
             fg = torch.zeros(n, dtype=torch.float32, device=dev)
             off = 0
             for p in ps:
@@ -52,7 +53,7 @@ class ExtraAdam(Optimizer):
                 if p.grad is not None:
                     fg[off:off + k].copy_(p.grad.reshape(-1))
                 p.grad = fg[off:off + k].view_as(p)
-                off += k
+                off += (k + al - 1) // al * al
             flats.append(dict(p=fp, g=fg, m=torch.zeros_like(fp), v=torch.zeros_like(fp), c=torch.empty_like(fp), n=n))
         self._flat = flats
 
@@ -73,6 +74,9 @@ class ExtraAdam(Optimizer):
     def _update(self, mode):
         if self._flat is None:
             self._flatten()
+        from .ops import invalidate_weight_cache
+
+        invalidate_weight_cache()   # parameters are about to change under autograd's version counter
         self._steps += 1
         lib = _lib.lib()
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)

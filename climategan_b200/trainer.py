@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from . import events, ops
 from .discriminator import create_discriminator
 from .generator import create_generator
 from .losses import (ADVENTAdversarialLoss, BCEWithLogits, CrossEntropy, FeatMatchLoss, GANLoss, GroundIntersectionLoss,
@@ -423,6 +423,88 @@ class Trainer:
             return fn(*args, **kwargs)
         finally:
             G._grad_ctx = orig
+
+    # ---------------------------------------------------------------- inference (trainer.py:218-334, 1824-1939)
+    def infer_all(self, x, numpy=True, stores={}, bin_value=-1, half=False, xla=False, cloudy=False, auto_resize_640=False,
+                  ignore_event=set(), return_masks=False):
+        """Dictionary of events ("flood", "wildfire", "smog") from a numpy array or tensor, single image or batch, HWC or CHW.
+        ``half`` is accepted for API compatibility: storage precision is the trainer's ``storage_dtype`` (bf16 by default)."""
+        import numpy as np
+
+        assert self.is_setup
+        assert len(x.shape) in {3, 4}, f"Unknown Data shape {x.shape}"
+        if not isinstance(x, torch.Tensor):
+            x = torch.tensor(x, device=self.device)
+        if len(x.shape) == 3:
+            x = x.unsqueeze(0)
+        if x.shape[1] != 3:
+            assert x.shape[-1] == 3, f"Unknown x shape to permute {x.shape}"
+            x = x.permute(0, 3, 1, 2)
+        x = x.to(self.device).float().contiguous()
+        if auto_resize_640 and (x.shape[-1] != 640 or x.shape[-2] != 640):
+            xs = ops.resize_bilinear(ops.to_storage(x, torch.float32), 640, 640, align_corners=False)
+            x = ops.from_storage(xs, 3)
+        if xla:
+            raise NotImplementedError("xla=True has no meaning here (sm_100a only)")
+        with torch.no_grad():
+            if self.has_painter:
+                self.G.painter.set_latent_shape(x.shape, True)
+            z = self.G.encode(x)
+            depth, z_depth = self.G.decode_d(z)
+            segmentation = self.G.decode_s(z, z_depth)
+            cond = self.G.make_m_cond(depth, segmentation, x) if self.opts.gen.m.use_spade else None
+            mask = self.G.mask(z=z, cond=cond, z_depth=z_depth)
+            wildfire = smog = flood = None
+            if "wildfire" not in ignore_event:
+                wildfire = self.compute_fire(x, seg_preds=segmentation)
+            if "smog" not in ignore_event:
+                smog = self.compute_smog(x, d=depth, s=segmentation)
+            if "flood" not in ignore_event:
+                flood = self.compute_flood(x, m=mask, s=segmentation, cloudy=cloudy, bin_value=bin_value)
+            if numpy:
+                # normalize -> NHWC -> uint8 on the device; one pinned D2H copy per event
+                conv = lambda t: None if t is None else events.to_uint8_nhwc(t).cpu().numpy()  # noqa: E731
+                flood, smog, wildfire = conv(flood), conv(smog), conv(wildfire)
+            output_data = {"flood": flood, "wildfire": wildfire, "smog": smog}
+            if return_masks:
+                m8 = events.mask_to_uint8(mask, bin_value)
+                output_data["mask"] = m8.cpu().numpy().astype(np.uint8)
+        return output_data
+
+    def compute_fire(self, x, seg_preds=None, z=None, z_depth=None):
+        """trainer.py:1824-1841."""
+        if seg_preds is None:
+            if z is None:
+                z = self.G.encode(x)
+            seg_preds = self.G.decode_s(z, z_depth)
+        return events.add_fire(x, seg_preds, self.opts.events.fire)
+
+    def compute_flood(self, x, z=None, z_depth=None, m=None, s=None, cloudy=None, bin_value=-1):
+        """trainer.py:1843-1877."""
+        if m is None:
+            if z is None:
+                z = self.G.encode(x)
+            if "d" in self.opts.tasks and self.opts.gen.m.use_dada and z_depth is None:
+                _, z_depth = self.G.decode_d(z)
+            m = self.G.mask(x=None, z=z, z_depth=z_depth)
+        if bin_value >= 0:
+            m = (m > bin_value).to(m.dtype)
+        if cloudy:
+            raise NotImplementedError("cloudy=True (paint_cloudy: Perlin-noise sky, generator.py:299-328) is not built")
+        with torch.no_grad():
+            return self.G.paint(m, x)
+
+    def compute_smog(self, x, z=None, d=None, s=None, use_sky_seg=False):
+        """trainer.py:1879-1939 (use_sky_seg is a TODO in the reference: sky_mask stays None)."""
+        if d is None:
+            if z is None:
+                z = self.G.encode(x)
+            d, _ = self.G.decode_d(z)
+        return events.add_smog(x, d, self.opts.events.smog)
+
+    def paint_and_mask(self, x):
+        """Mask then paint (the flood event without the other two)."""
+        return self.compute_flood(x)
 
     def losses_to_host(self):
         """One sync for all logged scalars (the reference calls .item() ~10x per step)."""

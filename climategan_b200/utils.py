@@ -156,6 +156,10 @@ def full_opts(nblocks=(2, 2, 3, 2), size=128, latent=16, n_up=4, ndf=8, n_layers
     o.dis.m = Dict(base, multi_level=False, architecture="base", gan_type="WGAN_norm", wgan_clamp_lower=-0.01,
                    wgan_clamp_upper=0.01)
     o.dis.s = Dict(base, gan_type="WGAN_norm", wgan_clamp_lower=-0.01, wgan_clamp_upper=0.01)
+    # shared/trainer/events.yaml
+    o.events = Dict(fire=Dict(kernel_size=281, kernel_sigma=140.5, transparency=200, sky_inc_factor=0.12, contrast_factor=1.5,
+                              brightness_factor=0.95, crop_bottom_sky_mask=True),
+                    smog=Dict(airlight=0.76, beta=2, vr=1, yellow_color=[224, 192, 29], alpha=20))
     o.train = Dict(
         amp=False, kitti=Dict(pretrain=False), pseudo=Dict(tasks=[], epochs=10), log_level=0, latent_domain_adaptation=False,
         lambdas=Dict(

@@ -252,6 +252,34 @@ int cgb_ground_intersection_loss(const float* pred, const float* ground, float* 
 int cgb_sigm_loss(const float* pred, const float* target, float* loss, float* gpred, float* ws, int32_t n, int32_t h, int32_t w,
                   float gmweight, int32_t scales, void* stream);
 
+/* ---- inference events (Trainer.infer_all, trainer.py:218-334) — NCHW fp32 images at the API edge ---------------------
+ * minmax_per_sample: per-sample min/max (tutils.normalize :567-576) -> mm[n][2].
+ * fire (climategan/fire.py:68-127): fire_tone = normalize(x,0,255), warm (+40,-10,-20), clamp, uint8, adjust_contrast(c),
+ *   adjust_brightness(b) with torchvision's uint8 truncation (gray_sum: n doubles scratch); sky_mask = argmax(seg)==sky_idx with
+ *   the bottom third cropped (:95-97); plane_resize_nearest = F.interpolate of the mask (:99-102); box_dilate =
+ *   increase_sky_mask (:15-47; on a binary mask the shifted sums + clamp are a box dilation, radius int(p*size)-1);
+ *   gauss_blur = kornia filter2d with get_gaussian_kernel2d (:104-111; kornia 0.5.10 is not vendored — restated: outer product
+ *   of two normalised 1-D Gaussians, reflect border), run as two 1-D passes; fire_paste = paste_tensor with the (255,g,0)
+ *   filter at transparency/255, uint8, adjust_brightness, the two "dummy" corner pixels (:113-125).
+ * smog (trainer.py:1879-1939): HazeRD transmission exp(-beta*d) on srgb2lrgb(normalize(x)) with d = normalize(1/normalize(d,
+ *   .3,1),.1,1) bilinearly upsampled (align_corners), airlight, lrgb2srgb, yellow filter (alpha and colour already /255).
+ * to_uint8_nhwc: normalize(t) -> NHWC -> (t*255).astype(uint8) (trainer.py:312-327); mask_to_uint8: (m > bin)*255 (:330-332). */
+int cgb_minmax_per_sample(const float* x, float* mm, int32_t n, int64_t count, void* stream);
+int cgb_fire_tone(const float* x, const float* mm, float* out, double* gray_sum, int32_t n, int32_t hw, float contrast,
+                  float brightness, void* stream);
+int cgb_sky_mask(const float* seg, float* out, int32_t n, int32_t c, int32_t hs, int32_t ws, int32_t sky_idx, int32_t crop_bottom,
+                 void* stream);
+int cgb_plane_resize_nearest(const float* x, float* y, int32_t n, int32_t hi, int32_t wi, int32_t ho, int32_t wo, void* stream);
+int cgb_box_dilate(const float* x, float* tmp, float* y, int32_t n, int32_t h, int32_t w, int32_t radius_w, int32_t radius_h,
+                   void* stream);
+int cgb_gauss_blur(const float* x, float* tmp, float* y, int32_t n, int32_t h, int32_t w, int32_t ksize, float sigma, void* stream);
+int cgb_fire_paste(const float* img, const float* sky, float* out, int32_t n, int32_t h, int32_t w, float fr, float fg, float fb,
+                   float transparency, float brightness, void* stream);
+int cgb_smog(const float* x, const float* mmx, const float* d, const float* mmd, float* out, int32_t n, int32_t h, int32_t w,
+             int32_t hd, int32_t wd, float airlight, float beta, float alpha, float yr, float yg, float yb, void* stream);
+int cgb_to_uint8_nhwc(const float* x, const float* mm, uint8_t* out, int32_t n, int32_t hw, void* stream);
+int cgb_mask_to_uint8(const float* m, uint8_t* out, float bin_value, int64_t count, void* stream);
+
 /* ---- layout / elementwise ----------------------------------------------------------------
  * NCHW fp32 (the reference's tensor layout at the API edge) <-> NHWC storage. */
 int cgb_nchw_to_nhwc(const float* x, void* y, int32_t dtype, int32_t n, int32_t c, int32_t hw,

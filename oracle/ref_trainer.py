@@ -14,7 +14,7 @@ from oracle import refshim
 from climategan_b200.utils import full_opts, synth_batch  # noqa: E402,F401  (shared with the product's bench / tests)
 
 
-def build_reference_trainer(opts, size, vgg_seed=13):
+def build_reference_trainer(opts, size, vgg_seed=13, inference=False):
     """Returns the reference Trainer with G, D, optimisers and losses assembled (CPU, train mode, dropout disabled)."""
     trainer_mod, generator_mod, disc_mod, losses_mod, optim_mod, tutils_mod = refshim.load(
         "trainer", "generator", "discriminator", "losses", "optim", "tutils")
@@ -45,12 +45,27 @@ def build_reference_trainer(opts, size, vgg_seed=13):
 
     losses_mod.CustomBCELoss.__call__ = custom_bce_call
 
+    class _CpuTimer:  # utils.Timer defaults to cuda=True and records CUDA events (utils.py:919-959): patch (5) of SURVEY.md §8c
+        def __init__(self, name="", store=None, precision=3, ignore=False, cuda=False):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    trainer_mod.Timer = _CpuTimer
     dev = torch.device("cpu")
     t = trainer_mod.Trainer(opts, device=dev)
     t.G = generator_mod.create_generator(opts, device=dev, no_init=True)
     t.has_painter = "p" in opts.tasks
     if t.has_painter:
         t.G.painter.set_latent_shape(size, True)
+    if inference:
+        t.is_setup = True
+        t.G.eval()
+        return t
     t.D = disc_mod.create_discriminator(opts, dev, no_init=True)
     t.g_opt, t.g_scheduler, t.lr_names["G"] = optim_mod.get_optimizer(t.G, opts.gen.opt, opts.tasks)
     t.d_opt, t.d_scheduler, t.lr_names["D"] = optim_mod.get_optimizer(t.D, opts.dis.opt, opts.tasks, True)
@@ -64,12 +79,14 @@ def build_reference_trainer(opts, size, vgg_seed=13):
     return t
 
 
-def load_weights(t, seeds=(21, 22, 23)):
+def load_weights(t, seeds=(21, 22, 23), d=True):
     from tests.golden.weights import fill_state_dict
 
     g_shapes = [(k, tuple(v.shape)) for k, v in t.G.state_dict().items()]
-    d_shapes = [(k, tuple(v.shape)) for k, v in t.D.state_dict().items()]
     t.G.load_state_dict(fill_state_dict(g_shapes, seeds[0]), strict=True)
+    if not d:
+        return g_shapes, None, None
+    d_shapes = [(k, tuple(v.shape)) for k, v in t.D.state_dict().items()]
     t.D.load_state_dict(fill_state_dict(d_shapes, seeds[1]), strict=True)
     v_shapes = None
     if "p" in t.opts.tasks and "vgg" in t.losses["G"]["p"]:

@@ -16,16 +16,32 @@ CASES = {
     "dg48": ("dgrad", 16, 128, 48, 640, 640, 3, 1),
     "wg48": ("wgrad", 16, 128, 48, 640, 640, 3, 1),
     "wgsh": ("wgrad", 16, 32, 128, 640, 640, 1, 0),
+    # masker (full train step, 8 images per domain): (which, n, ci, co, h, w, k, pad, dil, stride)
+    "r3": ("fwd", 8, 256, 256, 80, 80, 3, 2, 2, 1),       # ResNet layer3 conv2, dilation 2 — the step's dominant class
+    "r3d": ("dgrad", 8, 256, 256, 80, 80, 3, 2, 2, 1),
+    "r3w": ("wgrad", 8, 256, 256, 80, 80, 3, 2, 2, 1),
+    "r1": ("fwd", 8, 256, 1024, 80, 80, 1, 0, 1, 1),      # layer3 conv3
+    "r1w": ("wgrad", 8, 256, 1024, 80, 80, 1, 0, 1, 1),
+    "r1b": ("fwd", 8, 1024, 256, 80, 80, 1, 0, 1, 1),     # layer3 conv1
+    "stem": ("fwd", 8, 8, 64, 640, 640, 7, 3, 1, 2),      # conv1 7x7 s2 on the 3-channel image
+    "aspp": ("fwd", 8, 2048, 256, 80, 80, 3, 12, 12, 1),  # ASPP atrous branch
+    "vgg3": ("fwd", 8, 256, 256, 160, 160, 3, 1, 1, 1),   # VGG19 conv3_x
+    "vgg3d": ("dgrad", 8, 256, 256, 160, 160, 3, 1, 1, 1),
+    "vgg2": ("fwd", 8, 128, 128, 320, 320, 3, 1, 1, 1),   # VGG19 conv2_2
+    "r2": ("fwd", 8, 128, 128, 80, 80, 3, 1, 1, 1),       # ResNet layer2 conv2
+    "r4": ("fwd", 8, 512, 512, 80, 80, 3, 4, 4, 1),       # ResNet layer4 conv2 (dilation 4)
+    "d3": ("fwd", 8, 512, 512, 39, 39, 4, 1, 1, 1),       # discriminator 512->512 4x4
 }
 names = sys.argv[1:] or list(CASES)
 reps = int(os.environ.get("REPS", "5"))
 for name in names:
-    which, n, ci, co, h, w, k, pad = CASES[name]
+    which, n, ci, co, h, w, k, pad, dil, stride = (tuple(CASES[name]) + (1, 1))[:10]
+    ho, wo = (h + 2 * pad - dil * (k - 1) - 1) // stride + 1, (w + 2 * pad - dil * (k - 1) - 1) // stride + 1
     x = torch.randn(n, h, w, ci, device=dev).bfloat16()
     wp = (torch.randn(co, k * k, ci, device=dev) * 0.05).bfloat16()
     bias = torch.zeros(co, device=dev)
-    g = ops.ConvGeom(k, k, 1, 1, pad, _lib.PAD_ZERO, _lib.ACT_NONE, 0.2, _lib.ENGINE_AUTO)
-    gy = torch.randn(n, h, w, co, device=dev).bfloat16()
+    g = ops.ConvGeom(k, k, stride, dil, pad, _lib.PAD_ZERO, _lib.ACT_NONE, 0.2, _lib.ENGINE_AUTO)
+    gy = torch.randn(n, ho, wo, co, device=dev).bfloat16()
     def run():
         if which == "fwd":
             return ops.conv_fwd_raw(x, wp, bias, None, g)
@@ -39,6 +55,6 @@ for name in names:
         run()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    flops = 2.0 * n * h * w * ci * co * k * k
-    byts = 2.0 * n * h * w * (ci + co)
-    print(f"{name:6s} {which:5s} {ci}->{co} k{k} @{h}x{w} n={n}: {ms:.3f} ms  {flops/ms/1e9:.1f} TFLOP/s  {byts/ms/1e6:.0f} GB/s (min HBM traffic)", flush=True)
+    flops = 2.0 * n * ho * wo * ci * co * k * k
+    byts = 2.0 * n * (h * w * ci + ho * wo * co)
+    print(f"{name:6s} {which:5s} {ci}->{co} k{k} d{dil} s{stride} @{h}x{w} n={n}: {ms:.3f} ms  {flops/ms/1e9:.1f} TFLOP/s  {byts/ms/1e6:.0f} GB/s (min HBM traffic)", flush=True)

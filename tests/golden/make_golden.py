@@ -321,6 +321,35 @@ def run_full_step_case(name="full_step", batch=2, size=128):
     print(name, "logs[0]", {k: round(v, 5) for k, v in logs[0].items()}, "npz bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
 
 
+def run_infer_all_case(name="infer_all", batch=2, size=320):
+    """The reference's OWN ``Trainer.infer_all`` (trainer.py:218-334) on CPU: eval-mode masker (ResNet [2,2,3,2]) + painter,
+    then wildfire / smog / flood compositing and the normalize -> uint8 NHWC edge.  ``random.seed(0)`` fixes the wildfire
+    filter's green value (fire.py:115); cloudy=False.  uint8 outputs are stored on a stride-2 pixel grid."""
+    import random
+
+    from oracle import ref_trainer as rt
+
+    opts = rt.full_opts(size=size)
+    t = rt.build_reference_trainer(opts, size, inference=True)
+    g_shapes, _, _ = rt.load_weights(t, d=False)
+    x = synth_inputs(batch, size, seed=9)[0]
+    random.seed(0)
+    out = t.infer_all(x.clone(), numpy=True, bin_value=0.5, return_masks=True)
+    random.seed(0)
+    raw = t.infer_all(x.clone(), numpy=False)
+    arrays = {k: v[:, ::2, ::2].copy() for k, v in out.items() if k != "mask"}
+    arrays["mask"] = out["mask"][:, :, ::2, ::2].copy()
+    for k, v in raw.items():
+        arrays["raw_" + k] = v.detach().numpy()[:, :, ::4, ::4].astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+    meta = {"case": name, "batch": batch, "size": size, "seeds": {"G": 21, "inputs": 9, "random": 0},
+            "g_shapes": [[k, list(s_)] for k, s_ in g_shapes],
+            "reference": "cc-ai/climategan @ /root/reference: climategan.trainer.Trainer.infer_all (unmodified), CPU, torch " + torch.__version__}
+    with open(os.path.join(HERE, name + ".json"), "w") as f:
+        json.dump(meta, f)
+    print(name, {k: (v.shape, str(v.dtype)) for k, v in arrays.items()}, "npz bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
+
+
 if __name__ == "__main__":
     if not refshim.available():
         sys.exit("reference tree not available; goldens can only be regenerated in the build container")
@@ -330,3 +359,4 @@ if __name__ == "__main__":
     run_step_case()
     run_masker_case()
     run_full_step_case()
+    run_infer_all_case()

@@ -102,3 +102,39 @@ def test_fc_discriminator(cuda):
         ref = F.conv2d(ref, m.weight, m.bias, stride=2, padding=1) if isinstance(m, torch.nn.Conv2d) else F.leaky_relu(ref, 0.2)
     out = fc_discriminator_forward(net.to(cuda), x.to(cuda), torch.float32)
     assert out.shape == (2, 1, 2, 2) and rel_max(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("train_uv", [False, True])
+def test_fc_discriminator_two_calls_before_backward(cuda, train_uv):
+    """The D step runs each AdvEnt discriminator on the r and then the s batch before ONE backward.  In the reference the
+    spectral-norm u / v Parameters are saved by reference and their .data swapped on every forward, so both backward passes
+    use the last forward's u, v in d(sigma)/dW (and, once run_epoch has flipped requires_grad on them, u and v get gradients
+    themselves).  Product (fp32) vs the oracle, which reproduces this through the same aliasing."""
+    from climategan_b200 import ops
+    from climategan_b200.discriminator import fc_discriminator_forward, get_fc_discriminator
+    from oracle import full_step_oracle as fo
+    from oracle.painter_oracle import SNState
+
+    torch.manual_seed(0)
+    net = get_fc_discriminator(num_classes=11, use_norm=True)
+    sd = {"D." + k: v.detach().clone() for k, v in net.state_dict().items()}
+    pa, pb = torch.softmax(torch.randn(2, 11, 32, 32), 1), torch.softmax(torch.randn(2, 11, 32, 32), 1)
+    osd = {k: v.clone().requires_grad_(train_uv or not k.endswith(("_u", "_v"))) for k, v in sd.items()}
+    sn = SNState(osd)
+    lo = fo.advent(pa, 1, osd, sn, "D", None, wgan=False) + fo.advent(pb, 0, osd, sn, "D", None, wgan=False)
+    lo.backward()
+    net = net.to(cuda)
+    for n, p in net.named_parameters():
+        p.requires_grad_(train_uv or not n.endswith(("_u", "_v")))
+    D = lambda t: fc_discriminator_forward(net, t, torch.float32)  # noqa: E731
+    lp = (ops.const_target_loss(D(ops.prob_2_entropy(pa.to(cuda))), ops.LOSS_BCE_LOGITS, 1.0)
+          + ops.const_target_loss(D(ops.prob_2_entropy(pb.to(cuda))), ops.LOSS_BCE_LOGITS, 0.0))
+    lp.backward()
+    assert abs(float(lp) - float(lo)) < 1e-5
+    for n, p in net.named_parameters():
+        go = osd["D." + n].grad
+        assert (go is None) == (p.grad is None), n
+        if go is not None:
+            assert rel_max(p.grad, go) < 2e-4, n
+        if n.endswith(("_u", "_v")):
+            assert rel_max(p, osd["D." + n]) < 1e-5, n
