@@ -107,6 +107,8 @@ SIGNATURES = {
     "cgb_bn_apply_fwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P], C.c_int),
     "cgb_bn_apply_bwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P], C.c_int),
     "cgb_bn_bwd_finalize": ([_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P], C.c_int),
+    "cgb_bn_train_fwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _F, _I, _F, _P], C.c_int),
+    "cgb_bn_train_bwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P], C.c_int),
     "cgb_bn_update_running": ([_P, _P, _P, _P, _I, _L, _F, _F, _P], C.c_int),
     "cgb_maxpool3s2_ceil_bwd": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_resize_bilinear_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
@@ -137,6 +139,7 @@ SIGNATURES = {
     "cgb_mask_to_uint8": ([_P, _P, _F, _L, _P], C.c_int),
     "cgb_resize_nearest_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_upsample_nearest_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_im2col_strided": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_im2col": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_nchw_to_nhwc": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_nhwc_to_nchw": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),

@@ -49,12 +49,27 @@ static std::vector<ProfRec> g_prof;
 static std::mutex g_prof_mu;
 static std::atomic<int> g_prof_on{0};
 
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t take_event() {
+  {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    if (!g_event_pool.empty()) {
+      cudaEvent_t e = g_event_pool.back();
+      g_event_pool.pop_back();
+      return e;
+    }
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
 struct ProfScope {
   bool on; ProfRec r; cudaStream_t st;
   ProfScope(const cgb_conv_desc* d, int which, bool tc, cudaStream_t s) : on(g_prof_on.load() != 0), st(s) {
     if (!on) return;
     r.d = *d; r.which = which; r.tc = tc ? 1 : 0;
-    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    r.a = take_event(); r.b = take_event();   // pooled: creating two events per launch costs more than recording them
     cudaEventRecord(r.a, st);
   }
   ~ProfScope() {
@@ -219,7 +234,7 @@ extern "C" int cgb_prof_dump(char* buf, int64_t cap) {
   for (auto& r : g_prof) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
-    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    g_event_pool.push_back(r.a); g_event_pool.push_back(r.b);
     char key[256];
     snprintf(key, sizeof(key), "%d %d %d %d %d %d %d %d %d %d %d %d %d", r.which, r.tc, r.d.n, r.d.hi, r.d.wi,
              r.d.ci, r.d.ho, r.d.wo, r.d.co, r.d.kh, r.d.kw, r.d.stride, r.d.dil);

@@ -28,6 +28,8 @@ static inline int grid_for(long long work, int block = 256) {
   }
 
 static inline int bn_chunks(long long npix) {
+  // measured: a 32-pixel floor (1184 CTAs on the 8x80x80 ResNet maps) and 4 pixels in flight per thread made these passes
+  // 10-40 % SLOWER (more per-CTA set-up and fp64 atomics than the extra parallelism buys) -- kept at a 256-pixel floor
   long long want = 148 * 8;
   long long maxc = (npix + 255) / 256;
   if (want > maxc) want = maxc;
@@ -57,25 +59,31 @@ bn_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, con
   }
   const long long p0 = (long long)blockIdx.x * px_per_chunk;
   const long long p1 = min(npix, p0 + px_per_chunk);
-  for (long long p = p0 + lane; p < p1; p += lanes) {
-    float xv[8], o[8];
-    Vec8<T>::load(x + p * c + v * 8, xv);
-    if (residual) {
-      float r[8];
-      Vec8<T>::load(residual + p * c + v * 8, r);
+  constexpr int U = 1;  // pixels in flight per thread (U = 4 measured slower, see bn_chunks)
+  for (long long p = p0 + lane; p < p1; p += (long long)lanes * U) {
+    float xv[U][8], r[U][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float t = fmaf(xv[j], A[j], B[j]) + r[j];
-        o[j] = t > 0.f ? t : t * neg;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float t = fmaf(xv[j], A[j], B[j]);
-        o[j] = t > 0.f ? t : t * neg;
+    for (int u = 0; u < U; ++u) {
+      const long long pp = p + (long long)u * lanes;
+      if (pp < p1) {
+        Vec8<T>::load(x + pp * c + v * 8, xv[u]);
+        if (residual) Vec8<T>::load(residual + pp * c + v * 8, r[u]);
       }
     }
-    Vec8<T>::store(y + p * c + v * 8, o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long pp = p + (long long)u * lanes;
+      if (pp < p1) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = fmaf(xv[u][j], A[j], B[j]);
+          if (residual) t += r[u][j];
+          o[j] = t > 0.f ? t : t * neg;
+        }
+        Vec8<T>::store(y + pp * c + v * 8, o);
+      }
+    }
   }
 }
 
@@ -102,25 +110,32 @@ bn_apply_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, con
     }
     const long long p0 = (long long)blockIdx.x * px_per_chunk;
     const long long p1 = min(npix, p0 + px_per_chunk);
-    for (long long p = p0 + lane; p < p1; p += lanes) {
-      float xv[8], g[8], o[8];
-      Vec8<T>::load(x + p * c + v * 8, xv);
-      Vec8<T>::load(gy + p * c + v * 8, g);
-      if (has_act) {
-        float yv[8];
-        Vec8<T>::load(y + p * c + v * 8, yv);
+    constexpr int U = 1;
+    for (long long p = p0 + lane; p < p1; p += (long long)lanes * U) {
+      float xv[U][8], g[U][8], yv[U][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = yv[j] > 0.f ? g[j] : g[j] * neg;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = g[j];
+      for (int u = 0; u < U; ++u) {
+        const long long pp = p + (long long)u * lanes;
+        if (pp < p1) {
+          Vec8<T>::load(x + pp * c + v * 8, xv[u]);
+          Vec8<T>::load(gy + pp * c + v * 8, g[u]);
+          if (has_act) Vec8<T>::load(y + pp * c + v * 8, yv[u]);
+        }
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1[j] += o[j];
-        s2[j] = fmaf(o[j], fmaf(xv[j], rs[j], nm[j]), s2[j]);
+      for (int u = 0; u < U; ++u) {
+        const long long pp = p + (long long)u * lanes;
+        if (pp < p1) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            o[j] = (!has_act || yv[u][j] > 0.f) ? g[u][j] : g[u][j] * neg;
+            s1[j] += o[j];
+            s2[j] = fmaf(o[j], fmaf(xv[u][j], rs[j], nm[j]), s2[j]);
+          }
+          Vec8<T>::store(gpre + pp * c + v * 8, o);
+        }
       }
-      Vec8<T>::store(gpre + p * c + v * 8, o);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -160,21 +175,36 @@ bn_bwd_finalize_kernel(const T* __restrict__ x, const float* __restrict__ mean, 
   }
   const long long p0 = (long long)blockIdx.x * px_per_chunk;
   const long long p1 = min(npix, p0 + px_per_chunk);
-  for (long long p = p0 + lane; p < p1; p += lanes) {
-    float xv[8], gv[8], o[8];
-    Vec8<T>::load(x + p * c + v * 8, xv);
-    Vec8<T>::load(gpre + p * c + v * 8, gv);
+  constexpr int U = 1;
+  for (long long p = p0 + lane; p < p1; p += (long long)lanes * U) {
+    float xv[U][8], gv[U][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], gv[j], fmaf(B[j], xv[j], Cc[j]));
-    Vec8<T>::store(gx + p * c + v * 8, o);
+    for (int u = 0; u < U; ++u) {
+      const long long pp = p + (long long)u * lanes;
+      if (pp < p1) {
+        Vec8<T>::load(x + pp * c + v * 8, xv[u]);
+        Vec8<T>::load(gpre + pp * c + v * 8, gv[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long pp = p + (long long)u * lanes;
+      if (pp < p1) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], gv[u][j], fmaf(B[j], xv[u][j], Cc[j]));
+        Vec8<T>::store(gx + pp * c + v * 8, o);
+      }
+    }
   }
 }
 
 // running_mean = (1-mom)*running_mean + mom*mean ; running_var likewise with the UNBIASED batch variance
 __global__ void bn_update_running_kernel(const float* __restrict__ mean, const float* __restrict__ rstd,
                                          float* __restrict__ rmean, float* __restrict__ rvar, int c, double count,
-                                         float momentum, float eps) {
+                                         float momentum, float eps, long long* __restrict__ num_batches_tracked) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && num_batches_tracked) num_batches_tracked[0] += 1;
   if (i >= c) return;
   const double rs = (double)rstd[i];
   double var = 1.0 / (rs * rs) - (double)eps;
@@ -824,8 +854,37 @@ extern "C" int cgb_bn_update_running(const float* mean, const float* rstd, float
   CGB_CHECK_DEVICE();
   CGB_REQUIRE(mean && rstd && running_mean && running_var && c > 0, "bn_update_running: bad arguments");
   bn_update_running_kernel<<<(c + 255) / 256, 256, 0, (cudaStream_t)stream>>>(mean, rstd, running_mean, running_var, c,
-                                                                             (double)count, momentum, eps);
+                                                                             (double)count, momentum, eps, nullptr);
   return after_launch("bn_update_running");
+}
+
+// One call for the whole train-mode forward: statistics -> running-stat update (+ num_batches_tracked) -> normalise/affine/
+// residual/activation.  Saves three Python->C round trips per BatchNorm (464 BatchNorm forwards per train step).
+extern "C" int cgb_instnorm_stats(const void* x, int32_t dtype, int32_t n, int32_t hw, int32_t c, float eps, double* ws,
+                                  float* mean, float* rstd, void* stream);
+extern "C" int cgb_bn_train_fwd(const void* x, const float* weight, const float* bias, const void* residual, void* y, float* mean,
+                                float* rstd, double* ws, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                int32_t dtype, int64_t npix, int32_t c, int32_t c_logical, float momentum, float eps, int32_t act,
+                                float slope, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(npix > 0 && npix < (1ll << 31), "bn_train_fwd: npix=%lld out of range", (long long)npix);
+  int s = cgb_instnorm_stats(x, dtype, 1, (int32_t)npix, c, eps, ws, mean, rstd, stream);
+  if (s) return s;
+  if (running_mean && running_var) {
+    bn_update_running_kernel<<<(c_logical + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        mean, rstd, running_mean, running_var, c_logical, (double)npix, momentum, eps, (long long*)num_batches_tracked);
+    if ((s = after_launch("bn_update_running"))) return s;
+  }
+  return cgb_bn_apply_fwd(x, mean, rstd, weight, bias, residual, y, dtype, npix, c, act, slope, stream);
+}
+
+// backward in one call: part 1 (activation mask, sums, gpre) then part 2 (gx) when the input needs a gradient
+extern "C" int cgb_bn_train_bwd(const void* x, const float* mean, const float* rstd, const float* weight, const void* y,
+                                const void* gy, void* gpre, void* gx, double* sums, int32_t dtype, int64_t npix, int32_t c,
+                                int32_t act, float slope, void* stream) {
+  int s = cgb_bn_apply_bwd(x, mean, rstd, y, gy, gpre, sums, dtype, npix, c, act, slope, stream);
+  if (s || !gx) return s;
+  return cgb_bn_bwd_finalize(x, mean, rstd, weight, sums, gpre, gx, dtype, npix, c, stream);
 }
 
 extern "C" int cgb_maxpool3s2_ceil_bwd(const void* x, const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi, int32_t wi,

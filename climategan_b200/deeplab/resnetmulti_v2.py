@@ -114,12 +114,25 @@ class ResNetMulti(nn.Module):
 
     def forward_storage(self, x):
         """x: storage [N,H,W,8] (3 real channels) -> z storage [N,H/8,W/8,2048]."""
+        # stem: the 7x7 stride-2 conv on the 3-channel image runs as im2col (147 -> 152 channels) + ONE K=152 GEMM
+        c1 = self.conv1
+        k, cin = c1.kernel_size[0], c1.in_channels
+        xc = ops.im2col_strided(x, cin, k, c1.padding[0], 1, c1.stride[0])
+        kk = k * k * cin
+
+        def as_gemm(w):   # [co, cin, k, k] -> [co, round8(k*k*cin), 1, 1] in the patches' tap-major order (autograd-native)
+            w2 = w.permute(0, 2, 3, 1).reshape(w.shape[0], kk)
+            return torch.nn.functional.pad(w2, (0, xc.shape[-1] - kk)).view(w.shape[0], xc.shape[-1], 1, 1)
+
         if self.training:
-            x = ops.conv2d(x, self.conv1.weight, None, stride=2, pad=3)
+            x = ops.conv2d(xc, as_gemm(c1.weight), None)
             x = ops.batchnorm_act(x, self.bn1, None, _lib.ACT_RELU)
         else:
-            w, b = fold_bn(self.conv1, self.bn1, x.dtype, cis=x.shape[-1])
-            x = ops.conv2d_infer(x, w, b, k=7, stride=2, pad=3, act=_lib.ACT_RELU)
+            scale = self.bn1.weight.detach() / torch.sqrt(self.bn1.running_var + self.bn1.eps)
+            w = as_gemm(c1.weight.detach() * scale.view(-1, 1, 1, 1))
+            b = self.bn1.bias.detach() - self.bn1.running_mean * scale
+            wp = ops.pack_weight(w, x.dtype, cis=xc.shape[-1])
+            x = ops.conv2d_infer(xc, wp, ops.pad_bias(b, wp.shape[0]), k=1, act=_lib.ACT_RELU)
         x = ops.maxpool3s2_ceil(x)
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
             for blk in layer:

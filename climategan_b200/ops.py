@@ -213,6 +213,19 @@ def im2col(x: torch.Tensor, c: int, k: int = 3, pad: int = 1, dil: int = 1) -> t
     return y
 
 
+def im2col_strided(x: torch.Tensor, c: int, k: int, pad: int, dil: int = 1, stride: int = 1) -> torch.Tensor:
+    """[N,H,W,Cs] storage tensor with c logical channels -> [N,Ho,Wo,round8(k*k*c)] patches (tap-major) at an output stride.
+    Not differentiable w.r.t. x (used on input images)."""
+    _chk_storage(x)
+    n, h, w, cs = x.shape
+    cs_out = round8(k * k * c)
+    ho, wo = (h + 2 * pad - dil * (k - 1) - 1) // stride + 1, (w + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    y = torch.empty((n, ho, wo, cs_out), dtype=x.dtype, device=x.device)
+    check(_L().cgb_im2col_strided(_p(x.detach()), _p(y), _DT[x.dtype], n, h, w, cs, c, k, pad, dil, stride, cs_out, _st()),
+          "im2col_strided")
+    return y
+
+
 def act_bwd_raw(gy, y, act, slope):
     gx = torch.empty_like(gy)
     check(_L().cgb_act_bwd(_p(gy), _p(y), _p(gx), _DT[gy.dtype], gy.numel(), act, slope, _st()), "act_bwd")
@@ -990,23 +1003,13 @@ class _BatchNormAct(Function):
     and one apply pass over x; the backward is two passes (see include/cgb200.h)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, running_mean, running_var, training, momentum, eps, act, slope):
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, nbt, training, momentum, eps, act, slope):
         _chk_storage(x)
         n, h, w, cs = x.shape
         npix = n * h * w
         c = weight.numel() if weight is not None else (running_mean.numel() if running_mean is not None else cs)
         dev = x.device
-        if training or running_mean is None:
-            mean, rstd = instnorm_stats(x.view(1, npix, 1, cs), eps)
-            mean, rstd = mean.view(cs), rstd.view(cs)
-            if running_mean is not None and training:
-                check(_L().cgb_bn_update_running(_p(mean), _p(rstd), _p(running_mean), _p(running_var), c, npix,
-                                                 float(momentum), float(eps), _st()), "bn_update_running")
-        else:
-            mean = torch.zeros(cs, dtype=torch.float32, device=dev)
-            rstd = torch.ones(cs, dtype=torch.float32, device=dev)
-            mean[:c] = running_mean
-            rstd[:c] = torch.rsqrt(running_var + eps)
+        batch_stats = bool(training or running_mean is None)
         wp = bp = None
         if weight is not None:
             if c == cs and weight.dtype == torch.float32 and "aliasparam" not in _DBG:
@@ -1018,10 +1021,24 @@ class _BatchNormAct(Function):
                 bp[:c] = bias.detach()
         y = torch.empty_like(x)
         res = residual.contiguous() if residual is not None else None
-        check(_L().cgb_bn_apply_fwd(_p(x), _p(mean), _p(rstd), _p(wp), _p(bp), _p(res), _p(y), _DT[x.dtype], npix, cs, act,
-                                    slope, _st()), "bn_apply_fwd")
+        stats = torch.empty((2, cs), dtype=torch.float32, device=dev)
+        mean, rstd = stats[0], stats[1]
+        if batch_stats:
+            ws = torch.empty((cs, 2), dtype=torch.float64, device=dev)
+            upd = running_mean is not None and training
+            check(_L().cgb_bn_train_fwd(_p(x), _p(wp), _p(bp), _p(res), _p(y), _p(mean), _p(rstd), _p(ws),
+                                        _p(running_mean) if upd else None, _p(running_var) if upd else None,
+                                        _p(nbt) if upd else None, _DT[x.dtype], npix, cs, c, float(momentum), float(eps), act,
+                                        slope, _st()), "bn_train_fwd")
+        else:
+            mean.zero_()
+            rstd.fill_(1.0)
+            mean[:c] = running_mean
+            rstd[:c] = torch.rsqrt(running_var + eps)
+            check(_L().cgb_bn_apply_fwd(_p(x), _p(mean), _p(rstd), _p(wp), _p(bp), _p(res), _p(y), _DT[x.dtype], npix, cs, act,
+                                        slope, _st()), "bn_apply_fwd")
         ctx.save_for_backward(x, mean, rstd, wp, y if act != _lib.ACT_NONE else None)
-        ctx.meta = (act, slope, c, residual is not None, bool(training or running_mean is None))
+        ctx.meta = (act, slope, c, residual is not None, batch_stats)
         return y
 
     @staticmethod
@@ -1033,29 +1050,32 @@ class _BatchNormAct(Function):
         gy = gy.contiguous()
         gpre = torch.empty_like(x)
         sums = torch.empty((cs, 2), dtype=torch.float64, device=x.device)
-        check(_L().cgb_bn_apply_bwd(_p(x), _p(mean), _p(rstd), _p(y), _p(gy), _p(gpre), _p(sums), _DT[x.dtype], npix, cs, act,
-                                    slope, _st()), "bn_apply_bwd")
         gw = gb = gx = None
+        if batch_stats:
+            gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+            check(_L().cgb_bn_train_bwd(_p(x), _p(mean), _p(rstd), _p(wp), _p(y), _p(gy), _p(gpre), _p(gx), _p(sums),
+                                        _DT[x.dtype], npix, cs, act, slope, _st()), "bn_train_bwd")
+        else:
+            check(_L().cgb_bn_apply_bwd(_p(x), _p(mean), _p(rstd), _p(y), _p(gy), _p(gpre), _p(sums), _DT[x.dtype], npix, cs,
+                                        act, slope, _st()), "bn_apply_bwd")
+            if ctx.needs_input_grad[0]:
+                gx = torch.empty_like(x)
+                check(_L().cgb_bn_bwd_finalize(_p(x), _p(mean), _p(rstd), _p(wp), _p(torch.zeros_like(sums)), _p(gpre), _p(gx),
+                                               _DT[x.dtype], npix, cs, _st()), "bn_bwd_finalize")
         if wp is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
             sf = sums[:c].float()
             gw = sf[:, 1] if ctx.needs_input_grad[1] else None
             gb = sf[:, 0] if ctx.needs_input_grad[2] else None
-        if ctx.needs_input_grad[0]:
-            gx = torch.empty_like(x)
-            s = sums if batch_stats else torch.zeros_like(sums)
-            check(_L().cgb_bn_bwd_finalize(_p(x), _p(mean), _p(rstd), _p(wp), _p(s), _p(gpre), _p(gx), _DT[x.dtype], npix, cs,
-                                           _st()), "bn_bwd_finalize")
-        return gx, gw, gb, (gpre if has_res else None), None, None, None, None, None, None, None
+        return gx, gw, gb, (gpre if has_res else None), None, None, None, None, None, None, None, None
 
 
 def batchnorm_act(x, bn, residual=None, act=_lib.ACT_NONE, slope=0.2):
     """``act(bn(x) (+ residual))`` for an ``nn.BatchNorm2d`` parameter container ``bn`` (train: batch statistics + running
     update, exactly F.batch_norm's semantics; eval: running statistics)."""
-    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
     momentum = 0.1 if bn.momentum is None else bn.momentum
-    return _BatchNormAct.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.training, momentum, bn.eps,
-                               act, slope)
+    nbt = bn.num_batches_tracked if (bn.training and bn.track_running_stats) else None   # incremented inside the kernel
+    return _BatchNormAct.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, nbt, bn.training, momentum,
+                               bn.eps, act, slope)
 
 
 def make_m_cond(d, s, xr, ns):

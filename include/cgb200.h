@@ -170,6 +170,11 @@ int cgb_upsample_nearest_bwd(const void* gy, void* gx, int32_t dtype, int32_t n,
  * GEMM for the tensor cores; computed once per resolution and shared by every SPADE layer at that resolution. */
 int cgb_im2col(const void* x, void* y, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t cs_in, int32_t c,
                int32_t k, int32_t pad, int32_t dil, int32_t cs_out, void* stream);
+/* The same with an output stride: y is [n, ho, wo, cs_out], ho = (h + 2*pad - dil*(k-1) - 1)/stride + 1.  Turns the ResNet stem
+ * (7x7 stride-2 conv on the 3-channel image, resnetmulti_v2.py:70) into one K=152 GEMM: as 49 taps of an 8-channel TMA box it
+ * ran at 100 GB/s. */
+int cgb_im2col_strided(const void* x, void* y, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t cs_in, int32_t c,
+                       int32_t k, int32_t pad, int32_t dil, int32_t stride, int32_t cs_out, void* stream);
 
 /* ---- masker (inference) helpers, NHWC storage ---------------------------------------------
  * nn.MaxPool2d(3, stride=2, padding=0, ceil_mode=True) (deeplab/resnetmulti_v2.py:76-78); caller passes ho/wo.
@@ -206,6 +211,16 @@ int cgb_bn_bwd_finalize(const void* x, const float* mean, const float* rstd, con
                         const void* gpre, void* gx, int32_t dtype, int64_t npix, int32_t c, void* stream);
 int cgb_bn_update_running(const float* mean, const float* rstd, float* running_mean, float* running_var, int32_t c,
                           int64_t count, float momentum, float eps, void* stream);
+/* The same, one call per direction (three fewer host round trips per BatchNorm): train_fwd = statistics (ws: 2*c doubles
+ * scratch) -> running update of the first c_logical channels, num_batches_tracked += 1 (both optional) -> apply;
+ * train_bwd = part 1 then part 2 (gx NULL: part 1 only). */
+int cgb_bn_train_fwd(const void* x, const float* weight, const float* bias, const void* residual, void* y, float* mean,
+                     float* rstd, double* ws, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                     int32_t dtype, int64_t npix, int32_t c, int32_t c_logical, float momentum, float eps, int32_t act,
+                     float slope, void* stream);
+int cgb_bn_train_bwd(const void* x, const float* mean, const float* rstd, const float* weight, const void* y, const void* gy,
+                     void* gpre, void* gx, double* sums, int32_t dtype, int64_t npix, int32_t c, int32_t act, float slope,
+                     void* stream);
 /* adjoints of cgb_maxpool3s2_ceil_fwd (gradient to the first maximum of each window, as ATen), cgb_resize_bilinear_fwd,
  * cgb_channel_mean; nn.ReflectionPad2d (blocks.py:66-67) as an explicit copy + its fold-back adjoint so reflect-padded
  * convs run as pad-0 convs on the tcgen05 engine; dst[n,hw,c] = src[n,c]*scale (AdaptiveAvgPool2d(1) backward and the

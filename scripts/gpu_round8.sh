@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -q -m gpu --tb=short > gpurun_out/pytest_gpu.log 2>&1
+echo "rc=$?" >> gpurun_out/pytest_gpu.log
+tail -6 gpurun_out/pytest_gpu.log | cut -c1-1200
+timeout 900 python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err
+echo "bench rc=$?"; head -c 330 gpurun_out/bench_full.json; echo; tail -2 gpurun_out/bench_full.err

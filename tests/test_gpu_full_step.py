@@ -159,7 +159,9 @@ def test_full_step_bf16_close_to_reference_trainer(cuda):
         ref, got = g[side + ".gradnorm"], out[side + ".gradnorm"]
         names = meta["g_param_names" if side == "G" else "d_param_names"]
         for n, a, b in zip(names, got, ref):
-            if b > 1e-4 and not n.endswith(("weight_u", "weight_v")) and abs(a - b) > 0.3 * b:
+            # aspp.global_avg_pool: BatchNorm over the 2 samples of a 1x1 map normalises to exactly +-1, so the gradient that
+            # reaches its conv is a rounding residue ~ eps / var — not comparable across precisions
+            if b > 1e-4 and not n.endswith(("weight_u", "weight_v")) and "global_avg_pool" not in n and abs(a - b) > 0.3 * b:
                 bad.append((n, a, b))
     for k in g:
         if ".grad::" in k and ("painter" in k or "decoders.m" in k or k.startswith("D.grad")):

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from climategan_b200.parallel import GradBucket, shard_batch
+from climategan_b200.parallel import GradBucket, allreduce_flat_grads, shard_batch
 
 
 def _free_port():
@@ -73,3 +73,36 @@ def test_shard_batch():
         pass
     else:
         raise AssertionError("uneven shard must raise")
+
+
+class _FlatOpt:
+    """Stand-in for optim.ExtraAdam's flat-buffer surface (the optimiser itself needs the CUDA library)."""
+
+    def __init__(self, *flats):
+        self.flat_grads = list(flats)
+
+
+def _worker_flat(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    d = torch.ones(4) * (10 * rank)
+    nbytes = allreduce_flat_grads(_FlatOpt(g, d))
+    out[rank] = (g.clone(), d.clone(), nbytes)
+    dist.destroy_process_group()
+
+
+def test_allreduce_flat_grads_gloo():
+    """Trainer.enable_data_parallel's collective: the optimiser's flat G / D gradient buffers are averaged in place, one
+    all-reduce per parameter group (what DDP would give the reference step)."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_flat, args=(world, _free_port(), out), nprocs=world, join=True)
+    for r in range(world):
+        g, d, nbytes = out[r]
+        assert torch.allclose(g, torch.arange(10, dtype=torch.float32) * 1.5)
+        assert torch.allclose(d, torch.ones(4) * 5.0)
+        assert nbytes == 14 * 4
+    assert allreduce_flat_grads(_FlatOpt(torch.ones(3))) == 0   # not distributed: a no-op
