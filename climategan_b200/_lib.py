@@ -83,6 +83,7 @@ SIGNATURES = {
     "cgb_conv2d_dgrad": ([_DP, _P, _P, _P, _I, _P, _P, _P], C.c_int),
     "cgb_conv2d_pack_dgrad_weight": ([_DP, _P, _P, _P], C.c_int),
     "cgb_conv2d_wgrad": ([_DP, _P, _P, _P, _P, _I, _P], C.c_int),
+    "cgb_instnorm_ws_doubles": ([_I, _I, _I], C.c_int64),
     "cgb_instnorm_stats": ([_P, _I, _I, _I, _I, _F, _P, _P, _P, _P], C.c_int),
     "cgb_spade_modulate_fwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),
     "cgb_spade_modulate_bwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),
@@ -106,6 +107,7 @@ SIGNATURES = {
     "cgb_make_m_cond": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_bn_apply_fwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P], C.c_int),
     "cgb_bn_apply_bwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P], C.c_int),
+    "cgb_bn_bwd_ws_doubles": ([_L, _I], C.c_int64),
     "cgb_bn_bwd_finalize": ([_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P], C.c_int),
     "cgb_bn_train_fwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _F, _I, _F, _P], C.c_int),
     "cgb_bn_train_bwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P], C.c_int),

@@ -87,19 +87,17 @@ bn_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, con
   }
 }
 
-// backward part 1: gpre = gy * act'(y); sums[c][0] += sum gpre ; sums[c][1] += sum gpre * xhat
+// backward part 1: gpre = gy * act'(y); per-chunk partial sums of gpre and gpre * xhat (no atomics: see in_stats_kernel)
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_apply_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const T* __restrict__ y, const T* __restrict__ gy, T* __restrict__ gpre, double* __restrict__ sums,
+                    const T* __restrict__ y, const T* __restrict__ gy, T* __restrict__ gpre, float* __restrict__ partial,
                     long long npix, int c, int px_per_chunk, float neg, int has_act) {
-  extern __shared__ float sm[];  // [2][c]
+  extern __shared__ float sm[];  // [256][16]
   const int cv = c >> 3;
   const int lanes = 256 / cv;
   const int tid = threadIdx.x;
   const int lane = tid / cv, v = tid - lane * cv;
-  for (int i = tid; i < 2 * c; i += 256) sm[i] = 0.f;
-  __syncthreads();
   if (lane < lanes) {
     float rs[8], nm[8], s1[8], s2[8];
 #pragma unroll
@@ -110,43 +108,67 @@ bn_apply_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, con
     }
     const long long p0 = (long long)blockIdx.x * px_per_chunk;
     const long long p1 = min(npix, p0 + px_per_chunk);
-    constexpr int U = 1;
-    for (long long p = p0 + lane; p < p1; p += (long long)lanes * U) {
-      float xv[U][8], g[U][8], yv[U][8];
+    for (long long p = p0 + lane; p < p1; p += lanes) {
+      float xv[8], g[8], o[8];
+      Vec8<T>::load(x + p * c + v * 8, xv);
+      Vec8<T>::load(gy + p * c + v * 8, g);
+      if (has_act) {
+        float yv[8];
+        Vec8<T>::load(y + p * c + v * 8, yv);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long pp = p + (long long)u * lanes;
-        if (pp < p1) {
-          Vec8<T>::load(x + pp * c + v * 8, xv[u]);
-          Vec8<T>::load(gy + pp * c + v * 8, g[u]);
-          if (has_act) Vec8<T>::load(y + pp * c + v * 8, yv[u]);
-        }
+        for (int j = 0; j < 8; ++j) o[j] = yv[j] > 0.f ? g[j] : g[j] * neg;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = g[j];
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long pp = p + (long long)u * lanes;
-        if (pp < p1) {
-          float o[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            o[j] = (!has_act || yv[u][j] > 0.f) ? g[u][j] : g[u][j] * neg;
-            s1[j] += o[j];
-            s2[j] = fmaf(o[j], fmaf(xv[u][j], rs[j], nm[j]), s2[j]);
-          }
-          Vec8<T>::store(gpre + pp * c + v * 8, o);
-        }
+      for (int j = 0; j < 8; ++j) {
+        s1[j] += o[j];
+        s2[j] = fmaf(o[j], fmaf(xv[j], rs[j], nm[j]), s2[j]);
       }
+      Vec8<T>::store(gpre + p * c + v * 8, o);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sm[v * 8 + j], s1[j]);
-      atomicAdd(&sm[c + v * 8 + j], s2[j]);
+      sm[tid * 16 + j] = s1[j];
+      sm[tid * 16 + 8 + j] = s2[j];
     }
   }
   __syncthreads();
+  float* out = partial + (long long)blockIdx.x * 2 * c;
   for (int i = tid; i < c; i += 256) {
-    atomicAdd(&sums[i * 2 + 0], (double)sm[i]);
-    atomicAdd(&sums[i * 2 + 1], (double)sm[c + i]);
+    const int vv = i >> 3, j = i & 7;
+    float S = 0.f, Q = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      S += sm[(l * cv + vv) * 16 + j];
+      Q += sm[(l * cv + vv) * 16 + 8 + j];
+    }
+    out[i] = S;
+    out[c + i] = Q;
+  }
+}
+
+// sums[c][2] (fp64) = sum over chunks of the partials
+__global__ void __launch_bounds__(512)
+bn_bwd_reduce_kernel(const float* __restrict__ partial, double* __restrict__ sums, int c, int chunks) {
+  __shared__ double sS[16][33], sQ[16][33];   // block (32 channels, 16 chunk groups), as in_stats_finalize_kernel
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ch = blockIdx.x * 32 + tx;
+  double S = 0.0, Q = 0.0;
+  if (ch < c) {
+    for (int k = ty; k < chunks; k += 16) {
+      S += (double)partial[(long long)k * 2 * c + ch];
+      Q += (double)partial[(long long)k * 2 * c + c + ch];
+    }
+  }
+  sS[ty][tx] = S;
+  sQ[ty][tx] = Q;
+  __syncthreads();
+  if (ty == 0 && ch < c) {
+#pragma unroll
+    for (int k = 1; k < 16; ++k) { S += sS[k][tx]; Q += sQ[k][tx]; }
+    sums[ch * 2 + 0] = S;
+    sums[ch * 2 + 1] = Q;
   }
 }
 
@@ -818,6 +840,13 @@ extern "C" int cgb_bn_apply_fwd(const void* x, const float* mean, const float* r
   return after_launch("bn_apply_fwd");
 }
 
+extern "C" int64_t cgb_bn_bwd_ws_doubles(int64_t npix, int32_t c) {
+  if (npix <= 0 || c <= 0) return 0;
+  const int chunks = bn_chunks(npix);
+  const int ppc = (int)((npix + chunks - 1) / chunks);
+  return 2 * (int64_t)c + ((npix + ppc - 1) / ppc) * c;   // sums[c][2] doubles, then chunks * 2c fp32 partials
+}
+
 extern "C" int cgb_bn_apply_bwd(const void* x, const float* mean, const float* rstd, const void* y, const void* gy, void* gpre,
                                 double* sums, int32_t dtype, int64_t npix, int32_t c, int32_t act, float slope, void* stream) {
   CGB_CHECK_DEVICE();
@@ -826,14 +855,17 @@ extern "C" int cgb_bn_apply_bwd(const void* x, const float* mean, const float* r
   REQ_C(c, "bn_apply_bwd");
   const float neg = act == CGB_ACT_NONE ? 1.f : (act == CGB_ACT_RELU ? 0.f : slope);
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)c, st);
   const int chunks = bn_chunks(npix);
   const int ppc = (int)((npix + chunks - 1) / chunks);
   const int grid = (int)((npix + ppc - 1) / ppc);
-  DISPATCH_T(dtype, bn_apply_bwd_kernel<T><<<grid, 256, 2 * c * sizeof(float), st>>>(
-                        (const T*)x, mean, rstd, (const T*)y, (const T*)gy, (T*)gpre, sums, npix, c, ppc, neg,
+  float* partial = reinterpret_cast<float*>(sums + 2 * (size_t)c);   // sums holds cgb_bn_bwd_ws_doubles(npix, c) doubles
+  DISPATCH_T(dtype, bn_apply_bwd_kernel<T><<<grid, 256, 256 * 16 * sizeof(float), st>>>(
+                        (const T*)x, mean, rstd, (const T*)y, (const T*)gy, (T*)gpre, partial, npix, c, ppc, neg,
                         act != CGB_ACT_NONE);)
-  return after_launch("bn_apply_bwd");
+  int s = after_launch("bn_apply_bwd");
+  if (s) return s;
+  bn_bwd_reduce_kernel<<<(c + 31) / 32, dim3(32, 16), 0, st>>>(partial, sums, c, grid);
+  return after_launch("bn_bwd_reduce");
 }
 
 extern "C" int cgb_bn_bwd_finalize(const void* x, const float* mean, const float* rstd, const float* weight, const double* sums,

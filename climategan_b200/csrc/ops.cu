@@ -18,19 +18,20 @@ static inline int pick_chunks(int n, int hw, int cv) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// instance-norm statistics: x [n,hw,c] -> sum, sumsq (fp64) per (n,c)
-// grid (chunks, n); block 256 threads = lanes x cv, cv = c/8 vector columns.
+// instance-norm statistics: x [n,hw,c] -> per-(n,c) sum and sum of squares.
+// grid (chunks, n); block 256 threads = lanes x cv, cv = c/8 vector columns.  No atomics: every thread parks its 16 partial
+// sums in shared memory, c threads fold the lanes and write ONE fp32 partial per (chunk, channel); the finalize kernel adds
+// the chunks in fp64.  (The first version folded through shared and fp64 global atomics: with 200-1184 CTAs hitting the same
+// 2c addresses the atomic tail cost more than the streaming pass itself, and made the result order-dependent.)
 template <typename T>
 __global__ void __launch_bounds__(256)
-in_stats_kernel(const T* __restrict__ x, double* __restrict__ ws, int hw, int c, int px_per_chunk) {
-  extern __shared__ float sm[];  // [2][c]
+in_stats_kernel(const T* __restrict__ x, float* __restrict__ partial, int hw, int c, int px_per_chunk) {
+  extern __shared__ float sm[];  // [256][16]
   const int cv = c >> 3;
   const int lanes = 256 / cv;
   const int tid = threadIdx.x;
   const int lane = tid / cv, v = tid - lane * cv;
   const int img = blockIdx.y;
-  for (int i = tid; i < 2 * c; i += 256) sm[i] = 0.f;
-  __syncthreads();
   if (lane < lanes) {
     float s[8], q[8];
 #pragma unroll
@@ -39,44 +40,64 @@ in_stats_kernel(const T* __restrict__ x, double* __restrict__ ws, int hw, int c,
     int p1 = p0 + px_per_chunk;
     if (p1 > hw) p1 = hw;
     const T* base = x + ((long long)img * hw) * c + v * 8;
-    constexpr int U = 1;   // pixels in flight per thread (4 measured slower)
-    for (int p = p0 + lane; p < p1; p += lanes * U) {
-      float f[U][8];
+    for (int p = p0 + lane; p < p1; p += lanes) {
+      float f[8];
+      Vec8<T>::load(base + (long long)p * c, f);
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (p + u * lanes < p1) Vec8<T>::load(base + (long long)(p + u * lanes) * c, f[u]);
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (p + u * lanes < p1) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            s[j] += f[u][j];
-            q[j] = fmaf(f[u][j], f[u][j], q[j]);
-          }
-        }
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        q[j] = fmaf(f[j], f[j], q[j]);
+      }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sm[v * 8 + j], s[j]);
-      atomicAdd(&sm[c + v * 8 + j], q[j]);
+      sm[tid * 16 + j] = s[j];
+      sm[tid * 16 + 8 + j] = q[j];
     }
   }
   __syncthreads();
+  float* out = partial + ((long long)img * gridDim.x + blockIdx.x) * 2 * c;
   for (int i = tid; i < c; i += 256) {
-    atomicAdd(&ws[((long long)img * c + i) * 2 + 0], (double)sm[i]);
-    atomicAdd(&ws[((long long)img * c + i) * 2 + 1], (double)sm[c + i]);
+    const int vv = i >> 3, j = i & 7;
+    float S = 0.f, Q = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      S += sm[(l * cv + vv) * 16 + j];
+      Q += sm[(l * cv + vv) * 16 + 8 + j];
+    }
+    out[i] = S;
+    out[c + i] = Q;
   }
 }
 
-__global__ void in_stats_finalize_kernel(const double* __restrict__ ws, float* __restrict__ mean,
-                                         float* __restrict__ rstd, int count, double inv_hw, float eps) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const double m = ws[2 * i] * inv_hw;
-  double var = ws[2 * i + 1] * inv_hw - m * m;
-  if (var < 0.0) var = 0.0;
-  mean[i] = (float)m;
-  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+// block (32 channels, 16 chunk groups): the chunk loop is split 16 ways and folded through shared memory, so a channel's 200
+// partials cost ~13 dependent loads instead of 200 (the serial version took longer than the streaming pass it finishes)
+__global__ void __launch_bounds__(512)
+in_stats_finalize_kernel(const float* __restrict__ partial, float* __restrict__ mean, float* __restrict__ rstd, int c,
+                         int chunks, double inv_hw, float eps) {
+  __shared__ double sS[16][33], sQ[16][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int img = blockIdx.y;
+  const int ch = blockIdx.x * 32 + tx;
+  double S = 0.0, Q = 0.0;
+  if (ch < c) {
+    const float* p = partial + (long long)img * chunks * 2 * c;
+    for (int k = ty; k < chunks; k += 16) {
+      S += (double)p[(long long)k * 2 * c + ch];
+      Q += (double)p[(long long)k * 2 * c + c + ch];
+    }
+  }
+  sS[ty][tx] = S;
+  sQ[ty][tx] = Q;
+  __syncthreads();
+  if (ty == 0 && ch < c) {
+#pragma unroll
+    for (int k = 1; k < 16; ++k) { S += sS[k][tx]; Q += sQ[k][tx]; }
+    const double m = S * inv_hw;
+    double var = Q * inv_hw - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[(long long)img * c + ch] = (float)m;
+    rstd[(long long)img * c + ch] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1079,6 +1100,13 @@ static inline int grid_for(long long work, int block = 256) {
     return CGB_BAD_ARG;                                 \
   }
 
+extern "C" int64_t cgb_instnorm_ws_doubles(int32_t n, int32_t hw, int32_t c) {
+  if (n <= 0 || hw <= 0 || c <= 0) return 0;
+  const int chunks = pick_chunks(n, hw, c / 8);
+  const int ppc = (hw + chunks - 1) / chunks;
+  return (int64_t)n * ((hw + ppc - 1) / ppc) * c;   // n * chunks * 2c floats
+}
+
 extern "C" int cgb_instnorm_stats(const void* x, int32_t dtype, int32_t n, int32_t hw, int32_t c,
                                   float eps, double* ws, float* mean, float* rstd, void* stream) {
   CGB_CHECK_DEVICE();
@@ -1086,14 +1114,15 @@ extern "C" int cgb_instnorm_stats(const void* x, int32_t dtype, int32_t n, int32
   CGB_REQUIRE(c % 8 == 0 && c >= 8 && c <= 2048, "instnorm_stats: c=%d must be a multiple of 8 in [8,2048]", c);
   CGB_REQUIRE(n > 0 && hw > 0, "instnorm_stats: empty input");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaMemsetAsync(ws, 0, sizeof(double) * 2 * (size_t)n * c, st);
   const int chunks = pick_chunks(n, hw, c / 8);
   const int ppc = (hw + chunks - 1) / chunks;
-  dim3 grid((hw + ppc - 1) / ppc, n);
-  DISPATCH_T(dtype, in_stats_kernel<T><<<grid, 256, 2 * c * sizeof(float), st>>>((const T*)x, ws, hw, c, ppc);)
+  const int gx = (hw + ppc - 1) / ppc;
+  dim3 grid(gx, n);
+  float* partial = reinterpret_cast<float*>(ws);   // cgb_instnorm_ws_doubles(n, hw, c) doubles = n*gx*2c floats
+  DISPATCH_T(dtype, in_stats_kernel<T><<<grid, 256, 256 * 16 * sizeof(float), st>>>((const T*)x, partial, hw, c, ppc);)
   int s = after_launch("in_stats");
   if (s) return s;
-  in_stats_finalize_kernel<<<(n * c + 255) / 256, 256, 0, st>>>(ws, mean, rstd, n * c, 1.0 / (double)hw, eps);
+  in_stats_finalize_kernel<<<dim3((c + 31) / 32, n), dim3(32, 16), 0, st>>>(partial, mean, rstd, c, gx, 1.0 / (double)hw, eps);
   return after_launch("in_stats_finalize");
 }
 

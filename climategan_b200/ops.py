@@ -191,11 +191,23 @@ def conv_wgrad_raw(x, gy, g: ConvGeom, want_bias: bool):
     return gw, gb
 
 
+_WS_CACHE = {}
+
+
+def _stats_ws(n: int, hw: int, c: int) -> int:
+    """doubles of scratch cgb_instnorm_stats needs for this shape (per-chunk partial sums)."""
+    k = (n, hw, c)
+    v = _WS_CACHE.get(k)
+    if v is None:
+        v = _WS_CACHE[k] = int(_L().cgb_instnorm_ws_doubles(n, hw, c))
+    return v
+
+
 def instnorm_stats(x: torch.Tensor, eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor]:
     """Per-(n,c) mean and 1/sqrt(var+eps) of a storage tensor (nn.InstanceNorm2d, norms.py:151)."""
     _chk_storage(x)
     n, h, w, c = x.shape
-    ws = torch.empty((n, c, 2), dtype=torch.float64, device=x.device)
+    ws = torch.empty((_stats_ws(n, h * w, c),), dtype=torch.float64, device=x.device)
     mean = torch.empty((n, c), dtype=torch.float32, device=x.device)
     rstd = torch.empty((n, c), dtype=torch.float32, device=x.device)
     check(_L().cgb_instnorm_stats(_p(x), _DT[x.dtype], n, h * w, c, eps, _p(ws), _p(mean), _p(rstd), _st()),
@@ -1024,7 +1036,7 @@ class _BatchNormAct(Function):
         stats = torch.empty((2, cs), dtype=torch.float32, device=dev)
         mean, rstd = stats[0], stats[1]
         if batch_stats:
-            ws = torch.empty((cs, 2), dtype=torch.float64, device=dev)
+            ws = torch.empty((_stats_ws(1, npix, cs),), dtype=torch.float64, device=dev)
             upd = running_mean is not None and training
             check(_L().cgb_bn_train_fwd(_p(x), _p(wp), _p(bp), _p(res), _p(y), _p(mean), _p(rstd), _p(ws),
                                         _p(running_mean) if upd else None, _p(running_var) if upd else None,
@@ -1049,7 +1061,12 @@ class _BatchNormAct(Function):
         npix = n * h * w
         gy = gy.contiguous()
         gpre = torch.empty_like(x)
-        sums = torch.empty((cs, 2), dtype=torch.float64, device=x.device)
+        k = ("bnbwd", npix, cs)
+        nd = _WS_CACHE.get(k)
+        if nd is None:
+            nd = _WS_CACHE[k] = int(_L().cgb_bn_bwd_ws_doubles(npix, cs))
+        sums_buf = torch.empty((nd,), dtype=torch.float64, device=x.device)   # sums[cs][2] + per-chunk partials
+        sums = sums_buf[: 2 * cs].view(cs, 2)
         gw = gb = gx = None
         if batch_stats:
             gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None

@@ -119,9 +119,11 @@ int cgb_conv2d_wgrad(const cgb_conv_desc* d, const void* x, const void* gy, floa
 
 /* ---- normalisation -----------------------------------------------------------------------
  * nn.InstanceNorm2d(affine=False), eps 1e-5, biased variance (climategan/norms.py:151,176;
- * discriminator.py:71-73).  x [n,hw,c] -> mean,rstd [n,c] fp32.  ws: n*c*2 doubles scratch. */
+ * discriminator.py:71-73).  x [n,hw,c] -> mean,rstd [n,c] fp32.  ws: cgb_instnorm_ws_doubles(n,hw,c) doubles scratch. */
 int cgb_instnorm_stats(const void* x, int32_t dtype, int32_t n, int32_t hw, int32_t c, float eps,
                        double* ws, float* mean, float* rstd, void* stream);
+/* scratch the call above needs, in doubles (per-chunk fp32 partial sums; no atomics, deterministic) */
+int64_t cgb_instnorm_ws_doubles(int32_t n, int32_t hw, int32_t c);
 
 /* SPADE de-normalisation + following activation (norms.py:184 then blocks.py:372-373,394):
  *   out = act( (x-mean)*rstd * (1+gamma) + beta ),  gamma = gb[...,0:c], beta = gb[...,c:2c]
@@ -199,7 +201,7 @@ int cgb_make_m_cond(const void* d, const void* s, const void* xr, float* mm, voi
  * cgb_instnorm_stats with n=1, hw=N*H*W.  weight/bias are per-channel fp32 (NULL = 1 / 0), padded to c.
  *   fwd:      y = act((x-mean)*rstd*weight + bias (+ residual))
  *   bwd (1):  gpre = gy*act'(y) (also the gradient of the residual) ; sums[c][0] = sum gpre (= gbias),
- *             sums[c][1] = sum gpre*xhat (= gweight)   (fp64, zeroed by the call)
+ *             sums[c][1] = sum gpre*xhat (= gweight)   (fp64; buffer of cgb_bn_bwd_ws_doubles(npix, c) doubles)
  *   bwd (2):  gx = weight*rstd*(gpre - sums0/M - xhat*sums1/M)
  *   running:  running_mean/var <- (1-momentum)*running + momentum*batch (unbiased variance), as F.batch_norm does. */
 int cgb_bn_apply_fwd(const void* x, const float* mean, const float* rstd, const float* weight, const float* bias,
@@ -207,12 +209,14 @@ int cgb_bn_apply_fwd(const void* x, const float* mean, const float* rstd, const 
                      void* stream);
 int cgb_bn_apply_bwd(const void* x, const float* mean, const float* rstd, const void* y, const void* gy, void* gpre,
                      double* sums, int32_t dtype, int64_t npix, int32_t c, int32_t act, float slope, void* stream);
+/* doubles `sums` must hold for cgb_bn_apply_bwd / cgb_bn_train_bwd: sums[c][2] followed by per-chunk fp32 partials */
+int64_t cgb_bn_bwd_ws_doubles(int64_t npix, int32_t c);
 int cgb_bn_bwd_finalize(const void* x, const float* mean, const float* rstd, const float* weight, const double* sums,
                         const void* gpre, void* gx, int32_t dtype, int64_t npix, int32_t c, void* stream);
 int cgb_bn_update_running(const float* mean, const float* rstd, float* running_mean, float* running_var, int32_t c,
                           int64_t count, float momentum, float eps, void* stream);
-/* The same, one call per direction (three fewer host round trips per BatchNorm): train_fwd = statistics (ws: 2*c doubles
- * scratch) -> running update of the first c_logical channels, num_batches_tracked += 1 (both optional) -> apply;
+/* The same, one call per direction (three fewer host round trips per BatchNorm): train_fwd = statistics (ws: cgb_instnorm_ws_doubles(1,npix,c)
+ * doubles of scratch) -> running update of the first c_logical channels, num_batches_tracked += 1 (both optional) -> apply;
  * train_bwd = part 1 then part 2 (gx NULL: part 1 only). */
 int cgb_bn_train_fwd(const void* x, const float* weight, const float* bias, const void* residual, void* y, float* mean,
                      float* rstd, double* ws, float* running_mean, float* running_var, int64_t* num_batches_tracked,

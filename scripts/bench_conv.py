@@ -31,6 +31,8 @@ CASES = {
     "r2": ("fwd", 8, 128, 128, 80, 80, 3, 1, 1, 1),       # ResNet layer2 conv2
     "r4": ("fwd", 8, 512, 512, 80, 80, 3, 4, 4, 1),       # ResNet layer4 conv2 (dilation 4)
     "d3": ("fwd", 8, 512, 512, 39, 39, 4, 1, 1, 1),       # discriminator 512->512 4x4
+    "sh8": ("fwd", 8, 32, 128, 640, 640, 1, 0, 1, 1),     # SPADE mlp_shared as a K=32 GEMM, painter batch of the full step
+    "gb48_8": ("fwd", 8, 128, 48, 640, 640, 3, 1, 1, 1),  # gamma||beta, painter batch of the full step
 }
 names = sys.argv[1:] or list(CASES)
 reps = int(os.environ.get("REPS", "5"))
