@@ -452,7 +452,7 @@ def main():
     step_tflops = world * B * gflop_per_image * 1e9 / (ms_per_step * 1e-3) / 1e12
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported at N=1 only
         rate, t, cores, sample = cpu_rate(args, 1 if args.workload == "full" else 2, 0 if args.workload == "full" else 1)
         cpu = {"value": rate, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample + f" ({t:.1f} s/step)"}
 
