@@ -34,6 +34,7 @@ import torch  # noqa: E402
 # Algorithmic conv FLOPs per image at 640x640 ([probe] hooks on F.conv2d in the reference):
 PAINTER_STEP_GFLOP = 1551.6   # C1: painter fwd + dgrad + wgrad, minus dgrad into the 3-channel conditioning
 FULL_STEP_GFLOP = 10113.0     # C3: one (r, s, rf) image triple through update_G + update_D (encoder 4x fwd + 2x bwd, ...)
+INFER_GFLOP = 1339.8          # C4: masker forward 816.9 + painter forward 522.9 per image
 
 
 def parse():
@@ -42,9 +43,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="full", choices=["full", "painter"],
+    ap.add_argument("--workload", default="full", choices=["full", "painter", "infer"],
                     help="full = Masker+Painter G+D train step (BASELINE.json metric; SURVEY.md §8d C3, 8 images/domain/GPU); "
-                         "painter = C1 painter-only fwd+bwd (configs[1], 16 images/GPU)")
+                         "painter = C1 painter-only fwd+bwd (configs[1], 16 images/GPU); "
+                         "infer = C4 Trainer.infer_all (masker + painter + flood/wildfire/smog compositing, 16 images/GPU)")
     ap.add_argument("--batch", type=int, default=0, help="images per domain per GPU per step (default: 8 full, 16 painter)")
     ap.add_argument("--size", type=int, default=640)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
@@ -54,6 +56,8 @@ def parse():
     a = ap.parse_args()
     if a.batch <= 0:
         a.batch = 8 if a.workload == "full" else 16
+    if a.workload == "infer":
+        a.no_cpu_baseline = True   # the CPU arm of this workload is the reference's own infer_all, which cannot travel
     if a.cpu_sample_batch <= 0:
         a.cpu_sample_batch = 2 if a.workload == "full" else 1
     return a
@@ -115,7 +119,8 @@ class ClockSampler(threading.Thread):
 
 
 def metric_name(args):
-    return "full_train_step_images_per_sec" if args.workload == "full" else "painter_fwd_bwd_images_per_sec"
+    return {"full": "full_train_step_images_per_sec", "painter": "painter_fwd_bwd_images_per_sec",
+            "infer": "infer_all_images_per_sec"}[args.workload]
 
 
 def workload_config(args):
@@ -128,6 +133,13 @@ def workload_config(args):
             "images_per_sec_convention": "per-domain images/s (reference batch_size convention); x3 for domain-images/s",
             "parallelism": f"dp{args.gpus} (per-image batch split; NCCL all-reduce of the flat G and D gradient buckets)",
             "l2_policy": "working set per step (tens of GB of activations) exceeds the 126 MB L2; no flush needed",
+        }
+    if args.workload == "infer":
+        return {
+            "workload": f"C4 Trainer.infer_all (deeplabv2 masker + SPADE painter inference, flood + wildfire + smog compositing, "
+                        f"uint8 NHWC outputs), batch {args.batch}/GPU, {args.size}x{args.size}",
+            "batch_per_gpu": args.batch, "size": args.size, "parallelism": f"dp{args.gpus} (independent replicas, no collective)",
+            "l2_policy": "activations per batch exceed the 126 MB L2; no flush needed",
         }
     return {
         "workload": f"C1 painter-only SPADE generator fwd+bwd (OmniGenerator.paint + L1 + backward), "
@@ -227,6 +239,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "infer":
+        print(json.dumps({"impl": "reference", "unavailable": "the infer workload's CPU arm is the reference's own Trainer.infer_all, "
+                          "which needs /root/reference (absent on the GPU box); its parity is pinned by tests/golden/infer_all.*"}))
+        return
     steps = max(1, min(args.steps, 1 if args.workload == "full" else 3))
     warmup = 0 if args.workload == "full" else max(1, min(args.warmup, 1))
     rate, t, cores, sample = cpu_rate(args, steps, warmup)
@@ -304,6 +320,32 @@ def build_full(args, dev, rank, world, dtype):
     return step, to_dev, h2d, FULL_STEP_GFLOP
 
 
+def build_infer(args, dev, rank, world, dtype):
+    import random
+
+    from climategan_b200.trainer import Trainer
+    from climategan_b200.utils import full_opts
+
+    B, S = args.batch, args.size
+    torch.manual_seed(0)
+    opts = full_opts(nblocks=(3, 4, 23, 3), size=S, latent=640, n_up=7, ndf=64, n_layers=4, num_d=3)
+    t = Trainer(opts, device=dev, storage_dtype=dtype).setup(inference=True, input_shape=(S, S))
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host = [(torch.rand(B, 3, S, S, generator=gen) * 2 - 1).pin_memory()]
+    random.seed(0)
+    state = {"numpy": False}
+
+    def step(x):
+        out = t.infer_all(x, numpy=state["numpy"])
+        return out["flood"]
+
+    def to_dev(nb):
+        state["numpy"] = nb          # the e2e leg (non_blocking H2D from pinned memory) also returns uint8 NHWC arrays on the host
+        return [host[0].to(dev, non_blocking=nb)]
+
+    return step, to_dev, int(host[0].numel() * 4), INFER_GFLOP
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -330,7 +372,8 @@ def main():
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     B = args.batch
 
-    step, to_dev, h2d_bytes, gflop_per_image = (build_full if args.workload == "full" else build_painter)(args, dev, rank, world, dtype)
+    builder = {"full": build_full, "painter": build_painter, "infer": build_infer}[args.workload]
+    step, to_dev, h2d_bytes, gflop_per_image = builder(args, dev, rank, world, dtype)
     resident = to_dev(False)
 
     def barrier():
@@ -384,12 +427,15 @@ def main():
     e2e = None
     if not args.no_e2e:
         def e2e_step():
-            loss = step(*to_dev(True))   # H2D of this step's inputs from pinned host memory
-            return float(loss.item())    # D2H read of the step result
+            res = step(*to_dev(True))    # H2D of this step's inputs from pinned host memory
+            if isinstance(res, torch.Tensor):
+                return float(res.sum().item()) if res.numel() > 1 else float(res.item())   # D2H read of the step result
+            return int(res[0, 0, 0, 0])  # infer: the uint8 NHWC events were already copied to the host by infer_all
 
         e2e_step()
         e2e_ms = timed(e2e_step, args.steps) / args.steps
-        e2e = {"value": world * B / (e2e_ms / 1e3), "unit": "img/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+        d2h = 4 if args.workload != "infer" else 3 * B * args.size * args.size * 3   # three uint8 NHWC events per image
+        e2e = {"value": world * B / (e2e_ms / 1e3), "unit": "img/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
                "ms_per_step": e2e_ms}
 
     if rank != 0:

@@ -137,6 +137,8 @@ SIGNATURES = {
     "cgb_gauss_blur": ([_P, _P, _P, _I, _I, _I, _I, _F, _P], C.c_int),
     "cgb_fire_paste": ([_P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _F, _P], C.c_int),
     "cgb_smog": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _F, _F, _F, _F, _P], C.c_int),
+    "cgb_perlin_noise": ([_P, _P, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_cloudy_mix": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P], C.c_int),
     "cgb_to_uint8_nhwc": ([_P, _P, _P, _I, _I, _P], C.c_int),
     "cgb_mask_to_uint8": ([_P, _P, _F, _L, _P], C.c_int),
     "cgb_resize_nearest_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),

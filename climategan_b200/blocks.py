@@ -85,15 +85,21 @@ class Conv2dBlock(nn.Module):
         import torch
 
         with torch.no_grad():
-            w, b = conv_weight_bias(self.conv)  # runs the spectral-norm power iteration, as the reference does in eval
-            if self.norm is not None:
-                scale = self.norm.weight / torch.sqrt(self.norm.running_var + self.norm.eps)
-                bb = self.norm.bias - self.norm.running_mean * scale
-                if b is not None:
-                    bb = bb + b * scale
-                w, b = w * scale.view(-1, 1, 1, 1), bb
-            wp = ops.pack_weight(w, x.dtype, cis=x.shape[-1])
-            return ops.conv2d_infer(x, wp, ops.pad_bias(b, wp.shape[0]), residual, k=self.kernel_size, stride=self.stride,
+            if self.norm is not None and not isinstance(self.conv, SpectralNorm):
+                from .deeplab.resnetmulti_v2 import fold_bn
+
+                wp, bp = fold_bn(self.conv, self.norm, x.dtype, cis=x.shape[-1])   # cached folded packing
+            else:
+                w, b = conv_weight_bias(self.conv)  # runs the spectral-norm power iteration, as the reference does in eval
+                if self.norm is not None:
+                    scale = self.norm.weight / torch.sqrt(self.norm.running_var + self.norm.eps)
+                    bb = self.norm.bias - self.norm.running_mean * scale
+                    if b is not None:
+                        bb = bb + b * scale
+                    w, b = w * scale.view(-1, 1, 1, 1), bb
+                wp = ops.pack_weight_cached(w, x.dtype, cis=x.shape[-1])
+                bp = ops.pad_bias(b, wp.shape[0])
+            return ops.conv2d_infer(x, wp, bp, residual, k=self.kernel_size, stride=self.stride,
                                     dil=self.dilation, pad=self.padding, pad_mode=self.pad_mode, act=self.act,
                                     slope=self.slope)
 

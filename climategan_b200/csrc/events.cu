@@ -264,6 +264,70 @@ mask_to_uint8_kernel(const float* __restrict__ m, uint8_t* __restrict__ out, flo
     out[i] = m[i] > bin_value ? 255 : 0;
 }
 
+// rand_perlin_2d (tutils.py:648-686): gradients from (res0+1) x (res1+1) random angles, quintic fade, sqrt(2) scale.
+// grid coordinate of pixel i along an axis = fmod(float(i * (res / size)), 1) exactly as torch.arange(0, res, res/size) % 1
+// (ATen evaluates start + i*step in double and rounds to float); cell = i / (size / res) (repeat_interleave of the gradients).
+__global__ void __launch_bounds__(256)
+perlin_kernel(const float* __restrict__ angles, float* __restrict__ out, int h, int w, int res0, int res1) {
+  const double step0 = (double)res0 / (double)h, step1 = (double)res1 / (double)w;
+  const int d0 = h / res0, d1 = w / res1;
+  const long long total = (long long)h * w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(i % w), py = (int)(i / w);
+    const float gy = fmodf((float)((double)py * step0), 1.f), gx = fmodf((float)((double)px * step1), 1.f);
+    const int cy = min(py / d0, res0 - 1), cx = min(px / d1, res1 - 1);
+    float n[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const float ang = angles[(cy + a) * (res1 + 1) + (cx + b)];
+        n[a][b] = (gy - (float)a) * cosf(ang) + (gx - (float)b) * sinf(ang);
+      }
+    const float t0 = gy * gy * gy * (gy * (gy * 6.f - 15.f) + 10.f);
+    const float t1 = gx * gx * gx * (gx * (gx * 6.f - 15.f) + 10.f);
+    const float l0 = n[0][0] + t0 * (n[1][0] - n[0][0]);   // lerp(n00, n10, t[...,0])
+    const float l1 = n[0][1] + t0 * (n[1][1] - n[0][1]);   // lerp(n01, n11, t[...,0])
+    out[i] = 1.4142135623730951f * (l0 + t1 * (l1 - l0));
+  }
+}
+
+// paint_cloudy's conditioning image (generator.py:318-325, tutils.mix_noise :689-694): sky = argmax(bilinear(s)) == sky_idx ;
+// y = sky * (weight * (noise - min noise) + (1 - weight) * x) + (1 - sky) * x
+__global__ void __launch_bounds__(256)
+cloudy_mix_kernel(const float* __restrict__ x, const float* __restrict__ seg, const float* __restrict__ noise,
+                  const float* __restrict__ mm_noise, float* __restrict__ out, int h, int w, int c, int hs, int ws, int sky_idx,
+                  float weight) {
+  const int im = blockIdx.y;
+  const int hw = h * w;
+  const float sh = (float)hs / (float)h, sw = (float)ws / (float)w;
+  const float nmin = mm_noise[0];
+  const float* sp = seg + (long long)im * c * hs * ws;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+    const int px = i % w, py = i / w;
+    const float fy = fmaxf(sh * (py + 0.5f) - 0.5f, 0.f), fx = fmaxf(sw * (px + 0.5f) - 0.5f, 0.f);   // align_corners=False
+    const int y0 = min((int)fy, hs - 1), x0 = min((int)fx, ws - 1);
+    const int y1 = min(y0 + 1, hs - 1), x1 = min(x0 + 1, ws - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    int best = 0;
+    float bv = -3.4e38f;
+    for (int k = 0; k < c; ++k) {
+      const float* q = sp + (long long)k * hs * ws;
+      const float v = (1.f - ly) * ((1.f - lx) * q[y0 * ws + x0] + lx * q[y0 * ws + x1]) +
+                      ly * ((1.f - lx) * q[y1 * ws + x0] + lx * q[y1 * ws + x1]);
+      if (v > bv) { bv = v; best = k; }
+    }
+    const float sky = best == sky_idx ? 1.f : 0.f;
+    const float nz = noise[i] - nmin;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const long long o = ((long long)im * 3 + ch) * hw + i;
+      const float xv = x[o];
+      out[o] = sky * (weight * nz + (1.f - weight) * xv) + (1.f - sky) * xv;
+    }
+  }
+}
+
 }  // namespace cgb
 
 using namespace cgb;
@@ -378,4 +442,22 @@ extern "C" int cgb_mask_to_uint8(const float* m, uint8_t* out, float bin_value, 
   CGB_REQUIRE(m && out && count > 0, "mask_to_uint8: bad arguments");
   mask_to_uint8_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(m, out, bin_value, count);
   return after_launch("mask_to_uint8");
+}
+
+extern "C" int cgb_perlin_noise(const float* angles, float* out, int32_t h, int32_t w, int32_t res0, int32_t res1, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(angles && out && h > 0 && w > 0 && res0 > 0 && res1 > 0 && h >= res0 && w >= res1, "perlin_noise: bad arguments");
+  perlin_kernel<<<grid_for((long long)h * w), 256, 0, (cudaStream_t)stream>>>(angles, out, h, w, res0, res1);
+  return after_launch("perlin_noise");
+}
+
+extern "C" int cgb_cloudy_mix(const float* x, const float* seg, const float* noise, const float* mm_noise, float* out, int32_t n,
+                              int32_t h, int32_t w, int32_t c, int32_t hs, int32_t ws, int32_t sky_idx, float weight,
+                              void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && seg && noise && mm_noise && out && n > 0 && c > 0, "cloudy_mix: bad arguments");
+  int gx = grid_for((long long)h * w);
+  if (gx > 148 * 2) gx = 148 * 2;
+  cloudy_mix_kernel<<<dim3(gx, n), 256, 0, (cudaStream_t)stream>>>(x, seg, noise, mm_noise, out, h, w, c, hs, ws, sky_idx, weight);
+  return after_launch("cloudy_mix");
 }

@@ -12,14 +12,20 @@ affine_par = True
 
 
 def fold_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d, dtype, cis=None):
-    """Packed weights/bias of conv followed by eval-mode BatchNorm: w' = w*g/sqrt(var+eps), b' = beta + (b-mean)*g/sqrt(..)."""
-    scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
-    w = conv.weight.detach() * scale.view(-1, 1, 1, 1)
-    b = bn.bias.detach() - bn.running_mean * scale
-    if conv.bias is not None:
-        b = b + conv.bias.detach() * scale
-    wp = ops.pack_weight(w, dtype, cis=cis)
-    return wp, ops.pad_bias(b, wp.shape[0])
+    """Packed weights/bias of conv followed by eval-mode BatchNorm: w' = w*g/sqrt(var+eps), b' = beta + (b-mean)*g/sqrt(..)
+    — what ``climategan/bn_fusion.py::fuse`` (:6-49) computes.  The folded packing is cached until any of the six tensors
+    changes (ops.cached_pack), so repeated inference forwards do not re-fold."""
+    def build():
+        scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+        w = conv.weight.detach() * scale.view(-1, 1, 1, 1)
+        b = bn.bias.detach() - bn.running_mean * scale
+        if conv.bias is not None:
+            b = b + conv.bias.detach() * scale
+        wp = ops.pack_weight(w, dtype, cis=cis)
+        return wp, ops.pad_bias(b, wp.shape[0])
+
+    deps = [conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var] + ([conv.bias] if conv.bias is not None else [])
+    return ops.cached_pack(deps, ("fold_bn", dtype, cis), build, uses_running_stats=True)
 
 
 class Bottleneck(nn.Module):

@@ -102,3 +102,22 @@ def mask_to_uint8(mask, bin_value):
     out = torch.empty(m.shape, dtype=torch.uint8, device=m.device)
     check(_L().cgb_mask_to_uint8(_p(m), _p(out), float(bin_value), m.numel(), _st()), "mask_to_uint8")
     return out
+
+
+def cloudy_input(x, s, sky_idx=9, res=(8, 8), weight=0.8):
+    """The intermediary cloudy image of OmniGenerator.paint_cloudy (generator.py:318-325): Perlin noise (tutils.py:648-694)
+    mixed into the sky region of x.  The (res+1)^2 gradient angles are drawn with ``torch.rand`` on the CPU generator — the
+    same draw the reference makes — and evaluated per pixel on the device."""
+    import math
+
+    x, s = _img(x), _img(s)
+    n, c3, h, w = x.shape
+    assert c3 == 3
+    angles = (2 * math.pi * torch.rand(res[0] + 1, res[1] + 1)).to(x.device)
+    noise = torch.empty((1, h, w), dtype=torch.float32, device=x.device)
+    check(_L().cgb_perlin_noise(_p(angles), _p(noise), h, w, res[0], res[1], _st()), "perlin_noise")
+    mm = minmax_per_sample(noise)
+    out = torch.empty_like(x)
+    check(_L().cgb_cloudy_mix(_p(x), _p(s), _p(noise), _p(mm), _p(out), n, h, w, s.shape[1], s.shape[2], s.shape[3], sky_idx,
+                              float(weight), _st()), "cloudy_mix")
+    return out

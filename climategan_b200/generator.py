@@ -63,6 +63,15 @@ class OmniGenerator(nn.Module):
             return ops.paste(x, m.to(x.dtype), fake)
         return fake
 
+    def paint_cloudy(self, m, x, s, sky_idx=9, res=(8, 8), weight=0.8):
+        """generator.py:299-328: paint through an intermediary image whose sky (argmax of the upsampled seg logits == sky_idx)
+        is replaced by Perlin noise, then paste the original content back."""
+        from . import events
+
+        noised_x = events.cloudy_input(x, s, sky_idx, res, weight)
+        fake = self.paint(m, noised_x, no_paste=True)
+        return ops.paste(x, m.to(x.dtype), fake)
+
     # ------------------------------------------------------------------ masker
     # z and z_depth are NHWC storage tensors (they only ever travel between these methods); d, s, m are NCHW fp32 like the
     # reference's.  Train mode records the autograd tape (BatchNorm on batch statistics, dropout active); eval mode runs the

@@ -91,15 +91,18 @@ def pack_weight_cached(w: torch.Tensor, dtype: torch.dtype, cis: Optional[int] =
     return wp
 
 
-def cached_pack(params, tag, builder):
+_BEPOCH = [0]   # bumped by every train-mode BatchNorm forward: running statistics are updated through raw kernels too
+
+
+def cached_pack(params, tag, builder, uses_running_stats=False):
     """Generic form of :func:`pack_weight_cached` for packings built from several nn.Parameters (SPADE's fused gamma||beta
     weights): ``builder()`` runs only when one of ``params`` changed since the cached copy was made."""
-    if not all(isinstance(p, torch.nn.Parameter) for p in params) or "wcache" in _DBG:
-        return builder()
+    if "wcache" in _DBG or not all(isinstance(p, torch.Tensor) and p.is_leaf for p in params):
+        return builder()   # (leaf tensors only: parameters and buffers, whose identity persists between calls)
     import weakref
 
     key = (tag,) + tuple(id(p) for p in params)
-    sig = (_WEPOCH[0],) + tuple((p._version, p.data_ptr()) for p in params)
+    sig = (_WEPOCH[0], _BEPOCH[0] if uses_running_stats else 0) + tuple((p._version, p.data_ptr()) for p in params)
     ent = _WCACHE.get(key)
     if ent is not None and ent[0] == sig and all(r() is p for r, p in zip(ent[1], params)):
         return ent[2]
@@ -1038,6 +1041,8 @@ class _BatchNormAct(Function):
         if batch_stats:
             ws = torch.empty((_stats_ws(1, npix, cs),), dtype=torch.float64, device=dev)
             upd = running_mean is not None and training
+            if upd:
+                _BEPOCH[0] += 1   # folded eval-mode packings (fold_bn) built from the running statistics are now stale
             check(_L().cgb_bn_train_fwd(_p(x), _p(wp), _p(bp), _p(res), _p(y), _p(mean), _p(rstd), _p(ws),
                                         _p(running_mean) if upd else None, _p(running_var) if upd else None,
                                         _p(nbt) if upd else None, _DT[x.dtype], npix, cs, c, float(momentum), float(eps), act,

@@ -489,9 +489,10 @@ class Trainer:
             m = self.G.mask(x=None, z=z, z_depth=z_depth)
         if bin_value >= 0:
             m = (m > bin_value).to(m.dtype)
-        if cloudy:
-            raise NotImplementedError("cloudy=True (paint_cloudy: Perlin-noise sky, generator.py:299-328) is not built")
         with torch.no_grad():
+            if cloudy:
+                assert s is not None
+                return self.G.paint_cloudy(m, x, s)
             return self.G.paint(m, x)
 
     def compute_smog(self, x, z=None, d=None, s=None, use_sky_seg=False):

@@ -296,6 +296,12 @@ int cgb_fire_paste(const float* img, const float* sky, float* out, int32_t n, in
                    float transparency, float brightness, void* stream);
 int cgb_smog(const float* x, const float* mmx, const float* d, const float* mmd, float* out, int32_t n, int32_t h, int32_t w,
              int32_t hd, int32_t wd, float airlight, float beta, float alpha, float yr, float yg, float yb, void* stream);
+/* paint_cloudy (generator.py:299-328): perlin_noise = rand_perlin_2d (tutils.py:648-686) from (res0+1)x(res1+1) random angles
+ * drawn by the caller; cloudy_mix = sky mask from argmax of the bilinearly upsampled seg logits == sky_idx, then mix_noise
+ * (tutils.py:689-694) with mm_noise = per-sample (min,max) of the noise plane. */
+int cgb_perlin_noise(const float* angles, float* out, int32_t h, int32_t w, int32_t res0, int32_t res1, void* stream);
+int cgb_cloudy_mix(const float* x, const float* seg, const float* noise, const float* mm_noise, float* out, int32_t n, int32_t h,
+                   int32_t w, int32_t c, int32_t hs, int32_t ws, int32_t sky_idx, float weight, void* stream);
 int cgb_to_uint8_nhwc(const float* x, const float* mm, uint8_t* out, int32_t n, int32_t hw, void* stream);
 int cgb_mask_to_uint8(const float* m, uint8_t* out, float bin_value, int64_t count, void* stream);
 

@@ -337,8 +337,12 @@ def run_infer_all_case(name="infer_all", batch=2, size=320):
     out = t.infer_all(x.clone(), numpy=True, bin_value=0.5, return_masks=True)
     random.seed(0)
     raw = t.infer_all(x.clone(), numpy=False)
+    torch.manual_seed(0)   # the Perlin angles of paint_cloudy come from torch.rand on the CPU generator (tutils.py:660)
+    random.seed(0)
+    cloudy = t.infer_all(x.clone(), numpy=False, cloudy=True)   # (ignore_event would hit an UnboundLocalError in the reference)
     arrays = {k: v[:, ::2, ::2].copy() for k, v in out.items() if k != "mask"}
     arrays["mask"] = out["mask"][:, :, ::2, ::2].copy()
+    arrays["raw_flood_cloudy"] = cloudy["flood"].detach().numpy()[:, :, ::4, ::4].astype(np.float32)
     for k, v in raw.items():
         arrays["raw_" + k] = v.detach().numpy()[:, :, ::4, ::4].astype(np.float32)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)

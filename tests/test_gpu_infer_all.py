@@ -47,6 +47,14 @@ def test_infer_all_fp32_matches_reference(cuda):
     for k in ("flood", "wildfire", "smog"):
         got = raw[k][:, :, ::4, ::4].cpu()
         assert rel_max(got, torch.from_numpy(g["raw_" + k])) < 2e-3, (k, rel_max(got, torch.from_numpy(g["raw_" + k])))
+    # third call, cloudy=True: the flood is painted through an intermediary image whose sky is Perlin noise; the noise's
+    # gradient angles come from torch.rand on the CPU generator in both implementations (tutils.py:660)
+    torch.manual_seed(0)
+    random.seed(meta["seeds"]["random"])
+    cl = t.infer_all(x.clone(), numpy=False, cloudy=True)
+    got = cl["flood"][:, :, ::4, ::4].cpu()
+    assert rel_max(got, torch.from_numpy(g["raw_flood_cloudy"])) < 3e-3, rel_max(got, torch.from_numpy(g["raw_flood_cloudy"]))
+    assert rel_max(got, torch.from_numpy(g["raw_flood"])) > 1e-2   # and it does differ from the non-cloudy flood
 
 
 def test_infer_all_bf16_close_to_reference(cuda):
