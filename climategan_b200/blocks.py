@@ -99,8 +99,14 @@ class Conv2dBlock(nn.Module):
                     w, b = w * scale.view(-1, 1, 1, 1), bb
                 wp = ops.pack_weight_cached(w, x.dtype, cis=x.shape[-1])
                 bp = ops.pad_bias(b, wp.shape[0])
+            pad, pad_mode = self.padding, self.pad_mode
+            if pad_mode == _lib.PAD_REFLECT and pad > 0:
+                # explicit reflect-padded copy + pad-0 conv: keeps the conv on the tcgen05 engine (the in-loader reflect
+                # padding only exists in the SIMT engine: 512->512 3x3 @80x80 took 13.7 ms there)
+                x = ops.reflect_pad(x, pad)
+                pad, pad_mode = 0, _lib.PAD_ZERO
             return ops.conv2d_infer(x, wp, bp, residual, k=self.kernel_size, stride=self.stride,
-                                    dil=self.dilation, pad=self.padding, pad_mode=self.pad_mode, act=self.act,
+                                    dil=self.dilation, pad=pad, pad_mode=pad_mode, act=self.act,
                                     slope=self.slope)
 
 

@@ -461,15 +461,31 @@ class Trainer:
                 smog = self.compute_smog(x, d=depth, s=segmentation)
             if "flood" not in ignore_event:
                 flood = self.compute_flood(x, m=mask, s=segmentation, cloudy=cloudy, bin_value=bin_value)
+            m8 = events.mask_to_uint8(mask, bin_value) if return_masks else None
             if numpy:
-                # normalize -> NHWC -> uint8 on the device; one pinned D2H copy per event
-                conv = lambda t: None if t is None else events.to_uint8_nhwc(t).cpu().numpy()  # noqa: E731
-                flood, smog, wildfire = conv(flood), conv(smog), conv(wildfire)
+                # normalize -> NHWC -> uint8 on the device, then asynchronous D2H copies into pinned staging buffers and ONE
+                # synchronisation for all events (the reference does .cpu() per event, each a blocking pageable copy)
+                dev8 = {"flood": flood, "smog": smog, "wildfire": wildfire}
+                dev8 = {k: events.to_uint8_nhwc(v) for k, v in dev8.items() if v is not None}
+                if m8 is not None:
+                    dev8["mask"] = m8
+                host8 = {k: self._pinned(k, v).copy_(v, non_blocking=True) for k, v in dev8.items()}
+                torch.cuda.current_stream().synchronize()
+                arr = {k: v.numpy().copy() for k, v in host8.items()}
+                flood, smog, wildfire = arr.get("flood"), arr.get("smog"), arr.get("wildfire")
+                m8 = arr.get("mask")
             output_data = {"flood": flood, "wildfire": wildfire, "smog": smog}
             if return_masks:
-                m8 = events.mask_to_uint8(mask, bin_value)
-                output_data["mask"] = m8.cpu().numpy().astype(np.uint8)
+                output_data["mask"] = m8 if numpy else m8.cpu().numpy().astype(np.uint8)
         return output_data
+
+    def _pinned(self, key, like):
+        """Pinned host staging buffer of ``like``'s shape / dtype, cached per output (cudaHostAlloc is expensive)."""
+        cache = self.__dict__.setdefault("_pinned_cache", {})
+        buf = cache.get(key)
+        if buf is None or buf.shape != like.shape or buf.dtype != like.dtype:
+            buf = cache[key] = torch.empty(like.shape, dtype=like.dtype, pin_memory=True)
+        return buf
 
     def compute_fire(self, x, seg_preds=None, z=None, z_depth=None):
         """trainer.py:1824-1841."""
