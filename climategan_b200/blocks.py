@@ -61,9 +61,11 @@ class Conv2dBlock(nn.Module):
             raise NotImplementedError("Unsupported activation: {}".format(activation))
         self.act, self.slope = _ACTS[activation]
         self.activation = None if activation == "none" else activation
-        conv = nn.Conv2d(input_dim, output_dim, kernel_size, stride, dilation=dilation,
-                         bias=self.use_bias if norm != "batch" else False)
-        self.conv = SpectralNorm(conv) if (norm == "spectral" or use_spectral_norm) else conv
+        if norm == "spectral" or use_spectral_norm:   # blocks.py:117-127: the spectral branch keeps the bias even with BatchNorm
+            self.conv = SpectralNorm(nn.Conv2d(input_dim, output_dim, kernel_size, stride, dilation=dilation, bias=self.use_bias))
+        else:
+            self.conv = nn.Conv2d(input_dim, output_dim, kernel_size, stride, dilation=dilation,
+                                  bias=self.use_bias if norm != "batch" else False)
 
     def forward(self, x, residual=None):
         """Training-capable forward (autograd tape): explicit reflect pad -> conv (tcgen05, pad 0) -> [train-mode
@@ -154,7 +156,9 @@ class SPADEResnetBlock(nn.Module):
             sh = self.norm_0.mlp_shared[0]
             if sh.kernel_size[0] ** 2 * sh.in_channels <= 64:
                 seg_col = ops.im2col(seg, sh.in_channels, sh.kernel_size[0], sh.kernel_size[0] // 2)
-        stats = ops.instnorm_stats(x)
+        # norm_0 / norm_s see the same x: with instance norm they share one statistics pass; the batch flavour (masker) has
+        # its own running statistics per SPADE layer
+        stats = ops.instnorm_stats(x) if self.param_free_norm == "instance" else None
         if self.learned_shortcut:
             # reference order (blocks.py:370,389): shortcut first -> conv_s's power iteration runs first
             w_s, _ = conv_weight_bias(self.conv_s)

@@ -1,13 +1,19 @@
 """Flood-mask decoders (``climategan/masker.py``): MaskBaseDecoder (:25-56) = BaseDecoder (``blocks.py:206-318``) with
-the masker options.  The SPADE mask decoder (:59-231) is not built."""
+the masker options, and MaskSpadeDecoder (:59-231; the paper / release configuration) for the deeplabv2 encoder: spectral-norm +
+BatchNorm ``fc_conv``, ``num_layers`` x [SPADEResnetBlock conditioned on make_m_cond's 15-channel tensor, nearest x2], spectral
+``mask_conv``.  The SPADE decoder is built for inference (its param-free norm is a BatchNorm read from running statistics)."""
 from __future__ import annotations
 
-from .blocks import BaseDecoder
+import torch
+import torch.nn as nn
+
+from . import ops
+from .blocks import BaseDecoder, Conv2dBlock, InterpolateNearest2d, SPADEResnetBlock
 
 
 def create_mask_decoder(opts, no_init=False, verbose=0):
     if opts.gen.m.use_spade:
-        raise NotImplementedError("MaskSpadeDecoder (gen.m.use_spade) is not built")
+        return MaskSpadeDecoder(opts)
     return MaskBaseDecoder(opts)
 
 
@@ -20,3 +26,40 @@ class MaskBaseDecoder(BaseDecoder):
                          proj_dim=opts.gen.m.proj_dim, output_dim=opts.gen.m.output_dim, norm=opts.gen.m.norm,
                          activ=opts.gen.m.activ, pad_type=opts.gen.m.pad_type, output_activ="none",
                          low_level_feats_dim=-1, use_dada=use_dada)
+
+
+class MaskSpadeDecoder(nn.Module):
+    def __init__(self, opts):
+        super().__init__()
+        self.opts = opts
+        sp = opts.gen.m.spade
+        latent_dim, cond_nc = sp.latent_dim, sp.cond_nc
+        spade_activation = "lrelu" if sp.activations.all_lrelu else None
+        self.num_layers = sp.num_layers
+        self.z_nc = latent_dim
+        if opts.gen.encoder.architecture != "deeplabv2":
+            raise NotImplementedError("MaskSpadeDecoder is built for the deeplabv2 encoder only (no low-level-feature branch)")
+        self.input_dim = 2048
+        self.fc_conv = Conv2dBlock(self.input_dim, self.z_nc, 3, padding=1, activation="lrelu", pad_type="reflect",
+                                   norm="spectral_batch")
+        self.spade_blocks = nn.Sequential(*[
+            SPADEResnetBlock(int(self.z_nc / (2 ** i)), int(self.z_nc / (2 ** (i + 1))), cond_nc, sp.spade_use_spectral_norm,
+                             sp.spade_param_free_norm, 3, spade_activation) for i in range(self.num_layers)])
+        self.final_nc = int(self.z_nc / (2 ** self.num_layers))
+        self.mask_conv = Conv2dBlock(self.final_nc, 1, 3, padding=1, activation="none", pad_type="reflect", norm="spectral")
+        self.upsample = InterpolateNearest2d(scale_factor=2)
+
+    def forward_storage(self, z, cond, z_depth=None):
+        """masker.py:212-231.  z: storage [N,h,w,2048]; cond: NCHW fp32 conditioning from ``OmniGenerator.make_m_cond``."""
+        if self.training:
+            raise NotImplementedError("MaskSpadeDecoder is built for inference (eval mode) only")
+        if cond is None:
+            raise ValueError("MaskSpadeDecoder needs the conditioning tensor (OmniGenerator.make_m_cond)")
+        with torch.no_grad():
+            y = self.fc_conv.forward_infer(z)
+            seg = ops.to_storage(cond, z.dtype)
+            for blk in self.spade_blocks:
+                seg_r = seg if seg.shape[1:3] == y.shape[1:3] else ops.resize_nearest(seg, y.shape[1], y.shape[2])
+                y = blk(y, seg_r)
+                y = self.upsample(y)
+            return self.mask_conv.forward_infer(y)

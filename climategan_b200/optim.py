@@ -104,6 +104,28 @@ class ExtraAdam(Optimizer):
         return loss
 
 
+    # -- checkpointing ----------------------------------------------------------------------------------
+    def state_dict(self):
+        """Flat moments / look-ahead copy per parameter group.  (Not interchangeable with the reference optimiser's
+        per-parameter state; the model state_dicts are.)"""
+        if self._flat is None:
+            self._flatten()
+        return {"steps": self._steps, "have_copy": self._have_copy,
+                "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],
+                "flat": [None if f is None else {"m": f["m"].clone(), "v": f["v"].clone(), "c": f["c"].clone()} for f in self._flat]}
+
+    def load_state_dict(self, state):
+        if self._flat is None:
+            self._flatten()
+        self._steps, self._have_copy = int(state["steps"]), bool(state["have_copy"])
+        for g, sg in zip(self.param_groups, state["param_groups"]):
+            g.update(sg)
+        for f, sf in zip(self._flat, state["flat"]):
+            if f is not None and sf is not None:
+                for k in ("m", "v", "c"):
+                    f[k].copy_(sf[k])
+
+
 def get_scheduler(optimizer, hyperparameters, iterations=-1):
     """optim.py:10-51."""
     policy = hyperparameters.get("lr_policy")

@@ -523,6 +523,71 @@ class Trainer:
         """Mask then paint (the flood event without the other two)."""
         return self.compute_flood(x)
 
+    # ---------------------------------------------------------------- checkpoints (trainer.py:337-412, 470-600)
+    def save(self):
+        """``{output_path}/checkpoints/latest_ckpt.pth`` with the reference's keys: G, g_opt, D, d_opt, epoch, step."""
+        from pathlib import Path
+
+        save_dir = Path(self.opts.output_path) / "checkpoints"
+        save_dir.mkdir(parents=True, exist_ok=True)
+        d = {"epoch": getattr(self.logger, "epoch", 0), "step": self.logger.global_step, "G": self.G.state_dict()}
+        if self.g_opt is not None:
+            d["g_opt"] = self.g_opt.state_dict()
+        if self.D is not None and sum(p.numel() for p in self.D.parameters()) > 0:
+            d["D"] = self.D.state_dict()
+            if self.d_opt is not None:
+                d["d_opt"] = self.d_opt.state_dict()
+        torch.save(d, save_dir / "latest_ckpt.pth")
+        return save_dir / "latest_ckpt.pth"
+
+    def resume(self, inference=False, checkpoint_path=None):
+        """Load ``checkpoints/latest_ckpt.pth`` (a reference checkpoint's G / D state_dicts load as they are: same keys)."""
+        from pathlib import Path
+
+        path = Path(checkpoint_path) if checkpoint_path else Path(self.opts.output_path) / "checkpoints" / "latest_ckpt.pth"
+        ckpt = torch.load(path, map_location=self.device)
+        if inference:
+            bad = self.G.load_state_dict(ckpt["G"], strict=False)
+            if bad.missing_keys:
+                print("WARNING: Missing keys in self.G.load_state_dict, keeping inits", bad.missing_keys)
+            if bad.unexpected_keys:
+                print("WARNING: Ignoring Unexpected keys in self.G.load_state_dict", bad.unexpected_keys)
+            return self
+        self.G.load_state_dict(ckpt["G"])
+        if "D" in ckpt and self.D is not None:
+            self.D.load_state_dict(ckpt["D"])
+        for opt, key in ((self.g_opt, "g_opt"), (self.d_opt, "d_opt")):
+            if opt is not None and key in ckpt and isinstance(ckpt[key], dict) and "flat" in ckpt[key]:
+                opt.load_state_dict(ckpt[key])
+        self.logger.global_step = int(ckpt.get("step", 0))
+        self.logger.epoch = int(ckpt.get("epoch", 0))
+        ops.invalidate_weight_cache()
+        return self
+
+    @classmethod
+    def resume_from_path(cls, path, overrides={}, setup=True, inference=False, new_exp=False, device=None, verbose=1,
+                         storage_dtype=torch.bfloat16, input_shape=(640, 640)):
+        """trainer.py:337-396: ``path`` holds ``opts.yaml`` and ``checkpoints/latest_ckpt.pth`` (comet re-attachment is out of
+        scope)."""
+        from pathlib import Path
+
+        import yaml
+
+        p = Path(path).expanduser().resolve()
+        assert p.exists() and (p / "checkpoints").is_dir(), f"{p} must contain checkpoints/"
+        cands = sorted(p.glob("opts*.yaml"))
+        assert cands, f"no opts*.yaml in {p}"
+        with open(cands[-1]) as f:
+            opts = Dict(yaml.safe_load(f))
+        opts.update(overrides or {})
+        opts.output_path = str(p)
+        opts.train.resume = True
+        t = cls(opts, device=device, verbose=verbose, storage_dtype=storage_dtype)
+        if setup:
+            t.setup(inference=inference, input_shape=input_shape)
+            t.resume(inference=inference)
+        return t
+
     def losses_to_host(self):
         """One sync for all logged scalars (the reference calls .item() ~10x per step)."""
         def conv(d):

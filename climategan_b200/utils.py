@@ -52,7 +52,14 @@ class Dict(dict):
                 self[k] = self._wrap(v)
 
     def to_dict(self):
-        return {k: (v.to_dict() if isinstance(v, Dict) else v) for k, v in self.items()}
+        def conv(v):
+            if isinstance(v, Dict):
+                return v.to_dict()
+            if isinstance(v, (list, tuple)):
+                return [conv(i) for i in v]
+            return v
+
+        return {k: conv(v) for k, v in self.items()}
 
 
 class _Pending(Dict):

@@ -153,3 +153,50 @@ def decode(sd, x, d_target, s_target, sn=None):
     s = seg_decoder(sd, z, z_depth, s_target)
     logits = mask_decoder(sd, sn, z)
     return {"z": z, "z_depth": z_depth, "d": d, "s": s, "m_logits": logits, "m": torch.sigmoid(logits)}
+
+
+# ---- MaskSpadeDecoder (masker.py:59-231), eval mode: norms.SPADE with a BatchNorm(affine=False) param-free norm ------------
+def spade_batch(sd, p, x, seg):
+    """norms.py:174-186 with param_free_norm = nn.BatchNorm2d(affine=False) read from running statistics (eval)."""
+    normalized = F.batch_norm(x, sd[p + ".param_free_norm.running_mean"], sd[p + ".param_free_norm.running_var"], None, None,
+                              False, 0.0, 1e-5)
+    seg = F.interpolate(seg, size=x.shape[2:], mode="nearest")
+    actv = F.relu(F.conv2d(seg, sd[p + ".mlp_shared.0.weight"], sd[p + ".mlp_shared.0.bias"], padding=1))
+    gamma = F.conv2d(actv, sd[p + ".mlp_gamma.weight"], sd[p + ".mlp_gamma.bias"], padding=1)
+    beta = F.conv2d(actv, sd[p + ".mlp_beta.weight"], sd[p + ".mlp_beta.bias"], padding=1)
+    return normalized * (1 + gamma) + beta
+
+
+def spade_resblock_batch(sd, sn, p, x, seg):
+    """blocks.py:369-392 with spectral-norm convs and last_activation lrelu; shortcut first (power-iteration order)."""
+    if p + ".conv_s.module.weight_bar" in sd:
+        x_s = F.conv2d(spade_batch(sd, p + ".norm_s", x, seg), sn.weight(p + ".conv_s.module"))
+    else:
+        x_s = x
+    dx = F.conv2d(F.leaky_relu(spade_batch(sd, p + ".norm_0", x, seg), 0.2), sn.weight(p + ".conv_0.module"),
+                  sd[p + ".conv_0.module.bias"], padding=1)
+    dx = F.conv2d(F.leaky_relu(spade_batch(sd, p + ".norm_1", dx, seg), 0.2), sn.weight(p + ".conv_1.module"),
+                  sd[p + ".conv_1.module.bias"], padding=1)
+    return F.leaky_relu(x_s + dx, 0.2)
+
+
+def mask_spade_decoder(sd, sn, z, cond, num_layers=3, p="decoders.m"):
+    y = F.pad(z, (1, 1, 1, 1), mode="reflect")
+    y = F.conv2d(y, sn.weight(p + ".fc_conv.conv.module"), sd[p + ".fc_conv.conv.module.bias"])
+    y = F.leaky_relu(bn(sd, p + ".fc_conv.norm", y), 0.2)
+    for i in range(num_layers):
+        y = spade_resblock_batch(sd, sn, f"{p}.spade_blocks.{i}", y, cond)
+        y = F.interpolate(y, size=(y.shape[-2] * 2, y.shape[-1] * 2), mode="nearest")
+    y = F.pad(y, (1, 1, 1, 1), mode="reflect")
+    return F.conv2d(y, sn.weight(p + ".mask_conv.conv.module"), sd[p + ".mask_conv.conv.module.bias"])
+
+
+def decode_spade(sd, x, d_target, s_target, sn=None):
+    """OmniGenerator.decode with gen.m.use_spade (generator.py:120-176)."""
+    sn = sn or SNState(sd)
+    z = encoder(sd, x)
+    d, z_depth = depth_decoder(sd, sn, z, d_target)
+    s = seg_decoder(sd, z, z_depth, s_target)
+    cond = make_m_cond(d, s, x)
+    logits = mask_spade_decoder(sd, sn, z, cond)
+    return {"d": d, "s": s, "m": torch.sigmoid(logits)}

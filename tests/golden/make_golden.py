@@ -354,6 +354,38 @@ def run_infer_all_case(name="infer_all", batch=2, size=320):
     print(name, {k: (v.shape, str(v.dtype)) for k, v in arrays.items()}, "npz bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
 
 
+def run_masker_spade_case(name="masker_spade", nblocks=(2, 2, 3, 2), batch=2, size=64):
+    """The paper / release masker configuration (gen.m.use_spade): reference OmniGenerator.decode in eval mode with the
+    MaskSpadeDecoder conditioned on make_m_cond(d, s, x) (masker.py:59-231).  Two consecutive decodes (the spectral-norm
+    power iteration advances on every forward)."""
+    generator_mod, blocks_mod = refshim.load("generator", "blocks")
+    from climategan_b200.utils import Dict, default_masker_opts
+
+    blocks_mod.SPADEResnetBlock.cuda = lambda self, *a, **k: self   # masker.py:196 hard-codes .cuda() (SURVEY.md §8c patch 1)
+    opts = default_masker_opts(nblocks=nblocks, size=size)
+    opts.gen.m.use_spade = True
+    opts.gen.m.spade.activations = Dict(all_lrelu=True)
+    torch.manual_seed(0)
+    G = generator_mod.OmniGenerator(opts)
+    shapes = [(k, tuple(v.shape)) for k, v in G.state_dict().items()]
+    G.load_state_dict(fill_state_dict(shapes, seed=78), strict=True)
+    G.eval()
+    x, _, _ = synth_inputs(batch, size, seed=4)
+    with torch.no_grad():
+        out1 = G.decode(x=x)
+        out2 = G.decode(x=x)
+    arrays = {"m1": out1["m"].numpy(), "m2": out2["m"].numpy(), "d": out1["d"].numpy(), "s": out1["s"].numpy()}
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+    meta = {"case": name, "nblocks": list(nblocks), "batch": batch, "size": size, "weight_seed": 78, "input_seed": 4,
+            "shapes": [[k, list(s_)] for k, s_ in shapes],
+            "reference": "cc-ai/climategan @ /root/reference (generator, masker.MaskSpadeDecoder, norms.SPADE(batch), blocks)",
+            "torch": torch.__version__}
+    with open(os.path.join(HERE, name + ".json"), "w") as f:
+        json.dump(meta, f)
+    print(name, "m range", float(out1["m"].min()), float(out1["m"].max()), "m1 vs m2", float((out1["m"] - out2["m"]).abs().max()),
+          "npz bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
+
+
 if __name__ == "__main__":
     if not refshim.available():
         sys.exit("reference tree not available; goldens can only be regenerated in the build container")
@@ -364,3 +396,4 @@ if __name__ == "__main__":
     run_masker_case()
     run_full_step_case()
     run_infer_all_case()
+    run_masker_spade_case()

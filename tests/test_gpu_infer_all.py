@@ -131,3 +131,44 @@ def test_event_kernels_against_torch(cuda):
     ref8 = (tt.permute(0, 2, 3, 1).numpy() * 255).astype(np.uint8)
     got8 = events.to_uint8_nhwc(img.to(cuda)).cpu().numpy()
     assert (np.abs(got8.astype(int) - ref8.astype(int)) <= 1).all() and (got8 == ref8).mean() > 0.999
+
+
+def test_save_resume_and_apply_events_cli(cuda, tmp_path):
+    """Trainer.save -> Trainer.resume_from_path (reference checkpoint layout: opts.yaml + checkpoints/latest_ckpt.pth with keys
+    G / g_opt / D / d_opt / epoch / step) and the apply_events.py CLI: events written as {stem}_{event}_{width}{suffix}.png."""
+    import subprocess
+    import sys
+
+    import yaml
+    from PIL import Image
+
+    size = 256
+    opts = full_opts(size=size)
+    opts.output_path = str(tmp_path / "run")
+    t = Trainer(opts, device=cuda, storage_dtype=torch.bfloat16).setup(input_shape=(size, size))
+    (tmp_path / "run").mkdir()
+    with open(tmp_path / "run" / "opts.yaml", "w") as f:
+        yaml.safe_dump(opts.to_dict(), f)
+    ckpt = t.save()
+    saved = torch.load(ckpt, map_location="cpu")
+    assert {"G", "g_opt", "D", "d_opt", "epoch", "step"} <= set(saved)
+    t2 = Trainer.resume_from_path(tmp_path / "run", inference=True, device=cuda, input_shape=(size, size))
+    for (k, a), (_, b) in zip(t.G.state_dict().items(), t2.G.state_dict().items()):
+        assert torch.equal(a, b), k
+    imgs = tmp_path / "imgs"
+    imgs.mkdir()
+    rs = np.random.RandomState(0)
+    for i, (h, w) in enumerate([(300, 400), (512, 512), (260, 700)]):
+        Image.fromarray(rs.randint(0, 255, size=(h, w, 3), dtype=np.uint8)).save(imgs / f"im{i}.png")
+    out = tmp_path / "out"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "apply_events.py"), "-i", str(imgs), "-o", str(out), "-r",
+                          str(tmp_path / "run"), "-t", str(size), "-b", "2", "--save_masks", "--no_cloudy", "--fuse"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    for i in range(3):
+        for ev in ("flood", "wildfire", "smog", "mask"):
+            f = out / f"im{i}_{ev}_{size}_no_cloudy.png"
+            assert f.exists(), (f, sorted(p.name for p in out.iterdir()))
+            im = np.asarray(Image.open(f))
+            assert im.shape[:2] == (size, size)

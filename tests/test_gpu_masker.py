@@ -88,3 +88,27 @@ def test_masker_full_size_shapes(cuda):
     for k in ("d", "s", "m"):
         assert bool(torch.isfinite(out[k]).all()), k
     assert float(out["m"].min()) >= 0.0 and float(out["m"].max()) <= 1.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_masker_spade_decoder_matches_reference_golden(cuda, dtype):
+    """gen.m.use_spade (paper / release configuration): MaskSpadeDecoder conditioned on make_m_cond(d, s, x) — SPADE with a
+    BatchNorm param-free norm read from running statistics — against the reference OmniGenerator.decode, two consecutive
+    decodes (the spectral-norm vectors advance).  Tolerances: fp32 storage 2e-4 of full scale, bf16 4e-2."""
+    from climategan_b200.utils import Dict
+
+    meta, g, sd, (x, _, _) = load_golden("masker_spade")
+    opts = default_masker_opts(nblocks=tuple(meta["nblocks"]), size=meta["size"])
+    opts.gen.m.use_spade = True
+    opts.gen.m.spade.activations = Dict(all_lrelu=True)
+    G = OmniGenerator(opts, storage_dtype=dtype)
+    G.load_state_dict(sd, strict=True)
+    G = G.to(cuda).eval()
+    tol = 2e-4 if dtype == torch.float32 else 4e-2
+    o1 = G.decode(x=x.to(cuda))
+    o2 = G.decode(x=x.to(cuda))
+    assert o1["m"].shape == (meta["batch"], 1, meta["size"], meta["size"])
+    assert rel_max(o1["m"], torch.from_numpy(g["m1"])) < tol, rel_max(o1["m"], torch.from_numpy(g["m1"]))
+    assert rel_max(o2["m"], torch.from_numpy(g["m2"])) < tol, rel_max(o2["m"], torch.from_numpy(g["m2"]))
+    with pytest.raises(NotImplementedError):
+        G.train().decode(x=x.to(cuda))

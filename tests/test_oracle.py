@@ -225,3 +225,19 @@ def test_full_step_oracle_matches_reference_trainer_golden():
         a = gsd[k].grad.numpy().reshape(-1)
         a = a[::max(1, -(-a.size // 8192))]
         assert np.abs(a - g["G.grad::" + k]).max() <= 1e-4 * np.abs(g["G.grad::" + k]).max(), k
+
+
+def test_masker_spade_oracle_matches_reference_golden():
+    """oracle MaskSpadeDecoder path (SPADE with BatchNorm running statistics, 15-channel conditioning) vs the reference
+    OmniGenerator.decode with gen.m.use_spade, two consecutive decodes."""
+    from oracle import masker_oracle as mo
+
+    meta, g, sd, (x, _, _) = load_golden("masker_spade")
+    sn = mo.SNState(sd)
+    with torch.no_grad():
+        q = meta["size"] // 4
+        o1 = mo.decode_spade(sd, x, q, q, sn)
+        o2 = mo.decode_spade(sd, x, q, q, sn)
+    assert rel_max(o1["m"], torch.from_numpy(g["m1"])) < 1e-5
+    assert rel_max(o2["m"], torch.from_numpy(g["m2"])) < 1e-5
+    assert rel_max(o1["d"], torch.from_numpy(g["d"])) < 1e-5 and rel_max(o1["s"], torch.from_numpy(g["s"])) < 1e-5
