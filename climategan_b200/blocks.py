@@ -219,16 +219,20 @@ class BaseDecoder(nn.Module):
     def __init__(self, n_upsample=4, n_res=4, input_dim=2048, proj_dim=64, output_dim=3, norm="batch", activ="relu",
                  pad_type="zero", output_activ="tanh", low_level_feats_dim=-1, use_dada=False):
         super().__init__()
-        if low_level_feats_dim > 0:
-            raise NotImplementedError("BaseDecoder low-level features (deeplabv3 encoder) are not built")
         self.low_level_feats_dim = low_level_feats_dim
         self.use_dada = use_dada
-        self.low_level_conv = None
         if proj_dim != -1:
             self.proj_conv = Conv2dBlock(input_dim, proj_dim, 1, 1, 0, norm=norm, activation=activ)
         else:
             self.proj_conv = None
             proj_dim = input_dim
+        if low_level_feats_dim > 0:   # deeplabv3 encoder: the backbone's layer1 features join the latent (blocks.py:237-258)
+            self.low_level_conv = Conv2dBlock(input_dim=low_level_feats_dim, output_dim=proj_dim, kernel_size=3, stride=1,
+                                              padding=1, pad_type=pad_type, norm=norm, activation=activ)
+            self.merge_feats_conv = Conv2dBlock(input_dim=2 * proj_dim, output_dim=proj_dim, kernel_size=1, stride=1, padding=0,
+                                                pad_type=pad_type, norm=norm, activation=activ)
+        else:
+            self.low_level_conv = None
         model = [ResBlocks(n_res, proj_dim, norm, activ, pad_type=pad_type)]
         dim = proj_dim
         for _ in range(n_upsample):
@@ -243,11 +247,24 @@ class BaseDecoder(nn.Module):
 
     def forward_storage(self, z, cond=None, z_depth=None):
         """blocks.py:291-318.  Train mode (or grad enabled on a training module): autograd forwards; eval: fused inference."""
+        import torch
+
         train = self.training
+        run = (lambda blk, t: blk(t)) if train else (lambda blk, t: blk.forward_infer(t))
+        low = None
+        if isinstance(z, (list, tuple)):
+            if self.low_level_conv is None:
+                z = z[0]
+            else:
+                z, low = z
+                low = run(self.low_level_conv, low)
+                low = ops.resize_bilinear(low, z.shape[1], z.shape[2], align_corners=False)
         if z_depth is not None and self.use_dada:
             z = ops.mul(z, z_depth)
         if self.proj_conv is not None:
-            z = self.proj_conv(z) if train else self.proj_conv.forward_infer(z)
+            z = run(self.proj_conv, z)
+        if low is not None:
+            z = run(self.merge_feats_conv, torch.cat([low, z], dim=-1))
         for m in self.model:
             if isinstance(m, InterpolateNearest2d) or train:
                 z = m(z)

@@ -242,7 +242,7 @@ __global__ void bn_update_running_kernel(const float* __restrict__ mean, const f
 template <typename T>
 __global__ void __launch_bounds__(256)
 maxpool3s2_ceil_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy, T* __restrict__ gx, long long total_vec,
-                           int hi, int wi, int ho, int wo, int c) {
+                           int hi, int wi, int ho, int wo, int c, int pad = 0) {
   const int cv = c >> 3;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i / cv;
@@ -255,20 +255,21 @@ maxpool3s2_ceil_bwd_kernel(const T* __restrict__ x, const T* __restrict__ gy, T*
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     Vec8<T>::load(x + pix * c + v * 8, me);
-    const int oy_a = max(0, (iy - 1) / 2), oy_b = min(ho - 1, iy / 2);  // windows with oy*2 <= iy <= oy*2+2
-    const int ox_a = max(0, (ix - 1) / 2), ox_b = min(wo - 1, ix / 2);
+    // windows (oy, ox) covering the pixel: oy*2 - pad <= iy <= oy*2 - pad + 2
+    const int oy_a = max(0, (iy + pad - 1) / 2), oy_b = min(ho - 1, (iy + pad) / 2);
+    const int ox_a = max(0, (ix + pad - 1) / 2), ox_b = min(wo - 1, (ix + pad) / 2);
     for (int oy = oy_a; oy <= oy_b; ++oy) {
-      if (!(oy * 2 <= iy && iy <= oy * 2 + 2)) continue;
+      if (!(oy * 2 - pad <= iy && iy <= oy * 2 - pad + 2)) continue;
       for (int ox = ox_a; ox <= ox_b; ++ox) {
-        if (!(ox * 2 <= ix && ix <= ox * 2 + 2)) continue;
+        if (!(ox * 2 - pad <= ix && ix <= ox * 2 - pad + 2)) continue;
         // is (iy, ix) the first maximum of window (oy, ox)?
         bool first[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) first[j] = true;
         for (int dy = 0; dy < 3; ++dy)
           for (int dx = 0; dx < 3; ++dx) {
-            const int sy = oy * 2 + dy, sx = ox * 2 + dx;
-            if (sy >= hi || sx >= wi || (sy == iy && sx == ix)) continue;
+            const int sy = oy * 2 + dy - pad, sx = ox * 2 + dx - pad;
+            if (sy < 0 || sx < 0 || sy >= hi || sx >= wi || (sy == iy && sx == ix)) continue;
             float f[8];
             Vec8<T>::load(x + ((img * hi + sy) * wi + sx) * c + v * 8, f);
             const bool before = (sy < iy) || (sy == iy && sx < ix);
@@ -927,6 +928,16 @@ extern "C" int cgb_maxpool3s2_ceil_bwd(const void* x, const void* gy, void* gx, 
   DISPATCH_T(dtype, maxpool3s2_ceil_bwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
                         (const T*)x, (const T*)gy, (T*)gx, total, hi, wi, ho, wo, c);)
   return after_launch("maxpool3s2_ceil_bwd");
+}
+
+extern "C" int cgb_maxpool3s2_bwd(const void* x, const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi, int32_t wi,
+                                  int32_t ho, int32_t wo, int32_t c, int32_t pad, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && gy && gx && c % 8 == 0 && c >= 8 && (pad == 0 || pad == 1), "maxpool3s2_bwd: bad arguments");
+  const long long total = (long long)n * hi * wi * (c / 8);
+  DISPATCH_T(dtype, maxpool3s2_ceil_bwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, (const T*)gy, (T*)gx, total, hi, wi, ho, wo, c, pad);)
+  return after_launch("maxpool3s2_bwd");
 }
 
 extern "C" int cgb_resize_bilinear_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t ho,

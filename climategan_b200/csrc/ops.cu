@@ -701,7 +701,8 @@ vgg_pre_bwd_kernel(const T* __restrict__ gy, const float* __restrict__ m, float*
 // nn.MaxPool2d(3, stride=2, padding=0, ceil_mode=True) (deeplab/resnetmulti_v2.py:76-78)
 template <typename T>
 __global__ void __launch_bounds__(256)
-maxpool3s2_ceil_kernel(const T* __restrict__ x, T* __restrict__ y, long long total_vec, int hi, int wi, int ho, int wo, int c) {
+maxpool3s2_ceil_kernel(const T* __restrict__ x, T* __restrict__ y, long long total_vec, int hi, int wi, int ho, int wo, int c,
+                       int pad = 0) {
   const int cv = c >> 3;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
     const long long pix = i / cv;
@@ -715,8 +716,8 @@ maxpool3s2_ceil_kernel(const T* __restrict__ x, T* __restrict__ y, long long tot
     for (int j = 0; j < 8; ++j) best[j] = -3.4e38f;
     for (int dy = 0; dy < 3; ++dy)
       for (int dx = 0; dx < 3; ++dx) {
-        const int sy = oy * 2 + dy, sx = ox * 2 + dx;
-        if (sy >= hi || sx >= wi) continue;
+        const int sy = oy * 2 + dy - pad, sx = ox * 2 + dx - pad;
+        if (sy < 0 || sx < 0 || sy >= hi || sx >= wi) continue;
         float f[8];
         Vec8<T>::load(x + ((img * hi + sy) * wi + sx) * c + v * 8, f);
 #pragma unroll
@@ -1457,6 +1458,16 @@ extern "C" int cgb_maxpool3s2_ceil_fwd(const void* x, void* y, int32_t dtype, in
   DISPATCH_T(dtype, maxpool3s2_ceil_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total, hi, wi,
                                                                                                 ho, wo, c);)
   return after_launch("maxpool3s2_ceil");
+}
+
+extern "C" int cgb_maxpool3s2_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t ho, int32_t wo,
+                                  int32_t c, int32_t pad, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y && c % 8 == 0 && c >= 8 && (pad == 0 || pad == 1), "maxpool3s2_fwd: bad arguments");
+  const long long total = (long long)n * ho * wo * (c / 8);
+  DISPATCH_T(dtype, maxpool3s2_ceil_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total, hi, wi,
+                                                                                                ho, wo, c, pad);)
+  return after_launch("maxpool3s2");
 }
 
 extern "C" int cgb_resize_bilinear_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t ho,

@@ -39,6 +39,8 @@ class DADADepthDecoder(nn.Module):
 
     def forward_storage(self, z):
         """z storage [N,h,w,2048] -> (depth storage [N,T,T,8] (1 real channel), z_depth storage or None)."""
+        if isinstance(z, (list, tuple)):   # deeplabv3 encoder: (z, low_level_feat) (depth.py:129-130)
+            z = z[0]
         run = (lambda blk, t: blk(t)) if self.training else (lambda blk, t: blk.forward_infer(t))
         z4 = run(self.enc4_3, run(self.enc4_2, run(self.enc4_1, z)))
         z_depth = run(self.dec4, z4) if self.do_feat_fusion else None

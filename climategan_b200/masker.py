@@ -19,13 +19,15 @@ def create_mask_decoder(opts, no_init=False, verbose=0):
 
 class MaskBaseDecoder(BaseDecoder):
     def __init__(self, opts):
-        if opts.gen.encoder.architecture == "deeplabv3":
-            raise NotImplementedError("the deeplabv3 encoder / low-level-feature branch is not built")
+        use_v3 = opts.gen.encoder.architecture == "deeplabv3"
+        if use_v3 and opts.gen.deeplabv3.backbone == "mobilenet":
+            raise NotImplementedError("the deeplabv3 mobilenet backbone is not built")
+        low_level_feats_dim = 256 if (use_v3 and opts.gen.m.use_low_level_feats) else -1   # masker.py:27-44
         use_dada = ("d" in opts.tasks) and opts.gen.m.use_dada
         super().__init__(n_upsample=opts.gen.m.n_upsample, n_res=opts.gen.m.n_res, input_dim=2048,
                          proj_dim=opts.gen.m.proj_dim, output_dim=opts.gen.m.output_dim, norm=opts.gen.m.norm,
                          activ=opts.gen.m.activ, pad_type=opts.gen.m.pad_type, output_activ="none",
-                         low_level_feats_dim=-1, use_dada=use_dada)
+                         low_level_feats_dim=low_level_feats_dim, use_dada=use_dada)
 
 
 class MaskSpadeDecoder(nn.Module):

@@ -816,6 +816,33 @@ class _MaxPool3s2Ceil(Function):
         return gx
 
 
+class _MaxPool3s2Pad1(Function):
+    @staticmethod
+    def forward(ctx, x):
+        _chk_storage(x)
+        n, hi, wi, c = x.shape
+        ho, wo = (hi + 2 - 3) // 2 + 1, (wi + 2 - 3) // 2 + 1
+        y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
+        check(_L().cgb_maxpool3s2_fwd(_p(x), _p(y), _DT[x.dtype], n, hi, wi, ho, wo, c, 1, _st()), "maxpool3s2")
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        n, hi, wi, c = x.shape
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        check(_L().cgb_maxpool3s2_bwd(_p(x), _p(gy), _p(gx), _DT[x.dtype], n, hi, wi, gy.shape[1], gy.shape[2], c, 1, _st()),
+              "maxpool3s2_bwd")
+        return gx
+
+
+def maxpool3s2_pad1(x):
+    """nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (deeplab/resnet101_v3.py:75)."""
+    return _MaxPool3s2Pad1.apply(x)
+
+
 def maxpool3s2_ceil(x):
     """nn.MaxPool2d(3, stride=2, padding=0, ceil_mode=True) (deeplab/resnetmulti_v2.py:76-78)."""
     return _MaxPool3s2Ceil.apply(x)

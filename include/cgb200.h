@@ -232,6 +232,12 @@ int cgb_bn_train_bwd(const void* x, const float* mean, const float* rstd, const 
  * with a counter-based mask from (seed, element index): the same call on the gradient is its backward. */
 int cgb_maxpool3s2_ceil_bwd(const void* x, const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi, int32_t wi,
                             int32_t ho, int32_t wo, int32_t c, void* stream);
+/* nn.MaxPool2d(3, stride=2, padding=pad) for pad in {0,1} (deeplab/resnet101_v3.py:75: the v3 stem pools with padding 1);
+ * the caller passes ho / wo (floor or ceil mode); the adjoint routes to the first maximum of each window. */
+int cgb_maxpool3s2_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t ho, int32_t wo, int32_t c,
+                       int32_t pad, void* stream);
+int cgb_maxpool3s2_bwd(const void* x, const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t ho,
+                       int32_t wo, int32_t c, int32_t pad, void* stream);
 int cgb_resize_bilinear_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t ho,
                             int32_t wo, int32_t c, int32_t align_corners, void* stream);
 int cgb_reflect_pad_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad,

@@ -386,6 +386,70 @@ def run_masker_spade_case(name="masker_spade", nblocks=(2, 2, 3, 2), batch=2, si
           "npz bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
 
 
+def v3_opts(size=128, nblocks=(2, 2, 3, 2)):
+    from climategan_b200.utils import default_masker_opts
+
+    opts = default_masker_opts(nblocks=nblocks, size=size)
+    opts.gen.encoder.architecture = "deeplabv3"
+    opts.gen.s.architecture = "deeplabv3"
+    opts.gen.deeplabv3.nblocks = list(nblocks)   # read by climategan_b200 only; the reference is patched below
+    return opts
+
+
+def run_masker_v3_case(name="masker_v3", nblocks=(2, 2, 3, 2), batch=2, size=128):
+    """The reference's DEFAULT masker architecture (defaults.yaml:101,136: deeplabv3 encoder + decoder, ResNet backbone at
+    output stride 8, mask decoder with low-level features), shallow copy [2,2,3,2] of the same architecture:
+    (i) eval-mode OmniGenerator.decode; (ii) train-mode encode + the three decoders, a fixed random linear functional of
+    (d, s, m) back-propagated: gradient norm of every parameter + sampled gradients + updated running statistics."""
+    generator_mod, deeplab_mod, resnet_mod = refshim.load("generator", "deeplab", "deeplab.resnet101_v3")
+    deeplab_mod.ResNet101 = lambda output_stride=8, BatchNorm=None, verbose=0, no_init=False: resnet_mod.ResNet(
+        resnet_mod.Bottleneck, list(nblocks), output_stride, BatchNorm, verbose=verbose, no_init=no_init)
+    opts = v3_opts(size, nblocks)
+    torch.manual_seed(0)
+    G = generator_mod.OmniGenerator(opts, no_init=True)
+    shapes = [(k, tuple(v.shape)) for k, v in G.state_dict().items()]
+    G.load_state_dict(fill_state_dict(shapes, seed=79), strict=True)
+    x, _, _ = synth_inputs(batch, size, seed=6)
+    G.eval()
+    with torch.no_grad():
+        out = G.decode(x=x)
+    arrays = {"d": out["d"].numpy(), "s": out["s"].numpy(), "m": out["m"].numpy()}
+    G.train()
+    for mod in G.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    rs = np.random.RandomState(123)
+    z = G.encode(x)
+    d, z_depth = G.decoders["d"](z)
+    s_ = G.decoders["s"](z, z_depth)
+    m = G.decoders["m"](z, z_depth=z_depth)
+    wd, ws, wm = (torch.from_numpy(rs.standard_normal(size=t.shape).astype(np.float32)) for t in (d, s_, m))
+    loss = (d * wd).mean() + (s_ * ws).mean() + (m * wm).mean()
+    loss.backward()
+    names = [k for k, _ in G.named_parameters()]
+    arrays["train_loss"] = np.float64(loss.item())
+    arrays["train_d"], arrays["train_s"], arrays["train_m"] = d.detach().numpy(), s_.detach().numpy(), m.detach().numpy()
+    arrays["gradnorm"] = np.array([float(p_.grad.norm()) if p_.grad is not None else -1.0 for _, p_ in G.named_parameters()])
+    gp = dict(G.named_parameters())
+    full = ["encoder.conv1.weight", "encoder.layer2.0.conv2.weight", "encoder.layer4.2.conv2.weight", "encoder.layer3.0.bn1.weight",
+            "decoders.s.aspp.conv_out.conv.weight", "decoders.s.decoder.conv_low.conv.bias", "decoders.s.decoder.conv_out.weight",
+            "decoders.m.low_level_conv.conv.module.weight_bar", "decoders.m.merge_feats_conv.conv.module.weight_bar"]
+    for k in full:
+        arrays["grad::" + k] = _sample(gp[k].grad.detach().numpy())
+    sd = G.state_dict()
+    for k in ("encoder.bn1.running_mean", "encoder.layer4.1.bn2.running_var", "decoders.s.aspp.conv_out.bn.running_var"):
+        arrays["final::" + k] = sd[k].numpy().copy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+    meta = {"case": name, "nblocks": list(nblocks), "batch": batch, "size": size, "weight_seed": 79, "input_seed": 6,
+            "functional_seed": 123, "shapes": [[k, list(s__)] for k, s__ in shapes], "param_names": names, "full": full,
+            "reference": "cc-ai/climategan @ /root/reference (generator, deeplab/resnet101_v3, deeplab/deeplab_v3, depth, masker, blocks)",
+            "torch": torch.__version__}
+    with open(os.path.join(HERE, name + ".json"), "w") as f:
+        json.dump(meta, f)
+    print(name, {k: tuple(v.shape) for k, v in out.items() if hasattr(v, "shape")}, "loss", float(loss), "npz bytes",
+          os.path.getsize(os.path.join(HERE, name + ".npz")))
+
+
 if __name__ == "__main__":
     if not refshim.available():
         sys.exit("reference tree not available; goldens can only be regenerated in the build container")
@@ -397,3 +461,4 @@ if __name__ == "__main__":
     run_full_step_case()
     run_infer_all_case()
     run_masker_spade_case()
+    run_masker_v3_case()

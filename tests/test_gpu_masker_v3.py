@@ -1,0 +1,93 @@
+"""GPU parity of the reference's DEFAULT masker architecture (deeplabv3: ResNet backbone at output stride 8 with multi-grid
+layer4, ASPPv3Plus + Decoder with the reference's 82x82 / swapped-argument quirks, mask decoder with low-level features)
+against goldens from the reference modules (tests/golden/masker_v3.*): eval decode, and a train-mode forward/backward."""
+import numpy as np
+import pytest
+import torch
+
+from climategan_b200.generator import OmniGenerator
+from tests.helpers import load_golden, rel_max
+
+pytestmark = pytest.mark.gpu
+
+
+def _opts(meta):
+    from climategan_b200.utils import default_masker_opts
+
+    opts = default_masker_opts(nblocks=tuple(meta["nblocks"]), size=meta["size"])
+    opts.gen.encoder.architecture = "deeplabv3"
+    opts.gen.s.architecture = "deeplabv3"
+    opts.gen.deeplabv3.nblocks = list(meta["nblocks"])
+    return opts
+
+
+def _sample(a, cap=8192):
+    a = a.detach().float().cpu().numpy().reshape(-1)
+    return a[::max(1, -(-a.size // cap))]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_masker_v3_matches_reference_golden(cuda, dtype):
+    """Tolerances: fp32 storage — eval d / s / m 2e-4 of full scale, train-mode predictions 2e-4, loss 1e-4, every gradient norm
+    2e-3, sampled gradients 2e-2 (the stem's gradient sits behind ~30 layers), running statistics 1e-4.  bf16 storage — eval
+    predictions 4e-2; train mode see below."""
+    meta, g, sd, (x, _, _) = load_golden("masker_v3")
+    G = OmniGenerator(_opts(meta), storage_dtype=dtype)
+    assert [(k, tuple(v.shape)) for k, v in G.state_dict().items()] == [(k, tuple(s)) for k, s in meta["shapes"]]
+    assert [k for k, _ in G.named_parameters()] == meta["param_names"]
+    G.load_state_dict(sd, strict=True)
+    G = G.to(cuda).eval()
+    x = x.to(cuda)
+    fp32 = dtype == torch.float32
+    tol = 2e-4 if fp32 else 4e-2
+    out = G.decode(x=x)
+    for k in ("d", "s", "m"):
+        assert rel_max(out[k], torch.from_numpy(g[k])) < tol, (k, rel_max(out[k], torch.from_numpy(g[k])))
+    # train mode, same call order as the golden (the eval decode above advanced the spectral-norm vectors)
+    G.train()
+    for mod in G.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    z = G.encode(x)
+    d, z_depth = G.decode_d(z)
+    s = G.decode_s(z, z_depth)
+    m = G.decode_m(z, z_depth=z_depth)
+    # bf16 + train-mode BatchNorm on this random-weight fixture: the depth head's last BatchNorm sees channels whose batch
+    # spread is a few bf16 steps of their mean (the running statistics used in eval are O(1)), so normalising by the BATCH
+    # deviation amplifies the storage rounding of its input ~10x: d is reported but not asserted in bf16; s and m (not behind
+    # such a channel, but behind ~30 batch-normalised bf16 layers on 2x16x16 maps) are held to 0.3 of full scale.
+    for k, t in (("train_d", d), ("train_s", s), ("train_m", m)):
+        err = rel_max(t, torch.from_numpy(g[k]))
+        if fp32:
+            assert err < tol, (k, err)
+        elif k != "train_d":
+            assert err < 0.3, (k, err)
+    rs = np.random.RandomState(meta["functional_seed"])
+    wd, ws, wm = (torch.from_numpy(rs.standard_normal(size=tuple(t.shape)).astype(np.float32)).to(cuda) for t in (d, s, m))
+    loss = (d * wd).mean() + (s * ws).mean() + (m * wm).mean()
+    loss.backward()
+    ref_loss = float(g["train_loss"])
+    if fp32:
+        assert abs(float(loss) - ref_loss) < 1e-4 * abs(ref_loss) + 1e-6
+    gp = dict(G.named_parameters())
+    bad = []
+    scale = g["gradnorm"].max()
+    for name, r in zip(meta["param_names"], g["gradnorm"]):
+        if r < 0:
+            continue
+        a = float(gp[name].grad.norm())
+        if fp32 and abs(a - r) > 2e-3 * r + 1e-6 * scale:
+            bad.append((name, a, r))
+        if not fp32 and not (name.startswith("decoders.d") or name.startswith("encoder")) and r > 1e-2 * scale \
+                and abs(a - r) > 0.3 * r:
+            bad.append((name, a, r))   # (the encoder / depth gradients inherit the depth head's amplification, see above)
+    assert not bad, bad[:10]
+    if fp32:
+        for k in meta["full"]:
+            a, b = _sample(gp[k].grad), g["grad::" + k]
+            # (+1e-7: a bias in front of a BatchNorm has an exactly-zero gradient, only rounding residue on both sides)
+            assert np.abs(a - b).max() <= 2e-2 * np.abs(b).max() + 1e-7, (k, float(np.abs(a - b).max() / np.abs(b).max()))
+        sdn = G.state_dict()
+        for k in g:
+            if k.startswith("final::"):
+                assert rel_max(sdn[k[7:]], torch.from_numpy(g[k])) < 1e-4, k

@@ -241,3 +241,38 @@ def test_masker_spade_oracle_matches_reference_golden():
     assert rel_max(o1["m"], torch.from_numpy(g["m1"])) < 1e-5
     assert rel_max(o2["m"], torch.from_numpy(g["m2"])) < 1e-5
     assert rel_max(o1["d"], torch.from_numpy(g["d"])) < 1e-5 and rel_max(o1["s"], torch.from_numpy(g["s"])) < 1e-5
+
+
+def _v3_functional(meta, d, s, m):
+    rs = np.random.RandomState(meta["functional_seed"])
+    wd, ws, wm = (torch.from_numpy(rs.standard_normal(size=tuple(t.shape)).astype(np.float32)) for t in (d, s, m))
+    return wd, ws, wm
+
+
+def test_masker_v3_oracle_matches_reference_golden():
+    """oracle/masker_v3_oracle.py (the reference's default deeplabv3 masker) vs the reference modules: eval decode, and a
+    train-mode forward/backward (batch-statistics BatchNorm) with the gradient norm of every parameter."""
+    from oracle import masker_oracle as mo
+    from oracle import masker_v3_oracle as v3
+
+    meta, g, sd, (x, _, _) = load_golden("masker_v3")
+    q = meta["size"] // 4
+    sdt = {k: v.clone() for k, v in sd.items()}
+    for k in meta["param_names"]:
+        sdt[k].requires_grad_(not k.endswith(("weight_u", "weight_v")))
+    sn = v3.SNState(sdt)   # one state through both passes: the eval decode advances the spectral-norm u / v first, as in the golden
+    with torch.no_grad():
+        out = v3.forward(sdt, x, q, q, sn)
+    for k in ("d", "s", "m"):
+        assert rel_max(out[k], torch.from_numpy(g[k])) < 1e-5, k
+    with mo.train_mode():
+        o = v3.forward(sdt, x, q, q, sn)
+    wd, ws, wm = _v3_functional(meta, o["d"], o["s"], o["m_logits"])
+    loss = (o["d"] * wd).mean() + (o["s"] * ws).mean() + (o["m_logits"] * wm).mean()
+    loss.backward()
+    assert abs(float(loss) - float(g["train_loss"])) < 1e-6 + 1e-5 * abs(float(g["train_loss"]))
+    for name, r in zip(meta["param_names"], g["gradnorm"]):
+        if r >= 0:
+            assert abs(float(sdt[name].grad.norm()) - r) <= 1e-4 * r + 1e-9, (name, float(sdt[name].grad.norm()), r)
+    for k in ("encoder.bn1.running_mean", "encoder.layer4.1.bn2.running_var", "decoders.s.aspp.conv_out.bn.running_var"):
+        assert rel_max(sdt[k], torch.from_numpy(g["final::" + k])) < 1e-5, k
