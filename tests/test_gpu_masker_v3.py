@@ -91,3 +91,35 @@ def test_masker_v3_matches_reference_golden(cuda, dtype):
         for k in g:
             if k.startswith("final::"):
                 assert rel_max(sdn[k[7:]], torch.from_numpy(g[k])) < 1e-4, k
+
+
+def test_full_train_step_runs_with_the_v3_masker(cuda):
+    """Trainer.update_G / update_D (tasks d, s, m, p) with the reference-default deeplabv3 encoder / decoder: z is the
+    (latent, low-level features) pair all the way through get_masker_loss and get_D_loss; losses finite, parameters move."""
+    from climategan_b200.trainer import Trainer
+    from climategan_b200.utils import full_opts, synth_batch
+
+    size = 128
+    opts = full_opts(size=size)
+    opts.gen.encoder.architecture = "deeplabv3"
+    opts.gen.s.architecture = "deeplabv3"
+    opts.gen.deeplabv3.nblocks = [2, 2, 3, 2]
+    torch.manual_seed(0)
+    t = Trainer(opts, device=cuda, storage_dtype=torch.bfloat16).setup(input_shape=(size, size))
+    assert type(t.G.encoder).__name__ == "ResNet" and t.G.decoders["m"].low_level_conv is not None
+    mdb = {dom: t.batch_to_device(b) for dom, b in synth_batch(opts, 2, size, 3).items()}
+    w0 = t.G.encoder.layer4[2].conv2.weight.detach().clone()
+    for _ in range(2):
+        t.update_G(mdb)
+        t.update_D(mdb)
+        t.logger.global_step += 1
+    logs = t.losses_to_host()
+    flat = []
+
+    def walk(d):
+        for v in d.values():
+            walk(v) if isinstance(v, dict) else flat.append(float(v))
+
+    walk(logs)
+    assert flat and all(np.isfinite(v) for v in flat), logs
+    assert not torch.equal(w0, t.G.encoder.layer4[2].conv2.weight.detach())
