@@ -815,7 +815,10 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
   int ws_bn = 0, ws_ntiles = 0, ws_stages = 0;
   const int twh = 8 + dil * (kw - 1), thh = 16 + dil * (kh - 1);
   const int a_stage = ((twh * thh * 128) + 1023) / 1024 * 1024;
-  if (stride == 1 && taps > 1 && wout >= 24 && hout >= 32 && twh <= 256 && thh <= 256 && a_stage <= 48 * 1024) {
+  // 1x1 convs with many output channels (ResNet 256->1024) re-stream 128 KB of weights per 128-pixel tile in the streaming
+  // kernel (L2 -> SM bound); holding a >= 128-channel weight slice resident makes them activation-bound instead
+  static const int ws_1x1 = getenv("CGB_WS_1X1") ? atoi(getenv("CGB_WS_1X1")) : 0;
+  if (stride == 1 && (taps > 1 || ws_1x1) && wout >= 24 && hout >= 32 && twh <= 256 && thh <= 256 && a_stage <= 48 * 1024) {
     for (int nt = 1; nt <= 8 && !use_ws; ++nt) {
       int bn = ((cout_s + nt - 1) / nt + 15) / 16 * 16;
       if (bn > 256) continue;
@@ -832,7 +835,7 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
       // max(N/2, (4096+32N)/128) cycles, scripts/exp/mma_rate.cu) and re-read the halo once per slice.
       static const int ws_max_co = getenv("CGB_WS_MAX_CO") ? atoi(getenv("CGB_WS_MAX_CO")) : 64;
       // ... and for wide outputs fed by a single 64-channel block (the dgrad of gamma||beta, 48->128: 1.82 vs 1.97 ms)
-      if (ws_bytes < 0.8 * stream_bytes && (cout_s <= ws_max_co || kblocks == 1)) {
+      if (ws_bytes < 0.8 * stream_bytes && (cout_s <= ws_max_co || kblocks == 1 || (taps == 1 && ws_1x1 && bn >= 128))) {
         use_ws = true; ws_bn = bn; ws_ntiles = nt; ws_stages = stg;
       }
       break;  // the smallest feasible n-split is the cheapest in activation re-reads
