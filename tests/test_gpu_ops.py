@@ -57,19 +57,27 @@ CONV_CASES = [
 @pytest.mark.parametrize("engine", ENGINES)
 def test_conv_fwd_bwd(cuda, case, dtype, engine):
     n, ci, co, h, w, k, stride, dil, pad, pad_mode, act = case
-    torch.manual_seed(CONV_CASES.index(case) * 7 + 1)  # deterministic (hash() of a tuple with str is salted per process)
-    x = _q(torch.randn(n, ci, h, w), dtype)
-    wt = _q(torch.randn(co, ci, k, k) / (ci * k * k) ** 0.5, dtype)
-    b = torch.randn(co) * 0.1
     pm = _lib.PAD_REFLECT if pad_mode == "reflect" else _lib.PAD_ZERO
-
-    # reference (fp64 CPU)
-    xr = x.double().requires_grad_(True)
-    wr = wt.double().requires_grad_(True)
-    br = b.double().requires_grad_(True)
-    xp = F.pad(xr, (pad,) * 4, mode="reflect") if pad_mode == "reflect" else F.pad(xr, (pad,) * 4)
-    yr = F.conv2d(xp, wr, br, stride=stride, dilation=dil)
     slope = 0.2
+    for attempt in range(16):
+        # deterministic (hash() of a tuple with str is salted per process)
+        torch.manual_seed(CONV_CASES.index(case) * 7 + 1 + 1000 * attempt)
+        x = _q(torch.randn(n, ci, h, w), dtype)
+        wt = _q(torch.randn(co, ci, k, k) / (ci * k * k) ** 0.5, dtype)
+        b = torch.randn(co) * 0.1
+
+        # reference (fp64 CPU)
+        xr = x.double().requires_grad_(True)
+        wr = wt.double().requires_grad_(True)
+        br = b.double().requires_grad_(True)
+        xp = F.pad(xr, (pad,) * 4, mode="reflect") if pad_mode == "reflect" else F.pad(xr, (pad,) * 4)
+        yr = F.conv2d(xp, wr, br, stride=stride, dilation=dil)
+        # a pre-activation within fp32 accumulation error of 0 flips the (l)relu gate against the fp64 reference and
+        # shows up as an O(gy*w) outlier in dgrad (seen with 256x40x40 outputs at K=1024): redraw until there is none
+        if act not in (_lib.ACT_RELU, _lib.ACT_LRELU) or float(yr.detach().abs().min()) > 2e-5:
+            break
+    else:
+        pytest.fail("no seed with a gate margin")
     yr = {_lib.ACT_NONE: lambda t: t, _lib.ACT_RELU: F.relu, _lib.ACT_LRELU: lambda t: F.leaky_relu(t, slope),
           _lib.ACT_TANH: torch.tanh}[act](yr)
     gy = _q(torch.randn_like(yr).float(), dtype)
