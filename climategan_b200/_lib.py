@@ -105,6 +105,7 @@ SIGNATURES = {
     "cgb_channel_mean": ([_P, _P, _I, _L, _I, _I, _P], C.c_int),
     "cgb_mul": ([_P, _P, _P, _I, _L, _P], C.c_int),
     "cgb_make_m_cond": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_make_m_cond_bwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_bn_apply_fwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P], C.c_int),
     "cgb_bn_apply_bwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P], C.c_int),
     "cgb_bn_bwd_ws_doubles": ([_L, _I], C.c_int64),
@@ -145,6 +146,7 @@ SIGNATURES = {
     "cgb_mask_to_uint8": ([_P, _P, _F, _L, _P], C.c_int),
     "cgb_resize_nearest_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_upsample_nearest_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_resize_nearest_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_im2col_strided": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_im2col": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_nchw_to_nhwc": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),

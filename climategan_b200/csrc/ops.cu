@@ -292,6 +292,53 @@ upsample_bwd_kernel(const T* __restrict__ gy, T* __restrict__ gx, long long tota
   }
 }
 
+// Adjoint of resize_nearest_kernel for ANY size ratio, gather form (deterministic, no atomics): an input pixel sums the
+// output pixels whose ATen nearest source index is that pixel.  Candidate rows / columns come from inverting
+// src = min(floor(dst * in/out), in-1) with one pixel of slack, then the forward formula itself decides membership.
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in) {
+  int s = (int)floorf(dst * scale);
+  return s > in - 1 ? in - 1 : s;
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+resize_nearest_bwd_kernel(const T* __restrict__ gy, T* __restrict__ gx, long long total_vec, int hi, int wi, int ho, int wo,
+                          int c) {
+  const int cv = c >> 3;
+  const float sh = (float)hi / (float)ho, sw = (float)wi / (float)wo;
+  const float rh = (float)ho / (float)hi, rw = (float)wo / (float)wi;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int v = (int)(i - pix * cv);
+    const int ix = (int)(pix % wi);
+    const long long t = pix / wi;
+    const int iy = (int)(t % hi);
+    const int img = (int)(t / hi);
+    int y0 = (int)floorf(iy * rh) - 1, y1 = (int)ceilf((iy + 1) * rh) + 1;
+    int x0 = (int)floorf(ix * rw) - 1, x1 = (int)ceilf((ix + 1) * rw) + 1;
+    if (y0 < 0) y0 = 0;
+    if (x0 < 0) x0 = 0;
+    if (y1 > ho - 1) y1 = ho - 1;
+    if (x1 > wo - 1) x1 = wo - 1;
+    if (iy == hi - 1) y1 = ho - 1;   // the clamp to in-1 folds every overshooting row / column onto the last one
+    if (ix == wi - 1) x1 = wo - 1;
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    for (int oy = y0; oy <= y1; ++oy) {
+      if (nearest_src(oy, sh, hi) != iy) continue;
+      for (int ox = x0; ox <= x1; ++ox) {
+        if (nearest_src(ox, sw, wi) != ix) continue;
+        float g[8];
+        Vec8<T>::load(gy + (((long long)img * ho + oy) * wo + ox) * c + v * 8, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s[j] += g[j];
+      }
+    }
+    Vec8<T>::store(gx + pix * c + v * 8, s);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // NCHW fp32 <-> NHWC storage.  Tile transpose through shared memory: 32 pixels x cs channels.
 template <typename T>
@@ -877,6 +924,11 @@ minmax_c0_kernel(const T* __restrict__ x, float* __restrict__ mm, int hw, int cs
   }
 }
 
+__global__ void mm_init_kernel(float* __restrict__ mm, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { mm[2 * i] = 3.4e38f; mm[2 * i + 1] = -3.4e38f; }
+}
+
 // OmniGenerator.make_m_cond (generator.py:196-230): cat[ normalize(d), softmax(s, dim=1), x resized ] -> 16-ch storage
 //   d [n,hw,8] (channel 0), s [n,hw,ss] with ns classes, xr [n,hw,8] (3 channels, already bilinear-resized), mm per-sample min/max
 template <typename T>
@@ -904,6 +956,75 @@ m_cond_kernel(const T* __restrict__ d, const T* __restrict__ s, const T* __restr
       for (int k = 0; k < 3; ++k) o[1 + ns + k] = to_f<T>(xr[p * 8 + k]);
     }
     for (int k = 0; k < cs_out; ++k) out[p * cs_out + k] = from_f<T>(o[k]);
+  }
+}
+
+// Adjoint of m_cond_kernel w.r.t. d and s (the conditioning is differentiable when gen.m.spade.detach is false,
+// defaults.yaml:182; generator.py:217-219).  One CTA per sample (d / s are size/4 maps: 160x160 at 640x640).
+//   y = (d - lo) / r, r = hi - lo (tutils.normalize :566-577):  gd_j = g_j / r - [j = argmin] S0 / r - ([j = argmax] - [j = argmin]) S1 / r
+//   with S0 = sum_i g_i, S1 = sum_i g_i y_i; argmin / argmax = first occurrence in row-major order (torch.min / max with dim).
+//   p = softmax(s): gs_k = p_k (g_k - sum_j g_j p_j), p read back from the forward's output.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+m_cond_bwd_kernel(const T* __restrict__ d, const T* __restrict__ out, const float* __restrict__ mm, const T* __restrict__ gout,
+                  T* __restrict__ gd, T* __restrict__ gs, int hw, int ss, int ns, int cs_out) {
+  const int img = blockIdx.x;
+  const long long base = (long long)img * hw;
+  const float lo = mm[2 * img], hi = mm[2 * img + 1];
+  const float inv_r = 1.f / (hi - lo);
+  float s0 = 0.f, s1 = 0.f;
+  int imin = 0x7fffffff, imax = 0x7fffffff;
+  for (int p = threadIdx.x; p < hw; p += blockDim.x) {
+    const float g = to_f<T>(gout[(base + p) * cs_out]);
+    const float v = to_f<T>(d[(base + p) * 8]);
+    s0 += g;
+    s1 += g * ((v - lo) * inv_r);
+    if (v == lo && p < imin) imin = p;
+    if (v == hi && p < imax) imax = p;
+  }
+  __shared__ float sh0[32], sh1[32];
+  __shared__ int shmin[32], shmax[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, o));
+    imax = min(imax, __shfl_xor_sync(0xffffffffu, imax, o));
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (lane == 0) { sh0[warp] = s0; sh1[warp] = s1; shmin[warp] = imin; shmax[warp] = imax; }
+  __syncthreads();
+  if (warp == 0) {
+    s0 = lane < nw ? sh0[lane] : 0.f;
+    s1 = lane < nw ? sh1[lane] : 0.f;
+    imin = lane < nw ? shmin[lane] : 0x7fffffff;
+    imax = lane < nw ? shmax[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, o));
+      imax = min(imax, __shfl_xor_sync(0xffffffffu, imax, o));
+    }
+    if (lane == 0) { sh0[0] = s0; sh1[0] = s1; shmin[0] = imin; shmax[0] = imax; }
+  }
+  __syncthreads();
+  s0 = sh0[0]; s1 = sh1[0]; imin = shmin[0]; imax = shmax[0];
+  for (int p = threadIdx.x; p < hw; p += blockDim.x) {
+    const long long q = base + p;
+    float g = to_f<T>(gout[q * cs_out]) * inv_r;
+    if (p == imin) g += (s1 - s0) * inv_r;
+    if (p == imax) g -= s1 * inv_r;
+    gd[q * 8] = from_f<T>(g);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) gd[q * 8 + k] = from_f<T>(0.f);
+    float dot = 0.f;
+    for (int k = 0; k < ns; ++k) dot += to_f<T>(gout[q * cs_out + 1 + k]) * to_f<T>(out[q * cs_out + 1 + k]);
+    for (int k = 0; k < ss; ++k) {
+      float v = 0.f;
+      if (k < ns) v = to_f<T>(out[q * cs_out + 1 + k]) * (to_f<T>(gout[q * cs_out + 1 + k]) - dot);
+      gs[q * ss + k] = from_f<T>(v);
+    }
   }
 }
 
@@ -1185,6 +1306,17 @@ extern "C" int cgb_resize_nearest_fwd(const void* x, void* y, int32_t dtype, int
   DISPATCH_T(dtype, resize_nearest_kernel<T><<<grid_for(total), 256, 0, st>>>((const T*)x, (T*)y, total, hi,
                                                                              wi, ho, wo, c);)
   return after_launch("resize_nearest");
+}
+
+extern "C" int cgb_resize_nearest_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi, int32_t wi,
+                                      int32_t ho, int32_t wo, int32_t c, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(gy && gx, "resize_nearest_bwd: null pointer");
+  CGB_REQUIRE(c % 8 == 0 && c >= 8 && hi > 0 && wi > 0 && ho > 0 && wo > 0, "resize_nearest_bwd: bad shape (c=%d)", c);
+  const long long total = (long long)n * hi * wi * (c / 8);
+  DISPATCH_T(dtype, resize_nearest_bwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)gy, (T*)gx, total,
+                                                                                                  hi, wi, ho, wo, c);)
+  return after_launch("resize_nearest_bwd");
 }
 
 extern "C" int cgb_upsample_nearest_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi,
@@ -1512,13 +1644,7 @@ extern "C" int cgb_make_m_cond(const void* d, const void* s, const void* xr, flo
   CGB_REQUIRE(d && s && mm && out, "make_m_cond: null pointer");
   CGB_REQUIRE(ns >= 1 && ns <= ss && 1 + ns + (xr ? 3 : 0) <= cs_out && cs_out <= 24, "make_m_cond: bad channel counts");
   cudaStream_t st = (cudaStream_t)stream;
-  // mm <- {+inf, -inf} per sample
-  {
-    std::vector<float> init(2 * (size_t)n);
-    for (int i = 0; i < n; ++i) { init[2 * i] = 3.4e38f; init[2 * i + 1] = -3.4e38f; }
-    cudaMemcpyAsync(mm, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice, st);
-    cudaStreamSynchronize(st);  // init is a stack/heap buffer: make the copy complete before it goes away (tiny, inference only)
-  }
+  mm_init_kernel<<<(n + 255) / 256, 256, 0, st>>>(mm, n);   // mm <- {+inf, -inf} per sample, stream-ordered (no host sync)
   dim3 g1((hw + 255) / 256 < 64 ? (hw + 255) / 256 : 64, n);
   DISPATCH_T(dtype, minmax_c0_kernel<T><<<g1, 256, 0, st>>>((const T*)d, mm, hw, 8);)
   int r = after_launch("minmax_c0");
@@ -1527,4 +1653,14 @@ extern "C" int cgb_make_m_cond(const void* d, const void* s, const void* xr, flo
   DISPATCH_T(dtype, m_cond_kernel<T><<<grid_for(pixels), 256, 0, st>>>((const T*)d, (const T*)s, (const T*)xr, mm, (T*)out, pixels,
                                                                       hw, ss, ns, cs_out);)
   return after_launch("m_cond");
+}
+
+extern "C" int cgb_make_m_cond_bwd(const void* d, const void* out, const float* mm, const void* gout, void* gd, void* gs,
+                                   int32_t dtype, int32_t n, int32_t hw, int32_t ss, int32_t ns, int32_t cs_out, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(d && out && mm && gout && gd && gs, "make_m_cond_bwd: null pointer");
+  CGB_REQUIRE(ns >= 1 && ns <= ss && 1 + ns <= cs_out && cs_out <= 24 && n > 0 && hw > 0, "make_m_cond_bwd: bad channel counts");
+  DISPATCH_T(dtype, m_cond_bwd_kernel<T><<<n, 1024, 0, (cudaStream_t)stream>>>((const T*)d, (const T*)out, mm, (const T*)gout,
+                                                                               (T*)gd, (T*)gs, hw, ss, ns, cs_out);)
+  return after_launch("m_cond_bwd");
 }

@@ -113,7 +113,9 @@ class OmniGenerator(nn.Module):
 
     def make_m_cond(self, d, s, x=None):
         """generator.py:196-230: d, s NCHW fp32 predictions; returns the NCHW conditioning tensor (12 or 15 channels)."""
-        with torch.no_grad():
+        with self._grad_ctx():
+            if self.opts.gen.m.spade.detach:
+                d, s = d.detach(), s.detach()
             dt = self.storage_dtype
             ds, ss = ops.to_storage(d, dt), ops.to_storage(s, dt)
             xr = None

@@ -1,7 +1,8 @@
 """Flood-mask decoders (``climategan/masker.py``): MaskBaseDecoder (:25-56) = BaseDecoder (``blocks.py:206-318``) with
 the masker options, and MaskSpadeDecoder (:59-231; the paper / release configuration) for the deeplabv2 encoder: spectral-norm +
 BatchNorm ``fc_conv``, ``num_layers`` x [SPADEResnetBlock conditioned on make_m_cond's 15-channel tensor, nearest x2], spectral
-``mask_conv``.  The SPADE decoder is built for inference (its param-free norm is a BatchNorm read from running statistics)."""
+``mask_conv``.  Eval mode reads the SPADE layers' BatchNorm running statistics through the fused inference kernels; train mode
+runs them on batch statistics with a gradient into both the latent and the conditioning tensor."""
 from __future__ import annotations
 
 import torch
@@ -53,10 +54,18 @@ class MaskSpadeDecoder(nn.Module):
 
     def forward_storage(self, z, cond, z_depth=None):
         """masker.py:212-231.  z: storage [N,h,w,2048]; cond: NCHW fp32 conditioning from ``OmniGenerator.make_m_cond``."""
-        if self.training:
-            raise NotImplementedError("MaskSpadeDecoder is built for inference (eval mode) only")
         if cond is None:
             raise ValueError("MaskSpadeDecoder needs the conditioning tensor (OmniGenerator.make_m_cond)")
+        if self.training:
+            # autograd forwards (the caller decides whether a tape is recorded): train-mode BatchNorm in fc_conv and in every
+            # SPADE layer (batch statistics + running update), gradient into z AND into cond (gen.m.spade.detach = false)
+            y = self.fc_conv(z)
+            seg = ops.to_storage(cond, z.dtype)
+            for blk in self.spade_blocks:
+                seg_r = seg if seg.shape[1:3] == y.shape[1:3] else ops.resize_nearest(seg, y.shape[1], y.shape[2])
+                y = blk(y, seg_r)
+                y = self.upsample(y)
+            return self.mask_conv(y)
         with torch.no_grad():
             y = self.fc_conv.forward_infer(z)
             seg = ops.to_storage(cond, z.dtype)

@@ -103,17 +103,22 @@ class SPADE(nn.Module):
                 segmap = ops.resize_nearest(segmap, x.shape[1], x.shape[2])
             if k * k * sh.in_channels <= 64:
                 seg_col = ops.im2col(segmap, sh.in_channels, k, k // 2)
+        batch_stats = False
         if isinstance(self.param_free_norm, nn.BatchNorm2d):
             bn = self.param_free_norm
-            if self.training:
-                raise NotImplementedError("SPADE with a BatchNorm param-free norm (MaskSpadeDecoder) is built for inference only")
-            n, cs = x.shape[0], x.shape[-1]
-            mean = torch.zeros(n, cs, dtype=torch.float32, device=x.device)
-            rstd = torch.ones(n, cs, dtype=torch.float32, device=x.device)
-            mean[:, : self.norm_nc] = bn.running_mean
-            rstd[:, : self.norm_nc] = torch.rsqrt(bn.running_var + bn.eps)
+            if bn.training or bn.running_mean is None:
+                # train mode (norms.py:154-155, 177): statistics over (N, H, W), running statistics updated; the backward
+                # differentiates through the batch statistics
+                mean, rstd = ops.batchnorm_stats_update(x, bn)
+                batch_stats = True
+            else:
+                n, cs = x.shape[0], x.shape[-1]
+                mean = torch.zeros(n, cs, dtype=torch.float32, device=x.device)
+                rstd = torch.ones(n, cs, dtype=torch.float32, device=x.device)
+                mean[:, : self.norm_nc] = bn.running_mean
+                rstd[:, : self.norm_nc] = torch.rsqrt(bn.running_var + bn.eps)
         else:
             mean, rstd = stats if stats is not None else ops.instnorm_stats(x, self.param_free_norm.eps)
         seg_in, is_col = (seg_col, True) if seg_col is not None else (segmap, False)
         return ops.spade(x, mean, rstd, seg_in, sh.weight, sh.bias, self.mlp_gamma.weight, self.mlp_gamma.bias,
-                         self.mlp_beta.weight, self.mlp_beta.bias, act, slope, seg_is_col=is_col)
+                         self.mlp_beta.weight, self.mlp_beta.bias, act, slope, seg_is_col=is_col, batch_stats=batch_stats)

@@ -300,9 +300,12 @@ class _Spade(Function):
     """
 
     @staticmethod
-    def forward(ctx, x, mean, rstd, seg, w_sh, b_sh, w_g, b_g, w_b, b_b, act, slope, engine, seg_is_col):
+    def forward(ctx, x, mean, rstd, seg, w_sh, b_sh, w_g, b_g, w_b, b_b, act, slope, engine, seg_is_col, batch_stats=False):
         dt = x.dtype
         n, h, w_, cs = x.shape
+        # batch_stats: mean / rstd are [1, cs] statistics over (N, H, W) (the masker's BatchNorm flavour, norms.py:154-155) —
+        # the modulation kernels then see the batch as ONE sample of N*H*W pixels (same memory, NHWC)
+        ns_, hw_ = (1, n * h * w_) if batch_stats else (n, h * w_)
         c = w_g.shape[0]
         k = w_sh.shape[2]
         pad = k // 2
@@ -338,25 +341,24 @@ class _Spade(Function):
         wp_gb, bp_gb = cached_pack([w_g, w_b, b_g, b_b], ("spade_gb", dt, cs, nh), build_gb)
         gb = conv_fwd_raw(actv, wp_gb, bp_gb, None, g_gb)
         out = torch.empty_like(x)
-        check(_L().cgb_spade_modulate_fwd(_p(x), _p(mean), _p(rstd), _p(gb), _p(out), _DT[dt], n, h * w_, cs,
+        check(_L().cgb_spade_modulate_fwd(_p(x), _p(mean), _p(rstd), _p(gb), _p(out), _DT[dt], ns_, hw_, cs,
                                           act, slope, _st()), "spade_modulate_fwd")
-        ctx.save_for_backward(x, mean, rstd, seg, actv, gb, wp_gb)
-        ctx.meta = (act, slope, g_sh, g_gb, tuple(w_sh.shape), tuple(w_g.shape), c, cs, seg_is_col)
+        ctx.save_for_backward(x, mean, rstd, seg, actv, gb, wp_gb, wp_sh)
+        ctx.meta = (act, slope, g_sh, g_gb, tuple(w_sh.shape), tuple(w_g.shape), c, cs, seg_is_col, ns_, hw_)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        x, mean, rstd, seg, actv, gb, wp_gb = ctx.saved_tensors
-        act, slope, g_sh, g_gb, sh_shape, g_shape, c, cs, seg_is_col = ctx.meta
-        n, h, w_, _ = x.shape
+        x, mean, rstd, seg, actv, gb, wp_gb, wp_sh = ctx.saved_tensors
+        act, slope, g_sh, g_gb, sh_shape, g_shape, c, cs, seg_is_col, ns_, hw_ = ctx.meta
         dt = x.dtype
         gout = gout.contiguous()
         ggb = torch.empty_like(gb)
         gx = torch.empty_like(x)
-        sums = torch.zeros((n, cs, 2), dtype=torch.float64, device=x.device)
+        sums = torch.zeros((ns_, cs, 2), dtype=torch.float64, device=x.device)
         check(_L().cgb_spade_modulate_bwd(_p(x), _p(mean), _p(rstd), _p(gb), _p(gout), _p(ggb), _p(gx), _p(sums),
-                                          _DT[dt], n, h * w_, cs, act, slope, _st()), "spade_modulate_bwd")
-        check(_L().cgb_instnorm_bwd(_p(x), _p(mean), _p(rstd), _p(sums), _p(gx), _DT[dt], n, h * w_, cs, _st()),
+                                          _DT[dt], ns_, hw_, cs, act, slope, _st()), "spade_modulate_bwd")
+        check(_L().cgb_instnorm_bwd(_p(x), _p(mean), _p(rstd), _p(sums), _p(gx), _DT[dt], ns_, hw_, cs, _st()),
               "instnorm_bwd")
         # gamma||beta conv: weight grads + data grad (ReLU of mlp_shared fused as a mask)
         gwp_gb, gbp_gb = conv_wgrad_raw(actv, ggb, g_gb, True)
@@ -374,14 +376,38 @@ class _Spade(Function):
         gb_sh = gbp_sh[: sh_shape[0]].clone()
         if not ctx.needs_input_grad[0]:
             gx = None
-        return gx, None, None, None, gw_sh, gb_sh, gw_g, gb_g, gw_b, gb_b, None, None, None, None
+        gseg = None
+        if ctx.needs_input_grad[3]:
+            # differentiable conditioning (the masker's make_m_cond(d, s, x) with gen.m.spade.detach = false): dgrad of mlp_shared
+            if seg_is_col:
+                raise NotImplementedError("SPADE: gradient w.r.t. an im2col'd conditioning tensor is not built")
+            gseg = conv_dgrad_raw(gactv, wp_sh, tuple(seg.shape), g_sh)
+        return gx, None, None, gseg, gw_sh, gb_sh, gw_g, gb_g, gw_b, gb_b, None, None, None, None, None
 
 
 def spade(x, mean, rstd, seg, w_sh, b_sh, w_g, b_g, w_b, b_b, act=_lib.ACT_NONE, slope=0.2,
-          engine=_lib.ENGINE_AUTO, seg_is_col=False):
+          engine=_lib.ENGINE_AUTO, seg_is_col=False, batch_stats=False):
     """seg: conditioning storage tensor at x's resolution, or (seg_is_col) its im2col patches from
-    :func:`im2col` — then SPADE.mlp_shared runs as one K=round8(9*cond_nc) GEMM."""
-    return _Spade.apply(x, mean, rstd, seg, w_sh, b_sh, w_g, b_g, w_b, b_b, act, slope, engine, seg_is_col)
+    :func:`im2col` — then SPADE.mlp_shared runs as one K=round8(9*cond_nc) GEMM.  batch_stats: mean / rstd are [1, Cs]
+    statistics over the whole batch (train-mode BatchNorm flavour); the backward differentiates through them too."""
+    return _Spade.apply(x, mean, rstd, seg, w_sh, b_sh, w_g, b_g, w_b, b_b, act, slope, engine, seg_is_col, batch_stats)
+
+
+def batchnorm_stats_update(x, bn):
+    """Train-mode statistics of a parameter-free ``nn.BatchNorm2d`` (SPADE's batch flavour): per-channel mean and
+    1/sqrt(biased var + eps) over (N, H, W) as [1, Cs] tensors, with the running-statistics update F.batch_norm does
+    (momentum, unbiased variance, num_batches_tracked)."""
+    _chk_storage(x)
+    n, h, w, cs = x.shape
+    mean, rstd = instnorm_stats(x.view(1, n * h, w, cs), bn.eps)
+    if bn.track_running_stats and bn.running_mean is not None:
+        c = bn.running_mean.numel()
+        momentum = 0.1 if bn.momentum is None else bn.momentum
+        _BEPOCH[0] += 1   # folded eval-mode packings built from running statistics are stale
+        check(_L().cgb_bn_update_running(_p(mean), _p(rstd), _p(bn.running_mean), _p(bn.running_var), c, n * h * w,
+                                         float(momentum), float(bn.eps), _st()), "bn_update_running")
+        bn.num_batches_tracked.add_(1)
+    return mean, rstd
 
 
 class _ResizeNearest(Function):
@@ -398,11 +424,13 @@ class _ResizeNearest(Function):
     @staticmethod
     def backward(ctx, gy):
         n, hi, wi, c = ctx.shape
-        if ctx.f < 1:
-            raise NotImplementedError("backward of nearest resize is only implemented for integer up-scaling")
         gy = gy.contiguous()
         gx = torch.empty(ctx.shape, dtype=gy.dtype, device=gy.device)
-        check(_L().cgb_upsample_nearest_bwd(_p(gy), _p(gx), _DT[gy.dtype], n, hi, wi, ctx.f, c, _st()), "upsample_bwd")
+        if ctx.f >= 1:
+            check(_L().cgb_upsample_nearest_bwd(_p(gy), _p(gx), _DT[gy.dtype], n, hi, wi, ctx.f, c, _st()), "upsample_bwd")
+        else:   # any other ratio (e.g. the masker's conditioning tensor down-sized to the latent's resolution)
+            check(_L().cgb_resize_nearest_bwd(_p(gy), _p(gx), _DT[gy.dtype], n, hi, wi, gy.shape[1], gy.shape[2], c, _st()),
+                  "resize_nearest_bwd")
         return gx, None, None
 
 
@@ -1127,18 +1155,41 @@ def batchnorm_act(x, bn, residual=None, act=_lib.ACT_NONE, slope=0.2):
                                bn.eps, act, slope)
 
 
+class _MakeMCond(Function):
+    """generator.py:196-230 on storage tensors; differentiable w.r.t. d and s (gen.m.spade.detach is false by default,
+    defaults.yaml:182), not w.r.t. the resized image."""
+
+    @staticmethod
+    def forward(ctx, d, s, xr, ns):
+        _chk_storage(d)
+        _chk_storage(s)
+        n, h, w, ss = s.shape
+        c_out = 1 + ns + (3 if xr is not None else 0)
+        cs_out = round8(c_out)
+        mm = torch.empty((n, 2), dtype=torch.float32, device=d.device)
+        out = torch.empty((n, h, w, cs_out), dtype=d.dtype, device=d.device)
+        check(_L().cgb_make_m_cond(_p(d), _p(s), _p(xr), _p(mm), _p(out), _DT[d.dtype], n, h * w, ss, ns, cs_out, _st()),
+              "make_m_cond")
+        ctx.save_for_backward(d, out, mm)
+        ctx.meta = (ss, ns, cs_out)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        d, out, mm = ctx.saved_tensors
+        ss, ns, cs_out = ctx.meta
+        n, h, w, _ = out.shape
+        gout = gout.contiguous()
+        gd = torch.empty_like(d)
+        gs = torch.empty((n, h, w, ss), dtype=out.dtype, device=out.device)
+        check(_L().cgb_make_m_cond_bwd(_p(d), _p(out), _p(mm), _p(gout), _p(gd), _p(gs), _DT[out.dtype], n, h * w, ss, ns, cs_out,
+                                       _st()), "make_m_cond_bwd")
+        return gd, gs, None, None
+
+
 def make_m_cond(d, s, xr, ns):
     """generator.py:196-230: cat[normalize(d), softmax(s, dim=1), x bilinear-resized] -> [N,H,W,round8(1+ns+3)]."""
-    _chk_storage(d)
-    _chk_storage(s)
-    n, h, w, ss = s.shape
-    c_out = 1 + ns + (3 if xr is not None else 0)
-    cs_out = round8(c_out)
-    mm = torch.empty((n, 2), dtype=torch.float32, device=d.device)
-    out = torch.empty((n, h, w, cs_out), dtype=d.dtype, device=d.device)
-    check(_L().cgb_make_m_cond(_p(d), _p(s), _p(xr), _p(mm), _p(out), _DT[d.dtype], n, h * w, ss, ns, cs_out, _st()),
-          "make_m_cond")
-    return out
+    return _MakeMCond.apply(d, s, xr.detach() if xr is not None else None, ns)
 
 
 # ------------------------------------------------------------------------------------------------

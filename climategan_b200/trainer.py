@@ -217,7 +217,8 @@ class Trainer:
                 elif task == "m":
                     cond = None
                     if self.opts.gen.m.use_spade:
-                        raise NotImplementedError("gen.m.use_spade (MaskSpadeDecoder) is not built")
+                        # trainer.py:1235-1239 (the .clone() there only shields d_pred / s_pred from in-place edits)
+                        cond = self.G.make_m_cond(d_pred, s_pred, x)
                     loss, _ = self.masker_m_loss(x, z, target, domain, "G", cond=cond, z_depth=z_depth, depth_preds=d_pred)
                     m_loss = m_loss + loss
                     self.logger.losses.gen.task["m"][domain] = loss.detach()
@@ -404,9 +405,12 @@ class Trainer:
                     step_loss, s_pred = self._no_g_tape(self.masker_s_loss, x, z, d_pred, z_depth, None, domain, for_="D")
                     disc_loss["s"]["Advent"] = disc_loss["s"]["Advent"] + step_loss * lam.advent.adv_main
                 if "m" in batch["data"] and "m" in self.opts.tasks:
-                    if "d" in self.opts.tasks and self.opts.gen.m.use_dada and d_pred is None:
+                    if "d" in self.opts.tasks and (self.opts.gen.m.use_spade or self.opts.gen.m.use_dada):   # trainer.py:1128-1136
                         with torch.no_grad():
-                            d_pred, z_depth = self.G.decode_d(z)
+                            if d_pred is None:
+                                d_pred, z_depth = self.G.decode_d(z)
+                            if self.opts.gen.m.use_spade:
+                                cond = self.G.make_m_cond(d_pred, s_pred, x)
                     step_loss, _ = self._no_g_tape(self.masker_m_loss, x, z, None, domain, for_="D", cond=cond,
                                                    z_depth=z_depth, depth_preds=d_pred)
                     disc_loss["m"]["Advent"] = disc_loss["m"]["Advent"] + step_loss * lam.advent.adv_main

@@ -138,8 +138,10 @@ def default_masker_opts(tasks=("m", "s", "d"), nblocks=(3, 4, 23, 3), size=640, 
     return o
 
 
-def full_opts(nblocks=(2, 2, 3, 2), size=128, latent=16, n_up=4, ndf=8, n_layers=3, num_d=2, tasks=("d", "s", "m", "p")):
-    """shared/trainer/defaults.yaml values on a small network (deeplabv2 encoder, as the north star names)."""
+def full_opts(nblocks=(2, 2, 3, 2), size=128, latent=16, n_up=4, ndf=8, n_layers=3, num_d=2, tasks=("d", "s", "m", "p"),
+              use_spade=False):
+    """shared/trainer/defaults.yaml values on a small network (deeplabv2 encoder, as the north star names).  use_spade: the
+    paper / release masker (MaskSpadeDecoder conditioned on make_m_cond(d, s, x), defaults.yaml:166-186)."""
     with_p = "p" in tasks
     o = default_masker_opts(tasks=tuple(t for t in tasks if t != "p"), nblocks=nblocks, size=size, with_painter=with_p,
                             latent_dim=latent, spade_n_up=n_up, ndf=ndf, n_layers=n_layers, num_D=num_d)
@@ -154,6 +156,9 @@ def full_opts(nblocks=(2, 2, 3, 2), size=128, latent=16, n_up=4, ndf=8, n_layers
     o.gen.m.use_ground_intersection = True
     o.gen.m.use_pl4m = False
     o.gen.m.use_proj = True
+    if use_spade:
+        o.gen.m.use_spade = True
+        o.gen.m.spade.activations = Dict(all_lrelu=True)
     o.gen.p.pl4m_epoch = 49
     o.gen.opt.lr = Dict(default=0.00005)
     o.dis.soft_shift = 0.0

@@ -166,6 +166,10 @@ int cgb_resize_nearest_fwd(const void* x, void* y, int32_t dtype, int32_t n, int
 /* adjoint of the above for integer up-scaling factors (ho = hi*f): gx = sum over the f*f replicas */
 int cgb_upsample_nearest_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi, int32_t wi,
                              int32_t f, int32_t c, void* stream);
+/* adjoint of cgb_resize_nearest_fwd for any size ratio (the masker's SPADE layers down-size a differentiable conditioning
+ * tensor, norms.py:179), gather form: gx[iy,ix] = sum of gy over the output pixels whose nearest source is (iy,ix) */
+int cgb_resize_nearest_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t hi, int32_t wi, int32_t ho, int32_t wo,
+                           int32_t c, void* stream);
 
 /* im2col of a few-channel NHWC tensor: y[n,oy,ox, tap*c + ch] = x[n, oy+dy*dil-pad, ox+dx*dil-pad, ch] (zero outside,
  * zero for channels >= k*k*c).  Turns the 3-channel SPADE.mlp_shared 3x3 conv (norms.py:164-166) into a K=32 1x1
@@ -193,6 +197,12 @@ int cgb_channel_mean(const void* x, void* y, int32_t dtype, int64_t pixels, int3
 int cgb_mul(const void* a, const void* b, void* y, int32_t dtype, int64_t count, void* stream);
 int cgb_make_m_cond(const void* d, const void* s, const void* xr, float* mm, void* out, int32_t dtype, int32_t n, int32_t hw,
                     int32_t ss, int32_t ns, int32_t cs_out, void* stream);
+/* Adjoint of cgb_make_m_cond w.r.t. d and s (gen.m.spade.detach = false, defaults.yaml:182; generator.py:217-219): through
+ * the per-sample min-max normalisation (first-occurrence argmin / argmax, as torch.min / max with dim) and the softmax.
+ * d [n,hw,8], out / gout [n,hw,cs_out] (the forward's output and its gradient), mm = the forward's per-sample {min,max};
+ * writes gd [n,hw,8] and gs [n,hw,ss] (pad channels zero). */
+int cgb_make_m_cond_bwd(const void* d, const void* out, const float* mm, const void* gout, void* gd, void* gs, int32_t dtype,
+                        int32_t n, int32_t hw, int32_t ss, int32_t ns, int32_t cs_out, void* stream);
 
 /* ---- masker training path -----------------------------------------------------------------
  * nn.BatchNorm2d in TRAIN mode (batch statistics; resnetmulti_v2.py:16-18,30-34,72 freeze only weight/bias;

@@ -266,7 +266,7 @@ def _sample(a, cap=8192):
     return a[::k].copy()
 
 
-def run_full_step_case(name="full_step", batch=2, size=128):
+def run_full_step_case(name="full_step", batch=2, size=128, tasks=("d", "s", "m", "p"), use_spade=False):
     """Two iterations of the reference's OWN ``Trainer.update_G`` / ``update_D`` (trainer.py:989-1032) on tasks [d,s,m,p]
     — deeplabv2 masker (ResNet [2,2,3,2], train-mode BatchNorm, dropout p=0) + SPADE painter + all three discriminators —
     driven as ``run_epoch`` does (oracle/ref_trainer.py).  Stores every logged loss, the gradient norm of every parameter
@@ -274,16 +274,27 @@ def run_full_step_case(name="full_step", batch=2, size=128):
     second iteration (ExtraAdam extrapolation then step)."""
     from oracle import ref_trainer as rt
 
-    opts = rt.full_opts(size=size)
+    opts = rt.full_opts(size=size, tasks=tasks, use_spade=use_spade)
+    if use_spade:
+        blocks_mod = refshim.load("blocks")
+        blocks_mod.SPADEResnetBlock.cuda = lambda self, *a, **k: self   # masker.py:196 hard-codes .cuda() (SURVEY.md §8c patch 1)
     t = rt.build_reference_trainer(opts, size)
     g_shapes, d_shapes, v_shapes = rt.load_weights(t)
     mdb = rt.synth_batch(opts, batch, size, seed=7)
     arrays = {}
     logs = []
     full_g = ["encoder.model.conv1.weight", "encoder.model.layer3.1.conv2.weight", "decoders.d.enc4_2.conv.weight", "decoders.d.enc4_2.norm.weight",
-              "decoders.s.aspp.aspp3.atrous_conv.weight", "decoders.s.conv.8.bias", "decoders.m.proj_conv.conv.module.weight_bar",
-              "decoders.m.model.6.conv.module.weight_bar", "painter.conv_img.weight"]
-    full_d = ["m.Advent.0.module.weight_bar", "s.Advent.8.module.weight_bar", "p.discriminator_0.model0.0.module.weight_bar"]
+              "decoders.s.aspp.aspp3.atrous_conv.weight", "decoders.s.conv.8.bias"]
+    if use_spade:   # MaskSpadeDecoder: fc_conv, a SPADE layer's three convs, a spectral conv of a block, the mask head
+        full_g += ["decoders.m.fc_conv.conv.module.weight_bar", "decoders.m.spade_blocks.0.norm_0.mlp_shared.0.weight",
+                   "decoders.m.spade_blocks.1.norm_1.mlp_gamma.weight", "decoders.m.spade_blocks.2.norm_s.mlp_beta.bias",
+                   "decoders.m.spade_blocks.1.conv_0.module.weight_bar", "decoders.m.mask_conv.conv.module.weight_bar"]
+    else:
+        full_g += ["decoders.m.proj_conv.conv.module.weight_bar", "decoders.m.model.6.conv.module.weight_bar"]
+    full_d = ["m.Advent.0.module.weight_bar", "s.Advent.8.module.weight_bar"]
+    if "p" in tasks:
+        full_g += ["painter.conv_img.weight"]
+        full_d += ["p.discriminator_0.model0.0.module.weight_bar"]
     for it in range(2):
         for p_ in t.D.parameters():
             p_.requires_grad = False
@@ -304,15 +315,22 @@ def run_full_step_case(name="full_step", batch=2, size=128):
         t.logger.global_step += 1
         logs.append(_flatten_logs(t.logger.losses.to_dict()))
     gsd, dsd = t.G.state_dict(), t.D.state_dict()
-    for k in full_g + ["encoder.model.bn1.running_mean", "encoder.model.layer4.0.bn2.running_var", "decoders.s.aspp.global_avg_pool.2.running_var",
-                       "decoders.d.enc4_1.norm.running_mean", "decoders.m.model.0.model.1.model.0.conv.module.weight_u"]:
+    finals = ["encoder.model.bn1.running_mean", "encoder.model.layer4.0.bn2.running_var", "decoders.s.aspp.global_avg_pool.2.running_var",
+              "decoders.d.enc4_1.norm.running_mean"]
+    if use_spade:
+        finals += ["decoders.m.spade_blocks.0.norm_0.param_free_norm.running_mean", "decoders.m.spade_blocks.2.norm_1.param_free_norm.running_var",
+                   "decoders.m.fc_conv.norm.running_var", "decoders.m.spade_blocks.1.conv_1.module.weight_u"]
+    else:
+        finals += ["decoders.m.model.0.model.1.model.0.conv.module.weight_u"]
+    for k in full_g + finals:
         arrays["G.final::" + k] = _sample(gsd[k].numpy())
     for k in full_d:
         arrays["D.final::" + k] = _sample(dsd[k].numpy())
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
     meta = {"case": name, "batch": batch, "size": size, "seeds": {"G": 21, "D": 22, "vgg": 23, "inputs": 7},
             "g_shapes": [[k, list(s_)] for k, s_ in g_shapes], "d_shapes": [[k, list(s_)] for k, s_ in d_shapes],
-            "v_shapes": [[k, list(s_)] for k, s_ in v_shapes], "g_param_names": [k for k, _ in t.G.named_parameters()],
+            "tasks": list(tasks), "use_spade": bool(use_spade),
+            "v_shapes": [[k, list(s_)] for k, s_ in (v_shapes or [])], "g_param_names": [k for k, _ in t.G.named_parameters()],
             "d_param_names": [k for k, _ in t.D.named_parameters()], "logs": logs, "full_g": full_g, "full_d": full_d,
             "reference": "cc-ai/climategan @ /root/reference: climategan.trainer.Trainer.update_G/update_D (unmodified), CPU, torch "
                          + torch.__version__}
@@ -459,6 +477,7 @@ if __name__ == "__main__":
     run_step_case()
     run_masker_case()
     run_full_step_case()
+    run_full_step_case(name="masker_step_spade", tasks=("d", "s", "m"), use_spade=True)
     run_infer_all_case()
     run_masker_spade_case()
     run_masker_v3_case()

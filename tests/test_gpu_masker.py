@@ -110,5 +110,8 @@ def test_masker_spade_decoder_matches_reference_golden(cuda, dtype):
     assert o1["m"].shape == (meta["batch"], 1, meta["size"], meta["size"])
     assert rel_max(o1["m"], torch.from_numpy(g["m1"])) < tol, rel_max(o1["m"], torch.from_numpy(g["m1"]))
     assert rel_max(o2["m"], torch.from_numpy(g["m2"])) < tol, rel_max(o2["m"], torch.from_numpy(g["m2"]))
-    with pytest.raises(NotImplementedError):
-        G.train().decode(x=x.to(cuda))
+    # train mode runs (batch-statistics SPADE, running statistics updated); its parity is tests/test_gpu_full_step.py's
+    rv = G.decoders["m"].spade_blocks[0].norm_0.param_free_norm.running_var.clone()
+    o3 = G.train().decode(x=x.to(cuda))
+    assert o3["m"].shape == o1["m"].shape and bool(torch.isfinite(o3["m"]).all())
+    assert not torch.equal(rv, G.decoders["m"].spade_blocks[0].norm_0.param_free_norm.running_var)
