@@ -3,6 +3,7 @@ constructor signatures and state_dict keys), operating on NHWC storage tensors t
 """
 from __future__ import annotations
 
+import torch
 import torch.nn as nn
 
 from . import _lib, ops
@@ -152,7 +153,8 @@ class SPADEResnetBlock(nn.Module):
     def forward(self, x, seg, seg_col=None):
         """x: storage [N,H,W,round8(fin)] ; seg: storage conditioning at the same H,W ; seg_col: its im2col
         patches (ops.im2col), computed here when not supplied and shared by the block's 2-3 SPADE layers."""
-        if seg_col is None:
+        if seg_col is None and not (torch.is_grad_enabled() and seg.requires_grad):
+            # (a conditioning tensor that needs a gradient takes the direct 3x3 mlp_shared path: im2col has no adjoint here)
             sh = self.norm_0.mlp_shared[0]
             if sh.kernel_size[0] ** 2 * sh.in_channels <= 64:
                 seg_col = ops.im2col(seg, sh.in_channels, sh.kernel_size[0], sh.kernel_size[0] // 2)

@@ -50,15 +50,17 @@ class OmniGenerator(nn.Module):
         """generator.py (no_z=True in defaults.yaml:148 -> None)."""
         if self.opts.gen.p.no_z:
             return None
-        raise NotImplementedError("gen.p.no_z=False is not built")
+        z = torch.empty(batch_size, self.opts.gen.p.latent_dim, self.painter.z_h, self.painter.z_w,
+                        device=device).normal_(mean=0, std=1.0)   # generator.py:183-194
+        return z.half() if force_half else z
 
     def paint(self, m, x, no_paste=False):
         """generator.py:279-297: fake = painter(z, x*(1-m)); return x*(1-m) + fake*m."""
         z_paint = self.sample_painter_z(x.shape[0], x.device)
-        assert z_paint is None
         p = self.painter
         cond = ops.mask_cond(x, m.to(x.dtype), p.storage_dtype)
-        fake = ops.from_storage(p.forward_storage(cond), 3)
+        z_st = ops.to_storage(z_paint.float(), p.storage_dtype) if z_paint is not None else None
+        fake = ops.from_storage(p.forward_storage(cond, z_st), 3)
         if self.opts.gen.p.paste_original_content and not no_paste:
             return ops.paste(x, m.to(x.dtype), fake)
         return fake

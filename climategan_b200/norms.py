@@ -101,7 +101,7 @@ class SPADE(nn.Module):
         if seg_col is None:
             if segmap.shape[1:3] != x.shape[1:3]:
                 segmap = ops.resize_nearest(segmap, x.shape[1], x.shape[2])
-            if k * k * sh.in_channels <= 64:
+            if k * k * sh.in_channels <= 64 and not (torch.is_grad_enabled() and segmap.requires_grad):
                 seg_col = ops.im2col(segmap, sh.in_channels, k, k // 2)
         batch_stats = False
         if isinstance(self.param_free_norm, nn.BatchNorm2d):

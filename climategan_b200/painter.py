@@ -10,7 +10,7 @@ import torch.nn as nn
 
 from . import _lib, ops
 from .blocks import InterpolateNearest2d, SPADEResnetBlock
-from .norms import SpectralNorm  # noqa: F401  (re-exported like the reference module)
+from .norms import SpectralNorm, conv_weight_bias
 
 
 def create_painter(opts, no_init=False, verbose=0):
@@ -50,8 +50,9 @@ class PainterSpadeDecoder(nn.Module):
         self.final_nc = self.z_nc // 2 ** (spade_n_up - 2)
         self.final_spade = block(self.final_nc, self.final_nc)
         self.final_shortcut = None
-        if opts.gen.p.use_final_shortcut:
-            raise NotImplementedError("gen.p.use_final_shortcut (off in defaults.yaml:155) is not built")
+        if opts.gen.p.use_final_shortcut:   # painter.py:101-109: the last block is conditioned on a learned 3-channel map of y
+            self.final_shortcut = nn.Sequential(SpectralNorm(nn.Conv2d(self.final_nc, 3, 1)), nn.BatchNorm2d(3),
+                                                nn.LeakyReLU(0.2, True))
         self.conv_img = nn.Conv2d(self.final_nc, 3, 3, padding=1)
         self.upsample = InterpolateNearest2d(scale_factor=2)
 
@@ -69,8 +70,9 @@ class PainterSpadeDecoder(nn.Module):
             self.z_w = self.z_w // (2 ** self.spade_n_up)
 
     # -- storage-level forward (used by OmniGenerator.paint to skip a layout round trip) --------
-    def forward_storage(self, cond_st: torch.Tensor) -> torch.Tensor:
-        """cond_st: storage [N,H,W,8] conditioning.  Returns storage [N,H,W,8] holding tanh(conv_img)."""
+    def forward_storage(self, cond_st: torch.Tensor, z_st: torch.Tensor = None) -> torch.Tensor:
+        """cond_st: storage [N,H,W,8] conditioning; z_st: optional storage latent [N,z_h,z_w,round8(latent_dim)] (gen.p.no_z =
+        false: OmniGenerator.sample_painter_z) replacing fc(cond).  Returns storage [N,H,W,8] holding tanh(conv_img)."""
         assert self.z_h is not None and self.z_w is not None
         segs = {}
 
@@ -88,7 +90,10 @@ class PainterSpadeDecoder(nn.Module):
                 cols[hw] = ops.im2col(seg, 3, 3, 1)
             return blk(y, seg, cols[hw])
 
-        z = ops.conv2d(seg_at(self.z_h, self.z_w), self.fc.weight, self.fc.bias, pad=1)
+        if z_st is None:   # painter.py:150-152
+            z = ops.conv2d(seg_at(self.z_h, self.z_w), self.fc.weight, self.fc.bias, pad=1)
+        else:
+            z = z_st
         y = run(self.head_0, z)
         y = self.upsample(y)
         y = run(self.G_middle_0, y)
@@ -97,12 +102,19 @@ class PainterSpadeDecoder(nn.Module):
         for up in self.up_spades:
             y = self.upsample(y)
             y = run(up, y)
-        y = run(self.final_spade, y)
+        if self.final_shortcut is not None:
+            # painter.py:163-164: cond <- lrelu(BatchNorm(SN conv1x1(y))), a DIFFERENTIABLE conditioning map: the block takes the
+            # direct 3x3 mlp_shared path (SPADE's gradient w.r.t. the conditioning), not the shared im2col patches
+            sn, bn = self.final_shortcut[0], self.final_shortcut[1]
+            w_fs, b_fs = conv_weight_bias(sn)
+            c_st = ops.batchnorm_act(ops.conv2d(y, w_fs, b_fs), bn, None, _lib.ACT_LRELU, 0.2)
+            y = self.final_spade(y, c_st)
+        else:
+            y = run(self.final_spade, y)
         y = ops.activation(y, _lib.ACT_LRELU, 0.2)
         return ops.conv2d(y, self.conv_img.weight, self.conv_img.bias, pad=1, act=_lib.ACT_TANH)
 
     def forward(self, z, cond):
-        if z is not None:
-            raise NotImplementedError("painter with an explicit z (gen.p.no_z=False) is not built; defaults use no_z")
         cond_st = ops.to_storage(cond, self.storage_dtype)
-        return ops.from_storage(self.forward_storage(cond_st), 3)
+        z_st = ops.to_storage(z, self.storage_dtype) if z is not None else None
+        return ops.from_storage(self.forward_storage(cond_st, z_st), 3)

@@ -82,6 +82,50 @@ def run_case(name, latent_dim, n_up, batch, size):
           os.path.getsize(os.path.join(HERE, name + ".npz")))
 
 
+def run_painter_z_case(name="painter_z_shortcut", latent_dim=40, n_up=3, batch=2, size=32):
+    """The painter's two non-default options together: an explicit latent z (gen.p.no_z = false, generator.py:179-194 /
+    painter.py:149-152: fc(cond) is bypassed) and gen.p.use_final_shortcut (painter.py:101-109, 163-164: the last SPADE block is
+    conditioned on lrelu(BatchNorm(SN conv1x1(y))), a learned map that receives a gradient through SPADE's mlp_shared).
+    ``painter(z, cond)`` is called directly with a seeded z (paint() would draw z from the global RNG)."""
+    painter_mod, generator_mod = refshim.load("painter", "generator")
+    opts = default_painter_opts(latent_dim=latent_dim, spade_n_up=n_up)
+    opts.gen.p.no_z = False
+    opts.gen.p.use_final_shortcut = True
+    torch.manual_seed(0)
+    G = generator_mod.OmniGenerator(opts)
+    G.painter.set_latent_shape(size, True)
+    shapes = [(k, tuple(v.shape)) for k, v in G.painter.state_dict().items()]
+    G.painter.load_state_dict(fill_state_dict(shapes, seed=4321), strict=True)
+    G.train()
+    x, m, target = synth_inputs(batch, size, seed=98)
+    z = torch.randn(batch, latent_dim, G.painter.z_h, G.painter.z_w, generator=torch.Generator().manual_seed(5))
+    out = G.painter(z, x * (1.0 - m))
+    loss = torch.nn.L1Loss()(out, target)
+    loss.backward()
+    sd_after = {k: v.clone() for k, v in G.painter.state_dict().items()}
+    G.eval()
+    with torch.no_grad():
+        out_eval = G.painter(z, x * (1.0 - m))
+    grads = {k: p.grad for k, p in G.painter.named_parameters() if p.grad is not None}
+    full = ["final_shortcut.0.module.weight_bar", "final_shortcut.1.weight", "final_shortcut.1.bias", "conv_img.weight",
+            "final_spade.norm_0.mlp_shared.0.weight", "final_spade.norm_1.mlp_gamma.weight", "head_0.conv_0.module.weight_bar",
+            "up_spades.0.norm_s.mlp_beta.bias"]
+    arrays = {"z": z.numpy(), "out": out.detach().numpy(), "out_eval": out_eval.numpy(), "loss": np.float32(loss.item()),
+              "grad_norms": np.array([float(grads[k].norm()) for k, _ in shapes if k in grads], dtype=np.float64),
+              "running_mean": sd_after["final_shortcut.1.running_mean"].numpy(),
+              "running_var": sd_after["final_shortcut.1.running_var"].numpy()}
+    for k in full:
+        arrays["grad::" + k] = grads[k].numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+    meta = {"case": name, "latent_dim": latent_dim, "spade_n_up": n_up, "batch": batch, "size": size, "weight_seed": 4321,
+            "input_seed": 98, "shapes": [[k, list(s_)] for k, s_ in shapes], "grad_keys": [k for k, _ in shapes if k in grads],
+            "full": full, "reference": "cc-ai/climategan @ /root/reference (climategan/{painter,generator,blocks,norms}.py)",
+            "torch": torch.__version__}
+    with open(os.path.join(HERE, name + ".json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print(name, "loss", float(loss), "fc grad present:", "fc.weight" in grads, "npz bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
+
+
 def run_disc_case(name="disc_small", ndf=8, n_layers=3, num_d=2, batch=2, size=64):
     """Painter discriminator D["p"] on cat(real, fake) + GANLoss(BCE) + FeatMatchLoss, as Trainer.get_painter_loss
     assembles them (climategan/trainer.py:1362-1383) — generator-side gradients w.r.t. the fake image and D's params."""
@@ -414,7 +458,7 @@ def v3_opts(size=128, nblocks=(2, 2, 3, 2)):
     return opts
 
 
-def run_masker_v3_case(name="masker_v3", nblocks=(2, 2, 3, 2), batch=2, size=128):
+def run_masker_v3_case(name="masker_v3", nblocks=(2, 2, 3, 2), batch=2, size=128, use_spade=False):
     """The reference's DEFAULT masker architecture (defaults.yaml:101,136: deeplabv3 encoder + decoder, ResNet backbone at
     output stride 8, mask decoder with low-level features), shallow copy [2,2,3,2] of the same architecture:
     (i) eval-mode OmniGenerator.decode; (ii) train-mode encode + the three decoders, a fixed random linear functional of
@@ -423,6 +467,13 @@ def run_masker_v3_case(name="masker_v3", nblocks=(2, 2, 3, 2), batch=2, size=128
     deeplab_mod.ResNet101 = lambda output_stride=8, BatchNorm=None, verbose=0, no_init=False: resnet_mod.ResNet(
         resnet_mod.Bottleneck, list(nblocks), output_stride, BatchNorm, verbose=verbose, no_init=no_init)
     opts = v3_opts(size, nblocks)
+    if use_spade:   # deeplabv3 encoder + MaskSpadeDecoder (low-level / high-level / merge convs, masker.py:118-158, 212-224)
+        from climategan_b200.utils import Dict
+
+        refshim.load("blocks").SPADEResnetBlock.cuda = lambda self, *a, **k: self   # masker.py:196 (SURVEY.md §8c patch 1)
+        opts.gen.m.use_spade = True
+        opts.gen.m.use_proj = True
+        opts.gen.m.spade.activations = Dict(all_lrelu=True)
     torch.manual_seed(0)
     G = generator_mod.OmniGenerator(opts, no_init=True)
     shapes = [(k, tuple(v.shape)) for k, v in G.state_dict().items()]
@@ -440,7 +491,10 @@ def run_masker_v3_case(name="masker_v3", nblocks=(2, 2, 3, 2), batch=2, size=128
     z = G.encode(x)
     d, z_depth = G.decoders["d"](z)
     s_ = G.decoders["s"](z, z_depth)
-    m = G.decoders["m"](z, z_depth=z_depth)
+    if use_spade:
+        m = G.decoders["m"](z, G.make_m_cond(d, s_, x), z_depth)   # conditioning NOT detached (defaults.yaml:182)
+    else:
+        m = G.decoders["m"](z, z_depth=z_depth)
     wd, ws, wm = (torch.from_numpy(rs.standard_normal(size=t.shape).astype(np.float32)) for t in (d, s_, m))
     loss = (d * wd).mean() + (s_ * ws).mean() + (m * wm).mean()
     loss.backward()
@@ -452,14 +506,21 @@ def run_masker_v3_case(name="masker_v3", nblocks=(2, 2, 3, 2), batch=2, size=128
     full = ["encoder.conv1.weight", "encoder.layer2.0.conv2.weight", "encoder.layer4.2.conv2.weight", "encoder.layer3.0.bn1.weight",
             "decoders.s.aspp.conv_out.conv.weight", "decoders.s.decoder.conv_low.conv.bias", "decoders.s.decoder.conv_out.weight",
             "decoders.m.low_level_conv.conv.module.weight_bar", "decoders.m.merge_feats_conv.conv.module.weight_bar"]
+    if use_spade:
+        full += ["decoders.m.high_level_conv.conv.module.weight_bar", "decoders.m.spade_blocks.0.norm_s.mlp_gamma.weight",
+                 "decoders.m.spade_blocks.2.conv_1.module.weight_bar", "decoders.d.upsample.2.weight"]
     for k in full:
         arrays["grad::" + k] = _sample(gp[k].grad.detach().numpy())
     sd = G.state_dict()
-    for k in ("encoder.bn1.running_mean", "encoder.layer4.1.bn2.running_var", "decoders.s.aspp.conv_out.bn.running_var"):
+    finals = ["encoder.bn1.running_mean", "encoder.layer4.1.bn2.running_var", "decoders.s.aspp.conv_out.bn.running_var"]
+    if use_spade:
+        finals += ["decoders.m.spade_blocks.1.norm_0.param_free_norm.running_var", "decoders.m.merge_feats_conv.norm.running_mean"]
+    for k in finals:
         arrays["final::" + k] = sd[k].numpy().copy()
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
     meta = {"case": name, "nblocks": list(nblocks), "batch": batch, "size": size, "weight_seed": 79, "input_seed": 6,
             "functional_seed": 123, "shapes": [[k, list(s__)] for k, s__ in shapes], "param_names": names, "full": full,
+            "use_spade": bool(use_spade),
             "reference": "cc-ai/climategan @ /root/reference (generator, deeplab/resnet101_v3, deeplab/deeplab_v3, depth, masker, blocks)",
             "torch": torch.__version__}
     with open(os.path.join(HERE, name + ".json"), "w") as f:
@@ -473,6 +534,7 @@ if __name__ == "__main__":
         sys.exit("reference tree not available; goldens can only be regenerated in the build container")
     for name, cfg in CASES.items():
         run_case(name, *cfg)
+    run_painter_z_case()
     run_disc_case()
     run_step_case()
     run_masker_case()
@@ -481,3 +543,4 @@ if __name__ == "__main__":
     run_infer_all_case()
     run_masker_spade_case()
     run_masker_v3_case()
+    run_masker_v3_case(name="masker_v3_spade", use_spade=True)

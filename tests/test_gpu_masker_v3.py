@@ -18,6 +18,12 @@ def _opts(meta):
     opts.gen.encoder.architecture = "deeplabv3"
     opts.gen.s.architecture = "deeplabv3"
     opts.gen.deeplabv3.nblocks = list(meta["nblocks"])
+    if meta.get("use_spade"):
+        from climategan_b200.utils import Dict
+
+        opts.gen.m.use_spade = True
+        opts.gen.m.use_proj = True
+        opts.gen.m.spade.activations = Dict(all_lrelu=True)
     return opts
 
 
@@ -26,12 +32,16 @@ def _sample(a, cap=8192):
     return a[::max(1, -(-a.size // cap))]
 
 
+@pytest.mark.parametrize("case", ["masker_v3", "masker_v3_spade"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_masker_v3_matches_reference_golden(cuda, dtype):
-    """Tolerances: fp32 storage — eval d / s / m 2e-4 of full scale, train-mode predictions 2e-4, loss 1e-4, every gradient norm
+def test_masker_v3_matches_reference_golden(cuda, dtype, case):
+    """masker_v3: the reference default (base mask decoder with low-level features).  masker_v3_spade: the deeplabv3 encoder
+    with the MaskSpadeDecoder (low-level / high-level / merge convs, SPADE conditioned on the NON-detached make_m_cond(d, s, x):
+    the mask functional back-propagates into the depth and segmentation decoders through the conditioning).  Tolerances: fp32 storage — eval d / s / m 2e-4 of full scale, train-mode predictions 2e-4, loss 1e-4, every gradient norm
     2e-3, sampled gradients 2e-2 (the stem's gradient sits behind ~30 layers), running statistics 1e-4.  bf16 storage — eval
     predictions 4e-2; train mode see below."""
-    meta, g, sd, (x, _, _) = load_golden("masker_v3")
+    meta, g, sd, (x, _, _) = load_golden(case)
+    spade = bool(meta.get("use_spade"))
     G = OmniGenerator(_opts(meta), storage_dtype=dtype)
     assert [(k, tuple(v.shape)) for k, v in G.state_dict().items()] == [(k, tuple(s)) for k, s in meta["shapes"]]
     assert [k for k, _ in G.named_parameters()] == meta["param_names"]
@@ -51,7 +61,7 @@ def test_masker_v3_matches_reference_golden(cuda, dtype):
     z = G.encode(x)
     d, z_depth = G.decode_d(z)
     s = G.decode_s(z, z_depth)
-    m = G.decode_m(z, z_depth=z_depth)
+    m = G.decode_m(z, cond=G.make_m_cond(d, s, x) if spade else None, z_depth=z_depth)
     # bf16 + train-mode BatchNorm on this random-weight fixture: the depth head's last BatchNorm sees channels whose batch
     # spread is a few bf16 steps of their mean (the running statistics used in eval are O(1)), so normalising by the BATCH
     # deviation amplifies the storage rounding of its input ~10x: d is reported but not asserted in bf16; s and m (not behind
@@ -60,7 +70,8 @@ def test_masker_v3_matches_reference_golden(cuda, dtype):
         err = rel_max(t, torch.from_numpy(g[k]))
         if fp32:
             assert err < tol, (k, err)
-        elif k != "train_d":
+        elif k != "train_d" and not (spade and k == "train_m"):
+            # (SPADE decoder: m is conditioned on the per-sample min-max normalisation of that same un-asserted d)
             assert err < 0.3, (k, err)
     rs = np.random.RandomState(meta["functional_seed"])
     wd, ws, wm = (torch.from_numpy(rs.standard_normal(size=tuple(t.shape)).astype(np.float32)).to(cuda) for t in (d, s, m))
@@ -76,17 +87,20 @@ def test_masker_v3_matches_reference_golden(cuda, dtype):
         if r < 0:
             continue
         a = float(gp[name].grad.norm())
-        if fp32 and abs(a - r) > 2e-3 * r + 1e-6 * scale:
+        # the SPADE decoder puts a train-mode BatchNorm under every SPADE layer and feeds the mask gradient back into the depth /
+        # segmentation decoders: same noise floor as tests/test_gpu_full_step.py's SPADE fixture (4e-3 / 50 %)
+        if fp32 and abs(a - r) > (4e-3 if spade else 2e-3) * r + 1e-6 * scale:
             bad.append((name, a, r))
         if not fp32 and not (name.startswith("decoders.d") or name.startswith("encoder")) and r > 1e-2 * scale \
-                and abs(a - r) > 0.3 * r:
+                and abs(a - r) > (0.5 if spade else 0.3) * r:
             bad.append((name, a, r))   # (the encoder / depth gradients inherit the depth head's amplification, see above)
     assert not bad, bad[:10]
     if fp32:
         for k in meta["full"]:
             a, b = _sample(gp[k].grad), g["grad::" + k]
             # (+1e-7: a bias in front of a BatchNorm has an exactly-zero gradient, only rounding residue on both sides)
-            assert np.abs(a - b).max() <= 2e-2 * np.abs(b).max() + 1e-7, (k, float(np.abs(a - b).max() / np.abs(b).max()))
+            assert np.abs(a - b).max() <= (6e-2 if spade else 2e-2) * np.abs(b).max() + 1e-7, \
+                (k, float(np.abs(a - b).max() / np.abs(b).max()))
         sdn = G.state_dict()
         for k in g:
             if k.startswith("final::"):

@@ -135,3 +135,60 @@ def test_full_size_properties(cuda):
         out_b = G.paint(m, x)
     # statistics use fp64 atomics whose summation order varies run to run: reproducible to bf16 noise only
     assert rel_l2(out_b, out) < 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_painter_explicit_z_and_final_shortcut_match_reference_golden(cuda, dtype):
+    """gen.p.no_z = false (an explicit latent replaces fc(cond), painter.py:149-152) with gen.p.use_final_shortcut (the last
+    SPADE block conditioned on lrelu(BatchNorm(SN conv1x1(y))), painter.py:101-109,163-164 — a conditioning map that receives a
+    gradient through SPADE's mlp_shared): train-mode forward + L1 + backward, then an eval-mode forward on the updated running
+    statistics, against the reference modules (tests/golden/painter_z_shortcut.*).  Tolerances as in
+    test_paint_matches_reference_golden."""
+    meta, g, sd, (x, m, t) = load_golden("painter_z_shortcut")
+    opts = default_painter_opts(latent_dim=meta["latent_dim"], spade_n_up=meta["spade_n_up"])
+    opts.gen.p.no_z = False
+    opts.gen.p.use_final_shortcut = True
+    G = OmniGenerator(opts, latent_shape=meta["size"], storage_dtype=dtype)
+    assert [(k, tuple(v.shape)) for k, v in G.painter.state_dict().items()] == [(k, tuple(s)) for k, s in meta["shapes"]]
+    G.painter.load_state_dict(sd, strict=True)
+    G = G.to(cuda).train()
+    x, m, t = x.to(cuda), m.to(cuda), t.to(cuda)
+    z = torch.from_numpy(g["z"]).to(cuda)
+    zs = G.sample_painter_z(meta["batch"], cuda)
+    assert zs.shape == z.shape and zs.dtype == torch.float32
+    out = G.painter(z, x * (1.0 - m))
+    loss = ops.l1_loss(out, t)
+    loss.backward()
+    tol = TOL[dtype]
+    assert rel_max(out, torch.from_numpy(g["out"])) < tol["fwd"]
+    assert abs(float(loss) - float(g["loss"])) / float(g["loss"]) < tol["loss"]
+    params = dict(G.painter.named_parameters())
+    assert params["fc.weight"].grad is None   # bypassed by the explicit z, as in the reference
+    bn = G.painter.final_shortcut[1]
+    stat_tol = 1e-4 if dtype == torch.float32 else 2e-2
+    assert rel_max(bn.running_mean, torch.from_numpy(g["running_mean"])) < stat_tol
+    assert rel_max(bn.running_var, torch.from_numpy(g["running_var"])) < stat_tol
+    for k in meta["full"]:
+        gr, gm = torch.from_numpy(g["grad::" + k]), params[k].grad
+        assert gm is not None, k
+        if dtype == torch.float32:
+            assert rel_max(gm, gr) < 1e-3, (k, rel_max(gm, gr))
+        else:
+            assert cosine(gm, gr) > 0.98 and rel_l2(gm, gr) < 0.25, (k, cosine(gm, gr), rel_l2(gm, gr))
+    norms_ref = dict(zip(meta["grad_keys"], g["grad_norms"]))
+    scale = max(norms_ref.values())
+    bad = []
+    for k, r in norms_ref.items():
+        if r < 1e-6:  # biases feeding an instance norm: mathematically zero gradient (rounding residue on both sides)
+            continue
+        a = float(params[k].grad.norm())
+        rt = 2e-3 if dtype == torch.float32 else 0.25
+        if abs(a - r) > rt * r + 1e-5 * scale:
+            bad.append((k, a, r))
+    assert not bad, bad[:10]
+    G.eval()
+    with torch.no_grad():
+        out_eval = G.painter(z, x * (1.0 - m))
+    assert rel_max(out_eval, torch.from_numpy(g["out_eval"])) < tol["fwd"]
+    # the full paint() path draws its own z
+    assert G.paint(m, x).shape == x.shape
