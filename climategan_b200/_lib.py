@@ -156,6 +156,8 @@ SIGNATURES = {
     "cgb_mask_cond": ([_P, _P, _P, _I, _I, _I, _I, _P], C.c_int),
     "cgb_paste_fwd": ([_P, _P, _P, _P, _I, _I, _P], C.c_int),
     "cgb_paste_bwd": ([_P, _P, _P, _I, _I, _P], C.c_int),
+    "cgb_mask_cond_bwd": ([_P, _P, _P, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_paste_bwd_mask": ([_P, _P, _P, _P, _I, _I, _P], C.c_int),
     "cgb_l1_loss": ([_P, _P, _P, _P, _L, _F, _P], C.c_int),
     "cgb_spectral_power_iter": ([_P, _P, _P, _P, _I, _I, _P], C.c_int),
 }

@@ -1109,6 +1109,43 @@ paste_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ m, fl
   }
 }
 
+// adjoints w.r.t. the MASK (painter loss for the masker, trainer.py:1618-1651: the mask is the masker's prediction):
+//   cond = x (1 - m)                 ->  gm = - sum_c x_c gcond_c
+//   out  = x (1 - m) + fake m        ->  gm =   sum_c gout_c (fake_c - x_c)
+template <typename T>
+__global__ void __launch_bounds__(256)
+mask_cond_bwd_kernel(const float* __restrict__ x, const T* __restrict__ gcond, float* __restrict__ gm, int hw, int cs,
+                     long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int img = (int)(i / hw);
+    const int p = (int)(i - (long long)img * hw);
+    float g[8];
+    Vec8<T>::load(gcond + i * cs, g);
+    float s = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) s += x[((long long)img * 3 + ch) * hw + p] * g[ch];
+    gm[i] = -s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+paste_bwd_mask_kernel(const float* __restrict__ gout, const float* __restrict__ x, const float* __restrict__ fake,
+                      float* __restrict__ gm, int hw, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / hw;
+    const int p = (int)(i - img * hw);
+    float s = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const long long j = (img * 3 + ch) * hw + p;
+      s += gout[j] * (fake[j] - x[j]);
+    }
+    gm[i] = s;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 l1_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ loss,
                float* __restrict__ ga, long long count, float scale) {
@@ -1427,6 +1464,25 @@ extern "C" int cgb_paste_bwd(const float* gout, const float* m, float* gfake, in
   const long long total = (long long)n * 3 * hw;
   paste_bwd_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(gout, m, gfake, hw, total);
   return after_launch("paste_bwd");
+}
+
+extern "C" int cgb_mask_cond_bwd(const float* x, const void* gcond, float* gm, int32_t dtype, int32_t n, int32_t hw, int32_t cs,
+                                 void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && gcond && gm && cs >= 8 && cs % 8 == 0, "mask_cond_bwd: bad arguments");
+  const long long total = (long long)n * hw;
+  DISPATCH_T(dtype, mask_cond_bwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, (const T*)gcond, gm, hw, cs,
+                                                                                             total);)
+  return after_launch("mask_cond_bwd");
+}
+
+extern "C" int cgb_paste_bwd_mask(const float* gout, const float* x, const float* fake, float* gm, int32_t n, int32_t hw,
+                                  void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(gout && x && fake && gm, "paste_bwd_mask: null pointer");
+  const long long total = (long long)n * hw;
+  paste_bwd_mask_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(gout, x, fake, gm, hw, total);
+  return after_launch("paste_bwd_mask");
 }
 
 extern "C" int cgb_l1_loss(const float* a, const float* b, float* loss, float* ga, int64_t count,

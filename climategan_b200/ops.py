@@ -361,23 +361,28 @@ class _Spade(Function):
         check(_L().cgb_instnorm_bwd(_p(x), _p(mean), _p(rstd), _p(sums), _p(gx), _DT[dt], ns_, hw_, cs, _st()),
               "instnorm_bwd")
         # gamma||beta conv: weight grads + data grad (ReLU of mlp_shared fused as a mask)
-        gwp_gb, gbp_gb = conv_wgrad_raw(actv, ggb, g_gb, True)
-        gactv = conv_dgrad_raw(ggb, wp_gb, tuple(actv.shape), g_gb, _lib.ACT_RELU, actv)
-        gwp_sh, gbp_sh = conv_wgrad_raw(seg, gactv, g_sh, True)
-        gw_g = unpack_weight_grad(gwp_gb[:cs], g_shape)
-        gw_b = unpack_weight_grad(gwp_gb[cs:], g_shape)
-        gb_g = gbp_gb[:c].clone()
-        gb_b = gbp_gb[cs:cs + c].clone()
-        if seg_is_col:
-            o_sh, i_sh, kk, _ = sh_shape
-            gw_sh = gwp_sh[:o_sh, 0, : kk * kk * i_sh].reshape(o_sh, kk, kk, i_sh).permute(0, 3, 1, 2).contiguous()
-        else:
-            gw_sh = unpack_weight_grad(gwp_sh, sh_shape)
-        gb_sh = gbp_sh[: sh_shape[0]].clone()
+        want_w = any(ctx.needs_input_grad[4:10])   # False while the painter is frozen (painter loss for the masker)
+        want_seg = ctx.needs_input_grad[3]
+        gw_sh = gb_sh = gw_g = gb_g = gw_b = gb_b = gactv = None
+        if want_w or want_seg:
+            gactv = conv_dgrad_raw(ggb, wp_gb, tuple(actv.shape), g_gb, _lib.ACT_RELU, actv)
+        if want_w:
+            gwp_gb, gbp_gb = conv_wgrad_raw(actv, ggb, g_gb, True)
+            gwp_sh, gbp_sh = conv_wgrad_raw(seg, gactv, g_sh, True)
+            gw_g = unpack_weight_grad(gwp_gb[:cs], g_shape)
+            gw_b = unpack_weight_grad(gwp_gb[cs:], g_shape)
+            gb_g = gbp_gb[:c].clone()
+            gb_b = gbp_gb[cs:cs + c].clone()
+            if seg_is_col:
+                o_sh, i_sh, kk, _ = sh_shape
+                gw_sh = gwp_sh[:o_sh, 0, : kk * kk * i_sh].reshape(o_sh, kk, kk, i_sh).permute(0, 3, 1, 2).contiguous()
+            else:
+                gw_sh = unpack_weight_grad(gwp_sh, sh_shape)
+            gb_sh = gbp_sh[: sh_shape[0]].clone()
         if not ctx.needs_input_grad[0]:
             gx = None
         gseg = None
-        if ctx.needs_input_grad[3]:
+        if want_seg:
             # differentiable conditioning (the masker's make_m_cond(d, s, x) with gen.m.spade.detach = false): dgrad of mlp_shared
             if seg_is_col:
                 raise NotImplementedError("SPADE: gradient w.r.t. an im2col'd conditioning tensor is not built")
@@ -519,17 +524,34 @@ def from_storage(x: torch.Tensor, c: int) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # compositing / losses
 # ------------------------------------------------------------------------------------------------
+class _MaskCond(Function):
+    @staticmethod
+    def forward(ctx, x, m, dtype):
+        n, c, h, w = x.shape
+        cond = torch.empty((n, h, w, 8), dtype=dtype, device=x.device)
+        check(_L().cgb_mask_cond(_p(x), _p(m), _p(cond), _DT[dtype], n, h * w, 8, _st()), "mask_cond")
+        ctx.save_for_backward(x)
+        return cond
+
+    @staticmethod
+    def backward(ctx, gcond):
+        (x,) = ctx.saved_tensors
+        n, _, h, w = x.shape
+        gcond = gcond.contiguous()
+        gm = torch.empty((n, 1, h, w), dtype=torch.float32, device=x.device)
+        check(_L().cgb_mask_cond_bwd(_p(x), _p(gcond), _p(gm), _DT[gcond.dtype], n, h * w, gcond.shape[-1], _st()), "mask_cond_bwd")
+        return None, gm, None
+
+
 def mask_cond(x: torch.Tensor, m: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """Painter conditioning ``x * (1 - m)`` (generator.py:294) written straight into storage layout.
-    Not differentiable (m is ground truth / detached in the painter step)."""
+    """Painter conditioning ``x * (1 - m)`` (generator.py:294) written straight into storage layout.  Differentiable w.r.t. the
+    mask only (the painter loss for the masker feeds the masker's prediction in, trainer.py:1618-1651); x is data."""
     _lib.require_device()
     x = x.detach().contiguous().float()
-    m = m.detach().contiguous().float()
+    m = m.contiguous().float()
     n, c, h, w = x.shape
     assert c == 3 and m.shape == (n, 1, h, w), (x.shape, m.shape)
-    cond = torch.empty((n, h, w, 8), dtype=dtype, device=x.device)
-    check(_L().cgb_mask_cond(_p(x), _p(m), _p(cond), _DT[dtype], n, h * w, 8, _st()), "mask_cond")
-    return cond
+    return _MaskCond.apply(x, m, dtype)
 
 
 class _Paste(Function):
@@ -541,22 +563,31 @@ class _Paste(Function):
         n, _, h, w = x.shape
         out = torch.empty_like(x)
         check(_L().cgb_paste_fwd(_p(x), _p(m), _p(fake), _p(out), n, h * w, _st()), "paste_fwd")
-        ctx.save_for_backward(m)
+        if ctx.needs_input_grad[1]:
+            ctx.save_for_backward(m, x, fake)
+        else:
+            ctx.save_for_backward(m)
         return out
 
     @staticmethod
     def backward(ctx, gout):
-        (m,) = ctx.saved_tensors
+        m = ctx.saved_tensors[0]
         gout = gout.contiguous()
         n, _, h, w = gout.shape
-        gf = torch.empty_like(gout)
-        check(_L().cgb_paste_bwd(_p(gout), _p(m), _p(gf), n, h * w, _st()), "paste_bwd")
-        return None, None, gf
+        gf = gm = None
+        if ctx.needs_input_grad[2]:
+            gf = torch.empty_like(gout)
+            check(_L().cgb_paste_bwd(_p(gout), _p(m), _p(gf), n, h * w, _st()), "paste_bwd")
+        if ctx.needs_input_grad[1]:
+            _, x, fake = ctx.saved_tensors
+            gm = torch.empty_like(m)
+            check(_L().cgb_paste_bwd_mask(_p(gout), _p(x), _p(fake), _p(gm), n, h * w, _st()), "paste_bwd_mask")
+        return None, gm, gf
 
 
 def paste(x, m, fake):
-    """``x * (1 - m) + fake * m`` (generator.py:295-296); gradient flows to ``fake`` only."""
-    return _Paste.apply(x, m, fake)
+    """``x * (1 - m) + fake * m`` (generator.py:295-296); gradient flows to ``fake`` and, when it asks for one, to the mask."""
+    return _Paste.apply(x.detach(), m, fake)
 
 
 class _L1(Function):

@@ -82,10 +82,15 @@ class PainterSpadeDecoder(nn.Module):
             return segs[(h, w)]
 
         cols = {}
+        # a conditioning tensor that carries a gradient (painter loss for the masker: cond = x (1 - predicted mask)) takes the
+        # direct 3x3 mlp_shared path in every SPADE layer — its dgrad is the gradient w.r.t. the conditioning
+        cond_grad = torch.is_grad_enabled() and cond_st.requires_grad
 
         def run(blk, y):
             hw = (y.shape[1], y.shape[2])
             seg = seg_at(*hw)
+            if cond_grad:
+                return blk(y, seg)
             if hw not in cols:  # im2col patches of the conditioning: once per resolution, shared by all SPADEs
                 cols[hw] = ops.im2col(seg, 3, 3, 1)
             return blk(y, seg, cols[hw])

@@ -316,7 +316,9 @@ class Trainer:
                     self.logger.losses.gen.task["m"]["gi"]["r"] = loss.detach()
                 weight = lam.G.m.pl4m
                 if self.use_pl4m and weight != 0:
-                    raise NotImplementedError("painter loss for the masker (pl4m; off until epoch 49, defaults.yaml:147) is not built")
+                    loss = self.painter_loss_for_masker(x, pred_prob) * weight
+                    full_loss = full_loss + loss
+                    self.logger.losses.gen.task["m"]["pl4m"]["r"] = loss.detach()
                 weight = lam.advent.ent_main
                 if self.opts.gen.m.use_minent and weight != 0:
                     loss = self.losses["G"]["tasks"]["m"]["minent"](prob) * weight
@@ -344,6 +346,28 @@ class Trainer:
                 full_loss = full_loss + loss
                 logger[domain] = loss.detach()
         return full_loss, prob
+
+    def painter_loss_for_masker(self, x, m):
+        """trainer.py:1618-1651 (pl4m; switched on at epoch gen.p.pl4m_epoch when gen.m.use_pl4m, trainer.py:899-909): the frozen
+        painter paints with the masker's PREDICTED mask and the painter discriminator scores the result; the gradient reaches
+        the masker through x (1 - m), the SPADE conditioning, the paste and the mask channel of D's input."""
+        if self.opts.dis.p.use_local_discriminator:
+            raise NotImplementedError("dis.p.use_local_discriminator (off in defaults.yaml) is not built")
+        frozen = [p for p in self.G.painter.parameters() if p.requires_grad]
+        for p in frozen:
+            p.requires_grad = False
+        try:
+            fake_flooded = self.G.paint(m, x)
+            real_cat = torch.cat([m, x], axis=1)
+            fake_cat = torch.cat([m, fake_flooded], axis=1)
+            real_fake_d = self.D["p"](torch.cat([real_cat, fake_cat], dim=0))
+            _, fake_d = divide_pred(real_fake_d)
+            return self.losses["G"]["p"]["gan"](fake_d, True, False)
+        finally:
+            # (the reference re-enables EVERY painter parameter, u / v included — harmless there: g_opt only holds what was
+            # trainable at construction; here the previous flags are restored)
+            for p in frozen:
+                p.requires_grad = True
 
     def get_painter_loss(self, multi_domain_batch):
         """trainer.py:1256-1387 (vgg, gan, featmatch; tv/context/reconstruction have lambda 0 in defaults.yaml:294-299)."""

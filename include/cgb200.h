@@ -345,6 +345,12 @@ int cgb_paste_fwd(const float* x, const float* m, const float* fake, float* out,
                   void* stream);
 /* gfake = gout * m */
 int cgb_paste_bwd(const float* gout, const float* m, float* gfake, int32_t n, int32_t hw, void* stream);
+/* Adjoints of the two above w.r.t. the MASK, for the painter loss of the masker (Trainer.painter_loss_for_masker,
+ * trainer.py:1618-1651: the mask is the masker's own prediction): gm = -sum_c x_c gcond_c and gm = sum_c gout_c (fake_c - x_c);
+ * gm fp32 [n,1,hw]. */
+int cgb_mask_cond_bwd(const float* x, const void* gcond, float* gm, int32_t dtype, int32_t n, int32_t hw, int32_t cs,
+                      void* stream);
+int cgb_paste_bwd_mask(const float* gout, const float* x, const float* fake, float* gm, int32_t n, int32_t hw, void* stream);
 
 /* ---- losses ------------------------------------------------------------------------------
  * mean |a-b| and its gradient w.r.t. a (nn.L1Loss; climategan/losses.py:290-301, FeatMatchLoss :86-103):

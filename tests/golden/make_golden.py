@@ -310,7 +310,7 @@ def _sample(a, cap=8192):
     return a[::k].copy()
 
 
-def run_full_step_case(name="full_step", batch=2, size=128, tasks=("d", "s", "m", "p"), use_spade=False):
+def run_full_step_case(name="full_step", batch=2, size=128, tasks=("d", "s", "m", "p"), use_spade=False, pl4m=False):
     """Two iterations of the reference's OWN ``Trainer.update_G`` / ``update_D`` (trainer.py:989-1032) on tasks [d,s,m,p]
     — deeplabv2 masker (ResNet [2,2,3,2], train-mode BatchNorm, dropout p=0) + SPADE painter + all three discriminators —
     driven as ``run_epoch`` does (oracle/ref_trainer.py).  Stores every logged loss, the gradient norm of every parameter
@@ -324,6 +324,7 @@ def run_full_step_case(name="full_step", batch=2, size=128, tasks=("d", "s", "m"
         blocks_mod.SPADEResnetBlock.cuda = lambda self, *a, **k: self   # masker.py:196 hard-codes .cuda() (SURVEY.md §8c patch 1)
     t = rt.build_reference_trainer(opts, size)
     g_shapes, d_shapes, v_shapes = rt.load_weights(t)
+    t.use_pl4m = bool(pl4m)   # what Trainer.train() flips at epoch gen.p.pl4m_epoch (trainer.py:899-909)
     mdb = rt.synth_batch(opts, batch, size, seed=7)
     arrays = {}
     logs = []
@@ -373,7 +374,7 @@ def run_full_step_case(name="full_step", batch=2, size=128, tasks=("d", "s", "m"
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
     meta = {"case": name, "batch": batch, "size": size, "seeds": {"G": 21, "D": 22, "vgg": 23, "inputs": 7},
             "g_shapes": [[k, list(s_)] for k, s_ in g_shapes], "d_shapes": [[k, list(s_)] for k, s_ in d_shapes],
-            "tasks": list(tasks), "use_spade": bool(use_spade),
+            "tasks": list(tasks), "use_spade": bool(use_spade), "pl4m": bool(pl4m),
             "v_shapes": [[k, list(s_)] for k, s_ in (v_shapes or [])], "g_param_names": [k for k, _ in t.G.named_parameters()],
             "d_param_names": [k for k, _ in t.D.named_parameters()], "logs": logs, "full_g": full_g, "full_d": full_d,
             "reference": "cc-ai/climategan @ /root/reference: climategan.trainer.Trainer.update_G/update_D (unmodified), CPU, torch "
@@ -540,6 +541,7 @@ if __name__ == "__main__":
     run_masker_case()
     run_full_step_case()
     run_full_step_case(name="masker_step_spade", tasks=("d", "s", "m"), use_spade=True)
+    run_full_step_case(name="full_step_pl4m", pl4m=True)
     run_infer_all_case()
     run_masker_spade_case()
     run_masker_v3_case()
