@@ -72,6 +72,20 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
+// TMA store (shared::cta -> global, bulk async group), used by the copy-out of the streaming kernel's epilogue
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -192,6 +206,9 @@ struct TcParams {
   int stages;
   int tmem_cols;               // >= 2*bn: two accumulator buffers
   int stage_pitch;             // bytes per staging row = bn*2 + 16
+  int tma_store;               // streaming kernel: copy-out by TMA store from a 128B-swizzled staging tile (bn % 64 == 0)
+  int staging_bufs;            // 1 or 2 staging tiles (2: the store of tile i overlaps the epilogue math of tile i+1)
+  int staging_tile_bytes;      // bytes of one staging tile: 128*stage_pitch, or ceil(bn/64) swizzled 16 KB halves (TMA store)
   int twh, thh;                // weight-stationary kernel: halo tile extent (pixels)
   int a_stage_bytes;           // weight-stationary kernel: bytes per halo stage (1024-aligned)
   int act;
@@ -224,7 +241,9 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 __device__ __forceinline__ void epi_chunk(const TcParams& p, const uint32_t (&r)[16], int c, int cn0, bool pix_ok,
                                           long long pix, float neg, bool mask_early, const float* __restrict__ bias,
                                           const __nv_bfloat16* __restrict__ residual,
-                                          const __nv_bfloat16* __restrict__ mask_src, uint8_t* my_row) {
+                                          const __nv_bfloat16* __restrict__ mask_src, uint8_t* my_row, int sw = -1) {
+  // sw < 0: padded row-major staging row (my_row + channel*2).  sw = row & 7: TMA-store staging — per 64-channel half a
+  // [128 rows][128 B] tile in the 128-byte swizzle (16-byte chunk index XOR row & 7), my_row = tile base + row*128
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int ch = cn0 + c * 16 + h * 8;
@@ -265,7 +284,13 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const uint32_t (&r)
         for (int j = 0; j < 8; ++j) v[j] *= act_grad_from_out(mm[j], p.dact, p.slope);
       }
     }
-    Vec8<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(my_row + (size_t)(c * 16 + h * 8) * 2), v);
+    if (sw < 0) {
+      Vec8<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(my_row + (size_t)(c * 16 + h * 8) * 2), v);
+    } else {
+      const int j = c * 2 + h;
+      Vec8<__nv_bfloat16>::store(
+          reinterpret_cast<__nv_bfloat16*>(my_row + (size_t)(j >> 3) * (128 * 128) + (size_t)(((j & 7) ^ sw) << 4)), v);
+    }
   }
 }
 
@@ -273,7 +298,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
                                               int n0, int cn0, const float* __restrict__ bias,
                                               const __nv_bfloat16* __restrict__ residual,
                                               const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y,
-                                              uint32_t tempty_bar, int warp, int lane) {
+                                              uint32_t tempty_bar, int warp, int lane, const CUtensorMap* tmY = nullptr,
+                                              uint32_t staging_u32 = 0) {
   const int q = warp & 3;              // TMEM lane quarter this warp may access
   const int half = (warp - 2) >> 2;    // EPI_PER_Q warps share a quarter: 16-column chunks interleaved among them
   const int row = q * 32 + lane;       // tile row == TMEM lane == pixel within the tile
@@ -288,9 +314,14 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
   const bool mask_early = (mask_src != nullptr) && !mask_late;
   const float neg = p.act == CGB_ACT_NONE ? 1.f : (p.act == CGB_ACT_RELU ? 0.f : p.slope);
 
+  const bool tma = tmY != nullptr;
+  if (tma && et == 0) {  // the bulk store that last read THIS staging tile has finished reading it
+    if (p.staging_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+  }
   epi_bar_sync();  // previous tile's copy-out has finished reading the staging buffer
   const uint32_t t_row = tmem_acc + ((uint32_t)(q * 32) << 16);
-  uint8_t* my_row = staging_gen + (size_t)row * p.stage_pitch;
+  uint8_t* my_row = staging_gen + (size_t)row * (tma ? 128 : p.stage_pitch);
+  const int sw = tma ? (row & 7) : -1;
   const int nchunks = p.bn >> 4;
   for (int c = half; c < nchunks; c += 2 * EPI_PER_Q) {
     uint32_t ra[16], rb[16];
@@ -298,13 +329,25 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
     tmem_ld16(t_row + (uint32_t)(c * 16), ra);
     if (two) tmem_ld16(t_row + (uint32_t)((c + EPI_PER_Q) * 16), rb);
     tmem_ld_wait();
-    epi_chunk(p, ra, c, cn0, pix_ok, pix, neg, mask_early, bias, residual, mask_src, my_row);
-    if (two) epi_chunk(p, rb, c + EPI_PER_Q, cn0, pix_ok, pix, neg, mask_early, bias, residual, mask_src, my_row);
+    epi_chunk(p, ra, c, cn0, pix_ok, pix, neg, mask_early, bias, residual, mask_src, my_row, sw);
+    if (two) epi_chunk(p, rb, c + EPI_PER_Q, cn0, pix_ok, pix, neg, mask_early, bias, residual, mask_src, my_row, sw);
   }
   // accumulator buffer drained: hand it back to the MMA warp
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(tempty_bar);
+  if (tma) {
+    // copy-out by the TMA unit: one bulk tensor store per 64-channel half of the tile; image borders, the batch tail and the
+    // channel tail are clipped by the tensor map, so no thread computes an address
+    fence_proxy_async_smem();   // this thread's staging writes -> visible to the async proxy
+    epi_bar_sync();             // staging complete
+    if (et == 0) {
+      for (int hb = 0; hb * 64 < p.bn; ++hb)
+        if (cn0 + hb * 64 < p.cout_s) tma_store_4d(tmY, staging_u32 + (uint32_t)hb * (128u * 128u), cn0 + hb * 64, ox0, oy0, n0);
+      tma_store_commit();
+    }
+    return;
+  }
   epi_bar_sync();  // staging complete
   // phase 2: lanes cover (rows_per_iter x chunks_per_row) 16-byte chunks; the row/chunk split of a lane is fixed, so
   // the only per-iteration work is the pixel address.  Consecutive lanes write consecutive chunks of a pixel and then
@@ -344,8 +387,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
 // smem: [stages x (A 16 KB | B bn*128 B)] [staging 128 x (bn*2+16) B] [barriers]
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
-               const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
                const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -353,7 +396,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t b_tile_bytes = (uint32_t)p.bn * 128u;
   const uint32_t stage_bytes = A_TILE_BYTES + b_tile_bytes;
   const uint32_t staging = base + (uint32_t)p.stages * stage_bytes;
-  const uint32_t bar_base = staging + 128u * (uint32_t)p.stage_pitch;
+  const uint32_t staging_tile = (uint32_t)p.staging_tile_bytes;
+  const uint32_t bar_base = staging + staging_tile * (uint32_t)p.staging_bufs;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(p.stages + s); };
   auto tfull_bar = [&](int b) { return bar_base + 16u * (uint32_t)p.stages + 8u * (uint32_t)b; };
@@ -371,6 +415,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (p.tma_store) prefetch_tmap(&tmY);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -466,9 +511,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tn = pt / (p.tiles_x * p.tiles_y);
       mbar_wait(tfull_bar(buf), bph);
       tc_fence_after();
-      epilogue_tile(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen, tx << p.tw_log, ty << p.th_log, tn << tn_log,
-                    nt * p.bn, bias, residual, mask_src, y, tempty_bar(buf), warp, lane);
+      const uint32_t sb = (p.staging_bufs == 2) ? (uint32_t)(lt & 1) * staging_tile : 0u;
+      epilogue_tile(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen + sb, tx << p.tw_log, ty << p.th_log, tn << tn_log,
+                    nt * p.bn, bias, residual, mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr,
+                    staging + sb);
     }
+    if (p.tma_store && threadIdx.x == 64) tma_store_wait_all();   // the issuing thread: every bulk store has completed
   }
 
   tc_fence_before();
@@ -492,8 +540,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // smem: [weights] [stages x halo tile] [staging] [barriers].  grid is a multiple of n_tiles; CTA c keeps n-tile c % n_tiles.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS)
-conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p,
-                  const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
+conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
                   const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -503,7 +551,7 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t w_bytes = (uint32_t)(p.kblocks * taps) * w_tap_bytes;
   const uint32_t a_base = base + w_bytes;
   const uint32_t staging = a_base + (uint32_t)p.stages * (uint32_t)p.a_stage_bytes;
-  const uint32_t bar_base = staging + 128u * (uint32_t)p.stage_pitch;
+  const uint32_t bar_base = staging + (uint32_t)p.staging_tile_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(p.stages + s); };
   auto tfull_bar = [&](int b) { return bar_base + 16u * (uint32_t)p.stages + 8u * (uint32_t)b; };
@@ -617,8 +665,9 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(tfull_bar(buf), bph);
       tc_fence_after();
       epilogue_tile(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen, tx << 3, ty << 4, img, cn0, bias, residual,
-                    mask_src, y, tempty_bar(buf), warp, lane);
+                    mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr, staging);
     }
+    if (p.tma_store && threadIdx.x == 64) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -702,6 +751,22 @@ static void pick_tile(int n, int h, int w, int stride, int* tw_log, int* th_log)
   *th_log = bh;
 }
 
+// TMA-store copy-out of the epilogue (on unless CGB_TMA_STORE=0): the tile leaves shared memory as bulk tensor stores of
+// 64-channel halves, so the N tile must be whole halves or the only N tile (the tensor map clips the channel tail)
+static bool tma_store_enabled() {
+  static const int v = getenv("CGB_TMA_STORE") ? atoi(getenv("CGB_TMA_STORE")) : 1;
+  return v != 0;
+}
+static bool tma_store_ok(int bn, int n_tiles, int dact, const void* mask_src) {
+  return tma_store_enabled() && (bn % 64 == 0 || n_tiles == 1) && !(mask_src && dact == CGB_ACT_RELU);
+}
+static int staging_tile_bytes_for(int bn, bool tma) {
+  const int plain = 128 * (bn * 2 + 16);
+  if (!tma) return plain;
+  const int halves = ((bn + 63) / 64) * (128 * 128);
+  return ((halves > plain ? halves : plain) + 1023) / 1024 * 1024;
+}
+
 static int pick_bn(int co) {
   // largest multiple of 16 <= 256 that tiles co with the least padded work
   const int co16 = (co + 15) / 16 * 16;
@@ -759,7 +824,12 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
   p.n_tiles = (cout_s + p.bn - 1) / p.bn;
   p.total_tiles = p.tiles_x * p.tiles_y * tiles_n * p.n_tiles;
   p.stage_pitch = p.bn * 2 + 16;
-  const int staging_bytes = 128 * p.stage_pitch;
+  // TMA-store copy-out: plain output mapping only (the strided parity-class dgrad keeps the per-thread copy-out)
+  p.tma_store = (tma_store_ok(p.bn, p.n_tiles, dact, mask_src) && out_stride == 1 && out_off_y == 0 && out_off_x == 0 &&
+                 hfull == hgrid && wfull == wgrid) ? 1 : 0;
+  p.staging_bufs = (p.tma_store && p.bn <= 128) ? 2 : 1;
+  p.staging_tile_bytes = staging_tile_bytes_for(p.bn, p.tma_store != 0);
+  const int staging_bytes = p.staging_tile_bytes * p.staging_bufs;
   int cols = 32;
   while (cols < 2 * p.bn) cols <<= 1;
   p.tmem_cols = cols;
@@ -784,13 +854,21 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
     cuuint32_t estr[3] = {1, 1, 1};
     if (!encode_map(&tmB, w, 3, dims, strides, box, estr, "weights")) return CGB_LAUNCH_FAILURE;
   }
+  CUtensorMap tmY = tmB;   // (any valid map when the TMA store is off: the kernel never touches it)
+  if (p.tma_store) {
+    cuuint64_t dims[4] = {(cuuint64_t)cout_s, (cuuint64_t)wfull, (cuuint64_t)hfull, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)cout_s * 2, (cuuint64_t)wfull * cout_s * 2, (cuuint64_t)hfull * wfull * cout_s * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(1 << p.tw_log), (cuuint32_t)(1 << p.th_log), (cuuint32_t)(1 << tn_log)};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (!encode_map(&tmY, out, 4, dims, strides, box, estr, "output")) return CGB_LAUNCH_FAILURE;
+  }
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
     cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
   });
   const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 16 * stages + 48 + 1024;
   dim3 grid((unsigned)(p.total_tiles < num_sms() ? p.total_tiles : num_sms()));
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, p, bias, (const __nv_bfloat16*)residual,
+  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
                                                  (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out);
   return after_launch("conv_tc");
 }
@@ -823,7 +901,7 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
       int bn = ((cout_s + nt - 1) / nt + 15) / 16 * 16;
       if (bn > 256) continue;
       const size_t wb = (size_t)kblocks * taps * bn * 128;
-      const size_t fixed = wb + 128 * (size_t)(bn * 2 + 16) + 1024 + 256;
+      const size_t fixed = wb + (size_t)staging_tile_bytes_for(bn, tma_store_ok(bn, nt, dact, mask_src)) + 1024 + 256;
       if (fixed + 2 * (size_t)a_stage > SMEM_LIMIT) continue;
       int stg = (int)((SMEM_LIMIT - fixed) / a_stage);
       if (stg > 6) stg = 6;
@@ -875,7 +953,10 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
   p.bn = ws_bn; p.n_tiles = ws_ntiles; p.stages = ws_stages;
   p.twh = twh; p.thh = thh; p.a_stage_bytes = a_stage;
   p.stage_pitch = p.bn * 2 + 16;
-  const int staging_bytes = 128 * p.stage_pitch;
+  p.tma_store = tma_store_ok(p.bn, p.n_tiles, dact, mask_src) ? 1 : 0;
+  p.staging_bufs = 1;
+  p.staging_tile_bytes = staging_tile_bytes_for(p.bn, p.tma_store != 0);
+  const int staging_bytes = p.staging_tile_bytes;
   int cols = 32;
   while (cols < 2 * p.bn) cols <<= 1;
   p.tmem_cols = cols;
@@ -894,10 +975,18 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
     cuuint32_t estr[3] = {1, 1, 1};
     if (!encode_map(&tmB, w, 3, dims, strides, box, estr, "weights")) return CGB_LAUNCH_FAILURE;
   }
+  CUtensorMap tmY = tmB;   // (any valid map when the TMA store is off: the kernel never touches it)
+  if (p.tma_store) {
+    cuuint64_t dims[4] = {(cuuint64_t)cout_s, (cuuint64_t)wout, (cuuint64_t)hout, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)cout_s * 2, (cuuint64_t)wout * cout_s * 2, (cuuint64_t)hout * wout * cout_s * 2};
+    cuuint32_t box[4] = {64, 8, 16, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (!encode_map(&tmY, out, 4, dims, strides, box, estr, "output")) return CGB_LAUNCH_FAILURE;
+  }
   const size_t smem = (size_t)p.kblocks * taps * p.bn * 128 + (size_t)p.stages * a_stage + staging_bytes + 16 * p.stages + 64 + 1024;
   int ctas = num_sms() / p.n_tiles * p.n_tiles;
   if (ctas > p.pix_tiles * p.n_tiles) ctas = p.pix_tiles * p.n_tiles;
-  conv_tc_ws_kernel<<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, p, bias, (const __nv_bfloat16*)residual,
+  conv_tc_ws_kernel<<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
                                                     (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out);
   return after_launch("conv_tc_ws");
 }

@@ -1,11 +1,12 @@
-"""Trainer — the step-level surface of ``climategan/trainer.py`` for the painter task (``opts.tasks == ["p"]``):
-``update_G`` (:989-1015), ``update_D`` (:1017-1032), ``get_G_loss`` (:1162-1182), ``get_painter_loss`` (:1256-1387),
-``get_D_loss`` (:1034-1160, painter branch :1071-1107), ``g_opt_step``/``d_opt_step`` (:674-694), ``batch_to_device``
-(:609-631), with the reference's ``multi_domain_batch`` dict contract and ``logger.losses.{gen,disc}`` keys.
+"""Trainer — the step-level surface of ``climategan/trainer.py``: ``update_G`` (:989-1015), ``update_D`` (:1017-1032),
+``get_G_loss`` (:1162-1182), ``get_masker_loss`` (:1184-1254) with ``masker_{d,s,m}_loss`` (:1389-1616) and
+``painter_loss_for_masker`` (:1618-1651), ``get_painter_loss`` (:1256-1387), ``get_D_loss`` (:1034-1160),
+``g_opt_step``/``d_opt_step`` (:674-694), ``batch_to_device`` (:609-631), ``infer_all`` (:218-334) and the event compositing
+(:1824-1939), ``save`` / ``resume`` / ``resume_from_path`` — with the reference's ``multi_domain_batch`` dict contract and
+``logger.losses.{gen,disc}`` keys, for tasks d, s, m (base or SPADE mask decoder, deeplabv2 / deeplabv3 encoder) and p.
 
 Every array op runs through libcgb200; the `.item()` syncs the reference performs per loss term are kept lazy here
 (``logger.losses`` stores device scalars; ``Trainer.losses_to_host()`` materialises them once).
-The masker tasks (m, s, d) are not built yet and raise.
 """
 from __future__ import annotations
 
