@@ -1073,6 +1073,13 @@ struct WgParams {
   long long sm, sn, st;        // gw index = m*sm + n*sn + tap*st
 };
 
+// 16-byte vector reduction into global memory (sm_90+): gw[0..3] += {a, b, c, d}
+__device__ __forceinline__ void red_add_v4(float* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)),
+               "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+               : "memory");
+}
+
 constexpr int BOX_BYTES = 128 * 128;  // 128 pixels x 64 channels bf16
 constexpr int WG_THREADS = 192;       // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
 
@@ -1204,10 +1211,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         tmem_ld16(t_row + (uint32_t)(t * p.bn + c0), r);
         tmem_ld_wait();
         if (!m_ok) continue;
+        if (p.sn == 1) {
+          // a lane's 16 accumulator columns are 16 consecutive floats of gw (M = output channels): four 16-byte vector
+          // reductions instead of 16 scalar ones — the scalar form made this epilogue the kernel's bottleneck (60 % of the
+          // warp samples in profiles/r01_wgrad_256to1024_k1_80x80_n8.txt).  n_dim, n0, c0 are multiples of 8: aligned.
+          float* dst = gw + tap_off + (long long)(n0 + c0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int nn = n0 + c0 + j;
-          if (nn < p.n_dim) atomicAdd(gw + tap_off + (long long)nn * p.sn, __uint_as_float(r[j]));
+          for (int j = 0; j < 16; j += 4)
+            if (n0 + c0 + j < p.n_dim) red_add_v4(dst + j, r[j], r[j + 1], r[j + 2], r[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int nn = n0 + c0 + j;
+            if (nn < p.n_dim) atomicAdd(gw + tap_off + (long long)nn * p.sn, __uint_as_float(r[j]));
+          }
         }
       }
     }
@@ -1366,10 +1383,20 @@ wgrad_tc_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         tmem_ld16(t_row + (uint32_t)(t * p.bn + c0), r);
         tmem_ld_wait();
         if (!m_ok) continue;
+        if (p.sn == 1) {
+          // a lane's 16 accumulator columns are 16 consecutive floats of gw (M = output channels): four 16-byte vector
+          // reductions instead of 16 scalar ones — the scalar form made this epilogue the kernel's bottleneck (60 % of the
+          // warp samples in profiles/r01_wgrad_256to1024_k1_80x80_n8.txt).  n_dim, n0, c0 are multiples of 8: aligned.
+          float* dst = gw + tap_off + (long long)(n0 + c0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int nn = n0 + c0 + j;
-          if (nn < p.n_dim) atomicAdd(gw + tap_off + (long long)nn * p.sn, __uint_as_float(r[j]));
+          for (int j = 0; j < 16; j += 4)
+            if (n0 + c0 + j < p.n_dim) red_add_v4(dst + j, r[j], r[j + 1], r[j + 2], r[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int nn = n0 + c0 + j;
+            if (nn < p.n_dim) atomicAdd(gw + tap_off + (long long)nn * p.sn, __uint_as_float(r[j]));
+          }
         }
       }
     }
