@@ -227,7 +227,7 @@ def test_spade_masker_step_bf16_close_to_reference_trainer(cuda):
     itself with weights perturbed by 1e-3 relative = the size of ONE bf16 rounding, activations left exact): mask-decoder and
     discriminator gradient directions move to cosine 0.91-0.98, the mask head's bias gradient norm by 59 %, other norms by up
     to 13 %.  Stated tolerances: first-iteration losses within 3e-2 relative (abs 2e-3); gradient norms within 50 % (the
-    mask head's bias, gradients below 1e-3 of the largest norm and the spectral-norm vectors excluded); cosine >= 0.8 for the sampled
+    single-element head biases, near-zero gradients and the spectral-norm vectors excluded); cosine >= 0.8 for the sampled
     discriminator gradients and >= 0.7 for the sampled mask-decoder gradients (measured on B200: 0.74 / 0.75 for the two
     tensors that read the bf16 trunk's latent directly — fc_conv and the first SPADE layer — and >= 0.8 for the rest).
     Per-op bf16 parity is held tight in tests/test_gpu_ops.py / test_gpu_masker_ops.py."""
@@ -240,11 +240,12 @@ def test_spade_masker_step_bf16_close_to_reference_trainer(cuda):
     for side in ("G", "D"):
         ref, got = g[side + ".gradnorm"], out[side + ".gradnorm"]
         names = meta["g_param_names" if side == "G" else "d_param_names"]
-        scale = ref[ref >= 0].max()
+        # single-element parameters (the bias of a 1-channel head: mask_conv, Advent.8) are skipped: their gradient is one signed
+        # sum over every output position, a cancellation bf16 cannot hold (the reference itself: 59 % under 1e-3 weight noise)
+        single = {k for k, shp in meta["g_shapes" if side == "G" else "d_shapes"] if int(np.prod(shp)) == 1}
         for n, a, b in zip(names, got, ref):
-            skip = n.endswith(("weight_u", "weight_v")) or "global_avg_pool" in n or n == "decoders.m.mask_conv.conv.module.bias"
-            # (gradients below 1e-3 of the largest norm — single-element head biases — are rounding-level in bf16)
-            if b > max(1e-4, 1e-3 * scale) and not skip and abs(a - b) > 0.5 * b:
+            skip = n.endswith(("weight_u", "weight_v")) or "global_avg_pool" in n or n in single
+            if b > 1e-4 and not skip and abs(a - b) > 0.5 * b:
                 bad.append((n, float(a), float(b)))
     for k in g:
         if ".grad::" in k and ("decoders.m" in k or k.startswith("D.grad")):
