@@ -115,6 +115,8 @@ class OmniGenerator(nn.Module):
 
     def make_m_cond(self, d, s, x=None):
         """generator.py:196-230: d, s NCHW fp32 predictions; returns the NCHW conditioning tensor (12 or 15 channels)."""
+        if self.opts.gen.m.spade.cond_nc == 15 and x is None:
+            raise ValueError("When using spade for the Masker with 15 channels, x MUST be provided")
         with self._grad_ctx():
             if self.opts.gen.m.spade.detach:
                 d, s = d.detach(), s.detach()
@@ -122,8 +124,6 @@ class OmniGenerator(nn.Module):
             ds, ss = ops.to_storage(d, dt), ops.to_storage(s, dt)
             xr = None
             if self.opts.gen.m.spade.cond_nc == 15:
-                if x is None:
-                    raise ValueError("When using spade for the Masker with 15 channels, x MUST be provided")
                 xr = ops.resize_bilinear(ops.to_storage(x, dt), s.shape[-2], s.shape[-1], align_corners=True)
             cond = ops.make_m_cond(ds, ss, xr, s.shape[1])
             return ops.from_storage(cond, 1 + s.shape[1] + (3 if xr is not None else 0))

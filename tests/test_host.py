@@ -102,3 +102,71 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("# oracle", ""), f"{f} references the oracle"
+
+
+def _names_shapes(module):
+    return [(k, tuple(v.shape)) for k, v in module.state_dict().items()]
+
+
+def test_generator_and_discriminator_surfaces_match_the_reference_for_every_built_configuration():
+    """state_dict keys / shapes / order and the parameter order of OmniGenerator and OmniDiscriminator against the lists the
+    REFERENCE modules produced (stored with the goldens), for every configuration that is built: v2 masker + painter (base mask
+    decoder), the SPADE mask decoder (paper / release configuration), the reference-default v3 masker with the base and with
+    the SPADE mask decoder, and the painter with use_final_shortcut.  Construction needs no GPU."""
+    import json
+
+    from climategan_b200.discriminator import OmniDiscriminator
+    from climategan_b200.generator import OmniGenerator
+    from climategan_b200.utils import Dict, default_masker_opts, full_opts
+    from tests.helpers import GOLDEN
+
+    def meta_of(name):
+        return json.load(open(os.path.join(GOLDEN, name + ".json")))
+
+    # full step (tasks d, s, m, p), base and pl4m fixtures share the architecture; SPADE-masker step (tasks d, s, m)
+    for name in ("full_step", "full_step_pl4m", "masker_step_spade"):
+        meta = meta_of(name)
+        opts = full_opts(size=meta["size"], tasks=tuple(meta.get("tasks", ("d", "s", "m", "p"))),
+                         use_spade=meta.get("use_spade", False))
+        G = OmniGenerator(opts, latent_shape=(meta["size"], meta["size"]))
+        D = OmniDiscriminator(opts)
+        assert _names_shapes(G) == [(k, tuple(s)) for k, s in meta["g_shapes"]], name
+        assert _names_shapes(D) == [(k, tuple(s)) for k, s in meta["d_shapes"]], name
+        assert [k for k, _ in G.named_parameters()] == meta["g_param_names"], name
+        assert [k for k, _ in D.named_parameters()] == meta["d_param_names"], name
+    # v3 masker, base and SPADE mask decoders
+    for name in ("masker_v3", "masker_v3_spade"):
+        meta = meta_of(name)
+        opts = default_masker_opts(nblocks=tuple(meta["nblocks"]), size=meta["size"])
+        opts.gen.encoder.architecture = "deeplabv3"
+        opts.gen.s.architecture = "deeplabv3"
+        opts.gen.deeplabv3.nblocks = list(meta["nblocks"])
+        if meta.get("use_spade"):
+            opts.gen.m.use_spade = True
+            opts.gen.m.use_proj = True
+            opts.gen.m.spade.activations = Dict(all_lrelu=True)
+        G = OmniGenerator(opts)
+        assert _names_shapes(G) == [(k, tuple(s)) for k, s in meta["shapes"]], name
+        assert [k for k, _ in G.named_parameters()] == meta["param_names"], name
+    # painter with the final shortcut (and an explicit latent)
+    meta = meta_of("painter_z_shortcut")
+    opts = default_painter_opts(latent_dim=meta["latent_dim"], spade_n_up=meta["spade_n_up"])
+    opts.gen.p.no_z = False
+    opts.gen.p.use_final_shortcut = True
+    assert _names_shapes(PainterSpadeDecoder(opts)) == [(k, tuple(s)) for k, s in meta["shapes"]]
+
+
+def test_make_m_cond_needs_x_for_15_channels():
+    """generator.py:220-225: cond_nc == 15 without x is a ValueError (checked before any kernel runs)."""
+    import pytest
+
+    from climategan_b200.generator import OmniGenerator
+    from climategan_b200.utils import Dict, default_masker_opts
+
+    opts = default_masker_opts(nblocks=(1, 1, 1, 1), size=64)
+    opts.gen.m.use_spade = True
+    opts.gen.m.spade.activations = Dict(all_lrelu=True)
+    G = OmniGenerator(opts)
+    d, s = torch.zeros(1, 1, 16, 16), torch.zeros(1, 11, 16, 16)
+    with pytest.raises(ValueError, match="x MUST be provided"):
+        G.make_m_cond(d, s, None)
