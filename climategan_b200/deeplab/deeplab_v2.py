@@ -104,8 +104,12 @@ class DeepLabV2Decoder(nn.Module):
             nn.Conv2d(256, 256, kernel_size=3, stride=1, padding=1, bias=False), nn.BatchNorm2d(256), nn.ReLU(), nn.Dropout(0.5),
             nn.Conv2d(256, 256, kernel_size=3, stride=1, padding=1, bias=False), nn.BatchNorm2d(256), nn.ReLU(), nn.Dropout(0.1),
         ]
-        if opts.gen.s.upsample_featuremaps:
-            raise NotImplementedError("gen.s.upsample_featuremaps (False in defaults.yaml:138) is not built")
+        self._c0 = 0   # index of the first conv in self.conv
+        if opts.gen.s.upsample_featuremaps:   # deeplab_v2.py:154-155: nearest x2 in front of the head (state_dict keys shift by 1)
+            from ..blocks import InterpolateNearest2d
+
+            conv_modules = [InterpolateNearest2d(scale_factor=2)] + conv_modules
+            self._c0 = 1
         conv_modules += [nn.Conv2d(256, opts.gen.s.output_dim, kernel_size=1, stride=1)]
         self.conv = nn.Sequential(*conv_modules)
         self.output_dim = opts.gen.s.output_dim
@@ -122,15 +126,18 @@ class DeepLabV2Decoder(nn.Module):
         if z_depth is not None and self.use_dada:
             z = ops.mul(z, z_depth)
         y = self.aspp.forward_storage(z)
-        last = self.conv[8]
+        c0 = self._c0
+        if c0:
+            y = self.conv[0](y)
+        last = self.conv[c0 + 8]
         if self.training:
-            for i in (0, 4):
+            for i in (c0, c0 + 4):
                 y = ops.conv2d(y, self.conv[i].weight, None, pad=1)
                 y = ops.batchnorm_act(y, self.conv[i + 1], None, _lib.ACT_RELU)
                 y = ops.dropout(y, self.conv[i + 3].p, True)
             y = ops.conv2d(y, last.weight, last.bias)
         else:
-            for i in (0, 4):
+            for i in (c0, c0 + 4):
                 w, b = fold_bn(self.conv[i], self.conv[i + 1], y.dtype, cis=y.shape[-1])
                 y = ops.conv2d_infer(y, w, b, k=3, pad=1, act=_lib.ACT_RELU)
             wl = ops.pack_weight(last.weight, y.dtype, cis=y.shape[-1])

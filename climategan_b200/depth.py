@@ -1,18 +1,51 @@
-"""DADA depth decoder (``climategan/depth.py:25-158``): same module tree / state_dict keys; inference forward on storage
-tensors (Conv2dBlock(norm="batch") = conv + folded eval BatchNorm + leaky-relu in one launch)."""
+"""Depth decoders (``climategan/depth.py``): DADADepthDecoder (:25-158) and BaseDepthDecoder (:161-230), same module trees /
+state_dict keys; forwards on storage tensors (eval: Conv2dBlock(norm="batch") = conv + folded BatchNorm + leaky-relu in one
+launch; train: batch-statistics BatchNorm on the autograd tape)."""
 from __future__ import annotations
 
 import torch.nn as nn
 
 from . import _lib, ops
-from .blocks import Conv2dBlock, InterpolateNearest2d
+from .blocks import BaseDecoder, Conv2dBlock, InterpolateNearest2d
 from .deeplab.deeplab_v2 import find_target_size
 
 
 def create_depth_decoder(opts, no_init=False, verbose=0):
     if opts.gen.d.architecture == "base":
-        raise NotImplementedError("gen.d.architecture=base is not built (dada only)")
+        return BaseDepthDecoder(opts)
     return DADADepthDecoder(opts)
+
+
+class BaseDepthDecoder(BaseDecoder):
+    """``climategan.depth.BaseDepthDecoder`` (depth.py:161-230): a BaseDecoder (1x1 projection, ResBlocks, 0 or 1 nearest-x2 +
+    3x3 halving conv, 3x3 head) followed by a bilinear (align_corners) resize to the depth target size.  One output channel
+    (regression), or ``gen.d.classify.linspace.buckets`` logits when depth is classified (``classify.enable``; the loss is then
+    a cross-entropy against bucketised log-depth, losses.py:399-405, transforms.py:264-291)."""
+
+    def __init__(self, opts):
+        low_level_feats_dim = -1
+        if opts.gen.encoder.architecture == "deeplabv3":
+            if opts.gen.deeplabv3.backbone == "mobilenet":
+                raise NotImplementedError("the deeplabv3 mobilenet backbone is not built")
+            if opts.gen.d.use_low_level_feats:
+                low_level_feats_dim = 256
+        output_dim = 1 if not opts.gen.d.classify.enable else opts.gen.d.classify.linspace.buckets
+        super().__init__(n_upsample=1 if opts.gen.d.upsample_featuremaps else 0, n_res=opts.gen.d.n_res, input_dim=2048,
+                         proj_dim=opts.gen.d.proj_dim, output_dim=output_dim, norm=opts.gen.d.norm, activ=opts.gen.d.activ,
+                         pad_type=opts.gen.d.pad_type, output_activ="none", low_level_feats_dim=low_level_feats_dim)
+        self._target_size = find_target_size(opts, "d")
+
+    def set_target_size(self, size):
+        self._target_size = size[:2] if isinstance(size, (list, tuple)) else (size, size)
+
+    def forward_storage(self, z, cond=None, z_depth=None):
+        """-> (depth / depth logits storage [N,T,T,round8(output_dim)], None): this decoder has no DADA feature to share."""
+        if self._target_size is None:
+            raise ValueError("self._target_size should be set with self.set_target_size()")
+        d = BaseDecoder.forward_storage(self, z)
+        ts = self._target_size
+        th, tw = (ts, ts) if isinstance(ts, int) else ts
+        return ops.resize_bilinear(d, th, tw, align_corners=True), None
 
 
 class DADADepthDecoder(nn.Module):

@@ -90,8 +90,9 @@ class OmniGenerator(nn.Module):
     def decode_d(self, z):
         """``self.decoders["d"](z)`` of the reference (depth.py:128-155): (d NCHW fp32 [N,1,T,T], z_depth storage)."""
         with self._grad_ctx():
-            d, z_depth = self.decoders["d"].forward_storage(z)
-            return ops.from_storage(d, 1), z_depth
+            dec = self.decoders["d"]
+            d, z_depth = dec.forward_storage(z)
+            return ops.from_storage(d, getattr(dec, "output_dim", 1)), z_depth   # (> 1: bucket logits, gen.d.classify)
 
     def decode_s(self, z, z_depth=None):
         """``self.decoders["s"](z, z_depth)`` (deeplab_v2.py:181-198): seg logits NCHW fp32 [N,11,T,T]."""

@@ -44,9 +44,13 @@ def get_losses(opts, verbose=0, device=None, storage_dtype=torch.bfloat16):
         losses["G"]["p"]["featmatch"] = FeatMatchLoss()
         losses["D"]["p"] = losses["G"]["p"]["gan"]
     if "d" in opts.tasks:
-        if opts.gen.d.classify.enable or opts.gen.d.loss == "dada":
-            raise NotImplementedError("depth loss: only gen.d.loss='sigm' without classification (defaults.yaml:124,127) is built")
-        losses["G"]["tasks"]["d"] = SIGMLoss(opts.train.lambdas.G.d.gml)
+        if opts.gen.d.classify.enable:
+            losses["G"]["tasks"]["d"] = CrossEntropy()   # losses.py:399-405: bucketised log-depth, loss name ignored
+        elif opts.gen.d.loss == "dada":
+            raise NotImplementedError("depth loss 'dada' (reverse Huber) is not built: gen.d.loss='sigm' (defaults.yaml:127) or "
+                                      "gen.d.classify.enable")
+        else:
+            losses["G"]["tasks"]["d"] = SIGMLoss(opts.train.lambdas.G.d.gml)
     if "s" in opts.tasks:
         losses["G"]["tasks"]["s"] = {"crossent": CrossEntropy(), "minent": MinentLoss(),
                                      "advent": ADVENTAdversarialLoss(opts, gan_type=opts.dis.s.gan_type)}
@@ -236,6 +240,8 @@ class Trainer:
         prediction, z_depth = self.G.decode_d(z)
         if weight == 0 or (domain == "r" and "d" not in self.pseudo_training_tasks):
             return self._zero(), prediction, z_depth    # the reference evaluates the loss and discards it
+        if self.opts.gen.d.classify.enable:
+            target = target.squeeze(1)                  # trainer.py:1398-1399 (bucket indices [B,1,H,W] -> [B,H,W])
         full_loss = self.losses["G"]["tasks"]["d"](prediction, target) * weight
         return full_loss, prediction, z_depth
 

@@ -128,7 +128,8 @@ def default_masker_opts(tasks=("m", "s", "d"), nblocks=(3, 4, 23, 3), size=640, 
     o.gen.deeplabv2 = Dict(nblocks=list(nblocks), use_pretrained=False)
     o.gen.deeplabv3 = Dict(backbone="resnet", output_stride=8)
     o.gen.d = Dict(architecture="dada", upsample_featuremaps=True, output_dim=1, norm="batch", loss="sigm",
-                   classify=Dict(enable=False))
+                   activ="lrelu", n_res=1, proj_dim=32, pad_type="reflect",    # default-gen anchor (defaults.yaml:89-100)
+                   classify=Dict(enable=False, linspace=Dict(min=0.35, max=6.95, buckets=256)))
     o.gen.s = Dict(architecture="deeplabv2", num_classes=11, output_dim=11, use_advent=True, use_minent=True,
                    upsample_featuremaps=False, use_dada=True, depth_feat_fusion=False, depth_dada_fusion=False)
     o.gen.m = Dict(use_spade=False, output_dim=1, n_res=3, n_upsample=3, proj_dim=64, norm="spectral", activ="lrelu",
@@ -139,7 +140,7 @@ def default_masker_opts(tasks=("m", "s", "d"), nblocks=(3, 4, 23, 3), size=640, 
 
 
 def full_opts(nblocks=(2, 2, 3, 2), size=128, latent=16, n_up=4, ndf=8, n_layers=3, num_d=2, tasks=("d", "s", "m", "p"),
-              use_spade=False):
+              use_spade=False, overrides=None):
     """shared/trainer/defaults.yaml values on a small network (deeplabv2 encoder, as the north star names).  use_spade: the
     paper / release masker (MaskSpadeDecoder conditioned on make_m_cond(d, s, x), defaults.yaml:166-186)."""
     with_p = "p" in tasks
@@ -179,6 +180,12 @@ def full_opts(nblocks=(2, 2, 3, 2), size=128, latent=16, n_up=4, ndf=8, n_layers
                    m=Dict(bce=1, tv=1, gi=0.05, pl4m=1),
                    p=Dict(context=0, dm=1, featmatch=10, gan=1, reconstruction=0, tv=0, vgg=10)),
             advent=Dict(ent_main=0.5, ent_aux=0.0, ent_var=0.1, adv_main=1.0, adv_aux=0.0, dis_main=1.0, dis_aux=0.0, WGAN_gp=10)))
+    for dotted, value in (overrides or {}).items():   # "gen.d.architecture": "base" — the reference's test-scenario notation
+        node = o
+        *path, leaf = dotted.split(".")
+        for k in path:
+            node = node[k]
+        node[leaf] = value
     return o
 
 
@@ -198,5 +205,7 @@ def synth_batch(opts, batch, size, seed):
         if dom != "rf":
             data["s"] = torch.from_numpy(rs.randint(0, 11, size=(batch, 1, q, q)).astype(np.int64))
             data["d"] = torch.from_numpy(rs.random_sample((batch, 1, q, q)).astype(np.float32))
+            if opts.gen.d.classify.enable and dom == "s":   # transforms.BucketizeDepth (:264-291): bucket indices on the sim domain
+                data["d"] = torch.from_numpy(rs.randint(0, opts.gen.d.classify.linspace.buckets, size=(batch, 1, q, q)).astype(np.int64))
         out[dom] = {"data": data, "domain": [dom] * batch, "mode": ["train"] * batch, "paths": {}}
     return out

@@ -1,9 +1,11 @@
-"""Sensitivity of the SPADE-masker step fixture (tests/golden/masker_step_spade.*): gradients of the REFERENCE Trainer's first
-update_G under a 1e-7 / 1e-6 relative perturbation of the generator weights (build container only; needs /root/reference).
-The numbers set the tolerances of tests/test_gpu_full_step.py::test_spade_masker_step_*.
-usage: PYTHONPATH=. python scripts/sensitivity_spade_step.py"""
+"""Sensitivity of a train-step fixture (default tests/golden/masker_step_spade.*): gradients of the REFERENCE Trainer's first
+update_G / update_D under a 1e-7 / 1e-6 / 1e-3 relative perturbation of the generator weights (build container only; needs
+/root/reference).  The numbers set the tolerances of tests/test_gpu_full_step.py::test_spade_masker_step_* and
+test_base_depth_classify_step_*.
+usage: PYTHONPATH=. python scripts/sensitivity_spade_step.py [fixture name]"""
 import json
 import os
+import sys
 
 import numpy as np
 import torch
@@ -13,13 +15,14 @@ from oracle import refshim
 from tests.golden.weights import fill_state_dict
 from tests.helpers import GOLDEN
 
-meta = json.load(open(os.path.join(GOLDEN, "masker_step_spade.json")))
+CASE = sys.argv[1] if len(sys.argv) > 1 else "masker_step_spade"
+meta = json.load(open(os.path.join(GOLDEN, CASE + ".json")))
 size, batch = meta["size"], meta["batch"]
 refshim.load("blocks").SPADEResnetBlock.cuda = lambda self, *a, **k: self
 
 
 def run(eps):
-    opts = rt.full_opts(size=size, tasks=tuple(meta["tasks"]), use_spade=True)
+    opts = rt.full_opts(size=size, tasks=tuple(meta["tasks"]), use_spade=meta.get("use_spade", False), overrides=meta.get("overrides"))
     t = rt.build_reference_trainer(opts, size)
     rt.load_weights(t)
     torch.manual_seed(0)

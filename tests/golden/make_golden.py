@@ -23,6 +23,11 @@ from oracle import refshim  # noqa: E402
 from tests.golden.weights import fill_state_dict, synth_inputs  # noqa: E402
 from climategan_b200.utils import default_painter_opts  # noqa: E402
 
+# reference test scenarios 2 + 12 (tests/test_trainer.py:208-260): base depth decoder classifying bucketised log-depth, no DADA
+# fusion, nearest-x2 in front of the segmentation head; 16 buckets keep the fixture small
+BASE_DEPTH_CLASSIFY = {"gen.d.architecture": "base", "gen.d.classify.enable": True, "gen.d.classify.linspace.buckets": 16,
+                       "gen.m.use_dada": False, "gen.s.use_dada": False, "gen.s.upsample_featuremaps": True}
+
 CASES = {
     # name: (latent_dim, spade_n_up, batch, size)   channels 40->40->40->20 exercise the %8 padding
     "painter_small": (40, 3, 2, 32),
@@ -310,7 +315,8 @@ def _sample(a, cap=8192):
     return a[::k].copy()
 
 
-def run_full_step_case(name="full_step", batch=2, size=128, tasks=("d", "s", "m", "p"), use_spade=False, pl4m=False):
+def run_full_step_case(name="full_step", batch=2, size=128, tasks=("d", "s", "m", "p"), use_spade=False, pl4m=False,
+                       overrides=None):
     """Two iterations of the reference's OWN ``Trainer.update_G`` / ``update_D`` (trainer.py:989-1032) on tasks [d,s,m,p]
     — deeplabv2 masker (ResNet [2,2,3,2], train-mode BatchNorm, dropout p=0) + SPADE painter + all three discriminators —
     driven as ``run_epoch`` does (oracle/ref_trainer.py).  Stores every logged loss, the gradient norm of every parameter
@@ -318,7 +324,8 @@ def run_full_step_case(name="full_step", batch=2, size=128, tasks=("d", "s", "m"
     second iteration (ExtraAdam extrapolation then step)."""
     from oracle import ref_trainer as rt
 
-    opts = rt.full_opts(size=size, tasks=tasks, use_spade=use_spade)
+    opts = rt.full_opts(size=size, tasks=tasks, use_spade=use_spade, overrides=overrides)
+    base_depth = opts.gen.d.architecture == "base"
     if use_spade:
         blocks_mod = refshim.load("blocks")
         blocks_mod.SPADEResnetBlock.cuda = lambda self, *a, **k: self   # masker.py:196 hard-codes .cuda() (SURVEY.md §8c patch 1)
@@ -328,8 +335,12 @@ def run_full_step_case(name="full_step", batch=2, size=128, tasks=("d", "s", "m"
     mdb = rt.synth_batch(opts, batch, size, seed=7)
     arrays = {}
     logs = []
-    full_g = ["encoder.model.conv1.weight", "encoder.model.layer3.1.conv2.weight", "decoders.d.enc4_2.conv.weight", "decoders.d.enc4_2.norm.weight",
-              "decoders.s.aspp.aspp3.atrous_conv.weight", "decoders.s.conv.8.bias"]
+    full_g = ["encoder.model.conv1.weight", "encoder.model.layer3.1.conv2.weight", "decoders.s.aspp.aspp3.atrous_conv.weight"]
+    if base_depth:   # BaseDepthDecoder: projection, a ResBlock conv, the head
+        full_g += ["decoders.d.proj_conv.conv.weight", "decoders.d.model.0.model.0.model.1.conv.weight", "decoders.d.model.0.model.0.model.0.norm.weight"]
+    else:
+        full_g += ["decoders.d.enc4_2.conv.weight", "decoders.d.enc4_2.norm.weight"]
+    full_g += ["decoders.s.conv.%d.bias" % (9 if opts.gen.s.upsample_featuremaps else 8)]
     if use_spade:   # MaskSpadeDecoder: fc_conv, a SPADE layer's three convs, a spectral conv of a block, the mask head
         full_g += ["decoders.m.fc_conv.conv.module.weight_bar", "decoders.m.spade_blocks.0.norm_0.mlp_shared.0.weight",
                    "decoders.m.spade_blocks.1.norm_1.mlp_gamma.weight", "decoders.m.spade_blocks.2.norm_s.mlp_beta.bias",
@@ -361,7 +372,7 @@ def run_full_step_case(name="full_step", batch=2, size=128, tasks=("d", "s", "m"
         logs.append(_flatten_logs(t.logger.losses.to_dict()))
     gsd, dsd = t.G.state_dict(), t.D.state_dict()
     finals = ["encoder.model.bn1.running_mean", "encoder.model.layer4.0.bn2.running_var", "decoders.s.aspp.global_avg_pool.2.running_var",
-              "decoders.d.enc4_1.norm.running_mean"]
+              "decoders.d.proj_conv.norm.running_mean" if base_depth else "decoders.d.enc4_1.norm.running_mean"]
     if use_spade:
         finals += ["decoders.m.spade_blocks.0.norm_0.param_free_norm.running_mean", "decoders.m.spade_blocks.2.norm_1.param_free_norm.running_var",
                    "decoders.m.fc_conv.norm.running_var", "decoders.m.spade_blocks.1.conv_1.module.weight_u"]
@@ -374,7 +385,7 @@ def run_full_step_case(name="full_step", batch=2, size=128, tasks=("d", "s", "m"
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
     meta = {"case": name, "batch": batch, "size": size, "seeds": {"G": 21, "D": 22, "vgg": 23, "inputs": 7},
             "g_shapes": [[k, list(s_)] for k, s_ in g_shapes], "d_shapes": [[k, list(s_)] for k, s_ in d_shapes],
-            "tasks": list(tasks), "use_spade": bool(use_spade), "pl4m": bool(pl4m),
+            "tasks": list(tasks), "use_spade": bool(use_spade), "pl4m": bool(pl4m), "overrides": overrides or {},
             "v_shapes": [[k, list(s_)] for k, s_ in (v_shapes or [])], "g_param_names": [k for k, _ in t.G.named_parameters()],
             "d_param_names": [k for k, _ in t.D.named_parameters()], "logs": logs, "full_g": full_g, "full_d": full_d,
             "reference": "cc-ai/climategan @ /root/reference: climategan.trainer.Trainer.update_G/update_D (unmodified), CPU, torch "
@@ -542,6 +553,7 @@ if __name__ == "__main__":
     run_full_step_case()
     run_full_step_case(name="masker_step_spade", tasks=("d", "s", "m"), use_spade=True)
     run_full_step_case(name="full_step_pl4m", pl4m=True)
+    run_full_step_case(name="masker_step_base_depth_classify", tasks=("d", "s", "m"), overrides=BASE_DEPTH_CLASSIFY)
     run_infer_all_case()
     run_masker_spade_case()
     run_masker_v3_case()

@@ -111,7 +111,8 @@ def _names_shapes(module):
 def test_generator_and_discriminator_surfaces_match_the_reference_for_every_built_configuration():
     """state_dict keys / shapes / order and the parameter order of OmniGenerator and OmniDiscriminator against the lists the
     REFERENCE modules produced (stored with the goldens), for every configuration that is built: v2 masker + painter (base mask
-    decoder), the SPADE mask decoder (paper / release configuration), the reference-default v3 masker with the base and with
+    decoder), the SPADE mask decoder (paper / release configuration), the base depth decoder with depth classification and the up-sampled segmentation
+    head, the reference-default v3 masker with the base and with
     the SPADE mask decoder, and the painter with use_final_shortcut.  Construction needs no GPU."""
     import json
 
@@ -124,10 +125,10 @@ def test_generator_and_discriminator_surfaces_match_the_reference_for_every_buil
         return json.load(open(os.path.join(GOLDEN, name + ".json")))
 
     # full step (tasks d, s, m, p), base and pl4m fixtures share the architecture; SPADE-masker step (tasks d, s, m)
-    for name in ("full_step", "full_step_pl4m", "masker_step_spade"):
+    for name in ("full_step", "full_step_pl4m", "masker_step_spade", "masker_step_base_depth_classify"):
         meta = meta_of(name)
         opts = full_opts(size=meta["size"], tasks=tuple(meta.get("tasks", ("d", "s", "m", "p"))),
-                         use_spade=meta.get("use_spade", False))
+                         use_spade=meta.get("use_spade", False), overrides=meta.get("overrides"))
         G = OmniGenerator(opts, latent_shape=(meta["size"], meta["size"]))
         D = OmniDiscriminator(opts)
         assert _names_shapes(G) == [(k, tuple(s)) for k, s in meta["g_shapes"]], name
