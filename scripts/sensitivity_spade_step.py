@@ -19,6 +19,11 @@ CASE = sys.argv[1] if len(sys.argv) > 1 else "masker_step_spade"
 meta = json.load(open(os.path.join(GOLDEN, CASE + ".json")))
 size, batch = meta["size"], meta["batch"]
 refshim.load("blocks").SPADEResnetBlock.cuda = lambda self, *a, **k: self
+if (meta.get("overrides") or {}).get("gen.encoder.architecture") == "deeplabv3":   # the fixture's shallow ResNet (make_golden.py)
+    _dl, _rn = refshim.load("deeplab", "deeplab.resnet101_v3")
+    _nb = list(meta["overrides"]["gen.deeplabv3.nblocks"])
+    _dl.ResNet101 = lambda output_stride=8, BatchNorm=None, verbose=0, no_init=False: _rn.ResNet(
+        _rn.Bottleneck, _nb, output_stride, BatchNorm, verbose=verbose, no_init=no_init)
 
 
 def run(eps):

@@ -28,6 +28,9 @@ from climategan_b200.utils import default_painter_opts  # noqa: E402
 BASE_DEPTH_CLASSIFY = {"gen.d.architecture": "base", "gen.d.classify.enable": True, "gen.d.classify.linspace.buckets": 16,
                        "gen.m.use_dada": False, "gen.s.use_dada": False, "gen.s.upsample_featuremaps": True}
 
+# the reference-DEFAULT masker (deeplabv3 encoder / decoder, mask decoder with low-level features; defaults.yaml:101,136)
+V3_MASKER = {"gen.encoder.architecture": "deeplabv3", "gen.s.architecture": "deeplabv3", "gen.deeplabv3.nblocks": [2, 2, 3, 2]}
+
 CASES = {
     # name: (latent_dim, spade_n_up, batch, size)   channels 40->40->40->20 exercise the %8 padding
     "painter_small": (40, 3, 2, 32),
@@ -329,6 +332,12 @@ def run_full_step_case(name="full_step", batch=2, size=128, tasks=("d", "s", "m"
     if use_spade:
         blocks_mod = refshim.load("blocks")
         blocks_mod.SPADEResnetBlock.cuda = lambda self, *a, **k: self   # masker.py:196 hard-codes .cuda() (SURVEY.md §8c patch 1)
+    v3 = opts.gen.encoder.architecture == "deeplabv3"
+    if v3:   # a shallow ResNet of the same architecture (the reference hard-codes [3,4,23,3], resnet101_v3.py:190-203)
+        deeplab_mod, resnet_mod = refshim.load("deeplab", "deeplab.resnet101_v3")
+        nb = list(opts.gen.deeplabv3.nblocks)
+        deeplab_mod.ResNet101 = lambda output_stride=8, BatchNorm=None, verbose=0, no_init=False: resnet_mod.ResNet(
+            resnet_mod.Bottleneck, nb, output_stride, BatchNorm, verbose=verbose, no_init=no_init)
     t = rt.build_reference_trainer(opts, size)
     g_shapes, d_shapes, v_shapes = rt.load_weights(t)
     t.use_pl4m = bool(pl4m)   # what Trainer.train() flips at epoch gen.p.pl4m_epoch (trainer.py:899-909)
@@ -351,6 +360,14 @@ def run_full_step_case(name="full_step", batch=2, size=128, tasks=("d", "s", "m"
     if "p" in tasks:
         full_g += ["painter.conv_img.weight"]
         full_d += ["p.discriminator_0.model0.0.module.weight_bar"]
+    if v3:   # deeplabv3 names: backbone without the .model prefix, ASPPv3Plus / Decoder, mask decoder with low-level features
+        full_g += ["encoder.conv1.weight", "encoder.layer3.1.conv2.weight", "encoder.layer4.1.conv2.weight",
+                   "decoders.s.aspp.conv_out.conv.weight", "decoders.s.decoder.conv_low.conv.bias", "decoders.s.decoder.conv_out.weight",
+                   "decoders.m.low_level_conv.conv.module.weight_bar", "decoders.m.merge_feats_conv.conv.module.weight_bar"]
+    # keep what this configuration actually has (task subsets, v2 / v3 names)
+    gp_names, dp_names = {k for k, _ in t.G.named_parameters()}, {k for k, _ in t.D.named_parameters()}
+    full_g = [k for k in full_g if k in gp_names]
+    full_d = [k for k in full_d if k in dp_names]
     for it in range(2):
         for p_ in t.D.parameters():
             p_.requires_grad = False
@@ -378,7 +395,9 @@ def run_full_step_case(name="full_step", batch=2, size=128, tasks=("d", "s", "m"
                    "decoders.m.fc_conv.norm.running_var", "decoders.m.spade_blocks.1.conv_1.module.weight_u"]
     else:
         finals += ["decoders.m.model.0.model.1.model.0.conv.module.weight_u"]
-    for k in full_g + finals:
+    if v3:
+        finals += ["encoder.bn1.running_mean", "encoder.layer4.1.bn2.running_var", "decoders.s.aspp.conv_out.bn.running_var"]
+    for k in full_g + [f for f in finals if f in gsd]:
         arrays["G.final::" + k] = _sample(gsd[k].numpy())
     for k in full_d:
         arrays["D.final::" + k] = _sample(dsd[k].numpy())
@@ -428,7 +447,7 @@ def run_infer_all_case(name="infer_all", batch=2, size=320):
     print(name, {k: (v.shape, str(v.dtype)) for k, v in arrays.items()}, "npz bytes", os.path.getsize(os.path.join(HERE, name + ".npz")))
 
 
-def run_masker_spade_case(name="masker_spade", nblocks=(2, 2, 3, 2), batch=2, size=64):
+def run_masker_spade_case(name="masker_spade", nblocks=(2, 2, 3, 2), batch=2, size=64, cond_nc=15):
     """The paper / release masker configuration (gen.m.use_spade): reference OmniGenerator.decode in eval mode with the
     MaskSpadeDecoder conditioned on make_m_cond(d, s, x) (masker.py:59-231).  Two consecutive decodes (the spectral-norm
     power iteration advances on every forward)."""
@@ -439,6 +458,7 @@ def run_masker_spade_case(name="masker_spade", nblocks=(2, 2, 3, 2), batch=2, si
     opts = default_masker_opts(nblocks=nblocks, size=size)
     opts.gen.m.use_spade = True
     opts.gen.m.spade.activations = Dict(all_lrelu=True)
+    opts.gen.m.spade.cond_nc = cond_nc   # 15: normalize(d) | softmax(s) | x ; 12: without x (reference test scenario 14)
     torch.manual_seed(0)
     G = generator_mod.OmniGenerator(opts)
     shapes = [(k, tuple(v.shape)) for k, v in G.state_dict().items()]
@@ -451,7 +471,7 @@ def run_masker_spade_case(name="masker_spade", nblocks=(2, 2, 3, 2), batch=2, si
     arrays = {"m1": out1["m"].numpy(), "m2": out2["m"].numpy(), "d": out1["d"].numpy(), "s": out1["s"].numpy()}
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
     meta = {"case": name, "nblocks": list(nblocks), "batch": batch, "size": size, "weight_seed": 78, "input_seed": 4,
-            "shapes": [[k, list(s_)] for k, s_ in shapes],
+            "shapes": [[k, list(s_)] for k, s_ in shapes], "cond_nc": cond_nc,
             "reference": "cc-ai/climategan @ /root/reference (generator, masker.MaskSpadeDecoder, norms.SPADE(batch), blocks)",
             "torch": torch.__version__}
     with open(os.path.join(HERE, name + ".json"), "w") as f:
@@ -554,7 +574,10 @@ if __name__ == "__main__":
     run_full_step_case(name="masker_step_spade", tasks=("d", "s", "m"), use_spade=True)
     run_full_step_case(name="full_step_pl4m", pl4m=True)
     run_full_step_case(name="masker_step_base_depth_classify", tasks=("d", "s", "m"), overrides=BASE_DEPTH_CLASSIFY)
+    run_full_step_case(name="masker_step_v3", tasks=("d", "s", "m"), overrides=V3_MASKER)
+    run_full_step_case(name="mask_only_step_v3", tasks=("m",), overrides=V3_MASKER)
     run_infer_all_case()
     run_masker_spade_case()
+    run_masker_spade_case(name="masker_spade12", cond_nc=12)
     run_masker_v3_case()
     run_masker_v3_case(name="masker_v3_spade", use_spade=True)

@@ -90,17 +90,19 @@ def test_masker_full_size_shapes(cuda):
     assert float(out["m"].min()) >= 0.0 and float(out["m"].max()) <= 1.0
 
 
+@pytest.mark.parametrize("case", ["masker_spade", "masker_spade12"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_masker_spade_decoder_matches_reference_golden(cuda, dtype):
+def test_masker_spade_decoder_matches_reference_golden(cuda, dtype, case):
     """gen.m.use_spade (paper / release configuration): MaskSpadeDecoder conditioned on make_m_cond(d, s, x) — SPADE with a
     BatchNorm param-free norm read from running statistics — against the reference OmniGenerator.decode, two consecutive
     decodes (the spectral-norm vectors advance).  Tolerances: fp32 storage 2e-4 of full scale, bf16 4e-2."""
     from climategan_b200.utils import Dict
 
-    meta, g, sd, (x, _, _) = load_golden("masker_spade")
+    meta, g, sd, (x, _, _) = load_golden(case)   # masker_spade12: cond_nc = 12, conditioning without x (reference scenario 14)
     opts = default_masker_opts(nblocks=tuple(meta["nblocks"]), size=meta["size"])
     opts.gen.m.use_spade = True
     opts.gen.m.spade.activations = Dict(all_lrelu=True)
+    opts.gen.m.spade.cond_nc = meta.get("cond_nc", 15)
     G = OmniGenerator(opts, storage_dtype=dtype)
     G.load_state_dict(sd, strict=True)
     G = G.to(cuda).eval()

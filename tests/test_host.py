@@ -125,7 +125,8 @@ def test_generator_and_discriminator_surfaces_match_the_reference_for_every_buil
         return json.load(open(os.path.join(GOLDEN, name + ".json")))
 
     # full step (tasks d, s, m, p), base and pl4m fixtures share the architecture; SPADE-masker step (tasks d, s, m)
-    for name in ("full_step", "full_step_pl4m", "masker_step_spade", "masker_step_base_depth_classify"):
+    for name in ("full_step", "full_step_pl4m", "masker_step_spade", "masker_step_base_depth_classify", "masker_step_v3",
+                 "mask_only_step_v3"):
         meta = meta_of(name)
         opts = full_opts(size=meta["size"], tasks=tuple(meta.get("tasks", ("d", "s", "m", "p"))),
                          use_spade=meta.get("use_spade", False), overrides=meta.get("overrides"))
