@@ -74,6 +74,7 @@ class _Logger:
     def __init__(self):
         self.losses = Dict(gen=Dict(), disc=Dict())
         self.global_step = 0
+        self.epoch = 0
 
     def log_losses(self, model_to_update="G", mode="train"):
         return None
@@ -89,7 +90,7 @@ class Trainer:
         self.logger = _Logger()
         self.G = self.D = self.g_opt = self.d_opt = self.losses = None
         self.g_scheduler = self.d_scheduler = None
-        self.kitti_pretrain = False
+        self.kitti_pretrain = bool(opts.train.kitti.pretrain)   # trainer.py:101
         self.use_pl4m = False
         self.data_parallel = False
         self.pseudo_training_tasks = set(opts.train.pseudo.tasks or [])
@@ -177,6 +178,57 @@ class Trainer:
         self.logger.losses.disc.total_loss = d_loss.detach()
         self.logger.log_losses(model_to_update="D", mode="train")
         return d_loss
+
+    # ---------------------------------------------------------------- epoch driver
+    def update_learning_rates(self):
+        """trainer.py:696-700."""
+        if self.g_scheduler is not None:
+            self.g_scheduler.step()
+        if self.d_scheduler is not None:
+            self.d_scheduler.step()
+
+    def run_epoch(self, train_loaders):
+        """trainer.py:924-987 for an iterable of multi-batch tuples (what ``zip(*loaders["train"].values())`` yields, :633): per
+        tuple — random domain order (tutils.shuffle_batch_tuple :318-328), batches to the device, update_G (with D frozen),
+        update_D unless the VKITTI2 pre-training is on (:971), global_step += 1 — then the learning-rate schedulers.  Data
+        loading, comet logging and the progress bar stay with the caller."""
+        import numpy as np
+
+        assert self.is_setup
+        self.G.train()
+        if self.D is not None:
+            self.D.train()
+        for multi_batch_tuple in train_loaders:
+            assert isinstance(multi_batch_tuple, (tuple, list)) and len(multi_batch_tuple) > 0
+            perm = np.random.permutation(len(multi_batch_tuple))
+            multi_domain_batch = {multi_batch_tuple[i]["domain"][0]: self.batch_to_device(multi_batch_tuple[i]) for i in perm}
+            self.update_G(multi_domain_batch)
+            if self.d_opt is not None and not self.kitti_pretrain:
+                self.update_D(multi_domain_batch)
+            self.logger.global_step += 1
+        if not self.kitti_pretrain:
+            self.update_learning_rates()
+
+    def train(self, train_loaders, epochs=None, on_epoch_end=None):
+        """trainer.py:888-922: ``epochs`` (default opts.train.epochs) calls of :meth:`run_epoch` with the epoch-boundary switches
+        of the reference — the painter loss for the masker turns on at epoch ``gen.p.pl4m_epoch`` (when ``gen.m.use_pl4m``), the
+        VKITTI2 pre-training ends after ``train.kitti.epochs`` epochs, pseudo-label training after ``train.pseudo.epochs``.
+        ``train_loaders``: an iterable of multi-batch tuples, or a callable ``epoch -> iterable`` (the caller swaps the kitti
+        loaders for the base ones there: ``switch_data``, :817-845).  ``on_epoch_end(trainer)`` stands where the reference
+        evaluates and saves."""
+        assert self.is_setup
+        n = self.opts.train.epochs if epochs is None else epochs
+        for self.logger.epoch in range(self.logger.epoch, self.logger.epoch + n):
+            if (self.logger.epoch == self.opts.gen.p.pl4m_epoch and "p" in self.opts.tasks and self.opts.gen.m.use_pl4m
+                    and sum(p.numel() for p in self.G.painter.parameters()) > 0):
+                self.use_pl4m = True
+            self.run_epoch(train_loaders(self.logger.epoch) if callable(train_loaders) else train_loaders)
+            if on_epoch_end is not None:
+                on_epoch_end(self)
+            if self.opts.train.kitti.epochs and self.logger.epoch == self.opts.train.kitti.epochs - 1:
+                self.kitti_pretrain = False
+            if self.opts.train.pseudo.epochs and self.logger.epoch == self.opts.train.pseudo.epochs - 1:
+                self.pseudo_training_tasks = set()
 
     def get_G_loss(self, multi_domain_batch, verbose=0):
         """trainer.py:1162-1182."""

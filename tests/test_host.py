@@ -172,3 +172,43 @@ def test_make_m_cond_needs_x_for_15_channels():
     d, s = torch.zeros(1, 1, 16, 16), torch.zeros(1, 11, 16, 16)
     with pytest.raises(ValueError, match="x MUST be provided"):
         G.make_m_cond(d, s, None)
+
+
+def test_run_epoch_and_train_follow_the_reference_control_flow():
+    """Trainer.run_epoch / train (trainer.py:888-987) with the compute stubbed out: one update_G + update_D per multi-batch
+    tuple and a global_step increment; no update_D (and no scheduler step) while the VKITTI2 pre-training is on; pl4m switches on
+    at gen.p.pl4m_epoch; kitti pre-training and pseudo-label training end at their epoch counts."""
+    import torch.nn as nn
+
+    from climategan_b200.trainer import Trainer
+    from climategan_b200.utils import full_opts
+
+    opts = full_opts(size=64)
+    opts.gen.m.use_pl4m = True
+    opts.gen.p.pl4m_epoch = 1
+    opts.train.kitti = {"pretrain": True, "epochs": 2}
+    opts.train.pseudo = {"tasks": ["d"], "epochs": 3}
+    opts.train.epochs = 4
+    t = Trainer(opts, device=torch.device("cpu"))
+    assert t.kitti_pretrain and t.pseudo_training_tasks == {"d"}
+    t.is_setup = True
+    t.G, t.D = nn.Module(), nn.Module()
+    t.G.painter = nn.Linear(2, 2)
+    t.d_opt = object()
+    calls, sched = [], []
+    t.update_G = lambda mdb: calls.append(("G", tuple(sorted(mdb)), t.use_pl4m, t.kitti_pretrain))
+    t.update_D = lambda mdb: calls.append(("D", tuple(sorted(mdb))))
+    t.batch_to_device = lambda b: b
+    t.update_learning_rates = lambda: sched.append(t.logger.epoch)
+    batches = [tuple({"domain": [d], "data": {}} for d in ("r", "s", "rf")) for _ in range(2)]
+    seen = []
+    t.train(lambda epoch: (seen.append(epoch), batches)[1], on_epoch_end=lambda tr: seen.append(("end", tr.logger.epoch)))
+    assert seen == [0, ("end", 0), 1, ("end", 1), 2, ("end", 2), 3, ("end", 3)]
+    assert t.logger.global_step == 8 and t.logger.epoch == 3
+    g_calls = [c for c in calls if c[0] == "G"]
+    assert len(g_calls) == 8 and all(c[1] == ("r", "rf", "s") for c in g_calls)
+    assert [c[2] for c in g_calls] == [False, False] + [True] * 6           # pl4m from epoch 1 on
+    assert [c[3] for c in g_calls] == [True] * 4 + [False] * 4             # kitti pre-training during epochs 0 and 1
+    assert len([c for c in calls if c[0] == "D"]) == 4                      # no update_D while pre-training
+    assert sched == [2, 3]                                                  # ... and no scheduler step
+    assert t.pseudo_training_tasks == set()
