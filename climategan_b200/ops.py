@@ -38,8 +38,13 @@ def _L():
     return _lib.lib()
 
 
+def _on_device(x: torch.Tensor) -> bool:
+    """The one place that decides whether a tensor may be handed to the library (there is no CPU path)."""
+    return x.is_cuda
+
+
 def _chk_storage(x: torch.Tensor, name: str = "x") -> None:
-    if x.dim() != 4 or not x.is_contiguous() or x.shape[-1] % 8 or x.dtype not in _DT or not x.is_cuda:
+    if x.dim() != 4 or not x.is_contiguous() or x.shape[-1] % 8 or x.dtype not in _DT or not _on_device(x):
         raise ValueError(
             f"{name}: expected a contiguous CUDA NHWC storage tensor with C%8==0 (fp32/bf16), got "
             f"shape={tuple(x.shape)} dtype={x.dtype} device={x.device} contiguous={x.is_contiguous()}"
@@ -511,7 +516,7 @@ class _FromStorage(Function):
 def to_storage(x_nchw: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """NCHW fp32 (reference layout) -> NHWC storage tensor with zero channel padding."""
     _lib.require_device()
-    if not x_nchw.is_cuda:
+    if not _on_device(x_nchw):
         raise _lib.CgbError("climategan_b200 tensors must live on a CUDA device (no CPU path)")
     return _ToStorage.apply(x_nchw, dtype)
 
