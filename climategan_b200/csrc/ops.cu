@@ -1466,6 +1466,43 @@ extern "C" int cgb_paste_bwd(const float* gout, const float* m, float* gfake, in
   return after_launch("paste_bwd");
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Forward weight packing in ONE launch: OIHW fp32 (the nn.Parameter / the spectrally-normalised weight) -> [cos][kh*kw][cis]
+// storage dtype, zero in the channel padding.  Replaces torch.zeros + permute/reshape copy + slice assignment (3 launches per
+// weight, ~400 weights re-packed after every optimiser update: the host-side profile, scripts/host_profile_dryrun.py).
+// One thread per 8 consecutive input channels of one (co, tap): reads are strided by kh*kw floats (weights are small and
+// L2-resident), writes are 16-byte vectors.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, long long total_vec, int o, int i, int taps, int cis) {
+  const int iv = cis >> 3;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_vec;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(idx % iv);
+    const long long r = idx / iv;
+    const int t = (int)(r % taps);
+    const int co = (int)(r / taps);
+    float vals[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ci = v * 8 + j;
+      vals[j] = (co < o && ci < i) ? w[((long long)co * i + ci) * taps + t] : 0.f;
+    }
+    Vec8<T>::store(wp + idx * 8, vals);
+  }
+}
+
+extern "C" int cgb_pack_weight(const float* w, void* wp, int32_t dtype, int32_t o, int32_t i, int32_t taps, int32_t cos,
+                               int32_t cis, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(w && wp, "pack_weight: null pointer");
+  CGB_REQUIRE(o >= 1 && i >= 1 && taps >= 1 && cos >= o && cis >= i && cis % 8 == 0, "pack_weight: bad shape o=%d i=%d cos=%d cis=%d",
+              o, i, cos, cis);
+  const long long total = (long long)cos * taps * (cis / 8);
+  DISPATCH_T(dtype, pack_weight_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(w, (T*)wp, total, o, i, taps, cis);)
+  return after_launch("pack_weight");
+}
+
 extern "C" int cgb_mask_cond_bwd(const float* x, const void* gcond, float* gm, int32_t dtype, int32_t n, int32_t hw, int32_t cs,
                                  void* stream) {
   CGB_CHECK_DEVICE();

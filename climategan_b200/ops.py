@@ -54,10 +54,22 @@ def _chk_storage(x: torch.Tensor, name: str = "x") -> None:
 # ------------------------------------------------------------------------------------------------
 # weight packing:  OIHW fp32  <->  [Os][kh*kw][Is] storage dtype
 # ------------------------------------------------------------------------------------------------
-def pack_weight(w: torch.Tensor, dtype: torch.dtype, cis: Optional[int] = None, cos: Optional[int] = None) -> torch.Tensor:
+# CGB_PACK_KERNEL=1: pack in one launch of cgb_pack_weight instead of three torch launches (written when the GPU budget of
+# round 1 was spent: bit-exactness against the torch path is tests/test_gpu_ops.py::test_pack_weight_kernel; off until run)
+_PACK_KERNEL = os.environ.get("CGB_PACK_KERNEL", "0") == "1"
+
+
+def pack_weight(w: torch.Tensor, dtype: torch.dtype, cis: Optional[int] = None, cos: Optional[int] = None,
+                kernel: Optional[bool] = None) -> torch.Tensor:
     o, i, kh, kw = w.shape
     cos = cos or round8(o)
     cis = cis or round8(i)
+    if (_PACK_KERNEL if kernel is None else kernel) and w.dtype == torch.float32:
+        wd = w.detach()
+        wd = wd if wd.is_contiguous() else wd.contiguous()
+        wp = torch.empty(cos, kh * kw, cis, dtype=dtype, device=w.device)
+        check(_L().cgb_pack_weight(_p(wd), _p(wp), _DT[dtype], o, i, kh * kw, cos, cis, _st()), "pack_weight")
+        return wp
     wp = torch.zeros(cos, kh * kw, cis, dtype=dtype, device=w.device)
     wp[:o, :, :i] = w.detach().permute(0, 2, 3, 1).reshape(o, kh * kw, i)
     return wp

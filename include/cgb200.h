@@ -111,6 +111,10 @@ int cgb_conv2d_dgrad(const cgb_conv_desc* d, const void* gy, const void* w, cons
  * wt[c][T-1-t][o] = w[o][t][c] — the stride-1 dgrad is then an ordinary conv of gy with wt (pad' = dil*(k-1)-pad).
  * cgb_conv2d_dgrad takes w (SIMT engine) and/or wt (tcgen05 engine; NULL -> SIMT). */
 int cgb_conv2d_pack_dgrad_weight(const cgb_conv_desc* d, const void* w, void* wt, void* stream);
+/* Forward packing in one launch: w OIHW fp32 [o][i][kh][kw] (nn.Conv2d.weight, or W / sigma of SpectralNorm, norms.py:111-112)
+ * -> wp [cos][taps = kh*kw][cis] in `dtype`, zeros in the channel padding (cos >= o, cis >= i, cis % 8 == 0). */
+int cgb_pack_weight(const float* w, void* wp, int32_t dtype, int32_t o, int32_t i, int32_t taps, int32_t cos, int32_t cis,
+                    void* stream);
 
 /* Weight (+bias) gradient: gw[co][kh*kw][ci] (fp32), gbias[co] (fp32, optional).
  * accumulate=0 zero-fills gw/gbias first. */
