@@ -107,7 +107,10 @@ class Trainer:
         if not inference:
             self.D = create_discriminator(self.opts, self.device, storage_dtype=self.storage_dtype)
             self.g_opt, self.g_scheduler, self.lr_names_g = get_optimizer(self.G, self.opts.gen.opt, self.opts.tasks)
-            self.d_opt, self.d_scheduler, self.lr_names_d = get_optimizer(self.D, self.opts.dis.opt, self.opts.tasks, True)
+            if sum(p.numel() for p in self.D.parameters()) > 0:
+                self.d_opt, self.d_scheduler, self.lr_names_d = get_optimizer(self.D, self.opts.dis.opt, self.opts.tasks, True)
+            else:   # no adversarial loss configured (trainer.py:762-767): nothing to optimise, update_D is never called
+                self.d_opt, self.d_scheduler = None, None
             self.losses = get_losses(self.opts, self.verbose, device=self.device, storage_dtype=self.storage_dtype)
             self.G.train()
             self.D.train()
@@ -170,6 +173,8 @@ class Trainer:
         return g_loss
 
     def update_D(self, multi_domain_batch, verbose=0):
+        if self.d_opt is None:   # run_epoch only calls update_D when there is a discriminator optimiser (trainer.py:971)
+            return None
         self.d_opt.zero_grad()
         d_loss = self.get_D_loss(multi_domain_batch, verbose)
         d_loss.backward()

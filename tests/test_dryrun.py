@@ -62,3 +62,43 @@ def _flat(d, prefix=""):
         else:
             out[prefix + k] = v
     return out
+
+
+_V3 = {"gen.encoder.architecture": "deeplabv3", "gen.s.architecture": "deeplabv3", "gen.deeplabv3.nblocks": [2, 2, 3, 2]}
+_BASE_D = {"gen.d.architecture": "base", "gen.m.use_dada": False, "gen.s.use_dada": False}
+MORE = {
+    # configurations without a golden of their own (the reference's scenario matrix, tests/test_trainer.py:205-308, and
+    # option combinations around it): the host path must run and enqueue the same work every step
+    "dada_ms": dict(tasks=("d", "s", "m"), overrides={"gen.m.use_dada": True}),
+    "v3_spade_msdp": dict(tasks=("d", "s", "m", "p"), use_spade=True, overrides=dict(_V3)),
+    "base_depth_regression": dict(tasks=("d", "s", "m"), overrides=dict(_BASE_D)),
+    "v3_base_depth_low_level": dict(tasks=("d", "s", "m"), overrides=dict(_V3, **_BASE_D, **{"gen.d.use_low_level_feats": True})),
+    "painter_only": dict(tasks=("p",)),
+    "spade_cond12_step": dict(tasks=("d", "s", "m"), use_spade=True, overrides={"gen.m.spade.cond_nc": 12}),
+    "spade_detached_cond": dict(tasks=("d", "s", "m"), use_spade=True, overrides={"gen.m.spade.detach": True}),
+    "no_adversarial_losses": dict(tasks=("d", "s", "m"), overrides={"gen.m.use_advent": False, "gen.s.use_advent": False}),
+    "depth_and_seg_only": dict(tasks=("d", "s")),
+    "adam": dict(tasks=("d", "s", "m", "p"), overrides={"gen.opt.optimizer": "Adam", "dis.opt.optimizer": "Adam"}),
+}
+
+
+@pytest.mark.parametrize("name", sorted(MORE))
+def test_other_configurations_run_the_host_path(name):
+    opts = full_opts(size=128, **MORE[name])
+    with noop_library() as lib:
+        t = Trainer(opts, device=torch.device("cpu")).setup(input_shape=(128, 128))
+        if name == "no_adversarial_losses":
+            assert t.d_opt is None   # trainer.py:762-767
+        mdb = {dom: t.batch_to_device(b) for dom, b in synth_batch(opts, 2, 128, 3).items()}
+        per_step = []
+        for _ in range(3):
+            before = dict(lib.calls)
+            t.update_G(mdb)
+            t.update_D(mdb)
+            t.logger.global_step += 1
+            per_step.append({k: v - before.get(k, 0) for k, v in lib.calls.items() if v != before.get(k, 0)})
+        assert per_step[1] == per_step[2]
+        trainable = [n for n, p in t.G.named_parameters() if p.requires_grad]
+        no_grad = [n for n in trainable if dict(t.G.named_parameters())[n].grad is None]
+        # every trainable generator parameter is reached by some loss (frozen BatchNorm affines are not trainable)
+        assert not no_grad, no_grad[:10]
