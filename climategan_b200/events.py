@@ -8,7 +8,7 @@ import random
 
 import torch
 
-from . import _lib
+from . import _lib, ops
 from ._lib import check
 
 
@@ -26,7 +26,7 @@ def _L():
 
 def _img(x):
     _lib.require_device()
-    if not x.is_cuda:
+    if not ops._on_device(x):
         raise _lib.CgbError("climategan_b200 tensors must live on a CUDA device (no CPU path)")
     return x.detach().contiguous().float()
 

@@ -102,3 +102,21 @@ def test_other_configurations_run_the_host_path(name):
         no_grad = [n for n in trainable if dict(t.G.named_parameters())[n].grad is None]
         # every trainable generator parameter is reached by some loss (frozen BatchNorm affines are not trainable)
         assert not no_grad, no_grad[:10]
+
+
+@pytest.mark.parametrize("name,kw", [("v2", {}), ("v3", dict(overrides=_V3)), ("v2_spade", dict(use_spade=True)),
+                                     ("v3_spade", dict(use_spade=True, overrides=_V3))])
+def test_infer_all_host_path(name, kw):
+    """Trainer.infer_all (trainer.py:218-334) — masker, painter, flood / wildfire / smog compositing, with and without the
+    cloudy sky — for the four masker configurations, tensors out (the uint8 edge needs pinned memory)."""
+    opts = full_opts(size=128, **kw)
+    with noop_library() as lib:
+        t = Trainer(opts, device=torch.device("cpu")).setup(inference=True, input_shape=(128, 128))
+        x = torch.rand(2, 3, 128, 128) * 2 - 1
+        out = t.infer_all(x, numpy=False, bin_value=0.5)
+        assert {k: tuple(v.shape) for k, v in out.items()} == {k: (2, 3, 128, 128) for k in ("flood", "wildfire", "smog")}
+        n1 = sum(lib.calls.values())
+        t.infer_all(x, numpy=False, bin_value=0.5)
+        assert sum(lib.calls.values()) == 2 * n1        # the same work every call
+        out = t.infer_all(x, numpy=False, cloudy=True, ignore_event={"smog"})
+        assert out["smog"] is None and out["flood"].shape == (2, 3, 128, 128)
