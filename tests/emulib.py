@@ -355,6 +355,304 @@ class EmuLib(NoopLib):
             P.copy_(Cc + u)
 
 
+    # ---- masker training path -------------------------------------------------------------------------------------------
+    def e_bn_train_fwd(self, x, weight, bias, residual, y, mean, rstd, ws, running_mean, running_var, nbt, dtype, npix, c,
+                       c_logical, momentum, eps, act, slope, stream):
+        dt = _DT[dtype]
+        X = _t(x, (npix, c), dt).double()
+        m, v = X.mean(0), X.var(0, unbiased=False)
+        Mn, Rs = _t(mean, (c,), torch.float32), _t(rstd, (c,), torch.float32)
+        Mn.copy_(m)
+        Rs.copy_(1.0 / torch.sqrt(v + eps))
+        rm, rv = _t(running_mean, (c_logical,), torch.float32), _t(running_var, (c_logical,), torch.float32)
+        if rm is not None and rv is not None:
+            unb = v[:c_logical] * npix / (npix - 1) if npix > 1 else v[:c_logical]
+            rm.copy_((1 - momentum) * rm + momentum * m[:c_logical].float())
+            rv.copy_((1 - momentum) * rv + momentum * unb.float())
+            nb = _t(nbt, (1,), torch.int64)
+            if nb is not None:
+                nb.add_(1)
+        self.e_bn_apply_fwd(x, mean, rstd, weight, bias, residual, y, dtype, npix, c, act, slope, stream)
+
+    def e_bn_apply_fwd(self, x, mean, rstd, weight, bias, residual, y, dtype, npix, c, act, slope, stream):
+        dt = _DT[dtype]
+        xhat = (_t(x, (npix, c), dt).float() - _t(mean, (c,), torch.float32)) * _t(rstd, (c,), torch.float32)
+        W, B = _t(weight, (c,), torch.float32), _t(bias, (c,), torch.float32)
+        pre = xhat * W + B if W is not None else xhat
+        R = _t(residual, (npix, c), dt)
+        if R is not None:
+            pre = pre + R.float()
+        _t(y, (npix, c), dt).copy_(_act(pre, act, slope))
+
+    def e_bn_train_bwd(self, x, mean, rstd, weight, y, gy, gpre, gx, sums, dtype, npix, c, act, slope, stream):
+        dt = _DT[dtype]
+        r = _t(rstd, (c,), torch.float32)
+        xhat = (_t(x, (npix, c), dt).float() - _t(mean, (c,), torch.float32)) * r
+        gp = _t(gy, (npix, c), dt).float()
+        if act != 0:
+            gp = gp * _dact_from_out(_t(y, (npix, c), dt).float(), act, slope)
+        _t(gpre, (npix, c), dt).copy_(gp)
+        S = _t(sums, (c, 2), torch.float64)
+        S[:, 0] = gp.double().sum(0)
+        S[:, 1] = (gp * xhat).double().sum(0)
+        GX = _t(gx, (npix, c), dt)
+        if GX is not None:
+            W = _t(weight, (c,), torch.float32)
+            k = r * W if W is not None else r
+            GX.copy_(k * (gp - S[:, 0].float() / npix - xhat * S[:, 1].float() / npix))
+
+    def e_bn_update_running(self, mean, rstd, running_mean, running_var, c, count, momentum, eps, stream):
+        m, r = _t(mean, (c,), torch.float32), _t(rstd, (c,), torch.float32)
+        var = torch.clamp(1.0 / (r.double() ** 2) - eps, min=0)
+        unb = var * count / (count - 1) if count > 1 else var
+        rm, rv = _t(running_mean, (c,), torch.float32), _t(running_var, (c,), torch.float32)
+        rm.copy_((1 - momentum) * rm + momentum * m)
+        rv.copy_((1 - momentum) * rv + momentum * unb.float())
+
+    def _nchw(self, p, n, h, w, c, dt):
+        return _t(p, (n, h, w, c), dt).float().permute(0, 3, 1, 2)
+
+    def _vjp(self, fn, X, gy):
+        with torch.enable_grad():
+            X = X.clone().requires_grad_(True)
+            (g,) = torch.autograd.grad(fn(X), X, gy)
+        return g
+
+    def e_reflect_pad_fwd(self, x, y, dtype, n, h, w, c, pad, stream):
+        dt = _DT[dtype]
+        _t(y, (n, h + 2 * pad, w + 2 * pad, c), dt).copy_(F.pad(self._nchw(x, n, h, w, c, dt), (pad,) * 4, mode="reflect").permute(0, 2, 3, 1))
+
+    def e_reflect_pad_bwd(self, gy, gx, dtype, n, h, w, c, pad, stream):
+        dt = _DT[dtype]
+        g = self._vjp(lambda X: F.pad(X, (pad,) * 4, mode="reflect"), torch.zeros(n, c, h, w), self._nchw(gy, n, h + 2 * pad, w + 2 * pad, c, dt))
+        _t(gx, (n, h, w, c), dt).copy_(g.permute(0, 2, 3, 1))
+
+    @staticmethod
+    def _pool(X, pad, ho):
+        hi = X.shape[-2]
+        ceil = ho != (hi + 2 * pad - 3) // 2 + 1
+        return F.max_pool2d(X, 3, 2, pad, ceil_mode=ceil)
+
+    def e_maxpool3s2_ceil_fwd(self, x, y, dtype, n, hi, wi, ho, wo, c, stream):
+        self.e_maxpool3s2_fwd(x, y, dtype, n, hi, wi, ho, wo, c, 0, stream)
+
+    def e_maxpool3s2_ceil_bwd(self, x, gy, gx, dtype, n, hi, wi, ho, wo, c, stream):
+        self.e_maxpool3s2_bwd(x, gy, gx, dtype, n, hi, wi, ho, wo, c, 0, stream)
+
+    def e_maxpool3s2_fwd(self, x, y, dtype, n, hi, wi, ho, wo, c, pad, stream):
+        dt = _DT[dtype]
+        Y = self._pool(self._nchw(x, n, hi, wi, c, dt), pad, ho)
+        assert tuple(Y.shape[-2:]) == (ho, wo), (Y.shape, ho, wo)
+        _t(y, (n, ho, wo, c), dt).copy_(Y.permute(0, 2, 3, 1))
+
+    def e_maxpool3s2_bwd(self, x, gy, gx, dtype, n, hi, wi, ho, wo, c, pad, stream):
+        dt = _DT[dtype]
+        g = self._vjp(lambda X: self._pool(X, pad, ho), self._nchw(x, n, hi, wi, c, dt), self._nchw(gy, n, ho, wo, c, dt))
+        _t(gx, (n, hi, wi, c), dt).copy_(g.permute(0, 2, 3, 1))
+
+    def e_resize_bilinear_fwd(self, x, y, dtype, n, hi, wi, ho, wo, c, align_corners, stream):
+        dt = _DT[dtype]
+        Y = F.interpolate(self._nchw(x, n, hi, wi, c, dt), size=(ho, wo), mode="bilinear", align_corners=bool(align_corners))
+        _t(y, (n, ho, wo, c), dt).copy_(Y.permute(0, 2, 3, 1))
+
+    def e_resize_bilinear_bwd(self, gy, gx, dtype, n, hi, wi, ho, wo, c, align_corners, stream):
+        dt = _DT[dtype]
+        g = self._vjp(lambda X: F.interpolate(X, size=(ho, wo), mode="bilinear", align_corners=bool(align_corners)),
+                      torch.zeros(n, c, hi, wi), self._nchw(gy, n, ho, wo, c, dt))
+        _t(gx, (n, hi, wi, c), dt).copy_(g.permute(0, 2, 3, 1))
+
+    def e_resize_bicubic_fwd(self, x, y, dtype, n, hi, wi, ho, wo, c, stream):
+        dt = _DT[dtype]
+        Y = F.interpolate(self._nchw(x, n, hi, wi, c, dt), size=(ho, wo), mode="bicubic", align_corners=False)
+        _t(y, (n, ho, wo, c), dt).copy_(Y.permute(0, 2, 3, 1))
+
+    def e_resize_nearest_bwd(self, gy, gx, dtype, n, hi, wi, ho, wo, c, stream):
+        dt = _DT[dtype]
+        g = self._vjp(lambda X: F.interpolate(X, size=(ho, wo), mode="nearest"), torch.zeros(n, c, hi, wi), self._nchw(gy, n, ho, wo, c, dt))
+        _t(gx, (n, hi, wi, c), dt).copy_(g.permute(0, 2, 3, 1))
+
+    def e_channel_mean(self, x, y, dtype, pixels, cs, c_logical, stream):
+        dt = _DT[dtype]
+        Y = _t(y, (pixels, 8), dt)
+        Y.zero_()
+        Y[:, 0] = _t(x, (pixels, cs), dt).float()[:, :c_logical].mean(1)
+
+    def e_channel_mean_bwd(self, gy, gx, dtype, pixels, cs, c_logical, stream):
+        dt = _DT[dtype]
+        G = _t(gx, (pixels, cs), dt)
+        G.zero_()
+        G[:, :c_logical] = (_t(gy, (pixels, 8), dt).float()[:, :1] / c_logical).expand(pixels, c_logical)
+
+    def e_mul(self, a, b, y, dtype, count, stream):
+        dt = _DT[dtype]
+        _t(y, (count,), dt).copy_(_t(a, (count,), dt).float() * _t(b, (count,), dt).float())
+
+    def e_broadcast_hw(self, src, dst, dtype, n, hw, c, scale, stream):
+        dt = _DT[dtype]
+        _t(dst, (n, hw, c), dt).copy_((_t(src, (n, 1, c), dt).float() * scale).expand(n, hw, c))
+
+    def e_dropout(self, x, y, dtype, count, p, seed, stream):
+        X = _t(x, (count,), _DT[dtype])
+        if p == 0:
+            _t(y, (count,), _DT[dtype]).copy_(X)
+            return
+        # a mask that is a function of (seed, element index), like the kernel's counter-based one (not the same stream: the
+        # parity fixtures run with p = 0); the same call on the gradient is the backward
+        keep = torch.rand(count, generator=torch.Generator().manual_seed(int(seed) % (2 ** 63))) >= p
+        _t(y, (count,), _DT[dtype]).copy_(X.float() * keep / (1 - p))
+
+    def e_im2col_strided(self, x, y, dtype, n, h, w, cs_in, c, k, pad, dil, stride, cs_out, stream):
+        dt = _DT[dtype]
+        ho, wo = (h + 2 * pad - dil * (k - 1) - 1) // stride + 1, (w + 2 * pad - dil * (k - 1) - 1) // stride + 1
+        X = _t(x, (n, h, w, cs_in), dt).float()[..., :c].permute(0, 3, 1, 2)
+        cols = F.unfold(X, k, dilation=dil, padding=pad, stride=stride)
+        cols = cols.view(n, c, k * k, ho * wo).permute(0, 3, 2, 1).reshape(n, ho, wo, k * k * c)
+        Y = _t(y, (n, ho, wo, cs_out), dt)
+        Y.zero_()
+        Y[..., : k * k * c] = cols
+
+    @staticmethod
+    def _m_cond(D, S, XR):
+        n = D.shape[0]
+        mn = D.reshape(n, -1).min(1)[0].reshape(n, 1, 1)
+        t = D - mn
+        t = t / t.reshape(n, -1).max(1)[0].reshape(n, 1, 1)
+        parts = [t, torch.softmax(S, -1)]
+        if XR is not None:
+            parts.append(XR)
+        return torch.cat(parts, -1)
+
+    def e_make_m_cond(self, d, s, xr, mm, out, dtype, n, hw, ss, ns, cs_out, stream):
+        dt = _DT[dtype]
+        D = _t(d, (n, hw, 8), dt).float()[..., :1]
+        S = _t(s, (n, hw, ss), dt).float()[..., :ns]
+        XR = _t(xr, (n, hw, 8), dt)
+        XR = XR.float()[..., :3] if XR is not None else None
+        MM = _t(mm, (n, 2), torch.float32)
+        MM[:, 0], MM[:, 1] = D.reshape(n, -1).min(1)[0], D.reshape(n, -1).max(1)[0]
+        res = self._m_cond(D, S, XR)
+        O = _t(out, (n, hw, cs_out), dt)
+        O.zero_()
+        O[..., : res.shape[-1]] = res
+
+    def e_make_m_cond_bwd(self, d, out, mm, gout, gd, gs, dtype, n, hw, ss, ns, cs_out, stream):
+        dt = _DT[dtype]
+        D = _t(d, (n, hw, 8), dt).float()[..., :1]
+        # the softmax is re-derived from the forward's output p: gs = p (g - <g, p>)
+        P = _t(out, (n, hw, cs_out), dt).float()[..., 1:1 + ns]
+        G = _t(gout, (n, hw, cs_out), dt).float()
+        g0, gp = G[..., :1], G[..., 1:1 + ns]
+        with torch.enable_grad():
+            Dg = D.clone().requires_grad_(True)
+            mn = Dg.reshape(n, -1).min(1)[0].reshape(n, 1, 1)
+            t = Dg - mn
+            t = t / t.reshape(n, -1).max(1)[0].reshape(n, 1, 1)
+            (gD,) = torch.autograd.grad(t, Dg, g0)
+        GD = _t(gd, (n, hw, 8), dt)
+        GD.zero_()
+        GD[..., :1] = gD
+        GS = _t(gs, (n, hw, ss), dt)
+        GS.zero_()
+        GS[..., :ns] = P * (gp - (gp * P).sum(-1, keepdim=True))
+
+    def e_mask_cond_bwd(self, x, gcond, gm, dtype, n, hw, cs, stream):
+        G = _t(gcond, (n, hw, cs), _DT[dtype]).float()[..., :3].permute(0, 2, 1)
+        _t(gm, (n, 1, hw), torch.float32).copy_(-(_t(x, (n, 3, hw), torch.float32) * G).sum(1, keepdim=True))
+
+    def e_paste_bwd_mask(self, gout, x, fake, gm, n, hw, stream):
+        d = _t(fake, (n, 3, hw), torch.float32) - _t(x, (n, 3, hw), torch.float32)
+        _t(gm, (n, 1, hw), torch.float32).copy_((_t(gout, (n, 3, hw), torch.float32) * d).sum(1, keepdim=True))
+
+    # ---- masker losses (NCHW fp32): value added to `loss`, gradient of that value written (include/cgb200.h) ----------------
+    def _loss(self, fn, X, loss, gx):
+        with torch.enable_grad():
+            Xg = X.clone().requires_grad_(True)
+            val = fn(Xg)
+            g = torch.autograd.grad(val, Xg, allow_unused=True)[0] if gx is not None else None
+        _t(loss, (1,), torch.float32).add_(val.detach().float())
+        if gx is not None:
+            gx.copy_(g if g is not None else torch.zeros_like(X))
+
+    def e_softmax_nchw_fwd(self, x, y, n, c, hw, stream):
+        _t(y, (n, c, hw), torch.float32).copy_(torch.softmax(_t(x, (n, c, hw), torch.float32), 1))
+
+    def e_softmax_nchw_bwd(self, y, gy, gx, n, c, hw, stream):
+        Y, G = _t(y, (n, c, hw), torch.float32), _t(gy, (n, c, hw), torch.float32)
+        _t(gx, (n, c, hw), torch.float32).copy_(Y * (G - (G * Y).sum(1, keepdim=True)))
+
+    def e_cross_entropy_nchw(self, logits, target, loss, glogits, n, c, hw, stream):
+        T = _t(target, (n, hw), torch.int64)
+        self._loss(lambda X: F.cross_entropy(X, T), _t(logits, (n, c, hw), torch.float32), loss, _t(glogits, (n, c, hw), torch.float32))
+
+    @staticmethod
+    def _entropy(P, c):
+        import math
+
+        return -P * torch.log2(P + 1e-30) / math.log2(c)
+
+    def e_entropy_nchw(self, p, depth, ge, out, n, c, hw, backward, stream):
+        P = _t(p, (n, c, hw), torch.float32)
+        D = _t(depth, (n, 1, hw), torch.float32)
+        f = (lambda X: self._entropy(X, c) * D) if D is not None else (lambda X: self._entropy(X, c))
+        O = _t(out, (n, c, hw), torch.float32)
+        if not backward:
+            O.copy_(f(P))
+        else:
+            O.copy_(self._vjp(f, P, _t(ge, (n, c, hw), torch.float32)))
+
+    def e_minent_loss(self, p, loss, gp, acc, n, c, hw, version, lambda_var, stream):
+        def f(X):
+            e = self._entropy(X, c)
+            if version == 1:
+                return e.sum() / (n * hw)
+            dm = e - e.sum() / (n * hw)
+            return (e + lambda_var * dm * dm).sum() / (n * hw)
+
+        self._loss(f, _t(p, (n, c, hw), torch.float32), loss, _t(gp, (n, c, hw), torch.float32))
+
+    def e_sigmoid_pair(self, logits, gprob, out, n, hw, backward, stream):
+        L = _t(logits, (n, 1, hw), torch.float32)
+        sg = torch.sigmoid(L)
+        if not backward:
+            _t(out, (n, 2, hw), torch.float32).copy_(torch.cat([sg, 1 - sg], 1))
+        else:
+            G = _t(gprob, (n, 2, hw), torch.float32)
+            _t(out, (n, 1, hw), torch.float32).copy_((G[:, :1] - G[:, 1:]) * sg * (1 - sg))
+
+    def e_tv_loss(self, x, loss, gx, n, c, h, w, stream):
+        def f(X):
+            h_tv = torch.pow(X[:, :, 1:, :] - X[:, :, : h - 1, :], 2).sum()
+            w_tv = torch.pow(X[:, :, :, 1:] - X[:, :, :, : w - 1], 2).sum()
+            return 2 * (h_tv / (c * (h - 1) * w) + w_tv / (c * h * (w - 1))) / n
+
+        self._loss(f, _t(x, (n, c, h, w), torch.float32), loss, _t(gx, (n, c, h, w), torch.float32))
+
+    def e_bce_logits_loss(self, x, target, loss, gx, count, stream):
+        T = _t(target, (count,), torch.float32)
+        self._loss(lambda X: F.binary_cross_entropy_with_logits(X, T), _t(x, (count,), torch.float32), loss, _t(gx, (count,), torch.float32))
+
+    def e_ground_intersection_loss(self, pred, ground, loss, count, stream):
+        v = (1.0 * ((_t(ground, (count,), torch.float32) - _t(pred, (count,), torch.float32)) > 0.5)).mean()
+        _t(loss, (1,), torch.float32).add_(v)
+
+    def e_sigm_loss(self, pred, target, loss, gpred, ws, n, h, w, gmweight, scales, stream):
+        T = _t(target, (n, 1, h, w), torch.float32)
+
+        def f(P):   # SIGMLoss.forward, losses.py:250-278 (Sobel kernels expanded to [B,1,3,3] as there)
+            t_p, t_t = torch.median(P), torch.median(T)
+            s_p, s_t = torch.mean(torch.abs(P - t_p)), torch.mean(torch.abs(T - t_t))
+            R = (P - t_p) / s_p - (T - t_t) / s_t
+            sx = torch.tensor([[1.0, 0, -1], [2, 0, -2], [1, 0, -1]]).expand(n, 1, 3, 3)
+            sy = torch.tensor([[1.0, 2, 1], [0, 0, 0], [-1, -2, -1]]).expand(n, 1, 3, 3)
+            gm = 0
+            for k in range(scales):
+                R_ = F.interpolate(R, scale_factor=1 / 2 ** k)
+                gm = gm + torch.sum(torch.abs(F.conv2d(R_, sx)) + torch.abs(F.conv2d(R_, sy)))
+            return 0.5 / (h * w) * torch.sum(torch.abs(R)) + gmweight / (h * w) * gm
+
+        self._loss(f, _t(pred, (n, 1, h, w), torch.float32), loss, _t(gpred, (n, 1, h, w), torch.float32))
+
+
 @contextlib.contextmanager
 def emulated_library():
     real = _lib.lib()

@@ -20,7 +20,7 @@ pytestmark = pytest.mark.gpu
 def _sample(a, cap=8192):
     a = a.detach().float().cpu().numpy().reshape(-1)
     k = max(1, -(-a.size // cap))
-    return a[::k]
+    return a[::k].copy()   # (a copy: on a CPU device .cpu().numpy() aliases the live gradient buffer — tests/test_emulated.py)
 
 
 def _flatten(d, prefix=""):

@@ -29,7 +29,7 @@ def _opts(meta):
 
 def _sample(a, cap=8192):
     a = a.detach().float().cpu().numpy().reshape(-1)
-    return a[::max(1, -(-a.size // cap))]
+    return a[::max(1, -(-a.size // cap))].copy()
 
 
 @pytest.mark.parametrize("case", ["masker_v3", "masker_v3_spade"])
