@@ -142,6 +142,12 @@ class EmuLib(NoopLib):
             s = GY.sum((0, 2, 3))
             gb.copy_(gb + s if accumulate else s)
 
+    def e_pack_weight(self, w, wp, dtype, o, i, taps, cos, cis, stream):
+        W = _t(w, (o, i, taps), torch.float32)
+        P = _t(wp, (cos, taps, cis), _DT[dtype])
+        P.zero_()
+        P[:o, :, :i] = W.permute(0, 2, 1)
+
     def e_im2col(self, x, y, dtype, n, h, w, cs_in, c, k, pad, dil, cs_out, stream):
         dt = _DT[dtype]
         X = _t(x, (n, h, w, cs_in), dt).float()[..., :c].permute(0, 3, 1, 2)
