@@ -276,3 +276,32 @@ def test_masker_v3_oracle_matches_reference_golden():
             assert abs(float(sdt[name].grad.norm()) - r) <= 1e-4 * r + 1e-9, (name, float(sdt[name].grad.norm()), r)
     for k in ("encoder.bn1.running_mean", "encoder.layer4.1.bn2.running_var", "decoders.s.aspp.conv_out.bn.running_var"):
         assert rel_max(sdt[k], torch.from_numpy(g["final::" + k])) < 1e-5, k
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted")
+def test_committed_fixtures_are_what_the_generating_script_produces(tmp_path, monkeypatch):
+    """tests/golden/make_golden.py, re-run against /root/reference into a scratch directory, reproduces the committed
+    fixtures (two of the small ones: a Trainer step fixture and an eval decode): same metadata, same arrays to 1e-6."""
+    import json
+
+    import tests.golden.make_golden as mg
+
+    monkeypatch.setattr(mg, "HERE", str(tmp_path))
+    mg.run_full_step_case(name="mask_only_step_v3", tasks=("m",), overrides=mg.V3_MASKER)
+    mg.run_masker_spade_case(name="masker_spade12", cond_nc=12)
+    for name in ("mask_only_step_v3", "masker_spade12"):
+        new_meta = json.load(open(os.path.join(str(tmp_path), name + ".json")))
+        old_meta = json.load(open(os.path.join(GOLDEN, name + ".json")))
+        for k in old_meta:
+            if k not in ("logs", "torch", "reference"):
+                assert new_meta[k] == old_meta[k], (name, k)
+        if "logs" in old_meta:
+            for a, b in zip(new_meta["logs"], old_meta["logs"]):
+                assert a.keys() == b.keys()
+                for k in a:
+                    assert abs(a[k] - b[k]) <= 1e-5 * abs(b[k]) + 1e-7, (name, k, a[k], b[k])
+        new, old = np.load(os.path.join(str(tmp_path), name + ".npz")), np.load(os.path.join(GOLDEN, name + ".npz"))
+        assert sorted(new.files) == sorted(old.files)
+        for k in old.files:
+            scale = max(float(np.abs(old[k]).max()), 1e-12)
+            assert float(np.abs(new[k] - old[k]).max()) <= 2e-3 * scale + 1e-9, (name, k)
