@@ -659,16 +659,131 @@ class EmuLib(NoopLib):
         self._loss(f, _t(pred, (n, 1, h, w), torch.float32), loss, _t(gpred, (n, 1, h, w), torch.float32))
 
 
+    # ---- inference events (Trainer.infer_all): restated from the contracts in include/cgb200.h ------------------------------
+    @staticmethod
+    def _norm(t, mm, lo=0.0, hi=1.0):   # tutils.normalize :566-577 with the per-sample (min, max) the caller computed
+        n = t.shape[0]
+        mn = mm[:, 0].view(n, *([1] * (t.dim() - 1)))
+        mx = mm[:, 1].view(n, *([1] * (t.dim() - 1)))
+        return lo + (hi - lo) * (t - mn) / (mx - mn)
+
+    def e_minmax_per_sample(self, x, mm, n, count, stream):
+        X = _t(x, (n, count), torch.float32)
+        M = _t(mm, (n, 2), torch.float32)
+        M[:, 0], M[:, 1] = X.min(1)[0], X.max(1)[0]
+
+    def e_fire_tone(self, x, mm, out, gray_sum, n, hw, contrast, brightness, stream):
+        from torchvision.transforms.functional import adjust_brightness, adjust_contrast
+
+        t = self._norm(_t(x, (n, 3, hw), torch.float32), _t(mm, (n, 2), torch.float32), 0, 255).clone()   # fire.py:80-86
+        t[:, 2] -= 20
+        t[:, 1] -= 10
+        t[:, 0] += 40
+        t = t.clamp_(0, 255).to(torch.uint8).view(n, 3, hw, 1)
+        t = adjust_brightness(adjust_contrast(t, contrast_factor=contrast), brightness_factor=brightness)            # :90-91
+        _t(out, (n, 3, hw), torch.float32).copy_(t.view(n, 3, hw).float())
+
+    def e_sky_mask(self, seg, out, n, c, hs, ws, sky_idx, crop_bottom, stream):
+        m = (torch.argmax(_t(seg, (n, c, hs, ws), torch.float32), 1) == sky_idx).float()                              # tutils :579-596
+        if crop_bottom:
+            m[:, 2 * hs // 3:, :] = 0                                                                                    # fire.py:95-97
+        _t(out, (n, hs, ws), torch.float32).copy_(m)
+
+    def e_plane_resize_nearest(self, x, y, n, hi, wi, ho, wo, stream):
+        _t(y, (n, ho, wo), torch.float32).copy_(F.interpolate(_t(x, (n, 1, hi, wi), torch.float32), (ho, wo))[:, 0])
+
+    def e_box_dilate(self, x, tmp, y, n, h, w, radius_w, radius_h, stream):
+        X = _t(x, (n, 1, h, w), torch.float32)                                    # increase_sky_mask on a binary mask, fire.py:15-47
+        Y = F.max_pool2d(F.pad(X, (radius_w, radius_w, radius_h, radius_h)), (2 * radius_h + 1, 2 * radius_w + 1), 1)
+        _t(y, (n, h, w), torch.float32).copy_((Y[:, 0] >= 1).float() if False else Y[:, 0].clamp(max=1))
+
+    def e_gauss_blur(self, x, tmp, y, n, h, w, ksize, sigma, stream):
+        ax = torch.arange(ksize, dtype=torch.float64) - ksize // 2              # kornia get_gaussian_kernel2d + filter2d, restated
+        g = torch.exp(-ax * ax / (2 * sigma * sigma))                            # (separable, in fp64: the 2-D kernel is an outer product)
+        g = g / g.sum()
+        X = F.pad(_t(x, (n, 1, h, w), torch.float32).double(), (ksize // 2,) * 4, mode="reflect")
+        X = F.conv2d(X, g.view(1, 1, 1, ksize))
+        X = F.conv2d(X, g.view(1, 1, ksize, 1))
+        _t(y, (n, h, w), torch.float32).copy_(X[:, 0])
+
+    def e_fire_paste(self, img, sky, out, n, h, w, fr, fg, fb, transparency, brightness, stream):
+        from torchvision.transforms.functional import adjust_brightness
+
+        I = _t(img, (n, 3, h, w), torch.float32)
+        m = transparency / 255.0 * _t(sky, (n, 1, h, w), torch.float32)                                               # fire.py:130-133
+        filt = torch.tensor([fr, fg, fb]).view(1, 3, 1, 1)
+        t = m * filt + (1.0 - m) * I
+        t = adjust_brightness(t.to(torch.uint8), brightness).float()                                                   # :120-121
+        t[:, :, 0, 0] = 255.0                                                                                           # :124-125
+        t[:, :, -1, -1] = 0.0
+        _t(out, (n, 3, h, w), torch.float32).copy_(t)
+
+    def e_smog(self, x, mmx, d, mmd, out, n, h, w, hd, wd, airlight, beta, alpha, yr, yg, yb, stream):
+        X = self._norm(_t(x, (n, 3, h, w), torch.float32), _t(mmx, (n, 2), torch.float32))                             # srgb2lrgb, tutils :534-538
+        irr = torch.where(X <= 0.04045, X / 12.92, ((X + 0.055) / 1.055) ** 2.4)
+        D = self._norm(_t(d, (n, 1, hd, wd), torch.float32), _t(mmd, (n, 2), torch.float32), 0.3, 1.0)               # trainer.py:1911-1913
+        D = 1.0 / D
+        mm2 = torch.stack([D.reshape(n, -1).min(1)[0], D.reshape(n, -1).max(1)[0]], 1)
+        D = self._norm(D, mm2, 0.1, 1.0)
+        D = F.interpolate(D, size=(h, w), mode="bilinear", align_corners=True)
+        tr = torch.exp(-beta * D)
+        sm = tr * irr + (1 - tr) * airlight
+        sm = torch.where(sm <= 0.0031308, 12.92 * sm, 1.055 * torch.pow(sm, 1 / 2.4) - 0.055)                        # lrgb2srgb :541-563
+        yel = torch.tensor([yr, yg, yb]).view(1, 3, 1, 1)
+        _t(out, (n, 3, h, w), torch.float32).copy_(sm * (1 - alpha) + yel * alpha)
+
+    def e_perlin_noise(self, angles, out, h, w, res0, res1, stream):
+        import math
+
+        A = _t(angles, (res0 + 1, res1 + 1), torch.float32)                                                             # rand_perlin_2d, tutils :648-686
+        delta = (res0 / h, res1 / w)
+        d = (h // res0, w // res1)
+        grid = torch.stack(torch.meshgrid(torch.arange(0, res0, delta[0]), torch.arange(0, res1, delta[1]), indexing="ij"), -1) % 1
+        grads = torch.stack((torch.cos(A), torch.sin(A)), -1)
+
+        def tile(s1, s2):
+            return grads[s1[0]:s1[1], s2[0]:s2[1]].repeat_interleave(d[0], 0).repeat_interleave(d[1], 1)
+
+        def dot(grad, shift):
+            return (torch.stack((grid[:h, :w, 0] + shift[0], grid[:h, :w, 1] + shift[1]), -1) * grad[:h, :w]).sum(-1)
+
+        n00, n10 = dot(tile([0, -1], [0, -1]), [0, 0]), dot(tile([1, None], [0, -1]), [-1, 0])
+        n01, n11 = dot(tile([0, -1], [1, None]), [0, -1]), dot(tile([1, None], [1, None]), [-1, -1])
+        t = grid[:h, :w]
+        t = 6 * t ** 5 - 15 * t ** 4 + 10 * t ** 3
+        res = math.sqrt(2) * torch.lerp(torch.lerp(n00, n10, t[..., 0]), torch.lerp(n01, n11, t[..., 0]), t[..., 1])
+        _t(out, (1, h, w), torch.float32).copy_(res.view(1, h, w))
+
+    def e_cloudy_mix(self, x, seg, noise, mm_noise, out, n, h, w, c, hs, ws, sky_idx, weight, stream):
+        X = _t(x, (n, 3, h, w), torch.float32)
+        S = F.interpolate(_t(seg, (n, c, hs, ws), torch.float32), (h, w), mode="bilinear")                            # generator.py:318-323
+        mask = (torch.argmax(S, 1, keepdim=True) == sky_idx).float()
+        nz = _t(noise, (1, 1, h, w), torch.float32) - _t(mm_noise, (1, 2), torch.float32)[0, 0]                      # mix_noise, tutils :689-694
+        _t(out, (n, 3, h, w), torch.float32).copy_(mask * (weight * nz + (1 - weight) * X) + (1 - mask) * X)
+
+    def e_to_uint8_nhwc(self, x, mm, out, n, hw, stream):
+        t = self._norm(_t(x, (n, 3, hw), torch.float32), _t(mm, (n, 2), torch.float32))                                # trainer.py:312-327
+        buf = (C.c_uint8 * (n * hw * 3)).from_address(_addr(out))
+        torch.frombuffer(buf, dtype=torch.uint8).view(n, hw, 3).copy_((t.permute(0, 2, 1) * 255).to(torch.uint8))
+
+    def e_mask_to_uint8(self, m, out, bin_value, count, stream):
+        buf = (C.c_uint8 * count).from_address(_addr(out))
+        torch.frombuffer(buf, dtype=torch.uint8).copy_(((_t(m, (count,), torch.float32) > bin_value) * 255).to(torch.uint8))
+
+
 @contextlib.contextmanager
 def emulated_library():
     real = _lib.lib()
     fake = EmuLib(real)
-    saved = (_lib._lib, ops._on_device, torch.cuda.current_stream)
+    from climategan_b200.trainer import Trainer
+
+    saved = (_lib._lib, ops._on_device, torch.cuda.current_stream, Trainer._pinned)
     _lib._lib = fake
     ops._on_device = lambda x: True
-    torch.cuda.current_stream = lambda *a, **k: types.SimpleNamespace(cuda_stream=0)
+    torch.cuda.current_stream = lambda *a, **k: types.SimpleNamespace(cuda_stream=0, synchronize=lambda: None)
+    Trainer._pinned = lambda self, key, like: torch.empty(like.shape, dtype=like.dtype)   # (pinned host memory needs a CUDA driver)
     try:
         yield fake
     finally:
-        _lib._lib, ops._on_device, torch.cuda.current_stream = saved
+        _lib._lib, ops._on_device, torch.cuda.current_stream, Trainer._pinned = saved
         ops.invalidate_weight_cache()
