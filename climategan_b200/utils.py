@@ -207,8 +207,8 @@ def synth_batch(opts, batch, size, seed):
             data["d"] = torch.from_numpy(rs.random_sample((batch, 1, q, q)).astype(np.float32))
             if opts.gen.d.classify.enable and dom == "s":   # transforms.BucketizeDepth (:264-291): bucket indices on the sim domain
                 data["d"] = torch.from_numpy(rs.randint(0, opts.gen.d.classify.linspace.buckets, size=(batch, 1, q, q)).astype(np.int64))
-            for task in ("s", "d"):   # a loader only yields the tasks being trained (data.py:446-484); the draws above keep
-                if task not in opts.tasks:   # the random stream identical whatever the task list
+            for task in ("s", "d", "m"):   # a loader only yields the tasks being trained (data.py:446-484); the draws above
+                if task not in opts.tasks:      # keep the random stream identical whatever the task list
                     del data[task]
         out[dom] = {"data": data, "domain": [dom] * batch, "mode": ["train"] * batch, "paths": {}}
     return out

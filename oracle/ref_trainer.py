@@ -21,8 +21,13 @@ def build_reference_trainer(opts, size, vgg_seed=13, inference=False):
     import torchvision
 
     # ---- CPU / offline patches of hard-coded assumptions ----
-    _orig_vgg19 = torchvision.models.vgg19
-    losses_mod.models.vgg19 = lambda pretrained=True: _orig_vgg19(weights=None)
+    _orig_vgg19 = getattr(torchvision.models.vgg19, "_cgb_orig", torchvision.models.vgg19)   # (idempotent: this runs per trainer)
+
+    def _vgg19_no_download(pretrained=True):
+        return _orig_vgg19(weights=None)
+
+    _vgg19_no_download._cgb_orig = _orig_vgg19
+    losses_mod.models.vgg19 = _vgg19_no_download
 
     def vgg_preprocess_cpu(batch):
         (r, g, b) = torch.chunk(batch, 3, dim=1)

@@ -561,6 +561,63 @@ def run_masker_v3_case(name="masker_v3", nblocks=(2, 2, 3, 2), batch=2, size=128
           os.path.getsize(os.path.join(HERE, name + ".npz")))
 
 
+# Option combinations around the reference's scenario matrix (tests/test_trainer.py:205-308) that have no full fixture: only the
+# logged losses of two Trainer iterations and the first-iteration gradient norms are kept (a few KB each).
+SWEEP = {
+    "dada_ms": dict(tasks=("d", "s", "m"), overrides={"gen.m.use_dada": True}),
+    "base_depth_regression": dict(tasks=("d", "s", "m"), overrides={"gen.d.architecture": "base", "gen.m.use_dada": False,
+                                                                    "gen.s.use_dada": False}),
+    "v3_spade_msdp": dict(tasks=("d", "s", "m", "p"), use_spade=True, overrides=dict(V3_MASKER)),
+    "spade_detached_cond": dict(tasks=("d", "s", "m"), use_spade=True, overrides={"gen.m.spade.detach": True}),
+    "adam": dict(tasks=("d", "s", "m", "p"), overrides={"gen.opt.optimizer": "Adam", "dis.opt.optimizer": "Adam"}),
+    "pseudo_labels": dict(tasks=("d", "s", "m"), overrides={"train.pseudo.tasks": ["d", "s"]}),
+    "minent_v1_no_gi": dict(tasks=("d", "s", "m"), overrides={"gen.m.use_minent_var": False, "gen.m.use_ground_intersection": False}),
+    "depth_and_seg_only": dict(tasks=("d", "s")),
+}
+
+
+def run_config_sweep(name="config_sweep", batch=2, size=128):
+    from oracle import ref_trainer as rt
+
+    refshim.load("blocks").SPADEResnetBlock.cuda = lambda self, *a, **k: self   # masker.py:196 (SURVEY.md §8c patch 1)
+    meta, arrays = {"batch": batch, "size": size, "seeds": {"G": 21, "D": 22, "vgg": 23, "inputs": 7}, "cases": {}}, {}
+    for case, kw in SWEEP.items():
+        opts = rt.full_opts(size=size, **kw)
+        if opts.gen.encoder.architecture == "deeplabv3":
+            deeplab_mod, resnet_mod = refshim.load("deeplab", "deeplab.resnet101_v3")
+            nb = list(opts.gen.deeplabv3.nblocks)
+            deeplab_mod.ResNet101 = lambda output_stride=8, BatchNorm=None, verbose=0, no_init=False, nb=nb: resnet_mod.ResNet(
+                resnet_mod.Bottleneck, nb, output_stride, BatchNorm, verbose=verbose, no_init=no_init)
+        t = rt.build_reference_trainer(opts, size)
+        g_shapes, d_shapes, v_shapes = rt.load_weights(t)
+        mdb = rt.synth_batch(opts, batch, size, seed=7)
+        logs = []
+        for it in range(2):
+            for p_ in t.D.parameters():
+                p_.requires_grad = False
+            t.update_G(mdb)
+            if it == 0:
+                arrays[case + "::G.gradnorm"] = np.array([float(p_.grad.norm()) if p_.grad is not None else -1.0
+                                                          for p_ in t.G.parameters()])
+            for p_ in t.D.parameters():
+                p_.requires_grad = True
+            if t.d_opt is not None:
+                t.update_D(mdb)
+                if it == 0:
+                    arrays[case + "::D.gradnorm"] = np.array([float(p_.grad.norm()) if p_.grad is not None else -1.0
+                                                              for p_ in t.D.parameters()])
+            t.logger.global_step += 1
+            logs.append(_flatten_logs(t.logger.losses.to_dict()))
+        meta["cases"][case] = {"kw": {k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()}, "logs": logs,
+                               "g_shapes": [[k, list(s_)] for k, s_ in g_shapes], "d_shapes": [[k, list(s_)] for k, s_ in d_shapes],
+                               "v_shapes": [[k, list(s_)] for k, s_ in (v_shapes or [])]}
+        print(case, {k: round(v, 5) for k, v in list(logs[0].items())[:6]})
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **arrays)
+    with open(os.path.join(HERE, name + ".json"), "w") as f:
+        json.dump(meta, f)
+    print(name, "bytes", os.path.getsize(os.path.join(HERE, name + ".npz")), os.path.getsize(os.path.join(HERE, name + ".json")))
+
+
 if __name__ == "__main__":
     if not refshim.available():
         sys.exit("reference tree not available; goldens can only be regenerated in the build container")
@@ -581,3 +638,4 @@ if __name__ == "__main__":
     run_masker_spade_case(name="masker_spade12", cond_nc=12)
     run_masker_v3_case()
     run_masker_v3_case(name="masker_v3_spade", use_spade=True)
+    run_config_sweep()

@@ -111,3 +111,70 @@ def test_infer_all_on_the_emulated_abi_matches_the_reference():
         got = cl["flood"][:, :, ::4, ::4]
         assert rel_max(got, torch.from_numpy(g["raw_flood_cloudy"])) < 3e-3
         assert rel_max(got, torch.from_numpy(g["raw_flood"])) > 1e-2
+
+
+def _sweep():
+    import json
+    import os
+
+    from tests.helpers import GOLDEN
+
+    return json.load(open(os.path.join(GOLDEN, "config_sweep.json")))
+
+
+@pytest.mark.parametrize("case", ["dada_ms", "base_depth_regression", "v3_spade_msdp", "spade_detached_cond", "adam", "pseudo_labels",
+                                  "minent_v1_no_gi", "depth_and_seg_only"])
+def test_option_sweep_on_the_emulated_abi_matches_the_reference_trainer(case):
+    """Option combinations around the reference's scenario matrix that have no full fixture (DADA on the mask decoder, base depth
+    regression, v3 encoder + SPADE mask decoder + painter, detached SPADE conditioning, plain Adam, pseudo labels on the real
+    domain, MinEnt v1 without the ground-intersection loss, tasks d + s alone): two iterations of update_G / update_D against the
+    reference's own Trainer (tests/golden/config_sweep.*, from make_golden.py::run_config_sweep) — every logged loss of the first
+    iteration within 1e-4, of the second within 3e-3, every gradient norm of the first backward within 1e-2 (G) / 1.5e-1 (D)."""
+    import os
+
+    import numpy as np
+
+    from climategan_b200.trainer import Trainer
+    from climategan_b200.utils import full_opts, synth_batch
+    from tests.golden.weights import fill_state_dict
+    from tests.helpers import GOLDEN
+
+    sweep = _sweep()
+    meta = sweep["cases"][case]
+    arrays = np.load(os.path.join(GOLDEN, "config_sweep.npz"))
+    size, batch = sweep["size"], sweep["batch"]
+    kw = dict(meta["kw"])
+    kw["tasks"] = tuple(kw["tasks"])
+    opts = full_opts(size=size, **kw)
+    with emulated_library():
+        t = Trainer(opts, device=torch.device("cpu"), storage_dtype=torch.float32).setup(input_shape=(size, size))
+        mk = lambda shapes, seed: fill_state_dict([(k, tuple(s)) for k, s in shapes], seed)  # noqa: E731
+        t.G.load_state_dict(mk(meta["g_shapes"], sweep["seeds"]["G"]), strict=True)
+        t.D.load_state_dict(mk(meta["d_shapes"], sweep["seeds"]["D"]), strict=True)
+        if meta["v_shapes"]:
+            t.losses["G"]["p"]["vgg"].vgg.load_state_dict(mk(meta["v_shapes"], sweep["seeds"]["vgg"]), strict=True)
+        for mod in t.G.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = 0.0
+        mdb = {dom: t.batch_to_device(b) for dom, b in synth_batch(opts, batch, size, sweep["seeds"]["inputs"]).items()}
+        for it in range(2):
+            t.update_G(mdb)
+            if it == 0:
+                gn = np.array([float(p.grad.norm()) if p.grad is not None and p.requires_grad else -1.0 for p in t.G.parameters()])
+            t.update_D(mdb)
+            if it == 0 and t.d_opt is not None:
+                dn = np.array([float(p.grad.norm()) if p.grad is not None and p.requires_grad else -1.0 for p in t.D.parameters()])
+            t.logger.global_step += 1
+            logs = t_step._flatten(t.losses_to_host())
+            tol, atol = (1e-4, 2e-6) if it == 0 else (3e-3, 2e-4)
+            bad = [(k, logs.get(k), r) for k, r in meta["logs"][it].items() if k not in logs or abs(logs[k] - r) > tol * abs(r) + atol]
+            assert not bad, (it, bad[:6])
+        for got, key, rtol in ((gn, case + "::G.gradnorm", 1e-2), (dn if t.d_opt is not None else None, case + "::D.gradnorm", 1.5e-1)):
+            if got is None:
+                continue
+            ref = arrays[key]
+            scale = ref[ref >= 0].max()
+            names = [n for n, _ in (t.G if key.endswith("G.gradnorm") else t.D).named_parameters()]
+            bad = [(n, a, b) for n, a, b in zip(names, got, ref)
+                   if b >= 0 and not n.endswith(("weight_u", "weight_v")) and (a < 0 or abs(a - b) > rtol * b + 1e-6 * scale)]
+            assert not bad, bad[:6]
