@@ -216,12 +216,16 @@ class OmniDiscriminator(nn.ModuleDict):
     def __init__(self, opts, storage_dtype=torch.bfloat16):
         super().__init__()
         if "p" in opts.tasks:
-            if opts.dis.p.use_local_discriminator:
-                raise NotImplementedError("dis.p.use_local_discriminator (off in defaults.yaml) is not built")
-            self["p"] = define_D(input_nc=4, ndf=opts.dis.p.ndf, n_layers=opts.dis.p.n_layers, norm=opts.dis.p.norm,
-                                 use_sigmoid=opts.dis.p.use_sigmoid,
-                                 get_intermediate_features=opts.dis.p.get_intermediate_features, num_D=opts.dis.p.num_D,
-                                 storage_dtype=storage_dtype)
+            if opts.dis.p.use_local_discriminator:   # discriminator.py:246-270: a global D on the image, a local one on image*mask
+                kw = dict(input_nc=3, ndf=opts.dis.p.ndf, n_layers=opts.dis.p.n_layers, norm=opts.dis.p.norm,
+                          use_sigmoid=opts.dis.p.use_sigmoid, get_intermediate_features=opts.dis.p.get_intermediate_features,
+                          num_D=opts.dis.p.num_D, storage_dtype=storage_dtype)
+                self["p"] = nn.ModuleDict({"global": define_D(**kw), "local": define_D(**kw)})
+            else:
+                self["p"] = define_D(input_nc=4, ndf=opts.dis.p.ndf, n_layers=opts.dis.p.n_layers, norm=opts.dis.p.norm,
+                                     use_sigmoid=opts.dis.p.use_sigmoid,
+                                     get_intermediate_features=opts.dis.p.get_intermediate_features, num_D=opts.dis.p.num_D,
+                                     storage_dtype=storage_dtype)
         if "m" in opts.tasks and opts.gen.m.use_advent:
             if opts.dis.m.architecture != "base":
                 raise NotImplementedError("dis.m.architecture=OmniDiscriminator is not built")

@@ -42,6 +42,7 @@ def get_losses(opts, verbose=0, device=None, storage_dtype=torch.bfloat16):
         if opts.train.lambdas.G.p.vgg != 0:
             losses["G"]["p"]["vgg"] = VGGLoss(device, storage_dtype=storage_dtype)
         losses["G"]["p"]["featmatch"] = FeatMatchLoss()
+        losses["G"]["p"]["tv"] = TVLoss()
         losses["D"]["p"] = losses["G"]["p"]["gan"]
     if "d" in opts.tasks:
         if opts.gen.d.classify.enable:
@@ -415,13 +416,16 @@ class Trainer:
         """trainer.py:1618-1651 (pl4m; switched on at epoch gen.p.pl4m_epoch when gen.m.use_pl4m, trainer.py:899-909): the frozen
         painter paints with the masker's PREDICTED mask and the painter discriminator scores the result; the gradient reaches
         the masker through x (1 - m), the SPADE conditioning, the paste and the mask channel of D's input."""
-        if self.opts.dis.p.use_local_discriminator:
-            raise NotImplementedError("dis.p.use_local_discriminator (off in defaults.yaml) is not built")
         frozen = [p for p in self.G.painter.parameters() if p.requires_grad]
         for p in frozen:
             p.requires_grad = False
         try:
             fake_flooded = self.G.paint(m, x)
+            if self.opts.dis.p.use_local_discriminator:                                # trainer.py:1628-1636
+                fake_d_global = self.D["p"]["global"](fake_flooded)
+                fake_d_local = self.D["p"]["local"](ops.paste(torch.zeros_like(x), m, fake_flooded))
+                return (self.losses["G"]["p"]["gan"](fake_d_global, True, False)
+                        + self.losses["G"]["p"]["gan"](fake_d_local, True, False))
             real_cat = torch.cat([m, x], axis=1)
             fake_cat = torch.cat([m, fake_flooded], axis=1)
             real_fake_d = self.D["p"](torch.cat([real_cat, fake_cat], dim=0))
@@ -445,11 +449,37 @@ class Trainer:
             loss = self.losses["G"]["p"]["vgg"](fake_flooded, x, m) * lambdas.G.p.vgg
             self.logger.losses.gen.p.vgg = loss.detach()
             step_loss = step_loss + loss
-        for name in ("tv", "context", "reconstruction"):
-            if lambdas.G.p[name] != 0:
-                raise NotImplementedError(f"painter loss '{name}' (lambda 0 in defaults.yaml) is not built")
+        # tv / context / reconstruction have lambda 0 in defaults.yaml:294-299.  `t * mask` is the paste kernel on a zero
+        # background (x (1 - m) + t m with x = 0): gradient to t, none to the mask, as in the reference where m is data.
+        zeros = torch.zeros_like(x)
+        mf = m.to(x.dtype)
+        if lambdas.G.p.tv != 0:                                                       # trainer.py:1292-1296, losses.py:140-171
+            loss = self.losses["G"]["p"]["tv"](ops.paste(zeros, mf, fake_flooded)) * lambdas.G.p.tv
+            self.logger.losses.gen.p.tv = loss.detach()
+            step_loss = step_loss + loss
+        if lambdas.G.p.context != 0:                                                  # masked L1 off the water, losses.py:281-287
+            loss = ops.l1_loss(ops.paste(zeros, 1.0 - mf, fake_flooded), ops.paste(zeros, 1.0 - mf, x).detach()) * lambdas.G.p.context
+            self.logger.losses.gen.p.context = loss.detach()
+            step_loss = step_loss + loss
+        if lambdas.G.p.reconstruction != 0:                                           # masked L1 on the water, losses.py:290-296
+            loss = ops.l1_loss(ops.paste(zeros, mf, fake_flooded), ops.paste(zeros, mf, x).detach()) * lambdas.G.p.reconstruction
+            self.logger.losses.gen.p.reconstruction = loss.detach()
+            step_loss = step_loss + loss
         if self.opts.gen.p.diff_aug.use:
             raise NotImplementedError("gen.p.diff_aug (off in defaults.yaml:158) is not built")
+        if self.opts.dis.p.use_local_discriminator:                                   # trainer.py:1322-1356
+            fake_d_global = self.D["p"]["global"](fake_flooded)
+            fake_d_local = self.D["p"]["local"](ops.paste(zeros, mf, fake_flooded))
+            real_d_global = self.D["p"]["global"](x)
+            loss = (self.losses["G"]["p"]["gan"](fake_d_global, True, False)
+                    + self.losses["G"]["p"]["gan"](fake_d_local, True, False)) * lambdas.G["p"]["gan"]
+            self.logger.losses.gen.p.gan = loss.detach()
+            step_loss = step_loss + loss
+            if self.opts.dis.p.get_intermediate_features:                             # (on the global discriminator only)
+                loss = self.losses["G"]["p"]["featmatch"](real_d_global, fake_d_global) * lambdas.G["p"]["featmatch"]
+                self.logger.losses.gen.p.featmatch = loss.detach() if isinstance(loss, torch.Tensor) else loss
+                step_loss = step_loss + loss
+            return step_loss
         real_cat = torch.cat([m, x], axis=1)
         fake_cat = ops.cat_mask_image(m, fake_flooded)
         real_fake_d = self.D["p"](torch.cat([real_cat, fake_cat], dim=0))
@@ -465,7 +495,8 @@ class Trainer:
 
     def get_D_loss(self, multi_domain_batch, verbose=0):
         """trainer.py:1034-1160."""
-        disc_loss = {"m": {"Advent": 0}, "s": {"Advent": 0}, "p": {"gan": 0}}
+        disc_loss = {"m": {"Advent": 0}, "s": {"Advent": 0},
+                     "p": {"global": 0, "local": 0} if self.opts.dis.p.use_local_discriminator else {"gan": 0}}   # trainer.py:1058-1066
         lam = self.opts.train.lambdas
         for domain, batch in multi_domain_batch.items():
             x = batch["data"]["x"]
@@ -474,6 +505,13 @@ class Trainer:
                 with torch.no_grad():
                     fake = self.G.paint(m, x)
                 fake = fake.detach()
+                if self.opts.dis.p.use_local_discriminator:                            # trainer.py:1084-1098
+                    zeros, mf = torch.zeros_like(x), m.to(x.dtype)
+                    Dp, Lp = self.D["p"], self.losses["D"]["p"]
+                    disc_loss["p"]["global"] = (Lp(Dp["global"](fake), False, True) + Lp(Dp["global"](x), True, True))
+                    disc_loss["p"]["local"] = (Lp(Dp["local"](ops.paste(zeros, mf, fake)), False, True)
+                                               + Lp(Dp["local"](ops.paste(zeros, mf, x)), True, True))
+                    continue
                 real_cat = torch.cat([m, x], axis=1)
                 fake_cat = torch.cat([m, fake], axis=1)
                 real_fake_d = self.D["p"](torch.cat([real_cat, fake_cat], dim=0))

@@ -147,7 +147,7 @@ def full_opts(nblocks=(2, 2, 3, 2), size=128, latent=16, n_up=4, ndf=8, n_layers
     o = default_masker_opts(tasks=tuple(t for t in tasks if t != "p"), nblocks=nblocks, size=size, with_painter=with_p,
                             latent_dim=latent, spade_n_up=n_up, ndf=ndf, n_layers=n_layers, num_D=num_d)
     o.tasks = list(tasks)
-    o.domains = ["r", "s"] + (["rf"] if with_p else [])
+    o.domains = (["r", "s"] if any(t in tasks for t in "msd") else []) + (["rf"] if with_p else [])   # painter alone: rf only
     o.gen.default = Dict(init_type="xavier", init_gain=0.02)
     for k in ("encoder", "d", "s", "m", "p"):
         o.gen[k].init_type = "xavier"

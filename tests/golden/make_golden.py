@@ -573,6 +573,12 @@ SWEEP = {
     "pseudo_labels": dict(tasks=("d", "s", "m"), overrides={"train.pseudo.tasks": ["d", "s"]}),
     "minent_v1_no_gi": dict(tasks=("d", "s", "m"), overrides={"gen.m.use_minent_var": False, "gen.m.use_ground_intersection": False}),
     "depth_and_seg_only": dict(tasks=("d", "s")),
+    # painter options off in defaults.yaml: the global + local discriminator pair (dis.p.use_local_discriminator), the same with
+    # the painter loss for the masker on, and the tv / context / reconstruction losses with non-zero weights
+    "painter_local_d": dict(tasks=("d", "s", "m", "p"), overrides={"dis.p.use_local_discriminator": True}),
+    "painter_local_d_pl4m": dict(tasks=("d", "s", "m", "p"), overrides={"dis.p.use_local_discriminator": True}, pl4m=True),
+    "painter_aux_losses": dict(tasks=("p",), overrides={"train.lambdas.G.p.tv": 1.0, "train.lambdas.G.p.context": 5.0,
+                                                        "train.lambdas.G.p.reconstruction": 2.0}),
 }
 
 
@@ -582,6 +588,8 @@ def run_config_sweep(name="config_sweep", batch=2, size=128):
     refshim.load("blocks").SPADEResnetBlock.cuda = lambda self, *a, **k: self   # masker.py:196 (SURVEY.md §8c patch 1)
     meta, arrays = {"batch": batch, "size": size, "seeds": {"G": 21, "D": 22, "vgg": 23, "inputs": 7}, "cases": {}}, {}
     for case, kw in SWEEP.items():
+        kw = dict(kw)
+        pl4m = kw.pop("pl4m", False)
         opts = rt.full_opts(size=size, **kw)
         if opts.gen.encoder.architecture == "deeplabv3":
             deeplab_mod, resnet_mod = refshim.load("deeplab", "deeplab.resnet101_v3")
@@ -590,6 +598,7 @@ def run_config_sweep(name="config_sweep", batch=2, size=128):
                 resnet_mod.Bottleneck, nb, output_stride, BatchNorm, verbose=verbose, no_init=no_init)
         t = rt.build_reference_trainer(opts, size)
         g_shapes, d_shapes, v_shapes = rt.load_weights(t)
+        t.use_pl4m = bool(pl4m)
         mdb = rt.synth_batch(opts, batch, size, seed=7)
         logs = []
         for it in range(2):
@@ -608,7 +617,7 @@ def run_config_sweep(name="config_sweep", batch=2, size=128):
                                                               for p_ in t.D.parameters()])
             t.logger.global_step += 1
             logs.append(_flatten_logs(t.logger.losses.to_dict()))
-        meta["cases"][case] = {"kw": {k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()}, "logs": logs,
+        meta["cases"][case] = {"kw": {k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()}, "logs": logs, "pl4m": bool(pl4m),
                                "g_shapes": [[k, list(s_)] for k, s_ in g_shapes], "d_shapes": [[k, list(s_)] for k, s_ in d_shapes],
                                "v_shapes": [[k, list(s_)] for k, s_ in (v_shapes or [])]}
         print(case, {k: round(v, 5) for k, v in list(logs[0].items())[:6]})
