@@ -1026,6 +1026,66 @@ extern "C" int cgb_cross_entropy_nchw(const float* logits, const int64_t* target
   return after_launch("cross_entropy_nchw");
 }
 
+// ---------------------------------------------------------------------------------------------------
+// DADADepthLoss (losses.py:596-620): reverse Huber (berHu) on |pred - label| with the threshold c = 0.2 * max over the WHOLE
+// batch — taken with .item() in the reference, so c is a constant of the graph:
+//   loss = ( sum_{a<=c} a + sum_{a>c} (a^2 + c^2) / (2c) ) / count ;  dl/dpred = sign(d)/count (a <= c) | d/(c*count) (a > c)
+// Depth maps are small (n x 160 x 160 at 640^2): one CTA, two passes over the data.
+__global__ void __launch_bounds__(1024)
+dada_depth_loss_kernel(const float* __restrict__ pred, const float* __restrict__ label, float* __restrict__ loss,
+                       float* __restrict__ gpred, long long count) {
+  __shared__ float sh[32];
+  __shared__ float s_c;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float mx = 0.f;
+  for (long long i = threadIdx.x; i < count; i += blockDim.x) mx = fmaxf(mx, fabsf(pred[i] - label[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) sh[warp] = mx;
+  __syncthreads();
+  if (warp == 0) {
+    mx = lane < nw ? sh[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) s_c = 0.2f * mx;
+  }
+  __syncthreads();
+  const float c = s_c;
+  const float inv_n = 1.f / (float)count;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < count; i += blockDim.x) {
+    const float d = pred[i] - label[i];
+    const float a = fabsf(d);
+    float g;
+    if (a <= c) {
+      s += a;
+      g = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+    } else {
+      s += (a * a + c * c) / (2.f * c);
+      g = d / c;
+    }
+    if (gpred) gpred[i] = g * inv_n;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __syncthreads();
+  if (lane == 0) sh[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    s = lane < nw ? sh[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) atomicAdd(loss, s * inv_n);
+  }
+}
+
+extern "C" int cgb_dada_depth_loss(const float* pred, const float* label, float* loss, float* gpred, int64_t count, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(pred && label && loss && count > 0, "dada_depth_loss: bad arguments");
+  dada_depth_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pred, label, loss, gpred, (long long)count);
+  return after_launch("dada_depth_loss");
+}
+
 extern "C" int cgb_entropy_nchw(const float* p, const float* depth, const float* ge, float* out, int32_t n, int32_t c, int32_t hw,
                                 int32_t backward, void* stream) {
   CGB_CHECK_DEVICE();

@@ -159,6 +159,13 @@ class CrossEntropy(nn.Module):
         return ops.cross_entropy_nchw(logits, target.to(logits.device).long())
 
 
+class DADADepthLoss:
+    """``climategan.losses.DADADepthLoss`` (:596-620)."""
+
+    def __call__(self, pred, label):
+        return ops.dada_depth_loss(pred, label)
+
+
 class TVLoss(nn.Module):
     def __init__(self, tvloss_weight=1):
         super().__init__()

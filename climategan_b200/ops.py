@@ -1356,6 +1356,17 @@ def sigm_loss(pred, target, gmweight=0.5, scales=4):
     return _FusedLoss.apply(pred, run)
 
 
+def dada_depth_loss(pred, target):
+    """DADADepthLoss (losses.py:596-620): reverse Huber with the batch-wide threshold 0.2 * max|pred - target|."""
+    assert tuple(pred.shape) == tuple(target.shape) and pred.shape[1] == 1, (pred.shape, target.shape)
+    tgt = _f32c(target.detach())
+
+    def run(x, loss, gx):
+        check(_L().cgb_dada_depth_loss(_p(x), _p(tgt), _p(loss), _p(gx), x.numel(), _st()), "dada_depth_loss")
+
+    return _FusedLoss.apply(pred, run)
+
+
 class _EntropyNCHW(Function):
     @staticmethod
     def forward(ctx, prob, depth):

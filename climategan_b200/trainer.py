@@ -15,7 +15,7 @@ import torch
 from . import events, ops
 from .discriminator import create_discriminator
 from .generator import create_generator
-from .losses import (ADVENTAdversarialLoss, BCEWithLogits, CrossEntropy, FeatMatchLoss, GANLoss, GroundIntersectionLoss,
+from .losses import (ADVENTAdversarialLoss, BCEWithLogits, CrossEntropy, DADADepthLoss, FeatMatchLoss, GANLoss, GroundIntersectionLoss,
                      HingeLoss, MinentLoss, SIGMLoss, TVLoss, VGGLoss)
 from .discriminator import fc_discriminator_forward
 from .optim import get_optimizer
@@ -48,8 +48,7 @@ def get_losses(opts, verbose=0, device=None, storage_dtype=torch.bfloat16):
         if opts.gen.d.classify.enable:
             losses["G"]["tasks"]["d"] = CrossEntropy()   # losses.py:399-405: bucketised log-depth, loss name ignored
         elif opts.gen.d.loss == "dada":
-            raise NotImplementedError("depth loss 'dada' (reverse Huber) is not built: gen.d.loss='sigm' (defaults.yaml:127) or "
-                                      "gen.d.classify.enable")
+            losses["G"]["tasks"]["d"] = DADADepthLoss()
         else:
             losses["G"]["tasks"]["d"] = SIGMLoss(opts.train.lambdas.G.d.gml)
     if "s" in opts.tasks:

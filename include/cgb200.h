@@ -288,6 +288,9 @@ int cgb_sigmoid_pair(const float* logits, const float* gprob, float* out, int32_
 int cgb_tv_loss(const float* x, float* loss, float* gx, int32_t n, int32_t c, int32_t h, int32_t w, void* stream);
 int cgb_bce_logits_loss(const float* x, const float* target, float* loss, float* gx, int64_t count, void* stream);
 int cgb_ground_intersection_loss(const float* pred, const float* ground, float* loss, int64_t count, void* stream);
+/* DADADepthLoss (losses.py:596-620; gen.d.loss = "dada"): reverse Huber on |pred - label| with threshold c = 0.2 * max over the
+ * whole batch (a constant of the graph: the reference takes it with .item()); adds the mean to `loss`, writes dloss/dpred. */
+int cgb_dada_depth_loss(const float* pred, const float* label, float* loss, float* gpred, int64_t count, void* stream);
 int cgb_sigm_loss(const float* pred, const float* target, float* loss, float* gpred, float* ws, int32_t n, int32_t h, int32_t w,
                   float gmweight, int32_t scales, void* stream);
 

@@ -641,6 +641,18 @@ class EmuLib(NoopLib):
         v = (1.0 * ((_t(ground, (count,), torch.float32) - _t(pred, (count,), torch.float32)) > 0.5)).mean()
         _t(loss, (1,), torch.float32).add_(v)
 
+    def e_dada_depth_loss(self, pred, label, loss, gpred, count, stream):
+        L = _t(label, (count,), torch.float32)
+
+        def f(P):   # DADADepthLoss.loss_calc_depth, losses.py:603-617 (the threshold is taken with .item(): a constant)
+            adiff = torch.abs(P - L)
+            c = 0.2 * float(adiff.max())
+            t1 = adiff * (adiff <= c).float()
+            t2 = (adiff * adiff + c * c) / (2 * c) * (adiff > c).float()
+            return (t1.sum() + t2.sum()) / count
+
+        self._loss(f, _t(pred, (count,), torch.float32), loss, _t(gpred, (count,), torch.float32))
+
     def e_sigm_loss(self, pred, target, loss, gpred, ws, n, h, w, gmweight, scales, stream):
         T = _t(target, (n, 1, h, w), torch.float32)
 

@@ -573,6 +573,7 @@ SWEEP = {
     "pseudo_labels": dict(tasks=("d", "s", "m"), overrides={"train.pseudo.tasks": ["d", "s"]}),
     "minent_v1_no_gi": dict(tasks=("d", "s", "m"), overrides={"gen.m.use_minent_var": False, "gen.m.use_ground_intersection": False}),
     "depth_and_seg_only": dict(tasks=("d", "s")),
+    "dada_depth_loss": dict(tasks=("d", "s", "m"), overrides={"gen.d.loss": "dada"}),
     # painter options off in defaults.yaml: the global + local discriminator pair (dis.p.use_local_discriminator), the same with
     # the painter loss for the masker on, and the tv / context / reconstruction losses with non-zero weights
     "painter_local_d": dict(tasks=("d", "s", "m", "p"), overrides={"dis.p.use_local_discriminator": True}),

@@ -123,11 +123,11 @@ def _sweep():
 
 
 @pytest.mark.parametrize("case", ["dada_ms", "base_depth_regression", "v3_spade_msdp", "spade_detached_cond", "adam", "pseudo_labels",
-                                  "minent_v1_no_gi", "depth_and_seg_only", "painter_local_d", "painter_local_d_pl4m",
+                                  "minent_v1_no_gi", "depth_and_seg_only", "dada_depth_loss", "painter_local_d", "painter_local_d_pl4m",
                                   "painter_aux_losses"])
 def test_option_sweep_on_the_emulated_abi_matches_the_reference_trainer(case):
     """Option combinations around the reference's scenario matrix that have no full fixture (DADA on the mask decoder, base depth
-    regression, v3 encoder + SPADE mask decoder + painter, detached SPADE conditioning, plain Adam, pseudo labels on the real
+    regression, the reverse-Huber depth loss, v3 encoder + SPADE mask decoder + painter, detached SPADE conditioning, plain Adam, pseudo labels on the real
     domain, MinEnt v1 without the ground-intersection loss, tasks d + s alone, the global + local painter discriminators with
     and without the painter loss for the masker, the painter's tv / context / reconstruction losses): two iterations of update_G / update_D against the
     reference's own Trainer (tests/golden/config_sweep.*, from make_golden.py::run_config_sweep) — every logged loss of the first
