@@ -74,9 +74,13 @@ def _id(run):
 @pytest.mark.parametrize("run", RUNS, ids=_id)
 def test_gpu_parity_test_on_the_emulated_abi(run):
     fn, kw = run
-    with emulated_library() as lib:
-        fn(torch.device("cpu"), **kw)
-        assert sum(lib.calls.values()) > 0
+    t_step.NORM_TOL_SCALE = 2.0   # (see tests/test_gpu_full_step.py)
+    try:
+        with emulated_library() as lib:
+            fn(torch.device("cpu"), **kw)
+            assert sum(lib.calls.values()) > 0
+    finally:
+        t_step.NORM_TOL_SCALE = 1.0
 
 
 def test_infer_all_on_the_emulated_abi_matches_the_reference():

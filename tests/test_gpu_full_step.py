@@ -16,6 +16,11 @@ from tests.helpers import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
+# 1 on the GPU.  tests/test_emulated.py re-runs the fp32 tests of this module on CPU against a plain-PyTorch emulation of the
+# C ABI and widens the generator gradient-NORM tolerances by 2 there: the emulation sums in ATen's order on whatever ISA the host
+# CPU has, and on these chaotic fixtures (see the docstrings) the realised error sits within a factor 1.3 of the GPU tolerance.
+NORM_TOL_SCALE = 1.0
+
 
 def _sample(a, cap=8192):
     a = a.detach().float().cpu().numpy().reshape(-1)
@@ -111,7 +116,7 @@ def test_full_step_fp32_matches_reference_trainer(cuda):
         # G: first backward of the run, 2e-3.  D: its backward runs AFTER the generator's first ExtraAdam update, which moves
         # every weight by +-lr whatever the size of its gradient (Adam's first step is sign-like), so last-bit differences in
         # near-zero generator gradients perturb the masker outputs the AdvEnt discriminators see: 5e-2 there.
-        rtol = 2e-3 if side == "G" else 5e-2
+        rtol = 2e-3 * NORM_TOL_SCALE if side == "G" else 5e-2
         # the spectral-norm u / v "gradients" of D (trained by the reference, see ops._SpectralWeight) are second-order small
         # and sit behind the same amplification: checked for presence and order of magnitude only (factor 10 + abs 1e-4)
         uv = lambda n: n.endswith(("weight_u", "weight_v"))  # noqa: E731
@@ -198,7 +203,7 @@ def test_spade_masker_step_fp32_matches_reference_trainer(cuda):
         mask = ref >= 0
         assert ((got >= 0) == mask).all(), [n for n, a, b in zip(names, got, ref) if (a >= 0) != (b >= 0)]
         scale = ref[mask].max()
-        rtol = 4e-3 if side == "G" else 5e-2
+        rtol = 4e-3 * NORM_TOL_SCALE if side == "G" else 5e-2
         uv = lambda n: n.endswith(("weight_u", "weight_v"))  # noqa: E731
         bad = [(n, a, b) for n, a, b in zip(names, got, ref) if b >= 0 and not uv(n) and abs(a - b) > rtol * b + 1e-6 * scale]
         bad += [(n, a, b) for n, a, b in zip(names, got, ref) if b >= 0 and uv(n) and not (b / 10 - 1e-4 <= a <= b * 10 + 1e-4)]
@@ -290,7 +295,7 @@ def test_full_step_with_pl4m_fp32_matches_reference_trainer(cuda):
         miss = [n for n, a, b, k_ in zip(names, got, ref, keep) if k_ and (a >= 0) != (b >= 0)]
         assert not miss, miss[:10]
         scale = ref[ref >= 0].max()
-        rtol = 2e-3 if side == "G" else 5e-2
+        rtol = 2e-3 * NORM_TOL_SCALE if side == "G" else 5e-2
         bad = [(n, a, b) for n, a, b, k_ in zip(names, got, ref, keep)
                if k_ and b >= 0 and not uv(n) and abs(a - b) > rtol * b + 1e-6 * scale]
         bad += [(n, a, b) for n, a, b, k_ in zip(names, got, ref, keep)
@@ -332,7 +337,7 @@ def _check_fp32_step(meta, g, out, g_norm_rtol, d_grad_tol, well, d_norm_rtol=5e
         mask = ref >= 0
         assert ((got >= 0) == mask).all(), [n for n, a, b in zip(names, got, ref) if (a >= 0) != (b >= 0)]
         scale = ref[mask].max()
-        rtol = g_norm_rtol if side == "G" else d_norm_rtol
+        rtol = g_norm_rtol * NORM_TOL_SCALE if side == "G" else d_norm_rtol
         uv = lambda n: n.endswith(("weight_u", "weight_v"))  # noqa: E731
         bad = [(n, a, b) for n, a, b in zip(names, got, ref) if b >= 0 and not uv(n) and abs(a - b) > rtol * b + 1e-6 * scale]
         bad += [(n, a, b) for n, a, b in zip(names, got, ref) if b >= 0 and uv(n) and not (b / 10 - 1e-4 <= a <= b * 10 + 1e-4)]
