@@ -3,6 +3,7 @@
 // scalar losses (cross-entropy, entropy maps, MinEnt, TV, BCE, ground intersection, MiDaS scale-invariant gradient
 // matching loss).  All HBM-bound: NHWC kernels are 16-byte vectorised over channels; NCHW fp32 loss kernels are
 // coalesced over pixels.  Reductions: registers -> shared atomics -> one fp64 atomic per channel per CTA.
+#include <climits>
 #include "common.cuh"
 
 namespace cgb {
@@ -1084,6 +1085,73 @@ extern "C" int cgb_dada_depth_loss(const float* pred, const float* label, float*
   CGB_REQUIRE(pred && label && loss && count > 0, "dada_depth_loss: bad arguments");
   dada_depth_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(pred, label, loss, gpred, (long long)count);
   return after_launch("dada_depth_loss");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Validation metrics (Trainer.eval_images trainer.py:1706-1799; accuracy / mIOU eval_metrics.py:68-130): both are functions of
+// the confusion matrix of argmax(pred, dim=1) against the integer label, so one pass over the logits replaces the reference's
+// .cpu() round trip and its Python loop over classes (two masked reductions + .item() per class).
+//   conf[p][l] += 1 per pixel, p = argmax_c logits[n][c][pix] (first maximum; a NaN counts as the maximum: torch.argmax),
+//   l = label if 0 <= label < c, else the extra column c (ignore index: counted in the prediction totals, never a match).
+// HBM-bound: c floats + one int64 per pixel, class-major reads coalesced across the pixels of a warp.  Counts go to a
+// shared-memory histogram (c (c+1) 32-bit cells, warp-aggregated with match.any) and are flushed once per CTA with 64-bit
+// atomics.
+__global__ void __launch_bounds__(256)
+argmax_confusion_kernel(const float* __restrict__ logits, const int64_t* __restrict__ label, unsigned long long* __restrict__ conf,
+                        long long* __restrict__ label_max, int c, long long hw, long long total) {
+  extern __shared__ unsigned int sh_conf[];
+  const int cells = c * (c + 1);
+  for (int i = threadIdx.x; i < cells; i += blockDim.x) sh_conf[i] = 0u;
+  __syncthreads();
+  long long lmax = LLONG_MIN;
+  const int lane = threadIdx.x & 31;
+  // block-uniform trip count, so the warp-level match below always runs with the full mask
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += (long long)gridDim.x * blockDim.x) {
+    const long long idx = base + threadIdx.x;
+    int cell = -1;
+    if (idx < total) {
+      const long long n = idx / hw;
+      const float* p = logits + n * c * hw + (idx - n * hw);
+      float best = p[0];
+      int bi = 0;
+      for (int k = 1; k < c; ++k) {
+        const float v = p[(long long)k * hw];
+        if (best == best && (v > best || v != v)) {
+          best = v;
+          bi = k;
+        }
+      }
+      const long long l = label[idx];
+      lmax = l > lmax ? l : lmax;
+      cell = bi * (c + 1) + ((l >= 0 && l < c) ? (int)l : c);
+    }
+    // neighbouring pixels mostly share (prediction, label): one shared-memory atomic per distinct cell of the warp
+    const unsigned peers = __match_any_sync(0xffffffffu, cell);
+    if (cell >= 0 && lane == __ffs(peers) - 1) atomicAdd(&sh_conf[cell], (unsigned)__popc(peers));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const long long other = __shfl_xor_sync(0xffffffffu, lmax, o);
+    lmax = other > lmax ? other : lmax;
+  }
+  if (lane == 0 && lmax != LLONG_MIN) atomicMax(label_max, lmax);
+  __syncthreads();
+  for (int i = threadIdx.x; i < cells; i += blockDim.x)
+    if (sh_conf[i]) atomicAdd(&conf[i], (unsigned long long)sh_conf[i]);
+}
+
+extern "C" int cgb_argmax_confusion(const float* logits, const int64_t* label, int64_t* conf, int64_t* label_max, int32_t n, int32_t c,
+                                    int64_t hw, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(logits && label && conf && label_max && n > 0 && hw > 0, "argmax_confusion: bad arguments");
+  CGB_REQUIRE(c >= 1 && c <= 64, "argmax_confusion: 1 <= classes <= 64, got %d", c);
+  const long long total = (long long)n * hw;
+  // (a CTA counts at most total / gridDim.x + 256 pixels: 32-bit cells cannot wrap below 2^32 pixels per CTA)
+  long long g = (total + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  argmax_confusion_kernel<<<(int)g, 256, (size_t)c * (c + 1) * sizeof(unsigned int), (cudaStream_t)stream>>>(
+      logits, label, (unsigned long long*)conf, (long long*)label_max, c, (long long)hw, total);
+  return after_launch("argmax_confusion");
 }
 
 extern "C" int cgb_entropy_nchw(const float* p, const float* depth, const float* ge, float* out, int32_t n, int32_t c, int32_t hw,

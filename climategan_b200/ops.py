@@ -55,7 +55,7 @@ def _chk_storage(x: torch.Tensor, name: str = "x") -> None:
 # weight packing:  OIHW fp32  <->  [Os][kh*kw][Is] storage dtype
 # ------------------------------------------------------------------------------------------------
 # CGB_PACK_KERNEL=1: pack in one launch of cgb_pack_weight instead of three torch launches (written when the GPU budget of
-# round 1 was spent: bit-exactness against the torch path is tests/test_gpu_ops.py::test_pack_weight_kernel; off until run)
+# round 1 was spent: bit-exactness against the torch path is tests/test_gpu_zz_new_kernels.py::test_pack_weight_kernel; off until run)
 _PACK_KERNEL = os.environ.get("CGB_PACK_KERNEL", "0") == "1"
 
 
@@ -1365,6 +1365,26 @@ def dada_depth_loss(pred, target):
         check(_L().cgb_dada_depth_loss(_p(x), _p(tgt), _p(loss), _p(gx), x.numel(), _st()), "dada_depth_loss")
 
     return _FusedLoss.apply(pred, run)
+
+
+def argmax_confusion(pred, label):
+    """Confusion matrix of argmax(pred, dim=1) against an integer label, on the device, in one launch — what accuracy and mIOU
+    (eval_metrics.py:68-130) are functions of.  pred [N,C,H,W] float, label [N,H,W] / [N,1,H,W] integer-valued.
+    Returns (conf int64 [C, C+1] — row = predicted class, column = label, last column = labels outside [0, C) —, label.max())."""
+    _lib.require_device()
+    if not _on_device(pred):
+        raise _lib.CgbError("climategan_b200 tensors must live on a CUDA device (no CPU path)")
+    n, c = pred.shape[0], pred.shape[1]
+    hw = pred[0, 0].numel()
+    lab = label.to(pred.device)
+    if lab.numel() != n * hw:
+        raise ValueError(f"argmax_confusion: label {tuple(label.shape)} does not match prediction {tuple(pred.shape)}")
+    lab = lab.reshape(n, hw).long().contiguous()
+    x = _f32c(pred.detach())
+    out = torch.zeros(c * (c + 1) + 1, dtype=torch.int64, device=pred.device)
+    out[-1] = torch.iinfo(torch.int64).min
+    check(_L().cgb_argmax_confusion(_p(x), _p(lab), _p(out), _p(out[-1:]), n, c, hw, _st()), "argmax_confusion")
+    return out[:-1].view(c, c + 1), out[-1]
 
 
 class _EntropyNCHW(Function):

@@ -652,6 +652,72 @@ class Trainer:
         """Mask then paint (the flood event without the other two)."""
         return self.compute_flood(x)
 
+    # ---------------------------------------------------------------- validation metrics (trainer.py:1706-1799)
+    def eval_images(self, mode, domain):
+        """trainer.py:1706-1799: accuracy and mIOU of the segmentation (and of the bucketised depth on the sim domain) over
+        ``self.display_images[mode][domain]``, one image at a time as in the reference.  Predictions stay on the device: each
+        (prediction, label) pair costs one pass over the logits (``eval_metrics.accuracy_and_mIOU``) and one 1 KB copy.
+        The mask block is guarded by ``"m" in self.opts`` exactly as the reference writes it (:1753) — false for the stock option
+        tree, whose top level has no such key, so the reference reports -1 for both mask metrics; same here."""
+        import numpy as np
+
+        from .eval_metrics import accuracy_and_mIOU
+
+        display_images = getattr(self, "display_images", None) or {}
+        if domain == "s" and self.kitti_pretrain:
+            domain = "kitti"
+        if domain == "rf" or domain not in display_images.get(mode, {}):
+            return
+        scores = {"m": {}}
+        if "s" in self.opts.tasks:
+            scores["s"] = {}
+        if "d" in self.opts.tasks and domain == "s" and self.opts.gen.d.classify.enable:
+            scores["d"] = {}
+        for task in scores:
+            scores[task] = {"accuracy": [], "mIOU": []}
+
+        def record(task, pred, label):
+            acc, miou = accuracy_and_mIOU(pred, label)
+            scores[task]["accuracy"].append(acc)
+            scores[task]["mIOU"].append(miou)
+
+        with torch.no_grad():
+            for im_set in display_images[mode][domain]:
+                x = im_set["data"]["x"].unsqueeze(0).to(self.device).float().contiguous()
+                z = self.G.encode(x)
+                s_pred = d_pred = z_depth = None
+                if "d" in scores:
+                    d_pred, z_depth = self.G.decode_d(z)
+                    if domain == "s":
+                        record("d", d_pred, im_set["data"]["d"].unsqueeze(0))
+                if "s" in scores:
+                    if z_depth is None and self.opts.gen.s.use_dada and "d" in self.opts.tasks:
+                        _, z_depth = self.G.decode_d(z)
+                    s_pred = self.G.decode_s(z, z_depth)
+                    record("s", s_pred, im_set["data"]["s"].unsqueeze(0))
+                if "m" in self.opts:
+                    cond = self.G.make_m_cond(d_pred, s_pred, x) if s_pred is not None and d_pred is not None else None
+                    if z_depth is None and self.opts.gen.m.use_dada and "d" in self.opts.tasks:
+                        _, z_depth = self.G.decode_d(z)
+                    pred_mask = (self.G.mask(z=z, cond=cond, z_depth=z_depth) > 0.5).float()
+                    m = im_set["data"]["m"].unsqueeze(0)
+                    acc, _ = accuracy_and_mIOU(pred_mask, m)                                     # one channel: see accuracy()
+                    _, miou = accuracy_and_mIOU(torch.cat([1 - pred_mask, pred_mask], dim=1), m)
+                    scores["m"]["accuracy"].append(acc)
+                    scores["m"]["mIOU"].append(miou)
+        scores = {task: {k: (float(np.mean(v)) if v else float("nan")) for k, v in met.items()} for task, met in scores.items()}
+        scores = {task: {k: (v if not np.isnan(v) else -1) for k, v in met.items()} for task, met in scores.items()}
+        flat = {f"{task}.{k}": v for task, met in scores.items() for k, v in met.items()}
+        self.metrics = getattr(self, "metrics", {})
+        self.metrics[f"metrics_{mode}_{domain}"] = flat
+        exp = getattr(self, "exp", None)
+        if exp is not None:
+            exp.log_metrics(flat, prefix=f"metrics_{mode}_{domain}", step=self.logger.global_step)
+        elif self.verbose > 0:
+            print(f"metrics_{mode}_{domain}")
+            print(flat)
+        return 0
+
     # ---------------------------------------------------------------- checkpoints (trainer.py:337-412, 470-600)
     def save(self):
         """``{output_path}/checkpoints/latest_ckpt.pth`` with the reference's keys: G, g_opt, D, d_opt, epoch, step."""

@@ -294,6 +294,15 @@ int cgb_dada_depth_loss(const float* pred, const float* label, float* loss, floa
 int cgb_sigm_loss(const float* pred, const float* target, float* loss, float* gpred, float* ws, int32_t n, int32_t h, int32_t w,
                   float gmweight, int32_t scales, void* stream);
 
+/* ---- validation metrics (Trainer.eval_images trainer.py:1706-1799; accuracy / mIOU climategan/eval_metrics.py:68-130) --------
+ * argmax_confusion: conf[p][l] += 1 per pixel with p = argmax over the class axis of logits [n][c][hw] fp32 (first maximum, NaN
+ *   counts as the maximum, like torch.argmax) and l = label [n][hw] int64, labels outside [0, c) counted in the extra column c.
+ *   conf is int64 [c][c+1] and ACCUMULATES (caller zeroes it); label_max is one int64, atomically raised to the largest label seen
+ *   (caller initialises it to INT64_MIN) — mIOU's two-class case scores only class label.max() (eval_metrics.py:105-107).
+ *   1 <= c <= 64.  Both metrics are integer functions of conf: bit-exact against the reference. */
+int cgb_argmax_confusion(const float* logits, const int64_t* label, int64_t* conf, int64_t* label_max, int32_t n, int32_t c,
+                         int64_t hw, void* stream);
+
 /* ---- inference events (Trainer.infer_all, trainer.py:218-334) — NCHW fp32 images at the API edge ---------------------
  * minmax_per_sample: per-sample min/max (tutils.normalize :567-576) -> mm[n][2].
  * fire (climategan/fire.py:68-127): fire_tone = normalize(x,0,255), warm (+40,-10,-20), clamp, uint8, adjust_contrast(c),

@@ -679,6 +679,15 @@ class EmuLib(NoopLib):
         mx = mm[:, 1].view(n, *([1] * (t.dim() - 1)))
         return lo + (hi - lo) * (t - mn) / (mx - mn)
 
+    def e_argmax_confusion(self, logits, label, conf, label_max, n, c, hw, stream):   # eval_metrics.py:68-124 (header contract)
+        P = torch.argmax(_t(logits, (n, c, hw), torch.float32), 1).reshape(-1)
+        L = _t(label, (n * hw,), torch.int64)
+        col = torch.where((L >= 0) & (L < c), L, torch.full_like(L, c))
+        Cm = _t(conf, (c * (c + 1),), torch.int64)
+        Cm += torch.bincount(P * (c + 1) + col, minlength=c * (c + 1))
+        M = _t(label_max, (1,), torch.int64)
+        M[0] = max(int(M[0]), int(L.max()))
+
     def e_minmax_per_sample(self, x, mm, n, count, stream):
         X = _t(x, (n, count), torch.float32)
         M = _t(mm, (n, 2), torch.float32)

@@ -59,9 +59,17 @@ RUNS = [
 
 import tests.test_gpu_infer_all as t_infer  # noqa: E402
 
+import tests.test_gpu_zz_new_kernels as t_new  # noqa: E402
+
 RUNS += [
     (t_infer.test_infer_all_bf16_close_to_reference, {}),
     (t_infer.test_infer_all_single_image_and_ignore, {}),
+    # the entry points that have not run on hardware yet: the tests' own logic and tolerances, against the header contracts
+    (t_new.test_dada_depth_loss, dict(n=2, h=16, w=12)),
+    (t_new.test_dada_depth_loss, dict(n=3, h=33, w=47)),
+    (t_new.test_pack_weight_kernel, dict(dtype=F32)),
+    (t_new.test_pack_weight_kernel, dict(dtype=BF16)),
+    (t_new.test_eval_metrics_match_reference_fixture_and_oracle, {}),
 ]
 
 

@@ -274,21 +274,3 @@ def test_sigm_loss(cuda, n, h, w):
     out.backward()
     assert abs(float(out) - float(ref)) < 2e-5 * abs(float(ref)), (float(out), float(ref))
     assert rel_max(pd.grad, pr.grad) < 2e-4
-
-
-@pytest.mark.parametrize("n,h,w", [(2, 16, 12), (3, 33, 47)])
-def test_dada_depth_loss(cuda, n, h, w):
-    """DADADepthLoss (losses.py:596-620; gen.d.loss = "dada"): reverse Huber with the batch-wide threshold 0.2 * max|pred - label|
-    (a constant of the graph), value and gradient against plain PyTorch."""
-    pred = _rand(n, 1, h, w, seed=1)
-    targ = _rand(n, 1, h, w, seed=2).abs()
-    pr = pred.clone().requires_grad_()
-    adiff = torch.abs(pr - targ)
-    c = 0.2 * float(adiff.max())
-    ref = ((adiff * (adiff <= c).float()).sum() + ((adiff * adiff + c * c) / (2 * c) * (adiff > c).float()).sum()) / adiff.numel()
-    ref.backward()
-    pd = pred.to(cuda).requires_grad_()
-    out = ops.dada_depth_loss(pd, targ.to(cuda))
-    out.backward()
-    assert abs(float(out) - float(ref)) < 1e-5 * abs(float(ref))
-    assert rel_max(pd.grad, pr.grad) < 1e-5

@@ -357,18 +357,3 @@ def test_bad_arguments_raise(cuda):
     with pytest.raises(_lib.CgbError):  # reflect pad >= size
         ops.conv2d(torch.zeros(1, 2, 2, 8, device=cuda), torch.zeros(8, 8, 5, 5, device=cuda), pad=2,
                    pad_mode=_lib.PAD_REFLECT)
-
-
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_pack_weight_kernel(cuda, dtype):
-    """cgb_pack_weight (one launch) against the torch packing (zeros + permute + slice copy): bit-exact, channel padding zero."""
-    torch.manual_seed(3)
-    for (o, i, k, cis, cos) in [(20, 40, 3, None, None), (128, 3, 3, 8, None), (1, 16, 3, None, 8), (64, 4, 4, 8, None),
-                                (1024, 256, 1, None, None), (11, 256, 1, 256, 16), (48, 128, 3, 128, 96)]:
-        w = torch.randn(o, i, k, k, device=cuda)
-        ref = ops.pack_weight(w, dtype, cis=cis, cos=cos, kernel=False)
-        got = ops.pack_weight(w, dtype, cis=cis, cos=cos, kernel=True)
-        assert got.shape == ref.shape and got.dtype == ref.dtype
-        assert torch.equal(got, ref), (o, i, k, cis, cos)
-    wt = torch.randn(8, 24, 3, 3, device=cuda).transpose(0, 1)   # non-contiguous input
-    assert torch.equal(ops.pack_weight(wt, dtype, kernel=True), ops.pack_weight(wt, dtype, kernel=False))

@@ -1,0 +1,73 @@
+"""GPU tests of the entry points written after the round's GPU budget was spent (they have not run on hardware yet).  The
+file sorts last on purpose: the suite is run with -x, and a first-run failure here must not hide the validated tests before it.
+Each kernel is also pinned on CPU through the emulated ABI (tests/test_emulated.py)."""
+import pytest
+import torch
+
+from climategan_b200 import ops
+from tests.helpers import rel_max
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(*shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g)
+
+
+@pytest.mark.parametrize("n,h,w", [(2, 16, 12), (3, 33, 47)])
+def test_dada_depth_loss(cuda, n, h, w):
+    """DADADepthLoss (losses.py:596-620; gen.d.loss = "dada"): reverse Huber with the batch-wide threshold 0.2 * max|pred - label|
+    (a constant of the graph), value and gradient against plain PyTorch."""
+    pred = _rand(n, 1, h, w, seed=1)
+    targ = _rand(n, 1, h, w, seed=2).abs()
+    pr = pred.clone().requires_grad_()
+    adiff = torch.abs(pr - targ)
+    c = 0.2 * float(adiff.max())
+    ref = ((adiff * (adiff <= c).float()).sum() + ((adiff * adiff + c * c) / (2 * c) * (adiff > c).float()).sum()) / adiff.numel()
+    ref.backward()
+    pd = pred.to(cuda).requires_grad_()
+    out = ops.dada_depth_loss(pd, targ.to(cuda))
+    out.backward()
+    assert abs(float(out) - float(ref)) < 1e-5 * abs(float(ref))
+    assert rel_max(pd.grad, pr.grad) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_pack_weight_kernel(cuda, dtype):
+    """cgb_pack_weight (one launch) against the torch packing (zeros + permute + slice copy): bit-exact, channel padding zero."""
+    torch.manual_seed(3)
+    for (o, i, k, cis, cos) in [(20, 40, 3, None, None), (128, 3, 3, 8, None), (1, 16, 3, None, 8), (64, 4, 4, 8, None),
+                                (1024, 256, 1, None, None), (11, 256, 1, 256, 16), (48, 128, 3, 128, 96)]:
+        w = torch.randn(o, i, k, k, device=cuda)
+        ref = ops.pack_weight(w, dtype, cis=cis, cos=cos, kernel=False)
+        got = ops.pack_weight(w, dtype, cis=cis, cos=cos, kernel=True)
+        assert got.shape == ref.shape and got.dtype == ref.dtype
+        assert torch.equal(got, ref), (o, i, k, cis, cos)
+    wt = torch.randn(8, 24, 3, 3, device=cuda).transpose(0, 1)   # non-contiguous input
+    assert torch.equal(ops.pack_weight(wt, dtype, kernel=True), ops.pack_weight(wt, dtype, kernel=False))
+
+
+def test_eval_metrics_match_reference_fixture_and_oracle(cuda):
+    """cgb_argmax_confusion -> accuracy / mIOU (eval_metrics.py:68-124; Trainer.eval_images): the fixture generated from the
+    reference's own functions (ties, absent classes, an ignore index, two-class masks, a ragged size), then the oracle at the full
+    640 x 640 / 11 classes / batch 8 with NaN logits, and the size-independent property sum(conf) = pixels."""
+    import numpy as np
+
+    from climategan_b200 import eval_metrics as em
+    from oracle import eval_metrics_oracle as o
+    from tests.golden.eval_cases import cases
+    from tests.test_eval_metrics import check_case
+
+    for name, (pred, label, kind) in cases().items():
+        check_case(name, pred.to(cuda), label.to(cuda), kind, em.accuracy, em.mIOU)
+    rs = np.random.RandomState(11)
+    pred = rs.standard_normal((8, 11, 640, 640)).astype(np.float32)
+    pred[rs.random_sample(pred.shape) < 1e-4] = np.nan          # a NaN is the maximum (torch.argmax / np.argmax)
+    label = rs.randint(0, 12, size=(8, 1, 640, 640)).astype(np.int64)    # 11 = out of range
+    conf, lmax = em.confusion(torch.from_numpy(pred).to(cuda), torch.from_numpy(label).to(cuda))
+    p = np.argmax(pred, axis=1).reshape(-1)
+    want = np.bincount(p * 12 + label.reshape(-1), minlength=11 * 12).reshape(11, 12)
+    assert conf.sum() == label.size and lmax == 11
+    assert np.array_equal(conf, want)
+    assert em.mIOU(torch.from_numpy(pred).to(cuda), torch.from_numpy(label).to(cuda)) == pytest.approx(o.miou(pred, label), rel=1e-14)
