@@ -134,6 +134,9 @@ SIGNATURES = {
     "cgb_ground_intersection_loss": ([_P, _P, _P, _L, _P], C.c_int),
     "cgb_sigm_loss": ([_P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _P], C.c_int),
     "cgb_dada_depth_loss": ([_P, _P, _P, _P, _L, _P], C.c_int),
+    "cgb_diff_aug_sum": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_diff_aug_fwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_diff_aug_bwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_argmax_confusion": ([_P, _P, _P, _P, _I, _I, _L, _P], C.c_int),
     "cgb_minmax_per_sample": ([_P, _P, _I, _L, _P], C.c_int),
     "cgb_fire_tone": ([_P, _P, _P, _P, _I, _I, _F, _F, _P], C.c_int),

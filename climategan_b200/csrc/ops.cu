@@ -1503,6 +1503,161 @@ extern "C" int cgb_pack_weight(const float* w, void* wp, int32_t dtype, int32_t 
   return after_launch("pack_weight");
 }
 
+// ---------------------------------------------------------------------------------------------------
+// DiffTransforms (climategan/transforms.py:505-626; gen.p.diff_aug, trainer.py:1079-1081, 1319-1321): differentiable augmentation
+// of the images the painter discriminator sees — brightness, contrast, saturation jitter, integer translation with zero fill,
+// cutout — fused into one pass over the image (the reference runs ~25 ATen kernels with two advanced-index gathers).
+// NCHW fp32, c <= 8.  params[n][8] = {b, cf, sf, tx, ty, ox, oy, -}: per-sample draws made by the caller ON THE DEVICE:
+//   v1 = x + b ; v2 = (v1 - mean_all(v1)) cf + mean_all(v1) ; v3 = (v2 - mean_ch(v2)) sf + mean_ch(v2)          (:505-533)
+//   y(i, j) = v3(i + tx, j + ty), 0 outside the image ; y = 0 inside the cutout box                               (:546-606)
+// (jitter off: b = 0, cf = sf = 1; translation off: tx = ty = 0; cutout off: cut_h = 0.)  One thread per pixel, the c channel
+// planes read / written coalesced over the pixel index.  sums: per-sample fp64 totals from diff_aug_sum_kernel.
+struct DiffAugGeom {
+  int c, h, w, cut_h, cut_w;
+};
+
+__device__ __forceinline__ bool diffaug_cut(const float* __restrict__ pr, const DiffAugGeom& g, int i, int j) {
+  if (g.cut_h <= 0) return false;
+  const int a = (int)pr[5] - g.cut_h / 2, b = (int)pr[6] - g.cut_w / 2;   // the reference clamps the box's indices into the image
+  return i >= max(a, 0) && i <= min(a + g.cut_h - 1, g.h - 1) && j >= max(b, 0) && j <= min(b + g.cut_w - 1, g.w - 1);
+}
+
+// mode 0: sums[n] += sum of t (the mean the contrast jitter is taken around);
+// mode 1: t is the output gradient: sums[n] += sum over the output pixels that are outside the cutout and whose source pixel is
+//         inside the image (the total that flows back through mean_all).
+__global__ void __launch_bounds__(256)
+diff_aug_sum_kernel(const float* __restrict__ t, const float* __restrict__ params, double* __restrict__ sums, DiffAugGeom g, int mode) {
+  const int n = blockIdx.y;
+  const float* pr = params + n * 8;
+  const int tx = (int)pr[3], ty = (int)pr[4];
+  const long long hw = (long long)g.h * g.w;
+  const float* base = t + (long long)n * g.c * hw;
+  double local = 0.0;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += (long long)gridDim.x * blockDim.x) {
+    if (mode == 1) {
+      const int i = (int)(pix / g.w), j = (int)(pix - (long long)i * g.w);
+      const int si = i + tx, sj = j + ty;
+      if (si < 0 || si >= g.h || sj < 0 || sj >= g.w || diffaug_cut(pr, g, i, j)) continue;
+    }
+    float s = 0.f;
+    for (int ch = 0; ch < g.c; ++ch) s += base[ch * hw + pix];
+    local += (double)s;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  __shared__ double sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) tot += sh[k];
+    atomicAdd(&sums[n], tot);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+diff_aug_fwd_kernel(const float* __restrict__ x, const float* __restrict__ params, const double* __restrict__ sums,
+                    float* __restrict__ y, DiffAugGeom g) {
+  const int n = blockIdx.y;
+  const float* pr = params + n * 8;
+  const float b = pr[0], cf = pr[1], sf = pr[2];
+  const int tx = (int)pr[3], ty = (int)pr[4];
+  const long long hw = (long long)g.h * g.w;
+  const float mean_b = (float)(sums[n] / (double)(g.c * hw)) + b;
+  const float* xb = x + (long long)n * g.c * hw;
+  float* yb = y + (long long)n * g.c * hw;
+  const float inv_c = 1.f / (float)g.c;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(pix / g.w), j = (int)(pix - (long long)i * g.w);
+    const int si = i + tx, sj = j + ty;
+    const bool live = si >= 0 && si < g.h && sj >= 0 && sj < g.w && !diffaug_cut(pr, g, i, j);
+    float v[8];
+    float mch = 0.f;
+    if (live) {
+      const long long src = (long long)si * g.w + sj;
+      for (int ch = 0; ch < g.c; ++ch) {
+        const float v1 = xb[ch * hw + src] + b;
+        v[ch] = (v1 - mean_b) * cf + mean_b;
+        mch += v[ch];
+      }
+      mch *= inv_c;
+    }
+    for (int ch = 0; ch < g.c; ++ch) yb[ch * hw + pix] = live ? (v[ch] - mch) * sf + mch : 0.f;
+  }
+}
+
+// adjoint w.r.t. x.  gsums[n] = diff_aug_sum_kernel(mode 1) of gy.
+__global__ void __launch_bounds__(256)
+diff_aug_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ params, const double* __restrict__ gsums,
+                    float* __restrict__ gx, DiffAugGeom g) {
+  const int n = blockIdx.y;
+  const float* pr = params + n * 8;
+  const float cf = pr[1], sf = pr[2];
+  const int tx = (int)pr[3], ty = (int)pr[4];
+  const long long hw = (long long)g.h * g.w;
+  const float through_mean = (1.f - cf) * (float)(gsums[n] / (double)(g.c * hw));
+  const float* gyb = gy + (long long)n * g.c * hw;
+  float* gxb = gx + (long long)n * g.c * hw;
+  const float inv_c = 1.f / (float)g.c;
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < hw; pix += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(pix / g.w), bcol = (int)(pix - (long long)a * g.w);   // a source pixel; it feeds output (a - tx, bcol - ty)
+    const int i = a - tx, j = bcol - ty;
+    const bool live = i >= 0 && i < g.h && j >= 0 && j < g.w && !diffaug_cut(pr, g, i, j);
+    float g3[8];
+    float gch = 0.f;
+    if (live) {
+      const long long dst = (long long)i * g.w + j;
+      for (int ch = 0; ch < g.c; ++ch) {
+        g3[ch] = gyb[ch * hw + dst];
+        gch += g3[ch];
+      }
+    }
+    for (int ch = 0; ch < g.c; ++ch) {
+      const float g2 = live ? sf * g3[ch] + (1.f - sf) * inv_c * gch : 0.f;
+      gxb[ch * hw + pix] = cf * g2 + through_mean;
+    }
+  }
+}
+
+static int diff_aug_check(const void* a, const void* b, const void* c, const void* d, int n, int ch, int h, int w, int cut_h,
+                          int cut_w) {
+  CGB_REQUIRE(a && b && c && d, "diff_aug: null pointer");
+  CGB_REQUIRE(n > 0 && n <= 65535 && ch >= 1 && ch <= 8 && h > 0 && w > 0 && cut_h >= 0 && cut_w >= 0 && (cut_h > 0) == (cut_w > 0),
+              "diff_aug: bad shape n=%d c=%d h=%d w=%d cut=%dx%d", n, ch, h, w, cut_h, cut_w);
+  return CGB_OK;
+}
+
+extern "C" int cgb_diff_aug_sum(const float* t, const float* params, double* sums, int32_t n, int32_t c, int32_t h, int32_t w,
+                                int32_t cut_h, int32_t cut_w, int32_t mode, void* stream) {
+  CGB_CHECK_DEVICE();
+  if (int s = diff_aug_check(t, params, sums, sums, n, c, h, w, cut_h, cut_w)) return s;
+  CGB_REQUIRE(mode == 0 || mode == 1, "diff_aug_sum: mode %d", mode);
+  int gx = grid_for((long long)h * w);
+  if (gx > 148 * 2) gx = 148 * 2;
+  diff_aug_sum_kernel<<<dim3(gx, n), 256, 0, (cudaStream_t)stream>>>(t, params, sums, DiffAugGeom{c, h, w, cut_h, cut_w}, mode);
+  return after_launch("diff_aug_sum");
+}
+
+extern "C" int cgb_diff_aug_fwd(const float* x, const float* params, const double* sums, float* y, int32_t n, int32_t c, int32_t h,
+                                int32_t w, int32_t cut_h, int32_t cut_w, void* stream) {
+  CGB_CHECK_DEVICE();
+  if (int s = diff_aug_check(x, params, sums, y, n, c, h, w, cut_h, cut_w)) return s;
+  int gx = grid_for((long long)h * w);
+  if (gx > 148 * 4) gx = 148 * 4;
+  diff_aug_fwd_kernel<<<dim3(gx, n), 256, 0, (cudaStream_t)stream>>>(x, params, sums, y, DiffAugGeom{c, h, w, cut_h, cut_w});
+  return after_launch("diff_aug_fwd");
+}
+
+extern "C" int cgb_diff_aug_bwd(const float* gy, const float* params, const double* gsums, float* gx_out, int32_t n, int32_t c,
+                                int32_t h, int32_t w, int32_t cut_h, int32_t cut_w, void* stream) {
+  CGB_CHECK_DEVICE();
+  if (int s = diff_aug_check(gy, params, gsums, gx_out, n, c, h, w, cut_h, cut_w)) return s;
+  int gx = grid_for((long long)h * w);
+  if (gx > 148 * 4) gx = 148 * 4;
+  diff_aug_bwd_kernel<<<dim3(gx, n), 256, 0, (cudaStream_t)stream>>>(gy, params, gsums, gx_out, DiffAugGeom{c, h, w, cut_h, cut_w});
+  return after_launch("diff_aug_bwd");
+}
+
 extern "C" int cgb_mask_cond_bwd(const float* x, const void* gcond, float* gm, int32_t dtype, int32_t n, int32_t hw, int32_t cs,
                                  void* stream) {
   CGB_CHECK_DEVICE();

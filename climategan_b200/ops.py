@@ -1367,6 +1367,45 @@ def dada_depth_loss(pred, target):
     return _FusedLoss.apply(pred, run)
 
 
+class _DiffAug(Function):
+    @staticmethod
+    def forward(ctx, x, params, cut_h, cut_w):
+        x = _f32c(x)
+        n, c, h, w = x.shape
+        sums = torch.zeros(n, dtype=torch.float64, device=x.device)
+        y = torch.empty_like(x)
+        L = _L()
+        check(L.cgb_diff_aug_sum(_p(x), _p(params), _p(sums), n, c, h, w, cut_h, cut_w, 0, _st()), "diff_aug_sum")
+        check(L.cgb_diff_aug_fwd(_p(x), _p(params), _p(sums), _p(y), n, c, h, w, cut_h, cut_w, _st()), "diff_aug_fwd")
+        ctx.save_for_backward(params)
+        ctx.cut = (cut_h, cut_w)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (params,) = ctx.saved_tensors
+        cut_h, cut_w = ctx.cut
+        gy = _f32c(gy)
+        n, c, h, w = gy.shape
+        gsums = torch.zeros(n, dtype=torch.float64, device=gy.device)
+        gx = torch.empty_like(gy)
+        L = _L()
+        check(L.cgb_diff_aug_sum(_p(gy), _p(params), _p(gsums), n, c, h, w, cut_h, cut_w, 1, _st()), "diff_aug_sum")
+        check(L.cgb_diff_aug_bwd(_p(gy), _p(params), _p(gsums), _p(gx), n, c, h, w, cut_h, cut_w, _st()), "diff_aug_bwd")
+        return gx, None, None, None
+
+
+def diff_aug(x, params, cut_h=0, cut_w=0):
+    """One differentiable augmentation of an NCHW fp32 image batch (DiffTransforms, transforms.py:493-626) from per-sample draws
+    ``params`` [N, 8] on the device — see include/cgb200.h for the row layout.  Three launches forward, two backward."""
+    _lib.require_device()
+    if not _on_device(x):
+        raise _lib.CgbError("climategan_b200 tensors must live on a CUDA device (no CPU path)")
+    if x.dim() != 4 or x.shape[1] > 8 or tuple(params.shape) != (x.shape[0], 8) or params.dtype != torch.float32:
+        raise ValueError(f"diff_aug: x [N,C<=8,H,W] and params [N,8] fp32 expected, got {tuple(x.shape)} / {tuple(params.shape)}")
+    return _DiffAug.apply(x, params.contiguous(), int(cut_h), int(cut_w))
+
+
 def argmax_confusion(pred, label):
     """Confusion matrix of argmax(pred, dim=1) against an integer label, on the device, in one launch — what accuracy and mIOU
     (eval_metrics.py:68-130) are functions of.  pred [N,C,H,W] float, label [N,H,W] / [N,1,H,W] integer-valued.

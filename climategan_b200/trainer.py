@@ -112,6 +112,11 @@ class Trainer:
             else:   # no adversarial loss configured (trainer.py:762-767): nothing to optimise, update_D is never called
                 self.d_opt, self.d_scheduler = None, None
             self.losses = get_losses(self.opts, self.verbose, device=self.device, storage_dtype=self.storage_dtype)
+            self.diff_transforms = None
+            if "p" in self.opts.tasks and self.opts.gen.p.diff_aug.use:                # trainer.py:772-773
+                from .transforms import DiffTransforms
+
+                self.diff_transforms = DiffTransforms(self.opts.gen.p.diff_aug)
             self.G.train()
             self.D.train()
         else:
@@ -464,8 +469,9 @@ class Trainer:
             loss = ops.l1_loss(ops.paste(zeros, mf, fake_flooded), ops.paste(zeros, mf, x).detach()) * lambdas.G.p.reconstruction
             self.logger.losses.gen.p.reconstruction = loss.detach()
             step_loss = step_loss + loss
-        if self.opts.gen.p.diff_aug.use:
-            raise NotImplementedError("gen.p.diff_aug (off in defaults.yaml:158) is not built")
+        if self.opts.gen.p.diff_aug.use:   # trainer.py:1319-1321: both D inputs, independent draws; the mask channel is not moved
+            fake_flooded = self.diff_transforms(fake_flooded)
+            x = self.diff_transforms(x)
         if self.opts.dis.p.use_local_discriminator:                                   # trainer.py:1322-1356
             fake_d_global = self.D["p"]["global"](fake_flooded)
             fake_d_local = self.D["p"]["local"](ops.paste(zeros, mf, fake_flooded))
@@ -503,6 +509,9 @@ class Trainer:
                 m = batch["data"]["m"]
                 with torch.no_grad():
                     fake = self.G.paint(m, x)
+                    if self.opts.gen.p.diff_aug.use:                                   # trainer.py:1079-1081
+                        fake = self.diff_transforms(fake)
+                        x = self.diff_transforms(x)
                 fake = fake.detach()
                 if self.opts.dis.p.use_local_discriminator:                            # trainer.py:1084-1098
                     zeros, mf = torch.zeros_like(x), m.to(x.dtype)

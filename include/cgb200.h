@@ -294,6 +294,23 @@ int cgb_dada_depth_loss(const float* pred, const float* label, float* loss, floa
 int cgb_sigm_loss(const float* pred, const float* target, float* loss, float* gpred, float* ws, int32_t n, int32_t h, int32_t w,
                   float gmweight, int32_t scales, void* stream);
 
+/* ---- differentiable augmentation (DiffTransforms, climategan/transforms.py:493-626; gen.p.diff_aug, trainer.py:1079-1081,
+ *      1319-1321) — NCHW fp32 images, 1 <= c <= 8 ---------------------------------------------------------------------------
+ * params [n][8] fp32 on the device, one row per sample: {b, cf, sf, tx, ty, ox, oy, unused} = brightness offset (rand - 0.5),
+ *   contrast factor (rand + 0.5), saturation factor (2 rand), row / column translation, cutout offsets (integers stored as floats):
+ *     v1 = x + b ; v2 = (v1 - mean_all(v1)) cf + mean_all(v1) ; v3 = (v2 - mean_ch(v2)) sf + mean_ch(v2)
+ *     y(i, j) = v3(i + tx, j + ty), zero outside the image ; y = 0 in rows [ox - cut_h/2, +cut_h) x columns [oy - cut_w/2, +cut_w)
+ *   clamped into the image (cut_h = cut_w = 0: no cutout; b = 0, cf = sf = 1: no jitter; tx = ty = 0: no translation).
+ * diff_aug_sum ACCUMULATES per-sample fp64 totals into sums[n] (caller zeroes): mode 0 of x (forward: mean_all), mode 1 of the
+ *   output gradient over the output pixels that are outside the cutout and whose source pixel is inside the image (backward).
+ * diff_aug_fwd: y from x, params and the mode-0 sums.  diff_aug_bwd: dL/dx from dL/dy, params and the mode-1 sums. */
+int cgb_diff_aug_sum(const float* t, const float* params, double* sums, int32_t n, int32_t c, int32_t h, int32_t w,
+                     int32_t cut_h, int32_t cut_w, int32_t mode, void* stream);
+int cgb_diff_aug_fwd(const float* x, const float* params, const double* sums, float* y, int32_t n, int32_t c, int32_t h,
+                     int32_t w, int32_t cut_h, int32_t cut_w, void* stream);
+int cgb_diff_aug_bwd(const float* gy, const float* params, const double* gsums, float* gx, int32_t n, int32_t c, int32_t h,
+                     int32_t w, int32_t cut_h, int32_t cut_w, void* stream);
+
 /* ---- validation metrics (Trainer.eval_images trainer.py:1706-1799; accuracy / mIOU climategan/eval_metrics.py:68-130) --------
  * argmax_confusion: conf[p][l] += 1 per pixel with p = argmax over the class axis of logits [n][c][hw] fp32 (first maximum, NaN
  *   counts as the maximum, like torch.argmax) and l = label [n][hw] int64, labels outside [0, c) counted in the extra column c.

@@ -679,6 +679,57 @@ class EmuLib(NoopLib):
         mx = mm[:, 1].view(n, *([1] * (t.dim() - 1)))
         return lo + (hi - lo) * (t - mn) / (mx - mn)
 
+    # ---- DiffTransforms (transforms.py:493-626), restated from the header contract ------------------------------------------
+    @staticmethod
+    def _diffaug_live(P, n, h, w, cut_h, cut_w):
+        """[n, h, w] bool over OUTPUT pixels: source inside the image and outside the cutout; plus the source indices."""
+        ii = torch.arange(h).view(1, h, 1)
+        jj = torch.arange(w).view(1, 1, w)
+        tx, ty = P[:, 3].long().view(n, 1, 1), P[:, 4].long().view(n, 1, 1)
+        si, sj = ii + tx, jj + ty
+        live = (si >= 0) & (si < h) & (sj >= 0) & (sj < w)
+        if cut_h > 0:
+            a = P[:, 5].long().view(n, 1, 1) - cut_h // 2
+            b = P[:, 6].long().view(n, 1, 1) - cut_w // 2
+            cut = (ii >= a.clamp(min=0)) & (ii <= (a + cut_h - 1).clamp(max=h - 1)) & (jj >= b.clamp(min=0)) & (jj <= (b + cut_w - 1).clamp(max=w - 1))
+            live = live & ~cut
+        return live, si.clamp(0, h - 1).expand(n, h, w), sj.clamp(0, w - 1).expand(n, h, w)
+
+    def e_diff_aug_sum(self, t, params, sums, n, c, h, w, cut_h, cut_w, mode, stream):
+        T = _t(t, (n, c, h, w), torch.float32).double()
+        S = _t(sums, (n,), torch.float64)
+        if mode == 1:
+            live, _, _ = self._diffaug_live(_t(params, (n, 8), torch.float32), n, h, w, cut_h, cut_w)
+            T = T * live.unsqueeze(1)
+        S += T.sum((1, 2, 3))
+
+    def e_diff_aug_fwd(self, x, params, sums, y, n, c, h, w, cut_h, cut_w, stream):
+        X = _t(x, (n, c, h, w), torch.float32)
+        P = _t(params, (n, 8), torch.float32)
+        b, cf, sf = (P[:, k].view(n, 1, 1, 1) for k in range(3))
+        mean_b = (_t(sums, (n,), torch.float64) / (c * h * w)).float().view(n, 1, 1, 1) + b
+        v2 = (X + b - mean_b) * cf + mean_b
+        mch = v2.mean(1, keepdim=True)
+        v3 = (v2 - mch) * sf + mch
+        live, si, sj = self._diffaug_live(P, n, h, w, cut_h, cut_w)
+        nn_ = torch.arange(n).view(n, 1, 1).expand(n, h, w)
+        moved = v3.permute(0, 2, 3, 1)[nn_, si, sj].permute(0, 3, 1, 2)
+        _t(y, (n, c, h, w), torch.float32).copy_(moved * live.unsqueeze(1))
+
+    def e_diff_aug_bwd(self, gy, params, gsums, gx, n, c, h, w, cut_h, cut_w, stream):
+        G = _t(gy, (n, c, h, w), torch.float32)
+        P = _t(params, (n, 8), torch.float32)
+        cf, sf = P[:, 1].view(n, 1, 1, 1), P[:, 2].view(n, 1, 1, 1)
+        live, si, sj = self._diffaug_live(P, n, h, w, cut_h, cut_w)
+        g3 = torch.zeros(n, h, w, c)
+        nn_ = torch.arange(n).view(n, 1, 1).expand(n, h, w)
+        src = (G * live.unsqueeze(1)).permute(0, 2, 3, 1)
+        g3.index_put_((nn_[live], si[live], sj[live]), src[live])          # a translation is one-to-one on the live pixels
+        g3 = g3.permute(0, 3, 1, 2)
+        g2 = sf * g3 + (1 - sf) * g3.mean(1, keepdim=True)
+        through = (1 - cf) * (_t(gsums, (n,), torch.float64) / (c * h * w)).float().view(n, 1, 1, 1)
+        _t(gx, (n, c, h, w), torch.float32).copy_(cf * g2 + through)
+
     def e_argmax_confusion(self, logits, label, conf, label_max, n, c, hw, stream):   # eval_metrics.py:68-124 (header contract)
         P = torch.argmax(_t(logits, (n, c, hw), torch.float32), 1).reshape(-1)
         L = _t(label, (n * hw,), torch.int64)

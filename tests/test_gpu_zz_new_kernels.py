@@ -71,3 +71,34 @@ def test_eval_metrics_match_reference_fixture_and_oracle(cuda):
     assert conf.sum() == label.size and lmax == 11
     assert np.array_equal(conf, want)
     assert em.mIOU(torch.from_numpy(pred).to(cuda), torch.from_numpy(label).to(cuda)) == pytest.approx(o.miou(pred, label), rel=1e-14)
+
+
+@pytest.mark.parametrize("shape,cut,shift", [((3, 3, 24, 40), (12, 20), (3, 5)), ((2, 3, 17, 23), (5, 7), (5, 7)),
+                                             ((2, 3, 640, 640), (320, 320), (80, 80)), ((2, 4, 16, 16), (0, 0), (8, 8))])
+def test_diff_aug_kernels(cuda, shape, cut, shift):
+    """cgb_diff_aug_sum / _fwd / _bwd (DiffTransforms, transforms.py:493-626) against the plain-PyTorch statement of the same op
+    (tests/helpers.torch_diff_aug, itself pinned to the reference's DiffTransforms in tests/test_diff_aug.py) on the same draws:
+    value and gradient, translations and cutout boxes that leave the image included."""
+    from tests.helpers import torch_diff_aug
+
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(h * w + n)
+    x = torch.randn(*shape, generator=g)
+    wgt = torch.randn(*shape, generator=g)
+    p = torch.zeros(n, 8)
+    p[:, 0] = torch.rand(n, generator=g) - 0.5
+    p[:, 1] = torch.rand(n, generator=g) + 0.5
+    p[:, 2] = torch.rand(n, generator=g) * 2
+    p[:, 3] = torch.randint(-shift[0], shift[0] + 1, (n,), generator=g).float()
+    p[:, 4] = torch.randint(-shift[1], shift[1] + 1, (n,), generator=g).float()
+    p[:, 5] = torch.randint(0, h + 1, (n,), generator=g).float()
+    p[:, 6] = torch.randint(0, w + 1, (n,), generator=g).float()
+    p[0, 3:7] = torch.tensor([shift[0], -shift[1], 0, w])        # extremes: largest shifts, box clamped at two corners
+    xr = x.clone().requires_grad_()
+    want = torch_diff_aug(xr, p, *cut)
+    (want * wgt).sum().backward()
+    xd = x.to(cuda).requires_grad_()
+    got = ops.diff_aug(xd, p.to(cuda), *cut)
+    (got * wgt.to(cuda)).sum().backward()
+    assert rel_max(got, want) < 2e-6
+    assert rel_max(xd.grad, xr.grad) < 2e-5
