@@ -583,12 +583,22 @@ SWEEP = {
 }
 
 
-def run_config_sweep(name="config_sweep", batch=2, size=128):
+# gen.p.diff_aug draws from torch's global generator in the middle of the step (transforms.py:493-606): the fixture and the tests
+# seed it before every update_G / update_D ("reseed"), after which both sides consume it identically
+SWEEP_DIFFAUG = {
+    "painter_diff_aug": dict(tasks=("p",), overrides={"gen.p.diff_aug.use": True, "gen.p.diff_aug.do_color_jittering": True,
+                                                      "gen.p.diff_aug.do_cutout": True, "gen.p.diff_aug.cutout_ratio": 0.5,
+                                                      "gen.p.diff_aug.do_translation": True,
+                                                      "gen.p.diff_aug.translation_ratio": 0.125}),
+}
+
+
+def run_config_sweep(name="config_sweep", batch=2, size=128, sweep=None, reseed=False):
     from oracle import ref_trainer as rt
 
     refshim.load("blocks").SPADEResnetBlock.cuda = lambda self, *a, **k: self   # masker.py:196 (SURVEY.md §8c patch 1)
     meta, arrays = {"batch": batch, "size": size, "seeds": {"G": 21, "D": 22, "vgg": 23, "inputs": 7}, "cases": {}}, {}
-    for case, kw in SWEEP.items():
+    for case, kw in (sweep or SWEEP).items():
         kw = dict(kw)
         pl4m = kw.pop("pl4m", False)
         opts = rt.full_opts(size=size, **kw)
@@ -600,11 +610,15 @@ def run_config_sweep(name="config_sweep", batch=2, size=128):
         t = rt.build_reference_trainer(opts, size)
         g_shapes, d_shapes, v_shapes = rt.load_weights(t)
         t.use_pl4m = bool(pl4m)
+        if "p" in opts.tasks and opts.gen.p.diff_aug.use:                            # Trainer.setup, trainer.py:772-773
+            t.diff_transforms = refshim.load("transforms").DiffTransforms(opts.gen.p.diff_aug)
         mdb = rt.synth_batch(opts, batch, size, seed=7)
         logs = []
         for it in range(2):
             for p_ in t.D.parameters():
                 p_.requires_grad = False
+            if reseed:
+                torch.manual_seed(1000 + it)
             t.update_G(mdb)
             if it == 0:
                 arrays[case + "::G.gradnorm"] = np.array([float(p_.grad.norm()) if p_.grad is not None else -1.0
@@ -612,6 +626,8 @@ def run_config_sweep(name="config_sweep", batch=2, size=128):
             for p_ in t.D.parameters():
                 p_.requires_grad = True
             if t.d_opt is not None:
+                if reseed:
+                    torch.manual_seed(2000 + it)
                 t.update_D(mdb)
                 if it == 0:
                     arrays[case + "::D.gradnorm"] = np.array([float(p_.grad.norm()) if p_.grad is not None else -1.0
@@ -649,3 +665,4 @@ if __name__ == "__main__":
     run_masker_v3_case()
     run_masker_v3_case(name="masker_v3_spade", use_spade=True)
     run_config_sweep()
+    run_config_sweep(name="config_sweep_diffaug", sweep=SWEEP_DIFFAUG, reseed=True)

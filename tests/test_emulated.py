@@ -145,7 +145,16 @@ def test_option_sweep_on_the_emulated_abi_matches_the_reference_trainer(case):
         run_sweep_case(case, torch.device("cpu"))
 
 
-def run_sweep_case(case, device, g_norm_rtol=1e-2):
+def test_painter_step_with_diff_aug_on_the_emulated_abi_matches_the_reference_trainer():
+    """gen.p.diff_aug (jitter + translation + cutout) in front of the painter discriminator: two iterations of update_G / update_D
+    against the reference's own Trainer under the same generator seeds (tests/golden/config_sweep_diffaug.*), same tolerances as
+    the option sweep."""
+    with emulated_library() as lib:
+        run_sweep_case("painter_diff_aug", torch.device("cpu"), fixture="config_sweep_diffaug", reseed=True)
+        assert lib.calls["cgb_diff_aug_fwd"] == 8 and lib.calls["cgb_diff_aug_bwd"] == 2
+
+
+def run_sweep_case(case, device, g_norm_rtol=1e-2, fixture="config_sweep", reseed=False):
     """Option combinations around the reference's scenario matrix that have no full fixture (DADA on the mask decoder, base depth
     regression, the reverse-Huber depth loss, v3 encoder + SPADE mask decoder + painter, detached SPADE conditioning, plain Adam, pseudo labels on the real
     domain, MinEnt v1 without the ground-intersection loss, tasks d + s alone, the global + local painter discriminators with
@@ -161,9 +170,11 @@ def run_sweep_case(case, device, g_norm_rtol=1e-2):
     from tests.golden.weights import fill_state_dict
     from tests.helpers import GOLDEN
 
-    sweep = _sweep()
+    import json
+
+    sweep = json.load(open(os.path.join(GOLDEN, fixture + ".json")))
     meta = sweep["cases"][case]
-    arrays = np.load(os.path.join(GOLDEN, "config_sweep.npz"))
+    arrays = np.load(os.path.join(GOLDEN, fixture + ".npz"))
     size, batch = sweep["size"], sweep["batch"]
     kw = dict(meta["kw"])
     kw["tasks"] = tuple(kw["tasks"])
@@ -182,9 +193,13 @@ def run_sweep_case(case, device, g_norm_rtol=1e-2):
         mdb = {dom: t.batch_to_device(b) for dom, b in synth_batch(opts, batch, size, sweep["seeds"]["inputs"]).items()}
         dn = None
         for it in range(2):
+            if reseed:   # the fixture seeds torch's generator before each step side (make_golden.py::SWEEP_DIFFAUG)
+                torch.manual_seed(1000 + it)
             t.update_G(mdb)
             if it == 0:
                 gn = np.array([float(p.grad.norm()) if p.grad is not None and p.requires_grad else -1.0 for p in t.G.parameters()])
+            if reseed:
+                torch.manual_seed(2000 + it)
             t.update_D(mdb)
             if it == 0 and t.d_opt is not None:
                 dn = np.array([float(p.grad.norm()) if p.grad is not None and p.requires_grad else -1.0 for p in t.D.parameters()])
