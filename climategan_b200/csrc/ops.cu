@@ -1575,14 +1575,19 @@ diff_aug_fwd_kernel(const float* __restrict__ x, const float* __restrict__ param
     float mch = 0.f;
     if (live) {
       const long long src = (long long)si * g.w + sj;
-      for (int ch = 0; ch < g.c; ++ch) {
-        const float v1 = xb[ch * hw + src] + b;
-        v[ch] = (v1 - mean_b) * cf + mean_b;
-        mch += v[ch];
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {   // (fixed trip count + predicate: v[] stays in registers)
+        if (ch < g.c) {
+          const float v1 = xb[ch * hw + src] + b;
+          v[ch] = (v1 - mean_b) * cf + mean_b;
+          mch += v[ch];
+        }
       }
       mch *= inv_c;
     }
-    for (int ch = 0; ch < g.c; ++ch) yb[ch * hw + pix] = live ? (v[ch] - mch) * sf + mch : 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch)
+      if (ch < g.c) yb[ch * hw + pix] = live ? (v[ch] - mch) * sf + mch : 0.f;
   }
 }
 
@@ -1607,14 +1612,20 @@ diff_aug_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ para
     float gch = 0.f;
     if (live) {
       const long long dst = (long long)i * g.w + j;
-      for (int ch = 0; ch < g.c; ++ch) {
-        g3[ch] = gyb[ch * hw + dst];
-        gch += g3[ch];
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        if (ch < g.c) {
+          g3[ch] = gyb[ch * hw + dst];
+          gch += g3[ch];
+        }
       }
     }
-    for (int ch = 0; ch < g.c; ++ch) {
-      const float g2 = live ? sf * g3[ch] + (1.f - sf) * inv_c * gch : 0.f;
-      gxb[ch * hw + pix] = cf * g2 + through_mean;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      if (ch < g.c) {
+        const float g2 = live ? sf * g3[ch] + (1.f - sf) * inv_c * gch : 0.f;
+        gxb[ch * hw + pix] = cf * g2 + through_mean;
+      }
     }
   }
 }
