@@ -100,5 +100,5 @@ def test_diff_aug_kernels(cuda, shape, cut, shift):
     xd = x.to(cuda).requires_grad_()
     got = ops.diff_aug(xd, p.to(cuda), *cut)
     (got * wgt.to(cuda)).sum().backward()
-    assert rel_max(got, want) < 2e-6
+    assert rel_max(got, want) < 5e-6     # fp32 rounding only (fp64 sample mean here, ATen's fp32 cascade sum in the reference)
     assert rel_max(xd.grad, xr.grad) < 2e-5
