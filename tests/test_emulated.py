@@ -70,6 +70,7 @@ RUNS += [
     (t_new.test_pack_weight_kernel, dict(dtype=F32)),
     (t_new.test_pack_weight_kernel, dict(dtype=BF16)),
     (t_new.test_eval_metrics_match_reference_fixture_and_oracle, {}),
+    (t_new.test_trainer_eval_images, {}),
     (t_new.test_diff_aug_kernels, dict(shape=(3, 3, 24, 40), cut=(12, 20), shift=(3, 5))),
     (t_new.test_diff_aug_kernels, dict(shape=(2, 3, 17, 23), cut=(5, 7), shift=(5, 7))),
     (t_new.test_diff_aug_kernels, dict(shape=(2, 4, 16, 16), cut=(0, 0), shift=(8, 8))),

@@ -72,20 +72,27 @@ def test_empty_classes_give_nan_and_bad_shapes_raise():
 
 
 def test_trainer_eval_images_on_the_emulated_abi():
+    from tests.emulib import emulated_library
+
+    with emulated_library():
+        check_trainer_eval_images(torch.device("cpu"))
+
+
+def check_trainer_eval_images(device):
     """Trainer.eval_images against the oracle metrics of the same trainer's own predictions (one image at a time, d on the sim
-    domain only, mask metrics -1 as in the reference — see the method's docstring), and the early returns (:1707-1711)."""
+    domain only, mask metrics -1 as in the reference — see the method's docstring), and the early returns (:1707-1711).
+    Shared with the GPU suite."""
     from climategan_b200.trainer import Trainer
     from climategan_b200.utils import full_opts, synth_batch
     from oracle import eval_metrics_oracle as o
-    from tests.emulib import emulated_library
 
     size = 64
     opts = full_opts(size=size, tasks=("d", "s", "m"), overrides={"gen.d.architecture": "base", "gen.d.classify.enable": True,
                                                                   "gen.d.classify.linspace.buckets": 16, "gen.m.use_dada": False,
                                                                   "gen.s.use_dada": False, "gen.s.upsample_featuremaps": True})
-    with emulated_library():
+    if True:
         torch.manual_seed(0)
-        t = Trainer(opts, device=torch.device("cpu"), storage_dtype=torch.float32).setup(inference=True, input_shape=(size, size))
+        t = Trainer(opts, device=device, storage_dtype=torch.float32).setup(inference=True, input_shape=(size, size))
         t.G.eval()
         batch = synth_batch(opts, 2, size, 5)["s"]["data"]
         sets = [{"data": {k: v[i] for k, v in batch.items()}} for i in range(2)]
@@ -97,13 +104,13 @@ def test_trainer_eval_images_on_the_emulated_abi():
         iou = {"s": [], "d": []}
         with torch.no_grad():
             for im in sets:
-                x = im["data"]["x"].unsqueeze(0)
+                x = im["data"]["x"].unsqueeze(0).to(device)
                 z = t.G.encode(x)
                 d_pred, _ = t.G.decode_d(z)
                 s_pred = t.G.decode_s(z, None)
                 for task, pred in (("d", d_pred), ("s", s_pred)):
-                    acc[task].append(o.accuracy(pred.numpy(), im["data"][task].unsqueeze(0).numpy()))
-                    iou[task].append(o.miou(pred.numpy(), im["data"][task].unsqueeze(0).numpy()))
+                    acc[task].append(o.accuracy(pred.cpu().numpy(), im["data"][task].unsqueeze(0).numpy()))
+                    iou[task].append(o.miou(pred.cpu().numpy(), im["data"][task].unsqueeze(0).numpy()))
     for task in ("s", "d"):
         assert got[f"{task}.accuracy"] == pytest.approx(np.mean(acc[task]), rel=1e-12)
         assert got[f"{task}.mIOU"] == pytest.approx(np.mean(iou[task]), rel=1e-12)

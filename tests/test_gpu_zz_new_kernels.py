@@ -102,3 +102,10 @@ def test_diff_aug_kernels(cuda, shape, cut, shift):
     (got * wgt.to(cuda)).sum().backward()
     assert rel_max(got, want) < 5e-6     # fp32 rounding only (fp64 sample mean here, ATen's fp32 cascade sum in the reference)
     assert rel_max(xd.grad, xr.grad) < 2e-5
+
+
+def test_trainer_eval_images(cuda):
+    """Trainer.eval_images (trainer.py:1706-1799) on the device against the oracle metrics of the trainer's own predictions."""
+    from tests.test_eval_metrics import check_trainer_eval_images
+
+    check_trainer_eval_images(cuda)
