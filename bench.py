@@ -7,10 +7,14 @@ Workloads:
            every masker loss, ExtraAdam), 8 images per domain (r, s, rf) per GPU, 640x640, bf16 storage / fp32 accumulate.
            "images/sec" = per-domain images per second (the reference's batch_size convention, data.py:512).
   painter  C1 / BASELINE.json configs[1]: painter-only OmniGenerator.paint + L1 + backward, 16 images per GPU.
-One "step" = one such pass over one batch of synthetic input.  N > 1: one process per GPU (torchrun), each rank its own
+  masker   C2 / configs[2]: Masker (tasks d,s,m) + AdvEnt discriminators update_G + update_D, 32 images per domain (r, s).
+  infer    C4 / configs[4]: Trainer.infer_all (masker + painter + flood / wildfire / smog), 16 images per GPU.
+One "step" = one such pass over one batch of synthetic input.  The train workloads replay forward + backward from a CUDA graph
+(Trainer.enable_cuda_graphs; --no-graphs times the eager step); the per-class kernel table comes from ONE extra eager step
+bracketed launch by launch with CUDA events, outside the timed region.  N > 1: one process per GPU (torchrun), each rank its own
 batch slice (weak scaling), G and D gradients all-reduced (mean) over NCCL as flat buckets after each backward.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload full|painter]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|gpu-eager] [--workload full|painter|masker|infer]
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the reference algorithm's CPU path (the oracle port — the reference
 itself is Python and /root/reference does not travel to the GPU box).
@@ -35,6 +39,7 @@ import torch  # noqa: E402
 PAINTER_STEP_GFLOP = 1551.6   # C1: painter fwd + dgrad + wgrad, minus dgrad into the 3-channel conditioning
 FULL_STEP_GFLOP = 10113.0     # C3: one (r, s, rf) image triple through update_G + update_D (encoder 4x fwd + 2x bwd, ...)
 INFER_GFLOP = 1339.8          # C4: masker forward 816.9 + painter forward 522.9 per image
+MASKER_STEP_GFLOP = 6710.9    # C2: one (r, s) image pair through update_G + update_D of the masker + AdvEnt discriminators
 
 
 def parse():
@@ -42,24 +47,30 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="full", choices=["full", "painter", "infer"],
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "gpu-eager"])
+    ap.add_argument("--workload", default="full", choices=["full", "painter", "masker", "infer"],
                     help="full = Masker+Painter G+D train step (BASELINE.json metric; SURVEY.md §8d C3, 8 images/domain/GPU); "
                          "painter = C1 painter-only fwd+bwd (configs[1], 16 images/GPU); "
+                         "masker = C2 masker + AdvEnt D train step (configs[2], 32 images/domain/GPU); "
                          "infer = C4 Trainer.infer_all (masker + painter + flood/wildfire/smog compositing, 16 images/GPU)")
     ap.add_argument("--batch", type=int, default=0, help="images per domain per GPU per step (default: 8 full, 16 painter)")
     ap.add_argument("--size", type=int, default=640)
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32", "fp16"])
+    ap.add_argument("--no-graphs", action="store_true", help="time the eager train step instead of the CUDA-graph replay")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the PyTorch-eager-on-this-GPU (cuDNN) baseline leg")
+    ap.add_argument("--eager-mode", default="tf32", choices=["tf32", "bf16"], help="--impl gpu-eager: fp32/TF32 or bf16 autocast")
+    ap.add_argument("--topk", type=int, default=int(os.environ.get("CGB_TOPK", "8")))
     ap.add_argument("--cpu-sample-batch", type=int, default=0, help="CPU baseline sample batch (default: 2 full, 1 painter)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
     if a.batch <= 0:
-        a.batch = 8 if a.workload == "full" else 16
+        a.batch = {"full": 8, "masker": 32}.get(a.workload, 16)
     if a.workload == "infer":
         a.no_cpu_baseline = True   # the CPU arm of this workload is the reference's own infer_all, which cannot travel
+        a.no_gpu_eager = True
     if a.cpu_sample_batch <= 0:
-        a.cpu_sample_batch = 2 if a.workload == "full" else 1
+        a.cpu_sample_batch = 1 if a.workload == "painter" else 2
     return a
 
 
@@ -120,7 +131,7 @@ class ClockSampler(threading.Thread):
 
 def metric_name(args):
     return {"full": "full_train_step_images_per_sec", "painter": "painter_fwd_bwd_images_per_sec",
-            "infer": "infer_all_images_per_sec"}[args.workload]
+            "masker": "masker_train_step_images_per_sec", "infer": "infer_all_images_per_sec"}[args.workload]
 
 
 def workload_config(args):
@@ -131,6 +142,16 @@ def workload_config(args):
                         f"{args.batch} images per domain (r,s,rf) per GPU, {args.size}x{args.size}",
             "batch_per_domain_per_gpu": args.batch, "domains": ["r", "s", "rf"], "size": args.size,
             "images_per_sec_convention": "per-domain images/s (reference batch_size convention); x3 for domain-images/s",
+            "parallelism": f"dp{args.gpus} (per-image batch split; NCCL all-reduce of the flat G and D gradient buckets)",
+            "l2_policy": "working set per step (tens of GB of activations) exceeds the 126 MB L2; no flush needed",
+        }
+    if args.workload == "masker":
+        return {
+            "workload": f"C2 Masker + AdvEnt discriminators train step (Trainer.update_G + update_D, tasks d,s,m; deeplabv2 ResNet-101 "
+                        f"encoder + DADA depth + DeepLab-v2 seg + base mask decoders, D[m] + D[s]), {args.batch} images per domain (r,s) "
+                        f"per GPU, {args.size}x{args.size}",
+            "batch_per_domain_per_gpu": args.batch, "domains": ["r", "s"], "size": args.size,
+            "images_per_sec_convention": "per-domain images/s (reference batch_size convention)",
             "parallelism": f"dp{args.gpus} (per-image batch split; NCCL all-reduce of the flat G and D gradient buckets)",
             "l2_policy": "working set per step (tens of GB of activations) exceeds the 126 MB L2; no flush needed",
         }
@@ -151,91 +172,98 @@ def workload_config(args):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU reference arm: the oracle port of the reference algorithm on the host cores
+# Baseline arms: the oracle port of the reference algorithm — on the host cores (CPU baseline / --impl reference) and, as the
+# "PyTorch eager on this GPU" bar SURVEY.md §8(d) asks for, on the B200 through ATen / cuDNN (--impl gpu-eager)
 # ------------------------------------------------------------------------------------------------
-def cpu_painter_rate(batch: int, size: int, steps: int, warmup: int):
-    from climategan_b200.painter import PainterSpadeDecoder
-    from climategan_b200.utils import default_painter_opts
-    from oracle import painter_oracle as po  # CPU baseline leg only
+def _oracle_step_fn(workload: str, batch: int, size: int, device: str):
+    """(one_step, sample description): one forward + backward of the workload through oracle/ (plain PyTorch ops on
+    reference-layout state_dicts) on `device`; the optimiser's elementwise update is not included (< 1 %)."""
+    from climategan_b200.utils import default_painter_opts, full_opts, synth_batch
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     torch.manual_seed(0)
-    holder = PainterSpadeDecoder(default_painter_opts())  # parameter container only (random init)
-    sd = {k: v.detach().clone() for k, v in holder.state_dict().items()}
-    for k, v in sd.items():
-        v.requires_grad_(not k.endswith(("_u", "_v")))
-    x = torch.rand(batch, 3, size, size) * 2 - 1
-    m = (torch.rand(batch, 1, size, size) > 0.5).float()
-    t = torch.rand(batch, 3, size, size) * 2 - 1
+    dev = torch.device(device)
     z = size // 2 ** 7
-    times = []
-    for i in range(warmup + steps):
-        for v in sd.values():
-            v.grad = None
-        t0 = time.perf_counter()
-        out = po.paint(sd, m, x, z, z, po.n_up_spades_of(sd))
-        loss = torch.nn.functional.l1_loss(out, t)
-        loss.backward()
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    mean_t = sum(times) / len(times)
-    sample = f"oracle (PyTorch fp32 restatement of the reference) paint+L1+backward, batch {batch} at {size}x{size}, {steps} timed steps"
-    return batch / mean_t, mean_t, cores, sample
 
+    def grads_on(sd, skip):
+        out = {}
+        for k, v in sd.items():
+            v = v.detach().clone().to(dev)
+            if v.dtype.is_floating_point and not k.endswith(skip):
+                v.requires_grad_(True)
+            out[k] = v
+        return out
 
-def cpu_full_rate(batch: int, size: int, steps: int, warmup: int):
-    """images/s (per domain) of the reference algorithm's full G+D step on the host cores: oracle/full_step_oracle.py
-    (get_G_loss + backward, get_D_loss + backward; the optimiser's elementwise update is not timed — < 1 % on CPU)."""
+    if workload == "painter":
+        from climategan_b200.painter import PainterSpadeDecoder
+        from oracle import painter_oracle as po  # baseline legs only
+
+        sd = grads_on(PainterSpadeDecoder(default_painter_opts()).state_dict(), ("_u", "_v"))   # parameter container only
+        x = (torch.rand(batch, 3, size, size) * 2 - 1).to(dev)
+        m = (torch.rand(batch, 1, size, size) > 0.5).float().to(dev)
+        t = (torch.rand(batch, 3, size, size) * 2 - 1).to(dev)
+
+        def one_step():
+            for v in sd.values():
+                v.grad = None
+            out = po.paint(sd, m, x, z, z, po.n_up_spades_of(sd))
+            torch.nn.functional.l1_loss(out, t).backward()
+
+        return one_step, f"oracle (PyTorch fp32 restatement of the reference) paint+L1+backward, batch {batch} at {size}x{size}"
+
     from climategan_b200.discriminator import OmniDiscriminator
     from climategan_b200.generator import OmniGenerator
     from climategan_b200.losses import Vgg19
-    from climategan_b200.utils import full_opts, synth_batch
-    from oracle import full_step_oracle as fo  # CPU baseline leg only
+    from oracle import full_step_oracle as fo  # baseline legs only
+    from oracle.painter_oracle import SNState
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    opts = full_opts(nblocks=(3, 4, 23, 3), size=size, latent=640, n_up=7, ndf=64, n_layers=4, num_d=3)
-    G, D, V = OmniGenerator(opts, latent_shape=(size, size)), OmniDiscriminator(opts), Vgg19()  # parameter containers only
-    gsd = {k: v.detach().clone() for k, v in G.state_dict().items()}
-    dsd = {k: v.detach().clone() for k, v in D.state_dict().items()}
-    vsd = {k: v.detach().clone() for k, v in V.state_dict().items()}
-    for k, v in gsd.items():
-        if v.dtype.is_floating_point and not k.endswith(("_u", "_v", "running_mean", "running_var")):
-            v.requires_grad_(True)
-    for k, v in dsd.items():
-        if v.dtype.is_floating_point and not k.endswith(("_u", "_v")):
-            v.requires_grad_(True)
+    tasks = ("d", "s", "m", "p") if workload == "full" else ("d", "s", "m")
+    opts = full_opts(nblocks=(3, 4, 23, 3), size=size, latent=640, n_up=7, ndf=64, n_layers=4, num_d=3, tasks=tasks)
+    gsd = grads_on(OmniGenerator(opts, latent_shape=(size, size)).state_dict(), ("_u", "_v", "running_mean", "running_var"))
+    dsd = grads_on(OmniDiscriminator(opts).state_dict(), ("_u", "_v"))
+    vsd = {k: v.detach().clone().to(dev) for k, v in Vgg19().state_dict().items()} if workload == "full" else None
     mdb = synth_batch(opts, batch, size, 1)
-    z = size // 2 ** 7
-    times = []
-    for i in range(warmup + steps):
+    mdb = {dom: {**b, "data": {k: v.to(dev) for k, v in b["data"].items()}} for dom, b in mdb.items()}
+
+    def one_step():
         for v in list(gsd.values()) + list(dsd.values()):
             v.grad = None
-        t0 = time.perf_counter()
-        loss, _ = fo.full_g_loss(gsd, dsd, vsd, mdb, z)
-        loss.backward()
-        ld, _ = fo.full_d_loss(gsd, dsd, mdb, z)
-        ld.backward()
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    mean_t = sum(times) / len(times)
-    sample = (f"oracle (PyTorch fp32 restatement of the reference's Trainer.update_G/update_D losses + backward), {batch} images "
-              f"per domain (r,s,rf) at {size}x{size} (2 is the minimum: train-mode BatchNorm), {steps} timed step(s), {warmup} warm-up")
-    return batch / mean_t, mean_t, cores, sample
+        if workload == "full":
+            loss, _ = fo.full_g_loss(gsd, dsd, vsd, mdb, z)
+            loss.backward()
+            ld, _ = fo.full_d_loss(gsd, dsd, mdb, z)
+            ld.backward()
+        else:
+            loss, _ = fo.masker_g_loss(gsd, dsd, mdb, SNState(gsd), SNState(dsd))
+            loss.backward()
+            md = fo.masker_d_loss(gsd, dsd, mdb, SNState(gsd), SNState(dsd))
+            (md["m"] + md["s"]).backward()
+
+    doms = "(r,s,rf)" if workload == "full" else "(r,s)"
+    what = "Trainer.update_G/update_D losses + backward" + ("" if workload == "full" else ", tasks d,s,m")
+    return one_step, (f"oracle (PyTorch fp32 restatement of the reference's {what}), {batch} images per domain {doms} at "
+                      f"{size}x{size}" + (" (2 is the minimum: train-mode BatchNorm)" if batch == 2 else ""))
 
 
 def cpu_rate(args, steps, warmup):
-    if args.workload == "full":
-        return cpu_full_rate(args.cpu_sample_batch, args.size, steps, warmup)
-    return cpu_painter_rate(args.cpu_sample_batch, args.size, steps, warmup)
+    """img/s of the reference algorithm on the host cores (oracle port, all threads): (rate, s/step, cores, sample)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    batch = args.cpu_sample_batch
+    one_step, sample = _oracle_step_fn(args.workload, batch, args.size, "cpu")
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        one_step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    mean_t = sum(times) / len(times)
+    return batch / mean_t, mean_t, cores, sample + f", {steps} timed step(s), {warmup} warm-up", batch
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port), all host threads, bounded sample."""
+    """--impl reference: the reference's CPU path (oracle port), all host threads, on a bounded sample of the workload.  The
+    line states the batch it ACTUALLY ran (`config.batch_per_domain_per_gpu`), not the GPU arm's.  Under torchrun (N > 1) rank 0
+    alone runs: the value is ONE CPU process whatever N is (`n_gpus` repeats the launch's N for the driver's bookkeeping)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -243,19 +271,84 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "the infer workload's CPU arm is the reference's own Trainer.infer_all, "
                           "which needs /root/reference (absent on the GPU box); its parity is pinned by tests/golden/infer_all.*"}))
         return
-    steps = max(1, min(args.steps, 1 if args.workload == "full" else 3))
-    warmup = 0 if args.workload == "full" else max(1, min(args.warmup, 1))
-    rate, t, cores, sample = cpu_rate(args, steps, warmup)
+    heavy = args.workload in ("full", "masker")
+    steps = max(1, min(args.steps, 2 if heavy else 3))
+    warmup = 1
+    rate, t, cores, sample, batch = cpu_rate(args, steps, warmup)
+    cfg_args = argparse.Namespace(**{**vars(args), "batch": batch})
+    cfg = workload_config(cfg_args)
+    cfg["note"] = (f"CPU arm: bounded sample of the GPU arm's workload — {batch} image(s) per domain instead of {args.batch}; img/s is "
+                   f"per-image and comparable.  One CPU process on {cores} host threads regardless of --gpus.")
     line = {
         "impl": "reference", "metric": metric_name(args), "value": rate, "unit": "img/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
+        "config": cfg,
         "cpu_baseline": {"value": rate, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def run_gpu_eager(args):
+    """--impl gpu-eager: the same oracle port executed by PyTorch eager ON THIS GPU (ATen / cuDNN kernels, the reference's own
+    execution model) — the "beat this" bar next to the CPU arm (last row).  fp32 with TF32 tensor cores
+    (cudnn.allow_tf32, the PyTorch default for convolutions) or bf16 autocast.  Halves the batch on out-of-memory."""
+    dev = "cuda:%d" % int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(dev)
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    batch = args.batch
+    err = None
+    while batch >= 2 or (args.workload == "painter" and batch >= 1):
+        try:
+            torch.set_default_device(dev)   # the oracle builds its small constant tensors with torch.tensor(...)
+            one_step, sample = _oracle_step_fn(args.workload, batch, args.size, dev)
+            ctx = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if args.eager_mode == "bf16" else (lambda: torch.autocast("cuda", enabled=False))
+            steps, warmup = max(1, min(args.steps, 3)), 2
+            for _ in range(warmup):
+                with ctx():
+                    one_step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                with ctx():
+                    one_step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            print(json.dumps({"impl": "gpu-eager", "metric": metric_name(args), "value": batch / (ms / 1e3), "unit": "img/s",
+                              "ms_per_step": ms, "batch": batch, "steps": steps, "warmup": warmup,
+                              "dtype": "fp32 storage, TF32 tensor cores (cudnn.allow_tf32)" if args.eager_mode == "tf32" else "bf16 autocast",
+                              "sample": sample + " — PyTorch eager (ATen/cuDNN) on this GPU",
+                              "max_mem_gib": torch.cuda.max_memory_allocated() / 2 ** 30}), flush=True)
+            return
+        except torch.cuda.OutOfMemoryError as e:   # noqa: PERF203
+            err = str(e).splitlines()[0]
+            batch //= 2
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            print(json.dumps({"impl": "gpu-eager", "unavailable": f"{type(e).__name__}: {str(e)[:300]}"}), flush=True)
+            return
+    print(json.dumps({"impl": "gpu-eager", "unavailable": f"out of memory down to batch 2: {err}"}), flush=True)
+
+
+def gpu_eager_baseline(args):
+    """Run both eager modes in child processes (their memory is returned before our arm starts) and parse their lines."""
+    out = {}
+    for mode in ("tf32", "bf16"):
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", "gpu-eager", "--workload", args.workload, "--batch", str(args.batch),
+               "--size", str(args.size), "--steps", "3", "--eager-mode", mode]
+        try:
+            res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "WORLD_SIZE": "1", "RANK": "0"})
+            lines = [ln for ln in res.stdout.strip().splitlines() if ln.startswith("{")]
+            out[mode] = json.loads(lines[-1]) if lines else {"unavailable": (res.stderr or "no output")[-300:]}
+        except Exception as e:  # noqa: BLE001
+            out[mode] = {"unavailable": f"{type(e).__name__}: {e}"}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -293,18 +386,22 @@ def build_painter(args, dev, rank, world, dtype):
 
 
 def build_full(args, dev, rank, world, dtype):
+    """C3 (tasks d,s,m,p) and C2 (`--workload masker`: tasks d,s,m) train steps through the Trainer."""
     from climategan_b200.trainer import Trainer
     from climategan_b200.utils import full_opts, synth_batch
 
     B, S = args.batch, args.size
     torch.manual_seed(0)  # identical initial weights on every rank
-    opts = full_opts(nblocks=(3, 4, 23, 3), size=S, latent=640, n_up=7, ndf=64, n_layers=4, num_d=3)
+    tasks = ("d", "s", "m", "p") if args.workload == "full" else ("d", "s", "m")
+    opts = full_opts(nblocks=(3, 4, 23, 3), size=S, latent=640, n_up=7, ndf=64, n_layers=4, num_d=3, tasks=tasks)
     opts.dis.soft_shift, opts.dis.flip_prob = 0.2, 0.05   # defaults.yaml:194-195 (label smoothing / flipping on, as in training)
     t = Trainer(opts, device=dev, storage_dtype=dtype).setup(input_shape=(S, S))
     mdb = synth_batch(opts, B, S, seed=1234 + rank)       # each rank its own slice of the global batch
     host = {dom: {k: v.pin_memory() for k, v in b["data"].items()} for dom, b in mdb.items()}
     if world > 1:
         t.enable_data_parallel()
+    if not args.no_graphs:
+        t.enable_cuda_graphs()
 
     def step(batch):
         t.update_G(batch)
@@ -317,7 +414,8 @@ def build_full(args, dev, rank, world, dtype):
                        "paths": {}} for dom, d in host.items()}]
 
     h2d = int(sum(v.numel() * v.element_size() for d in host.values() for v in d.values()))
-    return step, to_dev, h2d, FULL_STEP_GFLOP
+    step.trainer = t
+    return step, to_dev, h2d, FULL_STEP_GFLOP if args.workload == "full" else MASKER_STEP_GFLOP
 
 
 def build_infer(args, dev, rank, world, dtype):
@@ -352,6 +450,9 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
+    if args.impl == "gpu-eager":
+        run_gpu_eager(args)
+        return
 
     from climategan_b200 import _lib
 
@@ -362,6 +463,12 @@ def main():
     dev = torch.device("cuda", local)
     _lib.require_device()
     lib = _lib.lib()
+
+    # ---- PyTorch-eager-on-this-GPU bar (child processes, before our arm allocates; rank 0 at N=1 only)
+    eager = None
+    if world == 1 and not args.no_gpu_eager:
+        eager = gpu_eager_baseline(args)
+
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -369,11 +476,13 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
-    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    dtype = {"bf16": torch.bfloat16, "fp32": torch.float32, "fp16": torch.float16}[args.dtype]
     B = args.batch
 
-    builder = {"full": build_full, "painter": build_painter, "infer": build_infer}[args.workload]
+    builder = {"full": build_full, "masker": build_full, "painter": build_painter, "infer": build_infer}[args.workload]
     step, to_dev, h2d_bytes, gflop_per_image = builder(args, dev, rank, world, dtype)
+    trainer = getattr(step, "trainer", None)
+    graphs_on = trainer is not None and not args.no_graphs
     resident = to_dev(False)
 
     def barrier():
@@ -394,32 +503,20 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- warm-up (the last warm-up step runs with the per-launch event profiler on, so its event pool exists before timing)
     import ctypes as C
 
-    for i in range(args.warmup):
-        if i == args.warmup - 1:
-            lib.cgb_prof_enable(1)
+    # ---- warm-up: with graphs on, step 0 runs eagerly, step 1 captures + replays, later steps replay
+    warm = max(args.warmup, 3) if graphs_on else args.warmup
+    for _ in range(warm):
         step(*resident)
     barrier()
-    lib.cgb_prof_enable(0)
-    _scratch = C.create_string_buffer(1 << 22)
-    lib.cgb_prof_dump(_scratch, len(_scratch))   # discard the warm-up records (returns their events to the pool)
 
-    # ---- device-resident timed region (value), with clocks + per-launch conv timing
+    # ---- device-resident timed region (value), clocks sampled during it
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    lib.cgb_launch_count_reset()
-    lib.cgb_prof_enable(1)
     total_ms = timed(lambda: step(*resident), args.steps)
-    lib.cgb_prof_enable(0)
-    launches = int(lib.cgb_launch_count())
     clocks = sampler.stop() if rank == 0 else None
-    buf = C.create_string_buffer(1 << 22)
-    lib.cgb_prof_dump(buf, len(buf))
-    prof = [ln.split() for ln in buf.value.decode().strip().splitlines() if ln.strip()]
-
     ms_per_step = total_ms / args.steps
     value = world * B / (ms_per_step / 1e3)
 
@@ -438,12 +535,34 @@ def main():
         e2e = {"value": world * B / (e2e_ms / 1e3), "unit": "img/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
                "ms_per_step": e2e_ms}
 
+    # ---- ONE eager step bracketed launch by launch with CUDA events (outside the timed region): the per-class conv table and
+    #      the count of library launches a step consists of (what the graph replays)
+    if graphs_on:
+        trainer.enable_cuda_graphs(False)
+    step(*resident)
+    barrier()
+    lib.cgb_prof_enable(1)
+    step(*resident)                       # builds the event pool
+    barrier()
+    lib.cgb_prof_enable(0)
+    _scratch = C.create_string_buffer(1 << 22)
+    lib.cgb_prof_dump(_scratch, len(_scratch))
+    lib.cgb_launch_count_reset()
+    lib.cgb_prof_enable(1)
+    prof_ms = timed(lambda: step(*resident), 1)
+    lib.cgb_prof_enable(0)
+    launches_per_step = int(lib.cgb_launch_count())
+    buf = C.create_string_buffer(1 << 22)
+    lib.cgb_prof_dump(buf, len(buf))
+    prof = [ln.split() for ln in buf.value.decode().strip().splitlines() if ln.strip()]
+    eager_ms = timed(lambda: step(*resident), 2) / 2   # the eager (no graph, no per-launch events) step, for the record
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (largest share of conv time in the timed region)
+    # ---- rooflines
     peaks, peak_src = load_peaks()
     traffic = load_traffic()
     names = {0: "fwd", 1: "dgrad", 2: "wgrad"}
@@ -455,10 +574,9 @@ def main():
                          stride=stride, dil=dil, count=count, total_ms=tot))
     conv_ms = sum(r["total_ms"] for r in rows) or 1e-9
     rows.sort(key=lambda r: -r["total_ms"])
-    roofline = None
-    roofline_tensor = None
     tpeak = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
     hpeak = peaks["hbm_gbs"]
+    esz = 4 if args.dtype == "fp32" else 2
 
     def describe(r):
         """Roofline entry of one (op, shape) class.  The bound is decided by arithmetic intensity: algorithmic FLOPs
@@ -466,7 +584,6 @@ def main():
         machine ridge (measured bf16 peak / measured HBM bandwidth)."""
         avg_ms = r["total_ms"] / r["count"]
         flops = _logical_flops(r)
-        esz = 2 if args.dtype == "bf16" else 4
         px_in, px_out = r["n"] * r["hi"] * r["wi"], r["n"] * r["ho"] * r["wo"]
         wbytes = r["ci"] * r["co"] * r["k"] * r["k"] * esz
         if r["op"] == "wgrad":
@@ -477,8 +594,8 @@ def main():
         name = (f"conv {r['op']} [{r['engine']}] {r['ci']}->{r['co']} {r['k']}x{r['k']} s{r['stride']} d{r['dil']} "
                 f"@{r['hi']}x{r['wi']} n={r['n']}")
         tkey = f"{r['op']} {r['ci']}->{r['co']} k{r['k']} s{r['stride']} d{r['dil']} @{r['hi']}x{r['wi']} n={r['n']}"
-        common = {"kernel": name, "avg_launch_ms": avg_ms, "share_of_conv_time": r["total_ms"] / conv_ms,
-                  "conv_time_share_of_step": conv_ms / total_ms, "algorithmic_flops_per_launch": flops,
+        common = {"kernel": name, "avg_launch_ms": avg_ms, "launches_per_step": r["count"], "share_of_conv_time": r["total_ms"] / conv_ms,
+                  "share_of_step": r["total_ms"] / prof_ms, "algorithmic_flops_per_launch": flops,
                   "algorithmic_bytes_per_launch": byts, "traffic": traffic.get(tkey)}
         if flops / byts >= ridge:
             a = flops / (avg_ms * 1e-3) / 1e12
@@ -488,33 +605,56 @@ def main():
         return dict(bound="hbm", achieved=a, peak=hpeak, unit="GB/s", frac=a / hpeak,
                     peak_source=f"{peak_src} hbm_gbs", **common)
 
-    if rows:
-        roofline = describe(rows[0])  # the (op, shape) class with the largest share of the timed region
-        for r in rows:                # and the largest tensor-bound class, for the tensor-pipe figure
-            d = describe(r)
-            if d["bound"] == "tensor":
-                roofline_tensor = d
-                break
+    classes = [describe(r) for r in rows[:max(args.topk, 8)]]
     step_tflops = world * B * gflop_per_image * 1e9 / (ms_per_step * 1e-3) / 1e12
+    conv_flops = sum(_logical_flops(r) * r["count"] for r in rows)
+    conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12
+    roofline = None
+    if classes:
+        roofline = dict(classes[0])   # the (op, shape) class with the largest share of the step
+        roofline.update({
+            "note": "dominant = the conv class with the largest share of the step; no class exceeds a few % of it, so the step-level "
+                    "and conv-aggregate fractions below are the ones that describe the path",
+            "step_frac": step_tflops / (world * tpeak),
+            "step_tflops_algorithmic": step_tflops,
+            "conv_aggregate": {"tflops": conv_tflops, "frac": conv_tflops / tpeak, "conv_ms_per_step": conv_ms,
+                               "share_of_eager_profiled_step": conv_ms / prof_ms},
+            "top_classes": [{k: c[k] for k in ("kernel", "bound", "achieved", "unit", "frac", "avg_launch_ms", "launches_per_step",
+                                                "share_of_step")} for c in classes[:8]],
+        })
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported at N=1 only
-        rate, t, cores, sample = cpu_rate(args, 1 if args.workload == "full" else 2, 0 if args.workload == "full" else 1)
+        heavy = args.workload in ("full", "masker")
+        rate, t, cores, sample, cb = cpu_rate(args, 1 if heavy else 2, 1)
         cpu = {"value": rate, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample + f" ({t:.1f} s/step)"}
+
+    eager_line = None
+    if eager is not None:
+        best = max((v for v in eager.values() if "value" in v), key=lambda v: v["value"], default=None)
+        eager_line = {"value": best["value"] if best else None, "unit": "img/s", "dtype": best["dtype"] if best else None,
+                      "ms_per_step": best["ms_per_step"] if best else None, "batch": best["batch"] if best else None,
+                      "what": "the oracle port (plain PyTorch ops, reference layout) run by PyTorch eager on this B200 through "
+                              "ATen/cuDNN — the faster of fp32+TF32 and bf16 autocast; no Blackwell kernel ships in the reference",
+                      "modes": eager}
 
     line = {
         "metric": metric_name(args), "value": value, "unit": "img/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": workload_config(args),
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-        "roofline": roofline, "roofline_top_tensor_kernel": roofline_tensor, "cpu_baseline": cpu,
+        "config": {**workload_config(args), "execution": ("CUDA-graph replay of zero_grad+forward+backward per update; optimiser + "
+                                                          "all-reduce eager" if graphs_on else "eager")},
+        "clocks": clocks, "e2e": e2e,
+        "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+        "gpu_launches_note": "library kernel launches one step consists of (counted on an eager step); with graphs on, the timed "
+                             "region replays exactly these as graph nodes",
+        "roofline": roofline, "cpu_baseline": cpu, "gpu_eager_baseline": eager_line,
         "step_tflops_algorithmic": step_tflops,
         "step_frac_of_bf16_peak": step_tflops / (world * tpeak),
-        "conv_time_share_of_step": conv_ms / total_ms,
+        "eager_ms_per_step": eager_ms, "profiled_eager_ms_per_step": prof_ms,
         "top_kernels": [
             {"kernel": f"{r['op']}[{r['engine']}] {r['ci']}->{r['co']} k{r['k']} s{r['stride']} d{r['dil']} @{r['hi']}x{r['wi']}",
-             "count": r["count"], "total_ms": round(r["total_ms"], 3)} for r in rows[:int(os.environ.get("CGB_TOPK", "8"))]],
+             "count": r["count"], "total_ms": round(r["total_ms"], 3)} for r in rows[:args.topk]],
     }
     print(json.dumps(line), flush=True)
     if world > 1:

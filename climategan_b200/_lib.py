@@ -80,6 +80,8 @@ SIGNATURES = {
     "cgb_prof_dump": ([C.c_char_p, C.c_int64], C.c_int),
     "cgb_conv2d_uses_tcgen05": ([_DP, C.c_int], C.c_int),
     "cgb_conv2d_fwd": ([_DP, _P, _P, _P, _P, _P, _P], C.c_int),
+    "cgb_conv2d_stats_rows": ([], C.c_int32),
+    "cgb_conv2d_fwd_stats": ([_DP, _P, _P, _P, _P, _P, _P, _P], C.c_int),
     "cgb_conv2d_dgrad": ([_DP, _P, _P, _P, _I, _P, _P, _P], C.c_int),
     "cgb_conv2d_pack_dgrad_weight": ([_DP, _P, _P, _P], C.c_int),
     "cgb_pack_weight": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
@@ -94,6 +96,7 @@ SIGNATURES = {
     "cgb_avgpool3s2_fwd": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_avgpool3s2_bwd": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_const_target_loss": ([_P, _P, _P, _L, _I, _F, _F, _P], C.c_int),
+    "cgb_const_target_loss_dev": ([_P, _P, _P, _L, _I, _P, _F, _P], C.c_int),
     "cgb_l1_loss_storage": ([_P, _P, _P, _P, _I, _L, _F, _P], C.c_int),
     "cgb_vgg_preprocess_fwd": ([_P, _P, _P, _I, _I, _I, _P], C.c_int),
     "cgb_vgg_preprocess_bwd": ([_P, _P, _P, _I, _I, _I, _P], C.c_int),
@@ -112,6 +115,7 @@ SIGNATURES = {
     "cgb_bn_bwd_ws_doubles": ([_L, _I], C.c_int64),
     "cgb_bn_bwd_finalize": ([_P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P], C.c_int),
     "cgb_bn_train_fwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _F, _I, _F, _P], C.c_int),
+    "cgb_bn_train_fwd_partials": ([_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _F, _I, _F, _P], C.c_int),
     "cgb_bn_train_bwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P], C.c_int),
     "cgb_bn_update_running": ([_P, _P, _P, _P, _I, _L, _F, _F, _P], C.c_int),
     "cgb_maxpool3s2_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
@@ -123,6 +127,7 @@ SIGNATURES = {
     "cgb_channel_mean_bwd": ([_P, _P, _I, _L, _I, _I, _P], C.c_int),
     "cgb_broadcast_hw": ([_P, _P, _I, _I, _I, _I, _F, _P], C.c_int),
     "cgb_dropout": ([_P, _P, _I, _L, _F, C.c_uint64, _P], C.c_int),
+    "cgb_dropout_dev": ([_P, _P, _I, _L, _F, _P, _P], C.c_int),
     "cgb_softmax_nchw_fwd": ([_P, _P, _I, _I, _I, _P], C.c_int),
     "cgb_softmax_nchw_bwd": ([_P, _P, _P, _I, _I, _I, _P], C.c_int),
     "cgb_cross_entropy_nchw": ([_P, _P, _P, _P, _I, _I, _I, _P], C.c_int),

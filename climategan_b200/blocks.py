@@ -77,8 +77,8 @@ class Conv2dBlock(nn.Module):
             x = ops.reflect_pad(x, pad)
             pad, pad_mode = 0, _lib.PAD_ZERO
         if self.norm is not None:
-            y = ops.conv2d(x, w, b, None, stride=self.stride, dil=self.dilation, pad=pad, pad_mode=pad_mode)
-            y = ops.batchnorm_act(y, self.norm, None, self.act, self.slope)
+            y = ops.conv_bn_act(x, w, self.norm, b, stride=self.stride, dil=self.dilation, pad=pad, pad_mode=pad_mode,
+                                act=self.act, slope=self.slope)
             return y if residual is None else y + residual
         return ops.conv2d(x, w, b, residual, stride=self.stride, dil=self.dilation, pad=pad, pad_mode=pad_mode,
                           act=self.act, slope=self.slope)

@@ -85,7 +85,8 @@ int conv_simt_fwd(const cgb_conv_desc*, const void*, const void*, const float*, 
 int conv_simt_dgrad(const cgb_conv_desc*, const void*, const void*, int, const void*, void*, cudaStream_t);
 int conv_simt_wgrad(const cgb_conv_desc*, const void*, const void*, float*, float*, cudaStream_t);
 bool conv_tc_supported(const cgb_conv_desc*, int which);
-int conv_tc_fwd(const cgb_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t);
+int conv_tc_fwd(const cgb_conv_desc*, const void*, const void*, const float*, const void*, void*, cudaStream_t, float* stats_out = nullptr);
+int conv_tc_stats_rows();
 int conv_tc_dgrad(const cgb_conv_desc*, const void*, const void*, int, const void*, void*, cudaStream_t);
 int conv_tc_wgrad(const cgb_conv_desc*, const void*, const void*, float*, float*, cudaStream_t);
 int pack_dgrad_weight(const cgb_conv_desc*, const void*, void*, cudaStream_t);
@@ -165,6 +166,26 @@ extern "C" int cgb_conv2d_fwd(const cgb_conv_desc* d, const void* x, const void*
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope ps(d, 0, tc, st);
   return tc ? conv_tc_fwd(d, x, w, bias, residual, y, st) : conv_simt_fwd(d, x, w, bias, residual, y, st);
+}
+
+// conv + per-channel statistics of its output in one launch (tcgen05 engine only): see include/cgb200.h
+extern "C" int32_t cgb_conv2d_stats_rows(void) { return conv_tc_stats_rows(); }
+
+extern "C" int cgb_conv2d_fwd_stats(const cgb_conv_desc* d, const void* x, const void* w, const float* bias,
+                                    const void* residual, void* y, float* stats_partial, void* stream) {
+  CGB_CHECK_DEVICE();
+  int s = validate(d, "conv2d_fwd_stats");
+  if (s) return s;
+  CGB_REQUIRE(x && w && y && stats_partial, "conv2d_fwd_stats: null pointer");
+  CGB_REQUIRE(!(residual && d->act != CGB_ACT_NONE && !d->res_before_act),
+              "conv2d_fwd_stats: residual after an activation requires act=none");
+  if (d->engine == CGB_ENGINE_SIMT || !conv_tc_supported(d, 0)) {
+    set_error("conv2d_fwd_stats: the epilogue statistics exist in the tcgen05 engine only (check cgb_conv2d_uses_tcgen05)");
+    return CGB_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(d, 0, true, st);
+  return conv_tc_fwd(d, x, w, bias, residual, y, st, stats_partial);
 }
 
 extern "C" int cgb_conv2d_pack_dgrad_weight(const cgb_conv_desc* d, const void* w, void* wt, void* stream) {

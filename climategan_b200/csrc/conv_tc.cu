@@ -221,6 +221,10 @@ struct TcParams {
   // stride-s dgrad runs as s*s stride-1 sub-convolutions, one per output parity class.
   int ntaps;
   int out_stride, out_off_y, out_off_x, hfull, wfull;
+  // per-channel sum / sum of squares of the stored output, accumulated by the epilogue (train-mode BatchNorm statistics of a
+  // conv -> BN chain without a statistics pass over the tensor): a [2][cout_s] fp32 table in shared memory at byte offset
+  // stats_off from the 1024-aligned base, flushed once per CTA to stats_out[blockIdx.x][2][cout_s]
+  int stats, stats_off;
   short tap_dy[64], tap_dx[64], tap_w[64];
 };
 
@@ -294,12 +298,52 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const uint32_t (&r)
   }
 }
 
+// ---- BatchNorm statistics from the staging tile -------------------------------------------------------------------
+// After phase 1 the tile sits in shared memory exactly as it will be stored (bf16).  Lane = one 16-byte chunk column (8
+// channels), warp = a row subset: every LDS.128 of a warp reads 32 consecutive chunks of ONE row (conflict-free in both
+// staging layouts), so a thread owns its 8 channels for all its rows and no cross-lane reduction is needed; one shared
+// atomic per (thread, channel, moment) per tile folds the 16 warps into the CTA's table.  Rows outside the image / batch
+// and channels beyond cout_s are skipped.  The epilogue has slack for this on every BatchNorm'd conv of the path (its
+// tiles are MMA- or L2-bound), so the statistics cost no wall time.
+__device__ __forceinline__ void epilogue_stats(const TcParams& p, const uint8_t* staging_gen, bool tma, int ox0, int oy0, int n0,
+                                               int cn0, float* tab, int warp, int lane) {
+  const int ew = warp - 2;                 // 0..EPI_WARPS-1
+  const int nchunk8 = p.bn >> 3;           // 16-byte chunk columns in the tile (<= 32)
+  if (lane >= nchunk8) return;
+  const int ch = cn0 + lane * 8;
+  if (ch >= p.cout_s) return;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  for (int r = ew; r < 128; r += EPI_WARPS) {
+    const int tw2 = r & ((1 << p.tw_log) - 1);
+    const int th2 = (r >> p.tw_log) & ((1 << p.th_log) - 1);
+    const int tn2 = r >> (p.tw_log + p.th_log);
+    if (ox0 + tw2 >= p.wout || oy0 + th2 >= p.hout || n0 + tn2 >= p.n) continue;
+    const uint8_t* src = tma ? staging_gen + (size_t)(lane >> 3) * (128 * 128) + (size_t)r * 128 + (size_t)(((lane & 7) ^ (r & 7)) << 4)
+                             : staging_gen + (size_t)r * p.stage_pitch + (size_t)lane * 16;
+    const uint4 raw = *reinterpret_cast<const uint4*>(src);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      s[2 * i] += f.x; s[2 * i + 1] += f.y;
+      q[2 * i] = fmaf(f.x, f.x, q[2 * i]); q[2 * i + 1] = fmaf(f.y, f.y, q[2 * i + 1]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(tab + ch + j, s[j]);
+    atomicAdd(tab + p.cout_s + ch + j, q[j]);
+  }
+}
+
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_acc, uint8_t* staging_gen, int ox0, int oy0,
                                               int n0, int cn0, const float* __restrict__ bias,
                                               const __nv_bfloat16* __restrict__ residual,
                                               const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y,
                                               uint32_t tempty_bar, int warp, int lane, const CUtensorMap* tmY = nullptr,
-                                              uint32_t staging_u32 = 0) {
+                                              uint32_t staging_u32 = 0, float* stats_tab = nullptr) {
   const int q = warp & 3;              // TMEM lane quarter this warp may access
   const int half = (warp - 2) >> 2;    // EPI_PER_Q warps share a quarter: 16-column chunks interleaved among them
   const int row = q * 32 + lane;       // tile row == TMEM lane == pixel within the tile
@@ -346,9 +390,11 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
         if (cn0 + hb * 64 < p.cout_s) tma_store_4d(tmY, staging_u32 + (uint32_t)hb * (128u * 128u), cn0 + hb * 64, ox0, oy0, n0);
       tma_store_commit();
     }
+    if (stats_tab) epilogue_stats(p, staging_gen, true, ox0, oy0, n0, cn0, stats_tab, warp, lane);
     return;
   }
   epi_bar_sync();  // staging complete
+  if (stats_tab) epilogue_stats(p, staging_gen, false, ox0, oy0, n0, cn0, stats_tab, warp, lane);
   // phase 2: lanes cover (rows_per_iter x chunks_per_row) 16-byte chunks; the row/chunk split of a lane is fixed, so
   // the only per-iteration work is the pixel address.  Consecutive lanes write consecutive chunks of a pixel and then
   // the next pixel: full 32-byte sectors, no read-modify-write.
@@ -389,7 +435,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
-               const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y) {
+               const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y, float* __restrict__ stats_out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // 1024-B alignment for the 128B swizzle atoms
@@ -405,12 +451,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_ptr_addr = bar_base + 16u * (uint32_t)p.stages + 32u;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
   uint8_t* staging_gen = smem_raw + (staging - raw);
+  float* stats_tab = p.stats ? reinterpret_cast<float*>(smem_raw + (base - raw) + (uint32_t)p.stats_off) : nullptr;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int taps = p.ntaps;
   const int iters = taps * p.kblocks;
   const int tn_log = 7 - p.tw_log - p.th_log;
+  if (stats_tab)
+    for (int i = threadIdx.x; i < 2 * p.cout_s; i += TC_THREADS) stats_tab[i] = 0.f;   // visible after the __syncthreads below
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -514,9 +563,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t sb = (p.staging_bufs == 2) ? (uint32_t)(lt & 1) * staging_tile : 0u;
       epilogue_tile(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen + sb, tx << p.tw_log, ty << p.th_log, tn << tn_log,
                     nt * p.bn, bias, residual, mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr,
-                    staging + sb);
+                    staging + sb, stats_tab);
     }
     if (p.tma_store && threadIdx.x == 64) tma_store_wait_all();   // the issuing thread: every bulk store has completed
+    if (stats_tab) {   // flush the CTA's table: one plain store per entry (a CTA without tiles still writes its zeros)
+      epi_bar_sync();
+      float* out = stats_out + (size_t)blockIdx.x * 2 * p.cout_s;
+      for (int i = threadIdx.x - 64; i < 2 * p.cout_s; i += EPI_THREADS) out[i] = stats_tab[i];
+    }
   }
 
   tc_fence_before();
@@ -541,8 +595,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
-                  const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y) {
+               const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
+               const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y, float* __restrict__ stats_out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -560,6 +614,9 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_ptr_addr = w_bar + 8u;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
   uint8_t* staging_gen = smem_raw + (staging - raw);
+  float* stats_tab = p.stats ? reinterpret_cast<float*>(smem_raw + (base - raw) + (uint32_t)p.stats_off) : nullptr;
+  if (stats_tab)
+    for (int i = threadIdx.x; i < 2 * p.cout_s; i += TC_THREADS) stats_tab[i] = 0.f;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -665,9 +722,14 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(tfull_bar(buf), bph);
       tc_fence_after();
       epilogue_tile(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen, tx << 3, ty << 4, img, cn0, bias, residual,
-                    mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr, staging);
+                    mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr, staging, stats_tab);
     }
     if (p.tma_store && threadIdx.x == 64) tma_store_wait_all();
+    if (stats_tab) {
+      epi_bar_sync();
+      float* out = stats_out + (size_t)blockIdx.x * 2 * p.cout_s;
+      for (int i = threadIdx.x - 64; i < 2 * p.cout_s; i += EPI_THREADS) out[i] = stats_tab[i];
+    }
   }
 
   tc_fence_before();
@@ -804,10 +866,13 @@ struct TapTable {
 static int launch_stream(const void* in, const void* w, void* out, int n, int hin, int win, int cin_s, int hgrid, int wgrid,
                          int cout_s, int wtaps_total, const TapTable& tt, int in_stride, int out_stride, int out_off_y,
                          int out_off_x, int hfull, int wfull, int act, float slope, const float* bias,
-                         const void* residual, int dact, const void* mask_src, cudaStream_t st, int res_before_act = 0) {
+                         const void* residual, int dact, const void* mask_src, cudaStream_t st, int res_before_act = 0,
+                         float* stats_out = nullptr) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.res_before_act = res_before_act;
+  p.stats = stats_out ? 1 : 0;
+  const int stats_bytes = stats_out ? 2 * cout_s * 4 + 16 : 0;
   p.n = n; p.hout = hgrid; p.wout = wgrid; p.cout_s = cout_s; p.cin_s = cin_s;
   p.stride = in_stride;
   p.kblocks = (cin_s + 63) / 64;
@@ -834,10 +899,11 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
   while (cols < 2 * p.bn) cols <<= 1;
   p.tmem_cols = cols;
   const int stage_bytes = A_TILE_BYTES + p.bn * 128;
-  int stages = (int)((SMEM_LIMIT - 1024 - 256 - staging_bytes) / stage_bytes);
+  int stages = (int)((SMEM_LIMIT - 1024 - 256 - staging_bytes - stats_bytes) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
+  p.stats_off = stages * stage_bytes + staging_bytes + 16 * stages + 64;
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)cin_s, (cuuint64_t)win, (cuuint64_t)hin, (cuuint64_t)n};
@@ -866,10 +932,14 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
   std::call_once(attr_once, [] {
     cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
   });
-  const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 16 * stages + 48 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 16 * stages + 64 + stats_bytes + 1024;
+  if (smem > SMEM_LIMIT) {
+    set_error("tcgen05 engine: tile does not fit shared memory (bn=%d, stats=%d)", p.bn, p.stats);
+    return CGB_UNSUPPORTED;
+  }
   dim3 grid((unsigned)(p.total_tiles < num_sms() ? p.total_tiles : num_sms()));
   conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
-                                                 (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out);
+                                                 (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
   return after_launch("conv_tc");
 }
 
@@ -877,8 +947,9 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
 static int launch_fprop(const void* in, const void* w, void* out, int n, int hin, int win, int cin_s, int hout, int wout,
                         int cout_s, int kh, int kw, int stride, int dil, int pad_y, int pad_x, int act, float slope,
                         const float* bias, const void* residual, int dact, const void* mask_src, cudaStream_t st,
-                        int res_before_act = 0) {
+                        int res_before_act = 0, float* stats_out = nullptr) {
   const int taps = kh * kw;
+  const int stats_bytes = stats_out ? 2 * cout_s * 4 + 16 : 0;
   // ---- traffic estimate of the streaming configuration
   int s_tw_log, s_th_log;
   pick_tile(n, hout, wout, stride, &s_tw_log, &s_th_log);
@@ -901,7 +972,7 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
       int bn = ((cout_s + nt - 1) / nt + 15) / 16 * 16;
       if (bn > 256) continue;
       const size_t wb = (size_t)kblocks * taps * bn * 128;
-      const size_t fixed = wb + (size_t)staging_tile_bytes_for(bn, tma_store_ok(bn, nt, dact, mask_src)) + 1024 + 256;
+      const size_t fixed = wb + (size_t)staging_tile_bytes_for(bn, tma_store_ok(bn, nt, dact, mask_src)) + 1024 + 256 + stats_bytes;
       if (fixed + 2 * (size_t)a_stage > SMEM_LIMIT) continue;
       int stg = (int)((SMEM_LIMIT - fixed) / a_stage);
       if (stg > 6) stg = 6;
@@ -932,7 +1003,7 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
       tt.w[t] = (short)t;
     }
     return launch_stream(in, w, out, n, hin, win, cin_s, hout, wout, cout_s, taps, tt, stride, 1, 0, 0, hout, wout, act, slope,
-                         bias, residual, dact, mask_src, st, res_before_act);
+                         bias, residual, dact, mask_src, st, res_before_act, stats_out);
   }
 
   TcParams p;
@@ -943,6 +1014,7 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
   p.kblocks = kblocks;
   p.act = act; p.slope = slope; p.dact = dact;
   p.out_stride = 1; p.hfull = hout; p.wfull = wout;
+  p.stats = stats_out ? 1 : 0;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
     cudaFuncSetAttribute(conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
@@ -983,18 +1055,23 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (!encode_map(&tmY, out, 4, dims, strides, box, estr, "output")) return CGB_LAUNCH_FAILURE;
   }
-  const size_t smem = (size_t)p.kblocks * taps * p.bn * 128 + (size_t)p.stages * a_stage + staging_bytes + 16 * p.stages + 64 + 1024;
+  p.stats_off = (int)((size_t)p.kblocks * taps * p.bn * 128 + (size_t)p.stages * a_stage + staging_bytes + 16 * p.stages + 64);
+  const size_t smem = (size_t)p.stats_off + stats_bytes + 1024;
   int ctas = num_sms() / p.n_tiles * p.n_tiles;
   if (ctas > p.pix_tiles * p.n_tiles) ctas = p.pix_tiles * p.n_tiles;
   conv_tc_ws_kernel<<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
-                                                    (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out);
+                                                    (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
   return after_launch("conv_tc_ws");
 }
 
+// stats_out (optional): [conv_tc_stats_rows()][2][co] fp32, zeroed here; row b receives CTA b's per-channel sum / sum of
+// squares of the stored output (rows beyond the launch's grid stay zero), for cgb_bn_train_fwd_partials
+int conv_tc_stats_rows() { return num_sms(); }
 int conv_tc_fwd(const cgb_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
-                cudaStream_t st) {
+                cudaStream_t st, float* stats_out) {
+  if (stats_out) cudaMemsetAsync(stats_out, 0, sizeof(float) * (size_t)num_sms() * 2 * d->co, st);
   return launch_fprop(x, w, y, d->n, d->hi, d->wi, d->ci, d->ho, d->wo, d->co, d->kh, d->kw, d->stride, d->dil, d->pad,
-                      d->pad, d->act, d->slope, bias, residual, CGB_ACT_NONE, nullptr, st, d->res_before_act);
+                      d->pad, d->act, d->slope, bias, residual, CGB_ACT_NONE, nullptr, st, d->res_before_act, stats_out);
 }
 
 // wt: dgrad packing [ci][taps][co] with the taps reversed (cgb_conv2d_pack_dgrad_weight)

@@ -28,28 +28,36 @@ static inline int grid_for(long long work, int block = 256) {
     return CGB_BAD_ARG;                                 \
   }
 
-static inline int bn_chunks(long long npix) {
-  // measured: a 32-pixel floor (1184 CTAs on the 8x80x80 ResNet maps) and 4 pixels in flight per thread made these passes
-  // 10-40 % SLOWER (more per-CTA set-up and fp64 atomics than the extra parallelism buys) -- kept at a 256-pixel floor
-  long long want = 148 * 8;
-  long long maxc = (npix + 255) / 256;
-  if (want > maxc) want = maxc;
-  if (want < 1) want = 1;
-  return (int)want;
+// ---------------------------------------------------------------------------------------------------
+// Train-mode BatchNorm passes.  All three are FLAT grid-stride kernels over the tensor's 16-byte channel vectors with
+// BN_U vectors in flight per thread.  The grid is sized so that (gridDim * 256) is a multiple of cv = c/8: a thread then
+// meets the SAME 8 channels on every iteration and keeps their per-channel coefficients in registers.
+// (Round 1 walked 256-pixel chunks with one load in flight per thread: on the 8x80x80 ResNet maps that is 200 CTAs and
+// ~6 KB in flight per SM — latency-bound at 0.4 of the HBM roofline, profiles/r01_full_step_torch_profiler.txt.)
+constexpr int BN_U = 4;
+
+static inline long long gcd_ll(long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; }
+
+// CTAs for a flat pass over total_vec vectors, a multiple of cv / gcd(cv, 256) so that a thread's channel vector is fixed
+static inline int bn_grid(long long total_vec, int cv) {
+  long long g = (total_vec + 256LL * BN_U - 1) / (256LL * BN_U);
+  const long long cap = 148LL * 4;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  const long long m = cv / gcd_ll(cv, 256);
+  g = (g + m - 1) / m * m;
+  return (int)g;
 }
 
-// ---------------------------------------------------------------------------------------------------
-// BatchNorm2d (train mode) apply: y = act(x*A + B (+ residual)), A = rstd*w, B = b - mean*A  (per channel)
-// grid (chunks); a thread owns one 8-channel vector and walks its chunk's pixels.
+// y = act(x*A + B (+ residual)), A = rstd*w, B = b - mean*A  (per channel)
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ weight, const float* __restrict__ bias, const T* __restrict__ residual,
-                    T* __restrict__ y, long long npix, int c, int px_per_chunk, float neg) {
-  const int cv = c >> 3;
-  const int lanes = 256 / cv;
-  const int lane = threadIdx.x / cv, v = threadIdx.x - lane * cv;
-  if (lane >= lanes) return;
+                    T* __restrict__ y, long long total_vec, int cv, float neg) {
+  const long long stride = (long long)gridDim.x * 256;
+  const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int v = (int)(i0 % cv);
   float A[8], B[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -58,23 +66,20 @@ bn_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, con
     A[j] = rstd[ch] * w;
     B[j] = b - mean[ch] * A[j];
   }
-  const long long p0 = (long long)blockIdx.x * px_per_chunk;
-  const long long p1 = min(npix, p0 + px_per_chunk);
-  constexpr int U = 1;  // pixels in flight per thread (U = 4 measured slower, see bn_chunks)
-  for (long long p = p0 + lane; p < p1; p += (long long)lanes * U) {
-    float xv[U][8], r[U][8];
+  for (long long i = i0; i < total_vec; i += stride * BN_U) {
+    float xv[BN_U][8], r[BN_U][8];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long pp = p + (long long)u * lanes;
-      if (pp < p1) {
-        Vec8<T>::load(x + pp * c + v * 8, xv[u]);
-        if (residual) Vec8<T>::load(residual + pp * c + v * 8, r[u]);
+    for (int u = 0; u < BN_U; ++u) {
+      const long long k = i + u * stride;
+      if (k < total_vec) {
+        Vec8<T>::load(x + k * 8, xv[u]);
+        if (residual) Vec8<T>::load(residual + k * 8, r[u]);
       }
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long pp = p + (long long)u * lanes;
-      if (pp < p1) {
+    for (int u = 0; u < BN_U; ++u) {
+      const long long k = i + u * stride;
+      if (k < total_vec) {
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -82,71 +87,67 @@ bn_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, con
           if (residual) t += r[u][j];
           o[j] = t > 0.f ? t : t * neg;
         }
-        Vec8<T>::store(y + pp * c + v * 8, o);
+        Vec8<T>::store(y + k * 8, o);
       }
     }
   }
 }
 
-// backward part 1: gpre = gy * act'(y); per-chunk partial sums of gpre and gpre * xhat (no atomics: see in_stats_kernel)
+// backward part 1: gpre = gy * act'(y); per-CTA partial sums of gpre and gpre * xhat (shared-memory table, then one plain
+// store per (CTA, channel): no global atomics — the fp64 fold over CTAs is bn_bwd_reduce_kernel)
 template <typename T>
 __global__ void __launch_bounds__(256)
 bn_apply_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const T* __restrict__ y, const T* __restrict__ gy, T* __restrict__ gpre, float* __restrict__ partial,
-                    long long npix, int c, int px_per_chunk, float neg, int has_act) {
-  extern __shared__ float sm[];  // [256][16]
-  const int cv = c >> 3;
-  const int lanes = 256 / cv;
-  const int tid = threadIdx.x;
-  const int lane = tid / cv, v = tid - lane * cv;
-  if (lane < lanes) {
-    float rs[8], nm[8], s1[8], s2[8];
+                    long long total_vec, int cv, float neg, int has_act) {
+  extern __shared__ float sm[];  // [2][c]
+  const int c = cv * 8;
+  for (int i = threadIdx.x; i < 2 * c; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * 256;
+  const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int v = (int)(i0 % cv);
+  float rs[8], nm[8], s1[8], s2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      rs[j] = rstd[v * 8 + j];
-      nm[j] = -mean[v * 8 + j] * rs[j];
-      s1[j] = s2[j] = 0.f;
-    }
-    const long long p0 = (long long)blockIdx.x * px_per_chunk;
-    const long long p1 = min(npix, p0 + px_per_chunk);
-    for (long long p = p0 + lane; p < p1; p += lanes) {
-      float xv[8], g[8], o[8];
-      Vec8<T>::load(x + p * c + v * 8, xv);
-      Vec8<T>::load(gy + p * c + v * 8, g);
-      if (has_act) {
-        float yv[8];
-        Vec8<T>::load(y + p * c + v * 8, yv);
+  for (int j = 0; j < 8; ++j) {
+    rs[j] = rstd[v * 8 + j];
+    nm[j] = -mean[v * 8 + j] * rs[j];
+    s1[j] = s2[j] = 0.f;
+  }
+  for (long long i = i0; i < total_vec; i += stride * BN_U) {
+    float xv[BN_U][8], g[BN_U][8], yv[BN_U][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = yv[j] > 0.f ? g[j] : g[j] * neg;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = g[j];
+    for (int u = 0; u < BN_U; ++u) {
+      const long long k = i + u * stride;
+      if (k < total_vec) {
+        Vec8<T>::load(x + k * 8, xv[u]);
+        Vec8<T>::load(gy + k * 8, g[u]);
+        if (has_act) Vec8<T>::load(y + k * 8, yv[u]);
       }
+    }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s1[j] += o[j];
-        s2[j] = fmaf(o[j], fmaf(xv[j], rs[j], nm[j]), s2[j]);
+    for (int u = 0; u < BN_U; ++u) {
+      const long long k = i + u * stride;
+      if (k < total_vec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = (!has_act || yv[u][j] > 0.f) ? g[u][j] : g[u][j] * neg;
+          s1[j] += o[j];
+          s2[j] = fmaf(o[j], fmaf(xv[u][j], rs[j], nm[j]), s2[j]);
+        }
+        Vec8<T>::store(gpre + k * 8, o);
       }
-      Vec8<T>::store(gpre + p * c + v * 8, o);
     }
+  }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sm[tid * 16 + j] = s1[j];
-      sm[tid * 16 + 8 + j] = s2[j];
-    }
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sm[v * 8 + j], s1[j]);
+    atomicAdd(&sm[c + v * 8 + j], s2[j]);
   }
   __syncthreads();
   float* out = partial + (long long)blockIdx.x * 2 * c;
-  for (int i = tid; i < c; i += 256) {
-    const int vv = i >> 3, j = i & 7;
-    float S = 0.f, Q = 0.f;
-    for (int l = 0; l < lanes; ++l) {
-      S += sm[(l * cv + vv) * 16 + j];
-      Q += sm[(l * cv + vv) * 16 + 8 + j];
-    }
-    out[i] = S;
-    out[c + i] = Q;
-  }
+  for (int i = threadIdx.x; i < 2 * c; i += 256) out[i] = sm[i];
 }
 
 // sums[c][2] (fp64) = sum over chunks of the partials
@@ -178,48 +179,79 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bn_bwd_finalize_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
                        const float* __restrict__ weight, const double* __restrict__ sums, const T* __restrict__ gpre,
-                       T* __restrict__ gx, long long npix, int c, int px_per_chunk) {
-  const int cv = c >> 3;
-  const int lanes = 256 / cv;
-  const int lane = threadIdx.x / cv, v = threadIdx.x - lane * cv;
-  if (lane >= lanes) return;
-  const double inv = 1.0 / (double)npix;
+                       T* __restrict__ gx, long long total_vec, int cv, double inv_npix) {
+  const long long stride = (long long)gridDim.x * 256;
+  const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int v = (int)(i0 % cv);
   float A[8], B[8], Cc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int ch = v * 8 + j;
     const float w = weight ? weight[ch] : 1.f;
     const float rs = rstd[ch], mu = mean[ch];
-    const float m1 = (float)(sums[ch * 2 + 0] * inv);
-    const float m2 = (float)(sums[ch * 2 + 1] * inv);
+    const float m1 = (float)(sums[ch * 2 + 0] * inv_npix);
+    const float m2 = (float)(sums[ch * 2 + 1] * inv_npix);
     A[j] = w * rs;
     B[j] = -w * rs * rs * m2;
     Cc[j] = w * (rs * rs * m2 * mu - rs * m1);
   }
-  const long long p0 = (long long)blockIdx.x * px_per_chunk;
-  const long long p1 = min(npix, p0 + px_per_chunk);
-  constexpr int U = 1;
-  for (long long p = p0 + lane; p < p1; p += (long long)lanes * U) {
-    float xv[U][8], gv[U][8];
+  for (long long i = i0; i < total_vec; i += stride * BN_U) {
+    float xv[BN_U][8], gv[BN_U][8];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long pp = p + (long long)u * lanes;
-      if (pp < p1) {
-        Vec8<T>::load(x + pp * c + v * 8, xv[u]);
-        Vec8<T>::load(gpre + pp * c + v * 8, gv[u]);
+    for (int u = 0; u < BN_U; ++u) {
+      const long long k = i + u * stride;
+      if (k < total_vec) {
+        Vec8<T>::load(x + k * 8, xv[u]);
+        Vec8<T>::load(gpre + k * 8, gv[u]);
       }
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long pp = p + (long long)u * lanes;
-      if (pp < p1) {
+    for (int u = 0; u < BN_U; ++u) {
+      const long long k = i + u * stride;
+      if (k < total_vec) {
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], gv[u][j], fmaf(B[j], xv[u][j], Cc[j]));
-        Vec8<T>::store(gx + pp * c + v * 8, o);
+        Vec8<T>::store(gx + k * 8, o);
       }
     }
   }
+}
+
+// mean / rstd (and the running-statistics update) from per-CTA partial sums [rows][2][c] — the statistics a tcgen05 conv's
+// epilogue accumulated for its own output (cgb_conv2d_fwd_stats).  block (32 channels, 16 row groups), fp64 fold.
+__global__ void __launch_bounds__(512)
+bn_finalize_partials_kernel(const float* __restrict__ partial, int rows, int c, int c_logical, double inv_npix, double count,
+                            float eps, float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ rmean,
+                            float* __restrict__ rvar, float momentum, long long* __restrict__ num_batches_tracked) {
+  __shared__ double sS[16][33], sQ[16][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ch = blockIdx.x * 32 + tx;
+  double S = 0.0, Q = 0.0;
+  if (ch < c) {
+    for (int k = ty; k < rows; k += 16) {
+      S += (double)partial[(long long)k * 2 * c + ch];
+      Q += (double)partial[(long long)k * 2 * c + c + ch];
+    }
+  }
+  sS[ty][tx] = S;
+  sQ[ty][tx] = Q;
+  __syncthreads();
+  if (ty == 0 && ch < c) {
+#pragma unroll
+    for (int k = 1; k < 16; ++k) { S += sS[k][tx]; Q += sQ[k][tx]; }
+    const double m = S * inv_npix;
+    double var = Q * inv_npix - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[ch] = (float)m;
+    rstd[ch] = (float)(1.0 / sqrt(var + (double)eps));
+    if (rmean && ch < c_logical) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      rmean[ch] = (1.f - momentum) * rmean[ch] + momentum * (float)m;
+      rvar[ch] = (1.f - momentum) * rvar[ch] + momentum * (float)unbiased;
+    }
+  }
+  if (blockIdx.x == 0 && tx == 0 && ty == 0 && num_batches_tracked) num_batches_tracked[0] += 1;
 }
 
 // running_mean = (1-mom)*running_mean + mom*mean ; running_var likewise with the UNBIASED batch variance
@@ -448,7 +480,9 @@ __device__ __forceinline__ uint32_t hash32(uint64_t k) {
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long total_vec, float p, uint64_t seed) {
+dropout_kernel(const T* __restrict__ x, T* __restrict__ y, long long total_vec, float p, uint64_t seed,
+               const unsigned long long* __restrict__ seed_dev) {
+  if (seed_dev) seed = *seed_dev;   // this step's seed, read from device memory (captured CUDA graphs)
   const float scale = 1.f / (1.f - p);
   const uint32_t thr = (uint32_t)((double)p * 4294967296.0);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
@@ -831,22 +865,20 @@ extern "C" int cgb_bn_apply_fwd(const void* x, const float* mean, const float* r
                                 void* stream) {
   CGB_CHECK_DEVICE();
   CGB_REQUIRE(x && mean && rstd && y && npix > 0, "bn_apply_fwd: bad arguments");
-  REQ_C(c, "bn_apply_fwd");
   CGB_REQUIRE(act == CGB_ACT_NONE || act == CGB_ACT_RELU || act == CGB_ACT_LRELU, "bn_apply_fwd: act must be none/relu/lrelu");
+  REQ_C(c, "bn_apply_fwd");
   const float neg = act == CGB_ACT_NONE ? 1.f : (act == CGB_ACT_RELU ? 0.f : slope);
-  const int chunks = bn_chunks(npix);
-  const int ppc = (int)((npix + chunks - 1) / chunks);
-  const int grid = (int)((npix + ppc - 1) / ppc);
-  DISPATCH_T(dtype, bn_apply_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, mean, rstd, weight, bias,
-                                                                                  (const T*)residual, (T*)y, npix, c, ppc, neg);)
+  const int cv = c / 8;
+  const long long total = (long long)npix * cv;
+  DISPATCH_T(dtype, bn_apply_fwd_kernel<T><<<bn_grid(total, cv), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, mean, rstd, weight, bias, (const T*)residual, (T*)y, total, cv, neg);)
   return after_launch("bn_apply_fwd");
 }
 
 extern "C" int64_t cgb_bn_bwd_ws_doubles(int64_t npix, int32_t c) {
   if (npix <= 0 || c <= 0) return 0;
-  const int chunks = bn_chunks(npix);
-  const int ppc = (int)((npix + chunks - 1) / chunks);
-  return 2 * (int64_t)c + ((npix + ppc - 1) / ppc) * c;   // sums[c][2] doubles, then chunks * 2c fp32 partials
+  const int cv = c / 8;
+  return 2 * (int64_t)c + (int64_t)bn_grid((long long)npix * cv, cv) * c;   // sums[c][2] doubles, then grid * 2c fp32 partials
 }
 
 extern "C" int cgb_bn_apply_bwd(const void* x, const float* mean, const float* rstd, const void* y, const void* gy, void* gpre,
@@ -857,12 +889,12 @@ extern "C" int cgb_bn_apply_bwd(const void* x, const float* mean, const float* r
   REQ_C(c, "bn_apply_bwd");
   const float neg = act == CGB_ACT_NONE ? 1.f : (act == CGB_ACT_RELU ? 0.f : slope);
   cudaStream_t st = (cudaStream_t)stream;
-  const int chunks = bn_chunks(npix);
-  const int ppc = (int)((npix + chunks - 1) / chunks);
-  const int grid = (int)((npix + ppc - 1) / ppc);
+  const int cv = c / 8;
+  const long long total = (long long)npix * cv;
+  const int grid = bn_grid(total, cv);
   float* partial = reinterpret_cast<float*>(sums + 2 * (size_t)c);   // sums holds cgb_bn_bwd_ws_doubles(npix, c) doubles
-  DISPATCH_T(dtype, bn_apply_bwd_kernel<T><<<grid, 256, 256 * 16 * sizeof(float), st>>>(
-                        (const T*)x, mean, rstd, (const T*)y, (const T*)gy, (T*)gpre, partial, npix, c, ppc, neg,
+  DISPATCH_T(dtype, bn_apply_bwd_kernel<T><<<grid, 256, 2 * c * sizeof(float), st>>>(
+                        (const T*)x, mean, rstd, (const T*)y, (const T*)gy, (T*)gpre, partial, total, cv, neg,
                         act != CGB_ACT_NONE);)
   int s = after_launch("bn_apply_bwd");
   if (s) return s;
@@ -875,11 +907,10 @@ extern "C" int cgb_bn_bwd_finalize(const void* x, const float* mean, const float
   CGB_CHECK_DEVICE();
   CGB_REQUIRE(x && mean && rstd && sums && gpre && gx && npix > 0, "bn_bwd_finalize: bad arguments");
   REQ_C(c, "bn_bwd_finalize");
-  const int chunks = bn_chunks(npix);
-  const int ppc = (int)((npix + chunks - 1) / chunks);
-  const int grid = (int)((npix + ppc - 1) / ppc);
-  DISPATCH_T(dtype, bn_bwd_finalize_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, mean, rstd, weight, sums,
-                                                                                     (const T*)gpre, (T*)gx, npix, c, ppc);)
+  const int cv = c / 8;
+  const long long total = (long long)npix * cv;
+  DISPATCH_T(dtype, bn_bwd_finalize_kernel<T><<<bn_grid(total, cv), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, mean, rstd, weight, sums, (const T*)gpre, (T*)gx, total, cv, 1.0 / (double)npix);)
   return after_launch("bn_bwd_finalize");
 }
 
@@ -909,6 +940,25 @@ extern "C" int cgb_bn_train_fwd(const void* x, const float* weight, const float*
         mean, rstd, running_mean, running_var, c_logical, (double)npix, momentum, eps, (long long*)num_batches_tracked);
     if ((s = after_launch("bn_update_running"))) return s;
   }
+  return cgb_bn_apply_fwd(x, mean, rstd, weight, bias, residual, y, dtype, npix, c, act, slope, stream);
+}
+
+// Train-mode forward whose statistics were accumulated by the producing conv's epilogue (cgb_conv2d_fwd_stats):
+// partial [rows][2][c] fp32 -> mean / rstd (+ running statistics, num_batches_tracked) -> normalise/affine/residual/activation.
+// One pass over x instead of two.
+extern "C" int cgb_bn_train_fwd_partials(const void* x, const float* partial, int32_t rows, const float* weight, const float* bias,
+                                         const void* residual, void* y, float* mean, float* rstd, float* running_mean,
+                                         float* running_var, int64_t* num_batches_tracked, int32_t dtype, int64_t npix, int32_t c,
+                                         int32_t c_logical, float momentum, float eps, int32_t act, float slope, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && partial && y && mean && rstd && rows > 0 && npix > 0, "bn_train_fwd_partials: bad arguments");
+  REQ_C(c, "bn_train_fwd_partials");
+  const bool upd = running_mean && running_var;
+  bn_finalize_partials_kernel<<<(c + 31) / 32, dim3(32, 16), 0, (cudaStream_t)stream>>>(
+      partial, rows, c, c_logical, 1.0 / (double)npix, (double)npix, eps, mean, rstd, upd ? running_mean : nullptr,
+      upd ? running_var : nullptr, momentum, upd ? (long long*)num_batches_tracked : nullptr);
+  int s = after_launch("bn_finalize_partials");
+  if (s) return s;
   return cgb_bn_apply_fwd(x, mean, rstd, weight, bias, residual, y, dtype, npix, c, act, slope, stream);
 }
 
@@ -997,8 +1047,17 @@ extern "C" int cgb_dropout(const void* x, void* y, int32_t dtype, int64_t count,
   CGB_CHECK_DEVICE();
   CGB_REQUIRE(x && y && count % 8 == 0 && p >= 0.f && p < 1.f, "dropout: bad arguments");
   const long long total = count / 8;
-  DISPATCH_T(dtype, dropout_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total, p, seed);)
+  DISPATCH_T(dtype, dropout_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total, p, seed, nullptr);)
   return after_launch("dropout");
+}
+
+extern "C" int cgb_dropout_dev(const void* x, void* y, int32_t dtype, int64_t count, float p, const uint64_t* seed_dev, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y && seed_dev && count % 8 == 0 && p >= 0.f && p < 1.f, "dropout_dev: bad arguments");
+  const long long total = count / 8;
+  DISPATCH_T(dtype, dropout_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+                        (const T*)x, (T*)y, total, p, 0ULL, (const unsigned long long*)seed_dev);)
+  return after_launch("dropout_dev");
 }
 
 extern "C" int cgb_softmax_nchw_fwd(const float* x, float* y, int32_t n, int32_t c, int32_t hw, void* stream) {

@@ -554,7 +554,8 @@ avgpool3s2_kernel(const T* __restrict__ src, T* __restrict__ dst, long long tota
 // loss[0] += scale * sum(l_i), gx_i = scale * dl_i/dx_i   (scale = weight / count)
 __global__ void __launch_bounds__(256)
 const_target_loss_kernel(const float* __restrict__ x, float* __restrict__ loss, float* __restrict__ gx, long long count,
-                         int kind, float t, float scale) {
+                         int kind, float t, float scale, const float* __restrict__ t_dev) {
+  if (t_dev) t = *t_dev;   // the target lives in device memory (a captured CUDA graph reads this step's draw from there)
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
     const float v = x[i];
@@ -1774,8 +1775,17 @@ extern "C" int cgb_const_target_loss(const float* x, float* loss, float* gx, int
   CGB_CHECK_DEVICE();
   CGB_REQUIRE(x && loss, "const_target_loss: null pointer");
   CGB_REQUIRE(kind >= 0 && kind <= 4 && count > 0, "const_target_loss: bad kind %d or count", kind);
-  const_target_loss_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(x, loss, gx, count, kind, target, scale);
+  const_target_loss_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(x, loss, gx, count, kind, target, scale, nullptr);
   return after_launch("const_target_loss");
+}
+
+extern "C" int cgb_const_target_loss_dev(const float* x, float* loss, float* gx, int64_t count, int32_t kind,
+                                         const float* target_dev, float scale, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && loss && target_dev, "const_target_loss_dev: null pointer");
+  CGB_REQUIRE(kind >= 0 && kind <= 4 && count > 0, "const_target_loss_dev: bad kind %d or count", kind);
+  const_target_loss_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(x, loss, gx, count, kind, 0.f, scale, target_dev);
+  return after_launch("const_target_loss_dev");
 }
 
 extern "C" int cgb_l1_loss_storage(const void* a, const void* b, float* loss, void* ga, int32_t dtype, int64_t count,

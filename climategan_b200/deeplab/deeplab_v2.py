@@ -38,8 +38,7 @@ class _ASPPModule(nn.Module):
     def forward_storage(self, x):
         c = self.atrous_conv
         if self.training:
-            y = ops.conv2d(x, c.weight, None, dil=c.dilation[0], pad=c.padding[0])
-            return ops.batchnorm_act(y, self.bn, None, _lib.ACT_RELU)
+            return ops.conv_bn_act(x, c.weight, self.bn, dil=c.dilation[0], pad=c.padding[0], act=_lib.ACT_RELU)
         w, b = fold_bn(c, self.bn, x.dtype, cis=x.shape[-1])
         return ops.conv2d_infer(x, w, b, k=c.kernel_size[0], dil=c.dilation[0], pad=c.padding[0], act=_lib.ACT_RELU)
 
@@ -84,8 +83,7 @@ class ASPP(nn.Module):
             x5 = ops.batchnorm_act(x5, self.global_avg_pool[2], None, _lib.ACT_RELU)   # batch stats over N only (1x1 maps)
             x5 = ops.broadcast_hw(x5, h, w)                        # bilinear 1x1 -> h x w = broadcast (deeplab_v2.py:116)
             y = torch.cat((x1, x2, x3, x4, x5), dim=-1)
-            y = ops.conv2d(y, self.conv1.weight, None)
-            y = ops.batchnorm_act(y, self.bn1, None, _lib.ACT_RELU)
+            y = ops.conv_bn_act(y, self.conv1.weight, self.bn1, act=_lib.ACT_RELU)
             return ops.dropout(y, self.dropout.p, True)
         wg, bg = fold_bn(self.global_avg_pool[1], self.global_avg_pool[2], x.dtype, cis=g.shape[-1])
         x5 = ops.conv2d_infer(g, wg, bg, k=1, act=_lib.ACT_RELU)
@@ -132,8 +130,7 @@ class DeepLabV2Decoder(nn.Module):
         last = self.conv[c0 + 8]
         if self.training:
             for i in (c0, c0 + 4):
-                y = ops.conv2d(y, self.conv[i].weight, None, pad=1)
-                y = ops.batchnorm_act(y, self.conv[i + 1], None, _lib.ACT_RELU)
+                y = ops.conv_bn_act(y, self.conv[i].weight, self.conv[i + 1], pad=1, act=_lib.ACT_RELU)
                 y = ops.dropout(y, self.conv[i + 3].p, True)
             y = ops.conv2d(y, last.weight, last.bias)
         else:

@@ -16,8 +16,7 @@ def conv_bn(x, conv: nn.Conv2d, bn: nn.BatchNorm2d, act=_lib.ACT_NONE, residual=
     """act(bn(conv(x)) (+ residual)) — the unit every DeepLab-v3 block is made of."""
     k, s, d, p = conv.kernel_size[0], conv.stride[0], conv.dilation[0], conv.padding[0]
     if training:
-        y = ops.conv2d(x, conv.weight, conv.bias, stride=s, dil=d, pad=p)
-        return ops.batchnorm_act(y, bn, residual, act)
+        return ops.conv_bn_act(x, conv.weight, bn, conv.bias, residual, stride=s, dil=d, pad=p, act=act)
     w, b = fold_bn(conv, bn, x.dtype, cis=x.shape[-1])
     return ops.conv2d_infer(x, w, b, residual, k=k, stride=s, dil=d, pad=p, act=act, res_before_act=1)
 
@@ -104,7 +103,7 @@ class ResNet(nn.Module):
             return torch.nn.functional.pad(w2, (0, xc.shape[-1] - kk)).view(w.shape[0], xc.shape[-1], 1, 1)
 
         if t:
-            y = ops.batchnorm_act(ops.conv2d(xc, as_gemm(c1.weight), None), self.bn1, None, _lib.ACT_RELU)
+            y = ops.conv_bn_act(xc, as_gemm(c1.weight), self.bn1, act=_lib.ACT_RELU)
         else:
             scale = self.bn1.weight.detach() / torch.sqrt(self.bn1.running_var + self.bn1.eps)
             wp = ops.pack_weight(as_gemm(c1.weight.detach() * scale.view(-1, 1, 1, 1)), x.dtype, cis=xc.shape[-1])

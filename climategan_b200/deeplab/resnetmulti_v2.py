@@ -64,17 +64,14 @@ class Bottleneck(nn.Module):
 
     def _forward_train(self, x):
         """resnetmulti_v2.py:40-56 in train mode: BatchNorm uses BATCH statistics (only its affine parameters are frozen,
-        :16-18) and updates its running statistics; conv -> [stats pass] -> [normalise + ReLU (+ residual) pass]."""
-        out = ops.conv2d(x, self.conv1.weight, None, stride=self.stride)
-        out = ops.batchnorm_act(out, self.bn1, None, _lib.ACT_RELU)
-        out = ops.conv2d(out, self.conv2.weight, None, dil=self.dilation, pad=self.dilation)
-        out = ops.batchnorm_act(out, self.bn2, None, _lib.ACT_RELU)
-        out = ops.conv2d(out, self.conv3.weight, None)
+        :16-18) and updates its running statistics; the conv's epilogue accumulates the statistics of its own output, so each
+        conv -> BN -> ReLU is the conv launch + ONE normalise / ReLU (/ residual) pass (ops.conv_bn_act)."""
+        out = ops.conv_bn_act(x, self.conv1.weight, self.bn1, stride=self.stride, act=_lib.ACT_RELU)
+        out = ops.conv_bn_act(out, self.conv2.weight, self.bn2, dil=self.dilation, pad=self.dilation, act=_lib.ACT_RELU)
         residual = x
         if self.downsample is not None:
-            residual = ops.conv2d(x, self.downsample[0].weight, None, stride=self.downsample[0].stride[0])
-            residual = ops.batchnorm_act(residual, self.downsample[1], None, _lib.ACT_NONE)
-        return ops.batchnorm_act(out, self.bn3, residual, _lib.ACT_RELU)
+            residual = ops.conv_bn_act(x, self.downsample[0].weight, self.downsample[1], stride=self.downsample[0].stride[0])
+        return ops.conv_bn_act(out, self.conv3.weight, self.bn3, residual=residual, act=_lib.ACT_RELU)
 
 
 class ResNetMulti(nn.Module):
@@ -131,8 +128,7 @@ class ResNetMulti(nn.Module):
             return torch.nn.functional.pad(w2, (0, xc.shape[-1] - kk)).view(w.shape[0], xc.shape[-1], 1, 1)
 
         if self.training:
-            x = ops.conv2d(xc, as_gemm(c1.weight), None)
-            x = ops.batchnorm_act(x, self.bn1, None, _lib.ACT_RELU)
+            x = ops.conv_bn_act(xc, as_gemm(c1.weight), self.bn1, act=_lib.ACT_RELU)
         else:
             scale = self.bn1.weight.detach() / torch.sqrt(self.bn1.running_var + self.bn1.eps)
             w = as_gemm(c1.weight.detach() * scale.view(-1, 1, 1, 1))

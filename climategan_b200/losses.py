@@ -29,20 +29,31 @@ class GANLoss(nn.Module):
         soft_change = float(torch.FloatTensor(1).uniform_(0, self.soft_shift))  # same RNG draw as losses.py:57
         return float(self.real_label) - soft_change if target_is_real else float(self.fake_label) + soft_change
 
-    def __call__(self, input, target_is_real, *args, **kwargs):
+    def _draw_targets(self, n, target_is_real):
+        """The host draws of one call, in the reference's order (losses.py:59-83): one ``random()`` for the flip decision, then
+        per prediction the (cumulative) flip and one ``uniform_`` for the soft label."""
         r = rand()
-        if isinstance(input, list):
-            loss = 0
-            for pred_i in input:
-                if isinstance(pred_i, list):
-                    pred_i = pred_i[-1]
-                if r < self.flip_prob:
-                    target_is_real = not target_is_real
-                loss = loss + ops.const_target_loss(pred_i, self.kind, self.get_target_value(target_is_real))
-            return loss / len(input)
-        if r < self.flip_prob:
-            target_is_real = not target_is_real
-        return ops.const_target_loss(input, self.kind, self.get_target_value(target_is_real))
+        vals = []
+        for _ in range(n):
+            if r < self.flip_prob:
+                target_is_real = not target_is_real
+            vals.append(self.get_target_value(target_is_real))
+        return vals
+
+    def __call__(self, input, target_is_real, *args, **kwargs):
+        from . import graphs
+
+        preds = [p[-1] if isinstance(p, list) else p for p in input] if isinstance(input, list) else [input]
+        n = len(preds)
+        tape = graphs.current_tape()
+        if tape is None:
+            targets = self._draw_targets(n, target_is_real)
+        else:   # capturing a CUDA graph: the labels live in device memory and are re-drawn before every replay
+            targets = tape.floats(lambda: self._draw_targets(n, target_is_real), n)
+        loss = 0
+        for pred_i, t in zip(preds, targets):
+            loss = loss + ops.const_target_loss(pred_i, self.kind, t)
+        return loss / n if isinstance(input, list) else loss
 
 
 class HingeLoss(nn.Module):

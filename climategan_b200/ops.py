@@ -54,9 +54,9 @@ def _chk_storage(x: torch.Tensor, name: str = "x") -> None:
 # ------------------------------------------------------------------------------------------------
 # weight packing:  OIHW fp32  <->  [Os][kh*kw][Is] storage dtype
 # ------------------------------------------------------------------------------------------------
-# CGB_PACK_KERNEL=1: pack in one launch of cgb_pack_weight instead of three torch launches (written when the GPU budget of
-# round 1 was spent: bit-exactness against the torch path is tests/test_gpu_zz_new_kernels.py::test_pack_weight_kernel; off until run)
-_PACK_KERNEL = os.environ.get("CGB_PACK_KERNEL", "0") == "1"
+# Weights are packed in ONE launch of cgb_pack_weight (bit-exact against the three-launch torch path:
+# tests/test_gpu_zz_new_kernels.py::test_pack_weight_kernel, green on B200); CGB_PACK_KERNEL=0 restores the torch path.
+_PACK_KERNEL = os.environ.get("CGB_PACK_KERNEL", "1") == "1"
 
 
 def pack_weight(w: torch.Tensor, dtype: torch.dtype, cis: Optional[int] = None, cos: Optional[int] = None,
@@ -170,13 +170,36 @@ class ConvGeom:
                         self.pad_mode, _DT[dtype], self.act, self.slope, self.engine, self.res_before_act)
 
 
-def conv_fwd_raw(x, wp, bias, residual, g: ConvGeom):
+_STATS_ROWS = []
+
+
+def _stats_rows() -> int:
+    if not _STATS_ROWS:
+        _STATS_ROWS.append(int(_L().cgb_conv2d_stats_rows()))
+    return _STATS_ROWS[0]
+
+
+_EPI_STATS = os.environ.get("CGB_EPILOGUE_STATS", "1") == "1"   # 0: BatchNorm statistics by a separate pass (A/B switch)
+
+
+def conv_fwd_raw(x, wp, bias, residual, g: ConvGeom, want_stats: bool = False):
+    """want_stats: also return the per-CTA partial sums [rows, 2, co] of the output's per-channel sum / sum of squares when the
+    launch runs on the tcgen05 engine (cgb_conv2d_fwd_stats) — (y, partial) with partial None on the SIMT engine."""
     _chk_storage(x)
     n, hi, wi, ci = x.shape
     co = wp.shape[0]
     assert wp.shape[2] == ci and wp.shape[1] == g.kh * g.kw and wp.dtype == x.dtype, (wp.shape, x.shape)
     d = g.desc(n, hi, wi, ci, co, x.dtype)
     y = torch.empty((n, d.ho, d.wo, co), dtype=x.dtype, device=x.device)
+    if want_stats:
+        partial = None
+        if _EPI_STATS and _L().cgb_conv2d_uses_tcgen05(C.byref(d), 0):
+            partial = torch.empty((_stats_rows(), 2, co), dtype=torch.float32, device=x.device)
+            check(_L().cgb_conv2d_fwd_stats(C.byref(d), _p(x), _p(wp), _p(bias), _p(residual), _p(y), _p(partial), _st()),
+                  "conv2d_fwd_stats")
+            return y, partial
+        check(_L().cgb_conv2d_fwd(C.byref(d), _p(x), _p(wp), _p(bias), _p(residual), _p(y), _st()), "conv2d_fwd")
+        return y, partial
     check(_L().cgb_conv2d_fwd(C.byref(d), _p(x), _p(wp), _p(bias), _p(residual), _p(y), _st()), "conv2d_fwd")
     return y
 
@@ -271,20 +294,30 @@ class _Conv2d(Function):
     """y = act(conv(x, w) + b) (+ residual); w is OIHW fp32 (master / spectrally normalised)."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, residual, g: ConvGeom):
+    def forward(ctx, x, w, bias, residual, g: ConvGeom, want_stats=False):
         wp = pack_weight_cached(w, x.dtype, cis=x.shape[-1])
         bp = pad_bias(bias, wp.shape[0])
-        y = conv_fwd_raw(x, wp, bp, residual, g)
+        partial = None
+        if want_stats:
+            y, partial = conv_fwd_raw(x, wp, bp, residual, g, True)
+        else:
+            y = conv_fwd_raw(x, wp, bp, residual, g)
+        ctx.want_stats = want_stats
         ctx.g = g
         ctx.w_shape = tuple(w.shape)
         ctx.has_bias = bias is not None
         ctx.nb = 0 if bias is None else bias.numel()
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, wp, y if g.act != _lib.ACT_NONE else None)
+        if want_stats:
+            if partial is None:
+                partial = torch.empty(0, dtype=torch.float32, device=x.device)   # "no statistics": the SIMT engine ran
+            ctx.mark_non_differentiable(partial)
+            return y, partial
         return y
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, gpartial=None):
         x, wp, y = ctx.saved_tensors
         g = ctx.g
         gy = gy.contiguous()
@@ -298,13 +331,30 @@ class _Conv2d(Function):
             if ctx.has_bias:
                 gb = gbp if (gbp.numel() == ctx.nb and "viewgrad" not in _DBG) else gbp[: ctx.nb].clone()
         gres = gy if ctx.has_res else None
-        return gx, gw, gb, gres, None
+        return gx, gw, gb, gres, None, None
 
 
 def conv2d(x, w, bias=None, residual=None, *, stride=1, dil=1, pad=0, pad_mode=_lib.PAD_ZERO,
-           act=_lib.ACT_NONE, slope=0.2, engine=_lib.ENGINE_AUTO):
+           act=_lib.ACT_NONE, slope=0.2, engine=_lib.ENGINE_AUTO, want_stats=False):
+    """want_stats: returns (y, partial) — see :func:`conv_fwd_raw`; partial is None when the conv did not produce statistics."""
     g = ConvGeom(w.shape[2], w.shape[3], stride, dil, pad, pad_mode, act, slope, engine)
+    if want_stats:
+        y, partial = _Conv2d.apply(x, w, bias, residual, g, True)
+        return y, (partial if partial.numel() else None)
     return _Conv2d.apply(x, w, bias, residual, g)
+
+
+def conv_bn_act(x, w, bn, bias=None, residual=None, *, stride=1, dil=1, pad=0, pad_mode=_lib.PAD_ZERO, act=_lib.ACT_NONE,
+                slope=0.2):
+    """conv -> BatchNorm (+ residual) -> activation for an ``nn.BatchNorm2d`` container ``bn`` (resnetmulti_v2.py:40-56,
+    blocks.py:138-144): in train mode the batch statistics are accumulated by the conv's own epilogue, so the chain is the conv
+    launch, one tiny finalize and ONE pass over the conv output (normalise + affine + residual + activation)."""
+    batch_stats = bool(bn.training or bn.running_mean is None)
+    if batch_stats:
+        y, partial = conv2d(x, w, bias, None, stride=stride, dil=dil, pad=pad, pad_mode=pad_mode, want_stats=True)
+    else:
+        y, partial = conv2d(x, w, bias, None, stride=stride, dil=dil, pad=pad, pad_mode=pad_mode), None
+    return batchnorm_act(y, bn, residual, act, slope, partial=partial)
 
 
 class _Spade(Function):
@@ -347,9 +397,15 @@ class _Spade(Function):
 
         # gamma || beta as ONE conv with co = 2*cs (norms.py:180-182 share the input actv)
         def build_gb():
-            wp = torch.zeros(2 * cs, k * k, nh, dtype=dt, device=x.device)
-            wp[:c] = w_g.detach().permute(0, 2, 3, 1).reshape(c, k * k, nh)
-            wp[cs:cs + c] = w_b.detach().permute(0, 2, 3, 1).reshape(c, k * k, nh)
+            if _PACK_KERNEL and w_g.dtype == torch.float32:   # two launches: each half is a [cs][taps][nh] packing of its own
+                wp = torch.empty(2 * cs, k * k, nh, dtype=dt, device=x.device)
+                for half, wsrc in ((wp[:cs], w_g), (wp[cs:], w_b)):
+                    check(_L().cgb_pack_weight(_p(wsrc.detach().contiguous()), _p(half), _DT[dt], c, nh, k * k, cs, nh, _st()),
+                          "pack_weight")
+            else:
+                wp = torch.zeros(2 * cs, k * k, nh, dtype=dt, device=x.device)
+                wp[:c] = w_g.detach().permute(0, 2, 3, 1).reshape(c, k * k, nh)
+                wp[cs:cs + c] = w_b.detach().permute(0, 2, 3, 1).reshape(c, k * k, nh)
             bp = torch.zeros(2 * cs, dtype=torch.float32, device=x.device)
             bp[:c] = b_g.detach()
             bp[cs:cs + c] = b_b.detach()
@@ -753,8 +809,12 @@ class _ConstTargetLoss(Function):
         x = x.contiguous().float()
         loss = torch.zeros((), dtype=torch.float32, device=x.device)
         gx = torch.empty_like(x)
-        check(_L().cgb_const_target_loss(_p(x), _p(loss), _p(gx), x.numel(), kind, float(target), 1.0 / x.numel(), _st()),
-              "const_target_loss")
+        if isinstance(target, torch.Tensor):   # a device-resident target (graphs.StepTape slot)
+            check(_L().cgb_const_target_loss_dev(_p(x), _p(loss), _p(gx), x.numel(), kind, _p(target), 1.0 / x.numel(), _st()),
+                  "const_target_loss_dev")
+        else:
+            check(_L().cgb_const_target_loss(_p(x), _p(loss), _p(gx), x.numel(), kind, float(target), 1.0 / x.numel(), _st()),
+                  "const_target_loss")
         ctx.save_for_backward(gx)
         return loss
 
@@ -765,7 +825,8 @@ class _ConstTargetLoss(Function):
 
 
 def const_target_loss(x, kind, target=0.0):
-    """mean-reduced BCE-with-logits / MSE / hinge against a constant target (fp32 tensor of any shape)."""
+    """mean-reduced BCE-with-logits / MSE / hinge against a constant target (fp32 tensor of any shape); ``target`` is a float
+    or a 1-element fp32 device tensor read at execution time."""
     return _ConstTargetLoss.apply(x, kind, target)
 
 
@@ -1085,34 +1146,46 @@ def reflect_pad(x, pad):
     return x if pad == 0 else _ReflectPad.apply(x, pad)
 
 
+def _dropout_raw(x, p, seed):
+    y = torch.empty_like(x)
+    if isinstance(seed, torch.Tensor):   # device-resident seed (graphs.StepTape slot)
+        check(_L().cgb_dropout_dev(_p(x), _p(y), _DT[x.dtype], x.numel(), p, _p(seed), _st()), "dropout_dev")
+    else:
+        check(_L().cgb_dropout(_p(x), _p(y), _DT[x.dtype], x.numel(), p, seed, _st()), "dropout")
+    return y
+
+
 class _Dropout(Function):
     @staticmethod
     def forward(ctx, x, p, seed):
         _chk_storage(x)
-        y = torch.empty_like(x)
-        check(_L().cgb_dropout(_p(x), _p(y), _DT[x.dtype], x.numel(), p, seed, _st()), "dropout")
         ctx.meta = (p, seed)
-        return y
+        return _dropout_raw(x, p, seed)
 
     @staticmethod
     def backward(ctx, g):
         p, seed = ctx.meta
-        g = g.contiguous()
-        gx = torch.empty_like(g)
-        check(_L().cgb_dropout(_p(g), _p(gx), _DT[g.dtype], g.numel(), p, seed, _st()), "dropout_bwd")
-        return gx, None, None
+        return _dropout_raw(g.contiguous(), p, seed), None, None
 
 
 _dropout_calls = [0]
 
 
+def _draw_dropout_seed():
+    return [int(torch.randint(0, 2 ** 62, (1,)).item())]
+
+
 def dropout(x, p, training):
     """nn.Dropout(p) (deeplab_v2.py:106,148,152).  The keep-mask comes from a counter-based hash of (seed, element index);
-    the seed is drawn from torch's CPU generator so torch.manual_seed makes runs reproducible."""
+    the seed is drawn from torch's CPU generator so torch.manual_seed makes runs reproducible.  While a CUDA graph is being
+    captured the seed lives in device memory and is re-drawn, from the same generator, before every replay."""
     if not training or p == 0.0:
         return x
+    from . import graphs
+
     _dropout_calls[0] += 1
-    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    tape = graphs.current_tape()
+    seed = _draw_dropout_seed()[0] if tape is None else tape.ints(_draw_dropout_seed, 1)[0]
     return _Dropout.apply(x, float(p), seed)
 
 
@@ -1121,7 +1194,7 @@ class _BatchNormAct(Function):
     and one apply pass over x; the backward is two passes (see include/cgb200.h)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, running_mean, running_var, nbt, training, momentum, eps, act, slope):
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, nbt, training, momentum, eps, act, slope, partial=None):
         _chk_storage(x)
         n, h, w, cs = x.shape
         npix = n * h * w
@@ -1141,7 +1214,17 @@ class _BatchNormAct(Function):
         res = residual.contiguous() if residual is not None else None
         stats = torch.empty((2, cs), dtype=torch.float32, device=dev)
         mean, rstd = stats[0], stats[1]
-        if batch_stats:
+        if batch_stats and partial is not None:
+            # the statistics came out of the producing conv's epilogue: finalize + running update + ONE apply pass
+            assert partial.shape[-1] == cs and partial.dtype == torch.float32, (partial.shape, cs)
+            upd = running_mean is not None and training
+            if upd:
+                _BEPOCH[0] += 1
+            check(_L().cgb_bn_train_fwd_partials(_p(x), _p(partial), partial.shape[0], _p(wp), _p(bp), _p(res), _p(y), _p(mean),
+                                                 _p(rstd), _p(running_mean) if upd else None, _p(running_var) if upd else None,
+                                                 _p(nbt) if upd else None, _DT[x.dtype], npix, cs, c, float(momentum), float(eps),
+                                                 act, slope, _st()), "bn_train_fwd_partials")
+        elif batch_stats:
             ws = torch.empty((_stats_ws(1, npix, cs),), dtype=torch.float64, device=dev)
             upd = running_mean is not None and training
             if upd:
@@ -1191,16 +1274,16 @@ class _BatchNormAct(Function):
             sf = sums[:c].float()
             gw = sf[:, 1] if ctx.needs_input_grad[1] else None
             gb = sf[:, 0] if ctx.needs_input_grad[2] else None
-        return gx, gw, gb, (gpre if has_res else None), None, None, None, None, None, None, None, None
+        return gx, gw, gb, (gpre if has_res else None), None, None, None, None, None, None, None, None, None
 
 
-def batchnorm_act(x, bn, residual=None, act=_lib.ACT_NONE, slope=0.2):
+def batchnorm_act(x, bn, residual=None, act=_lib.ACT_NONE, slope=0.2, partial=None):
     """``act(bn(x) (+ residual))`` for an ``nn.BatchNorm2d`` parameter container ``bn`` (train: batch statistics + running
     update, exactly F.batch_norm's semantics; eval: running statistics)."""
     momentum = 0.1 if bn.momentum is None else bn.momentum
     nbt = bn.num_batches_tracked if (bn.training and bn.track_running_stats) else None   # incremented inside the kernel
     return _BatchNormAct.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, nbt, bn.training, momentum,
-                               bn.eps, act, slope)
+                               bn.eps, act, slope, partial)
 
 
 class _MakeMCond(Function):

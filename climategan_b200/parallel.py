@@ -23,6 +23,16 @@ def shard_batch(t: torch.Tensor, rank: int, world: int) -> torch.Tensor:
     return t[rank * per:(rank + 1) * per]
 
 
+def _allreduce_mean(flat: torch.Tensor, group, world: int) -> None:
+    """Mean over the ranks in ONE pass: NCCL averages inside the collective (ReduceOp.AVG); gloo (the CPU tests) has no AVG, so
+    it sums and scales."""
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.mul_(1.0 / world)
+
+
 class GradBucket:
     """Flat fp32 gradient bucket over a fixed parameter list.
 
@@ -57,8 +67,7 @@ class GradBucket:
                 v.zero_()
             else:
                 v.copy_(p.grad)
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        self.flat.mul_(1.0 / world)
+        _allreduce_mean(self.flat, self.group, world)
         for p, v in zip(self.params, self.views):
             if p.grad is None:
                 p.grad = v.clone()
@@ -77,7 +86,6 @@ def allreduce_flat_grads(optimizer, group: Optional[dist.ProcessGroup] = None) -
         return 0
     total = 0
     for flat in optimizer.flat_grads:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.mul_(1.0 / world)
+        _allreduce_mean(flat, group, world)
         total += flat.numel() * 4
     return total

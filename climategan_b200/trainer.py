@@ -93,6 +93,8 @@ class Trainer:
         self.kitti_pretrain = bool(opts.train.kitti.pretrain)   # trainer.py:101
         self.use_pl4m = False
         self.data_parallel = False
+        self._use_graphs = False
+        self._graphs, self._graph_seen, self._graph_pool = {}, {}, None
         self.pseudo_training_tasks = set(opts.train.pseudo.tasks or [])
         self.domain_labels = {"s": 0, "r": 1}
 
@@ -165,12 +167,58 @@ class Trainer:
 
             allreduce_flat_grads(opt, self._dp_group)
 
+    # ---------------------------------------------------------------- CUDA-graph replay of forward + backward
+    def enable_cuda_graphs(self, flag=True):
+        """Replay ``zero_grad`` + loss + ``backward`` of update_G / update_D from a captured CUDA graph (graphs.py): the first
+        call with a given batch signature runs eagerly (warm-up), the second captures, later ones replay.  The optimiser
+        update and the data-parallel all-reduce stay eager.  Numerically identical to the eager step — same kernels, same
+        order, and the host-side random draws (GANLoss labels, dropout seeds) are re-made before every replay in the eager
+        order (tests/test_gpu_graphs.py).  A graph is keyed on everything that shapes the step's control flow: the batch's
+        domains / tasks / shapes, pl4m, kitti pre-training, pseudo-label tasks, train / eval mode."""
+        self._use_graphs = bool(flag)
+        self._graphs, self._graph_seen = {}, {}
+        return self
+
+    def reset_graphs(self):
+        """Drop every captured graph (call after changing options that the captured control flow depends on)."""
+        self._graphs, self._graph_seen = {}, {}
+
+    def _fwd_bwd(self, kind, data):
+        """The captured region: data = {domain: {task: tensor}}."""
+        mdb = {dom: {"data": d, "domain": [dom] * next(iter(d.values())).shape[0]} for dom, d in data.items()}
+        if kind == "G":
+            self.g_opt.zero_grad()
+            loss = self.get_G_loss(mdb)
+        else:
+            self.d_opt.zero_grad()
+            loss = self.get_D_loss(mdb)
+        loss.backward()
+        return loss.detach()
+
+    def _loss_backward(self, kind, multi_domain_batch):
+        data = {dom: {k: v for k, v in b["data"].items() if isinstance(v, torch.Tensor)} for dom, b in multi_domain_batch.items()}
+        if not self._use_graphs:
+            return self._fwd_bwd(kind, data)
+        from . import graphs
+
+        key = (kind, graphs.tree_signature(data), self.use_pl4m, self.kitti_pretrain, tuple(sorted(self.pseudo_training_tasks)),
+               self.G.training, self.D.training if self.D is not None else None)
+        seen = self._graph_seen.get(key, 0)
+        self._graph_seen[key] = seen + 1
+        if seen == 0:
+            return self._fwd_bwd(kind, data)    # eager warm-up: lazy initialisation (flat buffers, kernel attributes) happens here
+        step = self._graphs.get(key)
+        if step is None:
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            step = self._graphs[key] = graphs.GraphedStep(lambda d, kind=kind: self._fwd_bwd(kind, d), data, self.device,
+                                                          pool=self._graph_pool)
+        return step(data)
+
     # ---------------------------------------------------------------- update steps
     def update_G(self, multi_domain_batch, verbose=0):
         self._set_requires_grad(self.D, False)   # run_epoch freezes D around update_G (trainer.py:960-962)
-        self.g_opt.zero_grad()
-        g_loss = self.get_G_loss(multi_domain_batch, verbose)
-        g_loss.backward()
+        g_loss = self._loss_backward("G", multi_domain_batch)
         self._sync_grads(self.g_opt)
         self.g_opt_step()
         self._set_requires_grad(self.D, True)    # trainer.py:971-973
@@ -180,9 +228,7 @@ class Trainer:
     def update_D(self, multi_domain_batch, verbose=0):
         if self.d_opt is None:   # run_epoch only calls update_D when there is a discriminator optimiser (trainer.py:971)
             return None
-        self.d_opt.zero_grad()
-        d_loss = self.get_D_loss(multi_domain_batch, verbose)
-        d_loss.backward()
+        d_loss = self._loss_backward("D", multi_domain_batch)
         self._sync_grads(self.d_opt)
         self.d_opt_step()
         self.logger.losses.disc.total_loss = d_loss.detach()

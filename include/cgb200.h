@@ -98,6 +98,16 @@ int cgb_conv2d_uses_tcgen05(const cgb_conv_desc* d, int which /*0 fwd, 1 dgrad, 
 int cgb_conv2d_fwd(const cgb_conv_desc* d, const void* x, const void* w, const float* bias,
                    const void* residual, void* y, void* stream);
 
+/* The same conv, with the per-channel statistics of ITS OWN OUTPUT accumulated by the kernel's epilogue — the conv -> BatchNorm
+ * chains of the masker in train mode (climategan/deeplab/resnetmulti_v2.py:40-56, deeplab_v2.py:23,100-104,146, depth.py:57-105;
+ * Conv2dBlock with norm="batch", blocks.py:138-144) need batch statistics of the conv output before they can normalise it; here
+ * they come out of the conv launch instead of a second pass over the tensor.  tcgen05 engine only (cgb_conv2d_uses_tcgen05).
+ *   stats_partial: [cgb_conv2d_stats_rows()][2][co] fp32 (zeroed by the call): row b = CTA b's sum and sum of squares of the
+ *   STORED (storage-dtype-rounded) output over the pixels it produced; feed it to cgb_bn_train_fwd_partials. */
+int32_t cgb_conv2d_stats_rows(void);
+int cgb_conv2d_fwd_stats(const cgb_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
+                         float* stats_partial, void* stream);
+
 /* Data gradient of the same conv (autograd of F.conv2d w.r.t. its input):
  *   gx = conv_transpose(gy, w)   [n,hi,wi,ci]
  * dact/mask_src (optional): multiply gx by the derivative of the activation that PRODUCED x,
@@ -239,6 +249,12 @@ int cgb_bn_train_fwd(const void* x, const float* weight, const float* bias, cons
 int cgb_bn_train_bwd(const void* x, const float* mean, const float* rstd, const float* weight, const void* y, const void* gy,
                      void* gpre, void* gx, double* sums, int32_t dtype, int64_t npix, int32_t c, int32_t act, float slope,
                      void* stream);
+/* cgb_bn_train_fwd without its statistics pass: mean / rstd (fp64 fold) and the running update come from the per-CTA partial
+ * sums [rows][2][c] a cgb_conv2d_fwd_stats launch left behind, then the same apply pass. */
+int cgb_bn_train_fwd_partials(const void* x, const float* partial, int32_t rows, const float* weight, const float* bias,
+                              const void* residual, void* y, float* mean, float* rstd, float* running_mean, float* running_var,
+                              int64_t* num_batches_tracked, int32_t dtype, int64_t npix, int32_t c, int32_t c_logical,
+                              float momentum, float eps, int32_t act, float slope, void* stream);
 /* adjoints of cgb_maxpool3s2_ceil_fwd (gradient to the first maximum of each window, as ATen), cgb_resize_bilinear_fwd,
  * cgb_channel_mean; nn.ReflectionPad2d (blocks.py:66-67) as an explicit copy + its fold-back adjoint so reflect-padded
  * convs run as pad-0 convs on the tcgen05 engine; dst[n,hw,c] = src[n,c]*scale (AdaptiveAvgPool2d(1) backward and the
@@ -261,6 +277,9 @@ int cgb_reflect_pad_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int3
 int cgb_channel_mean_bwd(const void* gy, void* gx, int32_t dtype, int64_t pixels, int32_t cs, int32_t c_logical, void* stream);
 int cgb_broadcast_hw(const void* src, void* dst, int32_t dtype, int32_t n, int32_t hw, int32_t c, float scale, void* stream);
 int cgb_dropout(const void* x, void* y, int32_t dtype, int64_t count, float p, uint64_t seed, void* stream);
+/* Same, the seed read from device memory at execution time: a launch captured in a CUDA graph draws a fresh mask on every
+ * replay (the host writes this step's seed — torch's CPU generator, as above — into *seed_dev before the replay). */
+int cgb_dropout_dev(const void* x, void* y, int32_t dtype, int64_t count, float p, const uint64_t* seed_dev, void* stream);
 
 /* ---- masker losses (NCHW fp32, the layout Trainer.masker_{d,s,m}_loss receive; trainer.py:1389-1616) --------------
  * Each *_loss entry ADDS the mean-reduced loss to the device scalar `loss` (caller zeroes) and writes the gradient of
@@ -397,6 +416,10 @@ int cgb_l1_loss(const float* a, const float* b, float* loss, float* ga, int64_t 
  *   loss[0] += scale*sum(l_i) ; gx_i = scale*dl_i/dx_i  (gx optional; scale = weight/count). */
 int cgb_const_target_loss(const float* x, float* loss, float* gx, int64_t count, int32_t kind, float target, float scale,
                           void* stream);
+/* Same, the target read from device memory at execution time (GANLoss's soft-label / flip draws, losses.py:52-70, change every
+ * step: a launch captured in a CUDA graph must not bake one draw in). */
+int cgb_const_target_loss_dev(const float* x, float* loss, float* gx, int64_t count, int32_t kind, const float* target_dev,
+                              float scale, void* stream);
 /* L1 between two storage tensors (FeatMatchLoss, losses.py:86-103): loss[0] += scale*sum|a-b| ; ga = scale*sign(a-b). */
 int cgb_l1_loss_storage(const void* a, const void* b, float* loss, void* ga, int32_t dtype, int64_t count, float scale,
                         void* stream);

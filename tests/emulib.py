@@ -311,6 +311,9 @@ class EmuLib(NoopLib):
         if G is not None:
             G.copy_(g * scale)
 
+    def e_const_target_loss_dev(self, x, loss, gx, count, kind, target_dev, scale, stream):
+        self.e_const_target_loss(x, loss, gx, count, kind, float(_t(target_dev, (1,), torch.float32)[0]), scale, stream)
+
     def e_l1_loss_storage(self, a, b, loss, ga, dtype, count, scale, stream):
         dt = _DT[dtype]
         d = _t(a, (count,), dt).float() - _t(b, (count,), dt).float()
@@ -506,6 +509,9 @@ class EmuLib(NoopLib):
         # parity fixtures run with p = 0); the same call on the gradient is the backward
         keep = torch.rand(count, generator=torch.Generator().manual_seed(int(seed) % (2 ** 63))) >= p
         _t(y, (count,), _DT[dtype]).copy_(X.float() * keep / (1 - p))
+
+    def e_dropout_dev(self, x, y, dtype, count, p, seed_dev, stream):
+        self.e_dropout(x, y, dtype, count, p, int(_t(seed_dev, (1,), torch.int64)[0]), stream)
 
     def e_im2col_strided(self, x, y, dtype, n, h, w, cs_in, c, k, pad, dil, stride, cs_out, stream):
         dt = _DT[dtype]

@@ -117,6 +117,11 @@ def test_infer_all_host_path(name, kw):
         assert {k: tuple(v.shape) for k, v in out.items()} == {k: (2, 3, 128, 128) for k in ("flood", "wildfire", "smog")}
         n1 = sum(lib.calls.values())
         t.infer_all(x, numpy=False, bin_value=0.5)
-        assert sum(lib.calls.values()) == 2 * n1        # the same work every call
+        n2 = sum(lib.calls.values()) - n1
+        t.infer_all(x, numpy=False, bin_value=0.5)
+        n3 = sum(lib.calls.values()) - n1 - n2
+        # the same work every call once the folded-BatchNorm packings are cached (the first call issues their cgb_pack_weight
+        # launches; spectrally-normalised weights are re-packed on every call because their power iteration moves them)
+        assert n2 == n3 and n2 <= n1 and lib.calls["cgb_pack_weight"] > 0
         out = t.infer_all(x, numpy=False, cloudy=True, ignore_event={"smog"})
         assert out["smog"] is None and out["flood"].shape == (2, 3, 128, 128)

@@ -1,0 +1,67 @@
+"""CUDA-graph replay of the train step (Trainer.enable_cuda_graphs) against the eager step on the GPU: same weights, same
+inputs, same host seeds, dropout and GANLoss label smoothing / flipping ON (the draws a capture must not bake in) — after four
+update_G + update_D iterations (eager warm-up, capture, two replays) the logged losses and the parameters agree to the noise of
+the atomically-ordered reductions.  The iterations alternate between two batches of the same signature, so equal losses also
+prove that a replay reads the batch it is given and draws fresh labels / dropout masks."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from tests.test_gpu_full_step import _build, _flatten
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(cuda, dtype, graphs_on, iters=4):
+    meta, g, t, mdb = _build(cuda, dtype)
+    for m in t.G.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.1
+    gan = t.losses["G"]["p"]["gan"]
+    gan.soft_shift, gan.flip_prob = 0.2, 0.3
+    # a vanishing learning rate keeps the weights (almost) fixed: the atomically-ordered weight-gradient reductions differ in the
+    # last bits from run to run, and Adam's sign-like first steps would amplify that into 1e-3-level loss differences by the third
+    # iteration — enough to hide a wrong dropout mask.  Spectral-norm u / v and the BatchNorm running statistics still evolve.
+    for opt in (t.g_opt, t.d_opt):
+        for grp in opt.param_groups:
+            grp["lr"] = 1e-12
+    random.seed(11)
+    torch.manual_seed(11)
+    if graphs_on:
+        t.enable_cuda_graphs()
+    # two batches of the same signature, alternated: a replay must read the batch it is given (static-buffer copy)
+    mdb2 = {dom: {**b, "data": {k: v.flip(0).contiguous() for k, v in b["data"].items()}} for dom, b in mdb.items()}
+    logs = []
+    for it in range(iters):
+        batch = mdb if it % 2 == 0 else mdb2
+        t.update_G(batch)
+        t.update_D(batch)
+        t.logger.global_step += 1
+        logs.append(_flatten(t.losses_to_host()))
+    torch.cuda.synchronize()
+    params = {k: v.detach().float().cpu().numpy().copy() for k, v in list(t.G.state_dict().items()) + list(t.D.state_dict().items())
+              if v.dtype.is_floating_point}
+    return logs, params, t
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_graph_replay_matches_eager_step(cuda, dtype):
+    logs_e, params_e, _ = _run(cuda, dtype, False)
+    logs_g, params_g, t = _run(cuda, dtype, True)
+    assert len(t._graphs) == 2 and all(s.replays == 3 for s in t._graphs.values()), {k[0]: s.replays for k, s in t._graphs.items()}
+    assert all(s.tape.n_draws > 0 for s in t._graphs.values())
+    ltol = 2e-4 if dtype == torch.float32 else 2e-2
+    for it, (le, lg) in enumerate(zip(logs_e, logs_g)):
+        assert sorted(le) == sorted(lg)
+        for k in le:
+            assert abs(le[k] - lg[k]) <= ltol * abs(le[k]) + 1e-5, (it, k, le[k], lg[k])
+    # label flipping changes the GAN loss by O(1) and a different dropout mask the segmentation losses by O(1e-2): equal losses
+    # above mean the replays drew the eager step's labels and masks.  State that evolves outside the optimiser (spectral-norm
+    # u / v, BatchNorm running statistics) must agree too:
+    worst = 0.0
+    for k, a in params_e.items():
+        b = params_g[k]
+        worst = max(worst, float(np.abs(a - b).max() / max(np.abs(a).max(), 1e-12)))
+    assert worst < (1e-4 if dtype == torch.float32 else 2e-2), worst
