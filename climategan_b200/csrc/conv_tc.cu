@@ -301,20 +301,41 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const uint32_t (&r)
 // ---- BatchNorm statistics from the staging tile -------------------------------------------------------------------
 // After phase 1 the tile sits in shared memory exactly as it will be stored (bf16).  Lane = one 16-byte chunk column (8
 // channels), warp = a row subset: every LDS.128 of a warp reads 32 consecutive chunks of ONE row (conflict-free in both
-// staging layouts), so a thread owns its 8 channels for all its rows and no cross-lane reduction is needed; one shared
-// atomic per (thread, channel, moment) per tile folds the 16 warps into the CTA's table.  Rows outside the image / batch
-// and channels beyond cout_s are skipped.  The epilogue has slack for this on every BatchNorm'd conv of the path (its
-// tiles are MMA- or L2-bound), so the statistics cost no wall time.
+// staging layouts), so a thread owns its 8 channels for all its rows and no cross-lane reduction is needed.  The 16 running
+// sums live in REGISTERS across the CTA's tiles (a persistent CTA keeps meeting the same N tile: n_tiles divides the grid
+// for every BatchNorm'd conv of the path) and are folded into the CTA's shared-memory table only when the channel window
+// moves and once at the end.  The table is laid out [moment][channel % 8][channel / 8], so the 32 lanes of a fold hit 32
+// consecutive words.  (First version: 16 shared atomics per thread per tile at a stride of 8 words — an 8-way bank conflict
+// times 16 warps; it cost 30 us per conv, more than the statistics pass it replaced.)
+struct EpiStats {
+  float s[8], q[8];
+  int ch;   // first channel of the window the sums belong to, -1: none
+};
+
+__device__ __forceinline__ void epi_stats_flush(const TcParams& p, EpiStats& st, float* tab) {
+  if (st.ch >= 0) {
+    const int c8 = p.cout_s >> 3, v = st.ch >> 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(tab + j * c8 + v, st.s[j]);
+      atomicAdd(tab + p.cout_s + j * c8 + v, st.q[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) st.s[j] = st.q[j] = 0.f;
+  st.ch = -1;
+}
+
 __device__ __forceinline__ void epilogue_stats(const TcParams& p, const uint8_t* staging_gen, bool tma, int ox0, int oy0, int n0,
-                                               int cn0, float* tab, int warp, int lane) {
+                                               int cn0, float* tab, EpiStats& st, int warp, int lane) {
   const int ew = warp - 2;                 // 0..EPI_WARPS-1
   const int nchunk8 = p.bn >> 3;           // 16-byte chunk columns in the tile (<= 32)
-  if (lane >= nchunk8) return;
   const int ch = cn0 + lane * 8;
-  if (ch >= p.cout_s) return;
-  float s[8], q[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (lane >= nchunk8 || ch >= p.cout_s) return;
+  if (ch != st.ch) {
+    epi_stats_flush(p, st, tab);
+    st.ch = ch;
+  }
   for (int r = ew; r < 128; r += EPI_WARPS) {
     const int tw2 = r & ((1 << p.tw_log) - 1);
     const int th2 = (r >> p.tw_log) & ((1 << p.th_log) - 1);
@@ -327,14 +348,9 @@ __device__ __forceinline__ void epilogue_stats(const TcParams& p, const uint8_t*
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float2 f = __bfloat1622float2(h[i]);
-      s[2 * i] += f.x; s[2 * i + 1] += f.y;
-      q[2 * i] = fmaf(f.x, f.x, q[2 * i]); q[2 * i + 1] = fmaf(f.y, f.y, q[2 * i + 1]);
+      st.s[2 * i] += f.x; st.s[2 * i + 1] += f.y;
+      st.q[2 * i] = fmaf(f.x, f.x, st.q[2 * i]); st.q[2 * i + 1] = fmaf(f.y, f.y, st.q[2 * i + 1]);
     }
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(tab + ch + j, s[j]);
-    atomicAdd(tab + p.cout_s + ch + j, q[j]);
   }
 }
 
@@ -343,7 +359,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
                                               const __nv_bfloat16* __restrict__ residual,
                                               const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y,
                                               uint32_t tempty_bar, int warp, int lane, const CUtensorMap* tmY = nullptr,
-                                              uint32_t staging_u32 = 0, float* stats_tab = nullptr) {
+                                              uint32_t staging_u32 = 0, float* stats_tab = nullptr, EpiStats* est = nullptr) {
   const int q = warp & 3;              // TMEM lane quarter this warp may access
   const int half = (warp - 2) >> 2;    // EPI_PER_Q warps share a quarter: 16-column chunks interleaved among them
   const int row = q * 32 + lane;       // tile row == TMEM lane == pixel within the tile
@@ -390,11 +406,11 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
         if (cn0 + hb * 64 < p.cout_s) tma_store_4d(tmY, staging_u32 + (uint32_t)hb * (128u * 128u), cn0 + hb * 64, ox0, oy0, n0);
       tma_store_commit();
     }
-    if (stats_tab) epilogue_stats(p, staging_gen, true, ox0, oy0, n0, cn0, stats_tab, warp, lane);
+    if (stats_tab) epilogue_stats(p, staging_gen, true, ox0, oy0, n0, cn0, stats_tab, *est, warp, lane);
     return;
   }
   epi_bar_sync();  // staging complete
-  if (stats_tab) epilogue_stats(p, staging_gen, false, ox0, oy0, n0, cn0, stats_tab, warp, lane);
+  if (stats_tab) epilogue_stats(p, staging_gen, false, ox0, oy0, n0, cn0, stats_tab, *est, warp, lane);
   // phase 2: lanes cover (rows_per_iter x chunks_per_row) 16-byte chunks; the row/chunk split of a lane is fixed, so
   // the only per-iteration work is the pixel address.  Consecutive lanes write consecutive chunks of a pixel and then
   // the next pixel: full 32-byte sectors, no read-modify-write.
@@ -549,6 +565,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ================= epilogue warps =================
+    EpiStats est;
+    est.ch = -1;
+    epi_stats_flush(p, est, stats_tab);   // (zeroes the registers)
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -563,13 +582,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t sb = (p.staging_bufs == 2) ? (uint32_t)(lt & 1) * staging_tile : 0u;
       epilogue_tile(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen + sb, tx << p.tw_log, ty << p.th_log, tn << tn_log,
                     nt * p.bn, bias, residual, mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr,
-                    staging + sb, stats_tab);
+                    staging + sb, stats_tab, &est);
     }
     if (p.tma_store && threadIdx.x == 64) tma_store_wait_all();   // the issuing thread: every bulk store has completed
-    if (stats_tab) {   // flush the CTA's table: one plain store per entry (a CTA without tiles still writes its zeros)
+    if (stats_tab) {   // fold the registers, then write the CTA's table: one plain store per entry (a CTA without tiles writes zeros)
+      epi_stats_flush(p, est, stats_tab);
       epi_bar_sync();
       float* out = stats_out + (size_t)blockIdx.x * 2 * p.cout_s;
-      for (int i = threadIdx.x - 64; i < 2 * p.cout_s; i += EPI_THREADS) out[i] = stats_tab[i];
+      const int c8 = p.cout_s >> 3;
+      for (int i = threadIdx.x - 64; i < 2 * p.cout_s; i += EPI_THREADS) {
+        const int m = i >= p.cout_s ? 1 : 0, c = i - m * p.cout_s;
+        out[i] = stats_tab[m * p.cout_s + (c & 7) * c8 + (c >> 3)];
+      }
     }
   }
 
@@ -712,6 +736,9 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
+    EpiStats est;
+    est.ch = -1;
+    epi_stats_flush(p, est, stats_tab);
     int lt = 0;
     for (int pt = pt0; pt < p.pix_tiles; pt += pt_step, ++lt) {
       const int buf = lt & 1;
@@ -722,13 +749,18 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(tfull_bar(buf), bph);
       tc_fence_after();
       epilogue_tile(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen, tx << 3, ty << 4, img, cn0, bias, residual,
-                    mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr, staging, stats_tab);
+                    mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr, staging, stats_tab, &est);
     }
     if (p.tma_store && threadIdx.x == 64) tma_store_wait_all();
     if (stats_tab) {
+      epi_stats_flush(p, est, stats_tab);
       epi_bar_sync();
       float* out = stats_out + (size_t)blockIdx.x * 2 * p.cout_s;
-      for (int i = threadIdx.x - 64; i < 2 * p.cout_s; i += EPI_THREADS) out[i] = stats_tab[i];
+      const int c8 = p.cout_s >> 3;
+      for (int i = threadIdx.x - 64; i < 2 * p.cout_s; i += EPI_THREADS) {
+        const int m = i >= p.cout_s ? 1 : 0, c = i - m * p.cout_s;
+        out[i] = stats_tab[m * p.cout_s + (c & 7) * c8 + (c >> 3)];
+      }
     }
   }
 

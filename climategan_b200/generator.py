@@ -17,8 +17,22 @@ from .painter import create_painter
 
 def create_generator(opts, device="cuda", latent_shape=None, no_init=False, verbose=0,
                      storage_dtype: torch.dtype = torch.bfloat16):
-    """generator.py:24-61 (the painter needs no init_weights pass in the reference either)."""
+    """generator.py:24-61: every decoder except the segmentation one, and a "base" encoder, get ``init_weights`` with their
+    ``opts.gen[model].init_type / init_gain`` unless ``no_init`` (the painter and the DeepLab encoders keep their constructors'
+    initialisation, as in the reference)."""
     G = OmniGenerator(opts, latent_shape, verbose, no_init, storage_dtype=storage_dtype)
+    if no_init:
+        return G.to(device)
+    from .discriminator import init_weights
+
+    for model in G.decoders:
+        if model == "s":
+            continue
+        init_weights(G.decoders[model], init_type=opts.gen[model].init_type, init_gain=opts.gen[model].init_gain, verbose=verbose,
+                     caller=f"create_generator decoder {model}")
+    if G.encoder is not None and opts.gen.encoder.architecture == "base":
+        init_weights(G.encoder, init_type=opts.gen.encoder.init_type, init_gain=opts.gen.encoder.init_gain, verbose=verbose,
+                     caller="create_generator encoder")
     return G.to(device)
 
 
@@ -134,9 +148,18 @@ class OmniGenerator(nn.Module):
         assert x is not None or z is not None
         if z is None:
             z = self.encode(x)
+        if cond is None and self.opts.gen.m.use_spade:
+            # generator.py:257-262: the SPADE mask decoder's conditioning is built here, un-taped, from the depth and
+            # segmentation predictions (x is needed when cond_nc == 15: make_m_cond raises otherwise, as the reference does)
+            assert "s" in self.opts.tasks and "d" in self.opts.tasks
+            with torch.no_grad():
+                d_pred, z_d = self.decode_d(z)
+                s_pred = self.decode_s(z, z_d)
+                cond = self.make_m_cond(d_pred, s_pred, x)
         with self._grad_ctx():
             if z_depth is None and self.opts.gen.m.use_dada:
-                _, z_depth = self.decoders["d"].forward_storage(z)
+                with torch.no_grad():                                    # generator.py:263-266
+                    _, z_depth = self.decoders["d"].forward_storage(z)
             logits = self.decoders["m"].forward_storage(z, cond, z_depth)
             if sigmoid:
                 logits = ops.activation(logits, _lib.ACT_SIGMOID)

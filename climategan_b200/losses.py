@@ -141,13 +141,57 @@ class VGGLoss(nn.Module):
     ``forward(x, y, mask=None)`` takes the NCHW fp32 images *before* ``vgg_preprocess`` (the preprocess and the
     optional ``* m`` of trainer.py:1281-1283 run inside one kernel)."""
 
-    def __init__(self, device=None, storage_dtype=torch.bfloat16):
+    def __init__(self, device=None, storage_dtype=torch.bfloat16, weights=None):
+        """``weights``: a path to (or a state_dict of) torchvision's ``vgg19`` ImageNet weights — ``features.N.weight`` keys, as
+        ``torchvision.models.vgg19(pretrained=True)`` saves them, or this module's own ``sliceK.N.weight`` keys.  The reference
+        downloads them (losses.py:307); this package never touches the network, so WITHOUT ``weights`` (or the environment
+        variable ``CGB_VGG19_WEIGHTS``, or an installed torchvision checkpoint in the torch hub cache) the features are those of
+        a randomly initialised VGG and a loud warning says so — load real weights with :meth:`load_vgg19_weights` before
+        training for real."""
         super().__init__()
+        import os
+
         self.vgg = Vgg19(storage_dtype=storage_dtype).eval()
+        self.pretrained = False
+        weights = weights or os.environ.get("CGB_VGG19_WEIGHTS")
+        if weights is None:
+            hub = os.path.join(os.path.expanduser(os.environ.get("TORCH_HOME", "~/.cache/torch")), "hub", "checkpoints")
+            if os.path.isdir(hub):
+                cands = sorted(f for f in os.listdir(hub) if f.startswith("vgg19-") and f.endswith(".pth"))
+                weights = os.path.join(hub, cands[-1]) if cands else None
+        if weights is not None:
+            self.load_vgg19_weights(weights)
+        else:
+            import warnings
+
+            warnings.warn("VGGLoss: no ImageNet VGG19 weights were given (weights=..., CGB_VGG19_WEIGHTS, or torch hub cache): the "
+                          "perceptual loss runs on a RANDOMLY INITIALISED VGG19. Fine for benchmarks and parity tests, wrong for "
+                          "training (the reference uses torchvision's pretrained vgg19, losses.py:307).", stacklevel=2)
         if device is not None:
             self.vgg.to(device)
         self.weights = [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]
         self.channels = [64, 128, 256, 512, 512]
+
+    def load_vgg19_weights(self, weights):
+        """Load torchvision vgg19 weights (``features.N.*`` keys) or this module's ``sliceK.N.*`` keys."""
+        sd = torch.load(weights, map_location="cpu") if isinstance(weights, (str, bytes)) or hasattr(weights, "__fspath__") else weights
+        own = self.vgg.state_dict()
+        idx_to_key = {k.split(".")[1]: k.rsplit(".", 1)[0] for k in own}     # "0" -> "slice1.0"
+        mapped = {}
+        for k, v in sd.items():
+            if k in own:
+                mapped[k] = v
+            elif k.startswith("features."):
+                _, idx, leaf = k.split(".")
+                if idx in idx_to_key:
+                    mapped[f"{idx_to_key[idx]}.{leaf}"] = v
+        missing = sorted(set(own) - set(mapped))
+        if missing:
+            raise KeyError(f"VGG19 weights: {len(missing)} tensors missing, e.g. {missing[:3]}")
+        self.vgg.load_state_dict(mapped, strict=True)
+        self.pretrained = True
+        ops.invalidate_weight_cache()
+        return self
 
     def forward(self, x, y, mask=None):
         dt = self.vgg.storage_dtype

@@ -686,7 +686,7 @@ class Trainer:
                 z = self.G.encode(x)
             if "d" in self.opts.tasks and self.opts.gen.m.use_dada and z_depth is None:
                 _, z_depth = self.G.decode_d(z)
-            m = self.G.mask(x=None, z=z, z_depth=z_depth)
+            m = self.G.mask(x=x, z=z, z_depth=z_depth)     # trainer.py:1866 passes x: the SPADE masker's conditioning needs it
         if bin_value >= 0:
             m = (m > bin_value).to(m.dtype)
         with torch.no_grad():
@@ -790,12 +790,65 @@ class Trainer:
         torch.save(d, save_dir / "latest_ckpt.pth")
         return save_dir / "latest_ckpt.pth"
 
-    def resume(self, inference=False, checkpoint_path=None):
-        """Load ``checkpoints/latest_ckpt.pth`` (a reference checkpoint's G / D state_dicts load as they are: same keys)."""
+    @staticmethod
+    def _merge(source, destination):
+        """climategan/utils.py:68-105: recursive dict merge (source wins)."""
+        for key, value in source.items():
+            if isinstance(value, dict):
+                Trainer._merge(value, destination.setdefault(key, {}))
+            else:
+                destination[key] = value
+        return destination
+
+    def _checkpoint_from_load_paths(self, checkpoint_path=None):
+        """trainer.py:422-533: which file(s) to load — ``checkpoint_path`` (ours), else ``opts.load_paths.{m,p,pm}`` with the
+        reference's rules (a P+M model may be assembled from a masker and a painter checkpoint: their dicts are merged), else
+        ``{output_path}/checkpoints/latest_ckpt.pth``.  A directory stands for its ``checkpoints/latest_ckpt.pth``."""
         from pathlib import Path
 
-        path = Path(checkpoint_path) if checkpoint_path else Path(self.opts.output_path) / "checkpoints" / "latest_ckpt.pth"
-        ckpt = torch.load(path, map_location=self.device)
+        def as_file(p):
+            p = Path(p)
+            assert p.exists(), f"{p} does not exist"
+            p = p / "checkpoints/latest_ckpt.pth" if p.is_dir() else p
+            assert p.suffix == ".pth", p
+            return p
+
+        def load(p):
+            return torch.load(as_file(p), map_location=self.device)
+
+        if checkpoint_path is not None:
+            return load(checkpoint_path)
+        lp = self.opts.load_paths if "load_paths" in self.opts else {}
+        m_path, p_path, pm_path = (str(lp.get(k, "none") or "none") for k in ("m", "p", "pm"))
+        latest = Path(self.opts.output_path) / "checkpoints" / "latest_ckpt.pth"
+        if "m" in self.opts.tasks and "p" in self.opts.tasks:
+            if m_path == p_path == pm_path == "none":
+                return load(latest)
+            if pm_path != "none":
+                return load(pm_path)
+            if m_path != p_path:
+                print(f"Resuming P+M model from \n  -{p_path} \nand \n  -{m_path}")
+                return self._merge(load(m_path), load(p_path))
+            raise ValueError("Cannot resume a P+M model with provided load_paths:\n{}".format(dict(lp)))
+        if m_path != "none" and p_path != "none":
+            raise ValueError("Opts tasks are {} but received 2 values for the load_paths".format(self.opts.tasks))
+        if m_path != "none":
+            assert "m" in self.opts.tasks
+            return load(m_path)
+        if p_path != "none":
+            assert "p" in self.opts.tasks
+            return load(p_path)
+        return load(latest)
+
+    def resume(self, inference=False, checkpoint_path=None):
+        """trainer.py:422-588.  The model state_dicts of a reference checkpoint load as they are (same keys and shapes).  The
+        OPTIMISER state only round-trips between runs of this package: ExtraAdam keeps its moments in one flat buffer per
+        parameter group (optim.py), a layout the reference's per-parameter state cannot be poured into — such a state is skipped
+        WITH a warning and the moments restart from zero (a plain ``torch.optim.Adam`` state loads normally).  As in the
+        reference, an odd step is rounded up to an even one so that extragradient resumes on an extrapolation."""
+        import warnings
+
+        ckpt = self._checkpoint_from_load_paths(checkpoint_path)
         if inference:
             bad = self.G.load_state_dict(ckpt["G"], strict=False)
             if bad.missing_keys:
@@ -804,13 +857,38 @@ class Trainer:
                 print("WARNING: Ignoring Unexpected keys in self.G.load_state_dict", bad.unexpected_keys)
             return self
         self.G.load_state_dict(ckpt["G"])
-        if "D" in ckpt and self.D is not None:
+        if "D" in ckpt and self.D is not None and sum(p.numel() for p in self.D.parameters()) > 0:
             self.D.load_state_dict(ckpt["D"])
+        from .optim import ExtraAdam
+
+        restored_lookahead = {}
         for opt, key in ((self.g_opt, "g_opt"), (self.d_opt, "d_opt")):
-            if opt is not None and key in ckpt and isinstance(ckpt[key], dict) and "flat" in ckpt[key]:
-                opt.load_state_dict(ckpt[key])
-        self.logger.global_step = int(ckpt.get("step", 0))
+            if opt is None:
+                continue
+            state = ckpt.get(key)
+            if not isinstance(state, dict):
+                warnings.warn(f"resume: the checkpoint holds no '{key}': the optimiser restarts from zero moments")
+            elif isinstance(opt, ExtraAdam):
+                if "flat" in state:
+                    opt.load_state_dict(state)
+                    restored_lookahead[key] = bool(opt._have_copy)
+                else:
+                    warnings.warn(f"resume: '{key}' is a per-parameter optimiser state (a reference checkpoint); ExtraAdam here keeps "
+                                  "flat per-group moments and cannot load it — moments and step count restart from zero")
+            else:
+                try:
+                    opt.load_state_dict(state)                       # torch.optim.Adam & co: the reference's own format
+                except (ValueError, KeyError) as e:
+                    warnings.warn(f"resume: could not restore '{key}' ({e}); the optimiser restarts from zero moments")
         self.logger.epoch = int(ckpt.get("epoch", 0))
+        self.logger.global_step = int(ckpt.get("step", 0))
+        for _ in range(self.logger.epoch + 1):                           # trainer.py:553-555: replay the schedulers
+            self.update_learning_rates()
+        if self.logger.global_step % 2 != 0 and not any(restored_lookahead.values()):
+            self.logger.global_step += 1                                 # trainer.py:575-577: round to even for extragradient
+        for opt in (self.g_opt, self.d_opt):                             # a look-ahead copy without its parity makes no sense
+            if isinstance(opt, ExtraAdam) and self.logger.global_step % 2 == 0:
+                opt._have_copy = False
         ops.invalidate_weight_cache()
         return self
 

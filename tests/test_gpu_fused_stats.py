@@ -68,9 +68,13 @@ def test_batchnorm_train_fwd_bwd_at_size(cuda, shape, dtype, residual):
     xr = x.double().requires_grad_(True)
     rr = r.double().requires_grad_(True) if residual else None
     wr, br = bn.weight.detach().double().cpu().requires_grad_(True), bn.bias.detach().double().cpu().requires_grad_(True)
-    yr = F.batch_norm(xr, None, None, wr, br, True, 0.1, bn.eps)
-    yr = F.relu(yr + rr if residual else yr)
+    pre = F.batch_norm(xr, None, None, wr, br, True, 0.1, bn.eps)
+    pre = pre + rr if residual else pre
+    yr = F.relu(pre)
     yr.backward(gy.double())
+    # a pre-activation within rounding error of 0 flips the ReLU gate against the fp64 reference — an O(gy) difference in that
+    # one element of the gradients (among 10^7 elements a few always sit there): compare away from the gate
+    safe = (pre.detach().abs() > 1e-3)
 
     xs = ops.to_storage(x.to(cuda), dtype).requires_grad_(True)
     rs = ops.to_storage(r.to(cuda), dtype).requires_grad_(True) if residual else None
@@ -79,9 +83,10 @@ def test_batchnorm_train_fwd_bwd_at_size(cuda, shape, dtype, residual):
     tol = 2e-5 if dtype == torch.float32 else 1.5e-2
     assert rel_max(yn, yr) < tol
     yn.backward(gy.to(cuda))
-    assert rel_max(ops.from_storage(xs.grad, c), xr.grad) < tol * 2, "gx"
+    assert float(safe.double().mean()) > 0.99
+    assert rel_max(ops.from_storage(xs.grad, c).cpu() * safe, xr.grad * safe) < tol * 2, "gx"
     if residual:
-        assert rel_max(ops.from_storage(rs.grad, c), rr.grad) < tol * 2, "gresidual"
+        assert rel_max(ops.from_storage(rs.grad, c).cpu() * safe, rr.grad * safe) < tol * 2, "gresidual"
     assert rel_max(bn.weight.grad, wr.grad) < tol * 2 and rel_max(bn.bias.grad, br.grad) < tol * 2
 
 
