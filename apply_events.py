@@ -5,8 +5,8 @@
 ``{stem}_{event}_{width}{suffix}.png`` (``:616``).
 
 Same flags as the reference.  Host-side image I/O uses PIL (the reference uses skimage: bilinear + anti-aliasing resize, so
-the pre-processed pixels can differ in the last bits); ``--half`` is accepted (the storage precision is bf16 unless
-``--fp32``); ``--upload`` (comet.ml) is out of scope and refused.  Everything between the pre-processed batch and the uint8
+the pre-processed pixels can differ in the last bits); ``--half`` runs the generator with fp16 storage (the reference's
+``trainer.G.half()``, :465-468; bf16 otherwise, fp32 with ``--fp32``); ``--upload`` (comet.ml) is out of scope and refused.  Everything between the pre-processed batch and the uint8
 events runs through libcgb200 — there is no CPU fallback.
 """
 from __future__ import annotations

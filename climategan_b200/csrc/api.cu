@@ -119,7 +119,7 @@ static int validate(const cgb_conv_desc* d, const char* who) {
     set_error("%s: unknown pad_mode %d", who, d->pad_mode);
     return CGB_BAD_ARG;
   }
-  if (d->dtype != CGB_F32 && d->dtype != CGB_BF16) {
+  if (d->dtype != CGB_F32 && d->dtype != CGB_BF16 && d->dtype != CGB_F16) {
     set_error("%s: unknown dtype %d", who, d->dtype);
     return CGB_BAD_ARG;
   }

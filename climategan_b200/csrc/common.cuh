@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
@@ -79,6 +80,27 @@ struct Vec8<__nv_bfloat16> {
   }
 };
 
+template <>
+struct Vec8<__half> {   // fp16 storage: the inference-only --half mode (apply_events.py:467-468, trainer.py:263-264)
+  static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+    uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __half22float2(h[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&v)[8]) {
+    uint4 r;
+    __half2* h = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};
+
 template <typename T>
 __device__ __forceinline__ float to_f(T v);
 template <>
@@ -86,12 +108,17 @@ __device__ __forceinline__ float to_f<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
+template <>
+__device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+
 template <typename T>
 __device__ __forceinline__ T from_f(float v);
 template <>
 __device__ __forceinline__ float from_f<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+__device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
 
 // ---- activations ----------------------------------------------------------------------------------
 __device__ __forceinline__ float act_apply(float v, int act, float slope) {

@@ -294,6 +294,9 @@ int conv_simt_fwd(const cgb_conv_desc* d, const void* x, const void* w, const fl
   if (d->dtype == CGB_F32)
     conv_simt_kernel<float, 0><<<grid, 256, 0, st>>>(p, (const float*)x, (const float*)w, bias,
                                                      (const float*)residual, nullptr, (float*)y);
+  else if (d->dtype == CGB_F16)
+    conv_simt_kernel<__half, 0><<<grid, 256, 0, st>>>(p, (const __half*)x, (const __half*)w, bias, (const __half*)residual,
+                                                      nullptr, (__half*)y);
   else
     conv_simt_kernel<__nv_bfloat16, 0><<<grid, 256, 0, st>>>(
         p, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (const __nv_bfloat16*)residual,
@@ -310,6 +313,9 @@ int conv_simt_dgrad(const cgb_conv_desc* d, const void* gy, const void* w, int d
   if (d->dtype == CGB_F32)
     conv_simt_kernel<float, 1><<<grid, 256, 0, st>>>(p, (const float*)gy, (const float*)w, nullptr,
                                                      nullptr, (const float*)mask_src, (float*)gx);
+  else if (d->dtype == CGB_F16)
+    conv_simt_kernel<__half, 1><<<grid, 256, 0, st>>>(p, (const __half*)gy, (const __half*)w, nullptr, nullptr,
+                                                      (const __half*)mask_src, (__half*)gx);
   else
     conv_simt_kernel<__nv_bfloat16, 1><<<grid, 256, 0, st>>>(
         p, (const __nv_bfloat16*)gy, (const __nv_bfloat16*)w, nullptr, nullptr,
@@ -336,6 +342,8 @@ int conv_simt_wgrad(const cgb_conv_desc* d, const void* x, const void* gy, float
   if (d->dtype == CGB_F32)
     wgrad_simt_kernel<float><<<grid, 256, 0, st>>>(p, (const float*)x, (const float*)gy, gw, gbias,
                                                    splits, pps);
+  else if (d->dtype == CGB_F16)
+    wgrad_simt_kernel<__half><<<grid, 256, 0, st>>>(p, (const __half*)x, (const __half*)gy, gw, gbias, splits, pps);
   else
     wgrad_simt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, (const __nv_bfloat16*)x,
                                                            (const __nv_bfloat16*)gy, gw, gbias,

@@ -178,12 +178,27 @@ __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
 }
 __device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)lo; }
 
-// instruction descriptor: bf16 x bf16 -> fp32, M=128
-__host__ __device__ inline uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
+// packed-pair helpers for the two 16-bit storage types (bf16: training + inference; fp16: the inference-only --half mode)
+template <typename T> struct Pk;
+template <> struct Pk<__nv_bfloat16> {
+  using T2 = __nv_bfloat162;
+  static constexpr bool is_f16 = false;
+  static __device__ __forceinline__ float2 to_f2(T2 v) { return __bfloat1622float2(v); }
+  static __device__ __forceinline__ T2 zero2() { return __float2bfloat162_rn(0.f); }
+};
+template <> struct Pk<__half> {
+  using T2 = __half2;
+  static constexpr bool is_f16 = true;
+  static __device__ __forceinline__ float2 to_f2(T2 v) { return __half22float2(v); }
+  static __device__ __forceinline__ T2 zero2() { return __float2half2_rn(0.f); }
+};
+
+// instruction descriptor: (bf16 x bf16 | f16 x f16) -> fp32, M=128
+__host__ __device__ inline uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major, bool f16 = false) {
   uint32_t d = 0;
   d |= 1u << 4;                          // c_format  F32
-  d |= 1u << 7;                          // a_format  BF16
-  d |= 1u << 10;                         // b_format  BF16
+  d |= (f16 ? 0u : 1u) << 7;             // a_format  F16 = 0, BF16 = 1
+  d |= (f16 ? 0u : 1u) << 10;            // b_format
   d |= (a_mn_major ? 1u : 0u) << 15;     // a_major
   d |= (b_mn_major ? 1u : 0u) << 16;     // b_major
   d |= (uint32_t)(n >> 3) << 17;         // N >> 3
@@ -242,10 +257,11 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // ---- epilogue of one 128-pixel x bn tile, executed by the 8 epilogue warps --------------------------------
 // phase 1: TMEM -> registers (two tcgen05.ld in flight) -> bias / activation / residual / mask -> bf16 -> staging row
 // phase 2: coalesced 16-byte copy-out (consecutive threads write consecutive chunks of a pixel's channel vector)
+template <typename T>
 __device__ __forceinline__ void epi_chunk(const TcParams& p, const uint32_t (&r)[16], int c, int cn0, bool pix_ok,
                                           long long pix, float neg, bool mask_early, const float* __restrict__ bias,
-                                          const __nv_bfloat16* __restrict__ residual,
-                                          const __nv_bfloat16* __restrict__ mask_src, uint8_t* my_row, int sw = -1) {
+                                          const T* __restrict__ residual,
+                                          const T* __restrict__ mask_src, uint8_t* my_row, int sw = -1) {
   // sw < 0: padded row-major staging row (my_row + channel*2).  sw = row & 7: TMA-store staging — per 64-channel half a
   // [128 rows][128 B] tile in the 128-byte swizzle (16-byte chunk index XOR row & 7), my_row = tile base + row*128
 #pragma unroll
@@ -263,7 +279,7 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const uint32_t (&r)
       }
       if (pix_ok && residual && p.res_before_act) {
         float rr[8];
-        Vec8<__nv_bfloat16>::load(residual + pix * p.cout_s + ch, rr);
+        Vec8<T>::load(residual + pix * p.cout_s + ch, rr);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] += rr[j];
       }
@@ -277,23 +293,23 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const uint32_t (&r)
       }
       if (pix_ok && residual && !p.res_before_act) {
         float rr[8];
-        Vec8<__nv_bfloat16>::load(residual + pix * p.cout_s + ch, rr);
+        Vec8<T>::load(residual + pix * p.cout_s + ch, rr);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] += rr[j];
       }
       if (pix_ok && mask_early) {
         float mm[8];
-        Vec8<__nv_bfloat16>::load(mask_src + pix * p.cout_s + ch, mm);
+        Vec8<T>::load(mask_src + pix * p.cout_s + ch, mm);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] *= act_grad_from_out(mm[j], p.dact, p.slope);
       }
     }
     if (sw < 0) {
-      Vec8<__nv_bfloat16>::store(reinterpret_cast<__nv_bfloat16*>(my_row + (size_t)(c * 16 + h * 8) * 2), v);
+      Vec8<T>::store(reinterpret_cast<T*>(my_row + (size_t)(c * 16 + h * 8) * 2), v);
     } else {
       const int j = c * 2 + h;
-      Vec8<__nv_bfloat16>::store(
-          reinterpret_cast<__nv_bfloat16*>(my_row + (size_t)(j >> 3) * (128 * 128) + (size_t)(((j & 7) ^ sw) << 4)), v);
+      Vec8<T>::store(
+          reinterpret_cast<T*>(my_row + (size_t)(j >> 3) * (128 * 128) + (size_t)(((j & 7) ^ sw) << 4)), v);
     }
   }
 }
@@ -326,6 +342,7 @@ __device__ __forceinline__ void epi_stats_flush(const TcParams& p, EpiStats& st,
   st.ch = -1;
 }
 
+template <typename T>
 __device__ __forceinline__ void epilogue_stats(const TcParams& p, const uint8_t* staging_gen, bool tma, int ox0, int oy0, int n0,
                                                int cn0, float* tab, EpiStats& st, int warp, int lane) {
   const int ew = warp - 2;                 // 0..EPI_WARPS-1
@@ -344,20 +361,21 @@ __device__ __forceinline__ void epilogue_stats(const TcParams& p, const uint8_t*
     const uint8_t* src = tma ? staging_gen + (size_t)(lane >> 3) * (128 * 128) + (size_t)r * 128 + (size_t)(((lane & 7) ^ (r & 7)) << 4)
                              : staging_gen + (size_t)r * p.stage_pitch + (size_t)lane * 16;
     const uint4 raw = *reinterpret_cast<const uint4*>(src);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    const typename Pk<T>::T2* h = reinterpret_cast<const typename Pk<T>::T2*>(&raw);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(h[i]);
+      const float2 f = Pk<T>::to_f2(h[i]);
       st.s[2 * i] += f.x; st.s[2 * i + 1] += f.y;
       st.q[2 * i] = fmaf(f.x, f.x, st.q[2 * i]); st.q[2 * i + 1] = fmaf(f.y, f.y, st.q[2 * i + 1]);
     }
   }
 }
 
+template <typename T>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_acc, uint8_t* staging_gen, int ox0, int oy0,
                                               int n0, int cn0, const float* __restrict__ bias,
-                                              const __nv_bfloat16* __restrict__ residual,
-                                              const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y,
+                                              const T* __restrict__ residual,
+                                              const T* __restrict__ mask_src, T* __restrict__ y,
                                               uint32_t tempty_bar, int warp, int lane, const CUtensorMap* tmY = nullptr,
                                               uint32_t staging_u32 = 0, float* stats_tab = nullptr, EpiStats* est = nullptr) {
   const int q = warp & 3;              // TMEM lane quarter this warp may access
@@ -406,11 +424,11 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
         if (cn0 + hb * 64 < p.cout_s) tma_store_4d(tmY, staging_u32 + (uint32_t)hb * (128u * 128u), cn0 + hb * 64, ox0, oy0, n0);
       tma_store_commit();
     }
-    if (stats_tab) epilogue_stats(p, staging_gen, true, ox0, oy0, n0, cn0, stats_tab, *est, warp, lane);
+    if (stats_tab) epilogue_stats<T>(p, staging_gen, true, ox0, oy0, n0, cn0, stats_tab, *est, warp, lane);
     return;
   }
   epi_bar_sync();  // staging complete
-  if (stats_tab) epilogue_stats(p, staging_gen, false, ox0, oy0, n0, cn0, stats_tab, *est, warp, lane);
+  if (stats_tab) epilogue_stats<T>(p, staging_gen, false, ox0, oy0, n0, cn0, stats_tab, *est, warp, lane);
   // phase 2: lanes cover (rows_per_iter x chunks_per_row) 16-byte chunks; the row/chunk split of a lane is fixed, so
   // the only per-iteration work is the pixel address.  Consecutive lanes write consecutive chunks of a pixel and then
   // the next pixel: full 32-byte sectors, no read-modify-write.
@@ -432,9 +450,10 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
       uint4 val = *reinterpret_cast<const uint4*>(staging_gen + (size_t)r2 * p.stage_pitch + (size_t)c * 16);
       if (mask_late) {  // relu derivative: keep where the forward output was > 0 (packed bf16x2 compare + multiply)
         const uint4 mk = *reinterpret_cast<const uint4*>(mask_src + off);
-        const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&mk);
-        __nv_bfloat162* vh = reinterpret_cast<__nv_bfloat162*>(&val);
-        const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.f);
+        using T2 = typename Pk<T>::T2;
+        const T2* mh = reinterpret_cast<const T2*>(&mk);
+        T2* vh = reinterpret_cast<T2*>(&val);
+        const T2 zero2 = Pk<T>::zero2();
 #pragma unroll
         for (int j = 0; j < 4; ++j) vh[j] = __hmul2(vh[j], __hgt2(mh[j], zero2));
       }
@@ -448,10 +467,11 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
 // Persistent: grid = min(#tiles, #SMs); CTA c processes tiles c, c+grid, ...
 // smem: [stages x (A 16 KB | B bn*128 B)] [staging 128 x (bn*2+16) B] [barriers]
 // ------------------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
-               const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y, float* __restrict__ stats_out) {
+               const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const T* __restrict__ residual,
+               const T* __restrict__ mask_src, T* __restrict__ y, float* __restrict__ stats_out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;  // 1024-B alignment for the 128B swizzle atoms
@@ -527,7 +547,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    const uint32_t idesc = make_idesc(p.bn, false, false);
+    const uint32_t idesc = make_idesc(p.bn, false, false, Pk<T>::is_f16);
     const uint32_t hi1024 = desc_hi(1024u);
     const int ksteps_last = ((p.cin_s - (p.kblocks - 1) * 64) + 15) >> 4;
     int s = 0;
@@ -580,7 +600,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar(buf), bph);
       tc_fence_after();
       const uint32_t sb = (p.staging_bufs == 2) ? (uint32_t)(lt & 1) * staging_tile : 0u;
-      epilogue_tile(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen + sb, tx << p.tw_log, ty << p.th_log, tn << tn_log,
+      epilogue_tile<T>(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen + sb, tx << p.tw_log, ty << p.th_log, tn << tn_log,
                     nt * p.bn, bias, residual, mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr,
                     staging + sb, stats_tab, &est);
     }
@@ -617,10 +637,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // Tile = 16 rows x 8 pixels (each 8-row swizzle group is one image-row segment).
 // smem: [weights] [stages x halo tile] [staging] [barriers].  grid is a multiple of n_tiles; CTA c keeps n-tile c % n_tiles.
 // ------------------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
-               const __nv_bfloat16* __restrict__ mask_src, __nv_bfloat16* __restrict__ y, float* __restrict__ stats_out) {
+               const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const T* __restrict__ residual,
+               const T* __restrict__ mask_src, T* __restrict__ y, float* __restrict__ stats_out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -693,7 +714,7 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc(p.bn, false, false);
+    const uint32_t idesc = make_idesc(p.bn, false, false, Pk<T>::is_f16);
     const uint32_t hi_a = desc_hi((uint32_t)p.twh * 128u), hi_b = desc_hi(1024u);
     const int ksteps_last = ((p.cin_s - (p.kblocks - 1) * 64) + 15) >> 4;
     mbar_wait(w_bar, 0u);
@@ -748,7 +769,7 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int img = pt / (p.tiles_x * p.tiles_y);
       mbar_wait(tfull_bar(buf), bph);
       tc_fence_after();
-      epilogue_tile(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen, tx << 3, ty << 4, img, cn0, bias, residual,
+      epilogue_tile<T>(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen, tx << 3, ty << 4, img, cn0, bias, residual,
                     mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr, staging, stats_tab, &est);
     }
     if (p.tma_store && threadIdx.x == 64) tma_store_wait_all();
@@ -795,13 +816,13 @@ static EncodeTiledFn get_encode() {
 }
 
 static bool encode_map(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                       const cuuint32_t* box, const cuuint32_t* estr, const char* what) {
+                       const cuuint32_t* box, const cuuint32_t* estr, const char* what, bool f16 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("tcgen05 engine: cuTensorMapEncodeTiled is unavailable in this driver");
     return false;
   }
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box,
+  CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides, box,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -879,7 +900,9 @@ static int pick_bn(int co) {
 }
 
 bool conv_tc_supported(const cgb_conv_desc* d, int which) {
-  if (d->dtype != CGB_BF16) return false;
+  // bf16: every operator; fp16 (the inference-only --half mode): fprop and dgrad (tcgen05 kind::f16 takes either operand
+  // format); the fp16 weight gradient stays on the CUDA-core engine — nothing on the path trains in fp16
+  if (d->dtype != CGB_BF16 && !(d->dtype == CGB_F16 && which != 2)) return false;
   if (d->pad_mode != CGB_PAD_ZERO && d->pad > 0) return false;
   if (which == 0) return d->stride <= 2;
   if (which == 1) {
@@ -899,7 +922,7 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
                          int cout_s, int wtaps_total, const TapTable& tt, int in_stride, int out_stride, int out_off_y,
                          int out_off_x, int hfull, int wfull, int act, float slope, const float* bias,
                          const void* residual, int dact, const void* mask_src, cudaStream_t st, int res_before_act = 0,
-                         float* stats_out = nullptr) {
+                         float* stats_out = nullptr, bool f16 = false) {
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.res_before_act = res_before_act;
@@ -943,14 +966,14 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
     cuuint32_t box[4] = {64, (cuuint32_t)((1 << p.tw_log) * in_stride), (cuuint32_t)((1 << p.th_log) * in_stride),
                          (cuuint32_t)(1 << tn_log)};
     cuuint32_t estr[4] = {1, (cuuint32_t)in_stride, (cuuint32_t)in_stride, 1};
-    if (!encode_map(&tmA, in, 4, dims, strides, box, estr, "activations")) return CGB_LAUNCH_FAILURE;
+    if (!encode_map(&tmA, in, 4, dims, strides, box, estr, "activations", f16)) return CGB_LAUNCH_FAILURE;
   }
   {
     cuuint64_t dims[3] = {(cuuint64_t)cin_s, (cuuint64_t)wtaps_total, (cuuint64_t)cout_s};
     cuuint64_t strides[2] = {(cuuint64_t)cin_s * 2, (cuuint64_t)wtaps_total * cin_s * 2};
     cuuint32_t box[3] = {64, 1, (cuuint32_t)p.bn};
     cuuint32_t estr[3] = {1, 1, 1};
-    if (!encode_map(&tmB, w, 3, dims, strides, box, estr, "weights")) return CGB_LAUNCH_FAILURE;
+    if (!encode_map(&tmB, w, 3, dims, strides, box, estr, "weights", f16)) return CGB_LAUNCH_FAILURE;
   }
   CUtensorMap tmY = tmB;   // (any valid map when the TMA store is off: the kernel never touches it)
   if (p.tma_store) {
@@ -958,11 +981,12 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
     cuuint64_t strides[3] = {(cuuint64_t)cout_s * 2, (cuuint64_t)wfull * cout_s * 2, (cuuint64_t)hfull * wfull * cout_s * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)(1 << p.tw_log), (cuuint32_t)(1 << p.th_log), (cuuint32_t)(1 << tn_log)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    if (!encode_map(&tmY, out, 4, dims, strides, box, estr, "output")) return CGB_LAUNCH_FAILURE;
+    if (!encode_map(&tmY, out, 4, dims, strides, box, estr, "output", f16)) return CGB_LAUNCH_FAILURE;
   }
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
   });
   const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 16 * stages + 64 + stats_bytes + 1024;
   if (smem > SMEM_LIMIT) {
@@ -970,8 +994,12 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
     return CGB_UNSUPPORTED;
   }
   dim3 grid((unsigned)(p.total_tiles < num_sms() ? p.total_tiles : num_sms()));
-  conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
-                                                 (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
+  if (f16)
+    conv_tc_kernel<__half><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __half*)residual, (const __half*)mask_src,
+                                                           (__half*)out, stats_out);
+  else
+    conv_tc_kernel<__nv_bfloat16><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
+                                                                  (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
   return after_launch("conv_tc");
 }
 
@@ -979,7 +1007,7 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
 static int launch_fprop(const void* in, const void* w, void* out, int n, int hin, int win, int cin_s, int hout, int wout,
                         int cout_s, int kh, int kw, int stride, int dil, int pad_y, int pad_x, int act, float slope,
                         const float* bias, const void* residual, int dact, const void* mask_src, cudaStream_t st,
-                        int res_before_act = 0, float* stats_out = nullptr) {
+                        int res_before_act = 0, float* stats_out = nullptr, bool f16 = false) {
   const int taps = kh * kw;
   const int stats_bytes = stats_out ? 2 * cout_s * 4 + 16 : 0;
   // ---- traffic estimate of the streaming configuration
@@ -1035,7 +1063,7 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
       tt.w[t] = (short)t;
     }
     return launch_stream(in, w, out, n, hin, win, cin_s, hout, wout, cout_s, taps, tt, stride, 1, 0, 0, hout, wout, act, slope,
-                         bias, residual, dact, mask_src, st, res_before_act, stats_out);
+                         bias, residual, dact, mask_src, st, res_before_act, stats_out, f16);
   }
 
   TcParams p;
@@ -1049,7 +1077,8 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
   p.stats = stats_out ? 1 : 0;
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    cudaFuncSetAttribute(conv_tc_ws_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    cudaFuncSetAttribute(conv_tc_ws_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
   });
   p.tw_log = 3; p.th_log = 4;
   p.tiles_x = (wout + 7) / 8; p.tiles_y = (hout + 15) / 16;
@@ -1070,14 +1099,14 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
     cuuint64_t strides[3] = {(cuuint64_t)cin_s * 2, (cuuint64_t)win * cin_s * 2, (cuuint64_t)hin * win * cin_s * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)twh, (cuuint32_t)thh, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    if (!encode_map(&tmA, in, 4, dims, strides, box, estr, "activations")) return CGB_LAUNCH_FAILURE;
+    if (!encode_map(&tmA, in, 4, dims, strides, box, estr, "activations", f16)) return CGB_LAUNCH_FAILURE;
   }
   {
     cuuint64_t dims[3] = {(cuuint64_t)cin_s, (cuuint64_t)taps, (cuuint64_t)cout_s};
     cuuint64_t strides[2] = {(cuuint64_t)cin_s * 2, (cuuint64_t)taps * cin_s * 2};
     cuuint32_t box[3] = {64, 1, (cuuint32_t)p.bn};
     cuuint32_t estr[3] = {1, 1, 1};
-    if (!encode_map(&tmB, w, 3, dims, strides, box, estr, "weights")) return CGB_LAUNCH_FAILURE;
+    if (!encode_map(&tmB, w, 3, dims, strides, box, estr, "weights", f16)) return CGB_LAUNCH_FAILURE;
   }
   CUtensorMap tmY = tmB;   // (any valid map when the TMA store is off: the kernel never touches it)
   if (p.tma_store) {
@@ -1085,14 +1114,18 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
     cuuint64_t strides[3] = {(cuuint64_t)cout_s * 2, (cuuint64_t)wout * cout_s * 2, (cuuint64_t)hout * wout * cout_s * 2};
     cuuint32_t box[4] = {64, 8, 16, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    if (!encode_map(&tmY, out, 4, dims, strides, box, estr, "output")) return CGB_LAUNCH_FAILURE;
+    if (!encode_map(&tmY, out, 4, dims, strides, box, estr, "output", f16)) return CGB_LAUNCH_FAILURE;
   }
   p.stats_off = (int)((size_t)p.kblocks * taps * p.bn * 128 + (size_t)p.stages * a_stage + staging_bytes + 16 * p.stages + 64);
   const size_t smem = (size_t)p.stats_off + stats_bytes + 1024;
   int ctas = num_sms() / p.n_tiles * p.n_tiles;
   if (ctas > p.pix_tiles * p.n_tiles) ctas = p.pix_tiles * p.n_tiles;
-  conv_tc_ws_kernel<<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
-                                                    (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
+  if (f16)
+    conv_tc_ws_kernel<__half><<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __half*)residual,
+                                                              (const __half*)mask_src, (__half*)out, stats_out);
+  else
+    conv_tc_ws_kernel<__nv_bfloat16><<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
+                                                                     (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
   return after_launch("conv_tc_ws");
 }
 
@@ -1103,7 +1136,8 @@ int conv_tc_fwd(const cgb_conv_desc* d, const void* x, const void* w, const floa
                 cudaStream_t st, float* stats_out) {
   if (stats_out) cudaMemsetAsync(stats_out, 0, sizeof(float) * (size_t)num_sms() * 2 * d->co, st);
   return launch_fprop(x, w, y, d->n, d->hi, d->wi, d->ci, d->ho, d->wo, d->co, d->kh, d->kw, d->stride, d->dil, d->pad,
-                      d->pad, d->act, d->slope, bias, residual, CGB_ACT_NONE, nullptr, st, d->res_before_act, stats_out);
+                      d->pad, d->act, d->slope, bias, residual, CGB_ACT_NONE, nullptr, st, d->res_before_act, stats_out,
+                      d->dtype == CGB_F16);
 }
 
 // wt: dgrad packing [ci][taps][co] with the taps reversed (cgb_conv2d_pack_dgrad_weight)
@@ -1151,14 +1185,14 @@ int conv_tc_dgrad(const cgb_conv_desc* d, const void* gy, const void* wt, int da
         const int hc = (d->hi - ry + s_ - 1) / s_, wc = (d->wi - rx + s_ - 1) / s_;
         if (tt.ntaps == 0 || hc <= 0 || wc <= 0) continue;
         int r = launch_stream(gy, wt, gx, d->n, d->ho, d->wo, d->co, hc, wc, d->ci, T, tt, 1, s_, ry, rx, d->hi, d->wi,
-                              CGB_ACT_NONE, d->slope, nullptr, nullptr, dact, mask_src, st);
+                              CGB_ACT_NONE, d->slope, nullptr, nullptr, dact, mask_src, st, 0, nullptr, d->dtype == CGB_F16);
         if (r) return r;
       }
     return CGB_OK;
   }
   return launch_fprop(gy, wt, gx, d->n, d->ho, d->wo, d->co, d->hi, d->wi, d->ci, d->kh, d->kw, 1, d->dil,
                       d->dil * (d->kh - 1) - d->pad, d->dil * (d->kw - 1) - d->pad, CGB_ACT_NONE, d->slope, nullptr, nullptr,
-                      dact, mask_src, st);
+                      dact, mask_src, st, 0, nullptr, d->dtype == CGB_F16);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1728,6 +1762,8 @@ int pack_dgrad_weight(const cgb_conv_desc* d, const void* w, void* wt, cudaStrea
   if (grid > 148 * 8) grid = 148 * 8;
   if (d->dtype == CGB_F32)
     pack_dgrad_weight_kernel<float><<<grid, 256, 0, st>>>((const float*)w, (float*)wt, d->co, taps, d->ci);
+  else if (d->dtype == CGB_F16)
+    pack_dgrad_weight_kernel<__half><<<grid, 256, 0, st>>>((const __half*)w, (__half*)wt, d->co, taps, d->ci);
   else
     pack_dgrad_weight_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)w, (__nv_bfloat16*)wt, d->co, taps, d->ci);
   return after_launch("pack_dgrad_weight");

@@ -23,6 +23,9 @@ static inline int grid_for(long long work, int block = 256) {
   } else if ((dtype) == CGB_BF16) {                     \
     using T = __nv_bfloat16;                            \
     __VA_ARGS__                                         \
+  } else if ((dtype) == CGB_F16) {                      \
+    using T = __half;                                   \
+    __VA_ARGS__                                         \
   } else {                                              \
     set_error("unknown dtype %d", (int)(dtype));        \
     return CGB_BAD_ARG;                                 \

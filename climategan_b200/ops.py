@@ -1,7 +1,7 @@
 """Autograd operators over libcgb200 (the C ABI in include/cgb200.h).
 
 Tensors between operators are *storage tensors*: contiguous ``[N, H, W, Cs]`` (NHWC) with
-``Cs = round_up(C, 8)`` and zero pad channels, dtype ``torch.float32`` or ``torch.bfloat16``.
+``Cs = round_up(C, 8)`` and zero pad channels, dtype ``torch.float32``, ``torch.bfloat16`` or (inference) ``torch.float16``.
 The reference's NCHW fp32 tensors exist only at the API edges (:func:`to_storage`,
 :func:`from_storage`).  PyTorch is used for memory, streams and the autograd tape only; every
 array operation on an activation goes through a ``cgb_*`` entry point.  Nothing here has a CPU
@@ -19,7 +19,7 @@ from torch.autograd import Function
 from . import _lib
 from ._lib import ConvDesc, check
 
-_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}   # fp16: inference only (--half)
 
 
 def round8(c: int) -> int:
@@ -46,7 +46,7 @@ def _on_device(x: torch.Tensor) -> bool:
 def _chk_storage(x: torch.Tensor, name: str = "x") -> None:
     if x.dim() != 4 or not x.is_contiguous() or x.shape[-1] % 8 or x.dtype not in _DT or not _on_device(x):
         raise ValueError(
-            f"{name}: expected a contiguous CUDA NHWC storage tensor with C%8==0 (fp32/bf16), got "
+            f"{name}: expected a contiguous CUDA NHWC storage tensor with C%8==0 (fp32/bf16/fp16), got "
             f"shape={tuple(x.shape)} dtype={x.dtype} device={x.device} contiguous={x.is_contiguous()}"
         )
 

@@ -612,8 +612,22 @@ class Trainer:
     def infer_all(self, x, numpy=True, stores={}, bin_value=-1, half=False, xla=False, cloudy=False, auto_resize_640=False,
                   ignore_event=set(), return_masks=False):
         """Dictionary of events ("flood", "wildfire", "smog") from a numpy array or tensor, single image or batch, HWC or CHW.
-        ``half`` is accepted for API compatibility: storage precision is the trainer's ``storage_dtype`` (bf16 by default)."""
+        ``half=True`` (trainer.py:263-264, ``apply_events.py --half``): the generator runs with fp16 activation / weight storage
+        (tcgen05 ``kind::f16`` on fp16 operands, fp32 accumulation and statistics) for this call, whatever the trainer's
+        ``storage_dtype`` is; the compositing stays fp32 as in the reference (events are computed on ``.float()`` tensors)."""
         import numpy as np
+
+        if half and self.G.storage_dtype != torch.float16:
+            saved = (self.G.storage_dtype, getattr(self.G.painter, "storage_dtype", None))
+            self.G.storage_dtype = torch.float16
+            if saved[1] is not None:
+                self.G.painter.storage_dtype = torch.float16
+            try:
+                return self.infer_all(x, numpy, stores, bin_value, True, xla, cloudy, auto_resize_640, ignore_event, return_masks)
+            finally:
+                self.G.storage_dtype = saved[0]
+                if saved[1] is not None:
+                    self.G.painter.storage_dtype = saved[1]
 
         assert self.is_setup
         assert len(x.shape) in {3, 4}, f"Unknown Data shape {x.shape}"

@@ -39,7 +39,7 @@ typedef enum {
   CGB_UNSUPPORTED_ARCH = -4
 } cgb_status;
 
-typedef enum { CGB_F32 = 0, CGB_BF16 = 1 } cgb_dtype;
+typedef enum { CGB_F32 = 0, CGB_BF16 = 1, CGB_F16 = 2 } cgb_dtype;
 
 typedef enum {
   CGB_ACT_NONE = 0,

@@ -19,8 +19,8 @@ import torch.nn.functional as F
 from climategan_b200 import _lib, ops
 from tests.dryrun import NoopLib
 
-_DT = {0: torch.float32, 1: torch.bfloat16}
-_CT = {torch.float32: C.c_float, torch.bfloat16: C.c_uint16, torch.float64: C.c_double, torch.int64: C.c_int64}
+_DT = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16}
+_CT = {torch.float32: C.c_float, torch.bfloat16: C.c_uint16, torch.float16: C.c_uint16, torch.float64: C.c_double, torch.int64: C.c_int64}
 
 
 def _addr(p):
