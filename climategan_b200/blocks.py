@@ -95,11 +95,9 @@ class Conv2dBlock(nn.Module):
             else:
                 w, b = conv_weight_bias(self.conv)  # runs the spectral-norm power iteration, as the reference does in eval
                 if self.norm is not None:
-                    scale = self.norm.weight / torch.sqrt(self.norm.running_var + self.norm.eps)
-                    bb = self.norm.bias - self.norm.running_mean * scale
-                    if b is not None:
-                        bb = bb + b * scale
-                    w, b = w * scale.view(-1, 1, 1, 1), bb
+                    from .deeplab.resnetmulti_v2 import eval_bn_fold
+
+                    w, b = eval_bn_fold(w, b, self.norm)
                 wp = ops.pack_weight_cached(w, x.dtype, cis=x.shape[-1])
                 bp = ops.pad_bias(b, wp.shape[0])
             pad, pad_mode = self.padding, self.pad_mode

@@ -32,19 +32,21 @@ static inline int grid_for(long long work, int block = 256) {
   }
 
 // ---------------------------------------------------------------------------------------------------
-// Train-mode BatchNorm passes.  All three are FLAT grid-stride kernels over the tensor's 16-byte channel vectors with
-// BN_U vectors in flight per thread.  The grid is sized so that (gridDim * 256) is a multiple of cv = c/8: a thread then
-// meets the SAME 8 channels on every iteration and keeps their per-channel coefficients in registers.
-// (Round 1 walked 256-pixel chunks with one load in flight per thread: on the 8x80x80 ResNet maps that is 200 CTAs and
-// ~6 KB in flight per SM — latency-bound at 0.4 of the HBM roofline, profiles/r01_full_step_torch_profiler.txt.)
-constexpr int BN_U = 4;
+// Train-mode BatchNorm passes.  All three are FLAT grid-stride kernels over the tensor's 16-byte channel vectors.  The grid is
+// sized so that (gridDim * 256) is a multiple of cv = c/8: a thread then meets the SAME 8 channels on every iteration.
+// Per-channel coefficients live in a shared-memory table built once per CTA (registers hold only the vectors in flight:
+// <= 40 registers, 6-8 CTAs per SM).  History, measured on B200 (scripts/bench_hbm_kernels.py, profiles/r02_hbm_kernels.txt):
+//   round 1: 256-pixel chunks, one load in flight, 200 CTAs on the 8x80x80 maps            -> 0.35-0.45 of the HBM roofline
+//   first flat version: 4 vectors in flight held as fp32 (126-173 registers, 1-2 CTAs/SM)  -> 0.35-0.57 fwd, 0.24-0.34 bwd:
+//   occupancy, not instruction-level parallelism, is what hides the latency here (spade_mod_fwd, 2048 threads/SM: 0.87).
+constexpr int BN_U = 2;
 
 static inline long long gcd_ll(long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; }
 
 // CTAs for a flat pass over total_vec vectors, a multiple of cv / gcd(cv, 256) so that a thread's channel vector is fixed
 static inline int bn_grid(long long total_vec, int cv) {
   long long g = (total_vec + 256LL * BN_U - 1) / (256LL * BN_U);
-  const long long cap = 148LL * 4;
+  const long long cap = 148LL * 8;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   const long long m = cv / gcd_ll(cv, 256);
@@ -52,44 +54,60 @@ static inline int bn_grid(long long total_vec, int cv) {
   return (int)g;
 }
 
+template <typename T> struct Raw8;                      // the 8-channel vector as loaded (no conversion until it is used)
+template <> struct Raw8<float> { float4 a, b; };
+template <> struct Raw8<__nv_bfloat16> { uint4 a; };
+template <> struct Raw8<__half> { uint4 a; };
+template <typename T>
+__device__ __forceinline__ Raw8<T> ldraw(const T* p) { return *reinterpret_cast<const Raw8<T>*>(p); }
+template <typename T>
+__device__ __forceinline__ void cvt8(const Raw8<T>& r, float (&v)[8]) { Vec8<T>::load(reinterpret_cast<const T*>(&r), v); }
+
 // y = act(x*A + B (+ residual)), A = rstd*w, B = b - mean*A  (per channel)
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 bn_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ weight, const float* __restrict__ bias, const T* __restrict__ residual,
                     T* __restrict__ y, long long total_vec, int cv, float neg) {
+  extern __shared__ float tab[];   // A[c], B[c]
+  const int c = cv * 8;
+  for (int i = threadIdx.x; i < c; i += 256) {
+    const float a = rstd[i] * (weight ? weight[i] : 1.f);
+    tab[i] = a;
+    tab[c + i] = (bias ? bias[i] : 0.f) - mean[i] * a;
+  }
+  __syncthreads();
   const long long stride = (long long)gridDim.x * 256;
   const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
   const int v = (int)(i0 % cv);
-  float A[8], B[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int ch = v * 8 + j;
-    const float w = weight ? weight[ch] : 1.f, b = bias ? bias[ch] : 0.f;
-    A[j] = rstd[ch] * w;
-    B[j] = b - mean[ch] * A[j];
-  }
+  const float* Ap = tab + v * 8;
+  const float* Bp = tab + c + v * 8;
   for (long long i = i0; i < total_vec; i += stride * BN_U) {
-    float xv[BN_U][8], r[BN_U][8];
+    Raw8<T> xr[BN_U], rr[BN_U];
 #pragma unroll
     for (int u = 0; u < BN_U; ++u) {
       const long long k = i + u * stride;
       if (k < total_vec) {
-        Vec8<T>::load(x + k * 8, xv[u]);
-        if (residual) Vec8<T>::load(residual + k * 8, r[u]);
+        xr[u] = ldraw<T>(x + k * 8);
+        if (residual) rr[u] = ldraw<T>(residual + k * 8);
       }
     }
 #pragma unroll
     for (int u = 0; u < BN_U; ++u) {
       const long long k = i + u * stride;
       if (k < total_vec) {
-        float o[8];
+        float xv[8], o[8];
+        cvt8<T>(xr[u], xv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float t = fmaf(xv[u][j], A[j], B[j]);
-          if (residual) t += r[u][j];
-          o[j] = t > 0.f ? t : t * neg;
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(xv[j], Ap[j], Bp[j]);
+        if (residual) {
+          float r[8];
+          cvt8<T>(rr[u], r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * neg;
         Vec8<T>::store(y + k * 8, o);
       }
     }
@@ -99,58 +117,71 @@ bn_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, con
 // backward part 1: gpre = gy * act'(y); per-CTA partial sums of gpre and gpre * xhat (shared-memory table, then one plain
 // store per (CTA, channel): no global atomics — the fp64 fold over CTAs is bn_bwd_reduce_kernel)
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bn_apply_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
                     const T* __restrict__ y, const T* __restrict__ gy, T* __restrict__ gpre, float* __restrict__ partial,
                     long long total_vec, int cv, float neg, int has_act) {
-  extern __shared__ float sm[];  // [2][c]
+  extern __shared__ float sm[];  // sums [2][8][cv] (conflict-free fold), then rs[c], nm[c]
   const int c = cv * 8;
+  float* coef = sm + 2 * c;
   for (int i = threadIdx.x; i < 2 * c; i += 256) sm[i] = 0.f;
+  for (int i = threadIdx.x; i < c; i += 256) {
+    const float r = rstd[i];
+    coef[i] = r;
+    coef[c + i] = -mean[i] * r;
+  }
   __syncthreads();
   const long long stride = (long long)gridDim.x * 256;
   const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
   const int v = (int)(i0 % cv);
-  float rs[8], nm[8], s1[8], s2[8];
+  const float* rs = coef + v * 8;
+  const float* nm = coef + c + v * 8;
+  float s1[8], s2[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    rs[j] = rstd[v * 8 + j];
-    nm[j] = -mean[v * 8 + j] * rs[j];
-    s1[j] = s2[j] = 0.f;
-  }
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   for (long long i = i0; i < total_vec; i += stride * BN_U) {
-    float xv[BN_U][8], g[BN_U][8], yv[BN_U][8];
+    Raw8<T> xr[BN_U], gr[BN_U], yr[BN_U];
 #pragma unroll
     for (int u = 0; u < BN_U; ++u) {
       const long long k = i + u * stride;
       if (k < total_vec) {
-        Vec8<T>::load(x + k * 8, xv[u]);
-        Vec8<T>::load(gy + k * 8, g[u]);
-        if (has_act) Vec8<T>::load(y + k * 8, yv[u]);
+        xr[u] = ldraw<T>(x + k * 8);
+        gr[u] = ldraw<T>(gy + k * 8);
+        if (has_act) yr[u] = ldraw<T>(y + k * 8);
       }
     }
 #pragma unroll
     for (int u = 0; u < BN_U; ++u) {
       const long long k = i + u * stride;
       if (k < total_vec) {
-        float o[8];
+        float o[8], t[8];
+        cvt8<T>(gr[u], o);
+        if (has_act) {
+          cvt8<T>(yr[u], t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = t[j] > 0.f ? o[j] : o[j] * neg;
+        }
+        cvt8<T>(xr[u], t);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          o[j] = (!has_act || yv[u][j] > 0.f) ? g[u][j] : g[u][j] * neg;
           s1[j] += o[j];
-          s2[j] = fmaf(o[j], fmaf(xv[u][j], rs[j], nm[j]), s2[j]);
+          s2[j] = fmaf(o[j], fmaf(t[j], rs[j], nm[j]), s2[j]);
         }
         Vec8<T>::store(gpre + k * 8, o);
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&sm[v * 8 + j], s1[j]);
-    atomicAdd(&sm[c + v * 8 + j], s2[j]);
+  for (int j = 0; j < 8; ++j) {   // [moment][j][v]: the lanes of a warp (consecutive v) hit consecutive words
+    atomicAdd(&sm[j * cv + v], s1[j]);
+    atomicAdd(&sm[c + j * cv + v], s2[j]);
   }
   __syncthreads();
   float* out = partial + (long long)blockIdx.x * 2 * c;
-  for (int i = threadIdx.x; i < 2 * c; i += 256) out[i] = sm[i];
+  for (int i = threadIdx.x; i < 2 * c; i += 256) {
+    const int m = i >= c ? 1 : 0, ch = i - m * c;
+    out[i] = sm[m * c + (ch & 7) * cv + (ch >> 3)];
+  }
 }
 
 // sums[c][2] (fp64) = sum over chunks of the partials
@@ -179,42 +210,47 @@ bn_bwd_reduce_kernel(const float* __restrict__ partial, double* __restrict__ sum
 
 // backward part 2: gx = w*rstd*(gpre - s0/M - xhat*s1/M) = A*g + B*x + C
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 bn_bwd_finalize_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
                        const float* __restrict__ weight, const double* __restrict__ sums, const T* __restrict__ gpre,
                        T* __restrict__ gx, long long total_vec, int cv, double inv_npix) {
-  const long long stride = (long long)gridDim.x * 256;
-  const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
-  const int v = (int)(i0 % cv);
-  float A[8], B[8], Cc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int ch = v * 8 + j;
+  extern __shared__ float tab[];   // A[c], B[c], C[c]
+  const int c = cv * 8;
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
     const float w = weight ? weight[ch] : 1.f;
     const float rs = rstd[ch], mu = mean[ch];
     const float m1 = (float)(sums[ch * 2 + 0] * inv_npix);
     const float m2 = (float)(sums[ch * 2 + 1] * inv_npix);
-    A[j] = w * rs;
-    B[j] = -w * rs * rs * m2;
-    Cc[j] = w * (rs * rs * m2 * mu - rs * m1);
+    tab[ch] = w * rs;
+    tab[c + ch] = -w * rs * rs * m2;
+    tab[2 * c + ch] = w * (rs * rs * m2 * mu - rs * m1);
   }
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * 256;
+  const long long i0 = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int v = (int)(i0 % cv);
+  const float* A = tab + v * 8;
+  const float* B = tab + c + v * 8;
+  const float* Cc = tab + 2 * c + v * 8;
   for (long long i = i0; i < total_vec; i += stride * BN_U) {
-    float xv[BN_U][8], gv[BN_U][8];
+    Raw8<T> xr[BN_U], gr[BN_U];
 #pragma unroll
     for (int u = 0; u < BN_U; ++u) {
       const long long k = i + u * stride;
       if (k < total_vec) {
-        Vec8<T>::load(x + k * 8, xv[u]);
-        Vec8<T>::load(gpre + k * 8, gv[u]);
+        xr[u] = ldraw<T>(x + k * 8);
+        gr[u] = ldraw<T>(gpre + k * 8);
       }
     }
 #pragma unroll
     for (int u = 0; u < BN_U; ++u) {
       const long long k = i + u * stride;
       if (k < total_vec) {
-        float o[8];
+        float xv[8], gv[8], o[8];
+        cvt8<T>(xr[u], xv);
+        cvt8<T>(gr[u], gv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], gv[u][j], fmaf(B[j], xv[u][j], Cc[j]));
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(A[j], gv[j], fmaf(B[j], xv[j], Cc[j]));
         Vec8<T>::store(gx + k * 8, o);
       }
     }
@@ -873,7 +909,7 @@ extern "C" int cgb_bn_apply_fwd(const void* x, const float* mean, const float* r
   const float neg = act == CGB_ACT_NONE ? 1.f : (act == CGB_ACT_RELU ? 0.f : slope);
   const int cv = c / 8;
   const long long total = (long long)npix * cv;
-  DISPATCH_T(dtype, bn_apply_fwd_kernel<T><<<bn_grid(total, cv), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, bn_apply_fwd_kernel<T><<<bn_grid(total, cv), 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
                         (const T*)x, mean, rstd, weight, bias, (const T*)residual, (T*)y, total, cv, neg);)
   return after_launch("bn_apply_fwd");
 }
@@ -896,7 +932,7 @@ extern "C" int cgb_bn_apply_bwd(const void* x, const float* mean, const float* r
   const long long total = (long long)npix * cv;
   const int grid = bn_grid(total, cv);
   float* partial = reinterpret_cast<float*>(sums + 2 * (size_t)c);   // sums holds cgb_bn_bwd_ws_doubles(npix, c) doubles
-  DISPATCH_T(dtype, bn_apply_bwd_kernel<T><<<grid, 256, 2 * c * sizeof(float), st>>>(
+  DISPATCH_T(dtype, bn_apply_bwd_kernel<T><<<grid, 256, 4 * c * sizeof(float), st>>>(
                         (const T*)x, mean, rstd, (const T*)y, (const T*)gy, (T*)gpre, partial, total, cv, neg,
                         act != CGB_ACT_NONE);)
   int s = after_launch("bn_apply_bwd");
@@ -912,7 +948,7 @@ extern "C" int cgb_bn_bwd_finalize(const void* x, const float* mean, const float
   REQ_C(c, "bn_bwd_finalize");
   const int cv = c / 8;
   const long long total = (long long)npix * cv;
-  DISPATCH_T(dtype, bn_bwd_finalize_kernel<T><<<bn_grid(total, cv), 256, 0, (cudaStream_t)stream>>>(
+  DISPATCH_T(dtype, bn_bwd_finalize_kernel<T><<<bn_grid(total, cv), 256, 3 * c * sizeof(float), (cudaStream_t)stream>>>(
                         (const T*)x, mean, rstd, weight, sums, (const T*)gpre, (T*)gx, total, cv, 1.0 / (double)npix);)
   return after_launch("bn_bwd_finalize");
 }

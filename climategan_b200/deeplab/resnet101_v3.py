@@ -105,9 +105,10 @@ class ResNet(nn.Module):
         if t:
             y = ops.conv_bn_act(xc, as_gemm(c1.weight), self.bn1, act=_lib.ACT_RELU)
         else:
-            scale = self.bn1.weight.detach() / torch.sqrt(self.bn1.running_var + self.bn1.eps)
-            wp = ops.pack_weight(as_gemm(c1.weight.detach() * scale.view(-1, 1, 1, 1)), x.dtype, cis=xc.shape[-1])
-            b = self.bn1.bias.detach() - self.bn1.running_mean * scale
+            from .resnetmulti_v2 import eval_bn_fold
+
+            w, b = eval_bn_fold(c1.weight.detach(), None if c1.bias is None else c1.bias.detach(), self.bn1)
+            wp = ops.pack_weight(as_gemm(w), x.dtype, cis=xc.shape[-1])
             y = ops.conv2d_infer(xc, wp, ops.pad_bias(b, wp.shape[0]), k=1, act=_lib.ACT_RELU)
         y = ops.maxpool3s2_pad1(y)
         for blk in self.layer1:

@@ -11,20 +11,34 @@ from .. import _lib, ops
 affine_par = True
 
 
+def eval_bn_fold(w, b, bn):
+    """(w', b') of a conv weight / bias followed by eval-mode BatchNorm ``bn``: w' = w*g/sqrt(var+eps),
+    b' = beta + (b - mean)*g/sqrt(var+eps).  ``bn`` may be the identity layer ``bn_fusion.bn_fuse`` leaves behind — the fold
+    then already lives in the conv's own weight and bias."""
+    from ..bn_fusion import is_fused
+
+    if is_fused(bn):
+        return w, b
+    scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+    bb = bn.bias.detach() - bn.running_mean * scale
+    if b is not None:
+        bb = bb + b * scale
+    return w * scale.view(-1, 1, 1, 1), bb
+
+
 def fold_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d, dtype, cis=None):
     """Packed weights/bias of conv followed by eval-mode BatchNorm: w' = w*g/sqrt(var+eps), b' = beta + (b-mean)*g/sqrt(..)
     — what ``climategan/bn_fusion.py::fuse`` (:6-49) computes.  The folded packing is cached until any of the six tensors
     changes (ops.cached_pack), so repeated inference forwards do not re-fold."""
+    from ..bn_fusion import is_fused
+
     def build():
-        scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
-        w = conv.weight.detach() * scale.view(-1, 1, 1, 1)
-        b = bn.bias.detach() - bn.running_mean * scale
-        if conv.bias is not None:
-            b = b + conv.bias.detach() * scale
+        w, b = eval_bn_fold(conv.weight.detach(), None if conv.bias is None else conv.bias.detach(), bn)
         wp = ops.pack_weight(w, dtype, cis=cis)
         return wp, ops.pad_bias(b, wp.shape[0])
 
-    deps = [conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var] + ([conv.bias] if conv.bias is not None else [])
+    deps = [conv.weight] + ([] if is_fused(bn) else [bn.weight, bn.bias, bn.running_mean, bn.running_var])
+    deps += [conv.bias] if conv.bias is not None else []
     return ops.cached_pack(deps, ("fold_bn", dtype, cis), build, uses_running_stats=True)
 
 
@@ -130,10 +144,8 @@ class ResNetMulti(nn.Module):
         if self.training:
             x = ops.conv_bn_act(xc, as_gemm(c1.weight), self.bn1, act=_lib.ACT_RELU)
         else:
-            scale = self.bn1.weight.detach() / torch.sqrt(self.bn1.running_var + self.bn1.eps)
-            w = as_gemm(c1.weight.detach() * scale.view(-1, 1, 1, 1))
-            b = self.bn1.bias.detach() - self.bn1.running_mean * scale
-            wp = ops.pack_weight(w, x.dtype, cis=xc.shape[-1])
+            w, b = eval_bn_fold(c1.weight.detach(), None if c1.bias is None else c1.bias.detach(), self.bn1)
+            wp = ops.pack_weight(as_gemm(w), x.dtype, cis=xc.shape[-1])
             x = ops.conv2d_infer(xc, wp, ops.pad_bias(b, wp.shape[0]), k=1, act=_lib.ACT_RELU)
         x = ops.maxpool3s2_ceil(x)
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
