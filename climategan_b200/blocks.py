@@ -68,6 +68,17 @@ class Conv2dBlock(nn.Module):
             self.conv = nn.Conv2d(input_dim, output_dim, kernel_size, stride, dilation=dilation,
                                   bias=self.use_bias if norm != "batch" else False)
 
+    def _reference_leaf_order(self):
+        """Leaf order of the reference Conv2dBlock for bn_fusion.bn_fuse: pad, norm, activation, conv (blocks.py:66-136 registers
+        them in that order, so a block's own BatchNorm is never adjacent to its conv, nor to the previous block's)."""
+        order = [("pad", None)]
+        if self.norm is not None:
+            order.append(("norm", self.norm))
+        if self.activation is not None:
+            order.append(("activation", None))
+        order.append(("conv", self.conv))
+        return order
+
     def forward(self, x, residual=None):
         """Training-capable forward (autograd tape): explicit reflect pad -> conv (tcgen05, pad 0) -> [train-mode
         BatchNorm + activation as one apply pass] ; bias + activation ride in the conv epilogue when there is no norm."""

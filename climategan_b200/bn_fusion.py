@@ -41,8 +41,17 @@ def _leaves(module, prefix=()):
     not Sequential / ModuleList containers are the leaves (bn_fusion.py:17-35)."""
     out = []
     children = list(module.named_children())
+    order = getattr(module, "_reference_leaf_order", None)
+    if order is not None:
+        # a module of this package that registers fewer / differently ordered children than its reference counterpart states
+        # the reference's leaf sequence itself; None stands for a reference leaf that has no counterpart here (a padding or
+        # activation module) and only serves to break adjacency
+        children = order()
     for name, c in children:
-        out += _leaves(c, prefix + (name,))
+        if c is None:
+            out.append((prefix + (name,), None))
+        else:
+            out += _leaves(c, prefix + (name,))
     if not children and not isinstance(module, (nn.Sequential, nn.ModuleList)) and not hasattr(module, "_restricted"):
         out = [(prefix, module)]
     return out
