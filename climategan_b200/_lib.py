@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 ]
 
 F32, BF16, F16 = 0, 1, 2
-ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH, ACT_SIGMOID, ACT_SELU = 0, 1, 2, 3, 4, 5
 PAD_ZERO, PAD_REFLECT = 0, 1
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
 
@@ -124,6 +124,10 @@ SIGNATURES = {
     "cgb_resize_bilinear_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_reflect_pad_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_reflect_pad_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_replicate_pad_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_replicate_pad_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_affine_nc_fwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),
+    "cgb_affine_nc_bwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),
     "cgb_channel_mean_bwd": ([_P, _P, _I, _L, _I, _I, _P], C.c_int),
     "cgb_broadcast_hw": ([_P, _P, _I, _I, _I, _I, _F, _P], C.c_int),
     "cgb_dropout": ([_P, _P, _I, _L, _F, C.c_uint64, _P], C.c_int),

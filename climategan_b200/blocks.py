@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .norms import SPADE, SpectralNorm, conv_weight_bias
+from .norms import SPADE, AdaptiveInstanceNorm2d, LayerNorm, SpectralNorm, conv_weight_bias, instance_norm_act
 
 _ACTS = {
     "relu": (_lib.ACT_RELU, 0.0),
@@ -15,6 +15,8 @@ _ACTS = {
     "tanh": (_lib.ACT_TANH, 0.0),
     "sigmoid": (_lib.ACT_SIGMOID, 0.0),
     "none": (_lib.ACT_NONE, 0.0),
+    "selu": (_lib.ACT_SELU, 0.0),
+    "prelu": (_lib.ACT_NONE, 0.0),   # nn.PReLU(): a learnable slope, applied after the conv / norm (Conv2dBlock._prelu)
 }
 
 
@@ -32,20 +34,24 @@ class InterpolateNearest2d(nn.Module):
 class Conv2dBlock(nn.Module):
     """``climategan.blocks.Conv2dBlock`` (blocks.py:49-147): pad -> conv -> norm -> activation.
 
-    Built so far: pad_type zero/reflect, norm none / spectral, activations relu/lrelu/tanh/sigmoid/none
-    (bias + activation run in the conv epilogue; reflect/zero padding in the conv loader).
+    Every option of the reference: pad_type zero / reflect / replicate; norm none / spectral / batch / instance / layer / adain
+    (and the ``spectral_`` prefixed combinations); activation relu / lrelu / prelu / selu / tanh / sigmoid / none.  On the
+    default path (no norm, or BatchNorm) bias + activation ride in the conv epilogue and the BatchNorm statistics in it too;
+    the MUNIT-era normalisations (instance / layer / adain: no configuration of the reference selects them) run as a moments
+    pass + one per-(sample, channel) affine pass (norms.instance_norm_act, LayerNorm, AdaptiveInstanceNorm2d).
     """
 
     def __init__(self, input_dim, output_dim, kernel_size, stride=1, padding=0, dilation=1, norm="none",
                  activation="relu", pad_type="zero", bias=True):
         super().__init__()
         self.use_bias = bias
+        self.replicate = pad_type == "replicate"
         if pad_type == "reflect":
             self.pad_mode = _lib.PAD_REFLECT
-        elif pad_type == "zero":
+        elif pad_type in ("zero", "replicate"):      # replicate: an explicit padded copy (ops.replicate_pad), then a pad-0 conv
             self.pad_mode = _lib.PAD_ZERO
         else:
-            raise NotImplementedError("Unsupported padding type: {}".format(pad_type))
+            assert 0, "Unsupported padding type: {}".format(pad_type)
         self.padding, self.stride, self.dilation = padding, stride, dilation
         use_spectral_norm = False
         if norm.startswith("spectral_"):
@@ -55,13 +61,20 @@ class Conv2dBlock(nn.Module):
             self.norm = None
         elif norm == "batch":
             self.norm = nn.BatchNorm2d(output_dim)  # eval: folded into the conv (forward_infer); train: batch statistics
+        elif norm == "instance":
+            self.norm = nn.InstanceNorm2d(output_dim)   # affine=False, no running statistics (blocks.py:80-82): holds no state
+        elif norm == "layer":
+            self.norm = LayerNorm(output_dim)
+        elif norm == "adain":
+            self.norm = AdaptiveInstanceNorm2d(output_dim)
         else:
-            raise NotImplementedError("Conv2dBlock norm '{}' is not built yet".format(norm))
+            raise ValueError("Unsupported normalization: {}".format(norm))
+        self.output_dim = output_dim
         self.kernel_size = kernel_size
         if activation not in _ACTS:
-            raise NotImplementedError("Unsupported activation: {}".format(activation))
+            raise ValueError("Unsupported activation: {}".format(activation))
         self.act, self.slope = _ACTS[activation]
-        self.activation = None if activation == "none" else activation
+        self.activation = None if activation == "none" else (nn.PReLU() if activation == "prelu" else activation)
         if norm == "spectral" or use_spectral_norm:   # blocks.py:117-127: the spectral branch keeps the bias even with BatchNorm
             self.conv = SpectralNorm(nn.Conv2d(input_dim, output_dim, kernel_size, stride, dilation=dilation, bias=self.use_bias))
         else:
@@ -87,6 +100,25 @@ class Conv2dBlock(nn.Module):
         if pad_mode == _lib.PAD_REFLECT and pad > 0:
             x = ops.reflect_pad(x, pad)
             pad, pad_mode = 0, _lib.PAD_ZERO
+        elif self.replicate and pad > 0:
+            x = ops.replicate_pad(x, pad)
+            pad = 0
+        prelu = isinstance(self.activation, nn.PReLU)
+        if self.norm is not None and not isinstance(self.norm, nn.BatchNorm2d):
+            # instance / layer / adain: conv (bias in the epilogue) -> moments -> one affine + activation pass
+            y = ops.conv2d(x, w, b, None, stride=self.stride, dil=self.dilation, pad=pad, pad_mode=pad_mode)
+            if isinstance(self.norm, nn.InstanceNorm2d):
+                y = instance_norm_act(y, self.output_dim, self.norm.eps, act=self.act, slope=self.slope)
+            else:
+                y = self.norm(y, act=self.act, slope=self.slope)
+            y = self._prelu(y) if prelu else y
+            return y if residual is None else y + residual
+        if prelu:
+            y = ops.conv2d(x, w, b, None, stride=self.stride, dil=self.dilation, pad=pad, pad_mode=pad_mode)
+            if self.norm is not None:
+                y = ops.batchnorm_act(y, self.norm, None, _lib.ACT_NONE)
+            y = self._prelu(y)
+            return y if residual is None else y + residual
         if self.norm is not None:
             y = ops.conv_bn_act(x, w, self.norm, b, stride=self.stride, dil=self.dilation, pad=pad, pad_mode=pad_mode,
                                 act=self.act, slope=self.slope)
@@ -94,10 +126,22 @@ class Conv2dBlock(nn.Module):
         return ops.conv2d(x, w, b, residual, stride=self.stride, dil=self.dilation, pad=pad, pad_mode=pad_mode,
                           act=self.act, slope=self.slope)
 
+    def _prelu(self, x):
+        """nn.PReLU() (one learnable slope a): max(0, x) + a * min(0, x), as three affine passes so that autograd yields da."""
+        n, cs = x.shape[0], x.shape[-1]
+        one = torch.ones((n, cs), device=x.device)
+        zero = torch.zeros((n, cs), device=x.device)
+        pos = ops.affine_nc(x, one, zero, _lib.ACT_RELU)
+        neg = ops.affine_nc(x, -one, zero, _lib.ACT_RELU)                  # relu(-x) = -min(0, x)
+        return pos + ops.affine_nc(neg, -self.activation.weight.view(1, 1).expand(n, cs), zero)
+
     def forward_infer(self, x, residual=None):
         """Inference forward (no autograd tape): pad -> conv [-> eval BatchNorm folded] -> activation [+ residual]."""
         import torch
 
+        if self.replicate or isinstance(self.activation, nn.PReLU) or (self.norm is not None and not isinstance(self.norm, nn.BatchNorm2d)):
+            with torch.no_grad():     # the options off the default path share the training forward
+                return self.forward(x, residual)
         with torch.no_grad():
             if self.norm is not None and not isinstance(self.conv, SpectralNorm):
                 from .deeplab.resnetmulti_v2 import fold_bn

@@ -127,6 +127,7 @@ __device__ __forceinline__ float act_apply(float v, int act, float slope) {
     case CGB_ACT_LRELU: return v > 0.f ? v : v * slope;
     case CGB_ACT_TANH: return tanhf(v);
     case CGB_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    case CGB_ACT_SELU: return 1.0507009873554804934193349852946f * (v > 0.f ? v : 1.6732632423543772848170429916717f * (__expf(v) - 1.f));
     default: return v;
   }
 }
@@ -137,6 +138,8 @@ __device__ __forceinline__ float act_grad_from_out(float y, int act, float slope
     case CGB_ACT_LRELU: return y > 0.f ? 1.f : slope;
     case CGB_ACT_TANH: return 1.f - y * y;
     case CGB_ACT_SIGMOID: return y * (1.f - y);
+    // selu: y = s*x (x > 0) | s*a*(e^x - 1) (x <= 0)  ->  dy/dx = s | y + s*a
+    case CGB_ACT_SELU: return y > 0.f ? 1.0507009873554804934193349852946f : y + 1.0507009873554804934193349852946f * 1.6732632423543772848170429916717f;
     default: return 1.f;
   }
 }

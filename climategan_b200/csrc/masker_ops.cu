@@ -474,6 +474,136 @@ reflect_pad_bwd_kernel(const T* __restrict__ gy, T* __restrict__ gx, long long t
   }
 }
 
+// nn.ReplicationPad2d(pad), NHWC: forward is a clamped copy, backward a gather over the padding cells that replicate a border pixel
+template <typename T>
+__global__ void __launch_bounds__(256)
+replicate_pad_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long total_vec, int h, int w, int c, int pad) {
+  const int cv = c >> 3;
+  const int hp = h + 2 * pad, wp = w + 2 * pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int v = (int)(i - pix * cv);
+    const int ox = (int)(pix % wp);
+    const long long t = pix / wp;
+    const int oy = (int)(t % hp);
+    const long long img = t / hp;
+    const int sy = min(max(oy - pad, 0), h - 1), sx = min(max(ox - pad, 0), w - 1);
+    float f[8];
+    Vec8<T>::load(x + ((img * h + sy) * w + sx) * c + v * 8, f);
+    Vec8<T>::store(y + pix * c + v * 8, f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+replicate_pad_bwd_kernel(const T* __restrict__ gy, T* __restrict__ gx, long long total_vec, int h, int w, int c, int pad) {
+  const int cv = c >> 3;
+  const int wp = w + 2 * pad, hp = h + 2 * pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int v = (int)(i - pix * cv);
+    const int ix = (int)(pix % w);
+    const long long t = pix / w;
+    const int iy = (int)(t % h);
+    const long long img = t / h;
+    // padded rows / columns that read this pixel
+    const int y0 = iy == 0 ? 0 : iy + pad, y1 = iy == h - 1 ? hp - 1 : iy + pad;
+    const int x0 = ix == 0 ? 0 : ix + pad, x1 = ix == w - 1 ? wp - 1 : ix + pad;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int yy = y0; yy <= y1; ++yy)
+      for (int xx = x0; xx <= x1; ++xx) {
+        float g[8];
+        Vec8<T>::load(gy + ((img * hp + yy) * wp + xx) * c + v * 8, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += g[j];
+      }
+    Vec8<T>::store(gx + pix * c + v * 8, acc);
+  }
+}
+
+// per-(sample, channel) affine + activation (see include/cgb200.h); grid (chunks, n): a thread owns one channel vector
+template <typename T>
+__global__ void __launch_bounds__(256)
+affine_nc_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift, T* __restrict__ y,
+                     int hw, int c, int px_per_chunk, int act, float slope) {
+  const int cv = c >> 3;
+  const int lanes = 256 / cv;
+  const int lane = threadIdx.x / cv, v = threadIdx.x - lane * cv;
+  if (lane >= lanes) return;
+  const int img = blockIdx.y;
+  float A[8], B[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    A[j] = scale[(long long)img * c + v * 8 + j];
+    B[j] = shift[(long long)img * c + v * 8 + j];
+  }
+  const int p0 = blockIdx.x * px_per_chunk;
+  const int p1 = min(hw, p0 + px_per_chunk);
+  const T* xb = x + ((long long)img * hw) * c + v * 8;
+  T* yb = y + ((long long)img * hw) * c + v * 8;
+  for (int p = p0 + lane; p < p1; p += lanes) {
+    float f[8];
+    Vec8<T>::load(xb + (long long)p * c, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = act_apply(fmaf(f[j], A[j], B[j]), act, slope);
+    Vec8<T>::store(yb + (long long)p * c, f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+affine_nc_bwd_kernel(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ gy, const float* __restrict__ scale,
+                     T* __restrict__ gx, double* __restrict__ sums, int hw, int c, int px_per_chunk, int act, float slope) {
+  extern __shared__ float sm[];   // [2][c]
+  const int cv = c >> 3;
+  const int lanes = 256 / cv;
+  const int lane = threadIdx.x / cv, v = threadIdx.x - lane * cv;
+  const int img = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * c; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  if (lane < lanes) {
+    float A[8], s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      A[j] = scale[(long long)img * c + v * 8 + j];
+      s0[j] = s1[j] = 0.f;
+    }
+    const int p0 = blockIdx.x * px_per_chunk;
+    const int p1 = min(hw, p0 + px_per_chunk);
+    const long long base = ((long long)img * hw) * c + v * 8;
+    for (int p = p0 + lane; p < p1; p += lanes) {
+      float xv[8], g[8], o[8];
+      Vec8<T>::load(x + base + (long long)p * c, xv);
+      Vec8<T>::load(gy + base + (long long)p * c, g);
+      if (act != CGB_ACT_NONE) {
+        float yv[8];
+        Vec8<T>::load(y + base + (long long)p * c, yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] *= act_grad_from_out(yv[j], act, slope);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s0[j] += g[j];
+        s1[j] = fmaf(g[j], xv[j], s1[j]);
+        o[j] = g[j] * A[j];
+      }
+      Vec8<T>::store(gx + base + (long long)p * c, o);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sm[v * 8 + j], s0[j]);
+      atomicAdd(&sm[c + v * 8 + j], s1[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += 256) {
+    atomicAdd(&sums[((long long)img * c + i) * 2 + 0], (double)sm[i]);
+    atomicAdd(&sums[((long long)img * c + i) * 2 + 1], (double)sm[c + i]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // torch.mean(z, dim=1, keepdim=True) backward: gx[p, ch<c_logical] = gy[p,0]/c_logical
 template <typename T>
@@ -1060,6 +1190,58 @@ extern "C" int cgb_reflect_pad_bwd(const void* gy, void* gx, int32_t dtype, int3
   DISPATCH_T(dtype, reflect_pad_bwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)gy, (T*)gx, total, h,
                                                                                                 w, c, pad);)
   return after_launch("reflect_pad_bwd");
+}
+
+extern "C" int cgb_replicate_pad_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad,
+                                     void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && y && c % 8 == 0 && c >= 8 && pad >= 0 && h > 0 && w > 0, "replicate_pad_fwd: bad arguments");
+  const long long total = (long long)n * (h + 2 * pad) * (w + 2 * pad) * (c / 8);
+  DISPATCH_T(dtype, replicate_pad_fwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total, h, w, c, pad);)
+  return after_launch("replicate_pad_fwd");
+}
+
+extern "C" int cgb_replicate_pad_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t c,
+                                     int32_t pad, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(gy && gx && c % 8 == 0 && c >= 8 && pad >= 0 && h > 0 && w > 0, "replicate_pad_bwd: bad arguments");
+  const long long total = (long long)n * h * w * (c / 8);
+  DISPATCH_T(dtype, replicate_pad_bwd_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)gy, (T*)gx, total, h, w, c, pad);)
+  return after_launch("replicate_pad_bwd");
+}
+
+static inline int affine_chunks(int n, int hw) {
+  int want = (148 * 8 + n - 1) / n;
+  const int maxc = (hw + 63) / 64;
+  if (want > maxc) want = maxc;
+  return want < 1 ? 1 : want;
+}
+
+extern "C" int cgb_affine_nc_fwd(const void* x, const float* scale, const float* shift, void* y, int32_t dtype, int32_t n,
+                                 int32_t hw, int32_t c, int32_t act, float slope, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && scale && shift && y && n > 0 && hw > 0 && n <= 65535, "affine_nc_fwd: bad arguments");
+  REQ_C(c, "affine_nc_fwd");
+  CGB_REQUIRE(act >= CGB_ACT_NONE && act <= CGB_ACT_SELU, "affine_nc_fwd: unknown activation %d", act);
+  const int chunks = affine_chunks(n, hw);
+  const int ppc = (hw + chunks - 1) / chunks;
+  dim3 grid((hw + ppc - 1) / ppc, n);
+  DISPATCH_T(dtype, affine_nc_fwd_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, scale, shift, (T*)y, hw, c, ppc, act, slope);)
+  return after_launch("affine_nc_fwd");
+}
+
+extern "C" int cgb_affine_nc_bwd(const void* x, const void* y, const void* gy, const float* scale, void* gx, double* sums,
+                                 int32_t dtype, int32_t n, int32_t hw, int32_t c, int32_t act, float slope, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(x && gy && scale && gx && sums && n > 0 && hw > 0 && n <= 65535, "affine_nc_bwd: bad arguments");
+  CGB_REQUIRE(act == CGB_ACT_NONE || y, "affine_nc_bwd: y is required when an activation is fused");
+  REQ_C(c, "affine_nc_bwd");
+  const int chunks = affine_chunks(n, hw);
+  const int ppc = (hw + chunks - 1) / chunks;
+  dim3 grid((hw + ppc - 1) / ppc, n);
+  DISPATCH_T(dtype, affine_nc_bwd_kernel<T><<<grid, 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
+                        (const T*)x, (const T*)y, (const T*)gy, scale, (T*)gx, sums, hw, c, ppc, act, slope);)
+  return after_launch("affine_nc_bwd");
 }
 
 extern "C" int cgb_channel_mean_bwd(const void* gy, void* gx, int32_t dtype, int64_t pixels, int32_t cs, int32_t c_logical,

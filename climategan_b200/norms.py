@@ -14,6 +14,79 @@ def l2normalize(v, eps=1e-12):
     return v / (v.norm() + eps)
 
 
+def _pad_c(t, cs):
+    """[.., C] -> [.., Cs] zero padded (pad channels of a storage tensor must stay zero: scale = shift = 0 there)."""
+    return t if t.shape[-1] == cs else torch.nn.functional.pad(t, (0, cs - t.shape[-1]))
+
+
+def instance_norm_act(x, c, eps=1e-5, weight=None, bias=None, act=_lib.ACT_NONE, slope=0.2):
+    """act(instance_norm(x) [* weight[n, c] + bias[n, c]]) on a storage tensor with c logical channels: biased variance, eps
+    inside the square root (nn.InstanceNorm2d / F.batch_norm in training mode).  The statistics -> scale / shift algebra runs
+    on [N, C] tensors under autograd; the tensor-sized work is one moments pass and one affine pass (ops.moments / affine_nc)."""
+    cs = x.shape[-1]
+    m1, m2 = ops.moments(x)
+    var = (m2 - m1 * m1).clamp_min(0.0)
+    scale = torch.rsqrt(var + eps)
+    shift = -m1 * scale
+    if weight is not None:
+        w, b = _pad_c(weight.view(x.shape[0], -1), cs), _pad_c(bias.view(x.shape[0], -1), cs)
+        scale, shift = scale * w, shift * w + b
+    live = (torch.arange(cs, device=x.device) < c).to(scale.dtype)
+    return ops.affine_nc(x, scale * live, shift * live, act, slope)
+
+
+class AdaptiveInstanceNorm2d(nn.Module):
+    """``climategan.norms.AdaptiveInstanceNorm2d`` (norms.py:8-46): instance norm whose per-(sample, channel) ``weight`` /
+    ``bias`` ([B*C] tensors) are assigned from outside before the call; same dummy ``running_mean`` / ``running_var`` buffers
+    (state_dict surface)."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1):
+        super().__init__()
+        self.num_features = num_features
+        self.eps = eps
+        self.momentum = momentum
+        self.weight = None
+        self.bias = None
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features))
+
+    def forward(self, x, act=_lib.ACT_NONE, slope=0.2):
+        assert self.weight is not None and self.bias is not None, "Please assign weight and bias before calling AdaIN!"
+        return instance_norm_act(x, self.num_features, self.eps, self.weight, self.bias, act, slope)
+
+    def __repr__(self):
+        return self.__class__.__name__ + "(" + str(self.num_features) + ")"
+
+
+class LayerNorm(nn.Module):
+    """``climategan.norms.LayerNorm`` (norms.py:49-81; MUNIT's): per-SAMPLE mean and UNBIASED standard deviation over (C, H, W),
+    ``(x - mean) / (std + eps)`` — eps outside the square root — then a per-channel ``gamma`` / ``beta``."""
+
+    def __init__(self, num_features, eps=1e-5, affine=True):
+        super().__init__()
+        self.num_features = num_features
+        self.affine = affine
+        self.eps = eps
+        if self.affine:
+            self.gamma = nn.Parameter(torch.Tensor(num_features).uniform_())
+            self.beta = nn.Parameter(torch.zeros(num_features))
+
+    def forward(self, x, act=_lib.ACT_NONE, slope=0.2):
+        n, h, w, cs = x.shape
+        c = self.num_features
+        m1, m2 = ops.moments(x)
+        mu = m1[:, :c].mean(1, keepdim=True)                     # every channel has the same pixel count
+        e2 = m2[:, :c].mean(1, keepdim=True)
+        cnt = float(c * h * w)
+        var = ((e2 - mu * mu) * (cnt / max(cnt - 1.0, 1.0))).clamp_min(0.0)   # torch.std: unbiased
+        inv = 1.0 / (torch.sqrt(var) + self.eps)
+        scale = inv.expand(n, c)
+        shift = (-mu * inv).expand(n, c)
+        if self.affine:
+            scale, shift = scale * self.gamma.view(1, c), shift * self.gamma.view(1, c) + self.beta.view(1, c)
+        return ops.affine_nc(x, _pad_c(scale, cs), _pad_c(shift, cs), act, slope)
+
+
 class SpectralNorm(nn.Module):
     """Drop-in for ``climategan.norms.SpectralNorm`` (norms.py:84-143).
 

@@ -1155,6 +1155,94 @@ def _dropout_raw(x, p, seed):
     return y
 
 
+class _ReplicatePad(Function):
+    @staticmethod
+    def forward(ctx, x, pad):
+        _chk_storage(x)
+        n, h, w, c = x.shape
+        y = torch.empty((n, h + 2 * pad, w + 2 * pad, c), dtype=x.dtype, device=x.device)
+        check(_L().cgb_replicate_pad_fwd(_p(x), _p(y), _DT[x.dtype], n, h, w, c, pad, _st()), "replicate_pad_fwd")
+        ctx.meta = (n, h, w, c, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        n, h, w, c, pad = ctx.meta
+        gy = gy.contiguous()
+        gx = torch.empty((n, h, w, c), dtype=gy.dtype, device=gy.device)
+        check(_L().cgb_replicate_pad_bwd(_p(gy), _p(gx), _DT[gy.dtype], n, h, w, c, pad, _st()), "replicate_pad_bwd")
+        return gx, None
+
+
+def replicate_pad(x, pad):
+    """nn.ReplicationPad2d(pad) (blocks.py:68-69) as an explicit padded copy; the conv that follows runs with pad 0."""
+    return x if pad == 0 else _ReplicatePad.apply(x, pad)
+
+
+class _AffineNC(Function):
+    """y = act(x * scale[n, c] + shift[n, c]) on a storage tensor; differentiable w.r.t. x, scale and shift."""
+
+    @staticmethod
+    def forward(ctx, x, scale, shift, act, slope):
+        _chk_storage(x)
+        n, h, w, c = x.shape
+        scale, shift = scale.contiguous().float(), shift.contiguous().float()
+        assert scale.shape == (n, c) and shift.shape == (n, c), (scale.shape, shift.shape, x.shape)
+        y = torch.empty_like(x)
+        check(_L().cgb_affine_nc_fwd(_p(x), _p(scale), _p(shift), _p(y), _DT[x.dtype], n, h * w, c, act, slope, _st()), "affine_nc_fwd")
+        ctx.save_for_backward(x, scale, y if act != _lib.ACT_NONE else None)
+        ctx.meta = (act, slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, scale, y = ctx.saved_tensors
+        act, slope = ctx.meta
+        n, h, w, c = x.shape
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        sums = torch.zeros((n, c, 2), dtype=torch.float64, device=x.device)
+        check(_L().cgb_affine_nc_bwd(_p(x), _p(y), _p(gy), _p(scale), _p(gx), _p(sums), _DT[x.dtype], n, h * w, c, act, slope, _st()),
+              "affine_nc_bwd")
+        sf = sums.float()
+        return gx, sf[..., 1].contiguous(), sf[..., 0].contiguous(), None, None
+
+
+def affine_nc(x, scale, shift, act=_lib.ACT_NONE, slope=0.2):
+    """Per-(sample, channel) affine map + activation (cgb_affine_nc_fwd / _bwd); scale, shift: fp32 [N, Cs]."""
+    return _AffineNC.apply(x, scale, shift, act, slope)
+
+
+class _Moments(Function):
+    """Per-(sample, channel) first and second moments E[x], E[x^2] over the pixels of a storage tensor (fp32 [N, Cs] each).
+    Backward: gx = (g1 + 2 x g2) / HW — one cgb_affine_nc_fwd pass."""
+
+    @staticmethod
+    def forward(ctx, x):
+        _chk_storage(x)
+        mean, rstd = instnorm_stats(x, 0.0)
+        var = torch.where(torch.isfinite(rstd), 1.0 / (rstd * rstd), torch.zeros_like(rstd))   # (a constant channel: var = 0)
+        ctx.save_for_backward(x)
+        return mean, var + mean * mean
+
+    @staticmethod
+    def backward(ctx, g1, g2):
+        (x,) = ctx.saved_tensors
+        n, h, w, c = x.shape
+        inv = 1.0 / (h * w)
+        g1 = torch.zeros((n, c), device=x.device) if g1 is None else g1
+        g2 = torch.zeros((n, c), device=x.device) if g2 is None else g2
+        gx = torch.empty_like(x)
+        scale, shift = (2.0 * inv * g2).float().contiguous(), (inv * g1).float().contiguous()
+        check(_L().cgb_affine_nc_fwd(_p(x), _p(scale), _p(shift), _p(gx), _DT[x.dtype], n, h * w, c, _lib.ACT_NONE, 0.0, _st()),
+              "affine_nc_fwd")
+        return gx
+
+
+def moments(x):
+    return _Moments.apply(x)
+
+
 class _Dropout(Function):
     @staticmethod
     def forward(ctx, x, p, seed):

@@ -46,7 +46,8 @@ typedef enum {
   CGB_ACT_RELU = 1,
   CGB_ACT_LRELU = 2, /* slope given separately (0.2 everywhere in the reference) */
   CGB_ACT_TANH = 3,
-  CGB_ACT_SIGMOID = 4
+  CGB_ACT_SIGMOID = 4,
+  CGB_ACT_SELU = 5     /* nn.SELU (Conv2dBlock activation="selu", blocks.py:97-98); elementwise kernels only */
 } cgb_act;
 
 typedef enum { CGB_PAD_ZERO = 0, CGB_PAD_REFLECT = 1 } cgb_pad_mode;
@@ -275,6 +276,22 @@ int cgb_reflect_pad_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_
 int cgb_reflect_pad_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad,
                         void* stream);
 int cgb_channel_mean_bwd(const void* gy, void* gx, int32_t dtype, int64_t pixels, int32_t cs, int32_t c_logical, void* stream);
+/* nn.ReplicationPad2d(pad) (Conv2dBlock pad_type="replicate", blocks.py:68-69) as an explicit copy, and its adjoint (every
+ * border pixel gathers the gradients of the padding cells that replicate it; deterministic, no atomics). */
+int cgb_replicate_pad_fwd(const void* x, void* y, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad,
+                          void* stream);
+int cgb_replicate_pad_bwd(const void* gy, void* gx, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad,
+                          void* stream);
+/* Per-(sample, channel) affine map + activation, the building block of the Conv2dBlock normalisations that are not on the
+ * default path (norm = "instance" / "layer" / "adain", blocks.py:77-90; norms.py:8-49,51-81): the caller turns per-(n, c)
+ * moments into scale / shift with a few [n, c]-sized tensor ops and this kernel applies them in one pass.
+ *   fwd: y[n,p,ch] = act(x[n,p,ch] * scale[n,ch] + shift[n,ch])                       scale, shift: fp32 [n, c]
+ *   bwd: gpre = gy * act'(y) ; gx = gpre * scale ; sums[n][ch][0] += sum_p gpre ; sums[n][ch][1] += sum_p gpre * x
+ *        (sums fp64 [n, c, 2], zeroed by the caller: the gradients w.r.t. shift and scale). */
+int cgb_affine_nc_fwd(const void* x, const float* scale, const float* shift, void* y, int32_t dtype, int32_t n, int32_t hw,
+                      int32_t c, int32_t act, float slope, void* stream);
+int cgb_affine_nc_bwd(const void* x, const void* y, const void* gy, const float* scale, void* gx, double* sums, int32_t dtype,
+                      int32_t n, int32_t hw, int32_t c, int32_t act, float slope, void* stream);
 int cgb_broadcast_hw(const void* src, void* dst, int32_t dtype, int32_t n, int32_t hw, int32_t c, float scale, void* stream);
 int cgb_dropout(const void* x, void* y, int32_t dtype, int64_t count, float p, uint64_t seed, void* stream);
 /* Same, the seed read from device memory at execution time: a launch captured in a CUDA graph draws a fresh mask on every

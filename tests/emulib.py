@@ -50,6 +50,8 @@ def _act(x, act, slope):
         return F.leaky_relu(x, slope)
     if act == 3:
         return torch.tanh(x)
+    if act == 5:
+        return F.selu(x)
     return torch.sigmoid(x)
 
 
@@ -62,6 +64,9 @@ def _dact_from_out(y, act, slope):
         return torch.where(y > 0, torch.ones_like(y), torch.full_like(y, slope))
     if act == 3:
         return 1 - y * y
+    if act == 5:
+        sc, al = 1.0507009873554804934193349852946, 1.6732632423543772848170429916717
+        return torch.where(y > 0, torch.full_like(y, sc), y + sc * al)
     return y * (1 - y)
 
 
@@ -435,6 +440,31 @@ class EmuLib(NoopLib):
         dt = _DT[dtype]
         g = self._vjp(lambda X: F.pad(X, (pad,) * 4, mode="reflect"), torch.zeros(n, c, h, w), self._nchw(gy, n, h + 2 * pad, w + 2 * pad, c, dt))
         _t(gx, (n, h, w, c), dt).copy_(g.permute(0, 2, 3, 1))
+
+    def e_replicate_pad_fwd(self, x, y, dtype, n, h, w, c, pad, stream):
+        dt = _DT[dtype]
+        _t(y, (n, h + 2 * pad, w + 2 * pad, c), dt).copy_(F.pad(self._nchw(x, n, h, w, c, dt), (pad,) * 4, mode="replicate").permute(0, 2, 3, 1))
+
+    def e_replicate_pad_bwd(self, gy, gx, dtype, n, h, w, c, pad, stream):
+        dt = _DT[dtype]
+        g = self._vjp(lambda X: F.pad(X, (pad,) * 4, mode="replicate"), torch.zeros(n, c, h, w), self._nchw(gy, n, h + 2 * pad, w + 2 * pad, c, dt))
+        _t(gx, (n, h, w, c), dt).copy_(g.permute(0, 2, 3, 1))
+
+    def e_affine_nc_fwd(self, x, scale, shift, y, dtype, n, hw, c, act, slope, stream):
+        dt = _DT[dtype]
+        X = _t(x, (n, hw, c), dt).float()
+        out = _act(X * _t(scale, (n, 1, c), torch.float32) + _t(shift, (n, 1, c), torch.float32), act, slope)
+        _t(y, (n, hw, c), dt).copy_(out)
+
+    def e_affine_nc_bwd(self, x, y, gy, scale, gx, sums, dtype, n, hw, c, act, slope, stream):
+        dt = _DT[dtype]
+        X, G = _t(x, (n, hw, c), dt).float(), _t(gy, (n, hw, c), dt).float()
+        if act != 0:
+            G = G * _dact_from_out(_t(y, (n, hw, c), dt).float(), act, slope)
+        _t(gx, (n, hw, c), dt).copy_(G * _t(scale, (n, 1, c), torch.float32))
+        S = _t(sums, (n, c, 2), torch.float64)
+        S[..., 0] += G.double().sum(1)
+        S[..., 1] += (G.double() * X.double()).sum(1)
 
     @staticmethod
     def _pool(X, pad, ho):

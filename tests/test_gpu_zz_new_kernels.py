@@ -109,3 +109,60 @@ def test_trainer_eval_images(cuda):
     from tests.test_eval_metrics import check_trainer_eval_images
 
     check_trainer_eval_images(cuda)
+
+
+# ---- round 2: per-(sample, channel) affine + activation, replicate padding, SELU (Conv2dBlock options off the default path)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("act", [_lib.ACT_NONE, _lib.ACT_RELU, _lib.ACT_LRELU, _lib.ACT_TANH, _lib.ACT_SELU])
+def test_affine_nc_fwd_bwd(cuda, dtype, act):
+    import torch.nn.functional as F
+
+    torch.manual_seed(act + 1)
+    n, c, h, w = 3, 24, 19, 23
+    q = lambda t: t.to(dtype).float()  # noqa: E731
+    x = q(torch.randn(n, c, h, w))
+    sc, sh = torch.randn(n, c) * 0.5 + 1, torch.randn(n, c)
+    gy = q(torch.randn(n, c, h, w))
+    fn = {_lib.ACT_NONE: lambda t: t, _lib.ACT_RELU: F.relu, _lib.ACT_LRELU: lambda t: F.leaky_relu(t, 0.2), _lib.ACT_TANH: torch.tanh,
+          _lib.ACT_SELU: F.selu}[act]
+    xr, scr, shr = x.double().requires_grad_(True), sc.double().requires_grad_(True), sh.double().requires_grad_(True)
+    yr = fn(xr * scr.view(n, c, 1, 1) + shr.view(n, c, 1, 1))
+    yr.backward(gy.double())
+    xs = ops.to_storage(x.to(cuda), dtype).requires_grad_(True)
+    scg, shg = sc.to(cuda).requires_grad_(True), sh.to(cuda).requires_grad_(True)
+    y = ops.from_storage(ops.affine_nc(xs, scg, shg, act, 0.2), c)
+    y.backward(gy.to(cuda))
+    tol = 2e-5 if dtype == torch.float32 else 1.5e-2
+    assert rel_max(y, yr) < tol
+    assert rel_max(ops.from_storage(xs.grad, c), xr.grad) < tol
+    assert rel_max(scg.grad, scr.grad) < tol and rel_max(shg.grad, shr.grad) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_moments_and_replicate_pad(cuda, dtype):
+    import torch.nn.functional as F
+
+    torch.manual_seed(9)
+    n, c, h, w, pad = 2, 16, 13, 10, 2
+    x = torch.randn(n, c, h, w).to(dtype).float()
+    xr = x.double().requires_grad_(True)
+    m1r, m2r = xr.mean((2, 3)), (xr * xr).mean((2, 3))
+    g1, g2 = torch.randn(n, c), torch.randn(n, c)
+    (m1r * g1.double()).sum().backward(retain_graph=True)
+    (m2r * g2.double()).sum().backward()
+    xs = ops.to_storage(x.to(cuda), dtype).requires_grad_(True)
+    m1, m2 = ops.moments(xs)
+    ((m1 * g1.to(cuda)).sum() + (m2 * g2.to(cuda)).sum()).backward()
+    tol = 2e-5 if dtype == torch.float32 else 1.5e-2
+    assert rel_max(m1, m1r) < 1e-5 and rel_max(m2, m2r) < 1e-5
+    assert rel_max(ops.from_storage(xs.grad, c), xr.grad) < tol
+    # replicate pad forward / adjoint
+    xr2 = x.double().requires_grad_(True)
+    yr = F.pad(xr2, (pad,) * 4, mode="replicate")
+    gy = torch.randn_like(yr).to(dtype).double()
+    yr.backward(gy)
+    xs2 = ops.to_storage(x.to(cuda), dtype).requires_grad_(True)
+    y = ops.from_storage(ops.replicate_pad(xs2, pad), c)
+    assert rel_max(y, yr) == 0.0
+    y.backward(gy.float().to(cuda))
+    assert rel_max(ops.from_storage(xs2.grad, c), xr2.grad) < tol
