@@ -35,6 +35,8 @@ def parse_args():
     p.add_argument("--no_cloudy", action="store_true", default=False)
     p.add_argument("--keep_ratio_128", action="store_true", default=False)
     p.add_argument("--fuse", action="store_true", default=False)
+    p.add_argument("--cpu_preprocess", action="store_true", default=False,
+                   help="resize / crop on the host with PIL instead of on the GPU (not a reference flag)")
     p.add_argument("--save_masks", action="store_true", default=False)
     p.add_argument("-m", "--max_im_width", type=int, default=-1)
     p.add_argument("--upload", action="store_true")
@@ -61,8 +63,21 @@ def to_128(h, w, w_max=-1):
     return max(128, round(h / 128) * 128), max(128, round(w / 128) * 128)
 
 
+def read_image_u8(path):
+    """The decoded photograph, uint8 HWC RGB (RGBA is composited on white like skimage.color.rgba2rgb, apply_events.py:491)."""
+    import numpy as np
+    from PIL import Image
+
+    im = Image.open(path)
+    if im.mode == "RGBA":
+        bg = Image.new("RGBA", im.size, (255, 255, 255, 255))
+        im = Image.alpha_composite(bg, im)
+    return np.asarray(im.convert("RGB"), dtype=np.uint8)
+
+
 def load_image(path, target, keep_ratio, max_w):
-    """-> float32 HWC in [-1, 1] (utils.resize_and_crop / to_m1_p1 semantics: short side to `target`, centre crop)."""
+    """HOST version of the input edge (PIL), kept for --cpu_preprocess: -> float32 HWC in [-1, 1] (resize_and_crop / to_m1_p1
+    semantics: short side to `target`, centre crop).  The default path resizes on the GPU (events.InputEdge)."""
     import numpy as np
     from PIL import Image
 
@@ -116,7 +131,17 @@ def main():
     elif args.n_images > len(paths):
         paths = (base * (args.n_images // len(base) + 1))[: args.n_images]
     t0 = time.perf_counter()
-    data = [load_image(p, args.target_size, args.keep_ratio_128, args.max_im_width) for p in paths]
+    if args.cpu_preprocess:
+        data = [load_image(p, args.target_size, args.keep_ratio_128, args.max_im_width) for p in paths]
+        sizes = [d.shape[:2] for d in data]
+    else:
+        # decode on the host, resize / crop / rescale on the GPU (events.InputEdge: one kernel per image, pinned double-buffered H2D)
+        from climategan_b200.events import InputEdge
+
+        edge = InputEdge(trainer.device)
+        data = [read_image_u8(p) for p in paths]
+        sizes = [to_128(d.shape[0], d.shape[1], args.max_im_width) if args.keep_ratio_128 else (args.target_size, args.target_size)
+                 for d in data]
     t_pre = time.perf_counter() - t0
     print("Found", len(base), "images. Inferring on", len(data), "images.")
 
@@ -125,13 +150,17 @@ def main():
     i = 0
     while i < len(data):
         j = i
-        while j < len(data) and j - i < args.batch_size and data[j].shape == data[i].shape:
+        while j < len(data) and j - i < args.batch_size and sizes[j] == sizes[i]:
             j += 1
-        images = np.stack(data[i:j])
+        if args.cpu_preprocess:
+            images = np.stack(data[i:j])
+        else:
+            images = edge(data[i:j], args.target_size, keep_ratio_sizes=sizes[i:j] if args.keep_ratio_128 else None)
         ev = trainer.infer_all(images, numpy=True, bin_value=args.flood_mask_binarization, half=args.half,
                                cloudy=not args.no_cloudy, return_masks=args.save_masks)
         if args.save_input:
-            ev["input"] = ((images + 1) / 2 * 255).astype(np.uint8)
+            src = images if args.cpu_preprocess else images.permute(0, 2, 3, 1).cpu().numpy()
+            ev["input"] = ((src + 1) / 2 * 255).astype(np.uint8)
         all_events.append(ev)
         i = j
     torch.cuda.synchronize()
@@ -143,7 +172,7 @@ def main():
             names = [n for n in ev if ev[n] is not None]
             for b in range(len(ev[names[0]])):
                 stem = Path(paths[k % len(paths)]).stem
-                width = data[k].shape[1]
+                width = sizes[k][1]
                 suffix = ("_AR" if args.keep_ratio_128 else "") + ("_no_cloudy" if args.no_cloudy else "")
                 for name in names:
                     im = ev[name][b]

@@ -415,6 +415,12 @@ def build_full(args, dev, rank, world, dtype):
 
     h2d = int(sum(v.numel() * v.element_size() for d in host.values() for v in d.values()))
     step.trainer = t
+
+    def host_batches(count):   # what zip(*loaders) yields: pinned host batches (the same synthetic batch every step)
+        for _ in range(count):
+            yield [{dom: {"data": dict(d), "domain": [dom] * B, "mode": ["train"] * B, "paths": {}} for dom, d in host.items()}]
+
+    step.host_batches = host_batches
     return step, to_dev, h2d, FULL_STEP_GFLOP if args.workload == "full" else MASKER_STEP_GFLOP
 
 
@@ -523,11 +529,23 @@ def main():
     # ---- end-to-end through the public API with host buffers
     e2e = None
     if not args.no_e2e:
-        def e2e_step():
-            res = step(*to_dev(True))    # H2D of this step's inputs from pinned host memory
-            if isinstance(res, torch.Tensor):
-                return float(res.sum().item()) if res.numel() > 1 else float(res.item())   # D2H read of the step result
-            return int(res[0, 0, 0, 0])  # infer: the uint8 NHWC events were already copied to the host by infer_all
+        host_batches = getattr(step, "host_batches", None)
+        if host_batches is not None:
+            # the train workloads: every step's batch goes pinned host -> device through climategan_b200.data.DevicePrefetcher
+            # (side-stream copy two batches deep, the loader edge of data.py:506-539 / trainer.py:609-621), INSIDE the timed region
+            from climategan_b200.data import DevicePrefetcher
+
+            feed = DevicePrefetcher(host_batches(2 * args.steps + 4), dev, depth=2)
+
+            def e2e_step():
+                res = step(*next(feed))
+                return float(res.item())                                                   # D2H read of the step result
+        else:
+            def e2e_step():
+                res = step(*to_dev(True))    # H2D of this step's inputs from pinned host memory
+                if isinstance(res, torch.Tensor):
+                    return float(res.sum().item()) if res.numel() > 1 else float(res.item())   # D2H read of the step result
+                return int(res[0, 0, 0, 0])  # infer: the uint8 NHWC events were already copied to the host by infer_all
 
         e2e_step()
         e2e_ms = timed(e2e_step, args.steps) / args.steps

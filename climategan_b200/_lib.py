@@ -158,6 +158,7 @@ SIGNATURES = {
     "cgb_perlin_noise": ([_P, _P, _I, _I, _I, _I, _P], C.c_int),
     "cgb_cloudy_mix": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _F, _P], C.c_int),
     "cgb_to_uint8_nhwc": ([_P, _P, _P, _I, _I, _P], C.c_int),
+    "cgb_resize_crop_u8": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_mask_to_uint8": ([_P, _P, _F, _L, _P], C.c_int),
     "cgb_resize_nearest_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_upsample_nearest_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),

@@ -428,6 +428,61 @@ extern "C" int cgb_smog(const float* x, const float* mmx, const float* d, const 
   return after_launch("smog");
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Input edge of apply_events.py (resize_and_crop :211-241, to_m1_p1 :179-195; transforms.PrepareInference :292-360): a uint8 HWC
+// photograph of any size -> anti-aliased bilinear resize (triangle filter widened by the down-scale factor: what
+// F.interpolate(mode="bilinear", antialias=True, align_corners=False) computes) to (rh, rw) -> crop of size (th, tw) at
+// (top, left) -> optional truncation to uint8 (the reference quantises the resized image, :231) -> (v/255 - 0.5)*2 written
+// into image slot `img` of an NCHW fp32 batch.  One thread per output pixel; the taps of a pixel are read as 3-byte HWC
+// triples (neighbouring threads read neighbouring source pixels).  The CPU did this in the reference (skimage).
+__global__ void __launch_bounds__(256)
+resize_crop_u8_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, int h, int w, int rh, int rw, int top, int left,
+                      int th, int tw, int quantize) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= th * tw) return;
+  const int oy = idx / tw, ox = idx - oy * tw;
+  const float sy = (float)h / (float)rh, sx = (float)w / (float)rw;
+  const float supy = fmaxf(sy, 1.f), supx = fmaxf(sx, 1.f);
+  const float cy = ((float)(oy + top) + 0.5f) * sy, cx = ((float)(ox + left) + 0.5f) * sx;   // centre in source pixel-edge units
+  const int y0 = max((int)(cy - supy + 0.5f), 0), y1 = min((int)(cy + supy + 0.5f), h);
+  const int x0 = max((int)(cx - supx + 0.5f), 0), x1 = min((int)(cx + supx + 0.5f), w);
+  float acc[3] = {0.f, 0.f, 0.f}, wsum = 0.f;
+  for (int yy = y0; yy < y1; ++yy) {
+    const float wy = fmaxf(0.f, 1.f - fabsf(((float)yy + 0.5f - cy) / supy));
+    if (wy == 0.f) continue;
+    const uint8_t* row = src + ((long long)yy * w) * 3;
+    float racc[3] = {0.f, 0.f, 0.f}, rw_ = 0.f;
+    for (int xx = x0; xx < x1; ++xx) {
+      const float wx = fmaxf(0.f, 1.f - fabsf(((float)xx + 0.5f - cx) / supx));
+      racc[0] = fmaf(wx, (float)row[xx * 3 + 0], racc[0]);
+      racc[1] = fmaf(wx, (float)row[xx * 3 + 1], racc[1]);
+      racc[2] = fmaf(wx, (float)row[xx * 3 + 2], racc[2]);
+      rw_ += wx;
+    }
+    acc[0] = fmaf(wy, racc[0], acc[0]);
+    acc[1] = fmaf(wy, racc[1], acc[1]);
+    acc[2] = fmaf(wy, racc[2], acc[2]);
+    wsum = fmaf(wy, rw_, wsum);
+  }
+  const float inv = wsum > 0.f ? 1.f / wsum : 0.f;
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    float v = acc[ch] * inv;
+    if (quantize) v = floorf(fminf(fmaxf(v, 0.f), 255.f));
+    dst[(long long)ch * th * tw + idx] = (v * (1.f / 255.f) - 0.5f) * 2.f;
+  }
+}
+
+extern "C" int cgb_resize_crop_u8(const uint8_t* src, float* dst, int32_t h, int32_t w, int32_t rh, int32_t rw, int32_t top,
+                                  int32_t left, int32_t th, int32_t tw, int32_t quantize, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(src && dst && h > 0 && w > 0 && rh > 0 && rw > 0 && th > 0 && tw > 0, "resize_crop_u8: bad arguments");
+  CGB_REQUIRE(top >= 0 && left >= 0 && top + th <= rh && left + tw <= rw, "resize_crop_u8: the crop [%d:%d, %d:%d] leaves the resized image %dx%d",
+              top, top + th, left, left + tw, rh, rw);
+  resize_crop_u8_kernel<<<(th * tw + 255) / 256, 256, 0, (cudaStream_t)stream>>>(src, dst, h, w, rh, rw, top, left, th, tw, quantize);
+  return after_launch("resize_crop_u8");
+}
+
 extern "C" int cgb_to_uint8_nhwc(const float* x, const float* mm, uint8_t* out, int32_t n, int32_t hw, void* stream) {
   CGB_CHECK_DEVICE();
   CGB_REQUIRE(x && mm && out && n > 0 && hw > 0, "to_uint8_nhwc: bad arguments");

@@ -85,6 +85,66 @@ def add_smog(x, d, smog_opts):
     return out
 
 
+def resize_and_crop_size(h, w, to):
+    """apply_events.py:223-239: the resized shape (short side = ``to``, aspect ratio kept, ``int()`` truncation as there) and
+    the centred crop offsets."""
+    rh, rw = (to, int(to * w / h)) if h < w else (int(to * h / w), to)
+    return rh, rw, (rh - to) // 2, (rw - to) // 2
+
+
+class InputEdge:
+    """uint8 HWC photographs -> one NCHW fp32 batch in [-1, 1] on the device: the pre-processing of ``apply_events.py``
+    (:487-502: ``resize_and_crop`` + ``to_m1_p1``, or the ``--keep_ratio_128`` resize) as ONE kernel per image fed from pinned,
+    double-buffered host staging (the H2D copy of image i+1 overlaps the kernel of image i on the same stream's copy engine)."""
+
+    def __init__(self, device, quantize=True):
+        self.device = device
+        self.quantize = 1 if quantize else 0
+        self._stage = [None, None]
+        self._dev = [None, None]
+        self._copied = [None, None]     # event recorded after the H2D copy out of each pinned buffer
+        self._k = 0
+
+    def _buffers(self, nbytes):
+        k = self._k
+        self._k ^= 1
+        if self._copied[k] is not None:
+            self._copied[k].synchronize()   # the copy that last read this pinned buffer has finished: the host may overwrite it
+        if self._stage[k] is None or self._stage[k].numel() < nbytes:
+            self._stage[k] = torch.empty(nbytes, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+            self._dev[k] = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._stage[k], self._dev[k], k
+
+    def __call__(self, images, target=640, keep_ratio_sizes=None):
+        """images: list of uint8 [h, w, 3] numpy arrays / tensors.  ``keep_ratio_sizes``: per-image (H, W) for the
+        ``--keep_ratio_128`` mode (plain resize, no crop; all images of a batch must share it); otherwise resize_and_crop to
+        ``target``.  Returns fp32 [N, 3, T, T] (or [N, 3, H, W])."""
+        import numpy as np
+
+        if keep_ratio_sizes is not None:
+            assert len(set(keep_ratio_sizes)) == 1, "a batch needs one output size"
+            th, tw = keep_ratio_sizes[0]
+        else:
+            th = tw = target
+        out = torch.empty((len(images), 3, th, tw), dtype=torch.float32, device=self.device)
+        for i, im in enumerate(images):
+            a = torch.from_numpy(np.ascontiguousarray(im)) if not isinstance(im, torch.Tensor) else im.contiguous()
+            assert a.dtype == torch.uint8 and a.dim() == 3 and a.shape[2] == 3, (a.dtype, a.shape)
+            h, w = int(a.shape[0]), int(a.shape[1])
+            if keep_ratio_sizes is not None:
+                rh, rw, top, left = th, tw, 0, 0
+            else:
+                rh, rw, top, left = resize_and_crop_size(h, w, target)
+            host, dev, k = self._buffers(a.numel())
+            host[: a.numel()].copy_(a.reshape(-1))
+            dev[: a.numel()].copy_(host[: a.numel()], non_blocking=True)
+            if torch.cuda.is_available():
+                self._copied[k] = torch.cuda.Event()
+                self._copied[k].record()
+            check(_L().cgb_resize_crop_u8(_p(dev), _p(out[i]), h, w, rh, rw, top, left, th, tw, self.quantize, _st()), "resize_crop_u8")
+        return out
+
+
 def to_uint8_nhwc(t):
     """normalize(t) -> permute(0,2,3,1) -> (t*255).astype(uint8) (trainer.py:312-327) as one device kernel: uint8 [N,H,W,3]."""
     t = _img(t)

@@ -388,6 +388,11 @@ int cgb_perlin_noise(const float* angles, float* out, int32_t h, int32_t w, int3
 int cgb_cloudy_mix(const float* x, const float* seg, const float* noise, const float* mm_noise, float* out, int32_t n, int32_t h,
                    int32_t w, int32_t c, int32_t hs, int32_t ws, int32_t sky_idx, float weight, void* stream);
 int cgb_to_uint8_nhwc(const float* x, const float* mm, uint8_t* out, int32_t n, int32_t hw, void* stream);
+/* Input edge (apply_events.py resize_and_crop :211-241 + to_m1_p1 :179-195; transforms.PrepareInference :292-360, skimage on the
+ * CPU in the reference): src uint8 [h, w, 3] -> anti-aliased bilinear resize to (rh, rw) -> crop (th, tw) at (top, left) ->
+ * optional truncation to uint8 (:231) -> (v/255 - 0.5)*2 into dst fp32 [3, th, tw] (one image slot of an NCHW batch). */
+int cgb_resize_crop_u8(const uint8_t* src, float* dst, int32_t h, int32_t w, int32_t rh, int32_t rw, int32_t top, int32_t left,
+                       int32_t th, int32_t tw, int32_t quantize, void* stream);
 int cgb_mask_to_uint8(const float* m, uint8_t* out, float bin_value, int64_t count, void* stream);
 
 /* ---- layout / elementwise ----------------------------------------------------------------

@@ -1,10 +1,12 @@
-"""GPU tests of the entry points written after the round's GPU budget was spent (they have not run on hardware yet).  The
-file sorts last on purpose: the suite is run with -x, and a first-run failure here must not hide the validated tests before it.
-Each kernel is also pinned on CPU through the emulated ABI (tests/test_emulated.py)."""
+"""GPU tests of the smaller entry points off the default train path (reverse-Huber depth loss, one-launch weight packing,
+argmax-confusion metrics, diff-augment: green on B200 since round 1's driver run; per-(sample, channel) affine, moments,
+replicate padding: round 2), each against plain PyTorch.  The file sorts last on purpose: the suite is run with -x, and a
+first-run failure of a new kernel here must not hide the validated tests before it.  Each kernel is also pinned on CPU through
+the emulated ABI (tests/test_emulated.py, tests/test_conv2dblock_options.py)."""
 import pytest
 import torch
 
-from climategan_b200 import ops
+from climategan_b200 import _lib, ops
 from tests.helpers import rel_max
 
 pytestmark = pytest.mark.gpu
@@ -166,3 +168,42 @@ def test_moments_and_replicate_pad(cuda, dtype):
     assert rel_max(y, yr) == 0.0
     y.backward(gy.float().to(cuda))
     assert rel_max(ops.from_storage(xs2.grad, c), xr2.grad) < tol
+
+
+@pytest.mark.parametrize("shape,target", [((480, 853), 128), ((1200, 800), 256), ((300, 300), 128), ((97, 160), 128)])
+def test_input_edge_resize_and_crop(cuda, shape, target):
+    """events.InputEdge (cgb_resize_crop_u8): uint8 HWC photo -> anti-aliased bilinear resize (short side = target) -> centre crop
+    -> [-1, 1], against F.interpolate(mode="bilinear", antialias=True) + the reference's crop arithmetic (apply_events.py:223-241).
+    Up- and down-scaling, both orientations."""
+    import torch.nn.functional as F
+
+    from climategan_b200.events import InputEdge, resize_and_crop_size
+
+    h, w = shape
+    g = torch.Generator().manual_seed(h + w)
+    img = torch.randint(0, 256, (h, w, 3), generator=g, dtype=torch.uint8)
+    rh, rw, top, left = resize_and_crop_size(h, w, target)
+    ref = F.interpolate(img.permute(2, 0, 1)[None].float(), size=(rh, rw), mode="bilinear", antialias=True, align_corners=False)
+    ref = ref[:, :, top:top + target, left:left + target]
+    out = InputEdge(cuda, quantize=False)([img.numpy(), img.numpy()], target)
+    assert tuple(out.shape) == (2, 3, target, target) and torch.equal(out[0], out[1])
+    assert float((out[0].cpu() - (ref[0] / 255 - 0.5) * 2).abs().max()) < 2e-4
+    outq = InputEdge(cuda, quantize=True)([img.numpy()], target)       # the reference truncates the resized image to uint8 (:231)
+    want = (torch.floor(ref[0].clamp(0, 255)) / 255 - 0.5) * 2
+    d = (outq[0].cpu() - want).abs()
+    assert float((d > 1e-4).float().mean()) < 2e-3 and float(d.max()) <= 2.0 / 255 + 1e-4   # (floor flips where fp32 sums straddle an integer)
+
+
+def test_device_prefetcher_overlaps_and_orders_copies(cuda):
+    """climategan_b200.data.DevicePrefetcher on real streams: pinned H2D on a side stream, batches arrive intact and in order,
+    the consumer only waits on the copy's event."""
+    from climategan_b200.data import DevicePrefetcher
+
+    host = [{"data": {"x": torch.full((4, 3, 64, 64), float(i)).pin_memory(), "s": torch.full((4, 1, 16, 16), i, dtype=torch.int64)},
+             "domain": ["r"] * 4} for i in range(6)]
+    seen = []
+    for b in DevicePrefetcher(((h,) for h in host), cuda, depth=2):
+        x = b[0]["data"]["x"]
+        assert x.is_cuda and b[0]["data"]["s"].dtype == torch.int64 and b[0]["domain"] == ["r"] * 4
+        seen.append(float((x * 2).mean()) / 2)      # a kernel on the compute stream consuming the prefetched tensor
+    assert seen == [float(i) for i in range(6)]
