@@ -85,6 +85,7 @@ SIGNATURES = {
     "cgb_conv2d_dgrad": ([_DP, _P, _P, _P, _I, _P, _P, _P], C.c_int),
     "cgb_conv2d_pack_dgrad_weight": ([_DP, _P, _P, _P], C.c_int),
     "cgb_pack_weight": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_pack_weight_dual": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_conv2d_wgrad": ([_DP, _P, _P, _P, _P, _I, _P], C.c_int),
     "cgb_instnorm_ws_doubles": ([_I, _I, _I], C.c_int64),
     "cgb_instnorm_stats": ([_P, _I, _I, _I, _I, _F, _P, _P, _P, _P], C.c_int),

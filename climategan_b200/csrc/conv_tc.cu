@@ -239,7 +239,7 @@ struct TcParams {
   // per-channel sum / sum of squares of the stored output, accumulated by the epilogue (train-mode BatchNorm statistics of a
   // conv -> BN chain without a statistics pass over the tensor): a [2][cout_s] fp32 table in shared memory at byte offset
   // stats_off from the 1024-aligned base, flushed once per CTA to stats_out[blockIdx.x][2][cout_s]
-  int stats, stats_off;
+  int stats, stats_off, stats_rows;   // stats_rows: rows of stats_out (CTA 0 zeroes the rows beyond the launch's grid)
   short tap_dy[64], tap_dx[64], tap_w[64];
 };
 
@@ -614,6 +614,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m = i >= p.cout_s ? 1 : 0, c = i - m * p.cout_s;
         out[i] = stats_tab[m * p.cout_s + (c & 7) * c8 + (c >> 3)];
       }
+      if (blockIdx.x == 0) {   // rows no CTA owns (a launch smaller than the partial buffer) must read as zero
+        const size_t lo = (size_t)gridDim.x * 2 * p.cout_s, hi = (size_t)p.stats_rows * 2 * p.cout_s;
+        for (size_t i = lo + (threadIdx.x - 64); i < hi; i += EPI_THREADS) stats_out[i] = 0.f;
+      }
     }
   }
 
@@ -782,6 +786,10 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int m = i >= p.cout_s ? 1 : 0, c = i - m * p.cout_s;
         out[i] = stats_tab[m * p.cout_s + (c & 7) * c8 + (c >> 3)];
       }
+      if (blockIdx.x == 0) {   // rows no CTA owns (a launch smaller than the partial buffer) must read as zero
+        const size_t lo = (size_t)gridDim.x * 2 * p.cout_s, hi = (size_t)p.stats_rows * 2 * p.cout_s;
+        for (size_t i = lo + (threadIdx.x - 64); i < hi; i += EPI_THREADS) stats_out[i] = 0.f;
+      }
     }
   }
 
@@ -927,6 +935,7 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
   memset(&p, 0, sizeof(p));
   p.res_before_act = res_before_act;
   p.stats = stats_out ? 1 : 0;
+  p.stats_rows = num_sms();
   const int stats_bytes = stats_out ? 2 * cout_s * 4 + 16 : 0;
   p.n = n; p.hout = hgrid; p.wout = wgrid; p.cout_s = cout_s; p.cin_s = cin_s;
   p.stride = in_stride;
@@ -1036,6 +1045,10 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
       if (fixed + 2 * (size_t)a_stage > SMEM_LIMIT) continue;
       int stg = (int)((SMEM_LIMIT - fixed) / a_stage);
       if (stg > 6) stg = 6;
+      // a resident-weight 1x1 needs a deep activation ring (each 16 KB stage is only 4 MMAs of work): prefer a narrower N
+      // slice with >= ws_1x1_min_stages stages over the widest slice with two
+      static const int ws_1x1_min_stages = getenv("CGB_WS_1X1_MIN_STAGES") ? atoi(getenv("CGB_WS_1X1_MIN_STAGES")) : 4;
+      if (taps == 1 && ws_1x1 && stg < ws_1x1_min_stages && nt < 8) continue;
       const double ws_bytes = (double)((wout + 7) / 8) * ((hout + 15) / 16) * n * nt * kblocks * (double)(twh * thh * 128);
       // Measured on B200 (gpurun_out/ws_sweep.log -> profiles/r01_ws_vs_streaming.txt): the weight-stationary kernel only
       // wins for narrow outputs fed by few channels (gamma||beta 128->48 @640^2: 1.22 vs 1.50 ms; 24->24: 0.59 vs 2.03 ms).
@@ -1075,6 +1088,7 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
   p.act = act; p.slope = slope; p.dact = dact;
   p.out_stride = 1; p.hfull = hout; p.wfull = wout;
   p.stats = stats_out ? 1 : 0;
+  p.stats_rows = num_sms();
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
     cudaFuncSetAttribute(conv_tc_ws_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
@@ -1129,12 +1143,11 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
   return after_launch("conv_tc_ws");
 }
 
-// stats_out (optional): [conv_tc_stats_rows()][2][co] fp32, zeroed here; row b receives CTA b's per-channel sum / sum of
-// squares of the stored output (rows beyond the launch's grid stay zero), for cgb_bn_train_fwd_partials
+// stats_out (optional): [conv_tc_stats_rows()][2][co] fp32; row b receives CTA b's per-channel sum / sum of squares of the
+// stored output, rows beyond the launch's grid are zeroed by CTA 0 (no memset launch), for cgb_bn_train_fwd_partials
 int conv_tc_stats_rows() { return num_sms(); }
 int conv_tc_fwd(const cgb_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
                 cudaStream_t st, float* stats_out) {
-  if (stats_out) cudaMemsetAsync(stats_out, 0, sizeof(float) * (size_t)num_sms() * 2 * d->co, st);
   return launch_fprop(x, w, y, d->n, d->hi, d->wi, d->ci, d->ho, d->wo, d->co, d->kh, d->kw, d->stride, d->dil, d->pad,
                       d->pad, d->act, d->slope, bias, residual, CGB_ACT_NONE, nullptr, st, d->res_before_act, stats_out,
                       d->dtype == CGB_F16);

@@ -1555,6 +1555,56 @@ pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, long long to
   }
 }
 
+// the forward packing AND the dgrad packing wt[cis][taps-1-t][cos] = w[co][t][ci] (cgb_conv2d_pack_dgrad_weight's layout) in one
+// launch: the first total_fwd vectors belong to wp (8 consecutive ci), the rest to wt (8 consecutive co)
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_weight_dual_kernel(const float* __restrict__ w, T* __restrict__ wp, T* __restrict__ wt, long long total_fwd, long long total_all,
+                        int o, int i, int taps, int cos, int cis) {
+  const int iv = cis >> 3, ov = cos >> 3;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total_all; idx += (long long)gridDim.x * blockDim.x) {
+    float vals[8];
+    if (idx < total_fwd) {
+      const int v = (int)(idx % iv);
+      const long long r = idx / iv;
+      const int t = (int)(r % taps);
+      const int co = (int)(r / taps);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ci = v * 8 + j;
+        vals[j] = (co < o && ci < i) ? w[((long long)co * i + ci) * taps + t] : 0.f;
+      }
+      Vec8<T>::store(wp + idx * 8, vals);
+    } else {
+      const long long k = idx - total_fwd;
+      const int v = (int)(k % ov);
+      const long long r = k / ov;
+      const int tr = (int)(r % taps);        // position in wt = taps-1-t
+      const int ci = (int)(r / taps);
+      const int t = taps - 1 - tr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int co = v * 8 + j;
+        vals[j] = (co < o && ci < i) ? w[((long long)co * i + ci) * taps + t] : 0.f;
+      }
+      Vec8<T>::store(wt + k * 8, vals);
+    }
+  }
+}
+
+extern "C" int cgb_pack_weight_dual(const float* w, void* wp, void* wt, int32_t dtype, int32_t o, int32_t i, int32_t taps,
+                                    int32_t cos, int32_t cis, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(w && wp && wt, "pack_weight_dual: null pointer");
+  CGB_REQUIRE(o >= 1 && i >= 1 && taps >= 1 && cos >= o && cis >= i && cis % 8 == 0 && cos % 8 == 0,
+              "pack_weight_dual: bad shape o=%d i=%d cos=%d cis=%d", o, i, cos, cis);
+  const long long total_fwd = (long long)cos * taps * (cis / 8);
+  const long long total_all = total_fwd + (long long)cis * taps * (cos / 8);
+  DISPATCH_T(dtype, pack_weight_dual_kernel<T><<<grid_for(total_all), 256, 0, (cudaStream_t)stream>>>(w, (T*)wp, (T*)wt, total_fwd,
+                                                                                                   total_all, o, i, taps, cos, cis);)
+  return after_launch("pack_weight_dual");
+}
+
 extern "C" int cgb_pack_weight(const float* w, void* wp, int32_t dtype, int32_t o, int32_t i, int32_t taps, int32_t cos,
                                int32_t cis, void* stream) {
   CGB_CHECK_DEVICE();

@@ -60,7 +60,9 @@ _PACK_KERNEL = os.environ.get("CGB_PACK_KERNEL", "1") == "1"
 
 
 def pack_weight(w: torch.Tensor, dtype: torch.dtype, cis: Optional[int] = None, cos: Optional[int] = None,
-                kernel: Optional[bool] = None) -> torch.Tensor:
+                kernel: Optional[bool] = None, with_dgrad: bool = False) -> torch.Tensor:
+    """with_dgrad: also build the dgrad packing [cis][taps reversed][cos] in the same launch and hang it on the result
+    (``wp._cgb_wt``, where conv_dgrad_raw looks for it)."""
     o, i, kh, kw = w.shape
     cos = cos or round8(o)
     cis = cis or round8(i)
@@ -68,6 +70,11 @@ def pack_weight(w: torch.Tensor, dtype: torch.dtype, cis: Optional[int] = None, 
         wd = w.detach()
         wd = wd if wd.is_contiguous() else wd.contiguous()
         wp = torch.empty(cos, kh * kw, cis, dtype=dtype, device=w.device)
+        if with_dgrad and dtype != torch.float32:
+            wt = torch.empty(cis, kh * kw, cos, dtype=dtype, device=w.device)
+            check(_L().cgb_pack_weight_dual(_p(wd), _p(wp), _p(wt), _DT[dtype], o, i, kh * kw, cos, cis, _st()), "pack_weight_dual")
+            wp._cgb_wt = wt
+            return wp
         check(_L().cgb_pack_weight(_p(wd), _p(wp), _DT[dtype], o, i, kh * kw, cos, cis, _st()), "pack_weight")
         return wp
     wp = torch.zeros(cos, kh * kw, cis, dtype=dtype, device=w.device)
@@ -94,14 +101,14 @@ def invalidate_weight_cache() -> None:
 _DBG = set(os.environ.get("CGB_DEBUG_DISABLE", "").split(","))   # debugging switches: wcache, viewgrad, aliasparam
 
 
-def pack_weight_cached(w: torch.Tensor, dtype: torch.dtype, cis: Optional[int] = None) -> torch.Tensor:
+def pack_weight_cached(w: torch.Tensor, dtype: torch.dtype, cis: Optional[int] = None, with_dgrad: bool = False) -> torch.Tensor:
     if not isinstance(w, torch.nn.Parameter) or "wcache" in _DBG:
-        return pack_weight(w, dtype, cis=cis)
+        return pack_weight(w, dtype, cis=cis, with_dgrad=with_dgrad)
     key = (id(w), dtype, cis)
     ent = _WCACHE.get(key)
     if ent is not None and ent[0] == _WEPOCH[0] and ent[1] == w._version and ent[2] == w.data_ptr() and ent[3]() is w:
         return ent[4]
-    wp = pack_weight(w, dtype, cis=cis)
+    wp = pack_weight(w, dtype, cis=cis, with_dgrad=with_dgrad)
     import weakref
 
     _WCACHE[key] = (_WEPOCH[0], w._version, w.data_ptr(), weakref.ref(w), wp)
@@ -295,7 +302,8 @@ class _Conv2d(Function):
 
     @staticmethod
     def forward(ctx, x, w, bias, residual, g: ConvGeom, want_stats=False):
-        wp = pack_weight_cached(w, x.dtype, cis=x.shape[-1])
+        # a conv whose input needs a gradient will run a dgrad: pack the weight both ways in one launch
+        wp = pack_weight_cached(w, x.dtype, cis=x.shape[-1], with_dgrad=bool(ctx.needs_input_grad[0]))
         bp = pad_bias(bias, wp.shape[0])
         partial = None
         if want_stats:

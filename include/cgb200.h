@@ -126,6 +126,10 @@ int cgb_conv2d_pack_dgrad_weight(const cgb_conv_desc* d, const void* w, void* wt
  * -> wp [cos][taps = kh*kw][cis] in `dtype`, zeros in the channel padding (cos >= o, cis >= i, cis % 8 == 0). */
 int cgb_pack_weight(const float* w, void* wp, int32_t dtype, int32_t o, int32_t i, int32_t taps, int32_t cos, int32_t cis,
                     void* stream);
+/* The same plus the dgrad packing wt[cis][taps-1-t][cos] (cgb_conv2d_pack_dgrad_weight's layout) in ONE launch — weights change
+ * every optimiser step, and a weight whose conv needs a data gradient is packed both ways once per step. */
+int cgb_pack_weight_dual(const float* w, void* wp, void* wt, int32_t dtype, int32_t o, int32_t i, int32_t taps, int32_t cos,
+                         int32_t cis, void* stream);
 
 /* Weight (+bias) gradient: gw[co][kh*kw][ci] (fp32), gbias[co] (fp32, optional).
  * accumulate=0 zero-fills gw/gbias first. */

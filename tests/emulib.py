@@ -153,6 +153,13 @@ class EmuLib(NoopLib):
         P.zero_()
         P[:o, :, :i] = W.permute(0, 2, 1)
 
+    def e_pack_weight_dual(self, w, wp, wt, dtype, o, i, taps, cos, cis, stream):
+        self.e_pack_weight(w, wp, dtype, o, i, taps, cos, cis, stream)
+        W = _t(w, (o, i, taps), torch.float32)
+        T = _t(wt, (cis, taps, cos), _DT[dtype])
+        T.zero_()
+        T[:i, :, :o] = W.flip(2).permute(1, 2, 0)      # wt[ci][taps-1-t][co] = w[co][ci][t]
+
     def e_im2col(self, x, y, dtype, n, h, w, cs_in, c, k, pad, dil, cs_out, stream):
         dt = _DT[dtype]
         X = _t(x, (n, h, w, cs_in), dt).float()[..., :c].permute(0, 3, 1, 2)

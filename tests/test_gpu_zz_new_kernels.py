@@ -207,3 +207,19 @@ def test_device_prefetcher_overlaps_and_orders_copies(cuda):
         assert x.is_cuda and b[0]["data"]["s"].dtype == torch.int64 and b[0]["domain"] == ["r"] * 4
         seen.append(float((x * 2).mean()) / 2)      # a kernel on the compute stream consuming the prefetched tensor
     assert seen == [float(i) for i in range(6)]
+
+
+def test_pack_weight_dual_matches_the_two_separate_packings(cuda):
+    """cgb_pack_weight_dual: the forward packing and the dgrad packing in one launch, bit-exact against cgb_pack_weight +
+    cgb_conv2d_pack_dgrad_weight, with channel padding on both sides."""
+    torch.manual_seed(2)
+    for (o, i, k) in [(20, 40, 3), (256, 64, 1), (11, 3, 7)]:
+        w = torch.randn(o, i, k, k, device=cuda)
+        for dt in (torch.bfloat16, torch.float16):
+            a = ops.pack_weight(w, dt, with_dgrad=True)
+            b = ops.pack_weight(w, dt)
+            assert torch.equal(a, b)
+            g = ops.ConvGeom(k, k, 1, 1, k // 2)
+            gy = torch.zeros(1, 8, 8, b.shape[0], dtype=dt, device=cuda)
+            ops.conv_dgrad_raw(gy, b, (1, 8, 8, b.shape[2]), g)       # builds b._cgb_wt the old way
+            assert torch.equal(a._cgb_wt, b._cgb_wt)
