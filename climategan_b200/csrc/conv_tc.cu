@@ -155,6 +155,62 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- 2-CTA (cta_group::2) forms: a CTA pair of one cluster shares one 256 x N accumulator tile ------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads whose completion bytes are credited to a barrier of the LEADER CTA (mbar: a shared::cluster address)
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t mbar_cluster, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(mbar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t mbar_cluster, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(mbar_cluster), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[256 x N] (+)= A[256 x 16] * B[N x 16]^T : rows 0..127 from the leader's smem / TMEM, rows 128..255 from the peer's;
+// each CTA's smem holds N/2 rows of B
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
 // UMMA shared-memory descriptor, 128B swizzle (layout_type 2), descriptor version 1 (Blackwell).
 //   K-major  operand: rows (M/N index) of 128 B, 8-row swizzle atoms 1024 B apart (SBO); LBO unused (1).
 //   MN-major operand: rows are K indices of 128 B = 64 contiguous M/N elements; groups of 8 K-rows are SBO=1024 B
@@ -194,7 +250,7 @@ template <> struct Pk<__half> {
 };
 
 // instruction descriptor: (bf16 x bf16 | f16 x f16) -> fp32, M=128
-__host__ __device__ inline uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major, bool f16 = false) {
+__host__ __device__ inline uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major, bool f16 = false, int m = 128) {
   uint32_t d = 0;
   d |= 1u << 4;                          // c_format  F32
   d |= (f16 ? 0u : 1u) << 7;             // a_format  F16 = 0, BF16 = 1
@@ -202,7 +258,7 @@ __host__ __device__ inline uint32_t make_idesc(int n, bool a_mn_major, bool b_mn
   d |= (a_mn_major ? 1u : 0u) << 15;     // a_major
   d |= (b_mn_major ? 1u : 0u) << 16;     // b_major
   d |= (uint32_t)(n >> 3) << 17;         // N >> 3
-  d |= (uint32_t)(128 >> 4) << 24;       // M >> 4
+  d |= (uint32_t)(m >> 4) << 24;         // M >> 4 (128: one CTA; 256: a cta_group::2 pair)
   return d;
 }
 
@@ -377,7 +433,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
                                               const T* __restrict__ residual,
                                               const T* __restrict__ mask_src, T* __restrict__ y,
                                               uint32_t tempty_bar, int warp, int lane, const CUtensorMap* tmY = nullptr,
-                                              uint32_t staging_u32 = 0, float* stats_tab = nullptr, EpiStats* est = nullptr) {
+                                              uint32_t staging_u32 = 0, float* stats_tab = nullptr, EpiStats* est = nullptr,
+                                              bool tempty_is_cluster_addr = false) {
   const int q = warp & 3;              // TMEM lane quarter this warp may access
   const int half = (warp - 2) >> 2;    // EPI_PER_Q warps share a quarter: 16-column chunks interleaved among them
   const int row = q * 32 + lane;       // tile row == TMEM lane == pixel within the tile
@@ -413,12 +470,15 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
   // accumulator buffer drained: hand it back to the MMA warp
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive(tempty_bar);
+  if (lane == 0 && !tempty_is_cluster_addr) mbar_arrive(tempty_bar);
+  // (2-CTA kernel: ONE remote arrive per CTA on the leader's barrier, by thread 0 of the group after the staging barrier below —
+  //  sixteen ~500-cycle cluster arrives per tile and CTA showed up as a slow-down on the short-K 1x1 convs)
   if (tma) {
     // copy-out by the TMA unit: one bulk tensor store per 64-channel half of the tile; image borders, the batch tail and the
     // channel tail are clipped by the tensor map, so no thread computes an address
     fence_proxy_async_smem();   // this thread's staging writes -> visible to the async proxy
-    epi_bar_sync();             // staging complete
+    epi_bar_sync();             // staging complete (and every warp's TMEM reads are done)
+    if (et == 0 && tempty_is_cluster_addr) mbar_arrive_cluster(tempty_bar);
     if (et == 0) {
       for (int hb = 0; hb * 64 < p.bn; ++hb)
         if (cn0 + hb * 64 < p.cout_s) tma_store_4d(tmY, staging_u32 + (uint32_t)hb * (128u * 128u), cn0 + hb * 64, ox0, oy0, n0);
@@ -428,6 +488,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
     return;
   }
   epi_bar_sync();  // staging complete
+  if (et == 0 && tempty_is_cluster_addr) mbar_arrive_cluster(tempty_bar);
   if (stats_tab) epilogue_stats<T>(p, staging_gen, false, ox0, oy0, n0, cn0, stats_tab, *est, warp, lane);
   // phase 2: lanes cover (rows_per_iter x chunks_per_row) 16-byte chunks; the row/chunk split of a lane is fixed, so
   // the only per-iteration work is the pixel address.  Consecutive lanes write consecutive chunks of a pixel and then
@@ -626,6 +687,190 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Streaming kernel, CTA-PAIR form (tcgen05 cta_group::2): the two CTAs of a cluster own ONE 256-pixel x bn accumulator tile —
+// CTA r the pixel tile 2q + r (rows r*128.. of the accumulator, in its own TMEM) — and each stages only HALF of the weight
+// tile (bn/2 rows) per (tap, 64-channel block): the tensor cores of both SMs read both halves.  Per 256 output pixels the pair
+// pulls 2 A tiles + ONE B tile through L2 instead of 2 + 2: the streaming kernel's 1x1 and dilated ResNet convs are bound by
+// exactly that L2 -> SM traffic, and a stage shrinks from 16 KB + bn*128 B to 16 KB + bn*64 B (deeper
+// ring).  Protocol (barriers live at the same offsets in both CTAs):
+//   full[s]   (leader's is used): the leader's producer arms it with the bytes of BOTH CTAs' loads; every TMA load of the pair
+//             (cp.async.bulk.tensor ... cta_group::2) credits its bytes to the leader's barrier;
+//   empty[s]  (both): the leader's tcgen05.commit multicasts one arrive to each CTA when the MMAs that read stage s are done;
+//   tfull[b]  (both): same multicast commit after the last MMA of a tile — each CTA's epilogue drains its own TMEM half;
+//   tempty[b] (leader's is used): every epilogue warp of BOTH CTAs arrives on it (the peer's through mapa'd cluster addresses).
+// The MMA is issued by the leader's warp 1 only; the peer's warp 1 just takes part in the paired TMEM allocation.
+template <typename T>
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const T* __restrict__ residual,
+                const T* __restrict__ mask_src, T* __restrict__ y, float* __restrict__ stats_out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t b_half_bytes = (uint32_t)p.bn * 64u;               // bn/2 rows of 128 B
+  const uint32_t stage_bytes = A_TILE_BYTES + b_half_bytes;
+  const uint32_t staging = base + (uint32_t)p.stages * stage_bytes;
+  const uint32_t staging_tile = (uint32_t)p.staging_tile_bytes;
+  const uint32_t bar_base = staging + staging_tile * (uint32_t)p.staging_bufs;
+  auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(p.stages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 16u * (uint32_t)p.stages + 8u * (uint32_t)b; };
+  auto tempty_bar = [&](int b) { return bar_base + 16u * (uint32_t)p.stages + 16u + 8u * (uint32_t)b; };
+  const uint32_t tmem_ptr_addr = bar_base + 16u * (uint32_t)p.stages + 32u;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+  uint8_t* staging_gen = smem_raw + (staging - raw);
+  float* stats_tab = p.stats ? reinterpret_cast<float*>(smem_raw + (base - raw) + (uint32_t)p.stats_off) : nullptr;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int taps = p.ntaps;
+  const int iters = taps * p.kblocks;
+  const int tn_log = 7 - p.tw_log - p.th_log;
+  const int pix_tiles = p.total_tiles / p.n_tiles;                 // pixel tiles; the pair walks them two at a time
+  const int pair_tiles = ((pix_tiles + 1) >> 1) * p.n_tiles;       // (pixel-tile pair, n tile), n tile fastest
+  if (stats_tab)
+    for (int i = threadIdx.x; i < 2 * p.cout_s; i += TC_THREADS) stats_tab[i] = 0.f;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    if (p.tma_store) prefetch_tmap(&tmY);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 2);               // one arrive per CTA of the pair (thread 0 of its epilogue group)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  cluster_sync_all();            // barrier inits and the allocation of BOTH CTAs are visible before any remote arrive / load
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  // decode pair tile -> this CTA's pixel tile (out of range: n0 >= n, every load zero-filled, every store clipped)
+  auto decode = [&](int pt_tile, int& ox0, int& oy0, int& n0, int& cn0) {
+    const int nt = pt_tile % p.n_tiles;
+    const int pt = (pt_tile / p.n_tiles) * 2 + (int)rank;
+    const int tx = pt % p.tiles_x;
+    const int ty = (pt / p.tiles_x) % p.tiles_y;
+    const int tn = pt / (p.tiles_x * p.tiles_y);
+    ox0 = tx << p.tw_log; oy0 = ty << p.th_log; n0 = tn << tn_log; cn0 = nt * p.bn;
+  };
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs) =================
+    if (elect_one_sync()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t2 = pair; t2 < pair_tiles; t2 += npairs) {
+        int ox0, oy0, n0, cn0;
+        decode(t2, ox0, oy0, n0, cn0);
+        for (int tap = 0; tap < taps; ++tap) {
+          const int cx = ox0 * p.stride + p.tap_dx[tap];
+          const int cy = oy0 * p.stride + p.tap_dy[tap];
+          const int wtap = p.tap_w[tap];
+          for (int kb = 0; kb < p.kblocks; ++kb) {
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            const uint32_t a_dst = base + (uint32_t)s * stage_bytes;
+            const uint32_t lead_full = mapa_rank(full_bar(s), 0);
+            if (leader) mbar_expect_tx(full_bar(s), 2u * stage_bytes);
+            tma2_load_4d(a_dst, &tmA, lead_full, kb * 64, cx, cy, n0);
+            tma2_load_3d(a_dst + A_TILE_BYTES, &tmB, lead_full, kb * 64, wtap, cn0 + (int)rank * (p.bn >> 1));
+            if (++s == p.stages) { s = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader only) =================
+    if (leader) {
+      const uint32_t idesc = make_idesc(p.bn, false, false, Pk<T>::is_f16, 256);
+      const uint32_t hi1024 = desc_hi(1024u);
+      const int ksteps_last = ((p.cin_s - (p.kblocks - 1) * 64) + 15) >> 4;
+      int s = 0;
+      uint32_t ph = 0;
+      int lt = 0;
+      for (int t2 = pair; t2 < pair_tiles; t2 += npairs, ++lt) {
+        const int buf = lt & 1;
+        const uint32_t bph = (uint32_t)(lt >> 1) & 1u;
+        mbar_wait(tempty_bar(buf), bph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)(buf * p.bn);
+        int kb = 0;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const int ksteps = (kb == p.kblocks - 1) ? ksteps_last : 4;
+            const uint32_t a_addr = base + (uint32_t)s * stage_bytes;
+            const uint32_t a_lo = desc_lo(a_addr, 16u), b_lo = desc_lo(a_addr + A_TILE_BYTES, 16u);
+            uint32_t acc = it > 0 ? 1u : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (k < ksteps) {
+                umma2_bf16(d_addr, desc_join(a_lo + 2u * k, hi1024), desc_join(b_lo + 2u * k, hi1024), idesc, acc);
+                acc = 1u;
+              }
+            }
+            umma2_commit_mc(empty_bar(s));
+            if (it == iters - 1) umma2_commit_mc(tfull_bar(buf));
+          }
+          __syncwarp();
+          if (++kb == p.kblocks) kb = 0;
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ================= epilogue warps (both CTAs, each on its own 128 rows) =================
+    EpiStats est;
+    est.ch = -1;
+    epi_stats_flush(p, est, stats_tab);
+    int lt = 0;
+    for (int t2 = pair; t2 < pair_tiles; t2 += npairs, ++lt) {
+      const int buf = lt & 1;
+      const uint32_t bph = (uint32_t)(lt >> 1) & 1u;
+      int ox0, oy0, n0, cn0;
+      decode(t2, ox0, oy0, n0, cn0);
+      mbar_wait(tfull_bar(buf), bph);
+      tc_fence_after();
+      const uint32_t sb = (p.staging_bufs == 2) ? (uint32_t)(lt & 1) * staging_tile : 0u;
+      epilogue_tile<T>(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen + sb, ox0, oy0, n0, cn0, bias, residual, mask_src, y,
+                       mapa_rank(tempty_bar(buf), 0), warp, lane, p.tma_store ? &tmY : nullptr, staging + sb, stats_tab, &est, true);
+    }
+    if (p.tma_store && threadIdx.x == 64) tma_store_wait_all();
+    if (stats_tab) {
+      epi_stats_flush(p, est, stats_tab);
+      epi_bar_sync();
+      float* out = stats_out + (size_t)blockIdx.x * 2 * p.cout_s;
+      const int c8 = p.cout_s >> 3;
+      for (int i = threadIdx.x - 64; i < 2 * p.cout_s; i += EPI_THREADS) {
+        const int m = i >= p.cout_s ? 1 : 0, c = i - m * p.cout_s;
+        out[i] = stats_tab[m * p.cout_s + (c & 7) * c8 + (c >> 3)];
+      }
+      if (blockIdx.x == 0) {
+        const size_t lo = (size_t)gridDim.x * 2 * p.cout_s, hi = (size_t)p.stats_rows * 2 * p.cout_s;
+        for (size_t i = lo + (threadIdx.x - 64); i < hi; i += EPI_THREADS) stats_out[i] = 0.f;
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();            // neither CTA frees TMEM / exits while the other may still signal its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -997,6 +1242,63 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
     cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
     cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
   });
+  // ---- CTA-pair form (cta_group::2): half a weight tile per CTA — for launches with enough pixel tiles to fill 74 pairs
+  static const int tc2 = getenv("CGB_TC2") ? atoi(getenv("CGB_TC2")) : 1;
+  {
+    const int pix_tiles = p.total_tiles / p.n_tiles;
+    const int pair_tiles = ((pix_tiles + 1) / 2) * p.n_tiles;
+    // measured (scripts/exp/tc2_check.py, profiles/r02_tc2_pair_kernel.txt): the pair form wins on long reductions (ASPP 2048->256
+    // d12: 382 -> 324 us) and loses on short-K 1x1 convs (256->1024: 61 -> 68 us): CGB_TC2=1 takes it from tc2_min_k on, 2 always
+    static const int tc2_min_k = getenv("CGB_TC2_MIN_K") ? atoi(getenv("CGB_TC2_MIN_K")) : 2048;
+    const bool k_ok = tc2 >= 2 || (long long)tt.ntaps * cin_s >= tc2_min_k;
+    if (tc2 && k_ok && p.bn % 16 == 0 && pair_tiles >= num_sms() / 2) {
+      const int stage2 = A_TILE_BYTES + p.bn * 64;
+      int stages2 = (int)((SMEM_LIMIT - 1024 - 256 - staging_bytes - stats_bytes) / stage2);
+      if (stages2 > 10) stages2 = 10;
+      p.stages = stages2;
+      p.stats_off = stages2 * stage2 + staging_bytes + 16 * stages2 + 64;
+      // the pair's weight map delivers bn/2 rows per load
+      {
+        cuuint64_t dims[3] = {(cuuint64_t)cin_s, (cuuint64_t)wtaps_total, (cuuint64_t)cout_s};
+        cuuint64_t strides[2] = {(cuuint64_t)cin_s * 2, (cuuint64_t)wtaps_total * cin_s * 2};
+        cuuint32_t box[3] = {64, 1, (cuuint32_t)(p.bn / 2)};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if (!encode_map(&tmB, w, 3, dims, strides, box, estr, "weights (half tile)", f16)) return CGB_LAUNCH_FAILURE;
+      }
+      const size_t smem2 = (size_t)stages2 * stage2 + staging_bytes + 16 * stages2 + 64 + stats_bytes + 1024;
+      static std::once_flag attr2_once;
+      std::call_once(attr2_once, [] {
+        cudaFuncSetAttribute(conv_tc2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+        cudaFuncSetAttribute(conv_tc2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+      });
+      int npairs = num_sms() / 2;
+      if (npairs > pair_tiles) npairs = pair_tiles;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)(2 * npairs));
+      cfg.blockDim = dim3(TC_THREADS);
+      cfg.dynamicSmemBytes = smem2;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t e;
+      if (f16)
+        e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<__half>, tmA, tmB, tmY, p, bias, (const __half*)residual, (const __half*)mask_src,
+                               (__half*)out, stats_out);
+      else
+        e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<__nv_bfloat16>, tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
+                               (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("conv_tc2: cluster launch failed: %s", cudaGetErrorString(e));
+        return CGB_LAUNCH_FAILURE;
+      }
+      return after_launch("conv_tc2");
+    }
+  }
   const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 16 * stages + 64 + stats_bytes + 1024;
   if (smem > SMEM_LIMIT) {
     set_error("tcgen05 engine: tile does not fit shared memory (bn=%d, stats=%d)", p.bn, p.stats);
@@ -1394,6 +1696,174 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------------
+// wgrad, CTA-PAIR form (cta_group::2; cluster (2,1,1) over two neighbouring M tiles — grid (m tiles, pixel splits, z)): the pair accumulates D_tap[256][bn] —
+// CTA r the 128 M-side channels of ITS m tile, in its own TMEM — and each CTA stages only HALF of the N-side operand (bn/2
+// channels = whole 64-channel boxes).  The N-side tensor is then pulled through L2 once per PAIR of m tiles instead of once
+// per m tile: wgrad is the most L2-traffic-bound kernel of the engine (1024->256 1x1: 314 MB for 132 MB of operands).
+// Same barrier protocol as conv_tc2_kernel: every load credits the LEADER's full barrier, the leader's commits multicast to
+// both CTAs' empty / accumulator-ready barriers, the leader's warp 1 issues every MMA.
+__global__ void __launch_bounds__(WG_THREADS)
+wgrad_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WgParams p,
+                 float* __restrict__ gw) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const int nh_boxes = p.n_boxes >> 1;                                  // N-side boxes this CTA stages (its half)
+  const int s_boxes = p.x_is_m ? p.m_boxes : nh_boxes;                  // boxes per shifted (x) tile, per CTA
+  const int u_boxes = p.x_is_m ? nh_boxes : p.m_boxes;                  // boxes per un-shifted (gy) tile, per CTA
+  const uint32_t s_bytes = (uint32_t)s_boxes * BOX_BYTES, u_bytes = (uint32_t)u_boxes * BOX_BYTES;
+  const uint32_t s_base = base;
+  const uint32_t u_base = base + (uint32_t)p.stages_s * s_bytes;
+  const uint32_t bar_base = u_base + (uint32_t)p.stages_u * u_bytes;
+  auto s_full = [&](int i) { return bar_base + 8u * (uint32_t)i; };
+  auto s_empty = [&](int i) { return bar_base + 8u * (uint32_t)(p.stages_s + i); };
+  auto u_full = [&](int i) { return bar_base + 8u * (uint32_t)(2 * p.stages_s + i); };
+  auto u_empty = [&](int i) { return bar_base + 8u * (uint32_t)(2 * p.stages_s + p.stages_u + i); };
+  const uint32_t tmem_full_bar = bar_base + 16u * (uint32_t)(p.stages_s + p.stages_u);
+  const uint32_t tmem_ptr_addr = tmem_full_bar + 8u;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_ptr_addr - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();            // == blockIdx.x & 1 (cluster (2,1,1): the m tiles run along grid x)
+  const bool leader = rank == 0;
+  const int m0 = blockIdx.x * 128;
+  const int m_pair0 = (blockIdx.x & ~1) * 128;
+  const int grp = blockIdx.z % p.tap_groups;
+  const int n0 = (blockIdx.z / p.tap_groups) * p.bn;
+  const int nh0 = n0 + (int)rank * (p.bn >> 1);       // first N-side channel this CTA stages
+  const int taps = p.kh * p.kw;
+  const int tap0 = grp * p.taps_per_group;
+  int ntaps = taps - tap0;
+  if (ntaps > p.taps_per_group) ntaps = p.taps_per_group;
+  const int tile0 = blockIdx.y * p.tiles_per_cta;
+  int tile1 = tile0 + p.tiles_per_cta;
+  if (tile1 > p.total_tiles) tile1 = p.total_tiles;
+  const int tn_log = 7 - p.tw_log - p.th_log;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmG);
+    for (int i = 0; i < p.stages_s; ++i) { mbar_init(s_full(i), 1); mbar_init(s_empty(i), 1); }
+    for (int i = 0; i < p.stages_u; ++i) { mbar_init(u_full(i), 1); mbar_init(u_empty(i), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_ptr_addr, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  // M-side boxes that hold real channels, for this CTA and for the pair (the leader arms the barriers with the pair's bytes)
+  auto m_load_of = [&](int mm0) { return (p.m_dim - mm0 > 64) ? 2 : 1; };
+  const int m_load = m_load_of(m0);
+  const int m_load_pair = m_load_of(m_pair0) + m_load_of(m_pair0 + 128);
+  const int s_load = p.x_is_m ? m_load : nh_boxes, u_load = p.x_is_m ? nh_boxes : m_load;
+  const int s_load_pair = p.x_is_m ? m_load_pair : 2 * nh_boxes, u_load_pair = p.x_is_m ? 2 * nh_boxes : m_load_pair;
+  const int x_ch0 = p.x_is_m ? m0 : nh0;              // first channel of the x / gy slices THIS CTA stages
+  const int g_ch0 = p.x_is_m ? nh0 : m0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int ss = 0, us = 0;
+      uint32_t sph = 0, uph = 0;
+      for (int tile = tile0; tile < tile1; ++tile) {
+        const int tx = tile % p.tiles_x;
+        const int ty = (tile / p.tiles_x) % p.tiles_y;
+        const int tn = tile / (p.tiles_x * p.tiles_y);
+        const int ox0 = tx << p.tw_log, oy0 = ty << p.th_log, img0 = tn << tn_log;
+        mbar_wait(u_empty(us), uph ^ 1u);
+        const uint32_t lead_u = mapa_rank(u_full(us), 0);
+        if (leader) mbar_expect_tx(u_full(us), (uint32_t)u_load_pair * BOX_BYTES);
+        for (int b = 0; b < u_load; ++b)
+          tma2_load_4d(u_base + (uint32_t)us * u_bytes + (uint32_t)b * BOX_BYTES, &tmG, lead_u, g_ch0 + b * 64, ox0, oy0, img0);
+        if (++us == p.stages_u) { us = 0; uph ^= 1u; }
+        for (int t = 0; t < ntaps; ++t) {
+          const int tap = tap0 + t;
+          const int dy = tap / p.kw, dx = tap - dy * p.kw;
+          mbar_wait(s_empty(ss), sph ^ 1u);
+          const uint32_t lead_s = mapa_rank(s_full(ss), 0);
+          if (leader) mbar_expect_tx(s_full(ss), (uint32_t)s_load_pair * BOX_BYTES);
+          for (int b = 0; b < s_load; ++b)
+            tma2_load_4d(s_base + (uint32_t)ss * s_bytes + (uint32_t)b * BOX_BYTES, &tmX, lead_s, x_ch0 + b * 64,
+                         ox0 * p.stride - p.pad + dx * p.dil, oy0 * p.stride - p.pad + dy * p.dil, img0);
+          if (++ss == p.stages_s) { ss = 0; sph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      const uint32_t idesc = make_idesc(p.bn, true, true, false, 256);
+      int ss = 0, us = 0;
+      uint32_t sph = 0, uph = 0;
+      for (int tile = tile0; tile < tile1; ++tile) {
+        mbar_wait(u_full(us), uph);
+        const uint32_t u_addr = u_base + (uint32_t)us * u_bytes;
+        for (int t = 0; t < ntaps; ++t) {
+          mbar_wait(s_full(ss), sph);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t s_addr = s_base + (uint32_t)ss * s_bytes;
+            const uint32_t a_addr = p.x_is_m ? s_addr : u_addr;
+            const uint32_t b_addr = p.x_is_m ? u_addr : s_addr;
+            const uint32_t d_addr = tmem_base + (uint32_t)(t * p.bn);
+            const uint32_t a_lo = desc_lo(a_addr, BOX_BYTES), b_lo = desc_lo(b_addr, BOX_BYTES);
+            const uint32_t hi = desc_hi(1024u);
+            uint32_t acc = tile > tile0 ? 1u : 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              umma2_bf16(d_addr, desc_join(a_lo + 128u * k, hi), desc_join(b_lo + 128u * k, hi), idesc, acc);
+              acc = 1u;
+            }
+            umma2_commit_mc(s_empty(ss));
+            if (t == ntaps - 1) {
+              umma2_commit_mc(u_empty(us));
+              if (tile == tile1 - 1) umma2_commit_mc(tmem_full_bar);
+            }
+          }
+          __syncwarp();
+          if (++ss == p.stages_s) { ss = 0; sph ^= 1u; }
+        }
+        if (++us == p.stages_u) { us = 0; uph ^= 1u; }
+      }
+    }
+  } else if (tile1 > tile0) {
+    const int q = warp & 3;
+    const int m = m0 + q * 32 + lane;
+    const bool m_ok = m < p.m_dim;
+    mbar_wait(tmem_full_bar, 0u);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int t = 0; t < ntaps; ++t) {
+      const long long tap_off = (long long)(tap0 + t) * p.st + (long long)m * p.sm;
+      for (int c0 = 0; c0 < p.bn; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(t_row + (uint32_t)(t * p.bn + c0), r);
+        tmem_ld_wait();
+        if (!m_ok) continue;
+        if (p.sn == 1) {
+          float* dst = gw + tap_off + (long long)(n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            if (n0 + c0 + j < p.n_dim) red_add_v4(dst + j, r[j], r[j + 1], r[j + 2], r[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int nn = n0 + c0 + j;
+            if (nn < p.n_dim) atomicAdd(gw + tap_off + (long long)nn * p.sn, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // wgrad, halo variant (stride-1 k x k convs on large maps): the x tile is loaded ONCE per pixel tile as a halo box
 // (16 + dil*(ndy-1)) x (8 + dil*(kw-1)) pixels and every tap of the CTA's dy-group is an MN-major UMMA descriptor into
 // it (row-shifted start, 8-row group stride SBO = TWh*128 B) — instead of one shifted box per tap.  Tile = 16 rows x 8
@@ -1731,6 +2201,46 @@ int conv_tc_wgrad(const cgb_conv_desc* d, const void* x, const void* gy, float* 
     cuuint32_t box[4] = {64, (cuuint32_t)(1 << p.tw_log), (cuuint32_t)(1 << p.th_log), (cuuint32_t)(1 << tn_log)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (!encode_map(&tmG, gy, 4, dims, strides, box, estr, "wgrad gy")) return CGB_LAUNCH_FAILURE;
+  }
+  // ---- CTA-pair form: two neighbouring m tiles share one pass over the N-side operand (whole 64-channel boxes per half)
+  // measured (profiles/r02_tc2_pair_kernel.txt): 512->512 d4 235 -> 220 us, ASPP 438 -> 401 us, 256->256 d2 91 -> 89 us, the 1x1
+  // classes unchanged (+-1 %); L2 -> SM bytes of 256->256 d2: 498 -> 367 MB per launch (ncu l1tex__m_xbar2l1tex_read_bytes)
+  static const int tc2w = getenv("CGB_TC2_WGRAD") ? atoi(getenv("CGB_TC2_WGRAD")) : 1;
+  if (tc2w && m_tiles % 2 == 0 && p.bn % 128 == 0) {
+    const int nh_boxes = p.n_boxes / 2;
+    const int s2 = p.x_is_m ? p.m_boxes : nh_boxes, u2 = p.x_is_m ? nh_boxes : p.m_boxes;
+    WgParams q = p;
+    q.stages_u = 2;
+    int budget2 = 200 * 1024 - q.stages_u * u2 * BOX_BYTES;
+    q.stages_s = budget2 / (s2 * BOX_BYTES);
+    if (q.stages_s > 8) q.stages_s = 8;
+    if (q.stages_s >= 2) {
+      const size_t smem2 = (size_t)q.stages_s * s2 * BOX_BYTES + (size_t)q.stages_u * u2 * BOX_BYTES + 16 * (q.stages_s + q.stages_u) + 16 + 1024;
+      static std::once_flag attr2_once;
+      std::call_once(attr2_once, [] {
+        cudaFuncSetAttribute(wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      });
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)m_tiles, (unsigned)splits, (unsigned)zdim);
+      cfg.blockDim = dim3(WG_THREADS);
+      cfg.dynamicSmemBytes = smem2;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, wgrad_tc2_kernel, tmX, tmG, q, gw);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("wgrad_tc2: cluster launch failed: %s", cudaGetErrorString(e));
+        return CGB_LAUNCH_FAILURE;
+      }
+      int s2r = after_launch("wgrad_tc2");
+      if (s2r) return s2r;
+      return gbias ? launch_colsum(d, gy, gbias, st) : CGB_OK;
+    }
   }
   const size_t smem = (size_t)p.stages_s * s_boxes * BOX_BYTES + (size_t)p.stages_u * u_boxes * BOX_BYTES +
                       16 * (p.stages_s + p.stages_u) + 16 + 1024;
