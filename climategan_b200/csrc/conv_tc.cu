@@ -145,11 +145,22 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar, uint32_t elected
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
 }
@@ -297,24 +308,46 @@ struct TcParams {
   // stats_off from the 1024-aligned base, flushed once per CTA to stats_out[blockIdx.x][2][cout_s]
   int stats, stats_off, stats_rows;   // stats_rows: rows of stats_out (CTA 0 zeroes the rows beyond the launch's grid)
   short tap_dy[64], tap_dx[64], tap_w[64];
+  // debug (CGB_TC_TRACE=1): CTA 0 writes clock64() stamps [tile < 32][16] here — the per-role timeline of the pipeline
+  unsigned long long* trace;
+  // magic multipliers ceil(2^32 / d) for the epilogue's per-tile index decomposition (0: divide), see fdiv()
+  uint32_t mg_nt, mg_tx, mg_ty, mg_txy;
 };
 
-constexpr int EPI_WARPS = 16;                      // 4 per TMEM lane quarter (latency hiding: the epilogue is a long
-constexpr int EPI_PER_Q = EPI_WARPS / 4;           // dependent chain per warp, more warps -> more chains in flight)
+// 2 epilogue warps per TMEM lane quarter.  (Round 1 used 4: its run-time-flag epilogue was a long dependent chain per warp and
+// more warps meant more chains in flight.  The compile-time variants are issue-lean and keep two 32-column accumulator loads
+// in flight per warp; 16 warps capped the kernel at 96 registers per thread (576 threads), which spilled the BatchNorm partial
+// sums and the generic path — 8 warps leave 204.)
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_PER_Q = EPI_WARPS / 4;
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;    // warp 0: TMA producer, warp 1: MMA issuer, then the epilogue warps
 constexpr int EPI_THREADS = 32 * EPI_WARPS;
+static_assert(EPI_PER_Q == 2, "the rolling store maps the 2 warps of a lane quarter onto the two 32-column halves of a 64-channel half");
 constexpr int A_TILE_BYTES = 128 * 128;  // 128 pixels x 64 bf16
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }
+// x / d for launch-constant d: one IMAD.HI with the host's magic multiplier (exact while x * d < 2^32, checked on the host); the
+// epilogue's 16 warps decompose the tile index once per tile — as real divisions that was ~250 warp instructions per tile and warp
+__device__ __forceinline__ uint32_t fdiv(uint32_t x, uint32_t d, uint32_t m) {
+  if (d == 1u) return x;
+  return m ? __umulhi(x, m) : x / d;
+}
+static uint32_t magic_for(long long max_x, int d) {
+  if (d <= 1 || max_x * (long long)d >= (1ll << 32)) return 0u;
+  return (uint32_t)(((1ull << 32) + (unsigned long long)d - 1ull) / (unsigned long long)d);
+}
+__device__ __forceinline__ void tc_trace(unsigned long long* tr, int lt, int slot) {
+  if (tr && blockIdx.x == 0 && lt < 32) tr[lt * 16 + slot] = (unsigned long long)clock64();
+}
 
 // ---- epilogue of one 128-pixel x bn tile, executed by the 8 epilogue warps --------------------------------
 // phase 1: TMEM -> registers (two tcgen05.ld in flight) -> bias / activation / residual / mask -> bf16 -> staging row
 // phase 2: coalesced 16-byte copy-out (consecutive threads write consecutive chunks of a pixel's channel vector)
 template <typename T>
-__device__ __forceinline__ void epi_chunk(const TcParams& p, const uint32_t (&r)[16], int c, int cn0, bool pix_ok,
+__device__ __forceinline__ void epi_chunk(const TcParams& p, const uint32_t* r, int c, int cn0, bool pix_ok,
                                           long long pix, float neg, bool mask_early, const float* __restrict__ bias,
                                           const T* __restrict__ residual,
                                           const T* __restrict__ mask_src, uint8_t* my_row, int sw = -1) {
@@ -367,6 +400,104 @@ __device__ __forceinline__ void epi_chunk(const TcParams& p, const uint32_t (&r)
       Vec8<T>::store(
           reinterpret_cast<T*>(my_row + (size_t)(j >> 3) * (128 * 128) + (size_t)(((j & 7) ^ sw) << 4)), v);
     }
+  }
+}
+
+// ---- lean phase 1 (TMA-store staging, act in {none, relu, lrelu}) --------------------------------------------------------
+// The generic epi_chunk above costs ~230 warp instructions per 16-column chunk (per-element activation switch, 64-bit generic
+// addressing, per-8-channel re-tests of launch-uniform flags): with 4 epilogue warps per scheduler the epilogue of a
+// 128 x 256 tile took ~4100 cycles against 2048 cycles of MMAs for K = 256 — the short-K convs were bound by the epilogue's
+// instruction issue (CGB_TC_TRACE timeline, profiles/r02_epilogue_timeline.txt).  Here every launch-uniform decision is a
+// warp-uniform branch per chunk, the operand that needs DRAM latency (residual or derivative mask: never both) is fetched
+// before the accumulator wait, and the staging stores use 32-bit shared addresses.  Same arithmetic, same order, same bits.
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+enum { EPI_AUX_NONE = 0, EPI_AUX_RES_BEFORE = 1, EPI_AUX_RES_AFTER = 2, EPI_AUX_MASK = 3 };
+// kernel-level epilogue variants (template parameter of the fprop / dgrad kernels)
+// GENERIC: TMA-store tile with run-time flags (residual adds, ...); EXOTIC: tanh / sigmoid / selu epilogues (generic chunk code);
+// NOTMA: the per-thread copy-out (strided parity-class dgrad, ReLU-masked dgrad, N tiles that are not whole 64-channel halves)
+enum { EPI_GENERIC = 0, EPI_PLAIN = 1, EPI_BIAS = 2, EPI_BIAS_ACT = 3, EPI_MASK_RELU = 4, EPI_MASK_LRELU = 5, EPI_EXOTIC = 6, EPI_NOTMA = 7,
+       EPI_VARIANTS = 8 };
+
+template <typename T>
+__device__ __forceinline__ void epi_fast_fetch(const TcParams& p, int ch0, bool pix_ok, long long pixoff, const T* __restrict__ aux_src,
+                                               uint4* aux) {
+  aux[0] = make_uint4(0u, 0u, 0u, 0u);
+  aux[1] = make_uint4(0u, 0u, 0u, 0u);
+  if (pix_ok) {
+    if (ch0 < p.cout_s) aux[0] = __ldg(reinterpret_cast<const uint4*>(aux_src + pixoff + ch0));
+    if (ch0 + 8 < p.cout_s) aux[1] = __ldg(reinterpret_cast<const uint4*>(aux_src + pixoff + ch0 + 8));
+  }
+}
+
+// BIAS / ACT / AUX: 1 / 0 = known at compile time, -1 = decided at run time (the generic instantiation).  AUX adds two
+// compile-time mask flavours to the EPI_AUX_* kinds: the launch-uniform branches of the run-time form cost more issue slots than
+// the arithmetic (369 warp instructions per pair of chunks, most of them predicated-off bias adds and flag tests).
+enum { EPI_AUX_MASK_RELU = 4, EPI_AUX_MASK_LRELU = 5 };
+template <typename T, int BIAS, int ACT, int AUX>
+__device__ __forceinline__ void epi_fast_apply(const TcParams& p, const uint32_t* r, int ch0, int j0, float neg, int aux_kind_rt,
+                                               const float* __restrict__ bias, const uint4* aux, uint32_t row_u32,
+                                               uint32_t sw16) {
+  const bool has_bias = BIAS < 0 ? (bias != nullptr) : (BIAS != 0);
+  const bool has_act = ACT < 0 ? (p.act != CGB_ACT_NONE) : (ACT != 0);
+  const int aux_kind = AUX < 0 ? aux_kind_rt : AUX;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {   // one 16-byte staging chunk (8 channels) at a time: keeps the live set at 8 + 8 floats
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * h + j]);
+    if (has_bias) {
+      if (ch0 + 8 * h < p.cout_s) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + ch0 + 8 * h));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + ch0 + 8 * h + 4));
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+    }
+    float a[8];
+    if (aux_kind != EPI_AUX_NONE) {
+      const typename Pk<T>::T2* h2 = reinterpret_cast<const typename Pk<T>::T2*>(&aux[h]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = Pk<T>::to_f2(h2[i]);
+        a[2 * i] = f.x; a[2 * i + 1] = f.y;
+      }
+    }
+    if (aux_kind == EPI_AUX_RES_BEFORE) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += a[j];
+    }
+    if (has_act) {   // relu / lrelu (0 <= slope < 1): max(v, v*neg)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], v[j] * neg);
+    }
+    if (aux_kind == EPI_AUX_RES_AFTER) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += a[j];
+    }
+    if (aux_kind == EPI_AUX_MASK_RELU || (aux_kind == EPI_AUX_MASK && p.dact == CGB_ACT_RELU)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= (a[j] > 0.f ? 1.f : 0.f);
+    } else if (aux_kind == EPI_AUX_MASK_LRELU || (aux_kind == EPI_AUX_MASK && p.dact == CGB_ACT_LRELU)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= (a[j] > 0.f ? 1.f : p.slope);
+    } else if (aux_kind == EPI_AUX_MASK) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= act_grad_from_out(a[j], p.dact, p.slope);
+    }
+    const uint32_t j = (uint32_t)(j0 + h);
+    sts128(row_u32 + (j >> 3) * (128u * 128u) + (((j & 7u) << 4) ^ sw16), pack2<T>(v[0], v[1]), pack2<T>(v[2], v[3]),
+           pack2<T>(v[4], v[5]), pack2<T>(v[6], v[7]));
   }
 }
 
@@ -427,14 +558,126 @@ __device__ __forceinline__ void epilogue_stats(const TcParams& p, const uint8_t*
   }
 }
 
-template <typename T>
+// ---- copy-out by the TMA unit, two 64-channel halves at a time ("rolling store") --------------------------------------------
+// The 16 warps stage a PAIR of halves (each warp one 16-column chunk of its lane quarter per half), a barrier, the halves'
+// leaders (lane 0 of epilogue warp h for half h — bulk groups are per thread) issue their bulk tensor stores, and everybody
+// moves on to the next pair while the TMA unit reads this one: the stores overlap the staging of the next pair and, for the
+// last pair, the MMAs of the next tile.  Image borders, the batch tail and the channel tail are clipped by the tensor map, so
+// no thread computes a global address (unless a residual / derivative mask is read).
+// BIAS / ACT / AUX are compile-time (-1: run time): measured with ncu, the run-time form executed ~1000 warp instructions per
+// warp and tile (4 warps per scheduler -> ~4400 issue cycles per 128 x 256 tile against 2048 cycles of MMAs at K = 256), i.e.
+// the short-K convs were bound by the epilogue's instruction issue (profiles/r02_epilogue_timeline.txt).
+template <typename T, int BIAS, int ACT, int AUX, bool GENERIC_CHUNK>
+__device__ __forceinline__ void epi_tma_tile(const TcParams& p, uint32_t tmem_acc, uint8_t* staging_gen, uint32_t staging_u32, int ox0,
+                                             int oy0, int n0, int cn0, const float* __restrict__ bias,
+                                             const T* __restrict__ residual, const T* __restrict__ mask_src, uint32_t tempty_bar,
+                                             int warp, int lane, const CUtensorMap* tmY, float* stats_tab, EpiStats* est,
+                                             bool tempty_is_cluster_addr, int trace_lt) {
+  const int q = warp & 3;              // TMEM lane quarter this warp may access
+  const int g = (warp - 2) >> 2;       // 0..1: this warp's 32-column half of each 64-channel half
+  const int row = q * 32 + lane;       // tile row == TMEM lane == pixel within the tile
+  const int et = threadIdx.x - 64;
+  const uint32_t t_row = tmem_acc + ((uint32_t)(q * 32) << 16);
+  const int nchunks = p.bn >> 4;       // 16-column chunks in the tile
+  const int nh = (p.bn + 63) >> 6;
+  const int my_hb = (lane == 0 && (warp - 2) < nh) ? warp - 2 : -1;   // store leader of half my_hb (nh <= 4 <= EPI_WARPS)
+  const int aux_kind_rt = residual ? (p.res_before_act ? EPI_AUX_RES_BEFORE : EPI_AUX_RES_AFTER) : (mask_src ? EPI_AUX_MASK : EPI_AUX_NONE);
+  const bool any_aux = AUX < 0 ? (aux_kind_rt != EPI_AUX_NONE) : (AUX != EPI_AUX_NONE);
+  const T* aux_src = residual ? residual : mask_src;
+  const float neg = p.act == CGB_ACT_NONE ? 1.f : (p.act == CGB_ACT_RELU ? 0.f : p.slope);
+  bool pix_ok = false;
+  long long pix = 0;
+  if (any_aux || GENERIC_CHUNK) {   // only the tiles that read a second tensor need this thread's pixel address
+    const int tw_i = row & ((1 << p.tw_log) - 1);
+    const int th_i = (row >> p.tw_log) & ((1 << p.th_log) - 1);
+    const int tn_i = row >> (p.tw_log + p.th_log);
+    const int ox = ox0 + tw_i, oy = oy0 + th_i, img = n0 + tn_i;
+    pix_ok = (ox < p.wout) && (oy < p.hout) && (img < p.n);
+    pix = ((long long)img * p.hfull + (oy * p.out_stride + p.out_off_y)) * p.wfull + (ox * p.out_stride + p.out_off_x);
+  }
+  const long long pixoff = pix * p.cout_s;
+  const uint32_t row_u32 = staging_u32 + (uint32_t)row * 128u;
+  const uint32_t sw16 = (uint32_t)(row & 7) << 4;
+  uint8_t* my_row = staging_gen + (size_t)row * 128;
+  const bool mask_early = mask_src != nullptr;
+  auto wait_free = [&]() {   // this leader's store that last read the half about to be rewritten has finished reading it
+    if (p.staging_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+  };
+  // one 32-column group = chunks c, c+1 (the tile's last group may hold one chunk: bn is a multiple of 16)
+  auto process = [&](const uint32_t* r, const uint4* x, int c) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (c + k < nchunks) {
+        if (!GENERIC_CHUNK)
+          epi_fast_apply<T, BIAS, ACT, AUX>(p, r + 16 * k, cn0 + (c + k) * 16, (c + k) * 2, neg, aux_kind_rt, bias, x + 2 * k, row_u32, sw16);
+        else
+          epi_chunk(p, r + 16 * k, c + k, cn0, pix_ok, pix, neg, mask_early, bias, residual, mask_src, my_row, row & 7);
+      }
+    }
+  };
+  if (my_hb >= 0 && my_hb < 2) wait_free();
+  epi_bar_sync();
+  if (et == 0) tc_trace(p.trace, trace_lt, 7);
+  for (int hp = 0; hp < nh; hp += 2) {
+    const int c0 = hp * 4 + g * 2, c1 = c0 + 4;   // first chunk of this warp's 32 columns in half hp / hp + 1
+    const bool va = c0 < nchunks, vb = c1 < nchunks;
+    uint32_t ra[32], rb[32];
+    uint4 xa[4], xb[4];
+    if (va) { if (c0 + 1 < nchunks) tmem_ld32(t_row + (uint32_t)(c0 * 16), ra); else tmem_ld16(t_row + (uint32_t)(c0 * 16), ra); }
+    if (vb) { if (c1 + 1 < nchunks) tmem_ld32(t_row + (uint32_t)(c1 * 16), rb); else tmem_ld16(t_row + (uint32_t)(c1 * 16), rb); }
+    if (!GENERIC_CHUNK && any_aux) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (c0 + k < nchunks) epi_fast_fetch<T>(p, cn0 + (c0 + k) * 16, pix_ok, pixoff, aux_src, xa + 2 * k);
+        if (c1 + k < nchunks) epi_fast_fetch<T>(p, cn0 + (c1 + k) * 16, pix_ok, pixoff, aux_src, xb + 2 * k);
+      }
+    }
+    tmem_ld_wait();
+    if (hp + 2 >= nh) {   // this warp's last TMEM read of the tile: hand the accumulator buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0 && !tempty_is_cluster_addr) mbar_arrive(tempty_bar);
+    }
+    if (va) process(ra, xa, c0);
+    if (vb) process(rb, xb, c1);
+    fence_proxy_async_smem();   // this thread's staging writes -> visible to the async proxy
+    if (my_hb >= hp + 2 && my_hb < hp + 4) wait_free();   // the next pair's halves are free
+    epi_bar_sync();             // halves hp, hp+1 staged
+    if (my_hb >= hp && my_hb < hp + 2) {
+      if (cn0 + my_hb * 64 < p.cout_s) tma_store_4d(tmY, staging_u32 + (uint32_t)my_hb * (128u * 128u), cn0 + my_hb * 64, ox0, oy0, n0);
+      tma_store_commit();
+    }
+  }
+  if (et == 0) tc_trace(p.trace, trace_lt, 9);
+  // (2-CTA kernel: ONE remote arrive per CTA on the leader's barrier, after the last barrier — every warp's TMEM reads are
+  //  done; sixteen ~500-cycle cluster arrives per tile and CTA showed up as a slow-down on the short-K 1x1 convs)
+  if (et == 0 && tempty_is_cluster_addr) mbar_arrive_cluster(tempty_bar);
+  if (stats_tab) epilogue_stats<T>(p, staging_gen, true, ox0, oy0, n0, cn0, stats_tab, *est, warp, lane);
+}
+
+template <typename T, int EPI>
 __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_acc, uint8_t* staging_gen, int ox0, int oy0,
                                               int n0, int cn0, const float* __restrict__ bias,
                                               const T* __restrict__ residual,
                                               const T* __restrict__ mask_src, T* __restrict__ y,
                                               uint32_t tempty_bar, int warp, int lane, const CUtensorMap* tmY = nullptr,
                                               uint32_t staging_u32 = 0, float* stats_tab = nullptr, EpiStats* est = nullptr,
-                                              bool tempty_is_cluster_addr = false) {
+                                              bool tempty_is_cluster_addr = false, int trace_lt = 1 << 20) {
+  if constexpr (EPI != EPI_NOTMA) {
+    // EPI: the launch's epilogue variant, chosen on the host (epi_variant_for) and compiled into the kernel
+#define CGB_EPI_TILE(B, A, X, G)                                                                                                   \
+  epi_tma_tile<T, B, A, X, G>(p, tmem_acc, staging_gen, staging_u32, ox0, oy0, n0, cn0, bias, residual, mask_src, tempty_bar, warp, \
+                              lane, tmY, stats_tab, est, tempty_is_cluster_addr, trace_lt)
+    if constexpr (EPI == EPI_PLAIN) CGB_EPI_TILE(0, 0, EPI_AUX_NONE, false);              // conv -> BatchNorm (ResNet), plain dgrad
+    else if constexpr (EPI == EPI_BIAS) CGB_EPI_TILE(1, 0, EPI_AUX_NONE, false);          // gamma || beta, last layers
+    else if constexpr (EPI == EPI_BIAS_ACT) CGB_EPI_TILE(1, 1, EPI_AUX_NONE, false);      // conv + bias + (leaky) ReLU
+    else if constexpr (EPI == EPI_MASK_RELU) CGB_EPI_TILE(0, 0, EPI_AUX_MASK_RELU, false);    // dgrad through ReLU (CGB_MASK_TMA=1)
+    else if constexpr (EPI == EPI_MASK_LRELU) CGB_EPI_TILE(0, 0, EPI_AUX_MASK_LRELU, false);  // dgrad through LeakyReLU (painter, D)
+    else if constexpr (EPI == EPI_EXOTIC) CGB_EPI_TILE(-1, -1, -1, true);                 // tanh / sigmoid / selu: generic chunk code
+    else CGB_EPI_TILE(-1, -1, -1, false);                                                 // run-time flags (residual adds, ...)
+#undef CGB_EPI_TILE
+    return;
+  } else {
   const int q = warp & 3;              // TMEM lane quarter this warp may access
   const int half = (warp - 2) >> 2;    // EPI_PER_Q warps share a quarter: 16-column chunks interleaved among them
   const int row = q * 32 + lane;       // tile row == TMEM lane == pixel within the tile
@@ -445,48 +688,28 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
   const int ox = ox0 + tw_i, oy = oy0 + th_i, img = n0 + tn_i;
   const bool pix_ok = (ox < p.wout) && (oy < p.hout) && (img < p.n);
   const long long pix = ((long long)img * p.hfull + (oy * p.out_stride + p.out_off_y)) * p.wfull + (ox * p.out_stride + p.out_off_x);
-  const bool mask_late = (mask_src != nullptr) && (p.dact == CGB_ACT_RELU);  // 0/1 mask: exact on bf16
+  const bool mask_late = (mask_src != nullptr) && (p.dact == CGB_ACT_RELU) && (tmY == nullptr);  // 0/1 mask at the per-thread copy-out
   const bool mask_early = (mask_src != nullptr) && !mask_late;
   const float neg = p.act == CGB_ACT_NONE ? 1.f : (p.act == CGB_ACT_RELU ? 0.f : p.slope);
 
-  const bool tma = tmY != nullptr;
-  if (tma && et == 0) {  // the bulk store that last read THIS staging tile has finished reading it
-    if (p.staging_bufs == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
-  }
-  epi_bar_sync();  // previous tile's copy-out has finished reading the staging buffer
   const uint32_t t_row = tmem_acc + ((uint32_t)(q * 32) << 16);
-  uint8_t* my_row = staging_gen + (size_t)row * (tma ? 128 : p.stage_pitch);
-  const int sw = tma ? (row & 7) : -1;
   const int nchunks = p.bn >> 4;
+  // ---- per-thread copy-out from a padded row-major staging tile (strided parity-class dgrad, N tiles that are not whole halves) --
+  epi_bar_sync();  // previous tile's copy-out has finished reading the staging buffer
+  uint8_t* my_row = staging_gen + (size_t)row * p.stage_pitch;
   for (int c = half; c < nchunks; c += 2 * EPI_PER_Q) {
     uint32_t ra[16], rb[16];
     const bool two = (c + EPI_PER_Q) < nchunks;
     tmem_ld16(t_row + (uint32_t)(c * 16), ra);
     if (two) tmem_ld16(t_row + (uint32_t)((c + EPI_PER_Q) * 16), rb);
     tmem_ld_wait();
-    epi_chunk(p, ra, c, cn0, pix_ok, pix, neg, mask_early, bias, residual, mask_src, my_row, sw);
-    if (two) epi_chunk(p, rb, c + EPI_PER_Q, cn0, pix_ok, pix, neg, mask_early, bias, residual, mask_src, my_row, sw);
+    epi_chunk(p, ra, c, cn0, pix_ok, pix, neg, mask_early, bias, residual, mask_src, my_row, -1);
+    if (two) epi_chunk(p, rb, c + EPI_PER_Q, cn0, pix_ok, pix, neg, mask_early, bias, residual, mask_src, my_row, -1);
   }
   // accumulator buffer drained: hand it back to the MMA warp
   tc_fence_before();
   __syncwarp();
   if (lane == 0 && !tempty_is_cluster_addr) mbar_arrive(tempty_bar);
-  // (2-CTA kernel: ONE remote arrive per CTA on the leader's barrier, by thread 0 of the group after the staging barrier below —
-  //  sixteen ~500-cycle cluster arrives per tile and CTA showed up as a slow-down on the short-K 1x1 convs)
-  if (tma) {
-    // copy-out by the TMA unit: one bulk tensor store per 64-channel half of the tile; image borders, the batch tail and the
-    // channel tail are clipped by the tensor map, so no thread computes an address
-    fence_proxy_async_smem();   // this thread's staging writes -> visible to the async proxy
-    epi_bar_sync();             // staging complete (and every warp's TMEM reads are done)
-    if (et == 0 && tempty_is_cluster_addr) mbar_arrive_cluster(tempty_bar);
-    if (et == 0) {
-      for (int hb = 0; hb * 64 < p.bn; ++hb)
-        if (cn0 + hb * 64 < p.cout_s) tma_store_4d(tmY, staging_u32 + (uint32_t)hb * (128u * 128u), cn0 + hb * 64, ox0, oy0, n0);
-      tma_store_commit();
-    }
-    if (stats_tab) epilogue_stats<T>(p, staging_gen, true, ox0, oy0, n0, cn0, stats_tab, *est, warp, lane);
-    return;
-  }
   epi_bar_sync();  // staging complete
   if (et == 0 && tempty_is_cluster_addr) mbar_arrive_cluster(tempty_bar);
   if (stats_tab) epilogue_stats<T>(p, staging_gen, false, ox0, oy0, n0, cn0, stats_tab, *est, warp, lane);
@@ -521,6 +744,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
       *reinterpret_cast<uint4*>(y + off) = val;
     }
   }
+  }   // EPI_NOTMA
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -528,8 +752,8 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
 // Persistent: grid = min(#tiles, #SMs); CTA c processes tiles c, c+grid, ...
 // smem: [stages x (A 16 KB | B bn*128 B)] [staging 128 x (bn*2+16) B] [barriers]
 // ------------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(TC_THREADS)
+template <typename T, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const T* __restrict__ residual,
                const T* __restrict__ mask_src, T* __restrict__ y, float* __restrict__ stats_out) {
@@ -583,7 +807,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one_sync()) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
         const int nt = tile % p.n_tiles;
         const int pt = tile / p.n_tiles;
         const int tx = pt % p.tiles_x;
@@ -591,6 +816,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int tn = pt / (p.tiles_x * p.tiles_y);
         const int ox0 = tx << p.tw_log, oy0 = ty << p.th_log, n0 = tn << tn_log;
         const int cn0 = nt * p.bn;
+        tc_trace(p.trace, lt, 0);
         for (int tap = 0; tap < taps; ++tap) {
           const int cx = ox0 * p.stride + p.tap_dx[tap];
           const int cy = oy0 * p.stride + p.tap_dy[tap];
@@ -604,6 +830,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (++s == p.stages) { s = 0; ph ^= 1u; }
           }
         }
+        tc_trace(p.trace, lt, 1);
       }
     }
   } else if (warp == 1) {
@@ -619,11 +846,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t bph = (uint32_t)(lt >> 1) & 1u;
       mbar_wait(tempty_bar(buf), bph ^ 1u);  // epilogue has drained this accumulator buffer
       tc_fence_after();
+      if (lane == 0) tc_trace(p.trace, lt, 2);
       const uint32_t d_addr = tmem_base + (uint32_t)(buf * p.bn);
       int kb = 0;
       for (int it = 0; it < iters; ++it) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
+        if (lane == 0 && it == 0) tc_trace(p.trace, lt, 3);
+        if (lane == 0 && it == iters - 1) tc_trace(p.trace, lt, 4);
         if (elect_one_sync()) {
           const int ksteps = (kb == p.kblocks - 1) ? ksteps_last : 4;
           const uint32_t a_addr = base + (uint32_t)s * stage_bytes;
@@ -653,19 +883,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
       const uint32_t bph = (uint32_t)(lt >> 1) & 1u;
-      const int nt = tile % p.n_tiles;
-      const int pt = tile / p.n_tiles;
-      const int tx = pt % p.tiles_x;
-      const int ty = (pt / p.tiles_x) % p.tiles_y;
-      const int tn = pt / (p.tiles_x * p.tiles_y);
+      const int pt = (int)fdiv((uint32_t)tile, (uint32_t)p.n_tiles, p.mg_nt);
+      const int nt = tile - pt * p.n_tiles;
+      const int py = (int)fdiv((uint32_t)pt, (uint32_t)p.tiles_x, p.mg_tx);
+      const int tx = pt - py * p.tiles_x;
+      const int tn = (int)fdiv((uint32_t)py, (uint32_t)p.tiles_y, p.mg_ty);
+      const int ty = py - tn * p.tiles_y;
+      if (threadIdx.x == 64) tc_trace(p.trace, lt, 5);
       mbar_wait(tfull_bar(buf), bph);
       tc_fence_after();
+      if (threadIdx.x == 64) tc_trace(p.trace, lt, 6);
       const uint32_t sb = (p.staging_bufs == 2) ? (uint32_t)(lt & 1) * staging_tile : 0u;
-      epilogue_tile<T>(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen + sb, tx << p.tw_log, ty << p.th_log, tn << tn_log,
+      epilogue_tile<T, EPI>(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen + sb, tx << p.tw_log, ty << p.th_log, tn << tn_log,
                     nt * p.bn, bias, residual, mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr,
-                    staging + sb, stats_tab, &est);
+                    staging + sb, stats_tab, &est, false, lt);
+      if (threadIdx.x == 64) tc_trace(p.trace, lt, 10);
     }
-    if (p.tma_store && threadIdx.x == 64) tma_store_wait_all();   // the issuing thread: every bulk store has completed
+    if (p.tma_store && lane == 0 && warp < 6) tma_store_wait_all();   // every store leader: its bulk stores have completed   // the issuing thread: every bulk store has completed
     if (stats_tab) {   // fold the registers, then write the CTA's table: one plain store per entry (a CTA without tiles writes zeros)
       epi_stats_flush(p, est, stats_tab);
       epi_bar_sync();
@@ -703,8 +937,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   tfull[b]  (both): same multicast commit after the last MMA of a tile — each CTA's epilogue drains its own TMEM half;
 //   tempty[b] (leader's is used): every epilogue warp of BOTH CTAs arrives on it (the peer's through mapa'd cluster addresses).
 // The MMA is issued by the leader's warp 1 only; the peer's warp 1 just takes part in the paired TMEM allocation.
-template <typename T>
-__global__ void __launch_bounds__(TC_THREADS)
+template <typename T, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const T* __restrict__ residual,
                 const T* __restrict__ mask_src, T* __restrict__ y, float* __restrict__ stats_out) {
@@ -760,11 +994,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   // decode pair tile -> this CTA's pixel tile (out of range: n0 >= n, every load zero-filled, every store clipped)
   auto decode = [&](int pt_tile, int& ox0, int& oy0, int& n0, int& cn0) {
-    const int nt = pt_tile % p.n_tiles;
-    const int pt = (pt_tile / p.n_tiles) * 2 + (int)rank;
-    const int tx = pt % p.tiles_x;
-    const int ty = (pt / p.tiles_x) % p.tiles_y;
-    const int tn = pt / (p.tiles_x * p.tiles_y);
+    const int pq = (int)fdiv((uint32_t)pt_tile, (uint32_t)p.n_tiles, p.mg_nt);
+    const int nt = pt_tile - pq * p.n_tiles;
+    const int pt = pq * 2 + (int)rank;
+    const int py = (int)fdiv((uint32_t)pt, (uint32_t)p.tiles_x, p.mg_tx);
+    const int tx = pt - py * p.tiles_x;
+    const int tn = (int)fdiv((uint32_t)py, (uint32_t)p.tiles_y, p.mg_ty);
+    const int ty = py - tn * p.tiles_y;
     ox0 = tx << p.tw_log; oy0 = ty << p.th_log; n0 = tn << tn_log; cn0 = nt * p.bn;
   };
 
@@ -846,10 +1082,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(tfull_bar(buf), bph);
       tc_fence_after();
       const uint32_t sb = (p.staging_bufs == 2) ? (uint32_t)(lt & 1) * staging_tile : 0u;
-      epilogue_tile<T>(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen + sb, ox0, oy0, n0, cn0, bias, residual, mask_src, y,
+      epilogue_tile<T, EPI>(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen + sb, ox0, oy0, n0, cn0, bias, residual, mask_src, y,
                        mapa_rank(tempty_bar(buf), 0), warp, lane, p.tma_store ? &tmY : nullptr, staging + sb, stats_tab, &est, true);
     }
-    if (p.tma_store && threadIdx.x == 64) tma_store_wait_all();
+    if (p.tma_store && lane == 0 && warp < 6) tma_store_wait_all();   // every store leader: its bulk stores have completed
     if (stats_tab) {
       epi_stats_flush(p, est, stats_tab);
       epi_bar_sync();
@@ -886,8 +1122,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // Tile = 16 rows x 8 pixels (each 8-row swizzle group is one image-row segment).
 // smem: [weights] [stages x halo tile] [staging] [barriers].  grid is a multiple of n_tiles; CTA c keeps n-tile c % n_tiles.
 // ------------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(TC_THREADS)
+template <typename T, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const T* __restrict__ residual,
                const T* __restrict__ mask_src, T* __restrict__ y, float* __restrict__ stats_out) {
@@ -1013,15 +1249,16 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int pt = pt0; pt < p.pix_tiles; pt += pt_step, ++lt) {
       const int buf = lt & 1;
       const uint32_t bph = (uint32_t)(lt >> 1) & 1u;
-      const int tx = pt % p.tiles_x;
-      const int ty = (pt / p.tiles_x) % p.tiles_y;
-      const int img = pt / (p.tiles_x * p.tiles_y);
+      const int py = (int)fdiv((uint32_t)pt, (uint32_t)p.tiles_x, p.mg_tx);
+      const int tx = pt - py * p.tiles_x;
+      const int img = (int)fdiv((uint32_t)py, (uint32_t)p.tiles_y, p.mg_ty);
+      const int ty = py - img * p.tiles_y;
       mbar_wait(tfull_bar(buf), bph);
       tc_fence_after();
-      epilogue_tile<T>(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen, tx << 3, ty << 4, img, cn0, bias, residual,
+      epilogue_tile<T, EPI>(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen, tx << 3, ty << 4, img, cn0, bias, residual,
                     mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr, staging, stats_tab, &est);
     }
-    if (p.tma_store && threadIdx.x == 64) tma_store_wait_all();
+    if (p.tma_store && lane == 0 && warp < 6) tma_store_wait_all();   // every store leader: its bulk stores have completed
     if (stats_tab) {
       epi_stats_flush(p, est, stats_tab);
       epi_bar_sync();
@@ -1126,7 +1363,10 @@ static bool tma_store_enabled() {
   return v != 0;
 }
 static bool tma_store_ok(int bn, int n_tiles, int dact, const void* mask_src) {
-  return tma_store_enabled() && (bn % 64 == 0 || n_tiles == 1) && !(mask_src && dact == CGB_ACT_RELU);
+  // the ReLU-derivative mask stays at the per-thread copy-out, where its loads are coalesced (consecutive lanes = consecutive chunks
+  // of a pixel): read row-per-thread in phase 1 it cost 32 sectors in 32 lines per LDG (256->256 d2 dgrad: 54 -> 71 us)
+  static const int mask_tma = getenv("CGB_MASK_TMA") ? atoi(getenv("CGB_MASK_TMA")) : 0;
+  return tma_store_enabled() && (bn % 64 == 0 || n_tiles == 1) && (mask_tma || !(mask_src && dact == CGB_ACT_RELU));
 }
 static int staging_tile_bytes_for(int bn, bool tma) {
   const int plain = 128 * (bn * 2 + 16);
@@ -1165,6 +1405,49 @@ bool conv_tc_supported(const cgb_conv_desc* d, int which) {
   return d->stride <= 2 && d->co <= 2048;  // wgrad
 }
 
+// ---- epilogue variant of a launch (template parameter EPI of the kernels) ---------------------------------------------------
+static int epi_variant_for(bool tma_store, bool f16, const float* bias, const void* residual, const void* mask_src, int act, int dact) {
+  static const int on = getenv("CGB_EPI_VARIANTS") ? atoi(getenv("CGB_EPI_VARIANTS")) : 1;
+  if (!tma_store) return EPI_NOTMA;
+  if (act > CGB_ACT_LRELU || (residual && mask_src)) return EPI_EXOTIC;
+  if (!on || f16 || residual) return EPI_GENERIC;   // (fp16: inference-only mode, run-time flags)
+  if (mask_src) {
+    if (bias || act != CGB_ACT_NONE) return EPI_GENERIC;
+    return dact == CGB_ACT_RELU ? EPI_MASK_RELU : (dact == CGB_ACT_LRELU ? EPI_MASK_LRELU : EPI_GENERIC);
+  }
+  if (!bias) return act == CGB_ACT_NONE ? EPI_PLAIN : EPI_GENERIC;
+  return act == CGB_ACT_NONE ? EPI_BIAS : EPI_BIAS_ACT;
+}
+
+typedef void (*TcKernelBf16)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const float*, const __nv_bfloat16*,
+                             const __nv_bfloat16*, __nv_bfloat16*, float*);
+typedef void (*TcKernelF16)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const float*, const __half*,
+                            const __half*, __half*, float*);
+#define CGB_KERNEL_TABLES(NAME, KERNEL)                                                  \
+  static TcKernelBf16 NAME##_bf16(int epi) {                                             \
+    switch (epi) {                                                                       \
+      case EPI_PLAIN: return KERNEL<__nv_bfloat16, EPI_PLAIN>;                           \
+      case EPI_BIAS: return KERNEL<__nv_bfloat16, EPI_BIAS>;                             \
+      case EPI_BIAS_ACT: return KERNEL<__nv_bfloat16, EPI_BIAS_ACT>;                     \
+      case EPI_MASK_RELU: return KERNEL<__nv_bfloat16, EPI_MASK_RELU>;                   \
+      case EPI_MASK_LRELU: return KERNEL<__nv_bfloat16, EPI_MASK_LRELU>;                 \
+      case EPI_EXOTIC: return KERNEL<__nv_bfloat16, EPI_EXOTIC>;                         \
+      case EPI_NOTMA: return KERNEL<__nv_bfloat16, EPI_NOTMA>;                           \
+      default: return KERNEL<__nv_bfloat16, EPI_GENERIC>;                                \
+    }                                                                                    \
+  }                                                                                      \
+  static TcKernelF16 NAME##_f16(int epi) {   /* fp16: generic / exotic / per-thread */   \
+    switch (epi) {                                                                       \
+      case EPI_EXOTIC: return KERNEL<__half, EPI_EXOTIC>;                                \
+      case EPI_NOTMA: return KERNEL<__half, EPI_NOTMA>;                                  \
+      default: return KERNEL<__half, EPI_GENERIC>;                                       \
+    }                                                                                    \
+  }
+CGB_KERNEL_TABLES(stream_kernel, conv_tc_kernel)
+CGB_KERNEL_TABLES(pair_kernel, conv_tc2_kernel)
+CGB_KERNEL_TABLES(ws_kernel, conv_tc_ws_kernel)
+#undef CGB_KERNEL_TABLES
+
 // ---- streaming launch with an explicit tap table and output mapping ---------------------------------------------
 struct TapTable {
   int ntaps;
@@ -1197,6 +1480,9 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
   p.bn = pick_bn(cout_s);
   p.n_tiles = (cout_s + p.bn - 1) / p.bn;
   p.total_tiles = p.tiles_x * p.tiles_y * tiles_n * p.n_tiles;
+  p.mg_nt = magic_for(p.total_tiles + 2, p.n_tiles);
+  p.mg_tx = magic_for(p.total_tiles + 2, p.tiles_x);
+  p.mg_ty = magic_for(p.total_tiles + 2, p.tiles_y);
   p.stage_pitch = p.bn * 2 + 16;
   // TMA-store copy-out: plain output mapping only (the strided parity-class dgrad keeps the per-thread copy-out)
   p.tma_store = (tma_store_ok(p.bn, p.n_tiles, dact, mask_src) && out_stride == 1 && out_off_y == 0 && out_off_x == 0 &&
@@ -1239,17 +1525,20 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
   }
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(conv_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
-    cudaFuncSetAttribute(conv_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    for (int e = 0; e < EPI_VARIANTS; ++e) {
+      cudaFuncSetAttribute(stream_kernel_bf16(e), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+      cudaFuncSetAttribute(stream_kernel_f16(e), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    }
   });
   // ---- CTA-pair form (cta_group::2): half a weight tile per CTA — for launches with enough pixel tiles to fill 74 pairs
   static const int tc2 = getenv("CGB_TC2") ? atoi(getenv("CGB_TC2")) : 1;
   {
     const int pix_tiles = p.total_tiles / p.n_tiles;
     const int pair_tiles = ((pix_tiles + 1) / 2) * p.n_tiles;
-    // measured (scripts/exp/tc2_check.py, profiles/r02_tc2_pair_kernel.txt): the pair form wins on long reductions (ASPP 2048->256
-    // d12: 382 -> 324 us) and loses on short-K 1x1 convs (256->1024: 61 -> 68 us): CGB_TC2=1 takes it from tc2_min_k on, 2 always
-    static const int tc2_min_k = getenv("CGB_TC2_MIN_K") ? atoi(getenv("CGB_TC2_MIN_K")) : 2048;
+    // measured (scripts/exp/tc2_check.py, profiles/r02_tc2_pair_kernel.txt; with the compile-time epilogue variants:
+    // gpurun_out/g24_*.txt): the pair form wins from K = 512 on (512->2048 1x1: 108 -> 104 us, 128->160 3x3: 77 -> 70, ASPP
+    // 2048->256 d12: 386 -> 325) and loses at K = 256 (256->1024: 45 -> 53 us): CGB_TC2=1 takes it from tc2_min_k on, 2 always
+    static const int tc2_min_k = getenv("CGB_TC2_MIN_K") ? atoi(getenv("CGB_TC2_MIN_K")) : 512;
     const bool k_ok = tc2 >= 2 || (long long)tt.ntaps * cin_s >= tc2_min_k;
     if (tc2 && k_ok && p.bn % 16 == 0 && pair_tiles >= num_sms() / 2) {
       const int stage2 = A_TILE_BYTES + p.bn * 64;
@@ -1268,8 +1557,10 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
       const size_t smem2 = (size_t)stages2 * stage2 + staging_bytes + 16 * stages2 + 64 + stats_bytes + 1024;
       static std::once_flag attr2_once;
       std::call_once(attr2_once, [] {
-        cudaFuncSetAttribute(conv_tc2_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
-        cudaFuncSetAttribute(conv_tc2_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+        for (int e = 0; e < EPI_VARIANTS; ++e) {
+          cudaFuncSetAttribute(pair_kernel_bf16(e), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+          cudaFuncSetAttribute(pair_kernel_f16(e), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+        }
       });
       int npairs = num_sms() / 2;
       if (npairs > pair_tiles) npairs = pair_tiles;
@@ -1285,11 +1576,12 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       cudaError_t e;
+      const int epi2 = epi_variant_for(p.tma_store != 0, f16, bias, residual, mask_src, act, dact);
       if (f16)
-        e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<__half>, tmA, tmB, tmY, p, bias, (const __half*)residual, (const __half*)mask_src,
+        e = cudaLaunchKernelEx(&cfg, pair_kernel_f16(epi2), tmA, tmB, tmY, p, bias, (const __half*)residual, (const __half*)mask_src,
                                (__half*)out, stats_out);
       else
-        e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<__nv_bfloat16>, tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
+        e = cudaLaunchKernelEx(&cfg, pair_kernel_bf16(epi2), tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
                                (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
       if (e != cudaSuccess) {
         cudaGetLastError();
@@ -1305,12 +1597,34 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
     return CGB_UNSUPPORTED;
   }
   dim3 grid((unsigned)(p.total_tiles < num_sms() ? p.total_tiles : num_sms()));
+  // debug only (CGB_TC_TRACE=1): per-role clock64 stamps of CTA 0, printed after a synchronisation — never on in production
+  static const int tc_trace_on = getenv("CGB_TC_TRACE") ? atoi(getenv("CGB_TC_TRACE")) : 0;
+  static unsigned long long* trace_buf = nullptr;
+  if (tc_trace_on) {
+    if (!trace_buf) cudaMallocManaged(&trace_buf, 32 * 16 * sizeof(unsigned long long));
+    cudaStreamSynchronize(st);
+    memset(trace_buf, 0, 32 * 16 * sizeof(unsigned long long));
+    p.trace = trace_buf;
+  }
+  const int epi = epi_variant_for(p.tma_store != 0, f16, bias, residual, mask_src, act, dact);
   if (f16)
-    conv_tc_kernel<__half><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __half*)residual, (const __half*)mask_src,
+    stream_kernel_f16(epi)<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __half*)residual, (const __half*)mask_src,
                                                            (__half*)out, stats_out);
   else
-    conv_tc_kernel<__nv_bfloat16><<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
-                                                                  (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
+    stream_kernel_bf16(epi)<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
+                                                            (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
+  if (tc_trace_on) {
+    cudaStreamSynchronize(st);
+    const unsigned long long t0 = trace_buf[0];
+    fprintf(stderr, "[tc_trace] bn=%d n_tiles=%d tiles=%d stages=%d iters=%d tma_store=%d staging_bufs=%d\n", p.bn, p.n_tiles,
+            p.total_tiles, p.stages, p.ntaps * p.kblocks, p.tma_store, p.staging_bufs);
+    fprintf(stderr, "[tc_trace] tile: P.start P.issued | M.tempty M.full0 M.fullN | E.wait E.tfull E.stg_free E.ph1 E.bar E.done (cycles since start)\n");
+    for (int t = 0; t < 32 && trace_buf[t * 16] != 0; ++t) {
+      fprintf(stderr, "[tc_trace] %2d:", t);
+      for (int k = 0; k <= 15; ++k) fprintf(stderr, " %7lld%s", (long long)(trace_buf[t * 16 + k] - t0), (k == 1 || k == 4 || k == 10) ? " |" : "");
+      fprintf(stderr, "\n");
+    }
+  }
   return after_launch("conv_tc");
 }
 
@@ -1393,12 +1707,16 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
   p.stats_rows = num_sms();
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
-    cudaFuncSetAttribute(conv_tc_ws_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
-    cudaFuncSetAttribute(conv_tc_ws_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    for (int e = 0; e < EPI_VARIANTS; ++e) {
+      cudaFuncSetAttribute(ws_kernel_bf16(e), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+      cudaFuncSetAttribute(ws_kernel_f16(e), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LIMIT);
+    }
   });
   p.tw_log = 3; p.th_log = 4;
   p.tiles_x = (wout + 7) / 8; p.tiles_y = (hout + 15) / 16;
   p.pix_tiles = p.tiles_x * p.tiles_y * n;
+  p.mg_tx = magic_for(p.pix_tiles + 2, p.tiles_x);
+  p.mg_ty = magic_for(p.pix_tiles + 2, p.tiles_y);
   p.bn = ws_bn; p.n_tiles = ws_ntiles; p.stages = ws_stages;
   p.twh = twh; p.thh = thh; p.a_stage_bytes = a_stage;
   p.stage_pitch = p.bn * 2 + 16;
@@ -1436,12 +1754,13 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
   const size_t smem = (size_t)p.stats_off + stats_bytes + 1024;
   int ctas = num_sms() / p.n_tiles * p.n_tiles;
   if (ctas > p.pix_tiles * p.n_tiles) ctas = p.pix_tiles * p.n_tiles;
+  const int epi = epi_variant_for(p.tma_store != 0, f16, bias, residual, mask_src, act, dact);
   if (f16)
-    conv_tc_ws_kernel<__half><<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __half*)residual,
-                                                              (const __half*)mask_src, (__half*)out, stats_out);
+    ws_kernel_f16(epi)<<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __half*)residual, (const __half*)mask_src,
+                                                       (__half*)out, stats_out);
   else
-    conv_tc_ws_kernel<__nv_bfloat16><<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
-                                                                     (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
+    ws_kernel_bf16(epi)<<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
+                                                        (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
   return after_launch("conv_tc_ws");
 }
 

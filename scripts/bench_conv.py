@@ -41,7 +41,7 @@ for name in names:
     ho, wo = (h + 2 * pad - dil * (k - 1) - 1) // stride + 1, (w + 2 * pad - dil * (k - 1) - 1) // stride + 1
     x = torch.randn(n, h, w, ci, device=dev).bfloat16()
     wp = (torch.randn(co, k * k, ci, device=dev) * 0.05).bfloat16()
-    bias = torch.zeros(co, device=dev)
+    bias = None if os.environ.get("NOBIAS") else torch.zeros(co, device=dev)
     g = ops.ConvGeom(k, k, stride, dil, pad, _lib.PAD_ZERO, _lib.ACT_NONE, 0.2, _lib.ENGINE_AUTO)
     gy = torch.randn(n, ho, wo, co, device=dev).bfloat16()
     def run():

@@ -22,7 +22,7 @@ ev = prof.key_averages()
 rows = sorted(((e.device_time_total, e.count, e.key) for e in ev if e.device_time_total > 0 and e.device_type.name == "CUDA"), reverse=True)
 tot = sum(r[0] for r in rows)
 print(f"total CUDA kernel time {tot/1e3:.2f} ms over {sum(r[1] for r in rows)} launches")
-for tme, cnt, key in rows[:60]:
+for tme, cnt, key in rows[:150]:
     print(f"{tme/1e3:9.3f} ms {cnt:5d}x  {key[:120]}")
 cpu_rows = sorted(((e.self_cpu_time_total, e.count, e.key) for e in ev if e.self_cpu_time_total > 0), reverse=True)
 print(f"--- host side: self CPU time by op (total {sum(r[0] for r in cpu_rows)/1e3:.1f} ms)")
