@@ -697,6 +697,37 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
   // ---- per-thread copy-out from a padded row-major staging tile (strided parity-class dgrad, N tiles that are not whole halves) --
   epi_bar_sync();  // previous tile's copy-out has finished reading the staging buffer
   uint8_t* my_row = staging_gen + (size_t)row * p.stage_pitch;
+  // lean phase 1 for the common case of this path — the ReLU-masked dgrad (no bias, no activation, no residual; the 0/1 mask is
+  // applied by phase 2): 32-column accumulator loads, pack, 16-byte staging stores with 32-bit shared addresses
+  const bool lean = !bias && p.act == CGB_ACT_NONE && !residual && !mask_early;
+  if (lean) {
+    const uint32_t row_u32 = staging_u32 + (uint32_t)row * (uint32_t)p.stage_pitch;
+    const int ngroups = (nchunks + 1) >> 1;   // 32-column groups (the last may hold one 16-column chunk)
+    for (int ga = half; ga < ngroups; ga += 2 * EPI_PER_Q) {
+      const int gb = ga + EPI_PER_Q;
+      uint32_t ra[32], rb[32];
+      const bool fa = ga * 2 + 1 < nchunks, vb = gb < ngroups, fb = vb && (gb * 2 + 1 < nchunks);
+      if (fa) tmem_ld32(t_row + (uint32_t)(ga * 32), ra); else tmem_ld16(t_row + (uint32_t)(ga * 32), ra);
+      if (vb) { if (fb) tmem_ld32(t_row + (uint32_t)(gb * 32), rb); else tmem_ld16(t_row + (uint32_t)(gb * 32), rb); }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < 2 || fa)
+          sts128(row_u32 + (uint32_t)(ga * 64 + j * 16), pack2<T>(__uint_as_float(ra[8 * j]), __uint_as_float(ra[8 * j + 1])),
+                 pack2<T>(__uint_as_float(ra[8 * j + 2]), __uint_as_float(ra[8 * j + 3])),
+                 pack2<T>(__uint_as_float(ra[8 * j + 4]), __uint_as_float(ra[8 * j + 5])),
+                 pack2<T>(__uint_as_float(ra[8 * j + 6]), __uint_as_float(ra[8 * j + 7])));
+      if (vb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < 2 || fb)
+            sts128(row_u32 + (uint32_t)(gb * 64 + j * 16), pack2<T>(__uint_as_float(rb[8 * j]), __uint_as_float(rb[8 * j + 1])),
+                   pack2<T>(__uint_as_float(rb[8 * j + 2]), __uint_as_float(rb[8 * j + 3])),
+                   pack2<T>(__uint_as_float(rb[8 * j + 4]), __uint_as_float(rb[8 * j + 5])),
+                   pack2<T>(__uint_as_float(rb[8 * j + 6]), __uint_as_float(rb[8 * j + 7])));
+      }
+    }
+  } else
   for (int c = half; c < nchunks; c += 2 * EPI_PER_Q) {
     uint32_t ra[16], rb[16];
     const bool two = (c + EPI_PER_Q) < nchunks;
@@ -723,25 +754,42 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
   const int ch = cn0 + c * 8;
   if (rsub < rows_per_iter && ch < p.cout_s) {
     const int ew = warp - 2;  // 0..EPI_WARPS-1
-    for (int r2 = ew * rows_per_iter + rsub; r2 < 128; r2 += EPI_WARPS * rows_per_iter) {
-      const int tw2 = r2 & ((1 << p.tw_log) - 1);
-      const int th2 = (r2 >> p.tw_log) & ((1 << p.th_log) - 1);
-      const int tn2 = r2 >> (p.tw_log + p.th_log);
-      const int ox2 = ox0 + tw2, oy2 = oy0 + th2, img2 = n0 + tn2;
-      if (ox2 >= p.wout || oy2 >= p.hout || img2 >= p.n) continue;
-      const long long off = (((long long)img2 * p.hfull + (oy2 * p.out_stride + p.out_off_y)) * p.wfull +
-                             (ox2 * p.out_stride + p.out_off_x)) * p.cout_s + ch;
-      uint4 val = *reinterpret_cast<const uint4*>(staging_gen + (size_t)r2 * p.stage_pitch + (size_t)c * 16);
-      if (mask_late) {  // relu derivative: keep where the forward output was > 0 (packed bf16x2 compare + multiply)
-        const uint4 mk = *reinterpret_cast<const uint4*>(mask_src + off);
-        using T2 = typename Pk<T>::T2;
-        const T2* mh = reinterpret_cast<const T2*>(&mk);
-        T2* vh = reinterpret_cast<T2*>(&val);
-        const T2 zero2 = Pk<T>::zero2();
+    // four rows per batch: the four mask loads (DRAM / L2 latency) are in flight together — one load -> multiply -> store chain
+    // per row left ~8 serial global round trips per thread and tile (the 128->48 gamma||beta dgrad at 640^2: 1.2 ms -> see DESIGN)
+    constexpr int PB = 4;
+    const int rstep = EPI_WARPS * rows_per_iter;
+    for (int rb = ew * rows_per_iter + rsub; rb < 128; rb += PB * rstep) {
+      long long off[PB];
+      bool ok[PB];
+      uint4 val[PB], mk[PB];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) vh[j] = __hmul2(vh[j], __hgt2(mh[j], zero2));
+      for (int i = 0; i < PB; ++i) {
+        const int r2 = rb + i * rstep;
+        const int tw2 = r2 & ((1 << p.tw_log) - 1);
+        const int th2 = (r2 >> p.tw_log) & ((1 << p.th_log) - 1);
+        const int tn2 = r2 >> (p.tw_log + p.th_log);
+        const int ox2 = ox0 + tw2, oy2 = oy0 + th2, img2 = n0 + tn2;
+        ok[i] = r2 < 128 && ox2 < p.wout && oy2 < p.hout && img2 < p.n;
+        off[i] = (((long long)img2 * p.hfull + (oy2 * p.out_stride + p.out_off_y)) * p.wfull + (ox2 * p.out_stride + p.out_off_x)) *
+                     p.cout_s + ch;
+        if (ok[i]) {
+          val[i] = *reinterpret_cast<const uint4*>(staging_gen + (size_t)r2 * p.stage_pitch + (size_t)c * 16);
+          if (mask_late) mk[i] = __ldg(reinterpret_cast<const uint4*>(mask_src + off[i]));
+        }
       }
-      *reinterpret_cast<uint4*>(y + off) = val;
+#pragma unroll
+      for (int i = 0; i < PB; ++i) {
+        if (!ok[i]) continue;
+        if (mask_late) {  // relu derivative: keep where the forward output was > 0 (packed bf16x2 compare + multiply)
+          using T2 = typename Pk<T>::T2;
+          const T2* mh = reinterpret_cast<const T2*>(&mk[i]);
+          T2* vh = reinterpret_cast<T2*>(&val[i]);
+          const T2 zero2 = Pk<T>::zero2();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) vh[j] = __hmul2(vh[j], __hgt2(mh[j], zero2));
+        }
+        *reinterpret_cast<uint4*>(y + off[i]) = val[i];
+      }
     }
   }
   }   // EPI_NOTMA
