@@ -166,6 +166,7 @@ SIGNATURES = {
     "cgb_resize_nearest_bwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_im2col_strided": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_im2col": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
+    "cgb_col2im_strided": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_nchw_to_nhwc": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_nhwc_to_nchw": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_act_bwd": ([_P, _P, _P, _I, _L, _I, _F, _P], C.c_int),

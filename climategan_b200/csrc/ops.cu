@@ -1105,6 +1105,49 @@ im2col_kernel(const T* __restrict__ x, T* __restrict__ y, long long total_vec, i
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Adjoint of im2col_kernel (gather form, no atomics): gx[n,y,x,ch] = sum over the taps (dy,dx) and output pixels (oy,ox) with
+// oy*stride + dy*dil - pad == y, ox*stride + dx*dil - pad == x of g[n,oy,ox, tap*c + ch]; channels >= c of gx are zero.  Lets a
+// first-layer conv on an image that NEEDS a data gradient (the discriminator under the generator loss: D(fake) -> G,
+// discriminator.py:122, trainer.py:1421-1440) take the im2col + K = round8(k*k*c) GEMM route of the ResNet stem.
+// One thread per input pixel (the 8-channel storage vector).
+template <typename T>
+__global__ void __launch_bounds__(256)
+col2im_kernel(const T* __restrict__ g, T* __restrict__ gx, long long total_pix, int h, int w, int cs_in, int c, int k, int pad,
+              int dil, int stride, int ho, int wo, int cs_col) {
+  for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < total_pix; pix += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(pix % w);
+    const long long t = pix / w;
+    const int y = (int)(t % h);
+    const long long img = t / h;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int dy = 0; dy < k; ++dy) {
+      const int ny = y + pad - dy * dil;
+      if (ny < 0 || ny % stride) continue;
+      const int oy = ny / stride;
+      if (oy >= ho) continue;
+      for (int dx = 0; dx < k; ++dx) {
+        const int nx = x + pad - dx * dil;
+        if (nx < 0 || nx % stride) continue;
+        const int ox = nx / stride;
+        if (ox >= wo) continue;
+        const T* src = g + ((img * ho + oy) * wo + ox) * cs_col + (dy * k + dx) * c;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j < c) acc[j] += to_f<T>(src[j]);
+      }
+    }
+    for (int v = 0; v < cs_in; v += 8) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = v == 0 ? acc[j] : 0.f;
+      Vec8<T>::store(gx + pix * cs_in + v, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // compositing (generator.py:279-297)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -1435,6 +1478,19 @@ extern "C" int cgb_im2col_strided(const void* x, void* y, int32_t dtype, int32_t
   DISPATCH_T(dtype, im2col_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, total, h, w, cs_in, c,
                                                                                        k, pad, dil, cs_out, stride, ho, wo);)
   return after_launch("im2col_strided");
+}
+
+extern "C" int cgb_col2im_strided(const void* g, void* gx, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t cs_in, int32_t c,
+                                  int32_t k, int32_t pad, int32_t dil, int32_t stride, int32_t cs_col, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(g && gx, "col2im_strided: null pointer");
+  CGB_REQUIRE(cs_in % 8 == 0 && cs_col % 8 == 0 && c >= 1 && c <= 8 && c <= cs_in && k * k * c <= cs_col && stride >= 1,
+              "col2im_strided: bad arguments cs_in=%d c=%d (<= 8) k=%d cs_col=%d stride=%d", cs_in, c, k, cs_col, stride);
+  const int ho = (h + 2 * pad - dil * (k - 1) - 1) / stride + 1, wo = (w + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+  const long long total = (long long)n * h * w;
+  DISPATCH_T(dtype, col2im_kernel<T><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const T*)g, (T*)gx, total, h, w, cs_in, c, k,
+                                                                                       pad, dil, stride, ho, wo, cs_col);)
+  return after_launch("col2im_strided");
 }
 
 extern "C" int cgb_nchw_to_nhwc(const float* x, void* y, int32_t dtype, int32_t n, int32_t c, int32_t hw,

@@ -95,7 +95,10 @@ def _run_group(group: nn.Sequential, x):
     act = _lib.ACT_NONE
     if not has_norm:
         act = _lib.ACT_LRELU if has_lrelu else (_lib.ACT_SIGMOID if has_sigmoid else _lib.ACT_NONE)
-    y = ops.conv2d(x, w, b, stride=inner.stride[0], pad=inner.padding[0], act=act, slope=0.2)
+    if inner.in_channels <= 4:   # model0 on the image (+ mask): im2col + one short-K GEMM (ops.conv2d_first_layer)
+        y = ops.conv2d_first_layer(x, w, b, stride=inner.stride[0], pad=inner.padding[0], act=act, slope=0.2)
+    else:
+        y = ops.conv2d(x, w, b, stride=inner.stride[0], pad=inner.padding[0], act=act, slope=0.2)
     if has_norm:
         y = ops.instnorm_act(y, _lib.ACT_LRELU if has_lrelu else _lib.ACT_NONE, 0.2)
     return y
@@ -206,7 +209,9 @@ def fc_discriminator_forward(net: nn.Sequential, x_nchw, storage_dtype=torch.bfl
         if isinstance(m, (SpectralNorm, nn.Conv2d)):
             w, b = conv_weight_bias(m)
             lrelu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.LeakyReLU)
-            x = ops.conv2d(x, w, b, stride=2, pad=1, act=_lib.ACT_LRELU if lrelu else _lib.ACT_NONE, slope=0.2)
+            inner = m.module if isinstance(m, SpectralNorm) else m
+            conv = ops.conv2d_first_layer if inner.in_channels <= 4 else ops.conv2d   # the entropy-map input: im2col + one GEMM
+            x = conv(x, w, b, stride=2, pad=1, act=_lib.ACT_LRELU if lrelu else _lib.ACT_NONE, slope=0.2)
     return ops.from_storage(x, 1)
 
 

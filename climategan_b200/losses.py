@@ -129,7 +129,10 @@ class Vgg19(nn.Module):
         for k in range(1, 6):
             for m in getattr(self, f"slice{k}"):
                 if isinstance(m, nn.Conv2d):
-                    x = ops.conv2d(x, m.weight, m.bias, pad=1, act=_lib.ACT_RELU)  # conv + the ReLU that follows it
+                    if m.in_channels <= 4:   # conv1_1 on the image: im2col + one K = 32 GEMM
+                        x = ops.conv2d_first_layer(x, m.weight, m.bias, pad=1, act=_lib.ACT_RELU)
+                    else:
+                        x = ops.conv2d(x, m.weight, m.bias, pad=1, act=_lib.ACT_RELU)  # conv + the ReLU that follows it
                 elif isinstance(m, nn.MaxPool2d):
                     x = ops.maxpool2(x)
             outs.append(x)

@@ -288,6 +288,44 @@ def im2col_strided(x: torch.Tensor, c: int, k: int, pad: int, dil: int = 1, stri
     return y
 
 
+class _Im2colStrided(Function):
+    """Differentiable :func:`im2col_strided`: backward is the gather-form adjoint ``cgb_col2im_strided``."""
+
+    @staticmethod
+    def forward(ctx, x, c, k, pad, dil, stride):
+        ctx.geom = (tuple(x.shape), c, k, pad, dil, stride)
+        return im2col_strided(x, c, k, pad, dil, stride)
+
+    @staticmethod
+    def backward(ctx, g):
+        (n, h, w, cs), c, k, pad, dil, stride = ctx.geom
+        g = g.contiguous()
+        gx = torch.empty((n, h, w, cs), dtype=g.dtype, device=g.device)
+        check(_L().cgb_col2im_strided(_p(g), _p(gx), _DT[g.dtype], n, h, w, cs, c, k, pad, dil, stride, g.shape[-1], _st()),
+              "col2im_strided")
+        return gx, None, None, None, None, None
+
+
+# first-layer convs on images (<= 4 logical channels in an 8-channel storage vector): as k*k taps of an 8-channel TMA box the
+# tcgen05 engine runs them at a few % of either roofline (the discriminators' 4x4 stride-2 model0 at 640^2: 1.0-1.2 ms against a
+# 24 us HBM bound); as im2col + ONE K = round8(k*k*c) GEMM they are a short-K 1x1 conv.  CGB_IM2COL_FIRST=0 turns the route off.
+_IM2COL_FIRST = os.environ.get("CGB_IM2COL_FIRST", "1") != "0"
+
+
+def conv2d_first_layer(x, w, bias=None, *, stride=1, pad=0, act=_lib.ACT_NONE, slope=0.2):
+    """conv2d for a conv whose input is an image-like storage tensor with w.shape[1] <= 4 logical channels: im2col (differentiable
+    when x needs a gradient) + a 1x1 conv on the patches; falls back to :func:`conv2d` for anything else."""
+    co, cin, k, _ = w.shape
+    n, h, w_, cs = x.shape
+    if not (_IM2COL_FIRST and cin <= 4 and cs == 8 and k >= 3 and min(h, w_) >= 64 and x.dtype != torch.float32):
+        return conv2d(x, w, bias, stride=stride, pad=pad, act=act, slope=slope)
+    xc = _Im2colStrided.apply(x, cin, k, pad, 1, stride) if x.requires_grad else im2col_strided(x, cin, k, pad, 1, stride)
+    kk = k * k * cin
+    w2 = w.permute(0, 2, 3, 1).reshape(co, kk)                     # the patches' tap-major order (autograd-native)
+    w2 = torch.nn.functional.pad(w2, (0, xc.shape[-1] - kk)).view(co, xc.shape[-1], 1, 1)
+    return conv2d(xc, w2, bias, act=act, slope=slope)
+
+
 def act_bwd_raw(gy, y, act, slope):
     gx = torch.empty_like(gy)
     check(_L().cgb_act_bwd(_p(gy), _p(y), _p(gx), _DT[gy.dtype], gy.numel(), act, slope, _st()), "act_bwd")

@@ -200,6 +200,12 @@ int cgb_im2col(const void* x, void* y, int32_t dtype, int32_t n, int32_t h, int3
  * ran at 100 GB/s. */
 int cgb_im2col_strided(const void* x, void* y, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t cs_in, int32_t c,
                        int32_t k, int32_t pad, int32_t dil, int32_t stride, int32_t cs_out, void* stream);
+/* Adjoint of cgb_im2col_strided (gather form, deterministic): gx[n,y,x,ch] = sum of g[n,oy,ox, tap*c + ch] over the taps and output
+ * pixels that read input pixel (y,x); gx is [n,h,w,cs_in] (channels >= c zero), g is [n,ho,wo,cs_col], c <= 8.  With it a
+ * first-layer conv on an image that needs a data gradient — NLayerDiscriminator's model0 under the generator loss, D(fake) -> G
+ * (discriminator.py:122, trainer.py:1421-1440) — runs as im2col + ONE K = round8(k*k*c) GEMM like the ResNet stem. */
+int cgb_col2im_strided(const void* g, void* gx, int32_t dtype, int32_t n, int32_t h, int32_t w, int32_t cs_in, int32_t c,
+                       int32_t k, int32_t pad, int32_t dil, int32_t stride, int32_t cs_col, void* stream);
 
 /* ---- masker (inference) helpers, NHWC storage ---------------------------------------------
  * nn.MaxPool2d(3, stride=2, padding=0, ceil_mode=True) (deeplab/resnetmulti_v2.py:76-78); caller passes ho/wo.

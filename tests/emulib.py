@@ -560,6 +560,16 @@ class EmuLib(NoopLib):
         Y.zero_()
         Y[..., : k * k * c] = cols
 
+    def e_col2im_strided(self, g, gx, dtype, n, h, w, cs_in, c, k, pad, dil, stride, cs_col, stream):
+        dt = _DT[dtype]
+        ho, wo = (h + 2 * pad - dil * (k - 1) - 1) // stride + 1, (w + 2 * pad - dil * (k - 1) - 1) // stride + 1
+        G = _t(g, (n, ho, wo, cs_col), dt).float()[..., : k * k * c]
+        cols = G.reshape(n, ho * wo, k * k, c).permute(0, 3, 2, 1).reshape(n, c * k * k, ho * wo)   # unfold's channel-major order
+        X = F.fold(cols, (h, w), k, dilation=dil, padding=pad, stride=stride)                        # [n, c, h, w]
+        GX = _t(gx, (n, h, w, cs_in), dt)
+        GX.zero_()
+        GX[..., :c] = X.permute(0, 2, 3, 1)
+
     @staticmethod
     def _m_cond(D, S, XR):
         n = D.shape[0]
