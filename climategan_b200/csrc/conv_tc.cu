@@ -1183,7 +1183,7 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t w_bytes = (uint32_t)(p.kblocks * taps) * w_tap_bytes;
   const uint32_t a_base = base + w_bytes;
   const uint32_t staging = a_base + (uint32_t)p.stages * (uint32_t)p.a_stage_bytes;
-  const uint32_t bar_base = staging + (uint32_t)p.staging_tile_bytes;
+  const uint32_t bar_base = staging + (uint32_t)p.staging_tile_bytes * (uint32_t)p.staging_bufs;
   auto full_bar = [&](int s) { return bar_base + 8u * (uint32_t)s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (uint32_t)(p.stages + s); };
   auto tfull_bar = [&](int b) { return bar_base + 16u * (uint32_t)p.stages + 8u * (uint32_t)b; };
@@ -1303,8 +1303,11 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int ty = py - img * p.tiles_y;
       mbar_wait(tfull_bar(buf), bph);
       tc_fence_after();
-      epilogue_tile<T, EPI>(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen, tx << 3, ty << 4, img, cn0, bias, residual,
-                    mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr, staging, stats_tab, &est);
+      // two staging tiles when they fit (launch_fprop): the store of tile i overlaps the staging of tile i+1 — with one, every
+      // tile of a small-channel conv (24->24 at 640^2: 684 cycles of MMAs) waited ~1500 cycles for the previous bulk store
+      const uint32_t sb = (p.staging_bufs == 2) ? (uint32_t)(lt & 1) * (uint32_t)p.staging_tile_bytes : 0u;
+      epilogue_tile<T, EPI>(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen + sb, tx << 3, ty << 4, img, cn0, bias, residual,
+                    mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr, staging + sb, stats_tab, &est);
     }
     if (p.tma_store && lane == 0 && warp < 6) tma_store_wait_all();   // every store leader: its bulk stores have completed
     if (stats_tab) {
@@ -1769,9 +1772,17 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
   p.twh = twh; p.thh = thh; p.a_stage_bytes = a_stage;
   p.stage_pitch = p.bn * 2 + 16;
   p.tma_store = tma_store_ok(p.bn, p.n_tiles, dact, mask_src) ? 1 : 0;
-  p.staging_bufs = 1;
   p.staging_tile_bytes = staging_tile_bytes_for(p.bn, p.tma_store != 0);
-  const int staging_bytes = p.staging_tile_bytes;
+  {
+    // second staging tile if at least three activation stages remain (ws_stages was sized with one tile)
+    static const int ws_stg2 = getenv("CGB_WS_STAGING2") ? atoi(getenv("CGB_WS_STAGING2")) : 1;
+    const size_t fixed2 = (size_t)kblocks * taps * p.bn * 128 + 2 * (size_t)p.staging_tile_bytes + 1024 + 256 + stats_bytes;
+    int stg2 = fixed2 < SMEM_LIMIT ? (int)((SMEM_LIMIT - fixed2) / a_stage) : 0;
+    if (stg2 > 6) stg2 = 6;
+    p.staging_bufs = (ws_stg2 && p.tma_store && stg2 >= 3) ? 2 : 1;
+    if (p.staging_bufs == 2) p.stages = stg2;
+  }
+  const int staging_bytes = p.staging_tile_bytes * p.staging_bufs;
   int cols = 32;
   while (cols < 2 * p.bn) cols <<= 1;
   p.tmem_cols = cols;

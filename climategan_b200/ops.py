@@ -266,13 +266,25 @@ def instnorm_stats(x: torch.Tensor, eps: float = 1e-5) -> Tuple[torch.Tensor, to
 
 
 def im2col(x: torch.Tensor, c: int, k: int = 3, pad: int = 1, dil: int = 1) -> torch.Tensor:
-    """[N,H,W,Cs] storage tensor with c logical channels -> [N,H,W,round8(k*k*c)] patches (tap-major)."""
+    """[N,H,W,Cs] storage tensor with c logical channels -> [N,H,W,round8(k*k*c)] patches (tap-major).
+
+    When the rounding leaves a spare channel, channel k*k*c is set to ONE (a "bias tap"): the packed weight of the GEMM that
+    consumes the patches is zero there, so the forward is unchanged, and column k*k*c of that GEMM's weight gradient IS the bias
+    gradient (sum over pixels of gy) — SPADE's mlp_shared gets its bias gradient out of the wgrad launch instead of a separate
+    column-sum pass over the 128-channel gradient of actv (see _Spade.backward; has_bias_tap())."""
     _chk_storage(x)
     n, h, w, cs = x.shape
     cs_out = round8(k * k * c)
     y = torch.empty((n, h, w, cs_out), dtype=x.dtype, device=x.device)
     check(_L().cgb_im2col(_p(x), _p(y), _DT[x.dtype], n, h, w, cs, c, k, pad, dil, cs_out, _st()), "im2col")
+    if has_bias_tap(c, k):
+        y[..., k * k * c].fill_(1.0)
     return y
+
+
+def has_bias_tap(c: int, k: int) -> bool:
+    """True when :func:`im2col` patches of c channels and a k x k window carry the constant-one channel."""
+    return k * k * c < round8(k * k * c)
 
 
 def im2col_strided(x: torch.Tensor, c: int, k: int, pad: int, dil: int = 1, stride: int = 1) -> torch.Tensor:
@@ -487,7 +499,8 @@ class _Spade(Function):
             gactv = conv_dgrad_raw(ggb, wp_gb, tuple(actv.shape), g_gb, _lib.ACT_RELU, actv)
         if want_w:
             gwp_gb, gbp_gb = conv_wgrad_raw(actv, ggb, g_gb, True)
-            gwp_sh, gbp_sh = conv_wgrad_raw(seg, gactv, g_sh, True)
+            bias_tap = seg_is_col and has_bias_tap(sh_shape[1], sh_shape[2])   # the patches' constant-one channel (im2col)
+            gwp_sh, gbp_sh = conv_wgrad_raw(seg, gactv, g_sh, not bias_tap)
             gw_g = unpack_weight_grad(gwp_gb[:cs], g_shape)
             gw_b = unpack_weight_grad(gwp_gb[cs:], g_shape)
             gb_g = gbp_gb[:c].clone()
@@ -497,7 +510,10 @@ class _Spade(Function):
                 gw_sh = gwp_sh[:o_sh, 0, : kk * kk * i_sh].reshape(o_sh, kk, kk, i_sh).permute(0, 3, 1, 2).contiguous()
             else:
                 gw_sh = unpack_weight_grad(gwp_sh, sh_shape)
-            gb_sh = gbp_sh[: sh_shape[0]].clone()
+            if bias_tap:   # column k*k*cin of the patch GEMM's weight gradient = sum over pixels of gactv = the bias gradient
+                gb_sh = gwp_sh[: sh_shape[0], 0, sh_shape[2] * sh_shape[2] * sh_shape[1]].clone()
+            else:
+                gb_sh = gbp_sh[: sh_shape[0]].clone()
         if not ctx.needs_input_grad[0]:
             gx = None
         gseg = None
