@@ -2426,6 +2426,12 @@ static int try_wgrad_halo(const cgb_conv_desc* d, const void* x, const void* gy,
   p.m_dim = p.x_is_m ? d->ci : d->co;
   p.n_dim = p.x_is_m ? d->co : d->ci;
   p.bn = pick_bn(p.n_dim);
+  // all-taps-resident N tile: with kh*kw*bn <= 512 TMEM columns one CTA holds every tap's accumulator, the x halo tile is loaded
+  // once per pixel tile and gy once per N tile — the streaming form re-reads x once per tap and is L2 -> SM bound at ~6 TB/s
+  // (256->256 d2 @80^2: 88 us for 43 us of MMAs).  The price is a narrow MMA (N = 48: 44 cycles instead of 24 per K step).
+  static const int halo_bn = getenv("CGB_WG_HALO_BN") ? atoi(getenv("CGB_WG_HALO_BN")) : 0;
+  if (halo_bn >= 16 && halo_bn % 16 == 0 && p.kh * p.kw * p.bn > 512 && p.kh * p.kw * halo_bn <= 512 && p.n_dim > halo_bn)
+    p.bn = halo_bn;
   if (p.kw * p.bn > 512) return CGB_UNSUPPORTED;
   p.n_boxes = (p.bn + 63) / 64;
   p.rows_per_group = 512 / (p.kw * p.bn);
