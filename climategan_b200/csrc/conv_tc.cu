@@ -427,7 +427,8 @@ enum { EPI_AUX_NONE = 0, EPI_AUX_RES_BEFORE = 1, EPI_AUX_RES_AFTER = 2, EPI_AUX_
 // GENERIC: TMA-store tile with run-time flags (residual adds, ...); EXOTIC: tanh / sigmoid / selu epilogues (generic chunk code);
 // NOTMA: the per-thread copy-out (strided parity-class dgrad, ReLU-masked dgrad, N tiles that are not whole 64-channel halves)
 enum { EPI_GENERIC = 0, EPI_PLAIN = 1, EPI_BIAS = 2, EPI_BIAS_ACT = 3, EPI_MASK_RELU = 4, EPI_MASK_LRELU = 5, EPI_EXOTIC = 6, EPI_NOTMA = 7,
-       EPI_VARIANTS = 8 };
+       EPI_RES = 8,   // + residual, no bias / activation: the ResNet bottleneck's conv1 dgrad with the skip gradient added in
+       EPI_VARIANTS = 9 };
 
 template <typename T>
 __device__ __forceinline__ void epi_fast_fetch(const TcParams& p, int ch0, bool pix_ok, long long pixoff, const T* __restrict__ aux_src,
@@ -673,6 +674,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
     else if constexpr (EPI == EPI_BIAS_ACT) CGB_EPI_TILE(1, 1, EPI_AUX_NONE, false);      // conv + bias + (leaky) ReLU
     else if constexpr (EPI == EPI_MASK_RELU) CGB_EPI_TILE(0, 0, EPI_AUX_MASK_RELU, false);    // dgrad through ReLU (CGB_MASK_TMA=1)
     else if constexpr (EPI == EPI_MASK_LRELU) CGB_EPI_TILE(0, 0, EPI_AUX_MASK_LRELU, false);  // dgrad through LeakyReLU (painter, D)
+    else if constexpr (EPI == EPI_RES) CGB_EPI_TILE(0, 0, EPI_AUX_RES_AFTER, false);          // dgrad + skip gradient (ResNet bottleneck)
     else if constexpr (EPI == EPI_EXOTIC) CGB_EPI_TILE(-1, -1, -1, true);                 // tanh / sigmoid / selu: generic chunk code
     else CGB_EPI_TILE(-1, -1, -1, false);                                                 // run-time flags (residual adds, ...)
 #undef CGB_EPI_TILE
@@ -1359,6 +1361,14 @@ static EncodeTiledFn get_encode() {
 static bool encode_map(CUtensorMap* tm, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
                        const cuuint32_t* box, const cuuint32_t* estr, const char* what, bool f16 = false) {
   EncodeTiledFn enc = get_encode();
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs a current context on the calling thread.  An autograd worker thread whose
+  // first library call is a conv with cached packings reaches this point before any runtime call has bound the primary context
+  // (CUDA_ERROR_INVALID_CONTEXT, found by tests/test_conv_skip.py) — bind it once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(nullptr);
+    ctx_bound = true;
+  }
   if (!enc) {
     set_error("tcgen05 engine: cuTensorMapEncodeTiled is unavailable in this driver");
     return false;
@@ -1461,7 +1471,8 @@ static int epi_variant_for(bool tma_store, bool f16, const float* bias, const vo
   static const int on = getenv("CGB_EPI_VARIANTS") ? atoi(getenv("CGB_EPI_VARIANTS")) : 1;
   if (!tma_store) return EPI_NOTMA;
   if (act > CGB_ACT_LRELU || (residual && mask_src)) return EPI_EXOTIC;
-  if (!on || f16 || residual) return EPI_GENERIC;   // (fp16: inference-only mode, run-time flags)
+  if (!on || f16) return EPI_GENERIC;   // (fp16: inference-only mode, run-time flags)
+  if (residual) return (!bias && act == CGB_ACT_NONE && !mask_src) ? EPI_RES : EPI_GENERIC;
   if (mask_src) {
     if (bias || act != CGB_ACT_NONE) return EPI_GENERIC;
     return dact == CGB_ACT_RELU ? EPI_MASK_RELU : (dact == CGB_ACT_LRELU ? EPI_MASK_LRELU : EPI_GENERIC);
@@ -1484,6 +1495,7 @@ typedef void (*TcKernelF16)(const CUtensorMap, const CUtensorMap, const CUtensor
       case EPI_MASK_LRELU: return KERNEL<__nv_bfloat16, EPI_MASK_LRELU>;                 \
       case EPI_EXOTIC: return KERNEL<__nv_bfloat16, EPI_EXOTIC>;                         \
       case EPI_NOTMA: return KERNEL<__nv_bfloat16, EPI_NOTMA>;                           \
+      case EPI_RES: return KERNEL<__nv_bfloat16, EPI_RES>;                               \
       default: return KERNEL<__nv_bfloat16, EPI_GENERIC>;                                \
     }                                                                                    \
   }                                                                                      \

@@ -80,7 +80,14 @@ class Bottleneck(nn.Module):
         """resnetmulti_v2.py:40-56 in train mode: BatchNorm uses BATCH statistics (only its affine parameters are frozen,
         :16-18) and updates its running statistics; the conv's epilogue accumulates the statistics of its own output, so each
         conv -> BN -> ReLU is the conv launch + ONE normalise / ReLU (/ residual) pass (ops.conv_bn_act)."""
-        out = ops.conv_bn_act(x, self.conv1.weight, self.bn1, stride=self.stride, act=_lib.ACT_RELU)
+        if (self.downsample is None and self.stride == 1 and ops._CONV_SKIP and x.requires_grad and x.dtype != torch.float32
+                and torch.is_grad_enabled()):
+            # identity block: conv1 and the skip share x — the skip's gradient is added in conv1's dgrad epilogue (ops._Conv2dSkip)
+            batch_stats = bool(self.bn1.training or self.bn1.running_mean is None)
+            y1, partial, x = ops.conv2d_skip(x, self.conv1.weight, want_stats=batch_stats)
+            out = ops.batchnorm_act(y1, self.bn1, None, _lib.ACT_RELU, 0.2, partial=partial)
+        else:
+            out = ops.conv_bn_act(x, self.conv1.weight, self.bn1, stride=self.stride, act=_lib.ACT_RELU)
         out = ops.conv_bn_act(out, self.conv2.weight, self.bn2, dil=self.dilation, pad=self.dilation, act=_lib.ACT_RELU)
         residual = x
         if self.downsample is not None:

@@ -392,6 +392,62 @@ class _Conv2d(Function):
         return gx, gw, gb, gres, None, None
 
 
+class _Conv2dSkip(Function):
+    """A bias-free 1x1 stride-1 conv whose INPUT also feeds a skip connection (the ResNet bottleneck's conv1 and its identity
+    branch, resnetmulti_v2.py:40-56): ``y, partial, x_skip = f(x, w)`` with ``x_skip`` aliasing ``x``.  Autograd would sum the
+    two gradients of x with a separate pass over the 1024-channel tensor (66 bf16 adds per step, 4.8 ms); here the skip gradient
+    rides the dgrad launch as its epilogue residual: gx = conv(gy, wt) + g_skip, rounded once."""
+
+    @staticmethod
+    def forward(ctx, x, w, want_stats):
+        g = ConvGeom(1, 1, 1, 1, 0, _lib.PAD_ZERO, _lib.ACT_NONE, 0.0, _lib.ENGINE_AUTO)
+        wp = pack_weight_cached(w, x.dtype, cis=x.shape[-1], with_dgrad=True)
+        if want_stats:
+            y, partial = conv_fwd_raw(x, wp, None, None, g, True)
+        else:
+            y, partial = conv_fwd_raw(x, wp, None, None, g), None
+        if partial is None:
+            partial = torch.empty(0, dtype=torch.float32, device=x.device)
+        ctx.g, ctx.w_shape = g, tuple(w.shape)
+        ctx.save_for_backward(x, wp)
+        ctx.mark_non_differentiable(partial)
+        return y, partial, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, gy, gpartial, gskip):
+        x, wp = ctx.saved_tensors
+        g = ctx.g
+        gy = gy.contiguous()
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            wt = getattr(wp, "_cgb_wt", None)
+            n, hi, wi, ci = x.shape
+            d = g.desc(n, hi, wi, ci, wp.shape[0], gy.dtype)
+            if gskip is not None and wt is not None and wt.shape == (ci, 1, wp.shape[0]) and _L().cgb_conv2d_uses_tcgen05(C.byref(d), 1):
+                gx = conv_fwd_raw(gy, wt, None, gskip.contiguous(), g)      # the 1x1 dgrad IS a 1x1 conv with the transposed packing
+            else:
+                gx = conv_dgrad_raw(gy, wp, tuple(x.shape), g)
+                if gskip is not None:
+                    gx = gx + gskip
+        if ctx.needs_input_grad[1]:
+            gwp, _ = conv_wgrad_raw(x, gy, g, False)
+            gw = unpack_weight_grad(gwp, ctx.w_shape)
+        return gx, gw, None
+
+
+# Off by default: measured neutral on the full step (200.0 vs 200.8 ms, scripts/r02/gpu37.sh) — the residual operand of the TMA-path
+# epilogue is read row-per-thread (32 sectors in 32 lines per load), which costs what the separate bf16 add cost.  It becomes
+# a win once the epilogue's second operand arrives by TMA (DESIGN.md section 8, next steps).
+_CONV_SKIP = os.environ.get("CGB_CONV_SKIP", "0") != "0"
+
+
+def conv2d_skip(x, w, want_stats=False):
+    """(y, partial or None, x_skip) — see :class:`_Conv2dSkip`; w: [co, ci, 1, 1], no bias, stride 1."""
+    assert w.shape[2] == 1 and w.shape[3] == 1
+    y, partial, xs = _Conv2dSkip.apply(x, w, want_stats)
+    return y, (partial if partial.numel() else None), xs
+
+
 def conv2d(x, w, bias=None, residual=None, *, stride=1, dil=1, pad=0, pad_mode=_lib.PAD_ZERO,
            act=_lib.ACT_NONE, slope=0.2, engine=_lib.ENGINE_AUTO, want_stats=False):
     """want_stats: returns (y, partial) — see :func:`conv_fwd_raw`; partial is None when the conv did not produce statistics."""
