@@ -2575,8 +2575,27 @@ int conv_tc_wgrad(const cgb_conv_desc* d, const void* x, const void* gy, float* 
   const int m_tiles = (p.m_dim + 127) / 128;
   const int n_tiles = (p.n_dim + p.bn - 1) / p.bn;
   const int zdim = n_tiles * p.tap_groups;
-  // pixel splits: ~2 waves of CTAs over 148 SMs (1 CTA per SM: the accumulators own most of TMEM)
-  int splits = (148 * 2 + m_tiles * zdim - 1) / (m_tiles * zdim);
+  // pixel splits.  One CTA per SM (the accumulators own most of TMEM), so CTAs run in waves, and every CTA pays a fixed cost on
+  // top of its tiles: pipeline fill plus the fp32 reduction of its whole accumulator into gw (~8 tile times).  Round 1 always
+  // launched ~2 waves; one full wave is 20-28 % faster wherever m_tiles * zdim divides 148 well (256->256 d2 @80^2: 93 -> 71 us,
+  // 2048->512 1x1: 176 -> 126), but halves the machine where it does not (ASPP 2048->256: 80 slots) — pick the split count that
+  // minimises waves * (tiles per CTA + fixed cost).  CGB_WG_WAVES=n forces the old rule with n waves.
+  static const int wg_waves = getenv("CGB_WG_WAVES") ? atoi(getenv("CGB_WG_WAVES")) : 0;
+  const int slots = m_tiles * zdim;
+  int splits = 1;
+  if (wg_waves >= 1) {
+    splits = (148 * wg_waves + slots - 1) / slots;
+    if (wg_waves == 1) splits = 148 / slots > 0 ? 148 / slots : 1;
+  } else {
+    const int fixed = 8;
+    long long best = -1;
+    const int smax = (148 * 3 + slots - 1) / slots;
+    for (int sp = 1; sp <= smax && sp <= p.total_tiles; ++sp) {
+      const long long waves = ((long long)slots * sp + 147) / 148;
+      const long long cost = waves * ((p.total_tiles + sp - 1) / sp + fixed);
+      if (best < 0 || cost < best) { best = cost; splits = sp; }
+    }
+  }
   if (splits > p.total_tiles) splits = p.total_tiles;
   if (splits < 1) splits = 1;
   p.tiles_per_cta = (p.total_tiles + splits - 1) / splits;
