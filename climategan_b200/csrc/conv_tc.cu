@@ -2547,7 +2547,11 @@ int conv_tc_wgrad(const cgb_conv_desc* d, const void* x, const void* gy, float* 
   const int tiles_n = (d->n + (1 << tn_log) - 1) >> tn_log;
   p.total_tiles = p.tiles_x * p.tiles_y * tiles_n;
   const int taps = d->kh * d->kw;
-  p.x_is_m = d->ci >= d->co ? 1 : 0;
+  // M side = x only when the output channels cannot fill an M tile: with M = output channels a lane's 16 accumulator columns are
+  // 16 consecutive floats of gw (sn == 1) and the final reduction uses 16-byte vector reds; with M = x it is 16 scalar reds per
+  // chunk, and that reduction is a fixed ~20 us per CTA (CGB_WG_XM=1: the round-1 rule ci >= co)
+  static const int wg_xm = getenv("CGB_WG_XM") ? atoi(getenv("CGB_WG_XM")) : 0;
+  p.x_is_m = (d->ci >= d->co && (wg_xm || d->co < 128)) ? 1 : 0;
   p.m_dim = p.x_is_m ? d->ci : d->co;
   p.n_dim = p.x_is_m ? d->co : d->ci;
   p.bn = pick_bn(p.n_dim);
