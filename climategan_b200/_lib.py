@@ -118,6 +118,7 @@ SIGNATURES = {
     "cgb_bn_train_fwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _F, _I, _F, _P], C.c_int),
     "cgb_bn_train_fwd_partials": ([_P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _F, _I, _F, _P], C.c_int),
     "cgb_bn_train_bwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P], C.c_int),
+    "cgb_bn_train_bwd2": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _I, _F, _P], C.c_int),
     "cgb_bn_update_running": ([_P, _P, _P, _P, _I, _L, _F, _F, _P], C.c_int),
     "cgb_maxpool3s2_fwd": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_maxpool3s2_bwd": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], C.c_int),

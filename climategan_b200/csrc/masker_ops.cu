@@ -119,8 +119,8 @@ bn_apply_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, con
 template <typename T>
 __global__ void __launch_bounds__(256, 3)
 bn_apply_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const T* __restrict__ y, const T* __restrict__ gy, T* __restrict__ gpre, float* __restrict__ partial,
-                    long long total_vec, int cv, float neg, int has_act) {
+                    const T* __restrict__ y, const T* __restrict__ gy, const T* __restrict__ gy2, T* __restrict__ gpre,
+                    float* __restrict__ partial, long long total_vec, int cv, float neg, int has_act) {
   extern __shared__ float sm[];  // sums [2][8][cv] (conflict-free fold), then rs[c], nm[c]
   const int c = cv * 8;
   float* coef = sm + 2 * c;
@@ -140,13 +140,14 @@ bn_apply_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, con
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   for (long long i = i0; i < total_vec; i += stride * BN_U) {
-    Raw8<T> xr[BN_U], gr[BN_U], yr[BN_U];
+    Raw8<T> xr[BN_U], gr[BN_U], yr[BN_U], g2r[BN_U];
 #pragma unroll
     for (int u = 0; u < BN_U; ++u) {
       const long long k = i + u * stride;
       if (k < total_vec) {
         xr[u] = ldraw<T>(x + k * 8);
         gr[u] = ldraw<T>(gy + k * 8);
+        if (gy2) g2r[u] = ldraw<T>(gy2 + k * 8);
         if (has_act) yr[u] = ldraw<T>(y + k * 8);
       }
     }
@@ -156,6 +157,11 @@ bn_apply_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, con
       if (k < total_vec) {
         float o[8], t[8];
         cvt8<T>(gr[u], o);
+        if (gy2) {   // the output fed two consumers: their gradients are summed here (fp32) instead of by a separate pass
+          cvt8<T>(g2r[u], t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += t[j];
+        }
         if (has_act) {
           cvt8<T>(yr[u], t);
 #pragma unroll
@@ -1050,8 +1056,16 @@ extern "C" int64_t cgb_bn_bwd_ws_doubles(int64_t npix, int32_t c) {
   return 2 * (int64_t)c + (int64_t)bn_grid((long long)npix * cv, cv) * c;   // sums[c][2] doubles, then grid * 2c fp32 partials
 }
 
+static int bn_apply_bwd_impl(const void* x, const float* mean, const float* rstd, const void* y, const void* gy, const void* gy2,
+                             void* gpre, double* sums, int32_t dtype, int64_t npix, int32_t c, int32_t act, float slope, void* stream);
+
 extern "C" int cgb_bn_apply_bwd(const void* x, const float* mean, const float* rstd, const void* y, const void* gy, void* gpre,
                                 double* sums, int32_t dtype, int64_t npix, int32_t c, int32_t act, float slope, void* stream) {
+  return bn_apply_bwd_impl(x, mean, rstd, y, gy, nullptr, gpre, sums, dtype, npix, c, act, slope, stream);
+}
+
+static int bn_apply_bwd_impl(const void* x, const float* mean, const float* rstd, const void* y, const void* gy, const void* gy2,
+                             void* gpre, double* sums, int32_t dtype, int64_t npix, int32_t c, int32_t act, float slope, void* stream) {
   CGB_CHECK_DEVICE();
   CGB_REQUIRE(x && mean && rstd && gy && gpre && sums && npix > 0, "bn_apply_bwd: bad arguments");
   CGB_REQUIRE(act == CGB_ACT_NONE || y, "bn_apply_bwd: y is required when an activation is fused");
@@ -1063,7 +1077,7 @@ extern "C" int cgb_bn_apply_bwd(const void* x, const float* mean, const float* r
   const int grid = bn_grid(total, cv);
   float* partial = reinterpret_cast<float*>(sums + 2 * (size_t)c);   // sums holds cgb_bn_bwd_ws_doubles(npix, c) doubles
   DISPATCH_T(dtype, bn_apply_bwd_kernel<T><<<grid, 256, 4 * c * sizeof(float), st>>>(
-                        (const T*)x, mean, rstd, (const T*)y, (const T*)gy, (T*)gpre, partial, total, cv, neg,
+                        (const T*)x, mean, rstd, (const T*)y, (const T*)gy, (const T*)gy2, (T*)gpre, partial, total, cv, neg,
                         act != CGB_ACT_NONE);)
   int s = after_launch("bn_apply_bwd");
   if (s) return s;
@@ -1136,6 +1150,14 @@ extern "C" int cgb_bn_train_bwd(const void* x, const float* mean, const float* r
                                 const void* gy, void* gpre, void* gx, double* sums, int32_t dtype, int64_t npix, int32_t c,
                                 int32_t act, float slope, void* stream) {
   int s = cgb_bn_apply_bwd(x, mean, rstd, y, gy, gpre, sums, dtype, npix, c, act, slope, stream);
+  if (s || !gx) return s;
+  return cgb_bn_bwd_finalize(x, mean, rstd, weight, sums, gpre, gx, dtype, npix, c, stream);
+}
+
+extern "C" int cgb_bn_train_bwd2(const void* x, const float* mean, const float* rstd, const float* weight, const void* y,
+                                 const void* gy, const void* gy2, void* gpre, void* gx, double* sums, int32_t dtype, int64_t npix,
+                                 int32_t c, int32_t act, float slope, void* stream) {
+  int s = bn_apply_bwd_impl(x, mean, rstd, y, gy, gy2, gpre, sums, dtype, npix, c, act, slope, stream);
   if (s || !gx) return s;
   return cgb_bn_bwd_finalize(x, mean, rstd, weight, sums, gpre, gx, dtype, npix, c, stream);
 }

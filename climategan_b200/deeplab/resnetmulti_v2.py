@@ -64,6 +64,8 @@ class Bottleneck(nn.Module):
     def forward_storage(self, x):
         if self.training:
             return self._forward_train(x)
+        if isinstance(x, tuple):
+            x = x[0]
         dt = x.dtype
         w1, b1 = fold_bn(self.conv1, self.bn1, dt, cis=x.shape[-1])
         out = ops.conv2d_infer(x, w1, b1, k=1, stride=self.stride, act=_lib.ACT_RELU)
@@ -76,23 +78,25 @@ class Bottleneck(nn.Module):
         w3, b3 = fold_bn(self.conv3, self.bn3, dt, cis=out.shape[-1])
         return ops.conv2d_infer(out, w3, b3, residual, k=1, act=_lib.ACT_RELU, res_before_act=1)
 
-    def _forward_train(self, x):
+    def _forward_train(self, x, dual=False):
         """resnetmulti_v2.py:40-56 in train mode: BatchNorm uses BATCH statistics (only its affine parameters are frozen,
         :16-18) and updates its running statistics; the conv's epilogue accumulates the statistics of its own output, so each
         conv -> BN -> ReLU is the conv launch + ONE normalise / ReLU (/ residual) pass (ops.conv_bn_act)."""
+        # x may arrive as two aliases of the previous block's output (ops.batchnorm_act(dual=True)): one per consumer here
+        x, x_skip = x if isinstance(x, tuple) else (x, x)
         if (self.downsample is None and self.stride == 1 and ops._CONV_SKIP and x.requires_grad and x.dtype != torch.float32
                 and torch.is_grad_enabled()):
             # identity block: conv1 and the skip share x — the skip's gradient is added in conv1's dgrad epilogue (ops._Conv2dSkip)
             batch_stats = bool(self.bn1.training or self.bn1.running_mean is None)
-            y1, partial, x = ops.conv2d_skip(x, self.conv1.weight, want_stats=batch_stats)
+            y1, partial, x_skip = ops.conv2d_skip(x, self.conv1.weight, want_stats=batch_stats)
             out = ops.batchnorm_act(y1, self.bn1, None, _lib.ACT_RELU, 0.2, partial=partial)
         else:
             out = ops.conv_bn_act(x, self.conv1.weight, self.bn1, stride=self.stride, act=_lib.ACT_RELU)
         out = ops.conv_bn_act(out, self.conv2.weight, self.bn2, dil=self.dilation, pad=self.dilation, act=_lib.ACT_RELU)
-        residual = x
+        residual = x_skip
         if self.downsample is not None:
-            residual = ops.conv_bn_act(x, self.downsample[0].weight, self.downsample[1], stride=self.downsample[0].stride[0])
-        return ops.conv_bn_act(out, self.conv3.weight, self.bn3, residual=residual, act=_lib.ACT_RELU)
+            residual = ops.conv_bn_act(x_skip, self.downsample[0].weight, self.downsample[1], stride=self.downsample[0].stride[0])
+        return ops.conv_bn_act(out, self.conv3.weight, self.bn3, residual=residual, act=_lib.ACT_RELU, dual=dual)
 
 
 class ResNetMulti(nn.Module):
@@ -155,7 +159,14 @@ class ResNetMulti(nn.Module):
             wp = ops.pack_weight(as_gemm(w), x.dtype, cis=xc.shape[-1])
             x = ops.conv2d_infer(xc, wp, ops.pad_bias(b, wp.shape[0]), k=1, act=_lib.ACT_RELU)
         x = ops.maxpool3s2_ceil(x)
-        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
-            for blk in layer:
+        layers = (self.layer1, self.layer2, self.layer3, self.layer4)
+        blocks = [blk for layer in layers for blk in layer]
+        # every block's output but the last feeds exactly two consumers inside the next block (conv1 and the identity branch or
+        # its down-sampling conv): hand it over as two aliases (ops.batchnorm_act(dual=True))
+        dual_ok = self.training and ops._BN_DUAL and torch.is_grad_enabled() and x.dtype != torch.float32
+        for i, blk in enumerate(blocks):
+            if dual_ok and isinstance(blk, Bottleneck):
+                x = blk._forward_train(x, dual=i + 1 < len(blocks))
+            else:
                 x = blk.forward_storage(x)
         return x

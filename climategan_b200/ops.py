@@ -459,7 +459,7 @@ def conv2d(x, w, bias=None, residual=None, *, stride=1, dil=1, pad=0, pad_mode=_
 
 
 def conv_bn_act(x, w, bn, bias=None, residual=None, *, stride=1, dil=1, pad=0, pad_mode=_lib.PAD_ZERO, act=_lib.ACT_NONE,
-                slope=0.2):
+                slope=0.2, dual=False):
     """conv -> BatchNorm (+ residual) -> activation for an ``nn.BatchNorm2d`` container ``bn`` (resnetmulti_v2.py:40-56,
     blocks.py:138-144): in train mode the batch statistics are accumulated by the conv's own epilogue, so the chain is the conv
     launch, one tiny finalize and ONE pass over the conv output (normalise + affine + residual + activation)."""
@@ -468,7 +468,11 @@ def conv_bn_act(x, w, bn, bias=None, residual=None, *, stride=1, dil=1, pad=0, p
         y, partial = conv2d(x, w, bias, None, stride=stride, dil=dil, pad=pad, pad_mode=pad_mode, want_stats=True)
     else:
         y, partial = conv2d(x, w, bias, None, stride=stride, dil=dil, pad=pad, pad_mode=pad_mode), None
-    return batchnorm_act(y, bn, residual, act, slope, partial=partial)
+    return batchnorm_act(y, bn, residual, act, slope, partial=partial, dual=dual)
+
+
+# two aliases of a bottleneck's output (one per consumer) so that BatchNorm's backward sums their gradients in its own first pass
+_BN_DUAL = os.environ.get("CGB_BN_DUAL", "1") != "0"
 
 
 class _Spade(Function):
@@ -1400,7 +1404,8 @@ class _BatchNormAct(Function):
     and one apply pass over x; the backward is two passes (see include/cgb200.h)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, running_mean, running_var, nbt, training, momentum, eps, act, slope, partial=None):
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, nbt, training, momentum, eps, act, slope, partial=None,
+                dual=False):
         _chk_storage(x)
         n, h, w, cs = x.shape
         npix = n * h * w
@@ -1448,15 +1453,30 @@ class _BatchNormAct(Function):
                                         slope, _st()), "bn_apply_fwd")
         ctx.save_for_backward(x, mean, rstd, wp, y if act != _lib.ACT_NONE else None)
         ctx.meta = (act, slope, c, residual is not None, batch_stats)
+        ctx.dual = bool(dual)
+        if dual:
+            # the output feeds TWO consumers (a bottleneck's conv1 and identity branch): hand out two aliases so that the
+            # backward receives their gradients separately and sums them inside its first pass (cgb_bn_train_bwd2) —
+            # autograd would sum them with a separate pass over the tensor.  An unused alias arrives as None.
+            ctx.set_materialize_grads(False)
+            return y, y.view_as(y)
         return y
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, gy2=None):
         x, mean, rstd, wp, y = ctx.saved_tensors
         act, slope, c, has_res, batch_stats = ctx.meta
         n, h, w, cs = x.shape
         npix = n * h * w
+        if gy is None:
+            gy, gy2 = gy2, None
+        if gy is None:
+            return (None,) * 14
         gy = gy.contiguous()
+        if gy2 is not None:
+            gy2 = gy2.contiguous()
+            if not batch_stats:
+                gy, gy2 = gy + gy2, None
         gpre = torch.empty_like(x)
         k = ("bnbwd", npix, cs)
         nd = _WS_CACHE.get(k)
@@ -1467,8 +1487,12 @@ class _BatchNormAct(Function):
         gw = gb = gx = None
         if batch_stats:
             gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-            check(_L().cgb_bn_train_bwd(_p(x), _p(mean), _p(rstd), _p(wp), _p(y), _p(gy), _p(gpre), _p(gx), _p(sums),
-                                        _DT[x.dtype], npix, cs, act, slope, _st()), "bn_train_bwd")
+            if gy2 is not None:
+                check(_L().cgb_bn_train_bwd2(_p(x), _p(mean), _p(rstd), _p(wp), _p(y), _p(gy), _p(gy2), _p(gpre), _p(gx), _p(sums),
+                                             _DT[x.dtype], npix, cs, act, slope, _st()), "bn_train_bwd2")
+            else:
+                check(_L().cgb_bn_train_bwd(_p(x), _p(mean), _p(rstd), _p(wp), _p(y), _p(gy), _p(gpre), _p(gx), _p(sums),
+                                            _DT[x.dtype], npix, cs, act, slope, _st()), "bn_train_bwd")
         else:
             check(_L().cgb_bn_apply_bwd(_p(x), _p(mean), _p(rstd), _p(y), _p(gy), _p(gpre), _p(sums), _DT[x.dtype], npix, cs,
                                         act, slope, _st()), "bn_apply_bwd")
@@ -1480,16 +1504,16 @@ class _BatchNormAct(Function):
             sf = sums[:c].float()
             gw = sf[:, 1] if ctx.needs_input_grad[1] else None
             gb = sf[:, 0] if ctx.needs_input_grad[2] else None
-        return gx, gw, gb, (gpre if has_res else None), None, None, None, None, None, None, None, None, None
+        return gx, gw, gb, (gpre if has_res else None), None, None, None, None, None, None, None, None, None, None
 
 
-def batchnorm_act(x, bn, residual=None, act=_lib.ACT_NONE, slope=0.2, partial=None):
+def batchnorm_act(x, bn, residual=None, act=_lib.ACT_NONE, slope=0.2, partial=None, dual=False):
     """``act(bn(x) (+ residual))`` for an ``nn.BatchNorm2d`` parameter container ``bn`` (train: batch statistics + running
     update, exactly F.batch_norm's semantics; eval: running statistics)."""
     momentum = 0.1 if bn.momentum is None else bn.momentum
     nbt = bn.num_batches_tracked if (bn.training and bn.track_running_stats) else None   # incremented inside the kernel
     return _BatchNormAct.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, nbt, bn.training, momentum,
-                               bn.eps, act, slope, partial)
+                               bn.eps, act, slope, partial, dual)
 
 
 class _MakeMCond(Function):

@@ -260,6 +260,12 @@ int cgb_bn_train_fwd(const void* x, const float* weight, const float* bias, cons
 int cgb_bn_train_bwd(const void* x, const float* mean, const float* rstd, const float* weight, const void* y, const void* gy,
                      void* gpre, void* gx, double* sums, int32_t dtype, int64_t npix, int32_t c, int32_t act, float slope,
                      void* stream);
+/* The same when the BatchNorm'd output fed TWO consumers (the ResNet bottleneck's output: the next block's conv1 and its identity
+ * branch, resnetmulti_v2.py:40-56): gy and gy2 are the two incoming gradients, summed in fp32 inside the first pass instead of by
+ * a separate pass over the tensor (autograd's accumulation: 66 bf16 adds of [8,80,80,1024] per train step).  gy2 may be NULL. */
+int cgb_bn_train_bwd2(const void* x, const float* mean, const float* rstd, const float* weight, const void* y, const void* gy,
+                      const void* gy2, void* gpre, void* gx, double* sums, int32_t dtype, int64_t npix, int32_t c, int32_t act,
+                      float slope, void* stream);
 /* cgb_bn_train_fwd without its statistics pass: mean / rstd (fp64 fold) and the running update come from the per-CTA partial
  * sums [rows][2][c] a cgb_conv2d_fwd_stats launch left behind, then the same apply pass. */
 int cgb_bn_train_fwd_partials(const void* x, const float* partial, int32_t rows, const float* weight, const float* bias,

@@ -405,6 +405,14 @@ class EmuLib(NoopLib):
             pre = pre + R.float()
         _t(y, (npix, c), dt).copy_(_act(pre, act, slope))
 
+    def e_bn_train_bwd2(self, x, mean, rstd, weight, y, gy, gy2, gpre, gx, sums, dtype, npix, c, act, slope, stream):
+        if _addr(gy2) is None:
+            return self.e_bn_train_bwd(x, mean, rstd, weight, y, gy, gpre, gx, sums, dtype, npix, c, act, slope, stream)
+        dt = _DT[dtype]
+        tot = (_t(gy, (npix, c), dt).float() + _t(gy2, (npix, c), dt).float()).to(dt).contiguous()
+        self._keep = tot                                   # keep the temporary alive for the call
+        return self.e_bn_train_bwd(x, mean, rstd, weight, y, tot.data_ptr(), gpre, gx, sums, dtype, npix, c, act, slope, stream)
+
     def e_bn_train_bwd(self, x, mean, rstd, weight, y, gy, gpre, gx, sums, dtype, npix, c, act, slope, stream):
         dt = _DT[dtype]
         r = _t(rstd, (c,), torch.float32)
