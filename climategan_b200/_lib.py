@@ -18,7 +18,7 @@ _SOURCES = ["api.cu", "ops.cu", "masker_ops.cu", "events.cu", "conv_simt.cu", "c
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-lineinfo", "-O3", "-std=c++17",
+    "-lineinfo", "-O3", "-std=c++17", "--threads", "6",
     "-Xcompiler", "-fPIC", "-shared",
 ]
 
