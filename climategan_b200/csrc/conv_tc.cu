@@ -22,6 +22,7 @@
 #include <cuda.h>
 #include <mutex>
 #include <string.h>
+#include <type_traits>
 
 namespace cgb {
 
@@ -290,6 +291,7 @@ struct TcParams {
   int stage_pitch;             // bytes per staging row = bn*2 + 16
   int tma_store;               // streaming kernel: copy-out by TMA store from a 128B-swizzled staging tile (bn % 64 == 0)
   int staging_bufs;            // 1 or 2 staging tiles (2: the store of tile i overlaps the epilogue math of tile i+1)
+  int ws_unroll;               // weight-stationary kernel: unrolled 3x3 MMA issue (CGB_WS_UNROLL, default on)
   int staging_tile_bytes;      // bytes of one staging tile: 128*stage_pitch, or ceil(bn/64) swizzled 16 KB halves (TMA store)
   int twh, thh;                // weight-stationary kernel: halo tile extent (pixels)
   int a_stage_bytes;           // weight-stationary kernel: bytes per halo stage (1024-aligned)
@@ -1235,17 +1237,20 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t halo_bytes = (uint32_t)(p.twh * p.thh) * 128u;
       int s = 0;
       uint32_t ph = 0;
-      for (int pt = pt0; pt < p.pix_tiles; pt += pt_step) {
+      int lt = 0;
+      for (int pt = pt0; pt < p.pix_tiles; pt += pt_step, ++lt) {
         const int tx = pt % p.tiles_x;
         const int ty = (pt / p.tiles_x) % p.tiles_y;
         const int img = pt / (p.tiles_x * p.tiles_y);
         const int cx = (tx << 3) - p.pad_x, cy = (ty << 4) - p.pad_y;
+        tc_trace(p.trace, lt, 0);
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_expect_tx(full_bar(s), halo_bytes);
           tma_load_4d(a_base + (uint32_t)s * (uint32_t)p.a_stage_bytes, &tmA, full_bar(s), kb * 64, cx, cy, img);
           if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
+        tc_trace(p.trace, lt, 1);
       }
     }
   } else if (warp == 1) {
@@ -1261,15 +1266,41 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t bph = (uint32_t)(lt >> 1) & 1u;
       mbar_wait(tempty_bar(buf), bph ^ 1u);
       tc_fence_after();
+      if (lane == 0) tc_trace(p.trace, lt, 2);
       const uint32_t d_addr = tmem_base + (uint32_t)(buf * p.bn);
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
+        if (lane == 0 && kb == 0) tc_trace(p.trace, lt, 3);
+        if (lane == 0 && kb == p.kblocks - 1) tc_trace(p.trace, lt, 4);
         if (elect_one_sync()) {
           const int ksteps = (kb == p.kblocks - 1) ? ksteps_last : 4;
           const uint32_t a_lo0 = desc_lo(a_base + (uint32_t)s * (uint32_t)p.a_stage_bytes, 16u);
           uint32_t b_lo = desc_lo(base + (uint32_t)(kb * taps) * w_tap_bytes, 16u);
           uint32_t acc = kb > 0 ? 1u : 0u;
+          if (p.ws_unroll && p.kh == 3 && p.kw == 3) {
+            // 3x3 (every user of this kernel on the hot path): taps and K steps unrolled, operands of the form
+            // launch-constant + small compile-time multiples.  The generic loop below costs ~19 single-thread instructions per
+            // MMA (six R2UR moves among them): measured with CGB_TC_TRACE, the N = 48 gamma||beta MMAs took 74 cycles each and
+            // the N = 32 ones 113 against 44 / 40 of operand-read time — the issue loop, not the tensor pipe, was the bound.
+            const uint32_t row16 = (uint32_t)(p.dil * p.twh) * 8u, col16 = (uint32_t)p.dil * 8u, wtap16 = w_tap_bytes >> 4;
+            auto issue9 = [&](auto KS) {
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                const uint32_t a_lo = a_lo0 + (uint32_t)(t / 3) * row16 + (uint32_t)(t % 3) * col16;
+                const uint32_t b_t = b_lo + (uint32_t)t * wtap16;
+#pragma unroll
+                for (int k = 0; k < decltype(KS)::value; ++k) {
+                  umma_bf16(d_addr, desc_join(a_lo + 2u * k, hi_a), desc_join(b_t + 2u * k, hi_b), idesc, acc);
+                  acc = 1u;
+                }
+              }
+            };
+            if (ksteps == 4) issue9(std::integral_constant<int, 4>{});
+            else if (ksteps == 3) issue9(std::integral_constant<int, 3>{});
+            else if (ksteps == 2) issue9(std::integral_constant<int, 2>{});
+            else issue9(std::integral_constant<int, 1>{});
+          } else {
           for (int dy = 0; dy < p.kh; ++dy) {
             uint32_t a_lo = a_lo0 + (uint32_t)(dy * p.dil * p.twh) * 8u;
             for (int dx = 0; dx < p.kw; ++dx) {
@@ -1283,6 +1314,7 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               a_lo += (uint32_t)p.dil * 8u;
               b_lo += w_tap_bytes >> 4;
             }
+          }
           }
           umma_commit(empty_bar(s));
           if (kb == p.kblocks - 1) umma_commit(tfull_bar(buf));
@@ -1303,13 +1335,16 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int tx = pt - py * p.tiles_x;
       const int img = (int)fdiv((uint32_t)py, (uint32_t)p.tiles_y, p.mg_ty);
       const int ty = py - img * p.tiles_y;
+      if (threadIdx.x == 64) tc_trace(p.trace, lt, 5);
       mbar_wait(tfull_bar(buf), bph);
       tc_fence_after();
+      if (threadIdx.x == 64) tc_trace(p.trace, lt, 6);
       // two staging tiles when they fit (launch_fprop): the store of tile i overlaps the staging of tile i+1 — with one, every
       // tile of a small-channel conv (24->24 at 640^2: 684 cycles of MMAs) waited ~1500 cycles for the previous bulk store
       const uint32_t sb = (p.staging_bufs == 2) ? (uint32_t)(lt & 1) * (uint32_t)p.staging_tile_bytes : 0u;
       epilogue_tile<T, EPI>(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen + sb, tx << 3, ty << 4, img, cn0, bias, residual,
-                    mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr, staging + sb, stats_tab, &est);
+                    mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr, staging + sb, stats_tab, &est, false, lt);
+      if (threadIdx.x == 64) tc_trace(p.trace, lt, 10);
     }
     if (p.tma_store && lane == 0 && warp < 6) tma_store_wait_all();   // every store leader: its bulk stores have completed
     if (stats_tab) {
@@ -1464,6 +1499,34 @@ bool conv_tc_supported(const cgb_conv_desc* d, int which) {
     return d->stride == 2 && d->kh * d->kw <= 64;  // parity-class decomposition
   }
   return d->stride <= 2 && d->co <= 2048;  // wgrad
+}
+
+// debug only (CGB_TC_TRACE=1): per-role clock64 stamps of CTA 0, printed after a synchronisation — never on in production
+static unsigned long long* g_trace_buf = nullptr;
+static bool trace_on() {
+  static const int v = getenv("CGB_TC_TRACE") ? atoi(getenv("CGB_TC_TRACE")) : 0;
+  return v != 0;
+}
+static unsigned long long* trace_begin(cudaStream_t st) {
+  if (!trace_on()) return nullptr;
+  if (!g_trace_buf) cudaMallocManaged(&g_trace_buf, 32 * 16 * sizeof(unsigned long long));
+  cudaStreamSynchronize(st);
+  memset(g_trace_buf, 0, 32 * 16 * sizeof(unsigned long long));
+  return g_trace_buf;
+}
+static void trace_end(const TcParams& p, cudaStream_t st) {
+  if (!trace_on() || !g_trace_buf) return;
+  cudaStreamSynchronize(st);
+  const unsigned long long t0 = g_trace_buf[0];
+  fprintf(stderr, "[tc_trace] bn=%d n_tiles=%d tiles=%d stages=%d iters=%d tma_store=%d staging_bufs=%d\n", p.bn, p.n_tiles,
+          p.total_tiles ? p.total_tiles : p.pix_tiles, p.stages, (p.ntaps ? p.ntaps : 1) * p.kblocks, p.tma_store, p.staging_bufs);
+  fprintf(stderr, "[tc_trace] tile: P.start P.issued | M.tempty M.full0 M.fullN | E.wait E.tfull E.stg_free E.ph1 E.bar E.done (cycles since start)\n");
+  for (int t = 0; t < 32 && g_trace_buf[t * 16] != 0; ++t) {
+    fprintf(stderr, "[tc_trace] %2d:", t);
+    for (int k = 0; k <= 10; ++k)
+      fprintf(stderr, " %7lld%s", (long long)(g_trace_buf[t * 16 + k] - t0), (k == 1 || k == 4) ? " |" : "");
+    fprintf(stderr, "\n");
+  }
 }
 
 // ---- epilogue variant of a launch (template parameter EPI of the kernels) ---------------------------------------------------
@@ -1660,15 +1723,7 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
     return CGB_UNSUPPORTED;
   }
   dim3 grid((unsigned)(p.total_tiles < num_sms() ? p.total_tiles : num_sms()));
-  // debug only (CGB_TC_TRACE=1): per-role clock64 stamps of CTA 0, printed after a synchronisation — never on in production
-  static const int tc_trace_on = getenv("CGB_TC_TRACE") ? atoi(getenv("CGB_TC_TRACE")) : 0;
-  static unsigned long long* trace_buf = nullptr;
-  if (tc_trace_on) {
-    if (!trace_buf) cudaMallocManaged(&trace_buf, 32 * 16 * sizeof(unsigned long long));
-    cudaStreamSynchronize(st);
-    memset(trace_buf, 0, 32 * 16 * sizeof(unsigned long long));
-    p.trace = trace_buf;
-  }
+  p.trace = trace_begin(st);   // debug only (CGB_TC_TRACE=1), nullptr otherwise
   const int epi = epi_variant_for(p.tma_store != 0, f16, bias, residual, mask_src, act, dact);
   if (f16)
     stream_kernel_f16(epi)<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __half*)residual, (const __half*)mask_src,
@@ -1676,18 +1731,7 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
   else
     stream_kernel_bf16(epi)<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
                                                             (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
-  if (tc_trace_on) {
-    cudaStreamSynchronize(st);
-    const unsigned long long t0 = trace_buf[0];
-    fprintf(stderr, "[tc_trace] bn=%d n_tiles=%d tiles=%d stages=%d iters=%d tma_store=%d staging_bufs=%d\n", p.bn, p.n_tiles,
-            p.total_tiles, p.stages, p.ntaps * p.kblocks, p.tma_store, p.staging_bufs);
-    fprintf(stderr, "[tc_trace] tile: P.start P.issued | M.tempty M.full0 M.fullN | E.wait E.tfull E.stg_free E.ph1 E.bar E.done (cycles since start)\n");
-    for (int t = 0; t < 32 && trace_buf[t * 16] != 0; ++t) {
-      fprintf(stderr, "[tc_trace] %2d:", t);
-      for (int k = 0; k <= 15; ++k) fprintf(stderr, " %7lld%s", (long long)(trace_buf[t * 16 + k] - t0), (k == 1 || k == 4 || k == 10) ? " |" : "");
-      fprintf(stderr, "\n");
-    }
-  }
+  trace_end(p, st);
   return after_launch("conv_tc");
 }
 
@@ -1794,6 +1838,8 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
     p.staging_bufs = (ws_stg2 && p.tma_store && stg2 >= 3) ? 2 : 1;
     if (p.staging_bufs == 2) p.stages = stg2;
   }
+  static const int ws_unroll = getenv("CGB_WS_UNROLL") ? atoi(getenv("CGB_WS_UNROLL")) : 1;
+  p.ws_unroll = ws_unroll;
   const int staging_bytes = p.staging_tile_bytes * p.staging_bufs;
   int cols = 32;
   while (cols < 2 * p.bn) cols <<= 1;
@@ -1826,12 +1872,14 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
   int ctas = num_sms() / p.n_tiles * p.n_tiles;
   if (ctas > p.pix_tiles * p.n_tiles) ctas = p.pix_tiles * p.n_tiles;
   const int epi = epi_variant_for(p.tma_store != 0, f16, bias, residual, mask_src, act, dact);
+  p.trace = trace_begin(st);
   if (f16)
     ws_kernel_f16(epi)<<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __half*)residual, (const __half*)mask_src,
                                                        (__half*)out, stats_out);
   else
     ws_kernel_bf16(epi)<<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
                                                         (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
+  trace_end(p, st);
   return after_launch("conv_tc_ws");
 }
 
