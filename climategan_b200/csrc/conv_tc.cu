@@ -292,6 +292,8 @@ struct TcParams {
   int tma_store;               // streaming kernel: copy-out by TMA store from a 128B-swizzled staging tile (bn % 64 == 0)
   int staging_bufs;            // 1 or 2 staging tiles (2: the store of tile i overlaps the epilogue math of tile i+1)
   int ws_unroll;               // weight-stationary kernel: unrolled 3x3 MMA issue (CGB_WS_UNROLL, default on)
+  int aux_tma;                 // the epilogue's second operand (residual / derivative mask) arrives by TMA in the staging tile
+  int aux_bar_off;             // byte offset (from the aligned smem base) of its 8 mbarriers [staging buffer][half]
   int staging_tile_bytes;      // bytes of one staging tile: 128*stage_pitch, or ceil(bn/64) swizzled 16 KB halves (TMA store)
   int twh, thh;                // weight-stationary kernel: halo tile extent (pixels)
   int a_stage_bytes;           // weight-stationary kernel: bytes per halo stage (1024-aligned)
@@ -431,6 +433,7 @@ enum { EPI_AUX_NONE = 0, EPI_AUX_RES_BEFORE = 1, EPI_AUX_RES_AFTER = 2, EPI_AUX_
 enum { EPI_GENERIC = 0, EPI_PLAIN = 1, EPI_BIAS = 2, EPI_BIAS_ACT = 3, EPI_MASK_RELU = 4, EPI_MASK_LRELU = 5, EPI_EXOTIC = 6, EPI_NOTMA = 7,
        EPI_RES = 8,   // + residual, no bias / activation: the ResNet bottleneck's conv1 dgrad with the skip gradient added in
        EPI_VARIANTS = 9 };
+__host__ __device__ constexpr bool epi_may_aux(int epi) { return epi != EPI_PLAIN && epi != EPI_BIAS && epi != EPI_BIAS_ACT; }
 
 template <typename T>
 __device__ __forceinline__ void epi_fast_fetch(const TcParams& p, int ch0, bool pix_ok, long long pixoff, const T* __restrict__ aux_src,
@@ -561,6 +564,26 @@ __device__ __forceinline__ void epilogue_stats(const TcParams& p, const uint8_t*
   }
 }
 
+// ---- the epilogue's second operand (residual / derivative mask) by TMA, in place -------------------------------------------
+// Read row-per-thread from global memory (epi_fast_fetch) the operand bounds every masked dgrad of the 640^2 layers: 8 warps x 8
+// LDG.128 whose 32 lanes touch 32 different lines, ~2 us of DRAM latency per tile with 16 KB in flight per SM (48->128 gamma||beta
+// dgrad: 1.6 ms against 0.6 ms for the same launch without a mask).  With p.aux_tma the operand's tile is loaded by the TMA unit
+// INTO THE STAGING HALF THE RESULT WILL BE WRITTEN TO (same tensor map geometry and swizzle as the store, so every thread finds
+// the operand of its 16-byte chunk exactly where it is about to write): the half's store leader requests the next tile's operand
+// as soon as its bulk store of the current tile has finished reading the half, threads wait on the half's mbarrier, LDS, apply, STS.
+// No extra shared memory (the 48->128 launch has none left), no global address arithmetic in the epilogue.
+struct MaskPf {
+  int ox0, oy0, n0, cn0;    // the next tile of this CTA (n0 < 0: none)
+  uint32_t aux_phase;       // parity bits of the operand barriers, bit = staging buffer * 4 + half
+  int primed;               // the operand of the tile about to be processed has been requested
+  int sbuf;                 // staging buffer of the current tile
+};
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // ---- copy-out by the TMA unit, two 64-channel halves at a time ("rolling store") --------------------------------------------
 // The 16 warps stage a PAIR of halves (each warp one 16-column chunk of its lane quarter per half), a barrier, the halves'
 // leaders (lane 0 of epilogue warp h for half h — bulk groups are per thread) issue their bulk tensor stores, and everybody
@@ -575,7 +598,8 @@ __device__ __forceinline__ void epi_tma_tile(const TcParams& p, uint32_t tmem_ac
                                              int oy0, int n0, int cn0, const float* __restrict__ bias,
                                              const T* __restrict__ residual, const T* __restrict__ mask_src, uint32_t tempty_bar,
                                              int warp, int lane, const CUtensorMap* tmY, float* stats_tab, EpiStats* est,
-                                             bool tempty_is_cluster_addr, int trace_lt) {
+                                             bool tempty_is_cluster_addr, int trace_lt, MaskPf* pf, const CUtensorMap* tmX,
+                                             uint32_t aux_bar0) {
   const int q = warp & 3;              // TMEM lane quarter this warp may access
   const int g = (warp - 2) >> 2;       // 0..1: this warp's 32-column half of each 64-channel half
   const int row = q * 32 + lane;       // tile row == TMEM lane == pixel within the tile
@@ -588,9 +612,10 @@ __device__ __forceinline__ void epi_tma_tile(const TcParams& p, uint32_t tmem_ac
   const bool any_aux = AUX < 0 ? (aux_kind_rt != EPI_AUX_NONE) : (AUX != EPI_AUX_NONE);
   const T* aux_src = residual ? residual : mask_src;
   const float neg = p.act == CGB_ACT_NONE ? 1.f : (p.act == CGB_ACT_RELU ? 0.f : p.slope);
+  const bool aux_tma = !GENERIC_CHUNK && any_aux && p.aux_tma != 0 && pf != nullptr;
   bool pix_ok = false;
   long long pix = 0;
-  if (any_aux || GENERIC_CHUNK) {   // only the tiles that read a second tensor need this thread's pixel address
+  if ((any_aux && !aux_tma) || GENERIC_CHUNK) {   // only the tiles that read a second tensor from global memory need this thread's pixel address
     const int tw_i = row & ((1 << p.tw_log) - 1);
     const int th_i = (row >> p.tw_log) & ((1 << p.th_log) - 1);
     const int tn_i = row >> (p.tw_log + p.th_log);
@@ -618,7 +643,15 @@ __device__ __forceinline__ void epi_tma_tile(const TcParams& p, uint32_t tmem_ac
       }
     }
   };
+  // leader of half h: request the operand tile of (tile coordinates) into staging buffer sb (host: every half of an aux_tma launch
+  // starts inside the tensor; the tail channels of the last half are zero-filled by the tensor map)
+  auto aux_issue = [&](int sb, uint32_t stg_u32, int h, int c_, int x_, int y_, int n_) {
+    const uint32_t bar = aux_bar0 + 8u * (uint32_t)(sb * 4 + h);
+    mbar_expect_tx(bar, 128u * 128u);
+    tma_load_4d(stg_u32 + (uint32_t)h * (128u * 128u), tmX, bar, c_ + h * 64, x_, y_, n_);
+  };
   if (my_hb >= 0 && my_hb < 2) wait_free();
+  if (aux_tma && !pf->primed && my_hb >= 0) aux_issue(pf->sbuf, staging_u32, my_hb, cn0, ox0, oy0, n0);   // the CTA's first tile
   epi_bar_sync();
   if (et == 0) tc_trace(p.trace, trace_lt, 7);
   for (int hp = 0; hp < nh; hp += 2) {
@@ -629,10 +662,30 @@ __device__ __forceinline__ void epi_tma_tile(const TcParams& p, uint32_t tmem_ac
     if (va) { if (c0 + 1 < nchunks) tmem_ld32(t_row + (uint32_t)(c0 * 16), ra); else tmem_ld16(t_row + (uint32_t)(c0 * 16), ra); }
     if (vb) { if (c1 + 1 < nchunks) tmem_ld32(t_row + (uint32_t)(c1 * 16), rb); else tmem_ld16(t_row + (uint32_t)(c1 * 16), rb); }
     if (!GENERIC_CHUNK && any_aux) {
+      if (aux_tma) {   // the operand sits where this thread is about to write: halves hp, hp + 1 of this staging buffer
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        if (c0 + k < nchunks) epi_fast_fetch<T>(p, cn0 + (c0 + k) * 16, pix_ok, pixoff, aux_src, xa + 2 * k);
-        if (c1 + k < nchunks) epi_fast_fetch<T>(p, cn0 + (c1 + k) * 16, pix_ok, pixoff, aux_src, xb + 2 * k);
+        for (int hh = 0; hh < 2; ++hh) {
+          if (hp + hh < nh) {
+            const uint32_t bit = (uint32_t)(pf->sbuf * 4 + hp + hh);
+            mbar_wait(aux_bar0 + 8u * bit, (pf->aux_phase >> bit) & 1u);
+            pf->aux_phase ^= 1u << bit;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t ja = (uint32_t)((c0 + k) * 2 + h), jb = (uint32_t)((c1 + k) * 2 + h);
+            if (c0 + k < nchunks) xa[2 * k + h] = lds128(row_u32 + (ja >> 3) * (128u * 128u) + (((ja & 7u) << 4) ^ sw16));
+            if (c1 + k < nchunks) xb[2 * k + h] = lds128(row_u32 + (jb >> 3) * (128u * 128u) + (((jb & 7u) << 4) ^ sw16));
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          if (c0 + k < nchunks) epi_fast_fetch<T>(p, cn0 + (c0 + k) * 16, pix_ok, pixoff, aux_src, xa + 2 * k);
+          if (c1 + k < nchunks) epi_fast_fetch<T>(p, cn0 + (c1 + k) * 16, pix_ok, pixoff, aux_src, xb + 2 * k);
+        }
       }
     }
     tmem_ld_wait();
@@ -649,8 +702,19 @@ __device__ __forceinline__ void epi_tma_tile(const TcParams& p, uint32_t tmem_ac
     if (my_hb >= hp && my_hb < hp + 2) {
       if (cn0 + my_hb * 64 < p.cout_s) tma_store_4d(tmY, staging_u32 + (uint32_t)my_hb * (128u * 128u), cn0 + my_hb * 64, ox0, oy0, n0);
       tma_store_commit();
+      if (aux_tma && pf->n0 >= 0) {   // the next tile's operand into the half it will be staged in, once that half has been read
+        if (p.staging_bufs == 2) {
+          tma_store_wait_read<1>();   // (the store of the tile before this one read the other buffer)
+          aux_issue(pf->sbuf ^ 1, pf->sbuf ? staging_u32 - (uint32_t)p.staging_tile_bytes : staging_u32 + (uint32_t)p.staging_tile_bytes,
+                    my_hb, pf->cn0, pf->ox0, pf->oy0, pf->n0);
+        } else {
+          tma_store_wait_read<0>();
+          aux_issue(0, staging_u32, my_hb, pf->cn0, pf->ox0, pf->oy0, pf->n0);
+        }
+      }
     }
   }
+  if (aux_tma) pf->primed = pf->n0 >= 0 ? 1 : 0;
   if (et == 0) tc_trace(p.trace, trace_lt, 9);
   // (2-CTA kernel: ONE remote arrive per CTA on the leader's barrier, after the last barrier — every warp's TMEM reads are
   //  done; sixteen ~500-cycle cluster arrives per tile and CTA showed up as a slow-down on the short-K 1x1 convs)
@@ -665,12 +729,13 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
                                               const T* __restrict__ mask_src, T* __restrict__ y,
                                               uint32_t tempty_bar, int warp, int lane, const CUtensorMap* tmY = nullptr,
                                               uint32_t staging_u32 = 0, float* stats_tab = nullptr, EpiStats* est = nullptr,
-                                              bool tempty_is_cluster_addr = false, int trace_lt = 1 << 20) {
+                                              bool tempty_is_cluster_addr = false, int trace_lt = 1 << 20,
+                                              MaskPf* pf = nullptr, const CUtensorMap* tmX = nullptr, uint32_t aux_bar0 = 0) {
   if constexpr (EPI != EPI_NOTMA) {
     // EPI: the launch's epilogue variant, chosen on the host (epi_variant_for) and compiled into the kernel
 #define CGB_EPI_TILE(B, A, X, G)                                                                                                   \
   epi_tma_tile<T, B, A, X, G>(p, tmem_acc, staging_gen, staging_u32, ox0, oy0, n0, cn0, bias, residual, mask_src, tempty_bar, warp, \
-                              lane, tmY, stats_tab, est, tempty_is_cluster_addr, trace_lt)
+                              lane, tmY, stats_tab, est, tempty_is_cluster_addr, trace_lt, pf, tmX, aux_bar0)
     if constexpr (EPI == EPI_PLAIN) CGB_EPI_TILE(0, 0, EPI_AUX_NONE, false);              // conv -> BatchNorm (ResNet), plain dgrad
     else if constexpr (EPI == EPI_BIAS) CGB_EPI_TILE(1, 0, EPI_AUX_NONE, false);          // gamma || beta, last layers
     else if constexpr (EPI == EPI_BIAS_ACT) CGB_EPI_TILE(1, 1, EPI_AUX_NONE, false);      // conv + bias + (leaky) ReLU
@@ -699,7 +764,23 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
   const uint32_t t_row = tmem_acc + ((uint32_t)(q * 32) << 16);
   const int nchunks = p.bn >> 4;
   // ---- per-thread copy-out from a padded row-major staging tile (strided parity-class dgrad, N tiles that are not whole halves) --
+  // phase-2 geometry of this thread (fixed for the launch): chunk column c of rows rb0 + i * rstep
+  const int chunks_per_row = p.bn >> 3;                 // <= 32
+  const int rows_per_iter = 32 / chunks_per_row;        // >= 1
+  const int rsub = lane / chunks_per_row;
+  const int c = lane - rsub * chunks_per_row;
+  const int rstep = EPI_WARPS * rows_per_iter;
+  const int rb0 = (warp - 2) * rows_per_iter + rsub;
+  auto row_off = [&](int r2, int tx0, int ty0, int tn0, int ch2, bool& ok) -> long long {
+    const int tw2 = r2 & ((1 << p.tw_log) - 1);
+    const int th2 = (r2 >> p.tw_log) & ((1 << p.th_log) - 1);
+    const int tn2 = r2 >> (p.tw_log + p.th_log);
+    const int ox2 = tx0 + tw2, oy2 = ty0 + th2, img2 = tn0 + tn2;
+    ok = r2 < 128 && rsub < rows_per_iter && ch2 < p.cout_s && ox2 < p.wout && oy2 < p.hout && img2 < p.n;
+    return (((long long)img2 * p.hfull + (oy2 * p.out_stride + p.out_off_y)) * p.wfull + (ox2 * p.out_stride + p.out_off_x)) * p.cout_s + ch2;
+  };
   epi_bar_sync();  // previous tile's copy-out has finished reading the staging buffer
+  if (et == 0) tc_trace(p.trace, trace_lt, 7);
   uint8_t* my_row = staging_gen + (size_t)row * p.stage_pitch;
   // lean phase 1 for the common case of this path — the ReLU-masked dgrad (no bias, no activation, no residual; the 0/1 mask is
   // applied by phase 2): 32-column accumulator loads, pack, 16-byte staging stores with 32-bit shared addresses
@@ -745,55 +826,44 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
   tc_fence_before();
   __syncwarp();
   if (lane == 0 && !tempty_is_cluster_addr) mbar_arrive(tempty_bar);
+  if (et == 0) tc_trace(p.trace, trace_lt, 8);
   epi_bar_sync();  // staging complete
+  if (et == 0) tc_trace(p.trace, trace_lt, 9);
   if (et == 0 && tempty_is_cluster_addr) mbar_arrive_cluster(tempty_bar);
   if (stats_tab) epilogue_stats<T>(p, staging_gen, false, ox0, oy0, n0, cn0, stats_tab, *est, warp, lane);
   // phase 2: lanes cover (rows_per_iter x chunks_per_row) 16-byte chunks; the row/chunk split of a lane is fixed, so
   // the only per-iteration work is the pixel address.  Consecutive lanes write consecutive chunks of a pixel and then
   // the next pixel: full 32-byte sectors, no read-modify-write.
-  const int chunks_per_row = p.bn >> 3;                 // <= 32
-  const int rows_per_iter = 32 / chunks_per_row;        // >= 1
-  const int rsub = lane / chunks_per_row;
-  const int c = lane - rsub * chunks_per_row;
   const int ch = cn0 + c * 8;
-  if (rsub < rows_per_iter && ch < p.cout_s) {
-    const int ew = warp - 2;  // 0..EPI_WARPS-1
-    // four rows per batch: the four mask loads (DRAM / L2 latency) are in flight together — one load -> multiply -> store chain
-    // per row left ~8 serial global round trips per thread and tile (the 128->48 gamma||beta dgrad at 640^2: 1.2 ms -> see DESIGN)
-    constexpr int PB = 4;
-    const int rstep = EPI_WARPS * rows_per_iter;
-    for (int rb = ew * rows_per_iter + rsub; rb < 128; rb += PB * rstep) {
-      long long off[PB];
-      bool ok[PB];
-      uint4 val[PB], mk[PB];
+  // four rows per batch: the four mask loads (DRAM / L2 latency) are in flight together — one load -> multiply -> store chain
+  // per row left ~8 serial global round trips per thread and tile (the 128->48 gamma||beta dgrad at 640^2: 1.2 ms -> see DESIGN)
+  constexpr int PB = 4;
+#pragma unroll 1
+  for (int r0 = rb0; r0 < 128; r0 += PB * rstep) {
+    long long off[PB];
+    bool ok[PB];
+    uint4 val[PB], mk[PB];
 #pragma unroll
-      for (int i = 0; i < PB; ++i) {
-        const int r2 = rb + i * rstep;
-        const int tw2 = r2 & ((1 << p.tw_log) - 1);
-        const int th2 = (r2 >> p.tw_log) & ((1 << p.th_log) - 1);
-        const int tn2 = r2 >> (p.tw_log + p.th_log);
-        const int ox2 = ox0 + tw2, oy2 = oy0 + th2, img2 = n0 + tn2;
-        ok[i] = r2 < 128 && ox2 < p.wout && oy2 < p.hout && img2 < p.n;
-        off[i] = (((long long)img2 * p.hfull + (oy2 * p.out_stride + p.out_off_y)) * p.wfull + (ox2 * p.out_stride + p.out_off_x)) *
-                     p.cout_s + ch;
-        if (ok[i]) {
-          val[i] = *reinterpret_cast<const uint4*>(staging_gen + (size_t)r2 * p.stage_pitch + (size_t)c * 16);
-          if (mask_late) mk[i] = __ldg(reinterpret_cast<const uint4*>(mask_src + off[i]));
-        }
+    for (int i = 0; i < PB; ++i) {
+      const int r2 = r0 + i * rstep;
+      off[i] = row_off(r2, ox0, oy0, n0, ch, ok[i]);
+      if (ok[i]) {
+        val[i] = *reinterpret_cast<const uint4*>(staging_gen + (size_t)r2 * p.stage_pitch + (size_t)c * 16);
+        if (mask_late) mk[i] = __ldg(reinterpret_cast<const uint4*>(mask_src + off[i]));
       }
+    }
 #pragma unroll
-      for (int i = 0; i < PB; ++i) {
-        if (!ok[i]) continue;
-        if (mask_late) {  // relu derivative: keep where the forward output was > 0 (packed bf16x2 compare + multiply)
-          using T2 = typename Pk<T>::T2;
-          const T2* mh = reinterpret_cast<const T2*>(&mk[i]);
-          T2* vh = reinterpret_cast<T2*>(&val[i]);
-          const T2 zero2 = Pk<T>::zero2();
+    for (int i = 0; i < PB; ++i) {
+      if (!ok[i]) continue;
+      if (mask_late) {  // relu derivative: keep where the forward output was > 0 (packed bf16x2 compare + multiply)
+        using T2 = typename Pk<T>::T2;
+        const T2* mh = reinterpret_cast<const T2*>(&mk[i]);
+        T2* vh = reinterpret_cast<T2*>(&val[i]);
+        const T2 zero2 = Pk<T>::zero2();
 #pragma unroll
-          for (int j = 0; j < 4; ++j) vh[j] = __hmul2(vh[j], __hgt2(mh[j], zero2));
-        }
-        *reinterpret_cast<uint4*>(y + off[i]) = val[i];
+        for (int j = 0; j < 4; ++j) vh[j] = __hmul2(vh[j], __hgt2(mh[j], zero2));
       }
+      *reinterpret_cast<uint4*>(y + off[i]) = val[i];
     }
   }
   }   // EPI_NOTMA
@@ -807,7 +877,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
 template <typename T, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const T* __restrict__ residual,
+               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const TcParams p, const float* __restrict__ bias, const T* __restrict__ residual,
                const T* __restrict__ mask_src, T* __restrict__ y, float* __restrict__ stats_out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -838,6 +908,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     if (p.tma_store) prefetch_tmap(&tmY);
+    if (p.aux_tma) {
+      prefetch_tmap(&tmX);
+      for (int i = 0; i < 8; ++i) mbar_init(base + (uint32_t)p.aux_bar_off + 8u * (uint32_t)i, 1);
+    }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -931,6 +1005,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     EpiStats est;
     est.ch = -1;
     epi_stats_flush(p, est, stats_tab);   // (zeroes the registers)
+    MaskPf pf;
+    pf.n0 = -1;
+    pf.aux_phase = 0u;
+    pf.primed = 0;
+    pf.sbuf = 0;
     int lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       const int buf = lt & 1;
@@ -941,6 +1020,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tx = pt - py * p.tiles_x;
       const int tn = (int)fdiv((uint32_t)py, (uint32_t)p.tiles_y, p.mg_ty);
       const int ty = py - tn * p.tiles_y;
+      if constexpr (epi_may_aux(EPI)) {   // the next tile of this CTA, for the mask prefetch of the per-thread copy-out
+        const int tile2 = tile + (int)gridDim.x;
+        pf.n0 = -1;
+        pf.sbuf = (p.staging_bufs == 2) ? (lt & 1) : 0;
+        if ((mask_src || residual) && tile2 < p.total_tiles) {
+          const int pt2 = (int)fdiv((uint32_t)tile2, (uint32_t)p.n_tiles, p.mg_nt);
+          const int py2 = (int)fdiv((uint32_t)pt2, (uint32_t)p.tiles_x, p.mg_tx);
+          const int tn2 = (int)fdiv((uint32_t)py2, (uint32_t)p.tiles_y, p.mg_ty);
+          pf.cn0 = (tile2 - pt2 * p.n_tiles) * p.bn;
+          pf.ox0 = (pt2 - py2 * p.tiles_x) << p.tw_log;
+          pf.oy0 = (py2 - tn2 * p.tiles_y) << p.th_log;
+          pf.n0 = tn2 << tn_log;
+        }
+      }
       if (threadIdx.x == 64) tc_trace(p.trace, lt, 5);
       mbar_wait(tfull_bar(buf), bph);
       tc_fence_after();
@@ -948,7 +1041,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t sb = (p.staging_bufs == 2) ? (uint32_t)(lt & 1) * staging_tile : 0u;
       epilogue_tile<T, EPI>(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen + sb, tx << p.tw_log, ty << p.th_log, tn << tn_log,
                     nt * p.bn, bias, residual, mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr,
-                    staging + sb, stats_tab, &est, false, lt);
+                    staging + sb, stats_tab, &est, false, lt, epi_may_aux(EPI) ? &pf : nullptr, &tmX, base + (uint32_t)p.aux_bar_off);
       if (threadIdx.x == 64) tc_trace(p.trace, lt, 10);
     }
     if (p.tma_store && lane == 0 && warp < 6) tma_store_wait_all();   // every store leader: its bulk stores have completed   // the issuing thread: every bulk store has completed
@@ -992,7 +1085,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <typename T, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const T* __restrict__ residual,
+                const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const TcParams p, const float* __restrict__ bias, const T* __restrict__ residual,
                 const T* __restrict__ mask_src, T* __restrict__ y, float* __restrict__ stats_out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -1028,6 +1121,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     if (p.tma_store) prefetch_tmap(&tmY);
+    if (p.aux_tma) {
+      prefetch_tmap(&tmX);
+      for (int i = 0; i < 8; ++i) mbar_init(base + (uint32_t)p.aux_bar_off + 8u * (uint32_t)i, 1);
+    }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -1125,17 +1222,28 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     EpiStats est;
     est.ch = -1;
     epi_stats_flush(p, est, stats_tab);
+    MaskPf pf;
+    pf.n0 = -1;
+    pf.aux_phase = 0u;
+    pf.primed = 0;
+    pf.sbuf = 0;
     int lt = 0;
     for (int t2 = pair; t2 < pair_tiles; t2 += npairs, ++lt) {
       const int buf = lt & 1;
       const uint32_t bph = (uint32_t)(lt >> 1) & 1u;
       int ox0, oy0, n0, cn0;
       decode(t2, ox0, oy0, n0, cn0);
+      if constexpr (epi_may_aux(EPI)) {
+        pf.n0 = -1;
+        pf.sbuf = (p.staging_bufs == 2) ? (lt & 1) : 0;
+        if ((mask_src || residual) && t2 + npairs < pair_tiles) decode(t2 + npairs, pf.ox0, pf.oy0, pf.n0, pf.cn0);
+      }
       mbar_wait(tfull_bar(buf), bph);
       tc_fence_after();
       const uint32_t sb = (p.staging_bufs == 2) ? (uint32_t)(lt & 1) * staging_tile : 0u;
       epilogue_tile<T, EPI>(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen + sb, ox0, oy0, n0, cn0, bias, residual, mask_src, y,
-                       mapa_rank(tempty_bar(buf), 0), warp, lane, p.tma_store ? &tmY : nullptr, staging + sb, stats_tab, &est, true);
+                       mapa_rank(tempty_bar(buf), 0), warp, lane, p.tma_store ? &tmY : nullptr, staging + sb, stats_tab, &est, true,
+                       1 << 20, epi_may_aux(EPI) ? &pf : nullptr, &tmX, base + (uint32_t)p.aux_bar_off);
     }
     if (p.tma_store && lane == 0 && warp < 6) tma_store_wait_all();   // every store leader: its bulk stores have completed
     if (stats_tab) {
@@ -1177,7 +1285,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 template <typename T, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmY, const TcParams p, const float* __restrict__ bias, const T* __restrict__ residual,
+               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const TcParams p, const float* __restrict__ bias, const T* __restrict__ residual,
                const T* __restrict__ mask_src, T* __restrict__ y, float* __restrict__ stats_out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -1210,6 +1318,11 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (p.tma_store) prefetch_tmap(&tmY);
+    if (p.aux_tma) {
+      prefetch_tmap(&tmX);
+      for (int i = 0; i < 8; ++i) mbar_init(base + (uint32_t)p.aux_bar_off + 8u * (uint32_t)i, 1);
+    }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -1327,6 +1440,11 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     EpiStats est;
     est.ch = -1;
     epi_stats_flush(p, est, stats_tab);
+    MaskPf pf;
+    pf.n0 = -1;
+    pf.aux_phase = 0u;
+    pf.primed = 0;
+    pf.sbuf = 0;
     int lt = 0;
     for (int pt = pt0; pt < p.pix_tiles; pt += pt_step, ++lt) {
       const int buf = lt & 1;
@@ -1342,8 +1460,22 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // two staging tiles when they fit (launch_fprop): the store of tile i overlaps the staging of tile i+1 — with one, every
       // tile of a small-channel conv (24->24 at 640^2: 684 cycles of MMAs) waited ~1500 cycles for the previous bulk store
       const uint32_t sb = (p.staging_bufs == 2) ? (uint32_t)(lt & 1) * (uint32_t)p.staging_tile_bytes : 0u;
+      if constexpr (epi_may_aux(EPI)) {
+        const int pt2 = pt + pt_step;
+        pf.n0 = -1;
+        pf.sbuf = (p.staging_bufs == 2) ? (lt & 1) : 0;
+        if ((mask_src || residual) && pt2 < p.pix_tiles) {
+          const int py2 = (int)fdiv((uint32_t)pt2, (uint32_t)p.tiles_x, p.mg_tx);
+          const int img2 = (int)fdiv((uint32_t)py2, (uint32_t)p.tiles_y, p.mg_ty);
+          pf.ox0 = (pt2 - py2 * p.tiles_x) << 3;
+          pf.oy0 = (py2 - img2 * p.tiles_y) << 4;
+          pf.n0 = img2;
+          pf.cn0 = cn0;
+        }
+      }
       epilogue_tile<T, EPI>(p, tmem_base + (uint32_t)(buf * p.bn), staging_gen + sb, tx << 3, ty << 4, img, cn0, bias, residual,
-                    mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr, staging + sb, stats_tab, &est, false, lt);
+                    mask_src, y, tempty_bar(buf), warp, lane, p.tma_store ? &tmY : nullptr, staging + sb, stats_tab, &est, false, lt,
+                    epi_may_aux(EPI) ? &pf : nullptr, &tmX, base + (uint32_t)p.aux_bar_off);
       if (threadIdx.x == 64) tc_trace(p.trace, lt, 10);
     }
     if (p.tma_store && lane == 0 && warp < 6) tma_store_wait_all();   // every store leader: its bulk stores have completed
@@ -1458,11 +1590,26 @@ static bool tma_store_enabled() {
   static const int v = getenv("CGB_TMA_STORE") ? atoi(getenv("CGB_TMA_STORE")) : 1;
   return v != 0;
 }
+// the epilogue's second operand by TMA into the staging tile (struct MaskPf); CGB_AUX_TMA=0: row-per-thread global loads,
+// and the ReLU-masked dgrad back on the per-thread copy-out
+static bool aux_tma_enabled() {
+  static const int v = getenv("CGB_AUX_TMA") ? atoi(getenv("CGB_AUX_TMA")) : 1;
+  return v != 0;
+}
 static bool tma_store_ok(int bn, int n_tiles, int dact, const void* mask_src) {
   // the ReLU-derivative mask stays at the per-thread copy-out, where its loads are coalesced (consecutive lanes = consecutive chunks
   // of a pixel): read row-per-thread in phase 1 it cost 32 sectors in 32 lines per LDG (256->256 d2 dgrad: 54 -> 71 us)
   static const int mask_tma = getenv("CGB_MASK_TMA") ? atoi(getenv("CGB_MASK_TMA")) : 0;
-  return tma_store_enabled() && (bn % 64 == 0 || n_tiles == 1) && (mask_tma || !(mask_src && dact == CGB_ACT_RELU));
+  return tma_store_enabled() && (bn % 64 == 0 || n_tiles == 1) && (mask_tma || aux_tma_enabled() || !(mask_src && dact == CGB_ACT_RELU));
+}
+// second operand by TMA: a TMA-store launch with exactly one of residual / mask, an epilogue on the lean chunk code (no tanh /
+// sigmoid / selu), no statistics pass over the staging tile, and every 64-channel half of every N tile starting inside the tensor
+static bool aux_tma_ok(bool tma_store, int bn, int n_tiles, int cout_s, int act, const void* residual, const void* mask_src,
+                       const float* stats_out) {
+  if (!aux_tma_enabled() || !tma_store || stats_out || act > CGB_ACT_LRELU) return false;
+  if ((residual != nullptr) == (mask_src != nullptr)) return false;
+  const int last_cn0 = (n_tiles - 1) * bn, nh = (bn + 63) / 64;
+  return last_cn0 + (nh - 1) * 64 < cout_s;
 }
 static int staging_tile_bytes_for(int bn, bool tma) {
   const int plain = 128 * (bn * 2 + 16);
@@ -1544,9 +1691,9 @@ static int epi_variant_for(bool tma_store, bool f16, const float* bias, const vo
   return act == CGB_ACT_NONE ? EPI_BIAS : EPI_BIAS_ACT;
 }
 
-typedef void (*TcKernelBf16)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const float*, const __nv_bfloat16*,
+typedef void (*TcKernelBf16)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const float*, const __nv_bfloat16*,
                              const __nv_bfloat16*, __nv_bfloat16*, float*);
-typedef void (*TcKernelF16)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const float*, const __half*,
+typedef void (*TcKernelF16)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const float*, const __half*,
                             const __half*, __half*, float*);
 #define CGB_KERNEL_TABLES(NAME, KERNEL)                                                  \
   static TcKernelBf16 NAME##_bf16(int epi) {                                             \
@@ -1620,11 +1767,12 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
   while (cols < 2 * p.bn) cols <<= 1;
   p.tmem_cols = cols;
   const int stage_bytes = A_TILE_BYTES + p.bn * 128;
-  int stages = (int)((SMEM_LIMIT - 1024 - 256 - staging_bytes - stats_bytes) / stage_bytes);
+  int stages = (int)((SMEM_LIMIT - 1024 - 320 - staging_bytes - stats_bytes) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
   p.stats_off = stages * stage_bytes + staging_bytes + 16 * stages + 64;
+  p.aux_bar_off = p.stats_off + stats_bytes;
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[4] = {(cuuint64_t)cin_s, (cuuint64_t)win, (cuuint64_t)hin, (cuuint64_t)n};
@@ -1642,12 +1790,16 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
     if (!encode_map(&tmB, w, 3, dims, strides, box, estr, "weights", f16)) return CGB_LAUNCH_FAILURE;
   }
   CUtensorMap tmY = tmB;   // (any valid map when the TMA store is off: the kernel never touches it)
+  CUtensorMap tmX = tmB;   // (likewise when the second operand does not come by TMA)
+  p.aux_tma = aux_tma_ok(p.tma_store != 0, p.bn, p.n_tiles, cout_s, act, residual, mask_src, stats_out) ? 1 : 0;
   if (p.tma_store) {
     cuuint64_t dims[4] = {(cuuint64_t)cout_s, (cuuint64_t)wfull, (cuuint64_t)hfull, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)cout_s * 2, (cuuint64_t)wfull * cout_s * 2, (cuuint64_t)hfull * wfull * cout_s * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)(1 << p.tw_log), (cuuint32_t)(1 << p.th_log), (cuuint32_t)(1 << tn_log)};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (!encode_map(&tmY, out, 4, dims, strides, box, estr, "output", f16)) return CGB_LAUNCH_FAILURE;
+    if (p.aux_tma && !encode_map(&tmX, residual ? residual : mask_src, 4, dims, strides, box, estr, "epilogue operand", f16))
+      return CGB_LAUNCH_FAILURE;
   }
   static std::once_flag attr_once;
   std::call_once(attr_once, [] {
@@ -1668,10 +1820,11 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
     const bool k_ok = tc2 >= 2 || (long long)tt.ntaps * cin_s >= tc2_min_k;
     if (tc2 && k_ok && p.bn % 16 == 0 && pair_tiles >= num_sms() / 2) {
       const int stage2 = A_TILE_BYTES + p.bn * 64;
-      int stages2 = (int)((SMEM_LIMIT - 1024 - 256 - staging_bytes - stats_bytes) / stage2);
+      int stages2 = (int)((SMEM_LIMIT - 1024 - 320 - staging_bytes - stats_bytes) / stage2);
       if (stages2 > 10) stages2 = 10;
       p.stages = stages2;
       p.stats_off = stages2 * stage2 + staging_bytes + 16 * stages2 + 64;
+      p.aux_bar_off = p.stats_off + stats_bytes;
       // the pair's weight map delivers bn/2 rows per load
       {
         cuuint64_t dims[3] = {(cuuint64_t)cin_s, (cuuint64_t)wtaps_total, (cuuint64_t)cout_s};
@@ -1680,7 +1833,7 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
         cuuint32_t estr[3] = {1, 1, 1};
         if (!encode_map(&tmB, w, 3, dims, strides, box, estr, "weights (half tile)", f16)) return CGB_LAUNCH_FAILURE;
       }
-      const size_t smem2 = (size_t)stages2 * stage2 + staging_bytes + 16 * stages2 + 64 + stats_bytes + 1024;
+      const size_t smem2 = (size_t)stages2 * stage2 + staging_bytes + 16 * stages2 + 64 + stats_bytes + 64 + 1024;
       static std::once_flag attr2_once;
       std::call_once(attr2_once, [] {
         for (int e = 0; e < EPI_VARIANTS; ++e) {
@@ -1704,10 +1857,10 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
       cudaError_t e;
       const int epi2 = epi_variant_for(p.tma_store != 0, f16, bias, residual, mask_src, act, dact);
       if (f16)
-        e = cudaLaunchKernelEx(&cfg, pair_kernel_f16(epi2), tmA, tmB, tmY, p, bias, (const __half*)residual, (const __half*)mask_src,
+        e = cudaLaunchKernelEx(&cfg, pair_kernel_f16(epi2), tmA, tmB, tmY, tmX, p, bias, (const __half*)residual, (const __half*)mask_src,
                                (__half*)out, stats_out);
       else
-        e = cudaLaunchKernelEx(&cfg, pair_kernel_bf16(epi2), tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
+        e = cudaLaunchKernelEx(&cfg, pair_kernel_bf16(epi2), tmA, tmB, tmY, tmX, p, bias, (const __nv_bfloat16*)residual,
                                (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
       if (e != cudaSuccess) {
         cudaGetLastError();
@@ -1717,7 +1870,7 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
       return after_launch("conv_tc2");
     }
   }
-  const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 16 * stages + 64 + stats_bytes + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + staging_bytes + 16 * stages + 64 + stats_bytes + 64 + 1024;
   if (smem > SMEM_LIMIT) {
     set_error("tcgen05 engine: tile does not fit shared memory (bn=%d, stats=%d)", p.bn, p.stats);
     return CGB_UNSUPPORTED;
@@ -1726,10 +1879,10 @@ static int launch_stream(const void* in, const void* w, void* out, int n, int hi
   p.trace = trace_begin(st);   // debug only (CGB_TC_TRACE=1), nullptr otherwise
   const int epi = epi_variant_for(p.tma_store != 0, f16, bias, residual, mask_src, act, dact);
   if (f16)
-    stream_kernel_f16(epi)<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __half*)residual, (const __half*)mask_src,
+    stream_kernel_f16(epi)<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, tmX, p, bias, (const __half*)residual, (const __half*)mask_src,
                                                            (__half*)out, stats_out);
   else
-    stream_kernel_bf16(epi)<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
+    stream_kernel_bf16(epi)<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, tmY, tmX, p, bias, (const __nv_bfloat16*)residual,
                                                             (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
   trace_end(p, st);
   return after_launch("conv_tc");
@@ -1764,7 +1917,7 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
       int bn = ((cout_s + nt - 1) / nt + 15) / 16 * 16;
       if (bn > 256) continue;
       const size_t wb = (size_t)kblocks * taps * bn * 128;
-      const size_t fixed = wb + (size_t)staging_tile_bytes_for(bn, tma_store_ok(bn, nt, dact, mask_src)) + 1024 + 256 + stats_bytes;
+      const size_t fixed = wb + (size_t)staging_tile_bytes_for(bn, tma_store_ok(bn, nt, dact, mask_src)) + 1024 + 320 + stats_bytes;
       if (fixed + 2 * (size_t)a_stage > SMEM_LIMIT) continue;
       int stg = (int)((SMEM_LIMIT - fixed) / a_stage);
       if (stg > 6) stg = 6;
@@ -1832,7 +1985,7 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
   {
     // second staging tile if at least three activation stages remain (ws_stages was sized with one tile)
     static const int ws_stg2 = getenv("CGB_WS_STAGING2") ? atoi(getenv("CGB_WS_STAGING2")) : 1;
-    const size_t fixed2 = (size_t)kblocks * taps * p.bn * 128 + 2 * (size_t)p.staging_tile_bytes + 1024 + 256 + stats_bytes;
+    const size_t fixed2 = (size_t)kblocks * taps * p.bn * 128 + 2 * (size_t)p.staging_tile_bytes + 1024 + 320 + stats_bytes;
     int stg2 = fixed2 < SMEM_LIMIT ? (int)((SMEM_LIMIT - fixed2) / a_stage) : 0;
     if (stg2 > 6) stg2 = 6;
     p.staging_bufs = (ws_stg2 && p.tma_store && stg2 >= 3) ? 2 : 1;
@@ -1860,24 +2013,29 @@ static int launch_fprop(const void* in, const void* w, void* out, int n, int hin
     if (!encode_map(&tmB, w, 3, dims, strides, box, estr, "weights", f16)) return CGB_LAUNCH_FAILURE;
   }
   CUtensorMap tmY = tmB;   // (any valid map when the TMA store is off: the kernel never touches it)
+  CUtensorMap tmX = tmB;
+  p.aux_tma = aux_tma_ok(p.tma_store != 0, p.bn, p.n_tiles, cout_s, act, residual, mask_src, stats_out) ? 1 : 0;
   if (p.tma_store) {
     cuuint64_t dims[4] = {(cuuint64_t)cout_s, (cuuint64_t)wout, (cuuint64_t)hout, (cuuint64_t)n};
     cuuint64_t strides[3] = {(cuuint64_t)cout_s * 2, (cuuint64_t)wout * cout_s * 2, (cuuint64_t)hout * wout * cout_s * 2};
     cuuint32_t box[4] = {64, 8, 16, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     if (!encode_map(&tmY, out, 4, dims, strides, box, estr, "output", f16)) return CGB_LAUNCH_FAILURE;
+    if (p.aux_tma && !encode_map(&tmX, residual ? residual : mask_src, 4, dims, strides, box, estr, "epilogue operand", f16))
+      return CGB_LAUNCH_FAILURE;
   }
   p.stats_off = (int)((size_t)p.kblocks * taps * p.bn * 128 + (size_t)p.stages * a_stage + staging_bytes + 16 * p.stages + 64);
-  const size_t smem = (size_t)p.stats_off + stats_bytes + 1024;
+  p.aux_bar_off = p.stats_off + stats_bytes;
+  const size_t smem = (size_t)p.stats_off + stats_bytes + 64 + 1024;
   int ctas = num_sms() / p.n_tiles * p.n_tiles;
   if (ctas > p.pix_tiles * p.n_tiles) ctas = p.pix_tiles * p.n_tiles;
   const int epi = epi_variant_for(p.tma_store != 0, f16, bias, residual, mask_src, act, dact);
   p.trace = trace_begin(st);
   if (f16)
-    ws_kernel_f16(epi)<<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __half*)residual, (const __half*)mask_src,
+    ws_kernel_f16(epi)<<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, tmY, tmX, p, bias, (const __half*)residual, (const __half*)mask_src,
                                                        (__half*)out, stats_out);
   else
-    ws_kernel_bf16(epi)<<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, tmY, p, bias, (const __nv_bfloat16*)residual,
+    ws_kernel_bf16(epi)<<<ctas, TC_THREADS, smem, st>>>(tmA, tmB, tmY, tmX, p, bias, (const __nv_bfloat16*)residual,
                                                         (const __nv_bfloat16*)mask_src, (__nv_bfloat16*)out, stats_out);
   trace_end(p, st);
   return after_launch("conv_tc_ws");

@@ -33,9 +33,15 @@ CASES = {
     "d3": ("fwd", 8, 512, 512, 39, 39, 4, 1, 1, 1),       # discriminator 512->512 4x4
     "sh8": ("fwd", 8, 32, 128, 640, 640, 1, 0, 1, 1),     # SPADE mlp_shared as a K=32 GEMM, painter batch of the full step
     "gb48_8": ("fwd", 8, 128, 48, 640, 640, 3, 1, 1, 1),  # gamma||beta, painter batch of the full step
+    "gb80_640": ("fwd", 16, 128, 80, 640, 640, 3, 1, 1, 1),   # gamma||beta of the 40-channel block at 640^2 (C1 painter)
+    "dg80": ("dgrad", 16, 128, 80, 640, 640, 3, 1, 1, 1),
+    "wg80": ("wgrad", 16, 128, 80, 640, 640, 3, 1, 1, 1),
+    "vgg1d": ("dgrad", 8, 64, 64, 640, 640, 3, 1, 1, 1),      # VGG19 conv1_2 dgrad through ReLU
+    "vgg2d": ("dgrad", 8, 128, 128, 320, 320, 3, 1, 1, 1),
 }
 names = sys.argv[1:] or list(CASES)
 reps = int(os.environ.get("REPS", "5"))
+DACT = {"relu": _lib.ACT_RELU, "lrelu": _lib.ACT_LRELU, "none": _lib.ACT_NONE}[os.environ.get("DACT", "relu")]
 for name in names:
     which, n, ci, co, h, w, k, pad, dil, stride = (tuple(CASES[name]) + (1, 1))[:10]
     ho, wo = (h + 2 * pad - dil * (k - 1) - 1) // stride + 1, (w + 2 * pad - dil * (k - 1) - 1) // stride + 1
@@ -48,7 +54,7 @@ for name in names:
         if which == "fwd":
             return ops.conv_fwd_raw(x, wp, bias, None, g)
         if which == "dgrad":
-            return ops.conv_dgrad_raw(gy, wp, (n, h, w, ci), g, _lib.ACT_RELU, x)
+            return ops.conv_dgrad_raw(gy, wp, (n, h, w, ci), g, DACT, x if DACT != _lib.ACT_NONE else None)
         return ops.conv_wgrad_raw(x, gy, g, False)
     run(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

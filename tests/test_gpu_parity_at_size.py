@@ -27,6 +27,15 @@ CLASSES = [
     ("dgrad", 8, 1024, 256, 80, 80, 1, 1, 1, 0),
     ("dgrad", 8, 128, 80, 640, 640, 3, 1, 1, 1),    # the painter's heaviest dgrad (1.3 ms)
     ("dgrad", 8, 64, 128, 320, 320, 4, 2, 1, 1),    # stride-2 dgrad as parity-class sub-convolutions
+    # second epilogue operand (derivative mask / residual) delivered by TMA into the staging tile (conv_tc.cu, struct MaskPf)
+    ("dgrad_relu", 8, 128, 48, 640, 640, 3, 1, 1, 1),   # weight-stationary kernel, one staging tile, two halves
+    ("dgrad_relu", 8, 128, 80, 640, 640, 3, 1, 1, 1),   # streaming kernel, two staging tiles
+    ("dgrad_lrelu", 4, 128, 80, 321, 323, 3, 1, 1, 1),  # ragged borders: tile tails clipped by the tensor maps
+    ("dgrad_relu", 8, 256, 256, 160, 160, 3, 1, 1, 1),  # VGG conv3_x: N = 256, four halves, CTA-pair kernel
+    ("dgrad_relu", 8, 64, 64, 640, 640, 3, 1, 1, 1),    # VGG conv1_2: one half
+    ("dgrad_lrelu", 8, 320, 192, 80, 80, 3, 1, 1, 1),   # two N tiles of 160 channels: per-thread copy-out with the mask in phase 1
+    ("dgrad_relu", 8, 512, 64, 80, 80, 3, 1, 1, 1),     # two N tiles of 256 channels, TMA store, four halves each
+    ("fwd_res", 8, 256, 256, 80, 80, 3, 1, 1, 1),       # residual add in the epilogue
     ("wgrad", 8, 256, 256, 80, 80, 3, 1, 2, 2),
     ("wgrad", 8, 1024, 256, 80, 80, 1, 1, 1, 0),
     ("wgrad", 8, 256, 1024, 80, 80, 1, 1, 1, 0),
@@ -71,6 +80,23 @@ def test_bench_class_tcgen05_matches_simt_and_fp64(cuda, case):
     elif op == "dgrad":
         a = ops.conv_dgrad_raw(gy, wp, (n, h, w, ci), g_tc)
         b = ops.conv_dgrad_raw(gy, wp.clone(), (n, h, w, ci), g_simt)
+    elif op in ("dgrad_relu", "dgrad_lrelu"):
+        dact = _lib.ACT_RELU if op == "dgrad_relu" else _lib.ACT_LRELU
+        a = ops.conv_dgrad_raw(gy, wp, (n, h, w, ci), g_tc, dact, x)
+        b = ops.conv_dgrad_raw(gy, wp.clone(), (n, h, w, ci), g_simt, dact, x)
+        # the mask really acted: about half of the elements are zeroed (relu) / scaled by the slope (lrelu)
+        plain = ops.conv_dgrad_raw(gy, wp, (n, h, w, ci), g_tc)
+        neg = x.float() <= 0
+        if op == "dgrad_relu":
+            assert float(a[neg].abs().max()) == 0.0
+            assert torch.equal(a[~neg], plain[~neg])
+        else:
+            assert rel_max(a[neg].float(), 0.2 * plain[neg].float()) < 1.0 / 64
+            assert torch.equal(a[~neg], plain[~neg])
+    elif op == "fwd_res":
+        res = torch.randn(n, ho, wo, co, device=cuda).to(dt)
+        a = ops.conv_fwd_raw(x, wp, None, res, g_tc)
+        b = ops.conv_fwd_raw(x, wp, None, res, g_simt)
     else:
         a, _ = ops.conv_wgrad_raw(x, gy, g_tc, False)
         b, _ = ops.conv_wgrad_raw(x, gy, g_simt, False)
