@@ -51,15 +51,20 @@ def test_graph_replay_matches_eager_step(cuda, dtype):
     logs_e, params_e, _ = _run(cuda, dtype, False)
     # the eager step a second time: the run-to-run noise of the atomically-ordered reductions (bf16: small losses such as the
     # ground-intersection term move by 1-2 % between two eager runs) — a replay may differ from eager by that much, not more
-    logs_n = _run(cuda, dtype, False)[0] if dtype != torch.float32 else logs_e
+    # (three eager runs in all: one pair underestimates the spread now and then — the term gen.task.m.gi.r = 4.8e-3 moved by
+    #  0.5 % between two eager runs and by 2.5 % against the third, eager, warm-up iteration of the graph run)
+    noise_runs = [_run(cuda, dtype, False)[0] for _ in range(2)] if dtype != torch.float32 else []
     logs_g, params_g, t = _run(cuda, dtype, True)
     assert len(t._graphs) == 2 and all(s.replays == 3 for s in t._graphs.values()), {k[0]: s.replays for k, s in t._graphs.items()}
     assert all(s.tape.n_draws > 0 for s in t._graphs.values())
     ltol = 2e-4 if dtype == torch.float32 else 2e-2
-    for it, (le, lg, ln) in enumerate(zip(logs_e, logs_g, logs_n)):
+    floor = 1e-5 if dtype == torch.float32 else 1e-4
+    for it, (le, lg) in enumerate(zip(logs_e, logs_g)):
         assert sorted(le) == sorted(lg)
         for k in le:
-            assert abs(le[k] - lg[k]) <= max(ltol * abs(le[k]), 3 * abs(le[k] - ln[k])) + 1e-5, (it, k, le[k], lg[k], ln[k])
+            runs = [le[k]] + [n[it][k] for n in noise_runs]
+            spread = max(runs) - min(runs)
+            assert abs(le[k] - lg[k]) <= max(ltol * abs(le[k]), 3 * spread) + floor, (it, k, runs, lg[k])
     # label flipping changes the GAN loss by O(1) and a different dropout mask the segmentation losses by O(1e-2): equal losses
     # above mean the replays drew the eager step's labels and masks.  State that evolves outside the optimiser (spectral-norm
     # u / v, BatchNorm running statistics) must agree too:
