@@ -91,6 +91,7 @@ SIGNATURES = {
     "cgb_instnorm_stats": ([_P, _I, _I, _I, _I, _F, _P, _P, _P, _P], C.c_int),
     "cgb_spade_modulate_fwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),
     "cgb_spade_modulate_bwd": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),
+    "cgb_spade_modulate_bwd_bias": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),
     "cgb_instnorm_bwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P], C.c_int),
     "cgb_instnorm_apply_fwd": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),
     "cgb_instnorm_apply_bwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P], C.c_int),

@@ -144,20 +144,20 @@ __global__ void __launch_bounds__(256)
 spade_mod_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const T* __restrict__ gb,
                      const T* __restrict__ gout, T* __restrict__ ggb, T* __restrict__ gxhat,
-                     double* __restrict__ sums, int hw, int c, int px_per_chunk, int act, float slope) {
-  extern __shared__ float sm[];  // [2][c]
+                     double* __restrict__ sums, double* __restrict__ bsum, int hw, int c, int px_per_chunk, int act, float slope) {
+  extern __shared__ float sm[];  // [2][c] (+ [2][c] column sums of ggb when bsum is given)
   const int cv = c >> 3;
   const int lanes = 256 / cv;
   const int tid = threadIdx.x;
   const int lane = tid / cv, v = tid - lane * cv;
   const int img = blockIdx.y;
-  for (int i = tid; i < 2 * c; i += 256) sm[i] = 0.f;
+  for (int i = tid; i < (bsum ? 4 : 2) * c; i += 256) sm[i] = 0.f;
   __syncthreads();
   if (lane < lanes) {
-    float s1[8], s2[8], mu[8], rs[8];
+    float s1[8], s2[8], s3[8], s4[8], mu[8], rs[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      s1[j] = s2[j] = 0.f;
+      s1[j] = s2[j] = s3[j] = s4[j] = 0.f;
       mu[j] = mean[(long long)img * c + v * 8 + j];
       rs[j] = rstd[(long long)img * c + v * 8 + j];
     }
@@ -184,6 +184,8 @@ spade_mod_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean,
         gxh[j] = gs * (1.f + g[j]);
         s1[j] += gxh[j];
         s2[j] = fmaf(gxh[j], xh, s2[j]);
+        s3[j] += gg[j];    // bias gradients of mlp_gamma / mlp_beta = column sums of ggb (used when bsum is given)
+        s4[j] += gbt[j];
       }
       Vec8<T>::store(ggb + pix * 2 * c + v * 8, gg);
       Vec8<T>::store(ggb + pix * 2 * c + c + v * 8, gbt);
@@ -194,12 +196,21 @@ spade_mod_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean,
       atomicAdd(&sm[v * 8 + j], s1[j]);
       atomicAdd(&sm[c + v * 8 + j], s2[j]);
     }
+    if (bsum) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sm[2 * c + v * 8 + j], s3[j]);
+        atomicAdd(&sm[3 * c + v * 8 + j], s4[j]);
+      }
+    }
   }
   __syncthreads();
   for (int i = tid; i < c; i += 256) {
     atomicAdd(&sums[((long long)img * c + i) * 2 + 0], (double)sm[i]);
     atomicAdd(&sums[((long long)img * c + i) * 2 + 1], (double)sm[c + i]);
   }
+  if (bsum)
+    for (int i = tid; i < 2 * c; i += 256) atomicAdd(&bsum[i], (double)sm[2 * c + i]);   // [gamma bias || beta bias], over all images
 }
 
 // gx = rstd*(g - m1 - xhat*m2) = A*g + B*x + C with per-(n,c) constants held in registers (same chunked mapping)
@@ -1456,10 +1467,9 @@ extern "C" int cgb_spade_modulate_fwd(const void* x, const float* mean, const fl
   return after_launch("spade_mod_fwd");
 }
 
-extern "C" int cgb_spade_modulate_bwd(const void* x, const float* mean, const float* rstd,
-                                      const void* gb, const void* gout, void* ggb, void* gxhat,
-                                      double* sums, int32_t dtype, int32_t n, int32_t hw, int32_t c,
-                                      int32_t act, float slope, void* stream) {
+static int spade_modulate_bwd_impl(const void* x, const float* mean, const float* rstd, const void* gb, const void* gout, void* ggb,
+                                   void* gxhat, double* sums, double* bsum, int32_t dtype, int32_t n, int32_t hw, int32_t c,
+                                   int32_t act, float slope, void* stream) {
   CGB_CHECK_DEVICE();
   CGB_REQUIRE(x && mean && rstd && gb && gout && ggb && gxhat && sums, "spade_modulate_bwd: null pointer");
   CGB_REQUIRE(c % 8 == 0 && c >= 8 && c <= 2048, "spade_modulate_bwd: c=%d must be a multiple of 8 in [8,2048]", c);
@@ -1467,10 +1477,25 @@ extern "C" int cgb_spade_modulate_bwd(const void* x, const float* mean, const fl
   const int chunks = pick_chunks(n, hw, c / 8);
   const int ppc = (hw + chunks - 1) / chunks;
   dim3 grid((hw + ppc - 1) / ppc, n);
-  DISPATCH_T(dtype, spade_mod_bwd_kernel<T><<<grid, 256, 2 * c * sizeof(float), st>>>(
-                        (const T*)x, mean, rstd, (const T*)gb, (const T*)gout, (T*)ggb, (T*)gxhat, sums,
+  DISPATCH_T(dtype, spade_mod_bwd_kernel<T><<<grid, 256, (bsum ? 4 : 2) * c * sizeof(float), st>>>(
+                        (const T*)x, mean, rstd, (const T*)gb, (const T*)gout, (T*)ggb, (T*)gxhat, sums, bsum,
                         hw, c, ppc, act, slope);)
   return after_launch("spade_mod_bwd");
+}
+
+extern "C" int cgb_spade_modulate_bwd(const void* x, const float* mean, const float* rstd,
+                                      const void* gb, const void* gout, void* ggb, void* gxhat,
+                                      double* sums, int32_t dtype, int32_t n, int32_t hw, int32_t c,
+                                      int32_t act, float slope, void* stream) {
+  return spade_modulate_bwd_impl(x, mean, rstd, gb, gout, ggb, gxhat, sums, nullptr, dtype, n, hw, c, act, slope, stream);
+}
+
+extern "C" int cgb_spade_modulate_bwd_bias(const void* x, const float* mean, const float* rstd,
+                                           const void* gb, const void* gout, void* ggb, void* gxhat,
+                                           double* sums, double* bsum, int32_t dtype, int32_t n, int32_t hw, int32_t c,
+                                           int32_t act, float slope, void* stream) {
+  CGB_REQUIRE(bsum, "spade_modulate_bwd_bias: null bsum");
+  return spade_modulate_bwd_impl(x, mean, rstd, gb, gout, ggb, gxhat, sums, bsum, dtype, n, hw, c, act, slope, stream);
 }
 
 extern "C" int cgb_instnorm_bwd(const void* x, const float* mean, const float* rstd, const double* sums,

@@ -475,6 +475,9 @@ def conv_bn_act(x, w, bn, bias=None, residual=None, *, stride=1, dil=1, pad=0, p
 _BN_DUAL = os.environ.get("CGB_BN_DUAL", "1") != "0"
 
 
+_SPADE_BIAS_FUSED = os.environ.get("CGB_SPADE_BIAS_FUSED", "1") != "0"
+
+
 class _Spade(Function):
     """SPADE.forward (climategan/norms.py:174-186) + the leaky-relu that follows it in
     SPADEResnetBlock (blocks.py:372-373), as one autograd node.
@@ -546,19 +549,29 @@ class _Spade(Function):
         gout = gout.contiguous()
         ggb = torch.empty_like(gb)
         gx = torch.empty_like(x)
-        sums = torch.zeros((ns_, cs, 2), dtype=torch.float64, device=x.device)
-        check(_L().cgb_spade_modulate_bwd(_p(x), _p(mean), _p(rstd), _p(gb), _p(gout), _p(ggb), _p(gx), _p(sums),
-                                          _DT[dt], ns_, hw_, cs, act, slope, _st()), "spade_modulate_bwd")
+        want_w = any(ctx.needs_input_grad[4:10])   # False while the painter is frozen (painter loss for the masker)
+        # one zero-filled allocation: the instance-norm sums [ns, cs, 2] and, behind them, the bias gradients of mlp_gamma / mlp_beta
+        # [2 cs] — the modulation pass returns the column sums of ggb, so the gamma||beta wgrad launch needs no column-sum pass
+        buf = torch.zeros((ns_ * cs * 2 + (2 * cs if want_w and _SPADE_BIAS_FUSED else 0),), dtype=torch.float64, device=x.device)
+        sums = buf[: ns_ * cs * 2].view(ns_, cs, 2)
+        bsum = buf[ns_ * cs * 2:] if want_w and _SPADE_BIAS_FUSED else None
+        if bsum is not None:
+            check(_L().cgb_spade_modulate_bwd_bias(_p(x), _p(mean), _p(rstd), _p(gb), _p(gout), _p(ggb), _p(gx), _p(sums), _p(bsum),
+                                                   _DT[dt], ns_, hw_, cs, act, slope, _st()), "spade_modulate_bwd_bias")
+        else:
+            check(_L().cgb_spade_modulate_bwd(_p(x), _p(mean), _p(rstd), _p(gb), _p(gout), _p(ggb), _p(gx), _p(sums),
+                                              _DT[dt], ns_, hw_, cs, act, slope, _st()), "spade_modulate_bwd")
         check(_L().cgb_instnorm_bwd(_p(x), _p(mean), _p(rstd), _p(sums), _p(gx), _DT[dt], ns_, hw_, cs, _st()),
               "instnorm_bwd")
         # gamma||beta conv: weight grads + data grad (ReLU of mlp_shared fused as a mask)
-        want_w = any(ctx.needs_input_grad[4:10])   # False while the painter is frozen (painter loss for the masker)
         want_seg = ctx.needs_input_grad[3]
         gw_sh = gb_sh = gw_g = gb_g = gw_b = gb_b = gactv = None
         if want_w or want_seg:
             gactv = conv_dgrad_raw(ggb, wp_gb, tuple(actv.shape), g_gb, _lib.ACT_RELU, actv)
         if want_w:
-            gwp_gb, gbp_gb = conv_wgrad_raw(actv, ggb, g_gb, True)
+            gwp_gb, gbp_gb = conv_wgrad_raw(actv, ggb, g_gb, bsum is None)
+            if bsum is not None:
+                gbp_gb = bsum.float()
             bias_tap = seg_is_col and has_bias_tap(sh_shape[1], sh_shape[2])   # the patches' constant-one channel (im2col)
             gwp_sh, gbp_sh = conv_wgrad_raw(seg, gactv, g_sh, not bias_tap)
             gw_g = unpack_weight_grad(gwp_gb[:cs], g_shape)

@@ -158,6 +158,13 @@ int cgb_spade_modulate_bwd(const void* x, const float* mean, const float* rstd, 
                            const void* gout, void* ggb, void* gxhat, double* sums, int32_t dtype,
                            int32_t n, int32_t hw, int32_t c, int32_t act, float slope, void* stream);
 
+/* The same pass, also returning the bias gradients of SPADE.mlp_gamma / mlp_beta (norms.py:169-172, nn.Conv2d(nhidden, norm_nc, ...), bias on by default):
+ *   bsum[0:c] += sum_{n,hw} gs*xhat,  bsum[c:2c] += sum_{n,hw} gs   (fp64, the column sums of ggb; caller zeroes)
+ * so the weight-gradient launch of the gamma||beta conv needs no separate column-sum pass over ggb. */
+int cgb_spade_modulate_bwd_bias(const void* x, const float* mean, const float* rstd, const void* gb,
+                                const void* gout, void* ggb, void* gxhat, double* sums, double* bsum, int32_t dtype,
+                                int32_t n, int32_t hw, int32_t c, int32_t act, float slope, void* stream);
+
 /* Backward of instance norm, part 2 (in place on gxhat -> gx):
  *   gx = rstd * (gxhat - sums0/hw - xhat*sums1/hw) */
 int cgb_instnorm_bwd(const void* x, const float* mean, const float* rstd, const double* sums,

@@ -204,6 +204,13 @@ class EmuLib(NoopLib):
         S[..., 0] += gxh.double().sum(1)
         S[..., 1] += (gxh * xhat).double().sum(1)
 
+    def e_spade_modulate_bwd_bias(self, x, mean, rstd, gb, gout, ggb, gxhat, sums, bsum, dtype, n, hw, c, act, slope, stream):
+        self.e_spade_modulate_bwd(x, mean, rstd, gb, gout, ggb, gxhat, sums, dtype, n, hw, c, act, slope, stream)
+        # (the kernel sums the fp32 values before they are rounded to the storage type; the emulation sums what was stored —
+        #  identical in fp32 storage, within bf16 rounding otherwise)
+        B = _t(bsum, (2 * c,), torch.float64)
+        B += _t(ggb, (n, hw, 2 * c), _DT[dtype]).double().sum((0, 1))
+
     def e_instnorm_bwd(self, x, mean, rstd, sums, g, dtype, n, hw, c, stream):
         dt = _DT[dtype]
         X = _t(x, (n, hw, c), dt).float()
