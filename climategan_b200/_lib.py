@@ -172,6 +172,7 @@ SIGNATURES = {
     "cgb_nchw_to_nhwc": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_nhwc_to_nchw": ([_P, _P, _I, _I, _I, _I, _I, _P], C.c_int),
     "cgb_act_bwd": ([_P, _P, _P, _I, _L, _I, _F, _P], C.c_int),
+    "cgb_act_bwd_bias": ([_P, _P, _P, _P, _I, _L, _I, _I, _F, _P], C.c_int),
     "cgb_act_fwd": ([_P, _P, _I, _L, _I, _F, _P], C.c_int),
     "cgb_mask_cond": ([_P, _P, _P, _I, _I, _I, _I, _P], C.c_int),
     "cgb_paste_fwd": ([_P, _P, _P, _P, _I, _I, _P], C.c_int),

@@ -448,6 +448,44 @@ act_bwd_kernel(const T* __restrict__ gy, const T* __restrict__ y, T* __restrict_
   }
 }
 
+// gx = gy * act'(y) and gbias[c] += sum over pixels of gx (fp32, before the rounding to the storage type): the bias gradient of the
+// conv whose fused activation is being differentiated, so its weight-gradient launch needs no column-sum pass over gx
+template <typename T>
+__global__ void __launch_bounds__(256)
+act_bwd_bias_kernel(const T* __restrict__ gy, const T* __restrict__ y, T* __restrict__ gx, float* __restrict__ gbias,
+                    long long pixels, int c, long long px_per_cta, int act, float slope) {
+  extern __shared__ float sm[];
+  const int cv = c >> 3;
+  const int lanes = 256 / cv;
+  const int tid = threadIdx.x;
+  const int lane = tid / cv, v = tid - lane * cv;
+  for (int i = tid; i < c; i += 256) sm[i] = 0.f;
+  __syncthreads();
+  if (lane < lanes) {
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    const long long p0 = (long long)blockIdx.x * px_per_cta;
+    long long p1 = p0 + px_per_cta;
+    if (p1 > pixels) p1 = pixels;
+    for (long long px = p0 + lane; px < p1; px += lanes) {
+      float g[8], yy[8], o[8];
+      Vec8<T>::load(gy + px * c + v * 8, g);
+      Vec8<T>::load(y + px * c + v * 8, yy);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[j] = g[j] * act_grad_from_out(yy[j], act, slope);
+        s[j] += o[j];
+      }
+      Vec8<T>::store(gx + px * c + v * 8, o);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sm[v * 8 + j], s[j]);
+  }
+  __syncthreads();
+  for (int i = tid; i < c; i += 256) atomicAdd(gbias + i, sm[i]);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long count, int act, float slope) {
@@ -1650,6 +1688,22 @@ extern "C" int cgb_act_bwd(const void* gy, const void* y, void* gx, int32_t dtyp
   DISPATCH_T(dtype, act_bwd_kernel<T><<<grid_for(count / 8), 256, 0, st>>>((const T*)gy, (const T*)y, (T*)gx,
                                                                           count, act, slope);)
   return after_launch("act_bwd");
+}
+
+extern "C" int cgb_act_bwd_bias(const void* gy, const void* y, void* gx, float* gbias, int32_t dtype, int64_t npix, int32_t c,
+                                int32_t act, float slope, void* stream) {
+  CGB_CHECK_DEVICE();
+  CGB_REQUIRE(gy && y && gx && gbias, "act_bwd_bias: null pointer");
+  CGB_REQUIRE(c % 8 == 0 && c >= 8 && c <= 2048 && npix > 0, "act_bwd_bias: c=%d must be a multiple of 8 in [8,2048]", c);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(gbias, 0, (size_t)c * sizeof(float), st);
+  long long ctas = (npix * (c / 8) + 256LL * 8 - 1) / (256LL * 8);   // ~8 channel vectors per thread
+  if (ctas > 148 * 8) ctas = 148 * 8;
+  if (ctas < 1) ctas = 1;
+  const long long ppc = (npix + ctas - 1) / ctas;
+  DISPATCH_T(dtype, act_bwd_bias_kernel<T><<<(unsigned)((npix + ppc - 1) / ppc), 256, c * sizeof(float), st>>>(
+                        (const T*)gy, (const T*)y, (T*)gx, gbias, (long long)npix, c, ppc, act, slope);)
+  return after_launch("act_bwd_bias");
 }
 
 extern "C" int cgb_act_fwd(const void* x, void* y, int32_t dtype, int64_t count, int32_t act, float slope,

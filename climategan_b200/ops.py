@@ -344,6 +344,20 @@ def act_bwd_raw(gy, y, act, slope):
     return gx
 
 
+def act_bwd_bias_raw(gy, y, act, slope):
+    """(gx, gbias): :func:`act_bwd_raw` that also returns the per-channel sum of gx over pixels (fp32, storage channels) — the bias
+    gradient of the conv whose fused activation is being differentiated."""
+    gx = torch.empty_like(gy)
+    c = gy.shape[-1]
+    gbias = torch.empty((c,), dtype=torch.float32, device=gy.device)
+    check(_L().cgb_act_bwd_bias(_p(gy), _p(y), _p(gx), _p(gbias), _DT[gy.dtype], gy.numel() // c, c, act, slope, _st()),
+          "act_bwd_bias")
+    return gx, gbias
+
+
+_ACT_BIAS_FUSED = os.environ.get("CGB_ACT_BIAS_FUSED", "1") != "0"
+
+
 # ------------------------------------------------------------------------------------------------
 # autograd functions
 # ------------------------------------------------------------------------------------------------
@@ -379,12 +393,18 @@ class _Conv2d(Function):
         x, wp, y = ctx.saved_tensors
         g = ctx.g
         gy = gy.contiguous()
-        gpre = act_bwd_raw(gy, y, g.act, g.slope) if g.act != _lib.ACT_NONE else gy
+        gb_fused = None
+        if g.act != _lib.ACT_NONE and ctx.has_bias and ctx.needs_input_grad[2] and _ACT_BIAS_FUSED and gy.shape[-1] <= 2048:
+            gpre, gb_fused = act_bwd_bias_raw(gy, y, g.act, g.slope)   # the bias gradient rides the activation's backward pass
+        else:
+            gpre = act_bwd_raw(gy, y, g.act, g.slope) if g.act != _lib.ACT_NONE else gy
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = conv_dgrad_raw(gpre, wp, tuple(x.shape), g)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            gwp, gbp = conv_wgrad_raw(x, gpre, g, ctx.has_bias)
+            gwp, gbp = conv_wgrad_raw(x, gpre, g, ctx.has_bias and gb_fused is None)
+            if gb_fused is not None:
+                gbp = gb_fused
             gw = unpack_weight_grad(gwp, ctx.w_shape)
             if ctx.has_bias:
                 gb = gbp if (gbp.numel() == ctx.nb and "viewgrad" not in _DBG) else gbp[: ctx.nb].clone()

@@ -427,6 +427,11 @@ int cgb_nhwc_to_nchw(const void* x, float* y, int32_t dtype, int32_t n, int32_t 
 /* gx = gy * act'(y)  (y = activation output) */
 int cgb_act_bwd(const void* gy, const void* y, void* gx, int32_t dtype, int64_t count, int32_t act,
                 float slope, void* stream);
+/* The same on a [npix, c] tensor, also returning gbias[c] = sum over pixels of gx (fp32; zeroed here): the bias gradient of a
+ * Conv2dBlock's conv (blocks.py:138-144, nn.Conv2d(..., bias=True) -> activation), so the conv's weight-gradient launch needs
+ * no column-sum pass over gx. */
+int cgb_act_bwd_bias(const void* gy, const void* y, void* gx, float* gbias, int32_t dtype, int64_t npix, int32_t c,
+                     int32_t act, float slope, void* stream);
 /* y = act(x) elementwise (F.leaky_relu before conv_img, painter.py:166) */
 int cgb_act_fwd(const void* x, void* y, int32_t dtype, int64_t count, int32_t act, float slope,
                 void* stream);

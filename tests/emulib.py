@@ -239,6 +239,12 @@ class EmuLib(NoopLib):
         dt = _DT[dtype]
         _t(gx, (count,), dt).copy_(_t(gy, (count,), dt).float() * _dact_from_out(_t(y, (count,), dt).float(), act, slope))
 
+    def e_act_bwd_bias(self, gy, y, gx, gbias, dtype, npix, c, act, slope, stream):
+        dt = _DT[dtype]
+        o = _t(gy, (npix, c), dt).float() * _dact_from_out(_t(y, (npix, c), dt).float(), act, slope)
+        _t(gx, (npix, c), dt).copy_(o)
+        _t(gbias, (c,), torch.float32).copy_(o.sum(0))
+
     def e_nchw_to_nhwc(self, x, y, dtype, n, c, hw, cs, stream):
         Y = _t(y, (n, hw, cs), _DT[dtype])
         Y.zero_()

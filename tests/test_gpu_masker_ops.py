@@ -115,6 +115,25 @@ def test_maxpool3s2_ceil_fwd_bwd(cuda, h, w):
     assert rel_max(xd.grad, xr.grad) < 1e-6
 
 
+@pytest.mark.parametrize("pad", [0, 1])
+@pytest.mark.parametrize("n,c,h,w", [(2, 64, 80, 80), (1, 40, 37, 45), (3, 8, 33, 64)])
+def test_maxpool3s2_bwd_tiled_matches_torch(cuda, pad, n, c, h, w):
+    """The tiled backward (16-bit storage, maps >= 32 x 32: masker_ops.cu maxpool3s2_bwd_tiled_kernel) against F.max_pool2d's own
+    backward: small-integer inputs (many ties -> the first-maximum rule matters) and integer gradients, so bf16 sums are exact."""
+    g = torch.Generator().manual_seed(7)
+    x = torch.randint(0, 6, (n, c, h, w), generator=g).float()
+    xr = x.clone().requires_grad_()
+    y = F.max_pool2d(xr, 3, 2, pad, ceil_mode=(pad == 0))
+    gy = torch.randint(-8, 9, tuple(y.shape), generator=g).float()
+    y.backward(gy)
+    xd = x.to(cuda).requires_grad_()
+    pool = ops.maxpool3s2_ceil if pad == 0 else ops.maxpool3s2_pad1
+    yo = _nchw(pool(_st(xd, torch.bfloat16)), c)
+    yo.backward(gy.to(cuda))
+    assert torch.equal(yo.detach().float().cpu(), y.detach())
+    assert torch.equal(xd.grad.float().cpu(), xr.grad)
+
+
 @pytest.mark.parametrize("ac", [True, False])
 @pytest.mark.parametrize("hi,wi,ho,wo", [(5, 7, 10, 14), (8, 8, 16, 16), (6, 5, 13, 9), (12, 12, 5, 7)])
 def test_resize_bilinear_fwd_bwd(cuda, ac, hi, wi, ho, wo):
