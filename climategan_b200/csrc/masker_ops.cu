@@ -40,13 +40,13 @@ static inline int grid_for(long long work, int block = 256) {
 //   first flat version: 4 vectors in flight held as fp32 (126-173 registers, 1-2 CTAs/SM)  -> 0.35-0.57 fwd, 0.24-0.34 bwd:
 //   occupancy, not instruction-level parallelism, is what hides the latency here (spade_mod_fwd, 2048 threads/SM: 0.87).
 constexpr int BN_U = 2;
+constexpr long long BN_BWD_CAP = 148LL * 3;   // bn_apply_bwd_kernel: __launch_bounds__(256, 3) -> one resident wave
 
 static inline long long gcd_ll(long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return a; }
 
 // CTAs for a flat pass over total_vec vectors, a multiple of cv / gcd(cv, 256) so that a thread's channel vector is fixed
-static inline int bn_grid(long long total_vec, int cv) {
+static inline int bn_grid(long long total_vec, int cv, long long cap = 148LL * 8) {
   long long g = (total_vec + 256LL * BN_U - 1) / (256LL * BN_U);
-  const long long cap = 148LL * 8;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   const long long m = cv / gcd_ll(cv, 256);
@@ -191,14 +191,17 @@ bn_apply_bwd_kernel(const T* __restrict__ x, const float* __restrict__ mean, con
 }
 
 // sums[c][2] (fp64) = sum over chunks of the partials
-__global__ void __launch_bounds__(512)
+// (only c / 32 CTAs run here — 8 for a 256-channel layer — so the fold is latency-bound on its row loop: the backward pass
+//  launches one resident wave, BN_BWD_CAP = 3 CTAs per SM -> <= 444 partial rows instead of 1184, and 32 row groups per CTA:
+//  14 us -> see DESIGN.md)
+__global__ void __launch_bounds__(1024)
 bn_bwd_reduce_kernel(const float* __restrict__ partial, double* __restrict__ sums, int c, int chunks) {
-  __shared__ double sS[16][33], sQ[16][33];   // block (32 channels, 16 chunk groups), as in_stats_finalize_kernel
+  __shared__ double sS[32][33], sQ[32][33];   // block (32 channels, 32 chunk groups)
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int ch = blockIdx.x * 32 + tx;
   double S = 0.0, Q = 0.0;
   if (ch < c) {
-    for (int k = ty; k < chunks; k += 16) {
+    for (int k = ty; k < chunks; k += 32) {
       S += (double)partial[(long long)k * 2 * c + ch];
       Q += (double)partial[(long long)k * 2 * c + c + ch];
     }
@@ -208,7 +211,7 @@ bn_bwd_reduce_kernel(const float* __restrict__ partial, double* __restrict__ sum
   __syncthreads();
   if (ty == 0 && ch < c) {
 #pragma unroll
-    for (int k = 1; k < 16; ++k) { S += sS[k][tx]; Q += sQ[k][tx]; }
+    for (int k = 1; k < 32; ++k) { S += sS[k][tx]; Q += sQ[k][tx]; }
     sums[ch * 2 + 0] = S;
     sums[ch * 2 + 1] = Q;
   }
@@ -1173,7 +1176,7 @@ extern "C" int cgb_bn_apply_fwd(const void* x, const float* mean, const float* r
 extern "C" int64_t cgb_bn_bwd_ws_doubles(int64_t npix, int32_t c) {
   if (npix <= 0 || c <= 0) return 0;
   const int cv = c / 8;
-  return 2 * (int64_t)c + (int64_t)bn_grid((long long)npix * cv, cv) * c;   // sums[c][2] doubles, then grid * 2c fp32 partials
+  return 2 * (int64_t)c + (int64_t)bn_grid((long long)npix * cv, cv, BN_BWD_CAP) * c;   // sums[c][2] doubles, then grid * 2c fp32 partials
 }
 
 static int bn_apply_bwd_impl(const void* x, const float* mean, const float* rstd, const void* y, const void* gy, const void* gy2,
@@ -1194,14 +1197,14 @@ static int bn_apply_bwd_impl(const void* x, const float* mean, const float* rstd
   cudaStream_t st = (cudaStream_t)stream;
   const int cv = c / 8;
   const long long total = (long long)npix * cv;
-  const int grid = bn_grid(total, cv);
+  const int grid = bn_grid(total, cv, BN_BWD_CAP);
   float* partial = reinterpret_cast<float*>(sums + 2 * (size_t)c);   // sums holds cgb_bn_bwd_ws_doubles(npix, c) doubles
   DISPATCH_T(dtype, bn_apply_bwd_kernel<T><<<grid, 256, 4 * c * sizeof(float), st>>>(
                         (const T*)x, mean, rstd, (const T*)y, (const T*)gy, (const T*)gy2, (T*)gpre, partial, total, cv, neg,
                         act != CGB_ACT_NONE);)
   int s = after_launch("bn_apply_bwd");
   if (s) return s;
-  bn_bwd_reduce_kernel<<<(c + 31) / 32, dim3(32, 16), 0, st>>>(partial, sums, c, grid);
+  bn_bwd_reduce_kernel<<<(c + 31) / 32, dim3(32, 32), 0, st>>>(partial, sums, c, grid);
   return after_launch("bn_bwd_reduce");
 }
 
