@@ -7,7 +7,7 @@ namespace cgb {
 
 static inline int grid_for(long long work, int block = 256) {
   long long g = (work + block - 1) / block;
-  const long long cap = 148LL * 16;
+  static const long long cap = 148LL * (getenv("CGB_FLAT_CTAS") ? atoi(getenv("CGB_FLAT_CTAS")) : 16);
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;

@@ -10,7 +10,7 @@ namespace cgb {
 
 static inline int grid_for(long long work, int block = 256) {
   long long g = (work + block - 1) / block;
-  const long long cap = 148LL * 16;
+  static const long long cap = 148LL * (getenv("CGB_FLAT_CTAS") ? atoi(getenv("CGB_FLAT_CTAS")) : 16);
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
@@ -1168,7 +1168,11 @@ extern "C" int cgb_bn_apply_fwd(const void* x, const float* mean, const float* r
   const float neg = act == CGB_ACT_NONE ? 1.f : (act == CGB_ACT_RELU ? 0.f : slope);
   const int cv = c / 8;
   const long long total = (long long)npix * cv;
-  DISPATCH_T(dtype, bn_apply_fwd_kernel<T><<<bn_grid(total, cv), 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
+  // CTAs per SM, measured (profiles/r02_bn_grid_size.txt; 8 was the default until the end of round 2): one resident wave or less beats
+  // 1184 CTAs in 1.3-2 waves — plain pass 0.60 -> 0.75 of the HBM roof at 6 per SM, with a residual 0.70 -> 0.84 at 4
+  static const int fwd_ctas = getenv("CGB_BN_FWD_CTAS") ? atoi(getenv("CGB_BN_FWD_CTAS")) : 0;
+  const long long fwd_cap = 148LL * (fwd_ctas > 0 ? fwd_ctas : (residual ? 4 : 6));
+  DISPATCH_T(dtype, bn_apply_fwd_kernel<T><<<bn_grid(total, cv, fwd_cap), 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
                         (const T*)x, mean, rstd, weight, bias, (const T*)residual, (T*)y, total, cv, neg);)
   return after_launch("bn_apply_fwd");
 }
@@ -1215,7 +1219,8 @@ extern "C" int cgb_bn_bwd_finalize(const void* x, const float* mean, const float
   REQ_C(c, "bn_bwd_finalize");
   const int cv = c / 8;
   const long long total = (long long)npix * cv;
-  DISPATCH_T(dtype, bn_bwd_finalize_kernel<T><<<bn_grid(total, cv), 256, 3 * c * sizeof(float), (cudaStream_t)stream>>>(
+  static const long long fin_cap = 148LL * (getenv("CGB_BN_FIN_CTAS") ? atoi(getenv("CGB_BN_FIN_CTAS")) : 4);   // 0.70 -> 0.82 of the HBM roof (8 until the end of round 2)
+  DISPATCH_T(dtype, bn_bwd_finalize_kernel<T><<<bn_grid(total, cv, fin_cap), 256, 3 * c * sizeof(float), (cudaStream_t)stream>>>(
                         (const T*)x, mean, rstd, weight, sums, (const T*)gpre, (T*)gx, total, cv, 1.0 / (double)npix);)
   return after_launch("bn_bwd_finalize");
 }

@@ -9,8 +9,9 @@ namespace cgb {
 
 // number of pixel-chunks per image for the reduction kernels
 static inline int pick_chunks(int n, int hw, int cv) {
-  // target >= 8 CTAs per SM overall, each CTA >= 256 pixels
-  int want = (148 * 8 + n - 1) / n;
+  // target >= 4 CTAs per SM overall, each CTA >= 256 pixels
+  static const int per_sm = getenv("CGB_CHUNK_CTAS") ? atoi(getenv("CGB_CHUNK_CTAS")) : 4;   // measured: 8 -> 4 per SM: spade_mod_bwd 0.61 -> 0.68, in_stats 0.50 -> 0.54 of the HBM roof (profiles/r02_bn_grid_size.txt)
+  int want = (148 * per_sm + n - 1) / n;
   int maxc = (hw + 255) / 256;
   if (want > maxc) want = maxc;
   if (want < 1) want = 1;
@@ -1441,7 +1442,7 @@ using namespace cgb;
 
 static inline int grid_for(long long work, int block = 256) {
   long long g = (work + block - 1) / block;
-  const long long cap = 148LL * 16;
+  static const long long cap = 148LL * (getenv("CGB_FLAT_CTAS") ? atoi(getenv("CGB_FLAT_CTAS")) : 16);
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
