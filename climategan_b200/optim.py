@@ -5,6 +5,14 @@ parameter group over flat fp32 buffers (``cgb_extra_adam``) instead of ~10 eleme
 Parameters of a group are re-pointed to views of one flat buffer and so are their ``.grad`` tensors (autograd
 accumulates into the views in place; ``zero_grad`` is one memset).  The flat gradient buffer is also what the
 data-parallel all-reduce runs on (``flat_grads``), so no pack/unpack copies exist anywhere in the step.
+
+Known deviation: the fused kernel updates EVERY element of a group with one global step count ``t``.  The
+reference skips parameters whose ``.grad`` is None (``tutils.zero_grad`` sets them to None; ``optim.py:243-245``): no moment decay,
+no per-parameter ``state['step']`` increment.  A parameter that has never received a gradient behaves identically here (g = 0 and
+m = v = 0 give a zero update); one that STARTS receiving gradients late (the painter after ``train.kitti.pretrain``, a decoder
+absent from some domains) sees bias corrections computed with the global ``t`` instead of its own count — its first updates are
+up to (1 - b1) / sqrt(1 - b2) times larger than the reference's — and one that STOPS receiving gradients keeps moving on its
+momentum.  The step fixtures (every parameter gets a gradient on every step) are not affected; a run that switches tasks mid-way is.
 """
 from __future__ import annotations
 
