@@ -10,9 +10,15 @@
 //   * Both land in shared memory in the 128-byte-swizzled K-major layout UMMA descriptors address directly.
 //   * One elected thread issues tcgen05.mma (M=128, N=BN, K=16, bf16 x bf16 -> fp32) into a TMEM accumulator;
 //     tcgen05.commit releases smem stages back to the TMA producer through mbarriers.
-//   * 4 epilogue warps read the accumulator with tcgen05.ld (32 lanes x 16 columns per instruction) and apply
-//     bias / activation / residual add / activation-derivative mask, then store bf16 NHWC.
-//   Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue.
+//   * 8 epilogue warps (2 per TMEM lane quarter) read the accumulator with tcgen05.ld.32x32b.x32, apply bias / activation /
+//     residual add / activation-derivative mask (compile-time epilogue variants, EPI_*), stage the bf16 tile in shared memory
+//     as 64-channel halves in the 128-byte swizzle and hand each half to the TMA unit (bulk tensor store; "rolling store").
+//     The residual / mask operand itself arrives by TMA in the half the result is written to (struct EpiOperand).
+//     BatchNorm statistics of the stored output are accumulated from the staging tile (epilogue_stats).
+//   Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
+//   Kernels: conv_tc_kernel (streaming: one A box + one B box per (tap, 64-channel block)), conv_tc2_kernel (the same as a
+//   cta_group::2 CTA pair, half the weight tile per CTA), conv_tc_ws_kernel (weight-stationary: the CTA's weight slice resident,
+//   one halo box per 64-channel block serves all taps through shifted descriptors).
 //
 //   wgrad:  D[M = in-channels][N = out-channels] += X^T[M][K] * G^T[N][K]^T , K = pixels.  Both operands are
 //   "MN-major" for UMMA (the contraction index is the slow one in NHWC memory), loaded by the same shifted
@@ -572,7 +578,7 @@ __device__ __forceinline__ void epilogue_stats(const TcParams& p, const uint8_t*
 // the operand of its 16-byte chunk exactly where it is about to write): the half's store leader requests the next tile's operand
 // as soon as its bulk store of the current tile has finished reading the half, threads wait on the half's mbarrier, LDS, apply, STS.
 // No extra shared memory (the 48->128 launch has none left), no global address arithmetic in the epilogue.
-struct MaskPf {
+struct EpiOperand {
   int ox0, oy0, n0, cn0;    // the next tile of this CTA (n0 < 0: none)
   uint32_t aux_phase;       // parity bits of the operand barriers, bit = staging buffer * 4 + half
   int primed;               // the operand of the tile about to be processed has been requested
@@ -604,7 +610,7 @@ __device__ __forceinline__ void epi_tma_tile(const TcParams& p, uint32_t tmem_ac
                                              int oy0, int n0, int cn0, const float* __restrict__ bias,
                                              const T* __restrict__ residual, const T* __restrict__ mask_src, uint32_t tempty_bar,
                                              int warp, int lane, const CUtensorMap* tmY, float* stats_tab, EpiStats* est,
-                                             bool tempty_is_cluster_addr, int trace_lt, MaskPf* pf, const CUtensorMap* tmX,
+                                             bool tempty_is_cluster_addr, int trace_lt, EpiOperand* pf, const CUtensorMap* tmX,
                                              uint32_t aux_bar0) {
   const int q = warp & 3;              // TMEM lane quarter this warp may access
   const int g = (warp - 2) >> 2;       // 0..1: this warp's 32-column half of each 64-channel half
@@ -737,7 +743,7 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& p, uint32_t tmem_a
                                               uint32_t tempty_bar, int warp, int lane, const CUtensorMap* tmY = nullptr,
                                               uint32_t staging_u32 = 0, float* stats_tab = nullptr, EpiStats* est = nullptr,
                                               bool tempty_is_cluster_addr = false, int trace_lt = 1 << 20,
-                                              MaskPf* pf = nullptr, const CUtensorMap* tmX = nullptr, uint32_t aux_bar0 = 0) {
+                                              EpiOperand* pf = nullptr, const CUtensorMap* tmX = nullptr, uint32_t aux_bar0 = 0) {
   if constexpr (EPI != EPI_NOTMA) {
     // EPI: the launch's epilogue variant, chosen on the host (epi_variant_for) and compiled into the kernel
 #define CGB_EPI_TILE(B, A, X, G)                                                                                                   \
@@ -1012,7 +1018,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     EpiStats est;
     est.ch = -1;
     epi_stats_flush(p, est, stats_tab);   // (zeroes the registers)
-    MaskPf pf;
+    EpiOperand pf;
     pf.n0 = -1;
     pf.aux_phase = 0u;
     pf.primed = 0;
@@ -1230,7 +1236,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     EpiStats est;
     est.ch = -1;
     epi_stats_flush(p, est, stats_tab);
-    MaskPf pf;
+    EpiOperand pf;
     pf.n0 = -1;
     pf.aux_phase = 0u;
     pf.primed = 0;
@@ -1449,7 +1455,7 @@ conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     EpiStats est;
     est.ch = -1;
     epi_stats_flush(p, est, stats_tab);
-    MaskPf pf;
+    EpiOperand pf;
     pf.n0 = -1;
     pf.aux_phase = 0u;
     pf.primed = 0;
@@ -1609,7 +1615,7 @@ static bool tma_store_enabled() {
   static const int v = getenv("CGB_TMA_STORE") ? atoi(getenv("CGB_TMA_STORE")) : 1;
   return v != 0;
 }
-// the epilogue's second operand by TMA into the staging tile (struct MaskPf); CGB_AUX_TMA=0: row-per-thread global loads,
+// the epilogue's second operand by TMA into the staging tile (struct EpiOperand); CGB_AUX_TMA=0: row-per-thread global loads,
 // and the ReLU-masked dgrad back on the per-thread copy-out
 static bool aux_tma_enabled() {
   static const int v = getenv("CGB_AUX_TMA") ? atoi(getenv("CGB_AUX_TMA")) : 1;

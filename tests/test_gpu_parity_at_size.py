@@ -27,7 +27,7 @@ CLASSES = [
     ("dgrad", 8, 1024, 256, 80, 80, 1, 1, 1, 0),
     ("dgrad", 8, 128, 80, 640, 640, 3, 1, 1, 1),    # the painter's heaviest dgrad (1.3 ms)
     ("dgrad", 8, 64, 128, 320, 320, 4, 2, 1, 1),    # stride-2 dgrad as parity-class sub-convolutions
-    # second epilogue operand (derivative mask / residual) delivered by TMA into the staging tile (conv_tc.cu, struct MaskPf)
+    # second epilogue operand (derivative mask / residual) delivered by TMA into the staging tile (conv_tc.cu, struct EpiOperand)
     ("dgrad_relu", 8, 128, 48, 640, 640, 3, 1, 1, 1),   # weight-stationary kernel, one staging tile, two halves
     ("dgrad_relu", 8, 128, 80, 640, 640, 3, 1, 1, 1),   # streaming kernel, two staging tiles
     ("dgrad_lrelu", 4, 128, 80, 321, 323, 3, 1, 1, 1),  # ragged borders: tile tails clipped by the tensor maps
