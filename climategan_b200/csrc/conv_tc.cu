@@ -435,7 +435,8 @@ template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) 
 enum { EPI_AUX_NONE = 0, EPI_AUX_RES_BEFORE = 1, EPI_AUX_RES_AFTER = 2, EPI_AUX_MASK = 3 };
 // kernel-level epilogue variants (template parameter of the fprop / dgrad kernels)
 // GENERIC: TMA-store tile with run-time flags (residual adds, ...); EXOTIC: tanh / sigmoid / selu epilogues (generic chunk code);
-// NOTMA: the per-thread copy-out (strided parity-class dgrad, ReLU-masked dgrad, N tiles that are not whole 64-channel halves)
+// NOTMA: the per-thread copy-out (strided parity-class dgrad, N tiles that are not whole 64-channel halves; the ReLU-masked dgrad too
+// when CGB_AUX_TMA=0)
 enum { EPI_GENERIC = 0, EPI_PLAIN = 1, EPI_BIAS = 2, EPI_BIAS_ACT = 3, EPI_MASK_RELU = 4, EPI_MASK_LRELU = 5, EPI_EXOTIC = 6, EPI_NOTMA = 7,
        EPI_RES = 8,   // + residual, no bias / activation: the ResNet bottleneck's conv1 dgrad with the skip gradient added in
        EPI_VARIANTS = 9 };
@@ -1034,7 +1035,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tx = pt - py * p.tiles_x;
       const int tn = (int)fdiv((uint32_t)py, (uint32_t)p.tiles_y, p.mg_ty);
       const int ty = py - tn * p.tiles_y;
-      if constexpr (epi_may_aux(EPI)) {   // the next tile of this CTA, for the mask prefetch of the per-thread copy-out
+      if constexpr (epi_may_aux(EPI)) {   // the next tile of this CTA: its residual / mask operand is requested a tile ahead (EpiOperand)
         const int tile2 = tile + (int)gridDim.x;
         pf.n0 = -1;
         pf.sbuf = (p.staging_bufs == 2) ? (lt & 1) : 0;
@@ -1622,7 +1623,8 @@ static bool aux_tma_enabled() {
   return v != 0;
 }
 static bool tma_store_ok(int bn, int n_tiles, int dact, const void* mask_src) {
-  // the ReLU-derivative mask stays at the per-thread copy-out, where its loads are coalesced (consecutive lanes = consecutive chunks
+  // without the operand-by-TMA epilogue (CGB_AUX_TMA=0) the ReLU-derivative mask stays at the per-thread copy-out, where its loads are
+  // coalesced (consecutive lanes = consecutive chunks
   // of a pixel): read row-per-thread in phase 1 it cost 32 sectors in 32 lines per LDG (256->256 d2 dgrad: 54 -> 71 us)
   static const int mask_tma = getenv("CGB_MASK_TMA") ? atoi(getenv("CGB_MASK_TMA")) : 0;
   return tma_store_enabled() && (bn % 64 == 0 || n_tiles == 1) && (mask_tma || aux_tma_enabled() || !(mask_src && dact == CGB_ACT_RELU));
